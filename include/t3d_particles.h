@@ -1,0 +1,230 @@
+/*
+ * t3d_particles.h -- C ABI of the B200-native particle backend (libt3d_particles.so).
+ *
+ * This is the drop-in boundary for Tractor3D's ParticleEmitter hot path: per-frame
+ * emitOnce (spawn) -> update (integrate + lerp + sprite step + dead-particle removal) -> draw
+ * (billboard quads in SpriteBatch's vertex layout).  The reference has no FFI for this path
+ * (ParticleEmitter is a concrete C++ class), so each entry point names the reference member it
+ * replaces; "PE.cpp"/"PE.h" = Tractor3Dlib/{src,include}/graphics/ParticleEmitter.{cpp,h},
+ * "SB.cpp"/"SB.h" = .../graphics/SpriteBatch.{cpp,h}, "MB.cpp" = .../graphics/MeshBatch.cpp.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, POD structs; no engine types, no torch types.
+ *   - every function returns a t3d_status (0 = ok) and never exits the process; the text of the
+ *     last failure on the calling thread is available from t3d_last_error().  The C++ facade
+ *     (tractor3d_b200/host/ParticleEmitter.h) maps non-zero codes to GP_ERROR / GP_WARN
+ *     (reference include/pch.h:83-103).
+ *   - one t3d_ctx per GPU, driven from one host thread (the reference path is single-threaded and
+ *     non-reentrant: function-local statics at PE.cpp:720, PE.cpp:855, SB.cpp:337-339).
+ *   - emit/update/draw ENQUEUE work: consecutive calls on different emitters are coalesced into
+ *     one kernel launch per phase and flushed when a result is needed (get_count, download_*,
+ *     t3d_ctx_flush, t3d_ctx_sync) or when the phase changes for an emitter already queued.
+ *   - time is in milliseconds exactly as in the reference (PE.h:724, PE.h:415-420).
+ *   - matrices are column-major float[16] (reference include/math/Matrix.h:62).
+ *   - there is no CPU fallback: without a CUDA device t3d_ctx_create fails with T3D_ERR_CUDA.
+ */
+#ifndef T3D_PARTICLES_H
+#define T3D_PARTICLES_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T3D_ABI_VERSION 1
+
+typedef enum t3d_status {
+    T3D_OK = 0,
+    T3D_ERR_INVALID = 1,      /* bad argument (the reference would assert, e.g. PE.cpp:264, 289) */
+    T3D_ERR_CUDA = 2,         /* a CUDA call failed; t3d_last_error() names it */
+    T3D_ERR_CAPACITY = 3,     /* growth beyond the capacity fixed at create (PE.h:237 rewrites the field only) */
+    T3D_ERR_RNG_UNDERFLOW = 4,/* T3D_RNG_STREAM: not enough recorded draws were fed for this emit */
+    T3D_ERR_IO = 5,           /* .particle file missing or malformed (PE.cpp:79-83, 94-115) */
+    T3D_ERR_NO_NODE = 6       /* emitOnce/draw before a node world matrix was supplied (PE.cpp:289, 858) */
+} t3d_status;
+
+typedef struct t3d_ctx t3d_ctx;         /* one per GPU */
+typedef struct t3d_emitter t3d_emitter; /* replaces one tractor::ParticleEmitter */
+
+/* Blend modes, PE.h:157-163.  Carried for API fidelity; rasterisation is out of scope. */
+enum { T3D_BLEND_NONE = 0, T3D_BLEND_ALPHA = 1, T3D_BLEND_ADDITIVE = 2, T3D_BLEND_MULTIPLIED = 3 };
+
+/* Source of the emitter's random draws (the reference calls libc rand(), PE.cpp:359 and
+ * include/pch.h:151-152).  Every draw is a raw integer in [0, 2^31-1]. */
+enum {
+    T3D_RNG_LIBC = 0,   /* the library calls rand() itself, in the reference's order: same stream as the reference under the same srand() */
+    T3D_RNG_STREAM = 1, /* draws recorded from the reference are fed with t3d_emitter_feed_draws() */
+    T3D_RNG_DEVICE = 2  /* counter-based generator evaluated in the spawn kernel: draw j of particle serial s = t3d_device_rng_draw(seed, s, j) */
+};
+
+/* Billboard rotation behaviour in draw (SB.cpp:326-352). */
+enum {
+    T3D_ROT_FROZEN = 0,      /* reference-identical: one rotation matrix per process, latched from the first rotated quad (SB.cpp:339) */
+    T3D_ROT_PER_PARTICLE = 1 /* intended behaviour: createRotation(right x up, angle_i) for every quad */
+};
+
+/* Emitter configuration = the reference's private configuration members, PE.h:824-877, in the
+ * numeric types the reference stores them in (energy bounds are float there, PE.h:840-841). */
+typedef struct t3d_emitter_params {
+    uint32_t particle_count_max;   /* _particleCountMax; fixed at create */
+    uint32_t emission_rate;        /* _emissionRate, particles/s (PE.cpp:262-267) */
+    int32_t ellipsoid;             /* _ellipsoid */
+    float size_start_min, size_start_max, size_end_min, size_end_max;
+    float energy_min, energy_max;  /* ms */
+    float color_start[4], color_start_var[4], color_end[4], color_end_var[4];
+    float position[3], position_var[3];
+    float velocity[3], velocity_var[3];
+    float acceleration[3], acceleration_var[3];
+    float rotation_per_particle_speed_min, rotation_per_particle_speed_max;
+    float rotation_speed_min, rotation_speed_max;
+    float rotation_axis[3], rotation_axis_var[3];
+    int32_t orbit_position, orbit_velocity, orbit_acceleration;
+    int32_t sprite_animated, sprite_looped;
+    uint32_t sprite_frame_random_offset; /* _spriteFrameRandomOffset (unsigned in PE.h:867) */
+    int64_t sprite_frame_duration;       /* ms; _spriteFrameDurationSecs = (float)d / 1000.0f (PE.cpp:491-495) */
+    float texture_width, texture_height; /* _spriteTextureWidth/Height (PE.cpp:244-245) */
+    int32_t blend_mode;
+} t3d_emitter_params;
+
+/* Fills *p with the reference's defaults (PE.h:824-877; capacity 100, rate 10 as PE.cpp:133-143). */
+void t3d_emitter_params_default(t3d_emitter_params* p);
+
+/* Per-particle record as 34 columns of 32-bit words (struct-of-arrays; replaces
+ * ParticleEmitter::Particle, PE.h:792-822).  Energies are int32 on the device (the reference's
+ * `long` holds milliseconds; values must stay below 2^31). */
+enum {
+    T3D_COL_COLOR_START = 0,  /* 4 columns r,g,b,a */
+    T3D_COL_COLOR_END = 4,    /* 4 */
+    T3D_COL_COLOR = 8,        /* 4 */
+    T3D_COL_POSITION = 12,    /* 3 columns x,y,z */
+    T3D_COL_VELOCITY = 15,    /* 3 */
+    T3D_COL_ACCELERATION = 18,/* 3 */
+    T3D_COL_ROTATION_AXIS = 21,/* 3 */
+    T3D_COL_ENERGY_START = 24,/* int32 */
+    T3D_COL_ENERGY = 25,      /* int32 */
+    T3D_COL_SIZE_START = 26,
+    T3D_COL_SIZE_END = 27,
+    T3D_COL_SIZE = 28,
+    T3D_COL_ROT_PER_PARTICLE_SPEED = 29,
+    T3D_COL_ROTATION_SPEED = 30,
+    T3D_COL_ANGLE = 31,
+    T3D_COL_TIME_ON_FRAME = 32,
+    T3D_COL_FRAME = 33,       /* uint32 */
+    T3D_NUM_COLUMNS = 34
+};
+
+/* Output vertex, identical to SpriteBatch::SpriteVertex (SB.h:360-380): 36 bytes, 4 per quad in the
+ * order SB.cpp:355-359 emits them.  The triangle-strip index pattern of MB.cpp:126-141 is implicit
+ * ({4i..4i+3} stitched by two degenerate indices) and is not materialised per frame. */
+typedef struct t3d_sprite_vertex { float x, y, z, u, v, r, g, b, a; } t3d_sprite_vertex;
+#define T3D_FLOATS_PER_QUAD 36
+
+/* ---- library / context ------------------------------------------------------------------ */
+int t3d_abi_version(void);
+const char* t3d_last_error(void);
+
+/* Creates the per-GPU context.  `cuda_stream` may be NULL (the context creates its own stream) or a
+ * cudaStream_t owned by the caller on which all kernels and copies are then issued. */
+int t3d_ctx_create(int device, void* cuda_stream, t3d_ctx** out);
+int t3d_ctx_destroy(t3d_ctx* ctx);
+int t3d_ctx_flush(t3d_ctx* ctx);  /* launch everything queued; does not wait */
+int t3d_ctx_sync(t3d_ctx* ctx);   /* flush, then wait for the stream */
+int t3d_ctx_set_rotation_mode(t3d_ctx* ctx, int mode);            /* T3D_ROT_*; default FROZEN */
+/* Latches the process-wide billboard rotation explicitly, as if the first rotated quad ever drawn
+ * had axis u = right x up and this angle (SB.cpp:337-339). */
+int t3d_ctx_set_frozen_rotation(t3d_ctx* ctx, const float u[3], float angle);
+/* Returns the latched matrix (column-major 4x4) and whether it is latched yet. */
+int t3d_ctx_get_frozen_rotation(t3d_ctx* ctx, float m[16], int* latched);
+/* Forgets the function-local statics the reference keeps per process: the update rate-cap
+ * accumulator (PE.cpp:720) and the latched rotation (SB.cpp:339) -- i.e. "a fresh process". */
+int t3d_ctx_reset_statics(t3d_ctx* ctx);
+/* Device time in ms of the last flushed launch of each kind (CUDA events on the context's stream):
+ * which = 0 spawn, 1 update, 2 draw.  Waits for that launch to finish. */
+int t3d_ctx_last_kernel_ms(t3d_ctx* ctx, int which, float* ms);
+/* Number of kernels this library has launched on the context since creation. */
+int t3d_ctx_launch_count(t3d_ctx* ctx, uint64_t* n);
+/* Bytes staged host->device / device->host by the library since creation. */
+int t3d_ctx_transfer_bytes(t3d_ctx* ctx, uint64_t* h2d, uint64_t* d2h);
+
+/* ---- emitter lifecycle (PE.cpp:43-211) --------------------------------------------------- */
+/* Replaces ParticleEmitter::create(texture, blendMode, particleCountMax) + the 16 setters
+ * (PE.cpp:63-73, 193-208).  Installs one full-texture sprite frame like setTexture (PE.cpp:249-251). */
+int t3d_emitter_create(t3d_ctx* ctx, const t3d_emitter_params* params, t3d_emitter** out);
+/* Replaces ParticleEmitter::create(url) (PE.cpp:76-211): parses a `.particle` Properties file.
+ * The texture is not decoded; only the PNG header is read for width/height (PE.cpp:244-247). */
+int t3d_emitter_create_from_file(t3d_ctx* ctx, const char* url, t3d_emitter** out);
+/* Replaces ParticleEmitter::clone (PE.cpp:891-932): same configuration, no particles. */
+int t3d_emitter_clone(t3d_emitter* e, t3d_emitter** out);
+int t3d_emitter_destroy(t3d_emitter* e);
+
+/* ---- configuration (PE.cpp:262-267, 372-448, 485-590) ------------------------------------- */
+int t3d_emitter_set_params(t3d_emitter* e, const t3d_emitter_params* params); /* capacity must not grow */
+int t3d_emitter_get_params(t3d_emitter* e, t3d_emitter_params* params);
+int t3d_emitter_set_emission_rate(t3d_emitter* e, uint32_t rate);                   /* PE.cpp:262-267 */
+int t3d_emitter_set_sprite_tex_coords(t3d_emitter* e, uint32_t frame_count, const float* tex_coords); /* PE.cpp:512-523 */
+/* rects = frame_count x {x, y, width, height} in texels (PE.cpp:526-547) */
+int t3d_emitter_set_sprite_frame_rects(t3d_emitter* e, uint32_t frame_count, const float* rects);
+int t3d_emitter_set_sprite_frame_coords(t3d_emitter* e, uint32_t frame_count, int width, int height); /* PE.cpp:550-582 */
+int t3d_emitter_get_sprite_tex_coords(t3d_emitter* e, uint32_t* frame_count, float* tex_coords, size_t max_frames);
+int t3d_emitter_set_rng(t3d_emitter* e, int mode, uint64_t seed);
+int t3d_emitter_feed_draws(t3d_emitter* e, const int32_t* draws, size_t n);  /* T3D_RNG_STREAM */
+int t3d_emitter_pending_draws(t3d_emitter* e, size_t* n);
+
+/* ---- what the reference pulls from its Node / Scene each call ----------------------------- */
+/* Node::getWorldMatrix() of the emitter's node (PE.cpp:299).  Supplying it = Node::setDrawable. */
+int t3d_emitter_set_node_world(t3d_emitter* e, const float world[16]);
+/* getWorldMatrix() of the active camera's node (PE.cpp:860-864); only right=(m0,m1,m2), up=(m4,m5,m6) are used. */
+int t3d_emitter_set_camera_world(t3d_emitter* e, const float camera_world[16]);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+int t3d_emitter_start(t3d_emitter* e);                   /* PE.cpp:270-274 */
+int t3d_emitter_stop(t3d_emitter* e);                    /* PE.h:272 */
+int t3d_emitter_is_started(t3d_emitter* e, int* out);    /* PE.h:279 */
+int t3d_emitter_is_active(t3d_emitter* e, int* out);     /* PE.cpp:277-284 (may read the count back) */
+int t3d_emitter_emit_once(t3d_emitter* e, uint32_t particle_count);   /* PE.cpp:287-369 */
+int t3d_emitter_update(t3d_emitter* e, float elapsed_ms);             /* PE.cpp:713-832 */
+/* PE.cpp:835-888.  *draw_calls receives what the reference returns (0 if inactive, else 1). */
+int t3d_emitter_draw(t3d_emitter* e, uint32_t* draw_calls);
+int t3d_emitter_get_count(t3d_emitter* e, uint32_t* count);           /* PE.h:306; flushes + reads back */
+
+/* ---- batches: the same calls over many emitters, one launch per phase --------------------- */
+int t3d_batch_update(t3d_emitter* const* emitters, size_t n, float elapsed_ms);
+int t3d_batch_draw(t3d_emitter* const* emitters, size_t n);
+int t3d_batch_emit_once(t3d_emitter* const* emitters, size_t n, const uint32_t* particle_counts);
+int t3d_batch_get_counts(t3d_emitter* const* emitters, size_t n, uint32_t* counts);
+
+/* ---- results ------------------------------------------------------------------------------ */
+/* Device-resident vertex stream of the last draw: 4*n_quads t3d_sprite_vertex, quad i at [4i, 4i+4)
+ * in live-array order (what SpriteBatch::draw appended to MeshBatch, SB.cpp:355-362).  Flushes and
+ * reads the quad count back. */
+int t3d_emitter_vertices(t3d_emitter* e, const t3d_sprite_vertex** device_ptr, uint32_t* n_quads);
+int t3d_emitter_download_vertices(t3d_emitter* e, float* out, size_t max_quads, uint32_t* n_quads);
+/* Live particles as T3D_NUM_COLUMNS columns of `stride` words each: out[c*stride + i] for i < *count. */
+int t3d_emitter_download_state(t3d_emitter* e, uint32_t* out, size_t stride, uint32_t* count);
+int t3d_emitter_upload_state(t3d_emitter* e, const uint32_t* in, size_t stride, uint32_t count);
+
+/* ---- pure host helpers (no GPU needed): the scalar logic of the path ----------------------- */
+/* Raw 31-bit draw j of particle `serial` for T3D_RNG_DEVICE (same function the spawn kernel evaluates). */
+int32_t t3d_device_rng_draw(uint64_t seed, uint64_t serial, uint32_t j);
+/* PE.cpp:720-725: the process-wide update rate cap.  Returns 1 and sets *elapsed_ms when the update proceeds. */
+int t3d_host_rate_cap(double* running_time, float elapsed_time, float* elapsed_ms);
+/* PE.cpp:732-743: advances *emit_time and returns how many particles to emit this frame. */
+uint32_t t3d_host_emission_count(float* emit_time, float time_per_emission, float elapsed_ms);
+/* PE.cpp:526-582: uv table for a grid of width x height frames on a tex_w x tex_h texture. Returns frames written. */
+uint32_t t3d_host_sprite_frame_coords(uint32_t frame_count, int width, int height, float tex_w, float tex_h, float* tex_coords);
+/* Number of draws one spawned particle consumes starting at draws[0] (PE.cpp:312-364); 0 if the
+ * stream ends first.  Used to cut a recorded stream into per-particle offsets. */
+size_t t3d_host_particle_draws(const int32_t* draws, size_t n, int ellipsoid, uint32_t frame_random_offset);
+/* Parses a `.particle` file into params + sprite sheet description (PE.cpp:92-184). */
+int t3d_particle_file_parse(const char* url, t3d_emitter_params* params, uint32_t* frame_count,
+                            int* sprite_width, int* sprite_height, char* texture_path, size_t texture_path_len);
+/* Writes a `.particle` file in the sample's format (samples/browser/src/ParticlesSample.cpp:340-424). */
+int t3d_particle_file_save(const char* url, const char* name, const t3d_emitter_params* params,
+                           uint32_t frame_count, int sprite_width, int sprite_height, const char* texture_path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* T3D_PARTICLES_H */
