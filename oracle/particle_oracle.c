@@ -1,0 +1,650 @@
+/*
+ * particle_oracle.c -- TEST INFRASTRUCTURE, not product code (see particle_oracle.h).
+ *
+ * Plain-C restatement of the reference's particle path.  Every function cites the reference lines it
+ * follows:  PE.cpp = Tractor3Dlib/src/graphics/ParticleEmitter.cpp, PE.h = the matching header,
+ * SB.cpp = src/graphics/SpriteBatch.cpp, Matrix.cpp = src/math/Matrix.cpp,
+ * MathUtil.h = include/math/MathUtil.h, pch.h = include/pch.h.
+ *
+ * Floating point: compile with -O2 -ffp-contract=off (oracle/Makefile) so mul and add stay separate
+ * roundings, as in the reference build and in the --fmad=false kernels.  Expression order is kept
+ * exactly as the reference writes it (left-to-right sums, "+ w*m[12]" terms included) so that results
+ * are bit-identical to oracle/_ref, signed zeros included.
+ */
+#define _GNU_SOURCE
+#include "particle_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+/* ---- per-particle record: same field order as ParticleEmitter::Particle, PE.h:792-822 (144 B on LP64) ---- */
+typedef struct orc_particle {
+    float color_start[4], color_end[4], color[4];
+    float position[3], velocity[3], acceleration[3], rotation_axis[3];
+    long energy_start, energy;
+    float size_start, size_end, size;
+    float rotation_per_particle_speed, rotation_speed, angle, time_on_current_frame;
+    unsigned int frame;
+} orc_particle;
+
+struct orc_emitter {
+    t3d_emitter_params p;              /* PE.h:824-877 */
+    orc_particle* particles;           /* PE.cpp:31 */
+    unsigned int particle_count;
+    int started;
+    int has_node;
+    float node_world[16];
+    float camera_world[16];
+    float* tex_coords;                 /* frame_count * 4: u1, v1, u2, v2 */
+    unsigned int frame_count;
+    float percent_per_frame;           /* 1 / frame_count, PE.cpp:518, 532 */
+    float frame_duration_secs;         /* PE.cpp:494 */
+    float tex_w_ratio, tex_h_ratio;    /* PE.cpp:246-247 */
+    float time_per_emission;           /* PE.cpp:266 */
+    float emit_time;                   /* PE.h:876 */
+    int device_rng;
+    uint64_t rng_seed, rng_serial;
+    uint32_t rng_j;
+    float* vertices;                   /* capture of the last draw: 36 floats per quad */
+    size_t vertex_quads, vertex_cap;
+};
+
+/* =====================================================================================
+ * Draw source: stands in for libc rand() (PE.cpp:359; pch.h:151-152).
+ * ===================================================================================== */
+static uint64_t g_seq_state = 0x1234ULL;
+static int32_t* g_replay = NULL;
+static size_t g_replay_n = 0, g_replay_pos = 0;
+static int g_replaying = 0, g_recording = 0;
+static int32_t* g_recorded = NULL;
+static size_t g_recorded_n = 0, g_recorded_cap = 0;
+static uint64_t g_rand_calls = 0;
+
+static uint64_t splitmix64_next(uint64_t* s)
+{
+    uint64_t z = (*s += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+/* Specification of T3D_RNG_DEVICE: draw j of particle `serial` under `seed` is the top 31 bits of a
+ * splitmix64 finaliser over a key that mixes the three counters. */
+int32_t orc_device_rng_draw(uint64_t seed, uint64_t serial, uint32_t j)
+{
+    uint64_t z = seed + serial * 0xD1342543DE82EF95ULL + ((uint64_t)j + 1ULL) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return (int32_t)(z >> 33);
+}
+
+static void record(int32_t r)
+{
+    if (!g_recording) return;
+    if (g_recorded_n == g_recorded_cap) {
+        g_recorded_cap = g_recorded_cap ? g_recorded_cap * 2 : 4096;
+        g_recorded = (int32_t*)realloc(g_recorded, g_recorded_cap * sizeof(int32_t));
+    }
+    g_recorded[g_recorded_n++] = r;
+}
+
+static int32_t next_draw(orc_emitter* e)
+{
+    int32_t r;
+    if (e && e->device_rng) {
+        r = orc_device_rng_draw(e->rng_seed, e->rng_serial, e->rng_j++);
+    } else if (g_replaying) {
+        if (g_replay_pos >= g_replay_n) {
+            fprintf(stderr, "particle_oracle: replay stream exhausted after %zu draws\n", g_replay_pos);
+            abort();
+        }
+        r = g_replay[g_replay_pos++];
+    } else {
+        r = (int32_t)(splitmix64_next(&g_seq_state) >> 33);
+    }
+    ++g_rand_calls;
+    record(r);
+    return r;
+}
+
+void orc_rand_seed(uint64_t seed) { g_seq_state = seed; g_replaying = 0; }
+void orc_rand_replay(const int32_t* draws, size_t n)
+{
+    free(g_replay); g_replay = NULL; g_replay_n = g_replay_pos = 0; g_replaying = 0;
+    if (!draws) return;
+    g_replay = (int32_t*)malloc((n ? n : 1) * sizeof(int32_t));
+    memcpy(g_replay, draws, n * sizeof(int32_t));
+    g_replay_n = n; g_replaying = 1;
+}
+size_t orc_rand_replay_remaining(void) { return g_replaying ? g_replay_n - g_replay_pos : 0; }
+void orc_rand_record(int on) { g_recording = on != 0; g_recorded_n = 0; }
+size_t orc_rand_recorded(int32_t* out, size_t max)
+{
+    size_t n = g_recorded_n < max ? g_recorded_n : max;
+    if (out && n) memcpy(out, g_recorded, n * sizeof(int32_t));
+    return g_recorded_n;
+}
+uint64_t orc_rand_calls(void) { return g_rand_calls; }
+
+/* pch.h:151-152.  RAND_MAX is the int 2^31-1 on glibc; `(float)rand()/RAND_MAX` converts it to float,
+ * which rounds to 2^31, so the quotient is exactly r * 2^-31 (and can reach 1.0f). */
+static float random_0_1(orc_emitter* e) { return (float)next_draw(e) / (float)2147483647; }
+static float random_minus1_1(orc_emitter* e) { return (2.0f * ((float)next_draw(e) / (float)2147483647)) - 1.0f; }
+
+/* =====================================================================================
+ * Math used by the path.
+ * ===================================================================================== */
+/* MathUtil.h:195-200 (transformVector4, scalar form): left-to-right sum of four products. */
+static void transform_vector4(const float* m, float x, float y, float z, float w, float* dst)
+{
+    dst[0] = x * m[0] + y * m[4] + z * m[8] + w * m[12];
+    dst[1] = x * m[1] + y * m[5] + z * m[9] + w * m[13];
+    dst[2] = x * m[2] + y * m[6] + z * m[10] + w * m[14];
+}
+/* Matrix.cpp:965-968: transformPoint = w 1.  Arguments are taken by value, so dst may alias v. */
+static void transform_point(const float* m, const float* v, float* dst) { transform_vector4(m, v[0], v[1], v[2], 1.0f, dst); }
+/* Matrix.cpp:971-982: transformVector = w 0 (what `Vector3 *= Matrix` does, Matrix.h:1029-1033). */
+static void transform_vector(const float* m, float* v) { transform_vector4(m, v[0], v[1], v[2], 0.0f, v); }
+
+/* Matrix.cpp:348-406 (createRotation from axis + angle).  The reference build resolves cos/sin on a float
+ * to the float overloads, which gcc pairs into one sincosf call (checked in oracle/_ref's objects). */
+static void create_rotation(const float* axis, float angle, float* m)
+{
+    float x = axis[0], y = axis[1], z = axis[2];
+    float n = x * x + y * y + z * z;
+    if (n != 1.0f) {
+        n = sqrtf(n);
+        if (n > 0.000001f) {
+            n = 1.0f / n;
+            x *= n; y *= n; z *= n;
+        }
+    }
+    float s, c;
+    sincosf(angle, &s, &c);
+    float t = 1.0f - c;
+    float tx = t * x, ty = t * y, tz = t * z;
+    float txy = tx * y, txz = tx * z, tyz = ty * z;
+    float sx = s * x, sy = s * y, sz = s * z;
+    m[0] = c + tx * x; m[1] = txy + sz;   m[2] = txz - sy;   m[3] = 0.0f;
+    m[4] = txy - sz;   m[5] = c + ty * y; m[6] = tyz + sx;   m[7] = 0.0f;
+    m[8] = txz + sy;   m[9] = tyz - sx;   m[10] = c + tz * z; m[11] = 0.0f;
+    m[12] = 0.0f; m[13] = 0.0f; m[14] = 0.0f; m[15] = 1.0f;
+}
+
+/* =====================================================================================
+ * Process-wide statics of the reference.
+ * ===================================================================================== */
+static double g_running_time = 0;       /* PE.cpp:720 */
+static int g_rot_latched = 0;           /* SB.cpp:339: function-local static, initialised once */
+static float g_rot_matrix[16];
+static int g_rot_mode = T3D_ROT_FROZEN;
+
+void orc_reset_statics(void) { g_running_time = 0; g_rot_latched = 0; }
+void orc_set_rotation_mode(int mode) { g_rot_mode = mode; }
+void orc_set_frozen_rotation(const float u[3], float angle) { create_rotation(u, angle, g_rot_matrix); g_rot_latched = 1; }
+int orc_get_frozen_rotation(float m[16]) { if (g_rot_latched && m) memcpy(m, g_rot_matrix, sizeof(g_rot_matrix)); return g_rot_latched; }
+
+/* =====================================================================================
+ * Emitter configuration.
+ * ===================================================================================== */
+static void identity(float* m) { memset(m, 0, 16 * sizeof(float)); m[0] = m[5] = m[10] = m[15] = 1.0f; }
+
+void orc_emitter_set_emission_rate(orc_emitter* e, uint32_t rate)
+{
+    /* PE.cpp:262-267 */
+    e->p.emission_rate = rate;
+    e->time_per_emission = 1000.0f / (float)rate;
+}
+
+void orc_emitter_set_sprite_tex_coords(orc_emitter* e, uint32_t frame_count, const float* tex_coords)
+{
+    /* PE.cpp:512-523 */
+    e->frame_count = frame_count;
+    e->percent_per_frame = 1.0f / (float)frame_count;
+    float* nc = (float*)malloc(sizeof(float) * 4 * frame_count);
+    memcpy(nc, tex_coords, sizeof(float) * 4 * frame_count);
+    free(e->tex_coords);
+    e->tex_coords = nc;
+}
+
+void orc_emitter_set_sprite_frame_rects(orc_emitter* e, uint32_t frame_count, const float* rects)
+{
+    /* PE.cpp:526-547: rects are {x, y, width, height} in texels. */
+    e->frame_count = frame_count;
+    e->percent_per_frame = 1.0f / (float)frame_count;
+    free(e->tex_coords);
+    e->tex_coords = (float*)malloc(sizeof(float) * 4 * frame_count);
+    for (uint32_t i = 0; i < frame_count; ++i) {
+        const float* r = rects + 4 * i;
+        float* c = e->tex_coords + 4 * i;
+        c[0] = e->tex_w_ratio * r[0];
+        c[1] = 1.0f - e->tex_h_ratio * r[1];
+        c[2] = c[0] + e->tex_w_ratio * r[2];
+        c[3] = c[1] - e->tex_h_ratio * r[3];
+    }
+}
+
+void orc_emitter_set_sprite_frame_coords(orc_emitter* e, uint32_t frame_count, int width, int height)
+{
+    /* PE.cpp:550-582: walk the sheet left-to-right, top-to-bottom; the rect array has frame_count entries
+     * and entries the walk never reaches keep Rectangle's default (all zero). */
+    float* rects = (float*)calloc((size_t)frame_count * 4, sizeof(float));
+    unsigned int cols = (unsigned int)(e->p.texture_width / (float)width);
+    unsigned int rows = (unsigned int)(e->p.texture_height / (float)height);
+    unsigned int n = 0;
+    for (unsigned int i = 0; i < rows && n != frame_count; ++i) {
+        int y = (int)i * height;
+        for (unsigned int j = 0; j < cols; ++j) {
+            int x = (int)j * width;
+            float* r = rects + 4 * ((size_t)i * cols + j);
+            r[0] = (float)x; r[1] = (float)y; r[2] = (float)width; r[3] = (float)height;
+            if (++n == frame_count) break;
+        }
+    }
+    orc_emitter_set_sprite_frame_rects(e, frame_count, rects);
+    free(rects);
+}
+
+uint32_t orc_emitter_get_sprite_tex_coords(orc_emitter* e, float* out, size_t max_frames)
+{
+    size_t n = e->frame_count < max_frames ? e->frame_count : max_frames;
+    if (out) memcpy(out, e->tex_coords, sizeof(float) * 4 * n);
+    return e->frame_count;
+}
+
+void orc_emitter_set_params(orc_emitter* e, const t3d_emitter_params* p)
+{
+    uint32_t cap = e->p.particle_count_max;
+    float tw = e->p.texture_width, th = e->p.texture_height;
+    e->p = *p;
+    e->p.particle_count_max = cap; /* storage is sized once, PE.cpp:31 */
+    e->p.texture_width = tw; e->p.texture_height = th;
+    orc_emitter_set_emission_rate(e, p->emission_rate);
+    e->frame_duration_secs = (float)p->sprite_frame_duration / 1000.0f; /* PE.cpp:491-495 */
+}
+
+void orc_emitter_get_params(orc_emitter* e, t3d_emitter_params* p) { *p = e->p; }
+
+orc_emitter* orc_emitter_create(const t3d_emitter_params* p)
+{
+    orc_emitter* e = (orc_emitter*)calloc(1, sizeof(orc_emitter));
+    e->p = *p;
+    e->particles = (orc_particle*)calloc(p->particle_count_max ? p->particle_count_max : 1, sizeof(orc_particle));
+    identity(e->node_world);
+    identity(e->camera_world);
+    e->has_node = 1;
+    /* setTexture, PE.cpp:244-251: cache the texture size and its reciprocals, install one full-texture frame. */
+    e->tex_w_ratio = 1.0f / (float)(unsigned int)p->texture_width;
+    e->tex_h_ratio = 1.0f / (float)(unsigned int)p->texture_height;
+    float full[4] = { 0.0f, 0.0f, p->texture_width, p->texture_height };
+    orc_emitter_set_sprite_frame_rects(e, 1, full);
+    orc_emitter_set_params(e, p);
+    return e;
+}
+
+void orc_emitter_destroy(orc_emitter* e)
+{
+    if (!e) return;
+    free(e->particles); free(e->tex_coords); free(e->vertices); free(e);
+}
+
+void orc_emitter_set_node_world(orc_emitter* e, const float m[16]) { memcpy(e->node_world, m, 64); e->has_node = 1; }
+void orc_emitter_set_camera_world(orc_emitter* e, const float m[16]) { memcpy(e->camera_world, m, 64); }
+void orc_emitter_set_device_rng(orc_emitter* e, int enable, uint64_t seed) { e->device_rng = enable; e->rng_seed = seed; e->rng_serial = 0; }
+float orc_emitter_get_emit_time(orc_emitter* e) { return e->emit_time; }
+
+void orc_emitter_start(orc_emitter* e) { e->started = 1; }   /* PE.cpp:270-274 */
+void orc_emitter_stop(orc_emitter* e) { e->started = 0; }    /* PE.h:272 */
+int orc_emitter_is_started(orc_emitter* e) { return e->started; }
+int orc_emitter_is_active(orc_emitter* e)
+{
+    /* PE.cpp:277-284 */
+    if (e->started) return 1;
+    if (!e->has_node) return 0;
+    return e->particle_count > 0;
+}
+uint32_t orc_emitter_get_count(orc_emitter* e) { return e->particle_count; }
+
+/* =====================================================================================
+ * Spawn.
+ * ===================================================================================== */
+static float generate_scalar(orc_emitter* e, float min, float max) { return min + (max - min) * random_0_1(e); } /* PE.cpp:611-614 */
+
+static void generate_color(orc_emitter* e, const float* base, const float* var, float* dst)
+{
+    /* PE.cpp:669-679: x, y, z, w in that order, one draw each (consumed even when the variance is 0). */
+    dst[0] = base[0] + var[0] * random_minus1_1(e);
+    dst[1] = base[1] + var[1] * random_minus1_1(e);
+    dst[2] = base[2] + var[2] * random_minus1_1(e);
+    dst[3] = base[3] + var[3] * random_minus1_1(e);
+}
+
+static void generate_vector(orc_emitter* e, const float* base, const float* var, float* dst, int ellipsoid)
+{
+    if (ellipsoid) {
+        /* PE.cpp:629-650: rejection-sample the unit ball, then scale and translate. */
+        do {
+            dst[0] = random_minus1_1(e);
+            dst[1] = random_minus1_1(e);
+            dst[2] = random_minus1_1(e);
+        } while (sqrtf(dst[0] * dst[0] + dst[1] * dst[1] + dst[2] * dst[2]) > 1.0f); /* Vector3::length, Vector3.h:259 */
+        dst[0] *= var[0]; dst[1] *= var[1]; dst[2] *= var[2];
+        dst[0] += base[0]; dst[1] += base[1]; dst[2] += base[2];
+    } else {
+        /* PE.cpp:617-626 */
+        dst[0] = base[0] + var[0] * random_minus1_1(e);
+        dst[1] = base[1] + var[1] * random_minus1_1(e);
+        dst[2] = base[2] + var[2] * random_minus1_1(e);
+    }
+}
+
+void orc_emitter_emit_once(orc_emitter* e, uint32_t n)
+{
+    /* PE.cpp:287-369 */
+    const t3d_emitter_params* P = &e->p;
+    if (n + e->particle_count > P->particle_count_max) n = P->particle_count_max - e->particle_count; /* :293-296 */
+
+    float world[16];
+    memcpy(world, e->node_world, sizeof(world));
+    float translation[3] = { world[12], world[13], world[14] }; /* Matrix::getTranslation -> decompose, Matrix.cpp:517-523 */
+    world[12] = 0.0f; world[13] = 0.0f; world[14] = 0.0f;       /* :303-305 */
+
+    for (uint32_t i = 0; i < n; ++i) {
+        orc_particle* p = &e->particles[e->particle_count];
+        e->rng_j = 0;
+
+        generate_color(e, P->color_start, P->color_start_var, p->color_start);
+        generate_color(e, P->color_end, P->color_end_var, p->color_end);
+        memcpy(p->color, p->color_start, sizeof(p->color));
+
+        /* :316 -- the bounds are float members (PE.h:840-841), so the float overload is chosen and the
+         * result is truncated into the long fields. */
+        p->energy = p->energy_start = (long)generate_scalar(e, P->energy_min, P->energy_max);
+        p->size = p->size_start = generate_scalar(e, P->size_start_min, P->size_start_max);
+        p->size_end = generate_scalar(e, P->size_end_min, P->size_end_max);
+        p->rotation_per_particle_speed = generate_scalar(e, P->rotation_per_particle_speed_min, P->rotation_per_particle_speed_max);
+        p->angle = generate_scalar(e, 0.0f, p->rotation_per_particle_speed);
+        p->rotation_speed = generate_scalar(e, P->rotation_speed_min, P->rotation_speed_max);
+
+        generate_vector(e, P->position, P->position_var, p->position, P->ellipsoid); /* :325 */
+        generate_vector(e, P->velocity, P->velocity_var, p->velocity, 0);
+        generate_vector(e, P->acceleration, P->acceleration_var, p->acceleration, 0);
+        generate_vector(e, P->rotation_axis, P->rotation_axis_var, p->rotation_axis, 0);
+
+        if (P->orbit_position) transform_point(world, p->position, p->position);             /* :332-335 */
+        if (P->orbit_velocity) transform_point(world, p->velocity, p->velocity);             /* :337-340 */
+        if (P->orbit_acceleration) transform_point(world, p->acceleration, p->acceleration); /* :342-345 */
+        if (p->rotation_speed != 0.0f &&
+            !(p->rotation_axis[0] == 0.0f && p->rotation_axis[1] == 0.0f && p->rotation_axis[2] == 0.0f))
+            transform_point(world, p->rotation_axis, p->rotation_axis);                     /* :348-351 */
+
+        p->position[0] += translation[0]; p->position[1] += translation[1]; p->position[2] += translation[2]; /* :354 */
+
+        if (P->sprite_frame_random_offset > 0)
+            p->frame = (unsigned int)next_draw(e) % P->sprite_frame_random_offset;          /* :357-360 */
+        else
+            p->frame = 0;
+        p->time_on_current_frame = 0.0f;
+
+        ++e->particle_count;
+        ++e->rng_serial;
+    }
+}
+
+/* =====================================================================================
+ * Update.
+ * ===================================================================================== */
+void orc_emitter_update(orc_emitter* e, float elapsed_time)
+{
+    /* PE.cpp:713-832 */
+    if (!orc_emitter_is_active(e)) return;
+
+    g_running_time += elapsed_time;              /* :720-725, shared by every emitter of the process */
+    if (g_running_time < 8) return;
+    float elapsed_ms = (float)g_running_time;
+    g_running_time = 0;
+
+    float elapsed_secs = elapsed_ms * 0.001f;
+
+    if (e->started && e->p.emission_rate) {
+        e->emit_time += elapsed_ms;                                             /* :732 */
+        unsigned int emit_count = (unsigned int)(e->emit_time / e->time_per_emission);
+        if (emit_count) {
+            if ((int)e->time_per_emission > 0)                                 /* :740-743 */
+                e->emit_time = (float)fmod((double)e->emit_time, (double)e->time_per_emission);
+            orc_emitter_emit_once(e, emit_count);
+        }
+    }
+
+    const int animated = e->p.sprite_animated, looped = e->p.sprite_looped;
+    for (size_t i = 0; i < e->particle_count; ++i) {
+        orc_particle* p = &e->particles[i];
+        p->energy = (long)((float)p->energy - elapsed_ms);                      /* :753  long -= float */
+
+        if (p->energy > 0L) {
+            if (p->rotation_speed != 0.0f &&
+                !(p->rotation_axis[0] == 0.0f && p->rotation_axis[1] == 0.0f && p->rotation_axis[2] == 0.0f)) {
+                float rot[16];                                                  /* :757-763 */
+                create_rotation(p->rotation_axis, p->rotation_speed * elapsed_secs, rot);
+                transform_point(rot, p->velocity, p->velocity);
+                transform_point(rot, p->acceleration, p->acceleration);
+            }
+            p->velocity[0] += p->acceleration[0] * elapsed_secs;                /* :766-772 */
+            p->velocity[1] += p->acceleration[1] * elapsed_secs;
+            p->velocity[2] += p->acceleration[2] * elapsed_secs;
+            p->position[0] += p->velocity[0] * elapsed_secs;
+            p->position[1] += p->velocity[1] * elapsed_secs;
+            p->position[2] += p->velocity[2] * elapsed_secs;
+            p->angle += p->rotation_per_particle_speed * elapsed_secs;          /* :774 */
+
+            float percent = 1.0f - ((float)p->energy / (float)p->energy_start); /* :777 */
+            for (int k = 0; k < 4; ++k)
+                p->color[k] = p->color_start[k] + (p->color_end[k] - p->color_start[k]) * percent; /* :779-782 */
+            p->size = p->size_start + (p->size_end - p->size_start) * percent;  /* :784 */
+
+            if (animated) {
+                if (!looped) {                                                  /* :789-803 */
+                    float percent_spent = 0.0f;
+                    for (size_t k = 0; k < p->frame; ++k) percent_spent += e->percent_per_frame;
+                    p->time_on_current_frame = percent - percent_spent;
+                    if (p->frame < e->frame_count - 1 && p->time_on_current_frame >= e->percent_per_frame) ++p->frame;
+                } else {                                                        /* :804-818 */
+                    p->time_on_current_frame += elapsed_secs;
+                    if (p->time_on_current_frame >= e->frame_duration_secs) {
+                        p->time_on_current_frame -= e->frame_duration_secs;
+                        ++p->frame;
+                        if (p->frame == e->frame_count) p->frame = 0;
+                    }
+                }
+            }
+        } else {
+            /* :821-830 swap-with-last removal; the moved particle is not examined this frame. */
+            if (i != e->particle_count - 1) e->particles[i] = e->particles[e->particle_count - 1];
+            --e->particle_count;
+        }
+    }
+}
+
+/* =====================================================================================
+ * Draw.
+ * ===================================================================================== */
+static void billboard(const float* pos, const float* right, const float* up, float width, float height,
+                      float u1, float v1, float u2, float v2, const float* color, float angle, float* out)
+{
+    /* SB.cpp:292-363, with rotationPoint = (0.5, 0.5) as ParticleEmitter::draw passes it (PE.cpp:855). */
+    float tr[3] = { right[0] * (width * 0.5f), right[1] * (width * 0.5f), right[2] * (width * 0.5f) };
+    float tf[3] = { up[0] * (height * 0.5f), up[1] * (height * 0.5f), up[2] * (height * 0.5f) };
+    float p0[3], p1[3], p2[3], p3[3];
+    for (int k = 0; k < 3; ++k) { p0[k] = pos[k]; p0[k] -= tr[k]; p0[k] -= tf[k]; }
+    for (int k = 0; k < 3; ++k) { p1[k] = pos[k]; p1[k] += tr[k]; p1[k] -= tf[k]; }
+    for (int k = 0; k < 3; ++k) tf[k] = up[k] * height;
+    for (int k = 0; k < 3; ++k) { p2[k] = p0[k] + tf[k]; p3[k] = p1[k] + tf[k]; }
+
+    if (angle != 0) {
+        float rp[3];
+        for (int k = 0; k < 3; ++k) {
+            tr[k] = right[k] * (width * 0.5f);
+            tf[k] *= 0.5f;
+            rp[k] = p0[k];
+            rp[k] += tr[k];
+            rp[k] += tf[k];
+        }
+        float u[3] = { (right[1] * up[2]) - (right[2] * up[1]),   /* MathUtil.h:216-225 */
+                       (right[2] * up[0]) - (right[0] * up[2]),
+                       (right[0] * up[1]) - (right[1] * up[0]) };
+        float local[16];
+        const float* rot;
+        if (g_rot_mode == T3D_ROT_FROZEN) {
+            /* SB.cpp:339: `static Matrix rotation = createRotation(u, rotationAngle)` -- computed by the first
+             * rotated quad the process ever draws and reused by every later one. */
+            if (!g_rot_latched) { create_rotation(u, angle, g_rot_matrix); g_rot_latched = 1; }
+            rot = g_rot_matrix;
+        } else {
+            create_rotation(u, angle, local);
+            rot = local;
+        }
+        float* ps[4] = { p0, p1, p2, p3 };
+        for (int q = 0; q < 4; ++q) {
+            float* p = ps[q];
+            p[0] -= rp[0]; p[1] -= rp[1]; p[2] -= rp[2];
+            transform_vector(rot, p);
+            p[0] += rp[0]; p[1] += rp[1]; p[2] += rp[2];
+        }
+    }
+    /* SB.cpp:355-359 */
+    const float* ps[4] = { p0, p1, p2, p3 };
+    const float us[4] = { u1, u2, u1, u2 };
+    const float vs[4] = { v1, v1, v2, v2 };
+    for (int q = 0; q < 4; ++q) {
+        float* v = out + 9 * q;
+        v[0] = ps[q][0]; v[1] = ps[q][1]; v[2] = ps[q][2];
+        v[3] = us[q]; v[4] = vs[q];
+        v[5] = color[0]; v[6] = color[1]; v[7] = color[2]; v[8] = color[3];
+    }
+}
+
+uint32_t orc_emitter_draw(orc_emitter* e)
+{
+    /* PE.cpp:835-888 */
+    if (!orc_emitter_is_active(e)) return 0;
+    if (e->particle_count > 0) {
+        if (e->vertex_cap < e->particle_count) {
+            e->vertex_cap = e->particle_count;
+            e->vertices = (float*)realloc(e->vertices, e->vertex_cap * T3D_FLOATS_PER_QUAD * sizeof(float));
+        }
+        e->vertex_quads = 0; /* SpriteBatch::start() */
+        const float* cw = e->camera_world;
+        float right[3] = { cw[0], cw[1], cw[2] }; /* Matrix.cpp:692-701 */
+        float up[3] = { cw[4], cw[5], cw[6] };    /* Matrix.cpp:656-665 */
+        for (size_t i = 0; i < e->particle_count; ++i) {
+            const orc_particle* p = &e->particles[i];
+            const float* uv = e->tex_coords + (size_t)p->frame * 4;
+            billboard(p->position, right, up, p->size, p->size, uv[0], uv[1], uv[2], uv[3], p->color, p->angle,
+                      e->vertices + e->vertex_quads * T3D_FLOATS_PER_QUAD);
+            ++e->vertex_quads;
+        }
+    }
+    return 1;
+}
+
+uint32_t orc_emitter_get_vertices(orc_emitter* e, float* out, size_t max_quads)
+{
+    size_t n = e->vertex_quads < max_quads ? e->vertex_quads : max_quads;
+    if (out && n) memcpy(out, e->vertices, n * T3D_FLOATS_PER_QUAD * sizeof(float));
+    return (uint32_t)e->vertex_quads;
+}
+
+/* =====================================================================================
+ * State exchange in the column layout of include/t3d_particles.h.
+ * ===================================================================================== */
+static void put_f(uint32_t* out, size_t stride, int col, size_t i, float v) { memcpy(&out[(size_t)col * stride + i], &v, 4); }
+static float get_f(const uint32_t* in, size_t stride, int col, size_t i) { float v; memcpy(&v, &in[(size_t)col * stride + i], 4); return v; }
+
+uint32_t orc_emitter_get_state(orc_emitter* e, uint32_t* out, size_t stride)
+{
+    uint32_t n = e->particle_count;
+    if (!out) return n;
+    for (uint32_t i = 0; i < n; ++i) {
+        const orc_particle* p = &e->particles[i];
+        for (int k = 0; k < 4; ++k) {
+            put_f(out, stride, T3D_COL_COLOR_START + k, i, p->color_start[k]);
+            put_f(out, stride, T3D_COL_COLOR_END + k, i, p->color_end[k]);
+            put_f(out, stride, T3D_COL_COLOR + k, i, p->color[k]);
+        }
+        for (int k = 0; k < 3; ++k) {
+            put_f(out, stride, T3D_COL_POSITION + k, i, p->position[k]);
+            put_f(out, stride, T3D_COL_VELOCITY + k, i, p->velocity[k]);
+            put_f(out, stride, T3D_COL_ACCELERATION + k, i, p->acceleration[k]);
+            put_f(out, stride, T3D_COL_ROTATION_AXIS + k, i, p->rotation_axis[k]);
+        }
+        out[(size_t)T3D_COL_ENERGY_START * stride + i] = (uint32_t)(int32_t)p->energy_start;
+        out[(size_t)T3D_COL_ENERGY * stride + i] = (uint32_t)(int32_t)p->energy;
+        put_f(out, stride, T3D_COL_SIZE_START, i, p->size_start);
+        put_f(out, stride, T3D_COL_SIZE_END, i, p->size_end);
+        put_f(out, stride, T3D_COL_SIZE, i, p->size);
+        put_f(out, stride, T3D_COL_ROT_PER_PARTICLE_SPEED, i, p->rotation_per_particle_speed);
+        put_f(out, stride, T3D_COL_ROTATION_SPEED, i, p->rotation_speed);
+        put_f(out, stride, T3D_COL_ANGLE, i, p->angle);
+        put_f(out, stride, T3D_COL_TIME_ON_FRAME, i, p->time_on_current_frame);
+        out[(size_t)T3D_COL_FRAME * stride + i] = p->frame;
+    }
+    return n;
+}
+
+int orc_emitter_set_state(orc_emitter* e, const uint32_t* in, size_t stride, uint32_t n)
+{
+    if (n > e->p.particle_count_max) return 1;
+    for (uint32_t i = 0; i < n; ++i) {
+        orc_particle* p = &e->particles[i];
+        for (int k = 0; k < 4; ++k) {
+            p->color_start[k] = get_f(in, stride, T3D_COL_COLOR_START + k, i);
+            p->color_end[k] = get_f(in, stride, T3D_COL_COLOR_END + k, i);
+            p->color[k] = get_f(in, stride, T3D_COL_COLOR + k, i);
+        }
+        for (int k = 0; k < 3; ++k) {
+            p->position[k] = get_f(in, stride, T3D_COL_POSITION + k, i);
+            p->velocity[k] = get_f(in, stride, T3D_COL_VELOCITY + k, i);
+            p->acceleration[k] = get_f(in, stride, T3D_COL_ACCELERATION + k, i);
+            p->rotation_axis[k] = get_f(in, stride, T3D_COL_ROTATION_AXIS + k, i);
+        }
+        p->energy_start = (int32_t)in[(size_t)T3D_COL_ENERGY_START * stride + i];
+        p->energy = (int32_t)in[(size_t)T3D_COL_ENERGY * stride + i];
+        p->size_start = get_f(in, stride, T3D_COL_SIZE_START, i);
+        p->size_end = get_f(in, stride, T3D_COL_SIZE_END, i);
+        p->size = get_f(in, stride, T3D_COL_SIZE, i);
+        p->rotation_per_particle_speed = get_f(in, stride, T3D_COL_ROT_PER_PARTICLE_SPEED, i);
+        p->rotation_speed = get_f(in, stride, T3D_COL_ROTATION_SPEED, i);
+        p->angle = get_f(in, stride, T3D_COL_ANGLE, i);
+        p->time_on_current_frame = get_f(in, stride, T3D_COL_TIME_ON_FRAME, i);
+        p->frame = in[(size_t)T3D_COL_FRAME * stride + i];
+    }
+    e->particle_count = n;
+    return 0;
+}
+
+/* =====================================================================================
+ * Timing loops.
+ * ===================================================================================== */
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
+double orc_time_update(orc_emitter* e, float elapsed_ms, int frames)
+{
+    double t0 = now_s();
+    for (int i = 0; i < frames; ++i) orc_emitter_update(e, elapsed_ms);
+    return now_s() - t0;
+}
+double orc_time_draw(orc_emitter* e, int frames)
+{
+    double t0 = now_s();
+    for (int i = 0; i < frames; ++i) orc_emitter_draw(e);
+    return now_s() - t0;
+}
+double orc_time_frames(orc_emitter* e, float elapsed_ms, int frames)
+{
+    double t0 = now_s();
+    for (int i = 0; i < frames; ++i) { orc_emitter_update(e, elapsed_ms); orc_emitter_draw(e); }
+    return now_s() - t0;
+}
