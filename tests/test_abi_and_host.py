@@ -1,0 +1,243 @@
+"""CPU-side checks of the boundary: the shared library loads and exports every symbol include/t3d_particles.h
+declares, fails loudly without a GPU, and its pure-host helpers (the scalar logic of the path) agree with the
+oracle.  No compute call is made."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cpu_harness as H
+from tractor3d_b200 import abi, presets
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "t3d_particles.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(t3d_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = abi.load()
+    names = declared_functions()
+    assert len(names) >= 50
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/t3d_particles.h but not exported"
+    assert set(names) == set(abi.PROTOTYPES), set(names) ^ set(abi.PROTOTYPES)
+    assert lib.t3d_abi_version() == 1
+
+
+def test_params_struct_layout_matches_header_defaults():
+    lib = abi.load()
+    p = abi.EmitterParams()
+    lib.t3d_emitter_params_default(C.byref(p))
+    assert p.as_dict() == abi.default_params().as_dict()
+    assert C.sizeof(abi.EmitterParams) == 264  # sizeof(t3d_emitter_params) as compiled by gcc
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = abi.load()
+    h = C.c_void_p()
+    rc = lib.t3d_ctx_create(0, None, C.byref(h))
+    assert rc == abi.ERR_CUDA and not h.value
+    assert b"no CPU fallback" in lib.t3d_last_error()
+
+
+def test_device_rng_spec_matches_oracle_restatement():
+    lib, O = abi.load(), H.oracle()
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        seed, serial, j = int(rng.integers(0, 2**63)), int(rng.integers(0, 2**40)), int(rng.integers(0, 64))
+        a, b = lib.t3d_device_rng_draw(seed, serial, j), O.device_rng_draw(seed, serial, j)
+        assert a == b and 0 <= a < 2**31
+
+
+def test_rate_cap_and_emission_count_follow_the_oracle():
+    # Drive the oracle's update() with awkward dts and replay the same scalar logic through the host helpers.
+    lib = abi.load()
+    for rate, dts in ((300, [16.6667] * 50), (1000, [16.6667] * 50), (1200, [16.6667] * 40), (37, [3.0, 5.5, 2.1, 9.9] * 30),
+                      (999, [7.9, 0.2, 33.3] * 30)):
+        O = H.oracle(fresh=True)
+        p, _ = presets.smoke()
+        p.emission_rate = rate
+        p.particle_count_max = 1_000_000
+        p.energy_min = p.energy_max = 1e9
+        eo = O.emitter(p)
+        eo.start()
+        running, emit_time = C.c_double(0.0), C.c_float(0.0)
+        tpe = np.float32(1000.0) / np.float32(rate)
+        total = 0
+        for dt in dts:
+            eo.update(dt)
+            ms = C.c_float()
+            if lib.t3d_host_rate_cap(C.byref(running), dt, C.byref(ms)):
+                total += lib.t3d_host_emission_count(C.byref(emit_time), float(tpe), ms.value)
+            assert total == eo.count(), (rate, dt)
+            assert np.float32(emit_time.value) == np.float32(eo.emit_time())
+
+
+def test_sprite_frame_coords_follow_the_oracle():
+    lib, O = abi.load(), H.oracle()
+    for tw, th, n, w, h in ((1024, 256, 3, 256, 256), (256, 256, 16, 64, 64), (64, 64, 1, 64, 64), (300, 200, 7, 100, 50),
+                            (512, 512, 40, 128, 128)):
+        p = abi.default_params(texture_width=tw, texture_height=th)
+        eo = O.emitter(p)
+        eo.set_sprite_frame_coords(n, w, h)
+        out = np.zeros(n * 4, dtype=np.float32)
+        lib.t3d_host_sprite_frame_coords(n, w, h, tw, th, out.ctypes.data_as(C.POINTER(C.c_float)))
+        assert np.array_equal(out.view(np.uint32), eo.sprite_tex_coords().reshape(-1).view(np.uint32))
+
+
+def test_particle_draws_cuts_a_recorded_stream_like_the_oracle():
+    lib, O = abi.load(), H.oracle(fresh=True)
+    for ellipsoid, fro in ((0, 0), (0, 3), (1, 0), (1, 4)):
+        p, _ = presets.fire()
+        p.ellipsoid, p.sprite_frame_random_offset = ellipsoid, fro
+        O.rand_seed(100 + ellipsoid * 10 + fro)
+        eo = O.emitter(p)
+        lens = []
+        stream = []
+        for k in range(200):
+            O.rand_record(1)
+            eo.emit_once(1)
+            d = O.recorded()
+            lens.append(len(d)); stream.append(d)
+        allv = np.concatenate(stream).astype(np.int32)
+        pos = 0
+        for k in range(200):
+            n = lib.t3d_host_particle_draws(allv[pos:].ctypes.data_as(C.POINTER(C.c_int32)), len(allv) - pos, ellipsoid, fro)
+            assert n == lens[k]
+            pos += n
+        assert pos == len(allv)
+        if not ellipsoid:
+            assert set(lens) == {26 + (1 if fro else 0)}
+        else:
+            assert min(lens) == 26 + (1 if fro else 0) and max(lens) > min(lens)
+
+
+PARTICLE_TEXT = """
+// a test emitter
+particle sparks
+{
+    sprite
+    {
+        path = sheet.png
+        width = 32
+        height = 16
+        blendMode = MULTIPLIED
+        animated = true
+        looped = true
+        frameCount = 6
+        frameRandomOffset = 9
+        frameDuration = 33.7
+    }
+
+    particleCountMax = 777
+    emissionRate = 55
+    ellipsoid = true
+    orbitPosition = false
+    orbitVelocity = true
+    sizeStartMin = 0.25
+    sizeStartMax = 1e1
+    energyMin = 250
+    energyMax = 1250
+    colorStart = 1, 0.5, 0.25, 1
+    colorEnd = 0, 0, 0, 0.125
+    position = 1, 2, 3
+    velocityVar = 0.5, 0.5, 0.5
+    /* block
+       comment */
+    rotationSpeedMin = -2
+    rotationSpeedMax = 2.5
+    rotationAxis = 0, 1, 0
+    rotationPerParticleSpeedMax = 3
+}
+"""
+
+
+def _write_png(path, w, h):
+    import struct
+    import zlib
+    raw = b"".join(b"\x00" + b"\x00" * (w * 4) for _ in range(h))
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+    open(path, "wb").write(png)
+
+
+def _parse(lib, path):
+    p = abi.EmitterParams()
+    fc, sw, sh = C.c_uint32(), C.c_int(), C.c_int()
+    tex = C.create_string_buffer(1024)
+    rc = lib.t3d_particle_file_parse(path.encode(), C.byref(p), C.byref(fc), C.byref(sw), C.byref(sh), tex, 1024)
+    return rc, p, fc.value, sw.value, sh.value, tex.value.decode()
+
+
+def test_particle_file_parse_and_save_round_trip(tmp_path):
+    lib = abi.load()
+    _write_png(str(tmp_path / "sheet.png"), 96, 32)
+    f = tmp_path / "sparks.particle"
+    f.write_text(PARTICLE_TEXT)
+    rc, p, fc, sw, sh, tex = _parse(lib, str(f))
+    assert rc == abi.OK
+    assert (fc, sw, sh) == (6, 32, 16) and tex.endswith("sheet.png")
+    assert (p.texture_width, p.texture_height) == (96.0, 32.0)
+    assert p.particle_count_max == 777 and p.emission_rate == 55 and p.ellipsoid == 1
+    assert p.orbit_position == 0 and p.orbit_velocity == 1 and p.orbit_acceleration == 0
+    assert p.sprite_animated == 1 and p.sprite_looped == 1
+    assert p.sprite_frame_random_offset == 6          # min(frameRandomOffset, frameCount), PE.cpp:128
+    assert p.sprite_frame_duration == 33              # float -> long, PE.cpp:129/206
+    assert p.blend_mode == abi.BLEND_MULTIPLIED
+    assert (p.size_start_min, p.size_start_max, p.size_end_min) == (0.25, 10.0, 0.0)   # missing key -> 0
+    assert (p.energy_min, p.energy_max) == (250.0, 1250.0)
+    assert list(p.color_start) == [1, 0.5, 0.25, 1] and list(p.color_end) == [0, 0, 0, 0.125]
+    assert list(p.position) == [1, 2, 3] and list(p.velocity_var) == [0.5, 0.5, 0.5] and list(p.velocity) == [0, 0, 0]
+    assert (p.rotation_speed_min, p.rotation_speed_max) == (-2.0, 2.5) and list(p.rotation_axis) == [0, 1, 0]
+    assert p.rotation_per_particle_speed_max == 3.0
+    # save (the sample's writer omits rotationSpeed*/rotationAxis*, ParticlesSample.cpp:340-424) and re-parse
+    out = tmp_path / "saved.particle"
+    assert lib.t3d_particle_file_save(str(out).encode(), b"sparks", C.byref(p), fc, sw, sh, b"sheet.png") == abi.OK
+    rc, q, fc2, sw2, sh2, _ = _parse(lib, str(out))
+    assert rc == abi.OK and (fc2, sw2, sh2) == (fc, sw, sh)
+    dp, dq = p.as_dict(), q.as_dict()
+    for k in ("rotation_speed_min", "rotation_speed_max", "rotation_axis", "rotation_axis_var"):
+        dp.pop(k); dq.pop(k)
+    assert dp == dq
+
+
+def test_particle_file_errors(tmp_path):
+    lib = abi.load()
+    rc, *_ = _parse(lib, str(tmp_path / "missing.particle"))
+    assert rc == abi.ERR_IO
+    bad = tmp_path / "bad.particle"
+    bad.write_text("material m\n{\n}\n")
+    assert _parse(lib, str(bad))[0] == abi.ERR_IO          # namespace must be `particle` (PE.cpp:94)
+    nosprite = tmp_path / "nosprite.particle"
+    nosprite.write_text("particle p\n{\n    emissionRate = 3\n}\n")
+    assert _parse(lib, str(nosprite))[0] == abi.ERR_IO     # PE.cpp:101-106
+
+
+@pytest.mark.skipif(not (H.ref_available() and os.path.isdir("/root/reference/samples/browser/res/common/particles")),
+                    reason="needs the reference tree and oracle/_ref")
+@pytest.mark.parametrize("name", ["fire", "smoke", "explosion"])
+def test_stock_particle_files_parse_like_the_reference(name):
+    # The reference's own Properties parser (running inside oracle/_ref) and ours must agree on the stock files,
+    # and both must agree with the presets the benchmarks use.
+    lib, R = abi.load(), H.ref()
+    path = f"/root/reference/samples/browser/res/common/particles/{name}.particle"
+    rc, p, fc, sw, sh, _ = _parse(lib, path)
+    assert rc == abi.OK
+    h = R.emitter_create_from_file(path.encode())
+    er = H.CpuEmitter(R, handle=h)
+    assert p.as_dict() == er.params().as_dict()
+    preset, sprite = getattr(presets, name)()
+    assert preset.as_dict() == p.as_dict() and sprite == (fc, sw, sh)
+    table = np.zeros(fc * 4, dtype=np.float32)
+    lib.t3d_host_sprite_frame_coords(fc, sw, sh, p.texture_width, p.texture_height, table.ctypes.data_as(C.POINTER(C.c_float)))
+    assert np.array_equal(table.view(np.uint32), er.sprite_tex_coords().reshape(-1).view(np.uint32))

@@ -1,0 +1,296 @@
+"""GPU parity: the CUDA backend, called through the C ABI, against the plain-C oracle and against the golden
+vectors generated from the unmodified reference.
+
+Bar (BASELINE.json north_star): live counts and particle order exact; per-particle state and quad vertices
+within 1e-5 relative.  What is actually asserted is stricter: every column and every vertex is BIT-EXACT
+(kernels are built with --fmad=false and keep the reference's evaluation order), except in scenarios that
+run Matrix::createRotation per particle on the device (cosf/sinf differ from glibc's by a few ulp), where
+the tolerance is rtol=1e-5, atol=1e-6 and integer columns, counts and order stay exact.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cpu_harness as H
+import golden_io as G
+import scenarios as S
+from tractor3d_b200 import abi, presets
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+@pytest.fixture()
+def gpu():
+    from gpu_adapter import GpuLib
+    lib = GpuLib(rng_mode=abi.RNG_STREAM)
+    yield lib
+    lib.close()
+
+
+@pytest.mark.parametrize("name", G.names())
+def test_gpu_matches_reference_golden(gpu, name):
+    g = G.load(name)
+    sc = S.by_name(name)
+    e = S.new_emitter(gpu, sc)
+    snaps, _ = S.run(e, sc, feed=g["per_step_draws"])
+    assert e.pe.pending_draws() == 0, "the GPU path consumed a different number of draws than the reference"
+    S.compare(snaps, g["snaps"], exact=sc.exact, rtol=RTOL, atol=ATOL, what=name)
+
+
+@pytest.mark.parametrize("factory", S.ALL)
+def test_gpu_matches_oracle_recorded_stream(gpu, factory):
+    sc = factory()
+    O = H.oracle(fresh=True)
+    O.rand_seed(4321)
+    eo = S.new_emitter(O, sc)
+    snaps_o, rec = S.run(eo, sc, record_lib=O)
+    eg = S.new_emitter(gpu, sc)
+    snaps_g, _ = S.run(eg, sc, feed=rec)
+    assert eg.pe.pending_draws() == 0
+    S.compare(snaps_g, snaps_o, exact=sc.exact, rtol=RTOL, atol=ATOL, what=sc.name)
+
+
+@pytest.mark.parametrize("factory", [S.fire, S.explosion, S.burst_extinction, S.capacity_saturation])
+def test_gpu_device_rng_matches_oracle(factory):
+    # T3D_RNG_DEVICE: the spawn kernel evaluates the counter-based generator itself; the oracle restates it.
+    from gpu_adapter import GpuLib
+    sc = factory()
+    lib = GpuLib(rng_mode=abi.RNG_DEVICE, seed=0xC0FFEE)
+    try:
+        O = H.oracle(fresh=True)
+        eo = S.new_emitter(O, sc)
+        O.emitter_set_device_rng(eo.h, 1, 0xC0FFEE)
+        snaps_o, _ = S.run(eo, sc)
+        eg = S.new_emitter(lib, sc)
+        snaps_g, _ = S.run(eg, sc)
+        S.compare(snaps_g, snaps_o, exact=True, what=sc.name + " (device rng)")
+    finally:
+        lib.close()
+
+
+def test_gpu_libc_rand_mode_matches_oracle():
+    # T3D_RNG_LIBC: the library calls rand() itself in the reference's order; replay the same libc stream into the oracle.
+    from gpu_adapter import GpuLib
+    libc = C.CDLL(None)
+    sc = S.fire(frames=60)
+    libc.srand(1234)
+    stream = np.array([libc.rand() for _ in range(60000)], dtype=np.int32)
+    O = H.oracle(fresh=True)
+    O.replay(stream)
+    eo = S.new_emitter(O, sc)
+    snaps_o, _ = S.run(eo, sc)
+    lib = GpuLib(rng_mode=abi.RNG_LIBC)
+    try:
+        libc.srand(1234)
+        eg = S.new_emitter(lib, sc)
+        snaps_g, _ = S.run(eg, sc)
+        S.compare(snaps_g, snaps_o, exact=True, what="libc rand")
+    finally:
+        lib.close()
+
+
+def test_per_particle_rotation_mode_matches_restated_oracle():
+    # T3D_ROT_PER_PARTICLE has no reference behaviour to pin (SB.cpp:339 freezes the matrix): restated oracle, tolerance.
+    from gpu_adapter import GpuLib
+    sc = S.tilted_camera_moving_node()
+    O = H.oracle(fresh=True)
+    O.set_rotation_mode(abi.ROT_PER_PARTICLE)
+    O.rand_seed(77)
+    eo = S.new_emitter(O, sc)
+    snaps_o, rec = S.run(eo, sc, record_lib=O)
+    lib = GpuLib(rng_mode=abi.RNG_STREAM, rot_mode=abi.ROT_PER_PARTICLE)
+    try:
+        eg = S.new_emitter(lib, sc)
+        snaps_g, _ = S.run(eg, sc, feed=rec)
+        S.compare(snaps_g, snaps_o, exact=False, rtol=RTOL, atol=ATOL, what="per-particle rotation")
+        # state does not depend on the draw mode: still bit-exact
+        for a, b in zip(snaps_g, snaps_o):
+            assert np.array_equal(a["state"], b["state"])
+    finally:
+        lib.close()
+
+
+def test_frozen_rotation_latch_is_bit_exact_and_sticky(gpu):
+    params = abi.default_params(particle_count_max=64, rotation_per_particle_speed_min=0.5,
+                                rotation_per_particle_speed_max=2.5, position_var=[3, 3, 3])
+    O = H.oracle(fresh=True)
+    O.rand_seed(11)
+    eo = O.emitter(params)
+    O.rand_record(1)
+    eo.emit_once(32)
+    draws = O.recorded()
+    eg = gpu.emitter(params)
+    eg.feed_draws(draws)
+    eg.emit_once(32)
+    for f in range(3):
+        eo.update(S.DT); eg.update(S.DT)
+        eo.draw(); eg.draw()
+        assert np.array_equal(eg.vertices().view(np.uint32), eo.vertices().view(np.uint32)), f"frame {f}"
+    m_g, latched = gpu.ctx.frozen_rotation()
+    m_o = np.zeros(16, dtype=np.float32)
+    assert O.get_frozen_rotation(m_o.ctypes.data_as(H._P(C.c_float))) == 1 and latched
+    assert np.array_equal(m_g.view(np.uint32), m_o.view(np.uint32))
+
+
+def _big_population(n, seed, energy=(20.0, 400.0), animated=1, looped=1):
+    """Synthetic live population in the column layout (no spawning): for multi-tile update/removal tests."""
+    rng = np.random.default_rng(seed)
+    cols = np.zeros((abi.NUM_COLUMNS, n), dtype=np.uint32)
+    f = cols.view(np.float32)
+    f[0:8] = rng.random((8, n), dtype=np.float32)
+    f[8:12] = f[0:4]
+    f[12:21] = rng.standard_normal((9, n)).astype(np.float32)
+    f[21:24] = 0.0
+    es = rng.integers(int(energy[0]), int(energy[1]) + 1, n).astype(np.int32)
+    cols[abi.COL_ENERGY_START] = es.view(np.uint32)
+    cols[abi.COL_ENERGY] = es.view(np.uint32)
+    f[abi.COL_SIZE_START] = 1.0 + rng.random(n, dtype=np.float32)
+    f[abi.COL_SIZE_END] = 0.5 * rng.random(n, dtype=np.float32)
+    f[abi.COL_SIZE] = f[abi.COL_SIZE_START]
+    f[abi.COL_ROT_PER_PARTICLE_SPEED] = (rng.random(n, dtype=np.float32) - 0.5) * 3
+    f[abi.COL_ROTATION_SPEED] = 0.0
+    f[abi.COL_ANGLE] = rng.random(n, dtype=np.float32)
+    f[abi.COL_TIME_ON_FRAME] = 0.0
+    cols[abi.COL_FRAME] = rng.integers(0, 4, n).astype(np.uint32)
+    return cols
+
+
+@pytest.mark.parametrize("n", [1, 3, 1023, 1024, 1025, 4097, 200_003])
+def test_multi_tile_update_and_removal_order(gpu, n):
+    # One emitter spanning many 1024-particle tiles: the decoupled look-back scan must reproduce the sequential
+    # swap-with-last order exactly, at ragged sizes too.
+    p, sprite = presets.headline_64m(capacity=n + 5)
+    p.energy_min, p.energy_max = 20.0, 400.0
+    O = H.oracle(fresh=True)
+    eo = O.emitter(p); eo.set_sprite_frame_coords(*sprite)
+    eg = gpu.emitter(p); eg.set_sprite_frame_coords(*sprite)
+    cols = _big_population(n, seed=n)
+    eo.set_state(cols); eg.pe.upload_state(cols)
+    for f in range(12):
+        eo.update(S.DT); eg.update(S.DT)
+        assert eg.count() == eo.count(), f"frame {f}"
+        if f % 4 == 3 or eo.count() == 0:
+            assert np.array_equal(eg.state(), eo.state()), f"frame {f}"
+        if eo.count() == 0:
+            break
+    eo.draw(); eg.draw()
+    assert np.array_equal(eg.vertices().view(np.uint32), eo.vertices().view(np.uint32))
+
+
+def test_batch_of_mixed_emitters_one_launch_per_phase():
+    # BASELINE configs[1] in miniature: many independent emitters with mixed fire/smoke/explosion parameter sets,
+    # updated and drawn through the batch calls; every emitter must match its own oracle twin.
+    from gpu_adapter import GpuLib
+    lib = GpuLib(rng_mode=abi.RNG_DEVICE, seed=0)
+    try:
+        O = H.oracle(fresh=True)
+        twins = []
+        for k in range(48):
+            p, sprite = presets.MIXED[k % 3]()
+            p.particle_count_max = 700 + 13 * k
+            p.emission_rate = 200 + 10 * k
+            eg = lib.emitter(p); eg.set_sprite_frame_coords(*sprite)
+            eg.pe.set_rng(abi.RNG_DEVICE, 1000 + k)
+            eo = O.emitter(p); eo.set_sprite_frame_coords(*sprite)
+            O.emitter_set_device_rng(eo.h, 1, 1000 + k)
+            eg.start(); eo.start()
+            twins.append((eg, eo))
+        pes = [t[0].pe for t in twins]
+        launches0 = lib.ctx.launch_count()
+        frames = 40
+        for f in range(frames):
+            lib.ctx.batch_update(pes, S.DT)
+            lib.ctx.batch_draw(pes)
+            for _, eo in twins:
+                eo.update(S.DT); eo.draw()
+        lib.ctx.sync()
+        # spawn + update + draw (+ one latch for the frozen rotation): a handful of launches per frame, not 48 x 3
+        assert lib.ctx.launch_count() - launches0 <= frames * 3 + 2
+        counts = lib.ctx.batch_counts(pes)
+        for k, (eg, eo) in enumerate(twins):
+            assert counts[k] == eo.count(), f"emitter {k}"
+            assert np.array_equal(eg.state(), eo.state()), f"emitter {k}"
+            assert np.array_equal(eg.vertices().view(np.uint32), eo.vertices().view(np.uint32)), f"emitter {k}"
+    finally:
+        lib.close()
+
+
+def test_empty_and_inactive_emitters(gpu):
+    p, sprite = presets.smoke()
+    eg = gpu.emitter(p)
+    assert eg.count() == 0 and not eg.is_active()
+    eg.update(S.DT)                      # inactive: no-op (PE.cpp:715)
+    assert eg.draw() == 0                # PE.cpp:837
+    assert eg.vertices().shape[0] == 0
+    eg.start()
+    assert eg.is_active() and eg.draw() == 1 and eg.vertices().shape[0] == 0   # active but empty (PE.cpp:839)
+    eg.emit_once(0)
+    assert eg.count() == 0
+
+
+def test_errors_are_codes_not_exits(gpu):
+    from tractor3d_b200.emitter import T3DError
+    p, _ = presets.smoke()
+    eg = gpu.emitter(p)
+    bigger = p.copy(); bigger.particle_count_max = p.particle_count_max + 1
+    with pytest.raises(T3DError) as ei:
+        eg.set_params(bigger)
+    assert ei.value.code == abi.ERR_CAPACITY
+    with pytest.raises(T3DError) as ei:
+        eg.set_emission_rate(0)          # reference asserts (PE.cpp:264)
+    assert ei.value.code == abi.ERR_INVALID
+    with pytest.raises(T3DError) as ei:
+        eg.emit_once(10)                 # T3D_RNG_STREAM with nothing fed
+    assert ei.value.code == abi.ERR_RNG_UNDERFLOW
+    assert eg.count() == 0
+
+
+def test_large_population_properties():
+    # Size-independent properties at a size the oracle would take minutes for (16 Mi particles, device RNG):
+    #  * with long lifetimes nothing dies: the count is conserved and energy drops by exactly floor-steps;
+    #  * colour/size are the exact lerp of their endpoints at percent = 1 - e/e0 (recomputed on the host);
+    #  * with short lifetimes the population goes extinct and every intermediate count is non-increasing.
+    from gpu_adapter import GpuLib
+    lib = GpuLib(rng_mode=abi.RNG_DEVICE, seed=5)
+    try:
+        n = 16 * 1024 * 1024
+        p, sprite = presets.headline_64m(capacity=n)
+        eg = lib.emitter(p); eg.set_sprite_frame_coords(*sprite)
+        eg.emit_once(n + 12345)   # clamped on the device
+        assert eg.count() == n
+        for f in range(3):
+            eg.update(S.DT); eg.draw()
+        assert eg.count() == n
+        st = eg.state()
+        f32 = st.view(np.float32)
+        e0 = st[abi.COL_ENERGY_START].view(np.int32).astype(np.float32)
+        e = st[abi.COL_ENERGY].view(np.int32)
+        expect = e0.copy()
+        for f in range(3):
+            expect = np.trunc(expect - np.float32(S.DT)).astype(np.float32)
+        assert np.array_equal(e.astype(np.float32), expect)
+        percent = np.float32(1.0) - e.astype(np.float32) / e0
+        for c in range(4):
+            lerp = f32[abi.COL_COLOR_START + c] + (f32[abi.COL_COLOR_END + c] - f32[abi.COL_COLOR_START + c]) * percent
+            assert np.array_equal(lerp.view(np.uint32), st[abi.COL_COLOR + c])
+        verts = eg.vertices()
+        assert verts.shape == (n, 4, 9)
+        centre = verts[:, :, :3].mean(axis=1)
+        assert np.allclose(centre, f32[abi.COL_POSITION:abi.COL_POSITION + 3].T, rtol=1e-4, atol=1e-4)
+        del verts, st, f32
+        q = p.copy(); q.energy_min, q.energy_max = 30.0, 200.0
+        e2 = lib.emitter(q)
+        e2.emit_once(4 * 1024 * 1024)
+        prev = e2.count()
+        assert prev == 4 * 1024 * 1024
+        for f in range(16):
+            e2.update(S.DT)
+            c = e2.count()
+            assert c <= prev
+            prev = c
+        assert prev == 0
+    finally:
+        lib.close()

@@ -1,0 +1,452 @@
+// t3d_host.cpp -- pure host helpers (see t3d_host.h).  Compiled without FMA contraction so the few float
+// expressions here round exactly like the reference's scalar SSE code.
+//
+// PE.cpp = Tractor3Dlib/src/graphics/ParticleEmitter.cpp, Properties.cpp = src/scene/Properties.cpp,
+// ParticlesSample.cpp = samples/browser/src/ParticlesSample.cpp of the reference.
+#include "t3d_host.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "t3d_internal.h"
+
+static thread_local std::string g_host_error;
+const char* t3d_host_last_error() { return g_host_error.c_str(); }
+static int host_fail(int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_host_error = buf;
+    return code;
+}
+
+static inline float u11(int32_t r) { return (2.0f * ((float)r / 2147483648.0f)) - 1.0f; } // pch.h:151
+
+bool t3d_host_ellipsoid_accept(int32_t rx, int32_t ry, int32_t rz)
+{
+    const float x = u11(rx), y = u11(ry), z = u11(rz);
+    return !(sqrtf(x * x + y * y + z * z) > 1.0f); // Vector3::length() > 1.0f keeps looping
+}
+
+void t3d_host_sprite_rect_coords(uint32_t frame_count, const float* rects, float wr, float hr, float* out)
+{
+    for (uint32_t i = 0; i < frame_count; ++i)
+    {
+        const float* r = rects + 4 * i;
+        float* c = out + 4 * i;
+        c[0] = wr * r[0];
+        c[1] = 1.0f - hr * r[1];
+        c[2] = c[0] + wr * r[2];
+        c[3] = c[1] - hr * r[3];
+    }
+}
+
+extern "C" {
+
+void t3d_emitter_params_default(t3d_emitter_params* p)
+{
+    // PE.h:824-877 defaults; capacity/rate as create(Properties*) falls back to (PE.cpp:133-143).
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->particle_count_max = 100;
+    p->emission_rate = 10;
+    p->size_start_min = p->size_start_max = p->size_end_min = p->size_end_max = 1.0f;
+    p->energy_min = p->energy_max = 1000.0f;
+    for (int k = 0; k < 4; ++k) p->color_end[k] = 1.0f;
+    for (int k = 0; k < 3; ++k) p->velocity_var[k] = 1.0f;
+    p->texture_width = p->texture_height = 64.0f;
+    p->blend_mode = T3D_BLEND_ALPHA;
+}
+
+int32_t t3d_device_rng_draw(uint64_t seed, uint64_t serial, uint32_t j) { return t3d::device_rng_draw(seed, serial, j); }
+
+int t3d_host_rate_cap(double* running_time, float elapsed_time, float* elapsed_ms)
+{
+    // PE.cpp:720-725: PARTICLE_UPDATE_RATE_MAX = 8 ms.
+    *running_time += elapsed_time;
+    if (*running_time < 8) return 0;
+    *elapsed_ms = (float)*running_time;
+    *running_time = 0;
+    return 1;
+}
+
+uint32_t t3d_host_emission_count(float* emit_time, float time_per_emission, float elapsed_ms)
+{
+    // PE.cpp:732-743.  For rates above 1000/s (int)time_per_emission is 0 and emit_time is never reduced.
+    *emit_time += elapsed_ms;
+    const unsigned int emit_count = (unsigned int)(*emit_time / time_per_emission);
+    if (emit_count)
+    {
+        if ((int)time_per_emission > 0) *emit_time = (float)fmod((double)*emit_time, (double)time_per_emission);
+    }
+    return emit_count;
+}
+
+uint32_t t3d_host_sprite_frame_coords(uint32_t frame_count, int width, int height, float tex_w, float tex_h, float* tex_coords)
+{
+    // PE.cpp:550-582: frames walk the sheet left-to-right, top-to-bottom; rects the walk never reaches stay
+    // zero (Rectangle's default), exactly like the reference's `new Rectangle[frameCount]`.
+    if (!frame_count || !width || !height || !tex_coords) return 0;
+    std::vector<float> rects((size_t)frame_count * 4, 0.0f);
+    const unsigned int cols = (unsigned int)(tex_w / (float)width);
+    const unsigned int rows = (unsigned int)(tex_h / (float)height);
+    unsigned int n = 0;
+    for (unsigned int i = 0; i < rows && n != frame_count; ++i)
+    {
+        const int y = (int)i * height;
+        for (unsigned int j = 0; j < cols; ++j)
+        {
+            const int x = (int)j * width;
+            float* r = &rects[4 * ((size_t)i * cols + j)];
+            r[0] = (float)x;
+            r[1] = (float)y;
+            r[2] = (float)width;
+            r[3] = (float)height;
+            if (++n == frame_count) break;
+        }
+    }
+    const float wr = 1.0f / (float)(unsigned int)tex_w, hr = 1.0f / (float)(unsigned int)tex_h; // PE.cpp:246-247
+    t3d_host_sprite_rect_coords(frame_count, rects.data(), wr, hr, tex_coords);
+    return n;
+}
+
+size_t t3d_host_particle_draws(const int32_t* draws, size_t n, int ellipsoid, uint32_t frame_random_offset)
+{
+    // PE.cpp:312-364: 8 colour + 6 scalar draws, the position (3 per rejection-loop pass), 9 for
+    // velocity/acceleration/axis, one more when a random start frame is drawn.
+    size_t pos = 14;
+    if (ellipsoid)
+    {
+        while (true)
+        {
+            if (pos + 3 > n) return 0;
+            const bool ok = t3d_host_ellipsoid_accept(draws[pos], draws[pos + 1], draws[pos + 2]);
+            pos += 3;
+            if (ok) break;
+        }
+    }
+    else
+        pos += 3;
+    pos += 9 + (frame_random_offset > 0 ? 1 : 0);
+    return pos <= n ? pos : 0;
+}
+
+} // extern "C"
+
+// --------------------------------------------------------------------------------------------------
+// `.particle` files: the Properties text format restricted to what ParticleEmitter::create reads
+// (PE.cpp:92-184): nested namespaces `name [id] { ... }` and `key = value` lines, // and /* */ comments.
+// --------------------------------------------------------------------------------------------------
+namespace
+{
+struct Ns
+{
+    std::string name, id;
+    std::vector<std::pair<std::string, std::string>> props;
+    std::vector<std::unique_ptr<Ns>> children;
+    const std::string* find(const std::string& key) const
+    {
+        for (auto& kv : props)
+            if (kv.first == key) return &kv.second;
+        return nullptr;
+    }
+    const Ns* child(const std::string& n) const
+    {
+        for (auto& c : children)
+            if (c->name == n) return c.get();
+        return nullptr;
+    }
+};
+
+std::string trim(const std::string& s)
+{
+    const auto a = s.find_first_not_of(" \t\r\n");
+    if (a == std::string::npos) return "";
+    const auto b = s.find_last_not_of(" \t\r\n");
+    return s.substr(a, b - a + 1);
+}
+
+bool parse_file(const std::string& path, Ns* root, std::string* err)
+{
+    std::ifstream f(path);
+    if (!f)
+    {
+        *err = "cannot open '" + path + "'";
+        return false;
+    }
+    std::vector<Ns*> stack{ root };
+    Ns* awaiting_brace = nullptr; // a namespace header was read; its '{' is on a later line
+    bool in_comment = false;
+    std::string raw;
+    while (std::getline(f, raw))
+    {
+        std::string line = trim(raw);
+        if (line.empty()) continue;
+        if (in_comment)
+        {
+            if (line.size() >= 2 && (line.substr(0, 2) == "*/" || line.substr(line.size() - 2) == "*/")) in_comment = false;
+            continue;
+        }
+        if (line.size() >= 2 && line.substr(0, 2) == "/*")
+        {
+            if (!(line.size() >= 4 && line.substr(line.size() - 2) == "*/")) in_comment = true;
+            continue;
+        }
+        if (line.size() >= 2 && line.substr(0, 2) == "//") continue;
+        const auto eq = line.find('=');
+        if (eq != std::string::npos)
+        {
+            stack.back()->props.emplace_back(trim(line.substr(0, eq)), trim(line.substr(eq + 1)));
+            continue;
+        }
+        if (line[0] == '{')
+        {
+            if (!awaiting_brace)
+            {
+                *err = "unexpected '{'";
+                return false;
+            }
+            stack.push_back(awaiting_brace);
+            awaiting_brace = nullptr;
+            continue;
+        }
+        if (line[0] == '}')
+        {
+            if (stack.size() <= 1)
+            {
+                *err = "unbalanced '}'";
+                return false;
+            }
+            stack.pop_back();
+            continue;
+        }
+        // namespace header: name [id] [: parent] [{] [}]
+        const bool open = line.find('{') != std::string::npos, close = line.find('}') != std::string::npos;
+        std::string head = line.substr(0, line.find_first_of("{:"));
+        std::istringstream hs(head);
+        auto ns = std::make_unique<Ns>();
+        hs >> ns->name >> ns->id;
+        Ns* np = ns.get();
+        stack.back()->children.push_back(std::move(ns));
+        if (open && !close)
+            stack.push_back(np);
+        else if (!open)
+            awaiting_brace = np;
+    }
+    return true;
+}
+
+// Typed getters with Properties.cpp's conversions: getBool :940-944, getInt :947-962, getFloat :965-978,
+// getLong :981-994, getVector3/4 via sscanf :1214-1251.
+bool get_bool(const Ns* n, const char* k)
+{
+    const std::string* v = n->find(k);
+    return v && !v->empty() && *v == "true";
+}
+int get_int(const Ns* n, const char* k)
+{
+    const std::string* v = n->find(k);
+    if (!v || v->empty()) return 0;
+    try { return std::stoi(*v); } catch (...) { return 0; }
+}
+long get_long(const Ns* n, const char* k)
+{
+    const std::string* v = n->find(k);
+    if (!v) return 0;
+    try { return std::stol(*v); } catch (...) { return 0; }
+}
+float get_float(const Ns* n, const char* k)
+{
+    const std::string* v = n->find(k);
+    if (!v) return 0.0f;
+    try { return std::stof(*v); } catch (...) { return 0.0f; }
+}
+void get_vec(const Ns* n, const char* k, float* out, int dim)
+{
+    // The caller's vector keeps its default (zero) when the key is missing; a malformed value zeroes it.
+    for (int i = 0; i < dim; ++i) out[i] = 0.0f;
+    const std::string* v = n->find(k);
+    if (!v || v->empty()) return;
+    float t[4] = { 0, 0, 0, 0 };
+    const int got = dim == 3 ? sscanf(v->c_str(), "%f,%f,%f", &t[0], &t[1], &t[2])
+                             : sscanf(v->c_str(), "%f,%f,%f,%f", &t[0], &t[1], &t[2], &t[3]);
+    if (got == dim)
+        for (int i = 0; i < dim; ++i) out[i] = t[i];
+}
+int blend_from_string(const std::string& s)
+{
+    // PE.cpp:682-710
+    if (s == "BLEND_NONE" || s == "NONE" || s == "BLEND_OPAQUE" || s == "OPAQUE") return T3D_BLEND_NONE;
+    if (s == "BLEND_ALPHA" || s == "ALPHA" || s == "BLEND_TRANSPARENT" || s == "TRANSPARENT") return T3D_BLEND_ALPHA;
+    if (s == "BLEND_ADDITIVE" || s == "ADDITIVE") return T3D_BLEND_ADDITIVE;
+    if (s == "BLEND_MULTIPLIED" || s == "MULTIPLIED") return T3D_BLEND_MULTIPLIED;
+    return T3D_BLEND_ALPHA;
+}
+bool file_exists(const std::string& p)
+{
+    FILE* f = fopen(p.c_str(), "rb");
+    if (f) fclose(f);
+    return f != nullptr;
+}
+bool png_size(const std::string& p, unsigned* w, unsigned* h)
+{
+    FILE* f = fopen(p.c_str(), "rb");
+    if (!f) return false;
+    unsigned char hdr[24];
+    const size_t got = fread(hdr, 1, sizeof(hdr), f);
+    fclose(f);
+    if (got != sizeof(hdr) || memcmp(hdr + 1, "PNG", 3) != 0) return false;
+    *w = (hdr[16] << 24) | (hdr[17] << 16) | (hdr[18] << 8) | hdr[19];
+    *h = (hdr[20] << 24) | (hdr[21] << 16) | (hdr[22] << 8) | hdr[23];
+    return *w && *h;
+}
+} // namespace
+
+extern "C" int t3d_particle_file_parse(const char* url, t3d_emitter_params* params, uint32_t* frame_count, int* sprite_width,
+                                       int* sprite_height, char* texture_path, size_t texture_path_len)
+{
+    if (!url || !params) return host_fail(T3D_ERR_INVALID, "t3d_particle_file_parse: null argument");
+    Ns root;
+    std::string err;
+    if (!parse_file(url, &root, &err)) return host_fail(T3D_ERR_IO, "Failed to create particle emitter from file: %s", err.c_str());
+    // PE.cpp:85-86, 94: the (first) top-level namespace must be `particle`.
+    const Ns* particle = root.children.empty() ? nullptr : root.children.front().get();
+    if (!particle || particle->name != "particle")
+        return host_fail(T3D_ERR_IO, "Properties object must be non-null and have namespace equal to 'particle'.");
+    // PE.cpp:101-106: the first child namespace must be `sprite`.
+    const Ns* sprite = particle->children.empty() ? nullptr : particle->children.front().get();
+    if (!sprite || sprite->name != "sprite")
+        return host_fail(T3D_ERR_IO, "Failed to load particle emitter: required namespace 'sprite' is missing.");
+    // PE.cpp:110-115 + Properties::getPath (Properties.cpp:1077-1108): as given, else relative to the file.
+    const std::string* path = sprite->find("path");
+    if (!path || path->empty())
+        return host_fail(T3D_ERR_IO, "Failed to load particle emitter: required image file path ('path') is missing.");
+    std::string tex = *path;
+    if (!file_exists(tex))
+    {
+        std::string dir(url);
+        const auto slash = dir.find_last_of('/');
+        dir = slash == std::string::npos ? "" : dir.substr(0, slash + 1);
+        if (file_exists(dir + tex))
+            tex = dir + tex;
+        else
+            return host_fail(T3D_ERR_IO, "Failed to load particle emitter: required image file path ('path') is missing.");
+    }
+    unsigned tw = 0, th = 0;
+    if (!png_size(tex, &tw, &th)) return host_fail(T3D_ERR_IO, "Failed to create texture for particle emitter.");
+
+    t3d_emitter_params p;
+    t3d_emitter_params_default(&p);
+    const std::string* bm = sprite->find("blendMode");
+    if (!bm || bm->empty()) bm = sprite->find("blending"); // PE.cpp:117-122
+    p.blend_mode = blend_from_string(bm ? *bm : std::string());
+    const int sw = get_int(sprite, "width"), sh = get_int(sprite, "height");
+    p.sprite_animated = get_bool(sprite, "animated");
+    p.sprite_looped = get_bool(sprite, "looped");
+    const int fc = get_int(sprite, "frameCount");
+    p.sprite_frame_random_offset = (uint32_t)std::min(get_int(sprite, "frameRandomOffset"), fc); // PE.cpp:128
+    p.sprite_frame_duration = (long)get_float(sprite, "frameDuration"); // float -> setSpriteFrameDuration(long), PE.cpp:129, 206
+    p.particle_count_max = (unsigned int)get_int(particle, "particleCountMax");
+    if (p.particle_count_max == 0) p.particle_count_max = 100; // PE.cpp:133-137
+    p.emission_rate = (unsigned int)get_int(particle, "emissionRate");
+    if (p.emission_rate == 0) p.emission_rate = 10; // PE.cpp:139-143
+    p.ellipsoid = get_bool(particle, "ellipsoid");
+    p.size_start_min = get_float(particle, "sizeStartMin");
+    p.size_start_max = get_float(particle, "sizeStartMax");
+    p.size_end_min = get_float(particle, "sizeEndMin");
+    p.size_end_max = get_float(particle, "sizeEndMax");
+    p.energy_min = (float)get_long(particle, "energyMin"); // long -> setEnergy(long, long) -> float members, PE.cpp:150-151, 381-385
+    p.energy_max = (float)get_long(particle, "energyMax");
+    get_vec(particle, "colorStart", p.color_start, 4);
+    get_vec(particle, "colorStartVar", p.color_start_var, 4);
+    get_vec(particle, "colorEnd", p.color_end, 4);
+    get_vec(particle, "colorEndVar", p.color_end_var, 4);
+    get_vec(particle, "position", p.position, 3);
+    get_vec(particle, "positionVar", p.position_var, 3);
+    get_vec(particle, "velocity", p.velocity, 3);
+    get_vec(particle, "velocityVar", p.velocity_var, 3);
+    get_vec(particle, "acceleration", p.acceleration, 3);
+    get_vec(particle, "accelerationVar", p.acceleration_var, 3);
+    p.rotation_per_particle_speed_min = get_float(particle, "rotationPerParticleSpeedMin");
+    p.rotation_per_particle_speed_max = get_float(particle, "rotationPerParticleSpeedMax");
+    p.rotation_speed_min = get_float(particle, "rotationSpeedMin");
+    p.rotation_speed_max = get_float(particle, "rotationSpeedMax");
+    get_vec(particle, "rotationAxis", p.rotation_axis, 3);
+    get_vec(particle, "rotationAxisVar", p.rotation_axis_var, 3);
+    p.orbit_position = get_bool(particle, "orbitPosition");
+    p.orbit_velocity = get_bool(particle, "orbitVelocity");
+    p.orbit_acceleration = get_bool(particle, "orbitAcceleration");
+    p.texture_width = (float)tw;
+    p.texture_height = (float)th;
+    *params = p;
+    if (frame_count) *frame_count = (uint32_t)fc;
+    if (sprite_width) *sprite_width = sw;
+    if (sprite_height) *sprite_height = sh;
+    if (texture_path && texture_path_len) snprintf(texture_path, texture_path_len, "%s", tex.c_str());
+    return T3D_OK;
+}
+
+extern "C" int t3d_particle_file_save(const char* url, const char* name, const t3d_emitter_params* p, uint32_t frame_count,
+                                      int sprite_width, int sprite_height, const char* texture_path)
+{
+    // ParticlesSample.cpp:340-424 (saveFile): same keys, same order; like the sample it omits the
+    // rotationSpeed* / rotationAxis* keys.  The trailing `editor` block of the sample is UI state and is not written.
+    if (!url || !p) return host_fail(T3D_ERR_INVALID, "t3d_particle_file_save: null argument");
+    static const char* kBlend[] = { "NONE", "ALPHA", "ADDITIVE", "MULTIPLIED" };
+    auto B = [](int v) { return v ? "true" : "false"; };
+    std::ostringstream s; // default ostream float formatting, as the sample
+    auto V3 = [&](const float* v) { std::ostringstream t; t << v[0] << ", " << v[1] << ", " << v[2]; return t.str(); };
+    auto V4 = [&](const float* v) { std::ostringstream t; t << v[0] << ", " << v[1] << ", " << v[2] << ", " << v[3]; return t.str(); };
+    s << "particle " << (name ? name : "") << "\n{\n    sprite\n    {\n"
+      << "        path = " << (texture_path ? texture_path : "") << "\n"
+      << "        width = " << sprite_width << "\n"
+      << "        height = " << sprite_height << "\n"
+      << "        blendMode = " << kBlend[(p->blend_mode >= 0 && p->blend_mode < 4) ? p->blend_mode : 1] << "\n"
+      << "        animated = " << B(p->sprite_animated) << "\n"
+      << "        looped = " << B(p->sprite_looped) << "\n"
+      << "        frameCount = " << frame_count << "\n"
+      << "        frameRandomOffset = " << (int)p->sprite_frame_random_offset << "\n"
+      << "        frameDuration = " << (long)p->sprite_frame_duration << "\n"
+      << "    }\n\n"
+      << "    particleCountMax = " << p->particle_count_max << "\n"
+      << "    emissionRate = " << p->emission_rate << "\n"
+      << "    ellipsoid = " << B(p->ellipsoid) << "\n"
+      << "    orbitPosition = " << B(p->orbit_position) << "\n"
+      << "    orbitVelocity = " << B(p->orbit_velocity) << "\n"
+      << "    orbitAcceleration = " << B(p->orbit_acceleration) << "\n"
+      << "    sizeStartMin = " << p->size_start_min << "\n"
+      << "    sizeStartMax = " << p->size_start_max << "\n"
+      << "    sizeEndMin = " << p->size_end_min << "\n"
+      << "    sizeEndMax = " << p->size_end_max << "\n"
+      << "    energyMin = " << (long)p->energy_min << "\n" // getEnergyMin() returns long, PE.h:427
+      << "    energyMax = " << (long)p->energy_max << "\n"
+      << "    colorStart = " << V4(p->color_start) << "\n"
+      << "    colorStartVar = " << V4(p->color_start_var) << "\n"
+      << "    colorEnd = " << V4(p->color_end) << "\n"
+      << "    colorEndVar = " << V4(p->color_end_var) << "\n"
+      << "    position = " << V3(p->position) << "\n"
+      << "    positionVar = " << V3(p->position_var) << "\n"
+      << "    velocity = " << V3(p->velocity) << "\n"
+      << "    velocityVar = " << V3(p->velocity_var) << "\n"
+      << "    acceleration = " << V3(p->acceleration) << "\n"
+      << "    accelerationVar = " << V3(p->acceleration_var) << "\n"
+      << "    rotationPerParticleSpeedMin = " << p->rotation_per_particle_speed_min << "\n"
+      << "    rotationPerParticleSpeedMax = " << p->rotation_per_particle_speed_max << "\n"
+      << "}\n";
+    std::ofstream f(url);
+    if (!f) return host_fail(T3D_ERR_IO, "cannot write '%s'", url);
+    f << s.str();
+    return f.good() ? T3D_OK : host_fail(T3D_ERR_IO, "write to '%s' failed", url);
+}

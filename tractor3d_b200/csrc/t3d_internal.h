@@ -1,0 +1,148 @@
+// t3d_internal.h -- device-visible records shared by the kernels (t3d_kernels.cu) and the host runtime
+// (t3d_runtime.cu).  Nothing here is part of the ABI.
+#pragma once
+
+#include <cstdint>
+
+#include "../../include/t3d_particles.h"
+
+namespace t3d
+{
+
+// Particles per tile of the update kernel: 256 threads x 4 consecutive particles, so every column is
+// read and written with 128-bit accesses.
+constexpr int kUpdateThreads = 256;
+constexpr int kUpdateVec = 4;
+constexpr int kUpdateTile = kUpdateThreads * kUpdateVec;
+// Spawn and draw: one particle per thread.
+constexpr int kSpawnThreads = 256;
+constexpr int kDrawThreads = 256;
+constexpr int kMaxSmemFrames = 256; // sprite uv tables up to this many frames are staged in shared memory
+
+// Segment alignment inside a slab, in particles (128 B per column).
+constexpr uint32_t kSegmentAlign = 32;
+
+// Live count and spawn serial of one emitter.  Two copies: a kernel reads cnt[parity] and writes
+// cnt[parity ^ 1], so no CTA of a launch can observe the value another CTA of the same launch writes.
+struct EmitterCounts
+{
+    uint32_t count;
+    uint32_t drawn; // cnt[0].drawn: quads written by the last draw of this emitter
+    uint64_t serial; // particles ever spawned (key of the device generator)
+};
+
+enum : uint32_t
+{
+    kFlagAnimated = 1u,   // _spriteAnimated
+    kFlagLooped = 2u,     // _spriteLooped
+    kFlagMayRotate = 4u,  // some live particle may have rotationSpeed != 0: axis/rotSpeed columns are read
+    kFlagMaySpin = 8u,    // some live particle may have angle != 0 (used by the frozen-rotation latch)
+};
+
+// Spawn-time configuration: the float members of t3d_emitter_params the spawn kernel needs.
+struct SpawnParams
+{
+    float color_start[4], color_start_var[4], color_end[4], color_end_var[4];
+    float position[3], position_var[3], velocity[3], velocity_var[3], acceleration[3], acceleration_var[3];
+    float rotation_axis[3], rotation_axis_var[3];
+    float size_start_min, size_start_max, size_end_min, size_end_max;
+    float energy_min, energy_max;
+    float spin_min, spin_max;         // rotationPerParticleSpeed
+    float rot_speed_min, rot_speed_max;
+    uint32_t ellipsoid, orbit_position, orbit_velocity, orbit_acceleration;
+    uint32_t frame_random_offset;
+    uint32_t pad;
+    uint64_t rng_seed;
+};
+
+// Host-written part of the per-emitter device record.
+struct EmitterConst
+{
+    uint32_t* cols;   // column 0 of this emitter's segment; column c starts at cols + c * stride
+    float* vtx;       // vertex stream of this emitter: 36 floats per quad
+    const float* uv;  // frame_count * 4 floats (u1, v1, u2, v2)
+    uint32_t stride;  // words between columns (slab capacity)
+    uint32_t capacity;
+    uint32_t flags;
+    uint32_t frame_count;
+    float percent_per_frame;
+    float frame_duration_secs;
+    SpawnParams sp;
+};
+
+struct EmitterDev
+{
+    EmitterCounts cnt[2]; // device-owned
+    EmitterConst c;       // host-owned, re-uploaded when dirty
+};
+
+// One entry per emitter taking part in a launch.  tile_begin is the first global tile of the emitter in
+// this launch; entries are sorted by it and a CTA finds its emitter by binary search.
+struct UpdateItem
+{
+    EmitterDev* dev;
+    float elapsed_ms;
+    uint32_t parity; // which cnt[] copy is current on entry
+    uint32_t tile_begin;
+    uint32_t pad;
+};
+
+struct SpawnItem
+{
+    EmitterDev* dev;
+    const int32_t* draws;     // recorded draws for this emit (nullptr: device generator)
+    const uint32_t* offsets;  // per-particle start offset into draws (nullptr: constant stride)
+    uint32_t draw_stride;     // draws per particle when offsets == nullptr
+    uint32_t request;         // particles asked for (clamped to free capacity on the device)
+    uint32_t parity;
+    uint32_t tile_begin;
+    float world[16];          // node world matrix (PE.cpp:299)
+};
+
+struct DrawItem
+{
+    EmitterDev* dev;
+    uint32_t parity;
+    uint32_t tile_begin;
+    float right[3];
+    float up[3];
+};
+
+// Process-wide billboard rotation of the reference (SB.cpp:339), kept on the device.
+struct FrozenRotation
+{
+    float m[16];
+    int latched;
+    int pad[3];
+};
+
+// ---- launch wrappers (t3d_kernels.cu) ----
+void launch_spawn(void* stream, const SpawnItem* items, uint32_t n_items, uint32_t total_tiles);
+void launch_update(void* stream, const UpdateItem* items, uint32_t n_items, uint32_t total_tiles,
+                   unsigned long long* tile_status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch);
+void launch_draw(void* stream, const DrawItem* items, uint32_t n_items, uint32_t total_tiles, int rot_mode,
+                 const FrozenRotation* frozen);
+void launch_latch(void* stream, const DrawItem* items, uint32_t n_items, FrozenRotation* frozen);
+struct CountQuery
+{
+    const EmitterDev* dev;
+    uint32_t parity;
+    uint32_t pad;
+};
+// out[2*i] = live count, out[2*i+1] = quads written by the last draw, for each query.
+void launch_gather_counts(void* stream, const CountQuery* q, uint32_t n, uint32_t* out);
+
+// The counter-based generator of T3D_RNG_DEVICE (host + device).
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int32_t device_rng_draw(uint64_t seed, uint64_t serial, uint32_t j)
+{
+    uint64_t z = seed + serial * 0xD1342543DE82EF95ULL + ((uint64_t)j + 1ULL) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return (int32_t)(z >> 33);
+}
+
+} // namespace t3d

@@ -1,0 +1,823 @@
+// t3d_kernels.cu -- the sm_100a kernels of the particle path.
+//
+//   k_spawn   replaces the loop of ParticleEmitter::emitOnce          (PE.cpp:308-368 + generators :611-679)
+//   k_update  replaces the per-particle loop of ParticleEmitter::update (PE.cpp:750-831), including the
+//             swap-with-last removal, reproduced exactly by a prefix scan (see "removal" below)
+//   k_draw    replaces ParticleEmitter::draw's loop + SpriteBatch::draw   (PE.cpp:866-882, SB.cpp:292-363)
+//   k_latch   finds the first rotated quad for the reference's frozen billboard rotation (SB.cpp:339)
+//
+// PE.cpp = Tractor3Dlib/src/graphics/ParticleEmitter.cpp, SB.cpp = src/graphics/SpriteBatch.cpp,
+// Matrix.cpp = src/math/Matrix.cpp, MathUtil.h = include/math/MathUtil.h of the reference.
+//
+// Numerics: compiled with --fmad=false (and the default -prec-div=true -prec-sqrt=true), and every
+// expression keeps the reference's evaluation order, so all results are bit-identical to the reference's
+// SSE scalar code except where it calls cosf/sinf (Matrix.cpp:375-376), which differ by a few ulp.
+//
+// All three hot kernels are HBM-bound streaming kernels (no reuse, ~0.3 flop/B): no tensor cores, the
+// design rules are coalescing, 128-bit accesses and enough bytes in flight per SM.
+#include <cuda_runtime.h>
+
+#include "t3d_internal.h"
+
+namespace t3d
+{
+
+// --------------------------------------------------------------------------------------------------
+// helpers
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float u01(int32_t r)
+{
+    // pch.h:152: (float)rand()/RAND_MAX with RAND_MAX = 2^31-1 converted to float (= 2^31): exactly r * 2^-31.
+    return (float)r / 2147483648.0f;
+}
+__device__ __forceinline__ float u11(int32_t r) { return (2.0f * u01(r)) - 1.0f; } // pch.h:151
+
+// MathUtil.h:195-200, left-to-right sum of four products.
+__device__ __forceinline__ void transform4(const float* __restrict__ m, float x, float y, float z, float w, float& ox,
+                                           float& oy, float& oz)
+{
+    ox = x * m[0] + y * m[4] + z * m[8] + w * m[12];
+    oy = x * m[1] + y * m[5] + z * m[9] + w * m[13];
+    oz = x * m[2] + y * m[6] + z * m[10] + w * m[14];
+}
+
+// Matrix.cpp:348-406.  Only the 3x3 part is produced (m[12..14] are 0 and are added as such by callers).
+struct Rot3
+{
+    float m0, m1, m2, m4, m5, m6, m8, m9, m10;
+};
+__device__ __forceinline__ Rot3 create_rotation(float x, float y, float z, float angle)
+{
+    float n = x * x + y * y + z * z;
+    if (n != 1.0f)
+    {
+        n = sqrtf(n);
+        if (n > 0.000001f)
+        {
+            n = 1.0f / n;
+            x *= n;
+            y *= n;
+            z *= n;
+        }
+    }
+    float s, c;
+    sincosf(angle, &s, &c);
+    float t = 1.0f - c;
+    float tx = t * x, ty = t * y, tz = t * z;
+    float txy = tx * y, txz = tx * z, tyz = ty * z;
+    float sx = s * x, sy = s * y, sz = s * z;
+    Rot3 r;
+    r.m0 = c + tx * x;
+    r.m1 = txy + sz;
+    r.m2 = txz - sy;
+    r.m4 = txy - sz;
+    r.m5 = c + ty * y;
+    r.m6 = tyz + sx;
+    r.m8 = txz + sy;
+    r.m9 = tyz - sx;
+    r.m10 = c + tz * z;
+    return r;
+}
+// transformVector4 with a Rot3 (m[12..14] = 0): keeps the "+ w*0" term so signed zeros match.
+__device__ __forceinline__ void rot_apply(const Rot3& r, float w, float& x, float& y, float& z)
+{
+    float ox = x * r.m0 + y * r.m4 + z * r.m8 + w * 0.0f;
+    float oy = x * r.m1 + y * r.m5 + z * r.m9 + w * 0.0f;
+    float oz = x * r.m2 + y * r.m6 + z * r.m10 + w * 0.0f;
+    x = ox;
+    y = oy;
+    z = oz;
+}
+
+template <class Item>
+__device__ __forceinline__ uint32_t find_item(const Item* __restrict__ items, uint32_t n_items, uint32_t tile)
+{
+    uint32_t lo = 0, hi = n_items;
+    while (hi - lo > 1)
+    {
+        uint32_t mid = (lo + hi) >> 1;
+        if (items[mid].tile_begin <= tile)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// --------------------------------------------------------------------------------------------------
+// spawn
+// --------------------------------------------------------------------------------------------------
+struct DrawSource
+{
+    const int32_t* p; // recorded stream positioned at this particle's first draw, or nullptr
+    uint64_t seed, serial;
+    uint32_t j;
+    __device__ __forceinline__ int32_t next()
+    {
+        int32_t r = p ? p[j] : device_rng_draw(seed, serial, j);
+        ++j;
+        return r;
+    }
+};
+
+__global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __restrict__ items, uint32_t n_items)
+{
+    const uint32_t tile = blockIdx.x;
+    const SpawnItem& it = items[find_item(items, n_items, tile)];
+    EmitterDev* d = it.dev;
+    const uint32_t parity = it.parity;
+    const uint32_t count0 = d->cnt[parity].count;
+    const uint64_t serial0 = d->cnt[parity].serial;
+    const uint32_t cap = d->c.capacity;
+    // PE.cpp:293-296: never go over particleCountMax.
+    const uint32_t room = cap - count0;
+    const uint32_t n = it.request < room ? it.request : room;
+    const uint32_t i = (tile - it.tile_begin) * kSpawnThreads + threadIdx.x;
+    if (i == 0)
+    {
+        d->cnt[parity ^ 1].count = count0 + n;
+        d->cnt[parity ^ 1].serial = serial0 + n;
+    }
+    if (i >= n) return;
+
+    const SpawnParams& P = d->c.sp;
+    DrawSource src;
+    src.p = it.draws ? it.draws + (it.offsets ? it.offsets[i] : i * it.draw_stride) : nullptr;
+    src.seed = P.rng_seed;
+    src.serial = serial0 + i;
+    src.j = 0;
+
+    // PE.cpp:312-313 -> :669-679: x, y, z, w, one draw each.
+    float cs[4], ce[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) cs[k] = P.color_start[k] + P.color_start_var[k] * u11(src.next());
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ce[k] = P.color_end[k] + P.color_end_var[k] * u11(src.next());
+    // PE.cpp:316: float overload (the bounds are float members), truncated into the integer field.
+    const int energy = __float2int_rz(P.energy_min + (P.energy_max - P.energy_min) * u01(src.next()));
+    const float size_start = P.size_start_min + (P.size_start_max - P.size_start_min) * u01(src.next()); // :317
+    const float size_end = P.size_end_min + (P.size_end_max - P.size_end_min) * u01(src.next());         // :318
+    const float spin = P.spin_min + (P.spin_max - P.spin_min) * u01(src.next());                          // :319-320
+    const float angle = 0.0f + (spin - 0.0f) * u01(src.next());                                           // :321
+    const float rot_speed = P.rot_speed_min + (P.rot_speed_max - P.rot_speed_min) * u01(src.next());      // :322
+
+    float pos[3], vel[3], acc[3], axis[3];
+    if (P.ellipsoid)
+    {
+        // PE.cpp:629-650: rejection-sample the unit ball, scale, translate.
+        float x, y, z;
+        do
+        {
+            x = u11(src.next());
+            y = u11(src.next());
+            z = u11(src.next());
+        } while (sqrtf(x * x + y * y + z * z) > 1.0f);
+        pos[0] = x * P.position_var[0];
+        pos[1] = y * P.position_var[1];
+        pos[2] = z * P.position_var[2];
+        pos[0] += P.position[0];
+        pos[1] += P.position[1];
+        pos[2] += P.position[2];
+    }
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) pos[k] = P.position[k] + P.position_var[k] * u11(src.next()); // :617-626
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) vel[k] = P.velocity[k] + P.velocity_var[k] * u11(src.next());
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc[k] = P.acceleration[k] + P.acceleration_var[k] * u11(src.next());
+#pragma unroll
+    for (int k = 0; k < 3; ++k) axis[k] = P.rotation_axis[k] + P.rotation_axis_var[k] * u11(src.next());
+
+    // PE.cpp:298-305, 332-351: orbiting properties are rotated by the node's world matrix with its translation removed.
+    float w[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w[k] = it.world[k];
+    const float tx = w[12], ty = w[13], tz = w[14];
+    w[12] = 0.0f;
+    w[13] = 0.0f;
+    w[14] = 0.0f;
+    if (P.orbit_position) transform4(w, pos[0], pos[1], pos[2], 1.0f, pos[0], pos[1], pos[2]);
+    if (P.orbit_velocity) transform4(w, vel[0], vel[1], vel[2], 1.0f, vel[0], vel[1], vel[2]);
+    if (P.orbit_acceleration) transform4(w, acc[0], acc[1], acc[2], 1.0f, acc[0], acc[1], acc[2]);
+    if (rot_speed != 0.0f && !(axis[0] == 0.0f && axis[1] == 0.0f && axis[2] == 0.0f))
+        transform4(w, axis[0], axis[1], axis[2], 1.0f, axis[0], axis[1], axis[2]);
+    pos[0] += tx; // :354
+    pos[1] += ty;
+    pos[2] += tz;
+
+    uint32_t frame = 0; // :357-364
+    if (P.frame_random_offset > 0) frame = (uint32_t)src.next() % P.frame_random_offset;
+
+    uint32_t* cols = d->c.cols;
+    const size_t stride = d->c.stride;
+    const size_t slot = count0 + i;
+    auto F = [&](int c, float v) { cols[(size_t)c * stride + slot] = __float_as_uint(v); };
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        F(T3D_COL_COLOR_START + k, cs[k]);
+        F(T3D_COL_COLOR_END + k, ce[k]);
+        F(T3D_COL_COLOR + k, cs[k]); // :314
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+        F(T3D_COL_POSITION + k, pos[k]);
+        F(T3D_COL_VELOCITY + k, vel[k]);
+        F(T3D_COL_ACCELERATION + k, acc[k]);
+        F(T3D_COL_ROTATION_AXIS + k, axis[k]);
+    }
+    cols[(size_t)T3D_COL_ENERGY_START * stride + slot] = (uint32_t)energy;
+    cols[(size_t)T3D_COL_ENERGY * stride + slot] = (uint32_t)energy;
+    F(T3D_COL_SIZE_START, size_start);
+    F(T3D_COL_SIZE_END, size_end);
+    F(T3D_COL_SIZE, size_start);
+    F(T3D_COL_ROT_PER_PARTICLE_SPEED, spin);
+    F(T3D_COL_ROTATION_SPEED, rot_speed);
+    F(T3D_COL_ANGLE, angle);
+    F(T3D_COL_TIME_ON_FRAME, 0.0f); // :365
+    cols[(size_t)T3D_COL_FRAME * stride + slot] = frame;
+}
+
+// --------------------------------------------------------------------------------------------------
+// update + removal
+//
+// removal.  The reference walks i = 0.. and, when particle i is dead, copies the LAST live particle into
+// slot i, shrinks the count and moves on WITHOUT examining the particle it just moved (PE.cpp:821-830 and
+// the loop increment at :750).  With N = count on entry, dead(k) evaluated on the ORIGINAL particle k and
+// D(k) = number of dead originals with index < k:
+//     original k is examined        <=>  k + D(k) < N
+//     examined and alive            ->   updated in place
+//     examined and dead             ->   slot k receives the untouched original N-1-D(k) (nothing if that is k)
+//     new count                     =    N - D(K), K = number of examined originals
+// Sources (>= new count, never examined, never written) and destinations (< K) are disjoint, so the fill is
+// race-free in place.  D(k) is one exclusive scan: within a tile by warp shuffles, across the tiles of an
+// emitter by decoupled look-back over per-tile status words (tile ids are handed out by an atomic ticket,
+// so every predecessor of a running tile is itself running or finished).
+// --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// status word: [63:34] launch epoch, [33:32] 1 = tile aggregate, 2 = inclusive prefix, [31:0] dead count
+constexpr unsigned long long kStatusAggregate = 1ull << 32;
+constexpr unsigned long long kStatusPrefix = 2ull << 32;
+
+__device__ __forceinline__ float4 ldf4(const uint32_t* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ int4 ldi4(const uint32_t* p) { return *reinterpret_cast<const int4*>(p); }
+__device__ __forceinline__ void stf4(uint32_t* p, const float* v)
+{
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void unpack(const float4& v, float* a)
+{
+    a[0] = v.x;
+    a[1] = v.y;
+    a[2] = v.z;
+    a[3] = v.w;
+}
+__device__ __forceinline__ void unpack(const int4& v, int* a)
+{
+    a[0] = v.x;
+    a[1] = v.y;
+    a[2] = v.z;
+    a[3] = v.w;
+}
+
+__global__ void __launch_bounds__(kUpdateThreads)
+    k_update(const UpdateItem* __restrict__ items, uint32_t n_items, uint32_t total_tiles,
+             unsigned long long* __restrict__ tile_status, uint32_t* __restrict__ ticket, uint32_t ticket_base,
+             uint32_t epoch)
+{
+    constexpr int V = kUpdateVec;
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp[kUpdateThreads / 32];
+    __shared__ uint32_t s_excl;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= total_tiles) return;
+
+    const UpdateItem& it = items[find_item(items, n_items, tile)];
+    EmitterDev* d = it.dev;
+    const uint32_t parity = it.parity;
+    const uint32_t N = d->cnt[parity].count;
+    const uint32_t jt = tile - it.tile_begin; // tile index inside the emitter
+    const uint32_t first = jt * kUpdateTile;
+    if (first >= N)
+    {
+        if (jt == 0 && tid == 0)
+        {
+            d->cnt[parity ^ 1].count = 0;
+            d->cnt[parity ^ 1].serial = d->cnt[parity].serial;
+        }
+        return;
+    }
+
+    const float elapsed_ms = it.elapsed_ms;
+    const float secs = elapsed_ms * 0.001f; // PE.cpp:727
+    const uint32_t flags = d->c.flags;
+    const bool animated = (flags & kFlagAnimated) != 0;
+    const bool looped = (flags & kFlagLooped) != 0;
+    const bool may_rotate = (flags & kFlagMayRotate) != 0;
+    uint32_t* const cols = d->c.cols;
+    const size_t stride = d->c.stride;
+    const uint32_t k0 = first + tid * V;
+    const bool active = k0 < N;
+    auto col = [&](int c) -> uint32_t* { return cols + (size_t)c * stride + k0; };
+
+    // ---- loads: everything this thread's 4 particles need, issued before any dependent work ----
+    int en[V], est[V];
+    float px[V], py[V], pz[V], vx[V], vy[V], vz[V], ax[V], ay[V], az[V];
+    float spin[V], ang[V], ss[V], se[V];
+    float cs[4][V], ce[4][V];
+    float tf[V];
+    int fr[V];
+    float rx[V], ry[V], rz[V], rs[V];
+    if (active)
+    {
+        unpack(ldi4(col(T3D_COL_ENERGY)), en);
+        unpack(ldi4(col(T3D_COL_ENERGY_START)), est);
+        unpack(ldf4(col(T3D_COL_POSITION + 0)), px);
+        unpack(ldf4(col(T3D_COL_POSITION + 1)), py);
+        unpack(ldf4(col(T3D_COL_POSITION + 2)), pz);
+        unpack(ldf4(col(T3D_COL_VELOCITY + 0)), vx);
+        unpack(ldf4(col(T3D_COL_VELOCITY + 1)), vy);
+        unpack(ldf4(col(T3D_COL_VELOCITY + 2)), vz);
+        unpack(ldf4(col(T3D_COL_ACCELERATION + 0)), ax);
+        unpack(ldf4(col(T3D_COL_ACCELERATION + 1)), ay);
+        unpack(ldf4(col(T3D_COL_ACCELERATION + 2)), az);
+        unpack(ldf4(col(T3D_COL_ROT_PER_PARTICLE_SPEED)), spin);
+        unpack(ldf4(col(T3D_COL_ANGLE)), ang);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+        {
+            unpack(ldf4(col(T3D_COL_COLOR_START + c)), cs[c]);
+            unpack(ldf4(col(T3D_COL_COLOR_END + c)), ce[c]);
+        }
+        unpack(ldf4(col(T3D_COL_SIZE_START)), ss);
+        unpack(ldf4(col(T3D_COL_SIZE_END)), se);
+        if (animated)
+        {
+            unpack(ldf4(col(T3D_COL_TIME_ON_FRAME)), tf);
+            unpack(ldi4(col(T3D_COL_FRAME)), fr);
+        }
+        if (may_rotate)
+        {
+            unpack(ldf4(col(T3D_COL_ROTATION_AXIS + 0)), rx);
+            unpack(ldf4(col(T3D_COL_ROTATION_AXIS + 1)), ry);
+            unpack(ldf4(col(T3D_COL_ROTATION_AXIS + 2)), rz);
+            unpack(ldf4(col(T3D_COL_ROTATION_SPEED)), rs);
+        }
+    }
+
+    // ---- energy and the dead flags (PE.cpp:753-755: `long -= float`, then `> 0`) ----
+    bool valid[V], alive[V];
+    uint32_t my_dead = 0;
+#pragma unroll
+    for (int l = 0; l < V; ++l)
+    {
+        valid[l] = active && (k0 + l < N);
+        if (valid[l]) en[l] = __float2int_rz((float)en[l] - elapsed_ms);
+        alive[l] = valid[l] && en[l] > 0;
+        my_dead += (valid[l] && !alive[l]) ? 1u : 0u;
+    }
+
+    // ---- exclusive scan of the dead count inside the tile ----
+    uint32_t incl = my_dead;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t warp_base = 0, tile_dead = 0;
+#pragma unroll
+    for (int wi = 0; wi < kUpdateThreads / 32; ++wi)
+    {
+        uint32_t v = s_warp[wi];
+        if ((uint32_t)wi < warp) warp_base += v;
+        tile_dead += v;
+    }
+    const uint32_t thread_excl = warp_base + incl - my_dead;
+
+    // ---- decoupled look-back over the preceding tiles of this emitter ----
+    const unsigned long long tag = (unsigned long long)epoch << 34;
+    unsigned long long* my_status = tile_status + tile;
+    if (jt == 0)
+    {
+        if (tid == 0)
+        {
+            st_status(my_status, tag | kStatusPrefix | tile_dead);
+            s_excl = 0;
+        }
+    }
+    else if (warp == 0)
+    {
+        if (lane == 0) st_status(my_status, tag | kStatusAggregate | tile_dead);
+        uint32_t excl = 0;
+        int look = (int)jt - 1; // nearest predecessor, as a tile index inside the emitter
+        while (true)
+        {
+            const int idx = look - (int)lane;
+            unsigned long long s = tag | kStatusPrefix; // tiles before the emitter's first: prefix 0
+            if (idx >= 0)
+            {
+                const unsigned long long* sp = tile_status + (it.tile_begin + (uint32_t)idx);
+                do
+                {
+                    s = ld_status(sp);
+                } while ((s >> 34) != (unsigned long long)epoch || ((s >> 32) & 3ull) == 0ull);
+            }
+            const bool is_prefix = ((s >> 32) & 3ull) == 2ull;
+            const unsigned pmask = __ballot_sync(0xffffffffu, is_prefix);
+            const int first_p = __ffs((int)pmask) - 1; // pmask is never 0 past the emitter's first tile
+            uint32_t contrib = (pmask == 0u || (int)lane <= first_p) ? (uint32_t)s : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+            excl += contrib;
+            if (pmask != 0u) break;
+            look -= 32;
+        }
+        if (lane == 0)
+        {
+            st_status(my_status, tag | kStatusPrefix | (excl + tile_dead));
+            s_excl = excl;
+        }
+    }
+    __syncthreads();
+    const uint32_t tile_excl = s_excl;
+
+    if (!active) return;
+
+    // ---- per-particle update, PE.cpp:757-819 (computed for every live particle; stored only if examined) ----
+    float col_out[4][V], size_out[V];
+    const float ppf = d->c.percent_per_frame;
+    const float dur = d->c.frame_duration_secs;
+    const uint32_t frame_count = d->c.frame_count;
+#pragma unroll
+    for (int l = 0; l < V; ++l)
+    {
+        if (!alive[l]) continue;
+        if (may_rotate && rs[l] != 0.0f && !(rx[l] == 0.0f && ry[l] == 0.0f && rz[l] == 0.0f))
+        {
+            const Rot3 r = create_rotation(rx[l], ry[l], rz[l], rs[l] * secs); // :759
+            rot_apply(r, 1.0f, vx[l], vy[l], vz[l]);                            // :761
+            rot_apply(r, 1.0f, ax[l], ay[l], az[l]);                            // :762
+        }
+        vx[l] += ax[l] * secs; // :766-768
+        vy[l] += ay[l] * secs;
+        vz[l] += az[l] * secs;
+        px[l] += vx[l] * secs; // :770-772
+        py[l] += vy[l] * secs;
+        pz[l] += vz[l] * secs;
+        ang[l] += spin[l] * secs; // :774
+        const float percent = 1.0f - ((float)en[l] / (float)est[l]); // :777
+#pragma unroll
+        for (int c = 0; c < 4; ++c) col_out[c][l] = cs[c][l] + (ce[c][l] - cs[c][l]) * percent; // :779-782
+        size_out[l] = ss[l] + (se[l] - ss[l]) * percent;                                          // :784
+        if (animated)
+        {
+            if (!looped)
+            {
+                float spent = 0.0f; // :792-796, repeated addition
+                for (int q = 0; q < fr[l]; ++q) spent += ppf;
+                tf[l] = percent - spent;
+                if ((uint32_t)fr[l] < frame_count - 1u && tf[l] >= ppf) ++fr[l];
+            }
+            else
+            {
+                tf[l] += secs; // :808-817
+                if (tf[l] >= dur)
+                {
+                    tf[l] -= dur;
+                    ++fr[l];
+                    if ((uint32_t)fr[l] == frame_count) fr[l] = 0;
+                }
+            }
+        }
+    }
+
+    // ---- stores ----
+    bool examined[V];
+    uint32_t D[V];
+    {
+        uint32_t run = tile_excl + thread_excl;
+#pragma unroll
+        for (int l = 0; l < V; ++l)
+        {
+            D[l] = run;
+            examined[l] = valid[l] && (k0 + l + run < N);
+            run += (valid[l] && !alive[l]) ? 1u : 0u;
+        }
+    }
+    const bool all_store = examined[0] && alive[0] && examined[1] && alive[1] && examined[2] && alive[2] &&
+                           examined[3] && alive[3];
+    if (all_store)
+    {
+        *reinterpret_cast<int4*>(col(T3D_COL_ENERGY)) = make_int4(en[0], en[1], en[2], en[3]);
+        stf4(col(T3D_COL_VELOCITY + 0), vx);
+        stf4(col(T3D_COL_VELOCITY + 1), vy);
+        stf4(col(T3D_COL_VELOCITY + 2), vz);
+        stf4(col(T3D_COL_POSITION + 0), px);
+        stf4(col(T3D_COL_POSITION + 1), py);
+        stf4(col(T3D_COL_POSITION + 2), pz);
+        stf4(col(T3D_COL_ANGLE), ang);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) stf4(col(T3D_COL_COLOR + c), col_out[c]);
+        stf4(col(T3D_COL_SIZE), size_out);
+        if (animated)
+        {
+            stf4(col(T3D_COL_TIME_ON_FRAME), tf);
+            *reinterpret_cast<int4*>(col(T3D_COL_FRAME)) = make_int4(fr[0], fr[1], fr[2], fr[3]);
+        }
+        if (may_rotate)
+        {
+            stf4(col(T3D_COL_ACCELERATION + 0), ax);
+            stf4(col(T3D_COL_ACCELERATION + 1), ay);
+            stf4(col(T3D_COL_ACCELERATION + 2), az);
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int l = 0; l < V; ++l)
+        {
+            if (!examined[l]) continue;
+            if (alive[l])
+            {
+                auto S = [&](int c, float v) { col(c)[l] = __float_as_uint(v); };
+                col(T3D_COL_ENERGY)[l] = (uint32_t)en[l];
+                S(T3D_COL_VELOCITY + 0, vx[l]);
+                S(T3D_COL_VELOCITY + 1, vy[l]);
+                S(T3D_COL_VELOCITY + 2, vz[l]);
+                S(T3D_COL_POSITION + 0, px[l]);
+                S(T3D_COL_POSITION + 1, py[l]);
+                S(T3D_COL_POSITION + 2, pz[l]);
+                S(T3D_COL_ANGLE, ang[l]);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) S(T3D_COL_COLOR + c, col_out[c][l]);
+                S(T3D_COL_SIZE, size_out[l]);
+                if (animated)
+                {
+                    S(T3D_COL_TIME_ON_FRAME, tf[l]);
+                    col(T3D_COL_FRAME)[l] = (uint32_t)fr[l];
+                }
+                if (may_rotate)
+                {
+                    S(T3D_COL_ACCELERATION + 0, ax[l]);
+                    S(T3D_COL_ACCELERATION + 1, ay[l]);
+                    S(T3D_COL_ACCELERATION + 2, az[l]);
+                }
+            }
+            else
+            {
+                // PE.cpp:825-828: the last live particle, untouched this frame, takes the dead one's place.
+                const uint32_t src = N - 1u - D[l];
+                const uint32_t dst = k0 + l;
+                if (src != dst)
+                {
+#pragma unroll 2
+                    for (int c = 0; c < T3D_NUM_COLUMNS; ++c)
+                        cols[(size_t)c * stride + dst] = cols[(size_t)c * stride + src];
+                }
+            }
+        }
+    }
+
+    // ---- the last examined original publishes the new count (PE.cpp:829) ----
+#pragma unroll
+    for (int l = 0; l < V; ++l)
+    {
+        if (!examined[l]) continue;
+        const uint32_t dead_l = alive[l] ? 0u : 1u;
+        const bool next_examined = (k0 + l + 1u) + D[l] + dead_l < N;
+        if (!next_examined)
+        {
+            d->cnt[parity ^ 1].count = N - D[l] - dead_l;
+            d->cnt[parity ^ 1].serial = d->cnt[parity].serial;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// draw
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kDrawThreads)
+    k_draw(const DrawItem* __restrict__ items, uint32_t n_items, int rot_mode, const FrozenRotation* __restrict__ frozen)
+{
+    __shared__ __align__(16) float s_vtx[kDrawThreads * T3D_FLOATS_PER_QUAD];
+    __shared__ float s_uv[kMaxSmemFrames * 4];
+
+    const uint32_t tile = blockIdx.x;
+    const DrawItem& it = items[find_item(items, n_items, tile)];
+    const EmitterDev* d = it.dev;
+    const uint32_t N = d->cnt[it.parity].count;
+    const uint32_t first = (tile - it.tile_begin) * kDrawThreads;
+    const uint32_t tid = threadIdx.x;
+    if (first == 0 && tid == 0) const_cast<EmitterDev*>(d)->cnt[0].drawn = N;
+    if (first >= N) return;
+
+    const uint32_t frame_count = d->c.frame_count;
+    const float* __restrict__ uv_g = d->c.uv;
+    const bool uv_in_smem = frame_count <= (uint32_t)kMaxSmemFrames;
+    if (uv_in_smem)
+        for (uint32_t q = tid; q < frame_count * 4u; q += kDrawThreads) s_uv[q] = uv_g[q];
+    __syncthreads();
+
+    const uint32_t i = first + tid;
+    if (i < N)
+    {
+        const uint32_t* cols = d->c.cols;
+        const size_t stride = d->c.stride;
+        auto LF = [&](int c) { return __uint_as_float(cols[(size_t)c * stride + i]); };
+        const float pos[3] = { LF(T3D_COL_POSITION), LF(T3D_COL_POSITION + 1), LF(T3D_COL_POSITION + 2) };
+        const float size = LF(T3D_COL_SIZE);
+        const float color[4] = { LF(T3D_COL_COLOR), LF(T3D_COL_COLOR + 1), LF(T3D_COL_COLOR + 2), LF(T3D_COL_COLOR + 3) };
+        const float angle = LF(T3D_COL_ANGLE);
+        const uint32_t frame = cols[(size_t)T3D_COL_FRAME * stride + i];
+        const float* uv = uv_in_smem ? (s_uv + frame * 4u) : (uv_g + (size_t)frame * 4u);
+        const float u1 = uv[0], v1 = uv[1], u2 = uv[2], v2 = uv[3];
+
+        const float right[3] = { it.right[0], it.right[1], it.right[2] };
+        const float up[3] = { it.up[0], it.up[1], it.up[2] };
+        const float width = size, height = size;
+
+        // SB.cpp:306-324
+        float p0[3], p1[3], p2[3], p3[3], tfw[3];
+        const float hw = width * 0.5f, hh = height * 0.5f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            const float tr = right[k] * hw;
+            const float tf = up[k] * hh;
+            p0[k] = pos[k];
+            p0[k] -= tr;
+            p0[k] -= tf;
+            p1[k] = pos[k];
+            p1[k] += tr;
+            p1[k] -= tf;
+            tfw[k] = up[k] * height;
+            p2[k] = p0[k] + tfw[k];
+            p3[k] = p1[k] + tfw[k];
+        }
+        if (angle != 0) // SB.cpp:327
+        {
+            float rp[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+            {
+                const float tr = right[k] * (width * 0.5f); // rotationPoint.x = 0.5 (PE.cpp:855)
+                const float tf = tfw[k] * 0.5f;
+                rp[k] = p0[k];
+                rp[k] += tr;
+                rp[k] += tf;
+            }
+            Rot3 r;
+            if (rot_mode == T3D_ROT_FROZEN)
+            {
+                // SB.cpp:339: the matrix latched by the first rotated quad of the process.
+                r.m0 = frozen->m[0]; r.m1 = frozen->m[1]; r.m2 = frozen->m[2];
+                r.m4 = frozen->m[4]; r.m5 = frozen->m[5]; r.m6 = frozen->m[6];
+                r.m8 = frozen->m[8]; r.m9 = frozen->m[9]; r.m10 = frozen->m[10];
+            }
+            else
+            {
+                // MathUtil.h:216-225
+                const float ux = (right[1] * up[2]) - (right[2] * up[1]);
+                const float uy = (right[2] * up[0]) - (right[0] * up[2]);
+                const float uz = (right[0] * up[1]) - (right[1] * up[0]);
+                r = create_rotation(ux, uy, uz, angle);
+            }
+            float* ps[4] = { p0, p1, p2, p3 };
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+            {
+                float* p = ps[q];
+                p[0] -= rp[0];
+                p[1] -= rp[1];
+                p[2] -= rp[2];
+                rot_apply(r, 0.0f, p[0], p[1], p[2]); // Vector3 *= Matrix: transformVector, w = 0
+                p[0] += rp[0];
+                p[1] += rp[1];
+                p[2] += rp[2];
+            }
+        }
+        // SB.cpp:355-359: v0=(p0,u1,v1) v1=(p1,u2,v1) v2=(p2,u1,v2) v3=(p3,u2,v2), particle colour on all four.
+        float4* o = reinterpret_cast<float4*>(s_vtx + tid * T3D_FLOATS_PER_QUAD);
+        o[0] = make_float4(p0[0], p0[1], p0[2], u1);
+        o[1] = make_float4(v1, color[0], color[1], color[2]);
+        o[2] = make_float4(color[3], p1[0], p1[1], p1[2]);
+        o[3] = make_float4(u2, v1, color[0], color[1]);
+        o[4] = make_float4(color[2], color[3], p2[0], p2[1]);
+        o[5] = make_float4(p2[2], u1, v2, color[0]);
+        o[6] = make_float4(color[1], color[2], color[3], p3[0]);
+        o[7] = make_float4(p3[1], p3[2], u2, v2);
+        o[8] = make_float4(color[0], color[1], color[2], color[3]);
+    }
+    __syncthreads();
+
+    // Coalesced copy of the tile's vertices: nq quads * 144 B, contiguous in the emitter's vertex stream.
+    const uint32_t nq = (N - first) < (uint32_t)kDrawThreads ? (N - first) : (uint32_t)kDrawThreads;
+    float4* __restrict__ dst = reinterpret_cast<float4*>(d->c.vtx + (size_t)first * T3D_FLOATS_PER_QUAD);
+    const float4* src4 = reinterpret_cast<const float4*>(s_vtx);
+    for (uint32_t q = tid; q < nq * 9u; q += kDrawThreads) dst[q] = src4[q];
+}
+
+// --------------------------------------------------------------------------------------------------
+// frozen-rotation latch: first particle, in draw order, whose angle is non-zero (SB.cpp:327, 337-339).
+// One CTA.  Writes the axis u = right x up and the angle; the host turns them into the matrix with the
+// same libm sincosf the reference uses and uploads it (once per process).
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_latch(const DrawItem* __restrict__ items, uint32_t n_items, FrozenRotation* frozen)
+{
+    __shared__ uint32_t s_min;
+    if (frozen->latched) return;
+    for (uint32_t e = 0; e < n_items; ++e)
+    {
+        const DrawItem& it = items[e];
+        const EmitterDev* d = it.dev;
+        if (!(d->c.flags & kFlagMaySpin)) continue;
+        const uint32_t N = d->cnt[it.parity].count;
+        const uint32_t* ang = d->c.cols + (size_t)T3D_COL_ANGLE * d->c.stride;
+        for (uint32_t base = 0; base < N; base += 256)
+        {
+            if (threadIdx.x == 0) s_min = 0xffffffffu;
+            __syncthreads();
+            const uint32_t i = base + threadIdx.x;
+            if (i < N && __uint_as_float(ang[i]) != 0.0f) atomicMin(&s_min, i);
+            __syncthreads();
+            const uint32_t m = s_min;
+            __syncthreads();
+            if (m != 0xffffffffu)
+            {
+                if (threadIdx.x == 0)
+                {
+                    const float* r = it.right;
+                    const float* u = it.up;
+                    frozen->m[0] = (r[1] * u[2]) - (r[2] * u[1]);
+                    frozen->m[1] = (r[2] * u[0]) - (r[0] * u[2]);
+                    frozen->m[2] = (r[0] * u[1]) - (r[1] * u[0]);
+                    frozen->m[3] = __uint_as_float(ang[m]);
+                    frozen->latched = 2; // 2 = axis/angle found, matrix pending on the host
+                }
+                return;
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// launch wrappers
+// --------------------------------------------------------------------------------------------------
+void launch_spawn(void* stream, const SpawnItem* items, uint32_t n_items, uint32_t total_tiles)
+{
+    k_spawn<<<total_tiles, kSpawnThreads, 0, (cudaStream_t)stream>>>(items, n_items);
+}
+
+void launch_update(void* stream, const UpdateItem* items, uint32_t n_items, uint32_t total_tiles,
+                   unsigned long long* tile_status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch)
+{
+    k_update<<<total_tiles, kUpdateThreads, 0, (cudaStream_t)stream>>>(items, n_items, total_tiles, tile_status, ticket,
+                                                                      ticket_base, epoch);
+}
+
+void launch_draw(void* stream, const DrawItem* items, uint32_t n_items, uint32_t total_tiles, int rot_mode,
+                 const FrozenRotation* frozen)
+{
+    k_draw<<<total_tiles, kDrawThreads, 0, (cudaStream_t)stream>>>(items, n_items, rot_mode, frozen);
+}
+
+void launch_latch(void* stream, const DrawItem* items, uint32_t n_items, FrozenRotation* frozen)
+{
+    k_latch<<<1, 256, 0, (cudaStream_t)stream>>>(items, n_items, frozen);
+}
+
+__global__ void k_gather_counts(const CountQuery* __restrict__ q, uint32_t n, uint32_t* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[2 * i] = q[i].dev->cnt[q[i].parity].count;
+    out[2 * i + 1] = q[i].dev->cnt[0].drawn;
+}
+
+void launch_gather_counts(void* stream, const CountQuery* q, uint32_t n, uint32_t* out)
+{
+    k_gather_counts<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(q, n, out);
+}
+
+} // namespace t3d

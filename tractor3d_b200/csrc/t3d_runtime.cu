@@ -1,0 +1,1372 @@
+// t3d_runtime.cu -- host runtime behind the C ABI of include/t3d_particles.h.
+//
+// What lives here (all host code; the kernels are in t3d_kernels.cu):
+//   * the per-GPU context: slabs of struct-of-arrays particle storage in HBM, the per-emitter device
+//     records, pinned staging for per-launch descriptors, tile-status words for the removal scan;
+//   * the emitter object: the reference's configuration members and the scalar per-call logic that stays
+//     on the host exactly as the reference computes it -- isActive (PE.cpp:277-284), the process-wide
+//     update rate cap (PE.cpp:720-725), the emission count (PE.cpp:729-746), the capacity clamp
+//     (PE.cpp:293-296), the sprite uv table (PE.cpp:512-582);
+//   * a command queue that coalesces consecutive emit / update / draw calls on different emitters into one
+//     launch per phase, so a game loop that calls emitter->update() on 8 K emitters costs two launches.
+//
+// PE.cpp = Tractor3Dlib/src/graphics/ParticleEmitter.cpp of the reference.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "t3d_host.h"
+#include "t3d_internal.h"
+
+using namespace t3d;
+
+// --------------------------------------------------------------------------------------------------
+// errors
+// --------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define T3D_CUDA(call)                                                                                          \
+    do                                                                                                          \
+    {                                                                                                           \
+        cudaError_t err__ = (call);                                                                             \
+        if (err__ != cudaSuccess) return fail(T3D_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(err__)); \
+    } while (0)
+
+#define T3D_TRY(expr)                  \
+    do                                 \
+    {                                  \
+        int rc__ = (expr);             \
+        if (rc__ != T3D_OK) return rc__; \
+    } while (0)
+
+// --------------------------------------------------------------------------------------------------
+// objects
+// --------------------------------------------------------------------------------------------------
+namespace
+{
+
+enum Phase { PHASE_NONE = 0, PHASE_EMIT = 1, PHASE_UPDATE = 2, PHASE_DRAW = 3 };
+enum { KERNEL_SPAWN = 0, KERNEL_UPDATE = 1, KERNEL_DRAW = 2 };
+
+struct Slab
+{
+    uint32_t* cols{ nullptr }; // T3D_NUM_COLUMNS * capacity words
+    float* vtx{ nullptr };     // capacity * 36 floats, allocated at the first draw that needs it
+    uint32_t capacity{ 0 };
+    uint32_t used{ 0 };
+    uint32_t live_emitters{ 0 };
+};
+
+struct StagingSlot
+{
+    char* host{ nullptr };
+    char* dev{ nullptr };
+    size_t cap{ 0 };
+    cudaEvent_t done{ nullptr };
+    bool in_flight{ false };
+};
+
+struct PendingOp
+{
+    t3d_emitter* e;
+    float elapsed_ms;     // update
+    uint32_t emit_n;      // particles to spawn before the update (or the whole op for PHASE_EMIT)
+    size_t draws_begin;   // into ctx->pending_draws, when the draws come from the host
+    size_t draws_count;
+    size_t offsets_begin; // into ctx->pending_offsets (ellipsoid), or SIZE_MAX for constant stride
+    uint32_t draw_stride;
+    bool host_draws;
+    float world[16];
+    float right[3], up[3];
+};
+
+} // namespace
+
+struct t3d_ctx
+{
+    int device{ 0 };
+    cudaStream_t stream{ nullptr };
+    bool own_stream{ false };
+
+    std::vector<Slab> slabs;
+    uint32_t next_slab_particles{ 1u << 20 };
+
+    std::vector<EmitterDev*> dev_chunks; // arena of device records, kDevChunk per allocation
+    uint32_t dev_used{ 0 };
+    std::vector<EmitterDev*> dev_free;
+
+    StagingSlot staging[8];
+    int staging_next{ 0 };
+
+    unsigned long long* tile_status{ nullptr };
+    size_t tile_status_cap{ 0 };
+    uint32_t* ticket{ nullptr };
+    uint32_t ticket_base{ 0 };
+    uint32_t epoch{ 0 };
+
+    FrozenRotation* frozen_dev{ nullptr };
+    bool frozen_latched{ false };
+    float frozen_m[16];
+    int rot_mode{ T3D_ROT_FROZEN };
+
+    double running_time{ 0 }; // PE.cpp:720, one per process in the reference, one per context here
+
+    int phase{ PHASE_NONE };
+    std::vector<PendingOp> pending;
+    std::vector<int32_t> pending_draws;
+    std::vector<uint32_t> pending_offsets;
+
+    uint64_t launches{ 0 }, h2d_bytes{ 0 }, d2h_bytes{ 0 };
+    cudaEvent_t ev_start[3]{}, ev_stop[3]{};
+    bool ev_valid[3]{ false, false, false };
+
+    uint32_t* readback_host{ nullptr }; // pinned scratch for counts
+    size_t readback_cap{ 0 };
+    uint32_t* readback_dev{ nullptr };
+
+    std::vector<t3d_emitter*> emitters;
+};
+
+struct t3d_emitter
+{
+    t3d_ctx* ctx{ nullptr };
+    t3d_emitter_params p{};
+    std::vector<float> tex_coords; // frame_count * 4
+    uint32_t frame_count{ 1 };
+    float percent_per_frame{ 1.0f };
+    float frame_duration_secs{ 0.0f };
+    float tex_w_ratio{ 0 }, tex_h_ratio{ 0 };
+    float time_per_emission{ 100.0f };
+    float emit_time{ 0 };
+    bool started{ false };
+    bool has_node{ false }, has_camera{ false };
+    float node_world[16];
+    float camera_world[16];
+
+    int rng_mode{ T3D_RNG_LIBC };
+    uint64_t rng_seed{ 0 };
+    std::vector<int32_t> fed; // T3D_RNG_STREAM queue
+    size_t fed_head{ 0 };
+
+    EmitterDev* dev{ nullptr };
+    int slab{ -1 };
+    uint32_t seg_offset{ 0 }, seg_capacity{ 0 };
+    float* uv_dev{ nullptr };
+    uint32_t uv_cap{ 0 };
+    uint32_t parity{ 0 };
+    bool const_dirty{ true }, uv_dirty{ true };
+    bool may_rotate{ false }, may_spin{ false };
+    uint32_t count_ub{ 0 };     // upper bound of the live count (exact when count_exact)
+    bool count_exact{ true };
+    bool queued{ false };
+    bool last_draw_empty{ true }; // the last draw() submitted no quads (inactive or no particles)
+};
+
+constexpr uint32_t kDevChunk = 4096;
+
+// --------------------------------------------------------------------------------------------------
+// context plumbing
+// --------------------------------------------------------------------------------------------------
+static int use_device(t3d_ctx* c)
+{
+    T3D_CUDA(cudaSetDevice(c->device));
+    return T3D_OK;
+}
+
+static int staging_acquire(t3d_ctx* c, size_t bytes, StagingSlot** out)
+{
+    StagingSlot& s = c->staging[c->staging_next];
+    c->staging_next = (c->staging_next + 1) % 8;
+    if (s.in_flight)
+    {
+        T3D_CUDA(cudaEventSynchronize(s.done));
+        s.in_flight = false;
+    }
+    if (!s.done) T3D_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    if (s.cap < bytes)
+    {
+        if (s.host) cudaFreeHost(s.host);
+        if (s.dev) cudaFree(s.dev);
+        s.host = s.dev = nullptr;
+        size_t cap = std::max<size_t>(bytes + bytes / 2, 1 << 16);
+        T3D_CUDA(cudaMallocHost((void**)&s.host, cap));
+        T3D_CUDA(cudaMalloc((void**)&s.dev, cap));
+        s.cap = cap;
+    }
+    *out = &s;
+    return T3D_OK;
+}
+
+static int staging_submit(t3d_ctx* c, StagingSlot* s, size_t bytes)
+{
+    T3D_CUDA(cudaMemcpyAsync(s->dev, s->host, bytes, cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += bytes;
+    return T3D_OK;
+}
+
+static int staging_release(t3d_ctx* c, StagingSlot* s)
+{
+    T3D_CUDA(cudaEventRecord(s->done, c->stream));
+    s->in_flight = true;
+    return T3D_OK;
+}
+
+static int alloc_segment(t3d_ctx* c, uint32_t capacity, int* slab_out, uint32_t* offset_out, uint32_t* padded_out)
+{
+    uint32_t padded = (std::max(capacity, 1u) + kSegmentAlign - 1) / kSegmentAlign * kSegmentAlign;
+    for (size_t i = 0; i < c->slabs.size(); ++i)
+    {
+        Slab& s = c->slabs[i];
+        if (s.cols && s.capacity - s.used >= padded)
+        {
+            *slab_out = (int)i;
+            *offset_out = s.used;
+            *padded_out = padded;
+            s.used += padded;
+            s.live_emitters++;
+            return T3D_OK;
+        }
+    }
+    uint64_t want = std::max<uint64_t>(padded, c->next_slab_particles);
+    want = (want + 1023) / 1024 * 1024;
+    if (want > 0x7fffffffull) return fail(T3D_ERR_CAPACITY, "emitter capacity %u exceeds the 2^31 particle slab limit", capacity);
+    Slab s;
+    s.capacity = (uint32_t)want;
+    T3D_CUDA(cudaMalloc((void**)&s.cols, (size_t)T3D_NUM_COLUMNS * s.capacity * sizeof(uint32_t)));
+    s.used = padded;
+    s.live_emitters = 1;
+    c->slabs.push_back(s);
+    if (c->next_slab_particles < (1u << 26)) c->next_slab_particles *= 2;
+    *slab_out = (int)c->slabs.size() - 1;
+    *offset_out = 0;
+    *padded_out = padded;
+    return T3D_OK;
+}
+
+static int alloc_dev_record(t3d_ctx* c, EmitterDev** out)
+{
+    if (!c->dev_free.empty())
+    {
+        *out = c->dev_free.back();
+        c->dev_free.pop_back();
+    }
+    else
+    {
+        if (c->dev_chunks.empty() || c->dev_used == kDevChunk)
+        {
+            EmitterDev* chunk = nullptr;
+            T3D_CUDA(cudaMalloc((void**)&chunk, sizeof(EmitterDev) * kDevChunk));
+            c->dev_chunks.push_back(chunk);
+            c->dev_used = 0;
+        }
+        *out = c->dev_chunks.back() + c->dev_used++;
+    }
+    T3D_CUDA(cudaMemsetAsync(*out, 0, sizeof(EmitterDev), c->stream));
+    return T3D_OK;
+}
+
+static void host_create_rotation(const float u[3], float angle, float* m)
+{
+    // Matrix.cpp:348-406 on the host, with the same libm sincosf the reference build calls.
+    float x = u[0], y = u[1], z = u[2];
+    float n = x * x + y * y + z * z;
+    if (n != 1.0f)
+    {
+        n = sqrtf(n);
+        if (n > 0.000001f)
+        {
+            n = 1.0f / n;
+            x *= n;
+            y *= n;
+            z *= n;
+        }
+    }
+    float s, co;
+    sincosf(angle, &s, &co);
+    float t = 1.0f - co;
+    float tx = t * x, ty = t * y, tz = t * z;
+    float txy = tx * y, txz = tx * z, tyz = ty * z;
+    float sx = s * x, sy = s * y, sz = s * z;
+    m[0] = co + tx * x; m[1] = txy + sz;    m[2] = txz - sy;    m[3] = 0.0f;
+    m[4] = txy - sz;    m[5] = co + ty * y; m[6] = tyz + sx;    m[7] = 0.0f;
+    m[8] = txz + sy;    m[9] = tyz - sx;    m[10] = co + tz * z; m[11] = 0.0f;
+    m[12] = 0.0f; m[13] = 0.0f; m[14] = 0.0f; m[15] = 1.0f;
+}
+
+static int upload_frozen(t3d_ctx* c)
+{
+    FrozenRotation f;
+    memset(&f, 0, sizeof(f));
+    memcpy(f.m, c->frozen_m, sizeof(f.m));
+    f.latched = c->frozen_latched ? 1 : 0;
+    T3D_CUDA(cudaMemcpyAsync(c->frozen_dev, &f, sizeof(f), cudaMemcpyHostToDevice, c->stream));
+    T3D_CUDA(cudaStreamSynchronize(c->stream)); // `f` is on the stack
+    return T3D_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// per-emitter device constants
+// --------------------------------------------------------------------------------------------------
+static void fill_const(const t3d_emitter* e, EmitterConst* k)
+{
+    const t3d_ctx* c = e->ctx;
+    const Slab& s = c->slabs[e->slab];
+    memset(k, 0, sizeof(*k));
+    k->cols = s.cols + e->seg_offset;
+    k->vtx = s.vtx ? s.vtx + (size_t)e->seg_offset * T3D_FLOATS_PER_QUAD : nullptr;
+    k->uv = e->uv_dev;
+    k->stride = s.capacity;
+    k->capacity = e->p.particle_count_max;
+    k->flags = (e->p.sprite_animated ? kFlagAnimated : 0u) | (e->p.sprite_looped ? kFlagLooped : 0u) |
+               (e->may_rotate ? kFlagMayRotate : 0u) | (e->may_spin ? kFlagMaySpin : 0u);
+    k->frame_count = e->frame_count;
+    k->percent_per_frame = e->percent_per_frame;
+    k->frame_duration_secs = e->frame_duration_secs;
+    SpawnParams& sp = k->sp;
+    const t3d_emitter_params& p = e->p;
+    memcpy(sp.color_start, p.color_start, 16); memcpy(sp.color_start_var, p.color_start_var, 16);
+    memcpy(sp.color_end, p.color_end, 16); memcpy(sp.color_end_var, p.color_end_var, 16);
+    memcpy(sp.position, p.position, 12); memcpy(sp.position_var, p.position_var, 12);
+    memcpy(sp.velocity, p.velocity, 12); memcpy(sp.velocity_var, p.velocity_var, 12);
+    memcpy(sp.acceleration, p.acceleration, 12); memcpy(sp.acceleration_var, p.acceleration_var, 12);
+    memcpy(sp.rotation_axis, p.rotation_axis, 12); memcpy(sp.rotation_axis_var, p.rotation_axis_var, 12);
+    sp.size_start_min = p.size_start_min; sp.size_start_max = p.size_start_max;
+    sp.size_end_min = p.size_end_min; sp.size_end_max = p.size_end_max;
+    sp.energy_min = p.energy_min; sp.energy_max = p.energy_max;
+    sp.spin_min = p.rotation_per_particle_speed_min; sp.spin_max = p.rotation_per_particle_speed_max;
+    sp.rot_speed_min = p.rotation_speed_min; sp.rot_speed_max = p.rotation_speed_max;
+    sp.ellipsoid = p.ellipsoid != 0; sp.orbit_position = p.orbit_position != 0;
+    sp.orbit_velocity = p.orbit_velocity != 0; sp.orbit_acceleration = p.orbit_acceleration != 0;
+    sp.frame_random_offset = p.sprite_frame_random_offset;
+    sp.rng_seed = e->rng_seed;
+}
+
+static int sync_const(t3d_emitter* e)
+{
+    t3d_ctx* c = e->ctx;
+    if (e->uv_dirty)
+    {
+        const uint32_t need = e->frame_count * 4;
+        if (e->uv_cap < need)
+        {
+            // The old table may still be read by launches in flight on the stream.
+            if (e->uv_dev)
+            {
+                T3D_CUDA(cudaStreamSynchronize(c->stream));
+                cudaFree(e->uv_dev);
+            }
+            T3D_CUDA(cudaMalloc((void**)&e->uv_dev, sizeof(float) * need));
+            e->uv_cap = need;
+        }
+        T3D_CUDA(cudaMemcpyAsync(e->uv_dev, e->tex_coords.data(), sizeof(float) * need, cudaMemcpyHostToDevice, c->stream));
+        c->h2d_bytes += sizeof(float) * need;
+        e->uv_dirty = false;
+        e->const_dirty = true;
+    }
+    if (e->const_dirty)
+    {
+        EmitterConst k;
+        fill_const(e, &k);
+        // Pageable source: the runtime stages it before returning, so `k` may go out of scope.
+        T3D_CUDA(cudaMemcpyAsync(&e->dev->c, &k, sizeof(k), cudaMemcpyHostToDevice, c->stream));
+        c->h2d_bytes += sizeof(k);
+        e->const_dirty = false;
+    }
+    return T3D_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// flush: turn the queued ops of the current phase into launches
+// --------------------------------------------------------------------------------------------------
+static int time_begin(t3d_ctx* c, int k)
+{
+    if (!c->ev_start[k])
+    {
+        T3D_CUDA(cudaEventCreate(&c->ev_start[k]));
+        T3D_CUDA(cudaEventCreate(&c->ev_stop[k]));
+    }
+    T3D_CUDA(cudaEventRecord(c->ev_start[k], c->stream));
+    return T3D_OK;
+}
+static int time_end(t3d_ctx* c, int k)
+{
+    T3D_CUDA(cudaEventRecord(c->ev_stop[k], c->stream));
+    c->ev_valid[k] = true;
+    return T3D_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int launch_spawns(t3d_ctx* c)
+{
+    // Gather the ops that spawn.
+    uint32_t n_items = 0;
+    for (const PendingOp& op : c->pending) n_items += op.emit_n > 0 ? 1u : 0u;
+    if (!n_items) return T3D_OK;
+
+    const size_t items_bytes = align_up(sizeof(SpawnItem) * n_items, 16);
+    const size_t offs_bytes = align_up(sizeof(uint32_t) * c->pending_offsets.size(), 16);
+    const size_t draws_bytes = sizeof(int32_t) * c->pending_draws.size();
+    const size_t total = items_bytes + offs_bytes + draws_bytes;
+    StagingSlot* slot;
+    T3D_TRY(staging_acquire(c, total, &slot));
+    SpawnItem* items = reinterpret_cast<SpawnItem*>(slot->host);
+    const uint32_t* dev_offs = reinterpret_cast<const uint32_t*>(slot->dev + items_bytes);
+    const int32_t* dev_draws = reinterpret_cast<const int32_t*>(slot->dev + items_bytes + offs_bytes);
+    if (offs_bytes) memcpy(slot->host + items_bytes, c->pending_offsets.data(), sizeof(uint32_t) * c->pending_offsets.size());
+    if (draws_bytes) memcpy(slot->host + items_bytes + offs_bytes, c->pending_draws.data(), draws_bytes);
+
+    uint32_t tiles = 0, k = 0;
+    for (PendingOp& op : c->pending)
+    {
+        if (!op.emit_n) continue;
+        t3d_emitter* e = op.e;
+        T3D_TRY(sync_const(e));
+        SpawnItem& it = items[k++];
+        memset(&it, 0, sizeof(it));
+        it.dev = e->dev;
+        if (op.host_draws)
+        {
+            it.draws = dev_draws + op.draws_begin;
+            it.offsets = op.offsets_begin == SIZE_MAX ? nullptr : dev_offs + op.offsets_begin;
+            it.draw_stride = op.draw_stride;
+        }
+        it.request = op.emit_n;
+        it.parity = e->parity;
+        e->parity ^= 1u;
+        it.tile_begin = tiles;
+        memcpy(it.world, op.world, sizeof(it.world));
+        tiles += (op.emit_n + kSpawnThreads - 1) / kSpawnThreads;
+    }
+    T3D_TRY(staging_submit(c, slot, total));
+    T3D_TRY(time_begin(c, KERNEL_SPAWN));
+    launch_spawn(c->stream, reinterpret_cast<const SpawnItem*>(slot->dev), n_items, tiles);
+    T3D_CUDA(cudaGetLastError());
+    T3D_TRY(time_end(c, KERNEL_SPAWN));
+    c->launches++;
+    T3D_TRY(staging_release(c, slot));
+    return T3D_OK;
+}
+
+static int launch_updates(t3d_ctx* c)
+{
+    const uint32_t n_items = (uint32_t)c->pending.size();
+    StagingSlot* slot;
+    T3D_TRY(staging_acquire(c, sizeof(UpdateItem) * n_items, &slot));
+    UpdateItem* items = reinterpret_cast<UpdateItem*>(slot->host);
+    uint32_t tiles = 0;
+    for (uint32_t k = 0; k < n_items; ++k)
+    {
+        PendingOp& op = c->pending[k];
+        t3d_emitter* e = op.e;
+        T3D_TRY(sync_const(e));
+        UpdateItem& it = items[k];
+        it.dev = e->dev;
+        it.elapsed_ms = op.elapsed_ms;
+        it.parity = e->parity;
+        e->parity ^= 1u;
+        it.tile_begin = tiles;
+        it.pad = 0;
+        // At least one tile per emitter: tile 0 republishes the count into the other parity slot.
+        tiles += std::max(1u, (e->count_ub + kUpdateTile - 1) / kUpdateTile);
+    }
+    if (c->tile_status_cap < tiles)
+    {
+        if (c->tile_status)
+        {
+            T3D_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(c->tile_status);
+        }
+        size_t cap = std::max<size_t>(tiles + tiles / 2, 4096);
+        T3D_CUDA(cudaMalloc((void**)&c->tile_status, cap * sizeof(unsigned long long)));
+        T3D_CUDA(cudaMemsetAsync(c->tile_status, 0, cap * sizeof(unsigned long long), c->stream));
+        c->tile_status_cap = cap;
+    }
+    c->epoch++;
+    if (c->epoch >= (1u << 30))
+    {
+        T3D_CUDA(cudaMemsetAsync(c->tile_status, 0, c->tile_status_cap * sizeof(unsigned long long), c->stream));
+        c->epoch = 1;
+    }
+    T3D_TRY(staging_submit(c, slot, sizeof(UpdateItem) * n_items));
+    T3D_TRY(time_begin(c, KERNEL_UPDATE));
+    launch_update(c->stream, reinterpret_cast<const UpdateItem*>(slot->dev), n_items, tiles, c->tile_status, c->ticket,
+                  c->ticket_base, c->epoch);
+    T3D_CUDA(cudaGetLastError());
+    T3D_TRY(time_end(c, KERNEL_UPDATE));
+    c->ticket_base += tiles;
+    c->launches++;
+    T3D_TRY(staging_release(c, slot));
+    return T3D_OK;
+}
+
+static int launch_draws(t3d_ctx* c)
+{
+    const uint32_t n_items = (uint32_t)c->pending.size();
+    // Vertex storage is allocated per slab the first time one of its emitters is drawn.
+    for (PendingOp& op : c->pending)
+    {
+        Slab& s = c->slabs[op.e->slab];
+        if (!s.vtx)
+        {
+            T3D_CUDA(cudaMalloc((void**)&s.vtx, (size_t)s.capacity * T3D_FLOATS_PER_QUAD * sizeof(float)));
+            for (t3d_emitter* o : c->emitters)
+                if (o->slab == op.e->slab) o->const_dirty = true;
+        }
+    }
+    StagingSlot* slot;
+    T3D_TRY(staging_acquire(c, sizeof(DrawItem) * n_items, &slot));
+    DrawItem* items = reinterpret_cast<DrawItem*>(slot->host);
+    uint32_t tiles = 0;
+    bool any_spin = false;
+    for (uint32_t k = 0; k < n_items; ++k)
+    {
+        PendingOp& op = c->pending[k];
+        t3d_emitter* e = op.e;
+        T3D_TRY(sync_const(e));
+        DrawItem& it = items[k];
+        it.dev = e->dev;
+        it.parity = e->parity;
+        it.tile_begin = tiles;
+        memcpy(it.right, op.right, 12);
+        memcpy(it.up, op.up, 12);
+        tiles += std::max(1u, (e->count_ub + kDrawThreads - 1) / kDrawThreads);
+        any_spin = any_spin || e->may_spin;
+    }
+    T3D_TRY(staging_submit(c, slot, sizeof(DrawItem) * n_items));
+    if (c->rot_mode == T3D_ROT_FROZEN && !c->frozen_latched && any_spin)
+    {
+        // SB.cpp:337-339: the first rotated quad of the process fixes the rotation matrix for good.  Find it on
+        // the device, build the matrix on the host with the libm the reference uses, upload it.  Happens once.
+        launch_latch(c->stream, reinterpret_cast<const DrawItem*>(slot->dev), n_items, c->frozen_dev);
+        T3D_CUDA(cudaGetLastError());
+        c->launches++;
+        FrozenRotation f;
+        T3D_CUDA(cudaMemcpyAsync(&f, c->frozen_dev, sizeof(f), cudaMemcpyDeviceToHost, c->stream));
+        T3D_CUDA(cudaStreamSynchronize(c->stream));
+        c->d2h_bytes += sizeof(f);
+        if (f.latched == 2)
+        {
+            const float u[3] = { f.m[0], f.m[1], f.m[2] };
+            host_create_rotation(u, f.m[3], c->frozen_m);
+            c->frozen_latched = true;
+            T3D_TRY(upload_frozen(c));
+        }
+    }
+    T3D_TRY(time_begin(c, KERNEL_DRAW));
+    launch_draw(c->stream, reinterpret_cast<const DrawItem*>(slot->dev), n_items, tiles, c->rot_mode, c->frozen_dev);
+    T3D_CUDA(cudaGetLastError());
+    T3D_TRY(time_end(c, KERNEL_DRAW));
+    c->launches++;
+    T3D_TRY(staging_release(c, slot));
+    return T3D_OK;
+}
+
+static int flush(t3d_ctx* c)
+{
+    if (c->phase == PHASE_NONE || c->pending.empty())
+    {
+        c->phase = PHASE_NONE;
+        return T3D_OK;
+    }
+    T3D_TRY(use_device(c));
+    int rc = T3D_OK;
+    if (c->phase == PHASE_EMIT)
+        rc = launch_spawns(c);
+    else if (c->phase == PHASE_UPDATE)
+    {
+        rc = launch_spawns(c);
+        if (rc == T3D_OK) rc = launch_updates(c);
+    }
+    else if (c->phase == PHASE_DRAW)
+        rc = launch_draws(c);
+    for (PendingOp& op : c->pending) op.e->queued = false;
+    c->pending.clear();
+    c->pending_draws.clear();
+    c->pending_offsets.clear();
+    c->phase = PHASE_NONE;
+    return rc;
+}
+
+static int enqueue(t3d_ctx* c, int phase, const PendingOp& op)
+{
+    if (c->phase != phase || op.e->queued) T3D_TRY(flush(c));
+    c->phase = phase;
+    c->pending.push_back(op);
+    op.e->queued = true;
+    return T3D_OK;
+}
+
+// Reads the live count (and the quad count of the last draw) back; makes the host mirror exact.
+static int refresh_counts(t3d_ctx* c, t3d_emitter* const* es, size_t n, uint32_t* counts, uint32_t* drawn)
+{
+    T3D_TRY(flush(c));
+    T3D_TRY(use_device(c));
+    if (n == 0) return T3D_OK;
+    if (c->readback_cap < n)
+    {
+        if (c->readback_host) cudaFreeHost(c->readback_host);
+        if (c->readback_dev) cudaFree(c->readback_dev);
+        size_t cap = std::max<size_t>(n * 2, 256);
+        T3D_CUDA(cudaMallocHost((void**)&c->readback_host, cap * 2 * sizeof(uint32_t)));
+        T3D_CUDA(cudaMalloc((void**)&c->readback_dev, cap * 2 * sizeof(uint32_t)));
+        c->readback_cap = cap;
+    }
+    StagingSlot* slot;
+    T3D_TRY(staging_acquire(c, sizeof(CountQuery) * n, &slot));
+    CountQuery* q = reinterpret_cast<CountQuery*>(slot->host);
+    for (size_t i = 0; i < n; ++i)
+    {
+        q[i].dev = es[i]->dev;
+        q[i].parity = es[i]->parity;
+        q[i].pad = 0;
+    }
+    T3D_TRY(staging_submit(c, slot, sizeof(CountQuery) * n));
+    launch_gather_counts(c->stream, reinterpret_cast<const CountQuery*>(slot->dev), (uint32_t)n, c->readback_dev);
+    T3D_CUDA(cudaGetLastError());
+    c->launches++;
+    T3D_CUDA(cudaMemcpyAsync(c->readback_host, c->readback_dev, n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    T3D_TRY(staging_release(c, slot));
+    T3D_CUDA(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += n * 2 * sizeof(uint32_t);
+    for (size_t i = 0; i < n; ++i)
+    {
+        es[i]->count_ub = c->readback_host[2 * i];
+        es[i]->count_exact = true;
+        if (counts) counts[i] = c->readback_host[2 * i];
+        if (drawn) drawn[i] = c->readback_host[2 * i + 1];
+    }
+    return T3D_OK;
+}
+
+static int exact_count(t3d_emitter* e, uint32_t* out)
+{
+    if (!e->count_exact) T3D_TRY(refresh_counts(e->ctx, &e, 1, nullptr, nullptr));
+    *out = e->count_ub;
+    return T3D_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// host-side random draws for T3D_RNG_LIBC / T3D_RNG_STREAM
+// --------------------------------------------------------------------------------------------------
+namespace
+{
+struct HostDraws
+{
+    t3d_emitter* e;
+    bool underflow{ false };
+    int32_t next()
+    {
+        if (e->rng_mode == T3D_RNG_LIBC) return (int32_t)rand();
+        if (e->fed_head >= e->fed.size())
+        {
+            underflow = true;
+            return 0;
+        }
+        return e->fed[e->fed_head++];
+    }
+};
+} // namespace
+
+// Pulls the draws n particles consume (PE.cpp:312-364 order) into the context's pending buffers.
+static int collect_host_draws(t3d_emitter* e, uint32_t n, PendingOp* op)
+{
+    t3d_ctx* c = e->ctx;
+    const bool ellipsoid = e->p.ellipsoid != 0;
+    const uint32_t fro = e->p.sprite_frame_random_offset;
+    const uint32_t stride = 26u + (fro > 0 ? 1u : 0u);
+    HostDraws src{ e };
+    const size_t fed_head0 = e->fed_head;
+    const size_t d0 = c->pending_draws.size(), o0 = c->pending_offsets.size();
+    op->host_draws = true;
+    op->draws_begin = d0;
+    op->draw_stride = stride;
+    op->offsets_begin = ellipsoid ? o0 : SIZE_MAX;
+    std::vector<int32_t>& out = c->pending_draws;
+    if (!ellipsoid)
+    {
+        out.resize(d0 + (size_t)n * stride);
+        for (size_t i = d0; i < out.size(); ++i) out[i] = src.next();
+    }
+    else
+    {
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            c->pending_offsets.push_back((uint32_t)(out.size() - d0));
+            for (int k = 0; k < 14; ++k) out.push_back(src.next());
+            while (true)
+            {
+                const int32_t rx = src.next(), ry = src.next(), rz = src.next();
+                out.push_back(rx);
+                out.push_back(ry);
+                out.push_back(rz);
+                if (src.underflow || t3d_host_ellipsoid_accept(rx, ry, rz)) break; // PE.cpp:636-641
+            }
+            for (uint32_t k = 0; k < 9u + (fro > 0 ? 1u : 0u); ++k) out.push_back(src.next());
+        }
+    }
+    if (src.underflow)
+    {
+        out.resize(d0);
+        c->pending_offsets.resize(o0);
+        e->fed_head = fed_head0;
+        return fail(T3D_ERR_RNG_UNDERFLOW, "T3D_RNG_STREAM: %u particles need more draws than were fed", n);
+    }
+    op->draws_count = out.size() - d0;
+    // Drop consumed draws from the front of the queue now and then.
+    if (e->fed_head > (1u << 20) && e->fed_head * 2 > e->fed.size())
+    {
+        e->fed.erase(e->fed.begin(), e->fed.begin() + (ptrdiff_t)e->fed_head);
+        e->fed_head = 0;
+    }
+    return T3D_OK;
+}
+
+// Common part of emitOnce, direct or from update (PE.cpp:287-306): clamp, capture the node matrix, source the draws.
+static int prepare_emit(t3d_emitter* e, uint32_t n, PendingOp* op)
+{
+    if (!e->has_node) return fail(T3D_ERR_NO_NODE, "emitOnce: the emitter has no node world matrix (PE.cpp:289)");
+    const uint32_t cap = e->p.particle_count_max;
+    // Particles spawned from now on carry the current rotation settings.
+    if (e->p.rotation_speed_min != 0.0f || e->p.rotation_speed_max != 0.0f)
+    {
+        if (!e->may_rotate) e->const_dirty = true;
+        e->may_rotate = true;
+    }
+    if (e->p.rotation_per_particle_speed_min != 0.0f || e->p.rotation_per_particle_speed_max != 0.0f)
+    {
+        if (!e->may_spin) e->const_dirty = true;
+        e->may_spin = true;
+    }
+    memcpy(op->world, e->node_world, sizeof(op->world));
+    op->host_draws = false;
+    op->draws_begin = op->draws_count = 0;
+    op->offsets_begin = SIZE_MAX;
+    op->draw_stride = 0;
+    if (e->rng_mode == T3D_RNG_DEVICE)
+    {
+        // The kernel clamps against the live count it reads (PE.cpp:293-296); the host keeps an upper bound.
+        op->emit_n = n;
+        const uint64_t ub = (uint64_t)e->count_ub + n;
+        e->count_ub = (uint32_t)std::min<uint64_t>(ub, cap);
+        return T3D_OK;
+    }
+    // Host draws: the reference consumes draws only for particles that fit, so the clamp must be exact here.
+    if ((uint64_t)e->count_ub + n > cap)
+    {
+        uint32_t cnt;
+        T3D_TRY(exact_count(e, &cnt));
+        if ((uint64_t)cnt + n > cap) n = cap - cnt;
+    }
+    op->emit_n = n;
+    if (n)
+    {
+        T3D_TRY(collect_host_draws(e, n, op));
+        e->count_ub += n;
+    }
+    return T3D_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// C ABI
+// --------------------------------------------------------------------------------------------------
+extern "C" {
+
+int t3d_abi_version(void) { return T3D_ABI_VERSION; }
+const char* t3d_last_error(void) { return g_last_error.c_str(); }
+
+int t3d_ctx_create(int device, void* cuda_stream, t3d_ctx** out)
+{
+    if (!out) return fail(T3D_ERR_INVALID, "t3d_ctx_create: out is null");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t err = cudaGetDeviceCount(&n_dev);
+    if (err != cudaSuccess || n_dev == 0)
+        return fail(T3D_ERR_CUDA, "no CUDA device available (%s); this backend has no CPU fallback",
+                    err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0");
+    if (device < 0 || device >= n_dev) return fail(T3D_ERR_INVALID, "t3d_ctx_create: device %d out of range (0..%d)", device, n_dev - 1);
+    T3D_CUDA(cudaSetDevice(device));
+    t3d_ctx* c = new t3d_ctx();
+    c->device = device;
+    if (cuda_stream)
+        c->stream = (cudaStream_t)cuda_stream;
+    else
+    {
+        cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e2 != cudaSuccess)
+        {
+            delete c;
+            return fail(T3D_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e2));
+        }
+        c->own_stream = true;
+    }
+    if (cudaMalloc((void**)&c->ticket, sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemsetAsync(c->ticket, 0, sizeof(uint32_t), c->stream) != cudaSuccess ||
+        cudaMalloc((void**)&c->frozen_dev, sizeof(FrozenRotation)) != cudaSuccess ||
+        cudaMemsetAsync(c->frozen_dev, 0, sizeof(FrozenRotation), c->stream) != cudaSuccess)
+    {
+        delete c;
+        return fail(T3D_ERR_CUDA, "t3d_ctx_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    memset(c->frozen_m, 0, sizeof(c->frozen_m));
+    *out = c;
+    return T3D_OK;
+}
+
+int t3d_ctx_destroy(t3d_ctx* c)
+{
+    if (!c) return T3D_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    std::vector<t3d_emitter*> es = c->emitters;
+    for (t3d_emitter* e : es) t3d_emitter_destroy(e);
+    for (Slab& s : c->slabs)
+    {
+        if (s.cols) cudaFree(s.cols);
+        if (s.vtx) cudaFree(s.vtx);
+    }
+    for (EmitterDev* d : c->dev_chunks) cudaFree(d);
+    for (StagingSlot& s : c->staging)
+    {
+        if (s.host) cudaFreeHost(s.host);
+        if (s.dev) cudaFree(s.dev);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    if (c->tile_status) cudaFree(c->tile_status);
+    if (c->ticket) cudaFree(c->ticket);
+    if (c->frozen_dev) cudaFree(c->frozen_dev);
+    if (c->readback_host) cudaFreeHost(c->readback_host);
+    if (c->readback_dev) cudaFree(c->readback_dev);
+    for (int k = 0; k < 3; ++k)
+    {
+        if (c->ev_start[k]) cudaEventDestroy(c->ev_start[k]);
+        if (c->ev_stop[k]) cudaEventDestroy(c->ev_stop[k]);
+    }
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return T3D_OK;
+}
+
+int t3d_ctx_flush(t3d_ctx* c)
+{
+    if (!c) return fail(T3D_ERR_INVALID, "null context");
+    return flush(c);
+}
+
+int t3d_ctx_sync(t3d_ctx* c)
+{
+    if (!c) return fail(T3D_ERR_INVALID, "null context");
+    T3D_TRY(flush(c));
+    T3D_TRY(use_device(c));
+    T3D_CUDA(cudaStreamSynchronize(c->stream));
+    return T3D_OK;
+}
+
+int t3d_ctx_set_rotation_mode(t3d_ctx* c, int mode)
+{
+    if (!c || (mode != T3D_ROT_FROZEN && mode != T3D_ROT_PER_PARTICLE)) return fail(T3D_ERR_INVALID, "bad rotation mode %d", mode);
+    T3D_TRY(flush(c));
+    c->rot_mode = mode;
+    return T3D_OK;
+}
+
+int t3d_ctx_set_frozen_rotation(t3d_ctx* c, const float u[3], float angle)
+{
+    if (!c || !u) return fail(T3D_ERR_INVALID, "null argument");
+    T3D_TRY(flush(c));
+    T3D_TRY(use_device(c));
+    host_create_rotation(u, angle, c->frozen_m);
+    c->frozen_latched = true;
+    return upload_frozen(c);
+}
+
+int t3d_ctx_get_frozen_rotation(t3d_ctx* c, float m[16], int* latched)
+{
+    if (!c) return fail(T3D_ERR_INVALID, "null context");
+    T3D_TRY(flush(c));
+    if (m) memcpy(m, c->frozen_m, sizeof(c->frozen_m));
+    if (latched) *latched = c->frozen_latched ? 1 : 0;
+    return T3D_OK;
+}
+
+int t3d_ctx_reset_statics(t3d_ctx* c)
+{
+    if (!c) return fail(T3D_ERR_INVALID, "null context");
+    T3D_TRY(flush(c));
+    T3D_TRY(use_device(c));
+    c->running_time = 0;
+    c->frozen_latched = false;
+    memset(c->frozen_m, 0, sizeof(c->frozen_m));
+    return upload_frozen(c);
+}
+
+int t3d_ctx_last_kernel_ms(t3d_ctx* c, int which, float* ms)
+{
+    if (!c || which < 0 || which > 2 || !ms) return fail(T3D_ERR_INVALID, "bad argument");
+    T3D_TRY(flush(c));
+    if (!c->ev_valid[which]) return fail(T3D_ERR_INVALID, "no launch of kind %d has been recorded", which);
+    T3D_CUDA(cudaEventSynchronize(c->ev_stop[which]));
+    T3D_CUDA(cudaEventElapsedTime(ms, c->ev_start[which], c->ev_stop[which]));
+    return T3D_OK;
+}
+
+int t3d_ctx_launch_count(t3d_ctx* c, uint64_t* n)
+{
+    if (!c || !n) return fail(T3D_ERR_INVALID, "null argument");
+    *n = c->launches;
+    return T3D_OK;
+}
+
+int t3d_ctx_transfer_bytes(t3d_ctx* c, uint64_t* h2d, uint64_t* d2h)
+{
+    if (!c) return fail(T3D_ERR_INVALID, "null context");
+    if (h2d) *h2d = c->h2d_bytes;
+    if (d2h) *d2h = c->d2h_bytes;
+    return T3D_OK;
+}
+
+// ---- lifecycle ----
+static void apply_params(t3d_emitter* e, const t3d_emitter_params* p)
+{
+    const uint32_t cap = e->p.particle_count_max;
+    const float tw = e->p.texture_width, th = e->p.texture_height;
+    e->p = *p;
+    e->p.particle_count_max = cap;
+    e->p.texture_width = tw;
+    e->p.texture_height = th;
+    e->time_per_emission = 1000.0f / (float)p->emission_rate;                 // PE.cpp:262-267
+    e->frame_duration_secs = (float)p->sprite_frame_duration / 1000.0f;       // PE.cpp:491-495
+    e->const_dirty = true;
+}
+
+int t3d_emitter_create(t3d_ctx* c, const t3d_emitter_params* p, t3d_emitter** out)
+{
+    if (!c || !p || !out) return fail(T3D_ERR_INVALID, "t3d_emitter_create: null argument");
+    *out = nullptr;
+    if (p->particle_count_max == 0) return fail(T3D_ERR_INVALID, "particle_count_max must be > 0");
+    if (p->emission_rate == 0) return fail(T3D_ERR_INVALID, "emission_rate must be > 0 (PE.cpp:264)");
+    if (!(p->texture_width >= 1.0f) || !(p->texture_height >= 1.0f))
+        return fail(T3D_ERR_INVALID, "texture_width/height must be >= 1 (PE.cpp:54-55)");
+    T3D_TRY(use_device(c));
+    t3d_emitter* e = new t3d_emitter();
+    e->ctx = c;
+    e->p = *p;
+    int rc = alloc_segment(c, p->particle_count_max, &e->slab, &e->seg_offset, &e->seg_capacity);
+    if (rc == T3D_OK) rc = alloc_dev_record(c, &e->dev);
+    if (rc != T3D_OK)
+    {
+        delete e;
+        return rc;
+    }
+    // setTexture, PE.cpp:244-251
+    e->tex_w_ratio = 1.0f / (float)(unsigned int)p->texture_width;
+    e->tex_h_ratio = 1.0f / (float)(unsigned int)p->texture_height;
+    const float full[4] = { 0.0f, 0.0f, p->texture_width, p->texture_height };
+    e->tex_coords.resize(4);
+    t3d_host_sprite_rect_coords(1, full, e->tex_w_ratio, e->tex_h_ratio, e->tex_coords.data());
+    e->frame_count = 1;
+    e->percent_per_frame = 1.0f;
+    apply_params(e, p);
+    memset(e->node_world, 0, sizeof(e->node_world));
+    memset(e->camera_world, 0, sizeof(e->camera_world));
+    c->emitters.push_back(e);
+    *out = e;
+    return T3D_OK;
+}
+
+int t3d_emitter_create_from_file(t3d_ctx* c, const char* url, t3d_emitter** out)
+{
+    if (!c || !url || !out) return fail(T3D_ERR_INVALID, "t3d_emitter_create_from_file: null argument");
+    t3d_emitter_params p;
+    uint32_t frame_count = 0;
+    int sw = 0, sh = 0;
+    char tex[1024];
+    int rc = t3d_particle_file_parse(url, &p, &frame_count, &sw, &sh, tex, sizeof(tex));
+    if (rc != T3D_OK) return fail(rc, "%s", t3d_host_last_error());
+    T3D_TRY(t3d_emitter_create(c, &p, out));
+    // PE.cpp:207
+    return t3d_emitter_set_sprite_frame_coords(*out, frame_count, sw, sh);
+}
+
+int t3d_emitter_clone(t3d_emitter* e, t3d_emitter** out)
+{
+    if (!e || !out) return fail(T3D_ERR_INVALID, "null argument");
+    T3D_TRY(t3d_emitter_create(e->ctx, &e->p, out)); // PE.cpp:894-921
+    t3d_emitter* n = *out;
+    T3D_TRY(t3d_emitter_set_sprite_tex_coords(n, e->frame_count, e->tex_coords.data())); // PE.cpp:922
+    n->rng_mode = e->rng_mode;
+    n->rng_seed = e->rng_seed;
+    return T3D_OK;
+}
+
+int t3d_emitter_destroy(t3d_emitter* e)
+{
+    if (!e) return T3D_OK;
+    t3d_ctx* c = e->ctx;
+    if (e->queued) flush(c);
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (e->uv_dev) cudaFree(e->uv_dev);
+    if (e->dev) c->dev_free.push_back(e->dev);
+    Slab& s = c->slabs[e->slab];
+    if (--s.live_emitters == 0)
+    {
+        // Last emitter of the slab: give the memory back.
+        if (s.cols) cudaFree(s.cols);
+        if (s.vtx) cudaFree(s.vtx);
+        s.cols = nullptr;
+        s.vtx = nullptr;
+        s.capacity = s.used = 0;
+    }
+    c->emitters.erase(std::remove(c->emitters.begin(), c->emitters.end(), e), c->emitters.end());
+    delete e;
+    return T3D_OK;
+}
+
+// ---- configuration ----
+int t3d_emitter_set_params(t3d_emitter* e, const t3d_emitter_params* p)
+{
+    if (!e || !p) return fail(T3D_ERR_INVALID, "null argument");
+    if (p->emission_rate == 0) return fail(T3D_ERR_INVALID, "emission_rate must be > 0 (PE.cpp:264)");
+    if (p->particle_count_max > e->p.particle_count_max)
+        return fail(T3D_ERR_CAPACITY, "particle_count_max cannot grow past the %u fixed at create (asked %u)",
+                    e->p.particle_count_max, p->particle_count_max);
+    if (e->queued) T3D_TRY(flush(e->ctx));
+    apply_params(e, p);
+    return T3D_OK;
+}
+
+int t3d_emitter_get_params(t3d_emitter* e, t3d_emitter_params* p)
+{
+    if (!e || !p) return fail(T3D_ERR_INVALID, "null argument");
+    *p = e->p;
+    return T3D_OK;
+}
+
+int t3d_emitter_set_emission_rate(t3d_emitter* e, uint32_t rate)
+{
+    if (!e || rate == 0) return fail(T3D_ERR_INVALID, "emission rate must be > 0 (PE.cpp:264)");
+    e->p.emission_rate = rate;
+    e->time_per_emission = 1000.0f / (float)rate;
+    return T3D_OK;
+}
+
+static int install_tex_coords(t3d_emitter* e, uint32_t frame_count)
+{
+    e->frame_count = frame_count;
+    e->percent_per_frame = 1.0f / (float)frame_count; // PE.cpp:518, 532
+    e->uv_dirty = true;
+    return T3D_OK;
+}
+
+int t3d_emitter_set_sprite_tex_coords(t3d_emitter* e, uint32_t frame_count, const float* tex_coords)
+{
+    if (!e || !frame_count || !tex_coords) return fail(T3D_ERR_INVALID, "setSpriteTexCoords: bad argument (PE.cpp:514-515)");
+    if (e->queued) T3D_TRY(flush(e->ctx));
+    e->tex_coords.assign(tex_coords, tex_coords + (size_t)frame_count * 4);
+    return install_tex_coords(e, frame_count);
+}
+
+int t3d_emitter_set_sprite_frame_rects(t3d_emitter* e, uint32_t frame_count, const float* rects)
+{
+    if (!e || !frame_count || !rects) return fail(T3D_ERR_INVALID, "setSpriteFrameCoords: bad argument (PE.cpp:528-529)");
+    if (e->queued) T3D_TRY(flush(e->ctx));
+    e->tex_coords.resize((size_t)frame_count * 4);
+    t3d_host_sprite_rect_coords(frame_count, rects, e->tex_w_ratio, e->tex_h_ratio, e->tex_coords.data());
+    return install_tex_coords(e, frame_count);
+}
+
+int t3d_emitter_set_sprite_frame_coords(t3d_emitter* e, uint32_t frame_count, int width, int height)
+{
+    if (!e || !frame_count || !width || !height) return fail(T3D_ERR_INVALID, "setSpriteFrameCoords: bad argument (PE.cpp:552-553)");
+    if (e->queued) T3D_TRY(flush(e->ctx));
+    e->tex_coords.resize((size_t)frame_count * 4);
+    t3d_host_sprite_frame_coords(frame_count, width, height, e->p.texture_width, e->p.texture_height, e->tex_coords.data());
+    return install_tex_coords(e, frame_count);
+}
+
+int t3d_emitter_get_sprite_tex_coords(t3d_emitter* e, uint32_t* frame_count, float* tex_coords, size_t max_frames)
+{
+    if (!e) return fail(T3D_ERR_INVALID, "null emitter");
+    if (frame_count) *frame_count = e->frame_count;
+    if (tex_coords) memcpy(tex_coords, e->tex_coords.data(), sizeof(float) * 4 * std::min<size_t>(max_frames, e->frame_count));
+    return T3D_OK;
+}
+
+int t3d_emitter_set_rng(t3d_emitter* e, int mode, uint64_t seed)
+{
+    if (!e || mode < T3D_RNG_LIBC || mode > T3D_RNG_DEVICE) return fail(T3D_ERR_INVALID, "bad rng mode %d", mode);
+    if (e->queued) T3D_TRY(flush(e->ctx));
+    e->rng_mode = mode;
+    e->rng_seed = seed;
+    e->const_dirty = true;
+    return T3D_OK;
+}
+
+int t3d_emitter_feed_draws(t3d_emitter* e, const int32_t* draws, size_t n)
+{
+    if (!e || (!draws && n)) return fail(T3D_ERR_INVALID, "null argument");
+    e->fed.insert(e->fed.end(), draws, draws + n);
+    return T3D_OK;
+}
+
+int t3d_emitter_pending_draws(t3d_emitter* e, size_t* n)
+{
+    if (!e || !n) return fail(T3D_ERR_INVALID, "null argument");
+    *n = e->fed.size() - e->fed_head;
+    return T3D_OK;
+}
+
+int t3d_emitter_set_node_world(t3d_emitter* e, const float world[16])
+{
+    if (!e || !world) return fail(T3D_ERR_INVALID, "null argument");
+    memcpy(e->node_world, world, sizeof(e->node_world));
+    e->has_node = true;
+    return T3D_OK;
+}
+
+int t3d_emitter_set_camera_world(t3d_emitter* e, const float m[16])
+{
+    if (!e || !m) return fail(T3D_ERR_INVALID, "null argument");
+    memcpy(e->camera_world, m, sizeof(e->camera_world));
+    e->has_camera = true;
+    return T3D_OK;
+}
+
+// ---- the path ----
+int t3d_emitter_start(t3d_emitter* e)
+{
+    if (!e) return fail(T3D_ERR_INVALID, "null emitter");
+    e->started = true; // PE.cpp:270-274 (does not reset _emitTime)
+    return T3D_OK;
+}
+
+int t3d_emitter_stop(t3d_emitter* e)
+{
+    if (!e) return fail(T3D_ERR_INVALID, "null emitter");
+    e->started = false;
+    return T3D_OK;
+}
+
+int t3d_emitter_is_started(t3d_emitter* e, int* out)
+{
+    if (!e || !out) return fail(T3D_ERR_INVALID, "null argument");
+    *out = e->started ? 1 : 0;
+    return T3D_OK;
+}
+
+static int is_active(t3d_emitter* e, bool* out)
+{
+    // PE.cpp:277-284
+    if (e->started)
+    {
+        *out = true;
+        return T3D_OK;
+    }
+    if (!e->has_node || e->count_ub == 0)
+    {
+        *out = false;
+        return T3D_OK;
+    }
+    uint32_t cnt;
+    T3D_TRY(exact_count(e, &cnt));
+    *out = cnt > 0;
+    return T3D_OK;
+}
+
+int t3d_emitter_is_active(t3d_emitter* e, int* out)
+{
+    if (!e || !out) return fail(T3D_ERR_INVALID, "null argument");
+    bool a;
+    T3D_TRY(is_active(e, &a));
+    *out = a ? 1 : 0;
+    return T3D_OK;
+}
+
+int t3d_emitter_emit_once(t3d_emitter* e, uint32_t particle_count)
+{
+    if (!e) return fail(T3D_ERR_INVALID, "null emitter");
+    t3d_ctx* c = e->ctx;
+    if (c->phase != PHASE_EMIT || e->queued) T3D_TRY(flush(c));
+    PendingOp op{};
+    op.e = e;
+    T3D_TRY(prepare_emit(e, particle_count, &op));
+    if (op.emit_n == 0) return T3D_OK;
+    return enqueue(c, PHASE_EMIT, op);
+}
+
+int t3d_emitter_update(t3d_emitter* e, float elapsed_time)
+{
+    if (!e) return fail(T3D_ERR_INVALID, "null emitter");
+    t3d_ctx* c = e->ctx;
+    bool active;
+    T3D_TRY(is_active(e, &active));
+    if (!active) return T3D_OK; // PE.cpp:715
+    float elapsed_ms;
+    if (!t3d_host_rate_cap(&c->running_time, elapsed_time, &elapsed_ms)) return T3D_OK; // PE.cpp:720-725
+    if (c->phase != PHASE_UPDATE || e->queued) T3D_TRY(flush(c));
+    PendingOp op{};
+    op.e = e;
+    op.elapsed_ms = elapsed_ms;
+    op.offsets_begin = SIZE_MAX;
+    if (e->started && e->p.emission_rate)
+    {
+        const uint32_t emit_count = t3d_host_emission_count(&e->emit_time, e->time_per_emission, elapsed_ms); // PE.cpp:732-743
+        if (emit_count) T3D_TRY(prepare_emit(e, emit_count, &op));                                            // PE.cpp:744
+    }
+    if (e->count_ub > 0) e->count_exact = false; // particles may die in the kernel; the bound stays valid
+    return enqueue(c, PHASE_UPDATE, op);
+}
+
+int t3d_emitter_draw(t3d_emitter* e, uint32_t* draw_calls)
+{
+    if (!e) return fail(T3D_ERR_INVALID, "null emitter");
+    t3d_ctx* c = e->ctx;
+    if (draw_calls) *draw_calls = 0;
+    bool active;
+    T3D_TRY(is_active(e, &active));
+    e->last_draw_empty = true;
+    if (!active) return T3D_OK; // PE.cpp:837
+    if (draw_calls) *draw_calls = 1;
+    if (e->count_ub == 0) return T3D_OK; // PE.cpp:839
+    if (!e->has_node || !e->has_camera)
+        return fail(T3D_ERR_NO_NODE, "draw: the emitter needs a node and an active camera node (PE.cpp:858-859)");
+    PendingOp op{};
+    op.e = e;
+    op.offsets_begin = SIZE_MAX;
+    // PE.cpp:860-864: right = (m0, m1, m2), up = (m4, m5, m6) of the camera node's world matrix.
+    op.right[0] = e->camera_world[0]; op.right[1] = e->camera_world[1]; op.right[2] = e->camera_world[2];
+    op.up[0] = e->camera_world[4]; op.up[1] = e->camera_world[5]; op.up[2] = e->camera_world[6];
+    e->last_draw_empty = false;
+    return enqueue(c, PHASE_DRAW, op);
+}
+
+int t3d_emitter_get_count(t3d_emitter* e, uint32_t* count)
+{
+    if (!e || !count) return fail(T3D_ERR_INVALID, "null argument");
+    return refresh_counts(e->ctx, &e, 1, count, nullptr);
+}
+
+// ---- batches ----
+int t3d_batch_update(t3d_emitter* const* es, size_t n, float elapsed_ms)
+{
+    if (!es && n) return fail(T3D_ERR_INVALID, "null argument");
+    for (size_t i = 0; i < n; ++i) T3D_TRY(t3d_emitter_update(es[i], elapsed_ms));
+    return T3D_OK;
+}
+
+int t3d_batch_draw(t3d_emitter* const* es, size_t n)
+{
+    if (!es && n) return fail(T3D_ERR_INVALID, "null argument");
+    for (size_t i = 0; i < n; ++i) T3D_TRY(t3d_emitter_draw(es[i], nullptr));
+    return T3D_OK;
+}
+
+int t3d_batch_emit_once(t3d_emitter* const* es, size_t n, const uint32_t* counts)
+{
+    if ((!es || !counts) && n) return fail(T3D_ERR_INVALID, "null argument");
+    for (size_t i = 0; i < n; ++i) T3D_TRY(t3d_emitter_emit_once(es[i], counts[i]));
+    return T3D_OK;
+}
+
+int t3d_batch_get_counts(t3d_emitter* const* es, size_t n, uint32_t* counts)
+{
+    if ((!es || !counts) && n) return fail(T3D_ERR_INVALID, "null argument");
+    if (n == 0) return T3D_OK;
+    t3d_ctx* c = es[0]->ctx;
+    for (size_t i = 0; i < n; ++i)
+        if (es[i]->ctx != c) return fail(T3D_ERR_INVALID, "t3d_batch_get_counts: emitters belong to different contexts");
+    return refresh_counts(c, es, n, counts, nullptr);
+}
+
+// ---- results ----
+int t3d_emitter_vertices(t3d_emitter* e, const t3d_sprite_vertex** device_ptr, uint32_t* n_quads)
+{
+    if (!e) return fail(T3D_ERR_INVALID, "null emitter");
+    t3d_ctx* c = e->ctx;
+    uint32_t cnt, drawn;
+    T3D_TRY(refresh_counts(c, &e, 1, &cnt, &drawn));
+    const Slab& s = c->slabs[e->slab];
+    if (device_ptr)
+        *device_ptr = s.vtx ? reinterpret_cast<const t3d_sprite_vertex*>(s.vtx + (size_t)e->seg_offset * T3D_FLOATS_PER_QUAD) : nullptr;
+    if (n_quads) *n_quads = (s.vtx && !e->last_draw_empty) ? drawn : 0;
+    return T3D_OK;
+}
+
+int t3d_emitter_download_vertices(t3d_emitter* e, float* out, size_t max_quads, uint32_t* n_quads)
+{
+    if (!e) return fail(T3D_ERR_INVALID, "null emitter");
+    const t3d_sprite_vertex* dev;
+    uint32_t n;
+    T3D_TRY(t3d_emitter_vertices(e, &dev, &n));
+    if (n_quads) *n_quads = n;
+    const size_t m = std::min<size_t>(n, max_quads);
+    if (out && m)
+    {
+        t3d_ctx* c = e->ctx;
+        T3D_CUDA(cudaMemcpyAsync(out, dev, m * T3D_FLOATS_PER_QUAD * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        T3D_CUDA(cudaStreamSynchronize(c->stream));
+        c->d2h_bytes += m * T3D_FLOATS_PER_QUAD * sizeof(float);
+    }
+    return T3D_OK;
+}
+
+int t3d_emitter_download_state(t3d_emitter* e, uint32_t* out, size_t stride, uint32_t* count)
+{
+    if (!e) return fail(T3D_ERR_INVALID, "null emitter");
+    t3d_ctx* c = e->ctx;
+    uint32_t n;
+    T3D_TRY(refresh_counts(c, &e, 1, &n, nullptr));
+    if (count) *count = n;
+    if (!out || n == 0) return T3D_OK;
+    if (stride < n) return fail(T3D_ERR_INVALID, "download_state: stride %zu < live count %u", stride, n);
+    const Slab& s = c->slabs[e->slab];
+    T3D_CUDA(cudaMemcpy2DAsync(out, stride * sizeof(uint32_t), s.cols + e->seg_offset, (size_t)s.capacity * sizeof(uint32_t),
+                               (size_t)n * sizeof(uint32_t), T3D_NUM_COLUMNS, cudaMemcpyDeviceToHost, c->stream));
+    T3D_CUDA(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += (size_t)n * T3D_NUM_COLUMNS * sizeof(uint32_t);
+    return T3D_OK;
+}
+
+int t3d_emitter_upload_state(t3d_emitter* e, const uint32_t* in, size_t stride, uint32_t count)
+{
+    if (!e || (!in && count)) return fail(T3D_ERR_INVALID, "null argument");
+    if (count > e->p.particle_count_max) return fail(T3D_ERR_CAPACITY, "upload_state: %u particles exceed capacity %u", count, e->p.particle_count_max);
+    if (stride < count) return fail(T3D_ERR_INVALID, "upload_state: stride %zu < count %u", stride, count);
+    t3d_ctx* c = e->ctx;
+    T3D_TRY(flush(c));
+    T3D_TRY(use_device(c));
+    const Slab& s = c->slabs[e->slab];
+    if (count)
+        T3D_CUDA(cudaMemcpy2DAsync(s.cols + e->seg_offset, (size_t)s.capacity * sizeof(uint32_t), in, stride * sizeof(uint32_t),
+                                   (size_t)count * sizeof(uint32_t), T3D_NUM_COLUMNS, cudaMemcpyHostToDevice, c->stream));
+    T3D_CUDA(cudaMemcpyAsync(&e->dev->cnt[e->parity].count, &count, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    T3D_CUDA(cudaStreamSynchronize(c->stream));
+    c->h2d_bytes += (size_t)count * T3D_NUM_COLUMNS * sizeof(uint32_t) + sizeof(uint32_t);
+    e->count_ub = count;
+    e->count_exact = true;
+    // Uploaded particles may carry any rotation state.
+    e->may_rotate = e->may_spin = true;
+    e->const_dirty = true;
+    return T3D_OK;
+}
+
+} // extern "C"

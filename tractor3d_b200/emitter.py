@@ -1,0 +1,331 @@
+"""Python mirror of the reference's ParticleEmitter public interface over the C ABI.
+
+Method names and argument meaning follow Tractor3Dlib/include/graphics/ParticleEmitter.h:179-733
+(camelCase kept so parity tests read like calls on the reference class).  Every call goes through
+libt3d_particles.so; nothing here computes particle state.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+_P = C.POINTER
+IDENTITY = np.eye(4, dtype=np.float32).reshape(16)
+
+
+class T3DError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"t3d error {code}: {message}")
+        self.code = code
+
+
+def _check(lib, rc):
+    if rc != abi.OK:
+        raise T3DError(rc, lib.t3d_last_error().decode(errors="replace"))
+
+
+def _fptr(a):
+    return a.ctypes.data_as(_P(C.c_float))
+
+
+class Context:
+    """One per GPU (t3d_ctx).  `stream` may be a raw cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = abi.load()
+        self.h = C.c_void_p()
+        _check(self.lib, self.lib.t3d_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self.h)))
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.lib.t3d_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def flush(self):
+        _check(self.lib, self.lib.t3d_ctx_flush(self.h))
+
+    def sync(self):
+        _check(self.lib, self.lib.t3d_ctx_sync(self.h))
+
+    def set_rotation_mode(self, mode):
+        _check(self.lib, self.lib.t3d_ctx_set_rotation_mode(self.h, mode))
+
+    def set_frozen_rotation(self, u, angle):
+        a = np.ascontiguousarray(u, dtype=np.float32)
+        _check(self.lib, self.lib.t3d_ctx_set_frozen_rotation(self.h, _fptr(a), angle))
+
+    def frozen_rotation(self):
+        m = np.zeros(16, dtype=np.float32)
+        latched = C.c_int()
+        _check(self.lib, self.lib.t3d_ctx_get_frozen_rotation(self.h, _fptr(m), C.byref(latched)))
+        return m, bool(latched.value)
+
+    def reset_statics(self):
+        _check(self.lib, self.lib.t3d_ctx_reset_statics(self.h))
+
+    def last_kernel_ms(self, which):
+        ms = C.c_float()
+        _check(self.lib, self.lib.t3d_ctx_last_kernel_ms(self.h, which, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_uint64()
+        _check(self.lib, self.lib.t3d_ctx_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def transfer_bytes(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(self.lib, self.lib.t3d_ctx_transfer_bytes(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # -- batches --
+    @staticmethod
+    def _handles(emitters):
+        arr = (C.c_void_p * len(emitters))(*[e.h for e in emitters])
+        return arr
+
+    def batch_update(self, emitters, elapsed_ms, handles=None):
+        h = handles if handles is not None else self._handles(emitters)
+        _check(self.lib, self.lib.t3d_batch_update(h, len(h), elapsed_ms))
+
+    def batch_draw(self, emitters, handles=None):
+        h = handles if handles is not None else self._handles(emitters)
+        _check(self.lib, self.lib.t3d_batch_draw(h, len(h)))
+
+    def batch_emit_once(self, emitters, counts, handles=None):
+        h = handles if handles is not None else self._handles(emitters)
+        c = np.ascontiguousarray(counts, dtype=np.uint32)
+        _check(self.lib, self.lib.t3d_batch_emit_once(h, len(h), c.ctypes.data_as(_P(C.c_uint32))))
+
+    def batch_counts(self, emitters, handles=None):
+        h = handles if handles is not None else self._handles(emitters)
+        out = np.zeros(len(h), dtype=np.uint32)
+        _check(self.lib, self.lib.t3d_batch_get_counts(h, len(h), out.ctypes.data_as(_P(C.c_uint32))))
+        return out
+
+
+class ParticleEmitter:
+    """Drop-in for tractor::ParticleEmitter.  A fresh emitter is attached to an identity node and looks
+    through an identity camera node (what the reference takes from Node / Scene, PE.cpp:299, 860-861)."""
+
+    BLEND_NONE, BLEND_ALPHA, BLEND_ADDITIVE, BLEND_MULTIPLIED = range(4)
+
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.h = handle
+        self.set_node_world(IDENTITY)
+        self.set_camera_world(IDENTITY)
+
+    # -- creation (ParticleEmitter.h:179-205) --
+    @classmethod
+    def create(cls, ctx, params, sprite=None, rng=(abi.RNG_LIBC, 0)):
+        h = C.c_void_p()
+        _check(ctx.lib, ctx.lib.t3d_emitter_create(ctx.h, C.byref(params), C.byref(h)))
+        e = cls(ctx, h)
+        if sprite:
+            e.setSpriteFrameCoords(*sprite)
+        e.set_rng(*rng)
+        return e
+
+    @classmethod
+    def create_from_file(cls, ctx, url, rng=(abi.RNG_LIBC, 0)):
+        h = C.c_void_p()
+        _check(ctx.lib, ctx.lib.t3d_emitter_create_from_file(ctx.h, url.encode(), C.byref(h)))
+        e = cls(ctx, h)
+        e.set_rng(*rng)
+        return e
+
+    def clone(self):
+        h = C.c_void_p()
+        _check(self.lib, self.lib.t3d_emitter_clone(self.h, C.byref(h)))
+        return ParticleEmitter(self.ctx, h)
+
+    def release(self):
+        if self.h:
+            self.lib.t3d_emitter_destroy(self.h)
+            self.h = C.c_void_p()
+
+    # -- configuration --
+    def params(self):
+        p = abi.EmitterParams()
+        _check(self.lib, self.lib.t3d_emitter_get_params(self.h, C.byref(p)))
+        return p
+
+    def set_params(self, p):
+        _check(self.lib, self.lib.t3d_emitter_set_params(self.h, C.byref(p)))
+
+    def _edit(self, **kw):
+        p = self.params()
+        for k, v in kw.items():
+            if isinstance(v, (list, tuple, np.ndarray)):
+                typ = dict(abi.EmitterParams._fields_)[k]
+                setattr(p, k, typ(*[float(x) for x in v]))
+            else:
+                setattr(p, k, v)
+        self.set_params(p)
+
+    def getParticleCountMax(self):
+        return self.params().particle_count_max
+
+    def setEmissionRate(self, rate):
+        _check(self.lib, self.lib.t3d_emitter_set_emission_rate(self.h, rate))
+
+    def getEmissionRate(self):
+        return self.params().emission_rate
+
+    def setEllipsoid(self, v):
+        self._edit(ellipsoid=int(bool(v)))
+
+    def setSize(self, start_min, start_max, end_min, end_max):
+        self._edit(size_start_min=start_min, size_start_max=start_max, size_end_min=end_min, size_end_max=end_max)
+
+    def setEnergy(self, energy_min, energy_max):
+        # ParticleEmitter::setEnergy takes long and stores float (PE.cpp:381-385).
+        self._edit(energy_min=float(int(energy_min)), energy_max=float(int(energy_max)))
+
+    def setColor(self, start, start_var, end, end_var):
+        self._edit(color_start=start, color_start_var=start_var, color_end=end, color_end_var=end_var)
+
+    def setPosition(self, position, variance):
+        self._edit(position=position, position_var=variance)
+
+    def setVelocity(self, velocity, variance):
+        self._edit(velocity=velocity, velocity_var=variance)
+
+    def setAcceleration(self, acceleration, variance):
+        self._edit(acceleration=acceleration, acceleration_var=variance)
+
+    def setRotationPerParticle(self, speed_min, speed_max):
+        self._edit(rotation_per_particle_speed_min=speed_min, rotation_per_particle_speed_max=speed_max)
+
+    def setRotation(self, speed_min, speed_max, axis, axis_var):
+        self._edit(rotation_speed_min=speed_min, rotation_speed_max=speed_max, rotation_axis=axis, rotation_axis_var=axis_var)
+
+    def setSpriteAnimated(self, v):
+        self._edit(sprite_animated=int(bool(v)))
+
+    def setSpriteLooped(self, v):
+        self._edit(sprite_looped=int(bool(v)))
+
+    def setSpriteFrameRandomOffset(self, v):
+        self._edit(sprite_frame_random_offset=int(v))
+
+    def setSpriteFrameDuration(self, ms):
+        self._edit(sprite_frame_duration=int(ms))
+
+    def setOrbit(self, position, velocity, acceleration):
+        self._edit(orbit_position=int(bool(position)), orbit_velocity=int(bool(velocity)), orbit_acceleration=int(bool(acceleration)))
+
+    def setBlendMode(self, mode):
+        self._edit(blend_mode=int(mode))
+
+    def setSpriteTexCoords(self, tex_coords):
+        a = np.ascontiguousarray(tex_coords, dtype=np.float32).reshape(-1)
+        _check(self.lib, self.lib.t3d_emitter_set_sprite_tex_coords(self.h, a.size // 4, _fptr(a)))
+
+    def setSpriteFrameRects(self, rects):
+        a = np.ascontiguousarray(rects, dtype=np.float32).reshape(-1)
+        _check(self.lib, self.lib.t3d_emitter_set_sprite_frame_rects(self.h, a.size // 4, _fptr(a)))
+
+    def setSpriteFrameCoords(self, frame_count, width, height):
+        _check(self.lib, self.lib.t3d_emitter_set_sprite_frame_coords(self.h, frame_count, width, height))
+
+    def getSpriteFrameCount(self):
+        n = C.c_uint32()
+        _check(self.lib, self.lib.t3d_emitter_get_sprite_tex_coords(self.h, C.byref(n), None, 0))
+        return n.value
+
+    def sprite_tex_coords(self):
+        n = self.getSpriteFrameCount()
+        out = np.zeros(n * 4, dtype=np.float32)
+        _check(self.lib, self.lib.t3d_emitter_get_sprite_tex_coords(self.h, None, _fptr(out), n))
+        return out.reshape(n, 4)
+
+    def set_rng(self, mode, seed=0):
+        _check(self.lib, self.lib.t3d_emitter_set_rng(self.h, mode, seed))
+
+    def feed_draws(self, draws):
+        a = np.ascontiguousarray(draws, dtype=np.int32)
+        _check(self.lib, self.lib.t3d_emitter_feed_draws(self.h, a.ctypes.data_as(_P(C.c_int32)), a.size))
+
+    def pending_draws(self):
+        n = C.c_size_t()
+        _check(self.lib, self.lib.t3d_emitter_pending_draws(self.h, C.byref(n)))
+        return n.value
+
+    def set_node_world(self, m):
+        a = np.ascontiguousarray(m, dtype=np.float32).reshape(16)
+        _check(self.lib, self.lib.t3d_emitter_set_node_world(self.h, _fptr(a)))
+
+    def set_camera_world(self, m):
+        a = np.ascontiguousarray(m, dtype=np.float32).reshape(16)
+        _check(self.lib, self.lib.t3d_emitter_set_camera_world(self.h, _fptr(a)))
+
+    # -- the path --
+    def start(self):
+        _check(self.lib, self.lib.t3d_emitter_start(self.h))
+
+    def stop(self):
+        _check(self.lib, self.lib.t3d_emitter_stop(self.h))
+
+    def isStarted(self):
+        v = C.c_int()
+        _check(self.lib, self.lib.t3d_emitter_is_started(self.h, C.byref(v)))
+        return bool(v.value)
+
+    def isActive(self):
+        v = C.c_int()
+        _check(self.lib, self.lib.t3d_emitter_is_active(self.h, C.byref(v)))
+        return bool(v.value)
+
+    def emitOnce(self, n):
+        _check(self.lib, self.lib.t3d_emitter_emit_once(self.h, n))
+
+    def update(self, elapsed_ms):
+        _check(self.lib, self.lib.t3d_emitter_update(self.h, elapsed_ms))
+
+    def draw(self, wireframe=False):
+        v = C.c_uint32()
+        _check(self.lib, self.lib.t3d_emitter_draw(self.h, C.byref(v)))
+        return v.value
+
+    def getParticlesCount(self):
+        v = C.c_uint32()
+        _check(self.lib, self.lib.t3d_emitter_get_count(self.h, C.byref(v)))
+        return v.value
+
+    # -- results --
+    def state(self):
+        """(NUM_COLUMNS, n) uint32 copy of the live particles (column order of include/t3d_particles.h)."""
+        n = self.getParticlesCount()
+        out = np.zeros((abi.NUM_COLUMNS, max(n, 1)), dtype=np.uint32)
+        cnt = C.c_uint32()
+        _check(self.lib, self.lib.t3d_emitter_download_state(self.h, out.ctypes.data_as(_P(C.c_uint32)), out.shape[1], C.byref(cnt)))
+        return out[:, : cnt.value]
+
+    def upload_state(self, cols):
+        a = np.ascontiguousarray(cols, dtype=np.uint32)
+        assert a.ndim == 2 and a.shape[0] == abi.NUM_COLUMNS
+        _check(self.lib, self.lib.t3d_emitter_upload_state(self.h, a.ctypes.data_as(_P(C.c_uint32)), a.shape[1], a.shape[1]))
+
+    def vertices_device(self):
+        ptr, n = C.c_void_p(), C.c_uint32()
+        _check(self.lib, self.lib.t3d_emitter_vertices(self.h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def vertices(self, out=None):
+        """(n_quads, 4, 9) float32 copy of the vertex stream of the last draw()."""
+        _, n = self.vertices_device()
+        buf = out if out is not None else np.zeros((max(n, 1), 4, 9), dtype=np.float32)
+        got = C.c_uint32()
+        _check(self.lib, self.lib.t3d_emitter_download_vertices(self.h, _fptr(buf), buf.shape[0], C.byref(got)))
+        return buf[: min(got.value, buf.shape[0])]
