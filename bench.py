@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the ParticleEmitter hot path (update + billboard draw per frame) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            the CUDA backend through the C ABI
+    python bench.py --impl reference --gpus N ...            the reference's own CPU path on the host cores
+
+A step is one frame over the whole population: `update(1000/60 ms)` then `draw()` for every emitter
+(PE.cpp:713-888).  Workloads (BASELINE.json configs / SURVEY.md §8(d)):
+    c3  one emitter, 64 Mi particles, ellipsoid spawn, per-particle spin, looped sprite animation (N = 1 default)
+    c4  8 192 emitters x 32 Ki = 256 Mi particles, mixed fire/smoke/explosion sets, emitter e owned by rank e mod N
+        (N > 1 default; strong scaling, no per-frame collective; NCCL only gathers the end-of-run counters)
+    c2  1 024 emitters x 4 Ki (4 Mi particles), mixed sets
+    c5  high churn: 8 emitters per GPU, 1 Mi spawned per frame in total, energies 50..400 ms
+One JSON line is printed by rank 0.  `value` = particles x steps / device time of the timed region with all
+state resident in HBM; `e2e` = the same frames driven call by call through the public ParticleEmitter
+interface with the per-frame host inputs (node and camera matrices, elapsed time) coming from host memory and
+the per-frame results (live count, quad count) read back to the host every frame.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+DT = 1000.0 / 60.0
+MI = 1024 * 1024
+
+# Algorithmic bytes per unit, SURVEY.md Appendix C (materialised colour/size layout actually shipped):
+#   update: energy rw 8 + energyStart 4 + pos rw 24 + vel rw 24 + acc 12 + spin 4 + angle rw 8
+#           + colorStart/End 32 + color w 16 + sizeStart/End 8 + size w 4            = 144 B
+#           + frame rw 8 + timeOnFrame rw 8 when the sprite is animated               = 160 B
+#   draw:   pos 12 + size 4 + color 16 + angle 4 + frame 4 read, 4 x 36 B written     = 184 B
+#   spawn:  34 columns x 4 B written                                                   = 136 B
+UPDATE_BYTES, UPDATE_BYTES_ANIMATED, DRAW_BYTES, SPAWN_BYTES = 144, 160, 184, 136
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, torch copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index, uuid=None):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode()) if uuid else pynvml.nvmlDeviceGetHandleByIndex(index)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    def run(self):
+        if self.nvml is None:
+            return
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# workloads
+# --------------------------------------------------------------------------------------------------
+def build_population(ctx, workload, rank, world, particles):
+    """Creates this rank's emitters and fills them.  Returns (emitters, per_emitter_particles, animated_fraction, name)."""
+    from tractor3d_b200 import abi, presets
+    from tractor3d_b200.emitter import ParticleEmitter
+
+    emitters = []
+    if workload == "c3":
+        n = particles or 64 * MI
+        p, sprite = presets.headline_64m(capacity=n)
+        e = ParticleEmitter.create(ctx, p, sprite, (abi.RNG_DEVICE, 1234 + rank))
+        e.emitOnce(n)
+        emitters.append(e)
+        name = f"c3: 1 emitter x {n} particles, ellipsoid spawn, per-particle spin, looped 4-frame sprite animation"
+        return emitters, n, 1.0, name
+    if workload in ("c4", "c2"):
+        n_emitters, per = (8192, 32 * 1024) if workload == "c4" else (1024, 4096)
+        if particles:
+            per = max(32, particles // n_emitters)
+        animated = 0
+        for eid in range(rank, n_emitters, world):
+            p, sprite = presets.MIXED[eid % 3]()
+            p.particle_count_max = per
+            p.energy_min, p.energy_max = 1.0e6, 2.0e6   # stationary population
+            e = ParticleEmitter.create(ctx, p, sprite, (abi.RNG_DEVICE, eid))
+            emitters.append(e)
+            animated += 1 if p.sprite_animated else 0
+        ctx.batch_emit_once(emitters, [per] * len(emitters))
+        name = (f"{workload}: {n_emitters} emitters x {per} particles, fire/smoke/explosion parameter sets round-robin, "
+                f"emitter e owned by rank e mod {world}")
+        return emitters, per, animated / max(1, len(emitters)), name
+    if workload == "c5":
+        n_em, cap = 8, (particles or 64 * MI) // 8
+        for k in range(n_em):
+            p, sprite = presets.headline_64m(capacity=cap)
+            p.energy_min, p.energy_max = 50.0, 400.0
+            e = ParticleEmitter.create(ctx, p, sprite, (abi.RNG_DEVICE, 77 + rank * n_em + k))
+            emitters.append(e)
+        name = f"c5: {n_em} emitters/GPU, {MI // world} particles spawned per frame per GPU, energies 50..400 ms"
+        return emitters, cap, 1.0, name
+    raise SystemExit(f"unknown workload {workload}")
+
+
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if rank == 0:
+            print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; launch with torchrun --nproc-per-node {args.gpus}", file=sys.stderr)
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(2)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the particle backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from tractor3d_b200 import abi
+    from tractor3d_b200.emitter import Context
+
+    workload = args.workload or ("c3" if world == 1 else "c4")
+    stream = torch.cuda.Stream()
+    ctx = Context(local_rank, stream.cuda_stream)
+    emitters, per, animated_frac, wl_name = build_population(ctx, workload, rank, world, args.particles)
+    handles = Context._handles(emitters)
+    churn = workload == "c5"
+    spawn_per_frame = (MI // world) // len(emitters) if churn else 0
+
+    def frame():
+        if churn:
+            ctx.batch_emit_once(emitters, [spawn_per_frame] * len(emitters), handles)
+        ctx.batch_update(emitters, DT, handles)
+        ctx.batch_draw(emitters, handles)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    counts0 = ctx.batch_counts(emitters, handles)
+    local_particles = int(counts0.sum())
+    for _ in range(max(3, args.warmup)):
+        frame()
+    barrier()
+
+    # ---- timed region: K frames back to back, device time on the launching stream ----
+    sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(local_rank), "uuid", None))
+    sampler.start()
+    t_before = [ctx.kernel_time(k) for k in range(3)]
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            frame()
+        ctx.flush()
+        ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.result()
+    t_after = [ctx.kernel_time(k) for k in range(3)]
+    launches = ctx.launch_count() - launches0
+    counts1 = ctx.batch_counts(emitters, handles)
+    live_after = int(counts1.sum())
+    updates_done = (local_particles if not churn else int((counts0.sum() + counts1.sum()) // 2)) * args.steps
+
+    kern = {}
+    for k, nm in enumerate(("spawn", "update", "draw")):
+        dms, dn = t_after[k][0] - t_before[k][0], t_after[k][1] - t_before[k][1]
+        kern[nm] = {"ms_per_launch": (dms / dn) if dn else None, "launches": int(dn), "ms_total": dms}
+
+    # ---- e2e: the same frames through the per-emitter public calls, host inputs in, host results out, every frame ----
+    import numpy as np
+    e2e_steps = max(3, min(args.steps, 20))
+    nodes = np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (len(emitters), 1))
+    cam = np.eye(4, dtype=np.float32).reshape(16)
+    single = len(emitters) == 1
+    barrier()
+    h2d0, d2h0 = ctx.transfer_bytes()
+    t0 = time.perf_counter()
+    e2e_units = 0
+    for s in range(e2e_steps):
+        nodes[:, 12] = 0.001 * s
+        if single:
+            # exactly the calls a game makes on one emitter (ParticlesSample.cpp:897-898, 916-921)
+            e = emitters[0]
+            e.set_node_world(nodes[0])  # host -> library, every frame (Node::getWorldMatrix, PE.cpp:299)
+            e.set_camera_world(cam)     # (camera node world matrix, PE.cpp:860-861)
+            e.update(DT)
+            e.draw()
+            e2e_units += e.getParticlesCount()   # device -> host: live count (= quads drawn) of this frame
+        else:
+            ctx.batch_set_transforms(emitters, nodes, cam, handles)
+            if churn:
+                ctx.batch_emit_once(emitters, [spawn_per_frame] * len(emitters), handles)
+            ctx.batch_update(emitters, DT, handles)
+            ctx.batch_draw(emitters, handles)
+            c = ctx.batch_counts(emitters, handles)   # device -> host: live counts of this frame
+            e2e_units += int(c.sum())
+    ctx.sync()
+    t_e2e = time.perf_counter() - t0
+    h2d1, d2h1 = ctx.transfer_bytes()
+    matrix_bytes = 2 * 64 * len(emitters)   # the two float[16] the caller hands over per emitter per frame
+
+    # ---- e2e with the vertex stream copied to pinned host memory as well (PCIe-bound; reported for transparency) ----
+    e2e_v = None
+    if args.vertices_to_host and workload == "c3":
+        n = local_particles
+        host = torch.empty((n, 4, 9), dtype=torch.float32, pin_memory=True).numpy()
+        barrier()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            emitters[0].update(DT)
+            emitters[0].draw()
+            emitters[0].vertices(out=host)
+        t_v = time.perf_counter() - t0
+        e2e_v = {"value": n * reps / t_v, "unit": "particles/s", "d2h_bytes_per_step": n * 144, "steps": reps}
+        del host
+
+    # ---- reduce over ranks: max time, sum of work (the only collective, after the run) ----
+    if world > 1:
+        t = torch.tensor([ms_total, t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, t_e2e = float(t[0]), float(t[1])
+        w = torch.tensor([updates_done, e2e_units, local_particles, live_after, launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        updates_done, e2e_units, total_particles, live_after, launches = [int(x) for x in w]
+    else:
+        total_particles = local_particles
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        upd_bytes = UPDATE_BYTES + (UPDATE_BYTES_ANIMATED - UPDATE_BYTES) * animated_frac
+        per_launch_particles = local_particles if not churn else updates_done / args.steps
+        roof = {}
+        for nm, b in (("update", upd_bytes), ("draw", DRAW_BYTES)):
+            ms = kern[nm]["ms_per_launch"]
+            if ms:
+                ach = b * per_launch_particles / (ms * 1e-3) / 1e9
+                roof[nm] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                            "traffic": None, "bytes_per_unit": b, "units_per_launch": per_launch_particles,
+                            "ms_per_launch": ms, "peak_source": peak_src}
+        if churn and kern["spawn"]["ms_per_launch"]:
+            ms = kern["spawn"]["ms_per_launch"]
+            ach = SPAWN_BYTES * spawn_per_frame * len(emitters) / (ms * 1e-3) / 1e9
+            roof["spawn"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "bytes_per_unit": SPAWN_BYTES, "units_per_launch": spawn_per_frame * len(emitters), "ms_per_launch": ms}
+        dominant = max(roof, key=lambda k: kern[k]["ms_total"]) if roof else None
+        value = updates_done / (ms_total * 1e-3)
+        line = {
+            "metric": "particle updates/s (one step = update + billboard draw of every live particle; quads/s is the same number)",
+            "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong" if workload in ("c4", "c2") else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl_name, "particles_total": total_particles, "live_after": live_after,
+                       "dt_ms": DT, "rng": "device counter-based generator (T3D_RNG_DEVICE)",
+                       "rotation_mode": "frozen (reference-identical, SB.cpp:339)",
+                       "l2": "inputs larger than L2 (state + vertex stream >> 126 MB), no flush needed" if total_particles // world * 280 > 512 * MI
+                             else "working set may fit L2; no flush",
+                       "parallelism": f"emitter-ownership sharding x{world}, no per-frame collective"},
+            "quads_per_s": value,
+            "roofline": roof.get(dominant), "roofline_dominant_kernel": dominant, "rooflines": roof,
+            "kernels": kern, "gpu_launches": launches,
+            "e2e": {"value": e2e_units / t_e2e, "unit": "particles/s",
+                    "h2d_bytes_per_step": (h2d1 - h2d0) / e2e_steps + matrix_bytes, "d2h_bytes_per_step": (d2h1 - d2h0) / e2e_steps,
+                    "steps": e2e_steps,
+                    "what": "per-emitter set_node_world/set_camera_world/update/draw calls + live counts read back every frame; "
+                            "the vertex stream stays in HBM for the renderer (the reference hands it to GL, MeshBatch.cpp:299-303)"},
+            "e2e_vertices_to_host": e2e_v,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_single_core(args.cpu_particles)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU legs: the reference's own update()/draw() (oracle/_ref) or, where that was never built, the oracle port
+# --------------------------------------------------------------------------------------------------
+def _cpu_lib():
+    import cpu_harness as H
+    lib = H.ref(fresh=True)
+    return lib if lib is not None else H.oracle(fresh=True)
+
+
+def _cpu_worker(n_particles, frames, seed, q=None):
+    from tractor3d_b200 import presets
+    lib = _cpu_lib()
+    lib.rand_seed(seed)
+    p, sprite = presets.headline_64m(capacity=n_particles)
+    e = lib.emitter(p)
+    e.set_sprite_frame_coords(*sprite)
+    e.emit_once(n_particles)
+    e.update(DT); e.draw()                      # warm-up frame (also latches the frozen rotation)
+    t_u = lib.time_update(e.h, DT, frames)
+    t_d = lib.time_draw(e.h, frames)
+    out = (n_particles * frames, t_u, t_d, lib.kind)
+    if q is not None:
+        q.put(out)
+    return out
+
+
+def cpu_baseline_single_core(n_particles):
+    frames = 30
+    units, t_u, t_d, kind = _cpu_worker(n_particles, frames, 1)
+    return {"value": units / (t_u + t_d), "unit": "particles/s", "cores": 1, "kind": kind,
+            "sample": f"c3 parameters, 1 emitter x {n_particles} particles x {frames} frames of update()+draw(), one host core "
+                      f"(the reference path is single-threaded and non-reentrant)",
+            "update_only": units / t_u, "draw_only": units / t_d}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = min(len(os.sched_getaffinity(0)), 256)
+    n_particles = max(32 * 1024, args.cpu_particles // 4)
+    frames = 8
+    ctxm = mp.get_context("fork")
+    results = []
+    step_times = []
+    for step in range(args.warmup + args.steps):
+        q = ctxm.Queue()
+        procs = [ctxm.Process(target=_cpu_worker, args=(n_particles, frames, 100 + k, q)) for k in range(cores)]
+        for p in procs:
+            p.start()
+        outs = [q.get() for _ in procs]
+        for p in procs:
+            p.join()
+        if step >= args.warmup:
+            units = sum(o[0] for o in outs)
+            t = max(o[1] + o[2] for o in outs)   # slowest process
+            results.append(units / t)
+            step_times.append(t * 1e3)
+    kind = outs[0][3]
+    value = statistics.median(results)
+    line = {
+        "impl": "reference",
+        "metric": "particle updates/s (one step = update + billboard draw of every live particle; quads/s is the same number)",
+        "value": value, "unit": "particles/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": statistics.median(step_times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"c3 parameters; bounded sample: {cores} forked processes (one per host core; threads are invalid: "
+                               f"function-local statics and rand()) x 1 emitter x {n_particles} particles x {frames} frames per step"},
+        "cpu_baseline": {"value": value, "unit": "particles/s", "cores": cores, "kind": kind,
+                         "sample": f"{cores} processes x {n_particles} particles x {frames} frames of update()+draw() per step"},
+        "e2e": {"value": value, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default=None, choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--particles", type=int, default=0, help="override the population size of the workload")
+    ap.add_argument("--cpu-particles", type=int, default=2 * MI, help="population of the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--vertices-to-host", action="store_true", help="also time frames with the vertex stream copied to pinned host memory")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = args.steps if args.steps is not None else 3
+        args.warmup = args.warmup if args.warmup is not None else 1
+        run_reference(args)
+    else:
+        args.steps = args.steps if args.steps is not None else 100
+        args.warmup = args.warmup if args.warmup is not None else 10
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

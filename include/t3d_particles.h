@@ -143,6 +143,9 @@ int t3d_ctx_reset_statics(t3d_ctx* ctx);
 /* Device time in ms of the last flushed launch of each kind (CUDA events on the context's stream):
  * which = 0 spawn, 1 update, 2 draw.  Waits for that launch to finish. */
 int t3d_ctx_last_kernel_ms(t3d_ctx* ctx, int which, float* ms);
+/* Cumulative device time (ms) and number of launches of one kind since the context was created; every
+ * launch is bracketed by its own event pair, so a caller can difference two readings around a timed region. */
+int t3d_ctx_kernel_time(t3d_ctx* ctx, int which, double* total_ms, uint64_t* n_launches);
 /* Number of kernels this library has launched on the context since creation. */
 int t3d_ctx_launch_count(t3d_ctx* ctx, uint64_t* n);
 /* Bytes staged host->device / device->host by the library since creation. */
@@ -194,6 +197,9 @@ int t3d_batch_update(t3d_emitter* const* emitters, size_t n, float elapsed_ms);
 int t3d_batch_draw(t3d_emitter* const* emitters, size_t n);
 int t3d_batch_emit_once(t3d_emitter* const* emitters, size_t n, const uint32_t* particle_counts);
 int t3d_batch_get_counts(t3d_emitter* const* emitters, size_t n, uint32_t* counts);
+/* Per-frame scene inputs for many emitters at once: node_worlds = n x float[16] (or NULL to leave them),
+ * camera_world = one float[16] shared by all (or NULL).  Same meaning as the two per-emitter setters above. */
+int t3d_batch_set_transforms(t3d_emitter* const* emitters, size_t n, const float* node_worlds, const float* camera_world);
 
 /* ---- results ------------------------------------------------------------------------------ */
 /* Device-resident vertex stream of the last draw: 4*n_quads t3d_sprite_vertex, quad i at [4i, 4i+4)

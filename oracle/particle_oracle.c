@@ -530,6 +530,7 @@ static void billboard(const float* pos, const float* right, const float* up, flo
 uint32_t orc_emitter_draw(orc_emitter* e)
 {
     /* PE.cpp:835-888 */
+    e->vertex_quads = 0; /* nothing is submitted unless the batch is started and finished below */
     if (!orc_emitter_is_active(e)) return 0;
     if (e->particle_count > 0) {
         if (e->vertex_cap < e->particle_count) {

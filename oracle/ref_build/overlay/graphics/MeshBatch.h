@@ -1,6 +1,7 @@
 // Overlay stub for graphics/MeshBatch.h: a capture sink. add() keeps the exact bytes SpriteBatch hands
 // over (the reference memcpy's them into a client-side array, MeshBatch.cpp:87-148) so the harness can
-// read back the vertex stream of one draw(); start() clears, finish()/draw() are no-ops (GL dropped).
+// read back the vertex stream of one draw(); start() clears, finish() is a no-op and draw() (GL dropped) only
+// notes that the batch was submitted.
 #pragma once
 #include <cstring>
 #include <vector>
@@ -33,11 +34,12 @@ class MeshBatch
     void start() { _bytes.clear(); _vertexCount = 0; _started = true; }
     bool isStarted() const { return _started; }
     void finish() { _started = false; }
-    void draw() {}
+    void draw() { submitted = true; } // SpriteBatch::finish() -> MeshBatch::draw(): this is where GL would be called
     Material* getMaterial() const { return _material; }
     const std::vector<unsigned char>& capturedBytes() const { return _bytes; }
     size_t capturedVertexCount() const { return _vertexCount; }
     bool discard{ false };
+    bool submitted{ false }; // set when the batch was handed to "GL" since the harness last cleared it
   private:
     Material* _material{ nullptr };
     unsigned int _vertexSize{ 0 };

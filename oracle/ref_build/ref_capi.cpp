@@ -317,7 +317,12 @@ int t3dref_emitter_is_started(void* h) { return ((RefEmitter*)h)->pe->isStarted(
 int t3dref_emitter_is_active(void* h) { return ((RefEmitter*)h)->pe->isActive(); }
 void t3dref_emitter_emit_once(void* h, uint32_t n) { ((RefEmitter*)h)->pe->emitOnce(n); }
 void t3dref_emitter_update(void* h, float elapsed_ms) { ((RefEmitter*)h)->pe->update(elapsed_ms); }
-uint32_t t3dref_emitter_draw(void* h) { return ((RefEmitter*)h)->pe->draw(false); }
+uint32_t t3dref_emitter_draw(void* h)
+{
+    ParticleEmitter* e = ((RefEmitter*)h)->pe;
+    e->_spriteBatch->_batch->submitted = false; // an inactive or empty emitter submits nothing (PE.cpp:837-839)
+    return e->draw(false);
+}
 uint32_t t3dref_emitter_get_count(void* h) { return ((RefEmitter*)h)->pe->getParticlesCount(); }
 
 // Live particles as T3D_NUM_COLUMNS columns of `stride` words (same layout as t3d_emitter_download_state).
@@ -376,7 +381,7 @@ uint32_t t3dref_emitter_get_vertices(void* h, float* out, size_t max_quads)
 {
     ParticleEmitter* e = ((RefEmitter*)h)->pe;
     MeshBatch* mb = e->_spriteBatch->_batch.get();
-    size_t quads = mb->capturedVertexCount() / 4;
+    size_t quads = mb->submitted ? mb->capturedVertexCount() / 4 : 0; // what the last draw() handed to GL
     if (out)
     {
         size_t n = quads < max_quads ? quads : max_quads;

@@ -129,6 +129,7 @@ PROTOTYPES = {
     "t3d_ctx_get_frozen_rotation": (C.c_int, [_vp, _P(C.c_float), _P(C.c_int)]),
     "t3d_ctx_reset_statics": (C.c_int, [_vp]),
     "t3d_ctx_last_kernel_ms": (C.c_int, [_vp, C.c_int, _P(C.c_float)]),
+    "t3d_ctx_kernel_time": (C.c_int, [_vp, C.c_int, _P(C.c_double), _P(C.c_uint64)]),
     "t3d_ctx_launch_count": (C.c_int, [_vp, _P(C.c_uint64)]),
     "t3d_ctx_transfer_bytes": (C.c_int, [_vp, _P(C.c_uint64), _P(C.c_uint64)]),
     "t3d_emitter_create": (C.c_int, [_vp, _P(EmitterParams), _P(_vp)]),
@@ -159,6 +160,7 @@ PROTOTYPES = {
     "t3d_batch_draw": (C.c_int, [_P(_vp), C.c_size_t]),
     "t3d_batch_emit_once": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_uint32)]),
     "t3d_batch_get_counts": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_uint32)]),
+    "t3d_batch_set_transforms": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_float), _P(C.c_float)]),
     "t3d_emitter_vertices": (C.c_int, [_vp, _P(_vp), _P(C.c_uint32)]),
     "t3d_emitter_download_vertices": (C.c_int, [_vp, _P(C.c_float), C.c_size_t, _P(C.c_uint32)]),
     "t3d_emitter_download_state": (C.c_int, [_vp, _P(C.c_uint32), C.c_size_t, _P(C.c_uint32)]),

@@ -135,8 +135,14 @@ struct t3d_ctx
     std::vector<uint32_t> pending_offsets;
 
     uint64_t launches{ 0 }, h2d_bytes{ 0 }, d2h_bytes{ 0 };
-    cudaEvent_t ev_start[3]{}, ev_stop[3]{};
-    bool ev_valid[3]{ false, false, false };
+    // Per-kind launch timing: every launch is bracketed by a pair of events on the stream; pairs are
+    // resolved (and recycled) lazily when somebody asks for the totals.
+    struct EventPair { cudaEvent_t start, stop; };
+    std::vector<EventPair> ev_pending[3], ev_free;
+    double kernel_ms_total[3]{ 0, 0, 0 };
+    uint64_t kernel_launches[3]{ 0, 0, 0 };
+    float kernel_ms_last[3]{ 0, 0, 0 };
+    bool timing_enabled{ true };
 
     uint32_t* readback_host{ nullptr }; // pinned scratch for counts
     size_t readback_cap{ 0 };
@@ -396,20 +402,49 @@ static int sync_const(t3d_emitter* e)
 // --------------------------------------------------------------------------------------------------
 // flush: turn the queued ops of the current phase into launches
 // --------------------------------------------------------------------------------------------------
+static int resolve_timing(t3d_ctx* c, int k, bool wait)
+{
+    auto& v = c->ev_pending[k];
+    size_t done = 0;
+    for (; done < v.size(); ++done)
+    {
+        if (wait)
+            T3D_CUDA(cudaEventSynchronize(v[done].stop));
+        else if (cudaEventQuery(v[done].stop) != cudaSuccess)
+            break;
+        float ms = 0;
+        T3D_CUDA(cudaEventElapsedTime(&ms, v[done].start, v[done].stop));
+        c->kernel_ms_total[k] += ms;
+        c->kernel_ms_last[k] = ms;
+        c->kernel_launches[k]++;
+        c->ev_free.push_back(v[done]);
+    }
+    v.erase(v.begin(), v.begin() + (ptrdiff_t)done);
+    return T3D_OK;
+}
 static int time_begin(t3d_ctx* c, int k)
 {
-    if (!c->ev_start[k])
+    if (!c->timing_enabled) return T3D_OK;
+    if (c->ev_pending[k].size() >= 256) T3D_TRY(resolve_timing(c, k, true));
+    t3d_ctx::EventPair p;
+    if (!c->ev_free.empty())
     {
-        T3D_CUDA(cudaEventCreate(&c->ev_start[k]));
-        T3D_CUDA(cudaEventCreate(&c->ev_stop[k]));
+        p = c->ev_free.back();
+        c->ev_free.pop_back();
     }
-    T3D_CUDA(cudaEventRecord(c->ev_start[k], c->stream));
+    else
+    {
+        T3D_CUDA(cudaEventCreate(&p.start));
+        T3D_CUDA(cudaEventCreate(&p.stop));
+    }
+    T3D_CUDA(cudaEventRecord(p.start, c->stream));
+    c->ev_pending[k].push_back(p);
     return T3D_OK;
 }
 static int time_end(t3d_ctx* c, int k)
 {
-    T3D_CUDA(cudaEventRecord(c->ev_stop[k], c->stream));
-    c->ev_valid[k] = true;
+    if (!c->timing_enabled) return T3D_OK;
+    T3D_CUDA(cudaEventRecord(c->ev_pending[k].back().stop, c->stream));
     return T3D_OK;
 }
 
@@ -856,9 +891,11 @@ int t3d_ctx_destroy(t3d_ctx* c)
     if (c->readback_host) cudaFreeHost(c->readback_host);
     if (c->readback_dev) cudaFree(c->readback_dev);
     for (int k = 0; k < 3; ++k)
+        for (auto& p : c->ev_pending[k]) c->ev_free.push_back(p);
+    for (auto& p : c->ev_free)
     {
-        if (c->ev_start[k]) cudaEventDestroy(c->ev_start[k]);
-        if (c->ev_stop[k]) cudaEventDestroy(c->ev_stop[k]);
+        cudaEventDestroy(p.start);
+        cudaEventDestroy(p.stop);
     }
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -922,9 +959,19 @@ int t3d_ctx_last_kernel_ms(t3d_ctx* c, int which, float* ms)
 {
     if (!c || which < 0 || which > 2 || !ms) return fail(T3D_ERR_INVALID, "bad argument");
     T3D_TRY(flush(c));
-    if (!c->ev_valid[which]) return fail(T3D_ERR_INVALID, "no launch of kind %d has been recorded", which);
-    T3D_CUDA(cudaEventSynchronize(c->ev_stop[which]));
-    T3D_CUDA(cudaEventElapsedTime(ms, c->ev_start[which], c->ev_stop[which]));
+    T3D_TRY(resolve_timing(c, which, true));
+    if (!c->kernel_launches[which]) return fail(T3D_ERR_INVALID, "no launch of kind %d has been recorded", which);
+    *ms = c->kernel_ms_last[which];
+    return T3D_OK;
+}
+
+int t3d_ctx_kernel_time(t3d_ctx* c, int which, double* total_ms, uint64_t* n_launches)
+{
+    if (!c || which < 0 || which > 2) return fail(T3D_ERR_INVALID, "bad argument");
+    T3D_TRY(flush(c));
+    T3D_TRY(resolve_timing(c, which, true));
+    if (total_ms) *total_ms = c->kernel_ms_total[which];
+    if (n_launches) *n_launches = c->kernel_launches[which];
     return T3D_OK;
 }
 
@@ -1295,6 +1342,17 @@ int t3d_batch_get_counts(t3d_emitter* const* es, size_t n, uint32_t* counts)
     for (size_t i = 0; i < n; ++i)
         if (es[i]->ctx != c) return fail(T3D_ERR_INVALID, "t3d_batch_get_counts: emitters belong to different contexts");
     return refresh_counts(c, es, n, counts, nullptr);
+}
+
+int t3d_batch_set_transforms(t3d_emitter* const* es, size_t n, const float* node_worlds, const float* camera_world)
+{
+    if (!es && n) return fail(T3D_ERR_INVALID, "null argument");
+    for (size_t i = 0; i < n; ++i)
+    {
+        if (node_worlds) T3D_TRY(t3d_emitter_set_node_world(es[i], node_worlds + 16 * i));
+        if (camera_world) T3D_TRY(t3d_emitter_set_camera_world(es[i], camera_world));
+    }
+    return T3D_OK;
 }
 
 // ---- results ----

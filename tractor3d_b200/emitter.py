@@ -76,6 +76,12 @@ class Context:
         _check(self.lib, self.lib.t3d_ctx_last_kernel_ms(self.h, which, C.byref(ms)))
         return ms.value
 
+    def kernel_time(self, which):
+        """(total device ms, launches) of kind `which` (0 spawn, 1 update, 2 draw) since the context was created."""
+        ms, n = C.c_double(), C.c_uint64()
+        _check(self.lib, self.lib.t3d_ctx_kernel_time(self.h, which, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def launch_count(self):
         n = C.c_uint64()
         _check(self.lib, self.lib.t3d_ctx_launch_count(self.h, C.byref(n)))
@@ -104,6 +110,14 @@ class Context:
         h = handles if handles is not None else self._handles(emitters)
         c = np.ascontiguousarray(counts, dtype=np.uint32)
         _check(self.lib, self.lib.t3d_batch_emit_once(h, len(h), c.ctypes.data_as(_P(C.c_uint32))))
+
+    def batch_set_transforms(self, emitters, node_worlds=None, camera_world=None, handles=None):
+        """node_worlds: (n, 16) float32 or None; camera_world: (16,) float32 shared by all, or None."""
+        h = handles if handles is not None else self._handles(emitters)
+        nw = np.ascontiguousarray(node_worlds, dtype=np.float32).reshape(len(h), 16) if node_worlds is not None else None
+        cw = np.ascontiguousarray(camera_world, dtype=np.float32).reshape(16) if camera_world is not None else None
+        _check(self.lib, self.lib.t3d_batch_set_transforms(h, len(h), _fptr(nw) if nw is not None else None,
+                                                           _fptr(cw) if cw is not None else None))
 
     def batch_counts(self, emitters, handles=None):
         h = handles if handles is not None else self._handles(emitters)
