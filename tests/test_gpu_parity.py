@@ -286,11 +286,13 @@ def test_large_population_properties():
         e2.emit_once(4 * 1024 * 1024)
         prev = e2.count()
         assert prev == 4 * 1024 * 1024
-        for f in range(16):
+        for f in range(200):   # moved particles skip a frame's decrement (PE.cpp:825-829), so extinction takes a while
             e2.update(S.DT)
             c = e2.count()
             assert c <= prev
             prev = c
+            if c == 0:
+                break
         assert prev == 0
     finally:
         lib.close()

@@ -9,11 +9,10 @@
 namespace t3d
 {
 
-// Particles per tile of the update kernel: 256 threads x 4 consecutive particles, so every column is
-// read and written with 128-bit accesses.
-constexpr int kUpdateThreads = 256;
-constexpr int kUpdateVec = 4;
-constexpr int kUpdateTile = kUpdateThreads * kUpdateVec;
+// Particles per tile of the update kernel = particles per thread x threads per CTA of the selected variant
+// (t3d_update.cu).
+int update_tile_size();
+const char* update_variant_name();
 // Spawn and draw: one particle per thread.
 constexpr int kSpawnThreads = 256;
 constexpr int kDrawThreads = 256;

@@ -17,92 +17,11 @@
 // design rules are coalescing, 128-bit accesses and enough bytes in flight per SM.
 #include <cuda_runtime.h>
 
+#include "t3d_device.cuh"
 #include "t3d_internal.h"
 
 namespace t3d
 {
-
-// --------------------------------------------------------------------------------------------------
-// helpers
-// --------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float u01(int32_t r)
-{
-    // pch.h:152: (float)rand()/RAND_MAX with RAND_MAX = 2^31-1 converted to float (= 2^31): exactly r * 2^-31.
-    return (float)r / 2147483648.0f;
-}
-__device__ __forceinline__ float u11(int32_t r) { return (2.0f * u01(r)) - 1.0f; } // pch.h:151
-
-// MathUtil.h:195-200, left-to-right sum of four products.
-__device__ __forceinline__ void transform4(const float* __restrict__ m, float x, float y, float z, float w, float& ox,
-                                           float& oy, float& oz)
-{
-    ox = x * m[0] + y * m[4] + z * m[8] + w * m[12];
-    oy = x * m[1] + y * m[5] + z * m[9] + w * m[13];
-    oz = x * m[2] + y * m[6] + z * m[10] + w * m[14];
-}
-
-// Matrix.cpp:348-406.  Only the 3x3 part is produced (m[12..14] are 0 and are added as such by callers).
-struct Rot3
-{
-    float m0, m1, m2, m4, m5, m6, m8, m9, m10;
-};
-__device__ __forceinline__ Rot3 create_rotation(float x, float y, float z, float angle)
-{
-    float n = x * x + y * y + z * z;
-    if (n != 1.0f)
-    {
-        n = sqrtf(n);
-        if (n > 0.000001f)
-        {
-            n = 1.0f / n;
-            x *= n;
-            y *= n;
-            z *= n;
-        }
-    }
-    float s, c;
-    sincosf(angle, &s, &c);
-    float t = 1.0f - c;
-    float tx = t * x, ty = t * y, tz = t * z;
-    float txy = tx * y, txz = tx * z, tyz = ty * z;
-    float sx = s * x, sy = s * y, sz = s * z;
-    Rot3 r;
-    r.m0 = c + tx * x;
-    r.m1 = txy + sz;
-    r.m2 = txz - sy;
-    r.m4 = txy - sz;
-    r.m5 = c + ty * y;
-    r.m6 = tyz + sx;
-    r.m8 = txz + sy;
-    r.m9 = tyz - sx;
-    r.m10 = c + tz * z;
-    return r;
-}
-// transformVector4 with a Rot3 (m[12..14] = 0): keeps the "+ w*0" term so signed zeros match.
-__device__ __forceinline__ void rot_apply(const Rot3& r, float w, float& x, float& y, float& z)
-{
-    float ox = x * r.m0 + y * r.m4 + z * r.m8 + w * 0.0f;
-    float oy = x * r.m1 + y * r.m5 + z * r.m9 + w * 0.0f;
-    float oz = x * r.m2 + y * r.m6 + z * r.m10 + w * 0.0f;
-    x = ox;
-    y = oy;
-    z = oz;
-}
-
-template <class Item>
-__device__ __forceinline__ uint32_t find_item(const Item* __restrict__ items, uint32_t n_items, uint32_t tile)
-{
-    uint32_t lo = 0, hi = n_items;
-    while (hi - lo > 1)
-    {
-        uint32_t mid = (lo + hi) >> 1;
-        if (items[mid].tile_begin <= tile)
-            lo = mid;
-        else
-            hi = mid;
-    }
-    return lo;
-}
 
 // --------------------------------------------------------------------------------------------------
 // spawn
@@ -240,378 +159,6 @@ __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __rest
     F(T3D_COL_ANGLE, angle);
     F(T3D_COL_TIME_ON_FRAME, 0.0f); // :365
     cols[(size_t)T3D_COL_FRAME * stride + slot] = frame;
-}
-
-// --------------------------------------------------------------------------------------------------
-// update + removal
-//
-// removal.  The reference walks i = 0.. and, when particle i is dead, copies the LAST live particle into
-// slot i, shrinks the count and moves on WITHOUT examining the particle it just moved (PE.cpp:821-830 and
-// the loop increment at :750).  With N = count on entry, dead(k) evaluated on the ORIGINAL particle k and
-// D(k) = number of dead originals with index < k:
-//     original k is examined        <=>  k + D(k) < N
-//     examined and alive            ->   updated in place
-//     examined and dead             ->   slot k receives the untouched original N-1-D(k) (nothing if that is k)
-//     new count                     =    N - D(K), K = number of examined originals
-// Sources (>= new count, never examined, never written) and destinations (< K) are disjoint, so the fill is
-// race-free in place.  D(k) is one exclusive scan: within a tile by warp shuffles, across the tiles of an
-// emitter by decoupled look-back over per-tile status words (tile ids are handed out by an atomic ticket,
-// so every predecessor of a running tile is itself running or finished).
-// --------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// status word: [63:34] launch epoch, [33:32] 1 = tile aggregate, 2 = inclusive prefix, [31:0] dead count
-constexpr unsigned long long kStatusAggregate = 1ull << 32;
-constexpr unsigned long long kStatusPrefix = 2ull << 32;
-
-__device__ __forceinline__ float4 ldf4(const uint32_t* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ int4 ldi4(const uint32_t* p) { return *reinterpret_cast<const int4*>(p); }
-__device__ __forceinline__ void stf4(uint32_t* p, const float* v)
-{
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-}
-__device__ __forceinline__ void unpack(const float4& v, float* a)
-{
-    a[0] = v.x;
-    a[1] = v.y;
-    a[2] = v.z;
-    a[3] = v.w;
-}
-__device__ __forceinline__ void unpack(const int4& v, int* a)
-{
-    a[0] = v.x;
-    a[1] = v.y;
-    a[2] = v.z;
-    a[3] = v.w;
-}
-
-__global__ void __launch_bounds__(kUpdateThreads)
-    k_update(const UpdateItem* __restrict__ items, uint32_t n_items, uint32_t total_tiles,
-             unsigned long long* __restrict__ tile_status, uint32_t* __restrict__ ticket, uint32_t ticket_base,
-             uint32_t epoch)
-{
-    constexpr int V = kUpdateVec;
-    __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_warp[kUpdateThreads / 32];
-    __shared__ uint32_t s_excl;
-
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    if (tile >= total_tiles) return;
-
-    const UpdateItem& it = items[find_item(items, n_items, tile)];
-    EmitterDev* d = it.dev;
-    const uint32_t parity = it.parity;
-    const uint32_t N = d->cnt[parity].count;
-    const uint32_t jt = tile - it.tile_begin; // tile index inside the emitter
-    const uint32_t first = jt * kUpdateTile;
-    if (first >= N)
-    {
-        if (jt == 0 && tid == 0)
-        {
-            d->cnt[parity ^ 1].count = 0;
-            d->cnt[parity ^ 1].serial = d->cnt[parity].serial;
-        }
-        return;
-    }
-
-    const float elapsed_ms = it.elapsed_ms;
-    const float secs = elapsed_ms * 0.001f; // PE.cpp:727
-    const uint32_t flags = d->c.flags;
-    const bool animated = (flags & kFlagAnimated) != 0;
-    const bool looped = (flags & kFlagLooped) != 0;
-    const bool may_rotate = (flags & kFlagMayRotate) != 0;
-    uint32_t* const cols = d->c.cols;
-    const size_t stride = d->c.stride;
-    const uint32_t k0 = first + tid * V;
-    const bool active = k0 < N;
-    auto col = [&](int c) -> uint32_t* { return cols + (size_t)c * stride + k0; };
-
-    // ---- loads: everything this thread's 4 particles need, issued before any dependent work ----
-    int en[V], est[V];
-    float px[V], py[V], pz[V], vx[V], vy[V], vz[V], ax[V], ay[V], az[V];
-    float spin[V], ang[V], ss[V], se[V];
-    float cs[4][V], ce[4][V];
-    float tf[V];
-    int fr[V];
-    float rx[V], ry[V], rz[V], rs[V];
-    if (active)
-    {
-        unpack(ldi4(col(T3D_COL_ENERGY)), en);
-        unpack(ldi4(col(T3D_COL_ENERGY_START)), est);
-        unpack(ldf4(col(T3D_COL_POSITION + 0)), px);
-        unpack(ldf4(col(T3D_COL_POSITION + 1)), py);
-        unpack(ldf4(col(T3D_COL_POSITION + 2)), pz);
-        unpack(ldf4(col(T3D_COL_VELOCITY + 0)), vx);
-        unpack(ldf4(col(T3D_COL_VELOCITY + 1)), vy);
-        unpack(ldf4(col(T3D_COL_VELOCITY + 2)), vz);
-        unpack(ldf4(col(T3D_COL_ACCELERATION + 0)), ax);
-        unpack(ldf4(col(T3D_COL_ACCELERATION + 1)), ay);
-        unpack(ldf4(col(T3D_COL_ACCELERATION + 2)), az);
-        unpack(ldf4(col(T3D_COL_ROT_PER_PARTICLE_SPEED)), spin);
-        unpack(ldf4(col(T3D_COL_ANGLE)), ang);
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-        {
-            unpack(ldf4(col(T3D_COL_COLOR_START + c)), cs[c]);
-            unpack(ldf4(col(T3D_COL_COLOR_END + c)), ce[c]);
-        }
-        unpack(ldf4(col(T3D_COL_SIZE_START)), ss);
-        unpack(ldf4(col(T3D_COL_SIZE_END)), se);
-        if (animated)
-        {
-            unpack(ldf4(col(T3D_COL_TIME_ON_FRAME)), tf);
-            unpack(ldi4(col(T3D_COL_FRAME)), fr);
-        }
-        if (may_rotate)
-        {
-            unpack(ldf4(col(T3D_COL_ROTATION_AXIS + 0)), rx);
-            unpack(ldf4(col(T3D_COL_ROTATION_AXIS + 1)), ry);
-            unpack(ldf4(col(T3D_COL_ROTATION_AXIS + 2)), rz);
-            unpack(ldf4(col(T3D_COL_ROTATION_SPEED)), rs);
-        }
-    }
-
-    // ---- energy and the dead flags (PE.cpp:753-755: `long -= float`, then `> 0`) ----
-    bool valid[V], alive[V];
-    uint32_t my_dead = 0;
-#pragma unroll
-    for (int l = 0; l < V; ++l)
-    {
-        valid[l] = active && (k0 + l < N);
-        if (valid[l]) en[l] = __float2int_rz((float)en[l] - elapsed_ms);
-        alive[l] = valid[l] && en[l] > 0;
-        my_dead += (valid[l] && !alive[l]) ? 1u : 0u;
-    }
-
-    // ---- exclusive scan of the dead count inside the tile ----
-    uint32_t incl = my_dead;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (uint32_t)o) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t warp_base = 0, tile_dead = 0;
-#pragma unroll
-    for (int wi = 0; wi < kUpdateThreads / 32; ++wi)
-    {
-        uint32_t v = s_warp[wi];
-        if ((uint32_t)wi < warp) warp_base += v;
-        tile_dead += v;
-    }
-    const uint32_t thread_excl = warp_base + incl - my_dead;
-
-    // ---- decoupled look-back over the preceding tiles of this emitter ----
-    const unsigned long long tag = (unsigned long long)epoch << 34;
-    unsigned long long* my_status = tile_status + tile;
-    if (jt == 0)
-    {
-        if (tid == 0)
-        {
-            st_status(my_status, tag | kStatusPrefix | tile_dead);
-            s_excl = 0;
-        }
-    }
-    else if (warp == 0)
-    {
-        if (lane == 0) st_status(my_status, tag | kStatusAggregate | tile_dead);
-        uint32_t excl = 0;
-        int look = (int)jt - 1; // nearest predecessor, as a tile index inside the emitter
-        while (true)
-        {
-            const int idx = look - (int)lane;
-            unsigned long long s = tag | kStatusPrefix; // tiles before the emitter's first: prefix 0
-            if (idx >= 0)
-            {
-                const unsigned long long* sp = tile_status + (it.tile_begin + (uint32_t)idx);
-                do
-                {
-                    s = ld_status(sp);
-                } while ((s >> 34) != (unsigned long long)epoch || ((s >> 32) & 3ull) == 0ull);
-            }
-            const bool is_prefix = ((s >> 32) & 3ull) == 2ull;
-            const unsigned pmask = __ballot_sync(0xffffffffu, is_prefix);
-            const int first_p = __ffs((int)pmask) - 1; // pmask is never 0 past the emitter's first tile
-            uint32_t contrib = (pmask == 0u || (int)lane <= first_p) ? (uint32_t)s : 0u;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-            excl += contrib;
-            if (pmask != 0u) break;
-            look -= 32;
-        }
-        if (lane == 0)
-        {
-            st_status(my_status, tag | kStatusPrefix | (excl + tile_dead));
-            s_excl = excl;
-        }
-    }
-    __syncthreads();
-    const uint32_t tile_excl = s_excl;
-
-    if (!active) return;
-
-    // ---- per-particle update, PE.cpp:757-819 (computed for every live particle; stored only if examined) ----
-    float col_out[4][V], size_out[V];
-    const float ppf = d->c.percent_per_frame;
-    const float dur = d->c.frame_duration_secs;
-    const uint32_t frame_count = d->c.frame_count;
-#pragma unroll
-    for (int l = 0; l < V; ++l)
-    {
-        if (!alive[l]) continue;
-        if (may_rotate && rs[l] != 0.0f && !(rx[l] == 0.0f && ry[l] == 0.0f && rz[l] == 0.0f))
-        {
-            const Rot3 r = create_rotation(rx[l], ry[l], rz[l], rs[l] * secs); // :759
-            rot_apply(r, 1.0f, vx[l], vy[l], vz[l]);                            // :761
-            rot_apply(r, 1.0f, ax[l], ay[l], az[l]);                            // :762
-        }
-        vx[l] += ax[l] * secs; // :766-768
-        vy[l] += ay[l] * secs;
-        vz[l] += az[l] * secs;
-        px[l] += vx[l] * secs; // :770-772
-        py[l] += vy[l] * secs;
-        pz[l] += vz[l] * secs;
-        ang[l] += spin[l] * secs; // :774
-        const float percent = 1.0f - ((float)en[l] / (float)est[l]); // :777
-#pragma unroll
-        for (int c = 0; c < 4; ++c) col_out[c][l] = cs[c][l] + (ce[c][l] - cs[c][l]) * percent; // :779-782
-        size_out[l] = ss[l] + (se[l] - ss[l]) * percent;                                          // :784
-        if (animated)
-        {
-            if (!looped)
-            {
-                float spent = 0.0f; // :792-796, repeated addition
-                for (int q = 0; q < fr[l]; ++q) spent += ppf;
-                tf[l] = percent - spent;
-                if ((uint32_t)fr[l] < frame_count - 1u && tf[l] >= ppf) ++fr[l];
-            }
-            else
-            {
-                tf[l] += secs; // :808-817
-                if (tf[l] >= dur)
-                {
-                    tf[l] -= dur;
-                    ++fr[l];
-                    if ((uint32_t)fr[l] == frame_count) fr[l] = 0;
-                }
-            }
-        }
-    }
-
-    // ---- stores ----
-    bool examined[V];
-    uint32_t D[V];
-    {
-        uint32_t run = tile_excl + thread_excl;
-#pragma unroll
-        for (int l = 0; l < V; ++l)
-        {
-            D[l] = run;
-            examined[l] = valid[l] && (k0 + l + run < N);
-            run += (valid[l] && !alive[l]) ? 1u : 0u;
-        }
-    }
-    const bool all_store = examined[0] && alive[0] && examined[1] && alive[1] && examined[2] && alive[2] &&
-                           examined[3] && alive[3];
-    if (all_store)
-    {
-        *reinterpret_cast<int4*>(col(T3D_COL_ENERGY)) = make_int4(en[0], en[1], en[2], en[3]);
-        stf4(col(T3D_COL_VELOCITY + 0), vx);
-        stf4(col(T3D_COL_VELOCITY + 1), vy);
-        stf4(col(T3D_COL_VELOCITY + 2), vz);
-        stf4(col(T3D_COL_POSITION + 0), px);
-        stf4(col(T3D_COL_POSITION + 1), py);
-        stf4(col(T3D_COL_POSITION + 2), pz);
-        stf4(col(T3D_COL_ANGLE), ang);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) stf4(col(T3D_COL_COLOR + c), col_out[c]);
-        stf4(col(T3D_COL_SIZE), size_out);
-        if (animated)
-        {
-            stf4(col(T3D_COL_TIME_ON_FRAME), tf);
-            *reinterpret_cast<int4*>(col(T3D_COL_FRAME)) = make_int4(fr[0], fr[1], fr[2], fr[3]);
-        }
-        if (may_rotate)
-        {
-            stf4(col(T3D_COL_ACCELERATION + 0), ax);
-            stf4(col(T3D_COL_ACCELERATION + 1), ay);
-            stf4(col(T3D_COL_ACCELERATION + 2), az);
-        }
-    }
-    else
-    {
-#pragma unroll
-        for (int l = 0; l < V; ++l)
-        {
-            if (!examined[l]) continue;
-            if (alive[l])
-            {
-                auto S = [&](int c, float v) { col(c)[l] = __float_as_uint(v); };
-                col(T3D_COL_ENERGY)[l] = (uint32_t)en[l];
-                S(T3D_COL_VELOCITY + 0, vx[l]);
-                S(T3D_COL_VELOCITY + 1, vy[l]);
-                S(T3D_COL_VELOCITY + 2, vz[l]);
-                S(T3D_COL_POSITION + 0, px[l]);
-                S(T3D_COL_POSITION + 1, py[l]);
-                S(T3D_COL_POSITION + 2, pz[l]);
-                S(T3D_COL_ANGLE, ang[l]);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) S(T3D_COL_COLOR + c, col_out[c][l]);
-                S(T3D_COL_SIZE, size_out[l]);
-                if (animated)
-                {
-                    S(T3D_COL_TIME_ON_FRAME, tf[l]);
-                    col(T3D_COL_FRAME)[l] = (uint32_t)fr[l];
-                }
-                if (may_rotate)
-                {
-                    S(T3D_COL_ACCELERATION + 0, ax[l]);
-                    S(T3D_COL_ACCELERATION + 1, ay[l]);
-                    S(T3D_COL_ACCELERATION + 2, az[l]);
-                }
-            }
-            else
-            {
-                // PE.cpp:825-828: the last live particle, untouched this frame, takes the dead one's place.
-                const uint32_t src = N - 1u - D[l];
-                const uint32_t dst = k0 + l;
-                if (src != dst)
-                {
-#pragma unroll 2
-                    for (int c = 0; c < T3D_NUM_COLUMNS; ++c)
-                        cols[(size_t)c * stride + dst] = cols[(size_t)c * stride + src];
-                }
-            }
-        }
-    }
-
-    // ---- the last examined original publishes the new count (PE.cpp:829) ----
-#pragma unroll
-    for (int l = 0; l < V; ++l)
-    {
-        if (!examined[l]) continue;
-        const uint32_t dead_l = alive[l] ? 0u : 1u;
-        const bool next_examined = (k0 + l + 1u) + D[l] + dead_l < N;
-        if (!next_examined)
-        {
-            d->cnt[parity ^ 1].count = N - D[l] - dead_l;
-            d->cnt[parity ^ 1].serial = d->cnt[parity].serial;
-        }
-    }
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -787,13 +334,6 @@ __global__ void __launch_bounds__(256) k_latch(const DrawItem* __restrict__ item
 void launch_spawn(void* stream, const SpawnItem* items, uint32_t n_items, uint32_t total_tiles)
 {
     k_spawn<<<total_tiles, kSpawnThreads, 0, (cudaStream_t)stream>>>(items, n_items);
-}
-
-void launch_update(void* stream, const UpdateItem* items, uint32_t n_items, uint32_t total_tiles,
-                   unsigned long long* tile_status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch)
-{
-    k_update<<<total_tiles, kUpdateThreads, 0, (cudaStream_t)stream>>>(items, n_items, total_tiles, tile_status, ticket,
-                                                                      ticket_base, epoch);
 }
 
 void launch_draw(void* stream, const DrawItem* items, uint32_t n_items, uint32_t total_tiles, int rot_mode,

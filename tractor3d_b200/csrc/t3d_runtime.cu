@@ -508,6 +508,7 @@ static int launch_updates(t3d_ctx* c)
     T3D_TRY(staging_acquire(c, sizeof(UpdateItem) * n_items, &slot));
     UpdateItem* items = reinterpret_cast<UpdateItem*>(slot->host);
     uint32_t tiles = 0;
+    const uint32_t tile_size = (uint32_t)update_tile_size();
     for (uint32_t k = 0; k < n_items; ++k)
     {
         PendingOp& op = c->pending[k];
@@ -521,7 +522,7 @@ static int launch_updates(t3d_ctx* c)
         it.tile_begin = tiles;
         it.pad = 0;
         // At least one tile per emitter: tile 0 republishes the count into the other parity slot.
-        tiles += std::max(1u, (e->count_ub + kUpdateTile - 1) / kUpdateTile);
+        tiles += std::max(1u, (e->count_ub + tile_size - 1) / tile_size);
     }
     if (c->tile_status_cap < tiles)
     {

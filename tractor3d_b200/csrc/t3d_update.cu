@@ -1,0 +1,556 @@
+// t3d_update.cu -- the fused update + dead-particle removal kernel (replaces the per-particle loop of
+// ParticleEmitter::update, PE.cpp:750-831 of the reference).
+//
+// One thread owns V consecutive particles of one emitter and reads/writes every column with one V x 32-bit
+// access, so a warp touches 32 x V x 4 contiguous bytes per column per instruction.  The kernel is a pure
+// HBM stream: 144 B per particle (160 B with sprite animation, +28 B with axis rotation), no reuse.
+//
+// removal.  The reference walks i = 0.. and, when particle i is dead, copies the LAST live particle into
+// slot i, shrinks the count and moves on WITHOUT examining the particle it just moved (PE.cpp:821-830 and
+// the loop increment at :750).  With N = count on entry, dead(k) evaluated on the ORIGINAL particle k and
+// D(k) = number of dead originals with index < k:
+//     original k is examined        <=>  k + D(k) < N
+//     examined and alive            ->   updated in place
+//     examined and dead             ->   slot k receives the untouched original N-1-D(k) (nothing if that is k)
+//     new count                     =    N - D(K), K = number of examined originals
+// Sources (>= new count, never examined, never written) and destinations (< K) are disjoint, so the fill is
+// race-free in place.  D(k) is one exclusive scan: within a tile by warp shuffles, across the tiles of an
+// emitter by decoupled look-back over per-tile status words (tile ids are handed out by an atomic ticket,
+// so every predecessor of a running tile is itself running or finished).
+//
+// Numerics: --fmad=false, reference evaluation order (see t3d_kernels.cu).
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "t3d_device.cuh"
+#include "t3d_internal.h"
+
+namespace t3d
+{
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// status word: [63:34] launch epoch, [33:32] 1 = tile aggregate, 2 = inclusive prefix, [31:0] dead count
+constexpr unsigned long long kStatusAggregate = 1ull << 32;
+constexpr unsigned long long kStatusPrefix = 2ull << 32;
+
+// V x 32-bit streaming accesses (evict-first: every byte is touched once per frame).
+template <int V>
+struct Vec;
+template <>
+struct Vec<4>
+{
+    static __device__ __forceinline__ void ld(const uint32_t* p, float* a)
+    {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(p));
+        a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+    }
+    static __device__ __forceinline__ void ld(const uint32_t* p, int* a)
+    {
+        const int4 v = __ldcs(reinterpret_cast<const int4*>(p));
+        a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+    }
+    static __device__ __forceinline__ void st(uint32_t* p, const float* a)
+    {
+        __stcs(reinterpret_cast<float4*>(p), make_float4(a[0], a[1], a[2], a[3]));
+    }
+    static __device__ __forceinline__ void st(uint32_t* p, const int* a)
+    {
+        __stcs(reinterpret_cast<int4*>(p), make_int4(a[0], a[1], a[2], a[3]));
+    }
+};
+template <>
+struct Vec<2>
+{
+    static __device__ __forceinline__ void ld(const uint32_t* p, float* a)
+    {
+        const float2 v = __ldcs(reinterpret_cast<const float2*>(p));
+        a[0] = v.x; a[1] = v.y;
+    }
+    static __device__ __forceinline__ void ld(const uint32_t* p, int* a)
+    {
+        const int2 v = __ldcs(reinterpret_cast<const int2*>(p));
+        a[0] = v.x; a[1] = v.y;
+    }
+    static __device__ __forceinline__ void st(uint32_t* p, const float* a) { __stcs(reinterpret_cast<float2*>(p), make_float2(a[0], a[1])); }
+    static __device__ __forceinline__ void st(uint32_t* p, const int* a) { __stcs(reinterpret_cast<int2*>(p), make_int2(a[0], a[1])); }
+};
+template <>
+struct Vec<1>
+{
+    static __device__ __forceinline__ void ld(const uint32_t* p, float* a) { a[0] = __ldcs(reinterpret_cast<const float*>(p)); }
+    static __device__ __forceinline__ void ld(const uint32_t* p, int* a) { a[0] = __ldcs(reinterpret_cast<const int*>(p)); }
+    static __device__ __forceinline__ void st(uint32_t* p, const float* a) { __stcs(reinterpret_cast<float*>(p), a[0]); }
+    static __device__ __forceinline__ void st(uint32_t* p, const int* a) { __stcs(reinterpret_cast<int*>(p), a[0]); }
+};
+
+// What one thread holds of one V-particle group.  The record is processed in two halves -- motion (position,
+// velocity, acceleration, angle) and appearance (colour, size, sprite frame) -- each loaded, computed and stored
+// before the other is touched, so that only half of the record occupies registers at a time and more CTAs fit
+// on an SM; a compiler fence between the halves keeps the loads from being hoisted together again.
+template <int V>
+struct Motion
+{
+    float px[V], py[V], pz[V], vx[V], vy[V], vz[V], ax[V], ay[V], az[V];
+    float spin[V], ang[V];
+    float rx[V], ry[V], rz[V], rs[V];
+    __device__ __forceinline__ void load(const uint32_t* base, size_t stride, bool may_rotate)
+    {
+        auto col = [&](int c) -> const uint32_t* { return base + (size_t)c * stride; };
+        Vec<V>::ld(col(T3D_COL_POSITION + 0), px);
+        Vec<V>::ld(col(T3D_COL_POSITION + 1), py);
+        Vec<V>::ld(col(T3D_COL_POSITION + 2), pz);
+        Vec<V>::ld(col(T3D_COL_VELOCITY + 0), vx);
+        Vec<V>::ld(col(T3D_COL_VELOCITY + 1), vy);
+        Vec<V>::ld(col(T3D_COL_VELOCITY + 2), vz);
+        Vec<V>::ld(col(T3D_COL_ACCELERATION + 0), ax);
+        Vec<V>::ld(col(T3D_COL_ACCELERATION + 1), ay);
+        Vec<V>::ld(col(T3D_COL_ACCELERATION + 2), az);
+        Vec<V>::ld(col(T3D_COL_ROT_PER_PARTICLE_SPEED), spin);
+        Vec<V>::ld(col(T3D_COL_ANGLE), ang);
+        if (may_rotate)
+        {
+            Vec<V>::ld(col(T3D_COL_ROTATION_AXIS + 0), rx);
+            Vec<V>::ld(col(T3D_COL_ROTATION_AXIS + 1), ry);
+            Vec<V>::ld(col(T3D_COL_ROTATION_AXIS + 2), rz);
+            Vec<V>::ld(col(T3D_COL_ROTATION_SPEED), rs);
+        }
+    }
+};
+template <int V>
+struct Appearance
+{
+    int est[V];
+    float ss[V], se[V];
+    float cs[4][V], ce[4][V];
+    float tf[V];
+    int fr[V];
+    __device__ __forceinline__ void load(const uint32_t* base, size_t stride, bool animated)
+    {
+        auto col = [&](int c) -> const uint32_t* { return base + (size_t)c * stride; };
+        Vec<V>::ld(col(T3D_COL_ENERGY_START), est);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+        {
+            Vec<V>::ld(col(T3D_COL_COLOR_START + c), cs[c]);
+            Vec<V>::ld(col(T3D_COL_COLOR_END + c), ce[c]);
+        }
+        Vec<V>::ld(col(T3D_COL_SIZE_START), ss);
+        Vec<V>::ld(col(T3D_COL_SIZE_END), se);
+        if (animated)
+        {
+            Vec<V>::ld(col(T3D_COL_TIME_ON_FRAME), tf);
+            Vec<V>::ld(col(T3D_COL_FRAME), fr);
+        }
+    }
+};
+__device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
+
+// V = particles per thread per group, THREADS per CTA, SUB = groups per thread: a tile is V*THREADS*SUB
+// consecutive particles of one emitter and costs one look-back, so the scan frontier only has to advance
+// one tile per V*THREADS*SUB particles streamed.
+template <int V, int THREADS, int SUB, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+    k_update(const UpdateItem* __restrict__ items, uint32_t n_items, uint32_t total_tiles,
+             unsigned long long* __restrict__ tile_status, uint32_t* __restrict__ ticket, uint32_t ticket_base,
+             uint32_t epoch)
+{
+    constexpr int GROUP = V * THREADS;  // particles per sub-tile
+    constexpr int TILE = GROUP * SUB;
+    constexpr int WARPS = THREADS / 32;
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp[SUB][WARPS];
+    __shared__ uint32_t s_excl;
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= total_tiles) return;
+
+    const UpdateItem& it = items[find_item(items, n_items, tile)];
+    EmitterDev* d = it.dev;
+    const uint32_t parity = it.parity;
+    const uint32_t N = d->cnt[parity].count;
+    const uint32_t jt = tile - it.tile_begin; // tile index inside the emitter
+    const uint32_t first = jt * TILE;
+    if (first >= N)
+    {
+        if (jt == 0 && tid == 0)
+        {
+            d->cnt[parity ^ 1].count = 0;
+            d->cnt[parity ^ 1].serial = d->cnt[parity].serial;
+        }
+        return;
+    }
+
+    const float elapsed_ms = it.elapsed_ms;
+    const float secs = elapsed_ms * 0.001f; // PE.cpp:727
+    const uint32_t flags = d->c.flags;
+    const bool animated = (flags & kFlagAnimated) != 0;
+    const bool looped = (flags & kFlagLooped) != 0;
+    const bool may_rotate = (flags & kFlagMayRotate) != 0;
+    uint32_t* const cols = d->c.cols;
+    const size_t stride = d->c.stride;
+
+    // ---- phase A: the energy column of the whole tile -> dead flags (PE.cpp:753-755: `long -= float`, `> 0`) ----
+    int en[SUB][V];
+#pragma unroll
+    for (int s = 0; s < SUB; ++s)
+    {
+        const uint32_t k0 = first + s * GROUP + tid * V;
+        if (k0 < N) Vec<V>::ld(cols + (size_t)T3D_COL_ENERGY * stride + k0, en[s]);
+    }
+    // The motion half of the first group is requested now so that it is in flight while the scan and look-back run.
+    Motion<V> m;
+    {
+        const uint32_t k0 = first + tid * V;
+        if (k0 < N) m.load(cols + k0, stride, may_rotate);
+    }
+    uint32_t dead_bits = 0; // bit s*V+l: particle is valid and dead
+    uint32_t cnt[SUB];
+#pragma unroll
+    for (int s = 0; s < SUB; ++s)
+    {
+        const uint32_t k0 = first + s * GROUP + tid * V;
+        cnt[s] = 0;
+#pragma unroll
+        for (int l = 0; l < V; ++l)
+        {
+            if (k0 + l < N)
+            {
+                en[s][l] = __float2int_rz((float)en[s][l] - elapsed_ms);
+                if (!(en[s][l] > 0))
+                {
+                    dead_bits |= 1u << (s * V + l);
+                    cnt[s]++;
+                }
+            }
+        }
+    }
+
+    // ---- exclusive scan of the dead counts inside the tile (particle order: sub-tile, thread, lane) ----
+    uint32_t incl[SUB];
+#pragma unroll
+    for (int s = 0; s < SUB; ++s)
+    {
+        uint32_t v = cnt[s];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= (uint32_t)o) v += t;
+        }
+        incl[s] = v;
+        if (lane == 31) s_warp[s][warp] = v;
+    }
+    __syncthreads();
+    uint32_t base[SUB]; // dead particles of this tile that precede this thread's group s
+    uint32_t tile_dead = 0;
+#pragma unroll
+    for (int s = 0; s < SUB; ++s)
+    {
+        uint32_t before = tile_dead;
+#pragma unroll
+        for (int wi = 0; wi < WARPS; ++wi)
+        {
+            const uint32_t v = s_warp[s][wi];
+            if ((uint32_t)wi < warp) before += v;
+            tile_dead += v;
+        }
+        base[s] = before + incl[s] - cnt[s];
+    }
+
+    // ---- decoupled look-back over the preceding tiles of this emitter ----
+    const unsigned long long tag = (unsigned long long)epoch << 34;
+    unsigned long long* my_status = tile_status + tile;
+    if (jt == 0)
+    {
+        if (tid == 0)
+        {
+            st_status(my_status, tag | kStatusPrefix | tile_dead);
+            s_excl = 0;
+        }
+    }
+    else if (warp == 0)
+    {
+        if (lane == 0) st_status(my_status, tag | kStatusAggregate | tile_dead);
+        uint32_t excl = 0;
+        int look = (int)jt - 1; // nearest predecessor, as a tile index inside the emitter
+        while (true)
+        {
+            const int idx = look - (int)lane;
+            unsigned long long s = tag | kStatusPrefix; // before the emitter's first tile: prefix 0
+            if (idx >= 0)
+            {
+                const unsigned long long* sp = tile_status + (it.tile_begin + (uint32_t)idx);
+                do
+                {
+                    s = ld_status(sp);
+                } while ((s >> 34) != (unsigned long long)epoch || ((s >> 32) & 3ull) == 0ull);
+            }
+            const bool is_prefix = ((s >> 32) & 3ull) == 2ull;
+            const unsigned pmask = __ballot_sync(0xffffffffu, is_prefix);
+            const int first_p = __ffs((int)pmask) - 1;
+            uint32_t contrib = (pmask == 0u || (int)lane <= first_p) ? (uint32_t)s : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+            excl += contrib;
+            if (pmask != 0u) break;
+            look -= 32;
+        }
+        if (lane == 0)
+        {
+            st_status(my_status, tag | kStatusPrefix | (excl + tile_dead));
+            s_excl = excl;
+        }
+    }
+    __syncthreads();
+    const uint32_t tile_excl = s_excl;
+
+    // ---- phase B: stream the groups ----
+    const float ppf = d->c.percent_per_frame;
+    const float dur = d->c.frame_duration_secs;
+    const uint32_t frame_count = d->c.frame_count;
+#pragma unroll
+    for (int s = 0; s < SUB; ++s)
+    {
+        const uint32_t k0 = first + s * GROUP + tid * V;
+        if (k0 >= N) break;
+        uint32_t* const gbase = cols + k0;
+        auto col = [&](int c) -> uint32_t* { return gbase + (size_t)c * stride; };
+
+        // which originals the reference's loop examines, and what lands in each slot
+        bool valid[V], alive[V], examined[V];
+        uint32_t D[V];
+        bool all_store = true;
+        {
+            uint32_t run = tile_excl + base[s];
+#pragma unroll
+            for (int l = 0; l < V; ++l)
+            {
+                valid[l] = k0 + l < N;
+                alive[l] = valid[l] && !((dead_bits >> (s * V + l)) & 1u);
+                D[l] = run;
+                examined[l] = valid[l] && (k0 + l + run < N);
+                run += (valid[l] && !alive[l]) ? 1u : 0u;
+                all_store = all_store && examined[l] && alive[l];
+            }
+        }
+
+        // -- motion half: PE.cpp:757-774 --
+        if (s > 0) m.load(gbase, stride, may_rotate);
+#pragma unroll
+        for (int l = 0; l < V; ++l)
+        {
+            if (!alive[l]) continue;
+            if (may_rotate && m.rs[l] != 0.0f && !(m.rx[l] == 0.0f && m.ry[l] == 0.0f && m.rz[l] == 0.0f))
+            {
+                const Rot3 r = create_rotation(m.rx[l], m.ry[l], m.rz[l], m.rs[l] * secs); // :759
+                rot_apply(r, 1.0f, m.vx[l], m.vy[l], m.vz[l]);                              // :761
+                rot_apply(r, 1.0f, m.ax[l], m.ay[l], m.az[l]);                              // :762
+            }
+            m.vx[l] += m.ax[l] * secs; // :766-768
+            m.vy[l] += m.ay[l] * secs;
+            m.vz[l] += m.az[l] * secs;
+            m.px[l] += m.vx[l] * secs; // :770-772
+            m.py[l] += m.vy[l] * secs;
+            m.pz[l] += m.vz[l] * secs;
+            m.ang[l] += m.spin[l] * secs; // :774
+        }
+        if (all_store)
+        {
+            Vec<V>::st(col(T3D_COL_VELOCITY + 0), m.vx);
+            Vec<V>::st(col(T3D_COL_VELOCITY + 1), m.vy);
+            Vec<V>::st(col(T3D_COL_VELOCITY + 2), m.vz);
+            Vec<V>::st(col(T3D_COL_POSITION + 0), m.px);
+            Vec<V>::st(col(T3D_COL_POSITION + 1), m.py);
+            Vec<V>::st(col(T3D_COL_POSITION + 2), m.pz);
+            Vec<V>::st(col(T3D_COL_ANGLE), m.ang);
+            if (may_rotate)
+            {
+                Vec<V>::st(col(T3D_COL_ACCELERATION + 0), m.ax);
+                Vec<V>::st(col(T3D_COL_ACCELERATION + 1), m.ay);
+                Vec<V>::st(col(T3D_COL_ACCELERATION + 2), m.az);
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int l = 0; l < V; ++l)
+            {
+                if (!(examined[l] && alive[l])) continue;
+                auto S = [&](int c, float v) { col(c)[l] = __float_as_uint(v); };
+                S(T3D_COL_VELOCITY + 0, m.vx[l]);
+                S(T3D_COL_VELOCITY + 1, m.vy[l]);
+                S(T3D_COL_VELOCITY + 2, m.vz[l]);
+                S(T3D_COL_POSITION + 0, m.px[l]);
+                S(T3D_COL_POSITION + 1, m.py[l]);
+                S(T3D_COL_POSITION + 2, m.pz[l]);
+                S(T3D_COL_ANGLE, m.ang[l]);
+                if (may_rotate)
+                {
+                    S(T3D_COL_ACCELERATION + 0, m.ax[l]);
+                    S(T3D_COL_ACCELERATION + 1, m.ay[l]);
+                    S(T3D_COL_ACCELERATION + 2, m.az[l]);
+                }
+            }
+        }
+        compiler_fence();
+
+        // -- appearance half: PE.cpp:777-819 --
+        Appearance<V> a;
+        a.load(gbase, stride, animated);
+        float col_out[4][V], size_out[V];
+#pragma unroll
+        for (int l = 0; l < V; ++l)
+        {
+            if (!alive[l]) continue;
+            const float percent = 1.0f - ((float)en[s][l] / (float)a.est[l]); // :777
+#pragma unroll
+            for (int c = 0; c < 4; ++c) col_out[c][l] = a.cs[c][l] + (a.ce[c][l] - a.cs[c][l]) * percent; // :779-782
+            size_out[l] = a.ss[l] + (a.se[l] - a.ss[l]) * percent;                                          // :784
+            if (animated)
+            {
+                if (!looped)
+                {
+                    float spent = 0.0f; // :792-796, repeated addition
+                    for (int q = 0; q < a.fr[l]; ++q) spent += ppf;
+                    a.tf[l] = percent - spent;
+                    if ((uint32_t)a.fr[l] < frame_count - 1u && a.tf[l] >= ppf) ++a.fr[l];
+                }
+                else
+                {
+                    a.tf[l] += secs; // :808-817
+                    if (a.tf[l] >= dur)
+                    {
+                        a.tf[l] -= dur;
+                        ++a.fr[l];
+                        if ((uint32_t)a.fr[l] == frame_count) a.fr[l] = 0;
+                    }
+                }
+            }
+        }
+        if (all_store)
+        {
+            Vec<V>::st(col(T3D_COL_ENERGY), en[s]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) Vec<V>::st(col(T3D_COL_COLOR + c), col_out[c]);
+            Vec<V>::st(col(T3D_COL_SIZE), size_out);
+            if (animated)
+            {
+                Vec<V>::st(col(T3D_COL_TIME_ON_FRAME), a.tf);
+                Vec<V>::st(col(T3D_COL_FRAME), a.fr);
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int l = 0; l < V; ++l)
+            {
+                if (!(examined[l] && alive[l])) continue;
+                auto S = [&](int c, float v) { col(c)[l] = __float_as_uint(v); };
+                col(T3D_COL_ENERGY)[l] = (uint32_t)en[s][l];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) S(T3D_COL_COLOR + c, col_out[c][l]);
+                S(T3D_COL_SIZE, size_out[l]);
+                if (animated)
+                {
+                    S(T3D_COL_TIME_ON_FRAME, a.tf[l]);
+                    col(T3D_COL_FRAME)[l] = (uint32_t)a.fr[l];
+                }
+            }
+            // PE.cpp:825-828: the last live particle, untouched this frame, takes a dead one's place.  Sources lie
+            // beyond every examined slot, so no thread writes what is read here.
+#pragma unroll
+            for (int l = 0; l < V; ++l)
+            {
+                if (!examined[l] || alive[l]) continue;
+                const uint32_t src = N - 1u - D[l];
+                const uint32_t dst = k0 + l;
+                if (src != dst)
+                {
+#pragma unroll 2
+                    for (int c = 0; c < T3D_NUM_COLUMNS; ++c)
+                        cols[(size_t)c * stride + dst] = cols[(size_t)c * stride + src];
+                }
+            }
+        }
+
+        // the last examined original publishes the new count (PE.cpp:829)
+#pragma unroll
+        for (int l = 0; l < V; ++l)
+        {
+            if (!examined[l]) continue;
+            const uint32_t dead_l = alive[l] ? 0u : 1u;
+            const bool next_examined = (k0 + l + 1u) + D[l] + dead_l < N;
+            if (!next_examined)
+            {
+                d->cnt[parity ^ 1].count = N - D[l] - dead_l;
+                d->cnt[parity ^ 1].serial = d->cnt[parity].serial;
+            }
+        }
+        compiler_fence();
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// variants: {particles per thread per group, threads per CTA, groups per thread, min CTAs per SM}.  The
+// default is chosen from measurements on B200 (profiles/); T3D_UPDATE_VARIANT selects another for experiments.
+// --------------------------------------------------------------------------------------------------
+struct UpdateVariant
+{
+    const char* name;
+    int tile;
+    void (*launch)(cudaStream_t, uint32_t, const UpdateItem*, uint32_t, unsigned long long*, uint32_t*, uint32_t, uint32_t);
+};
+
+template <int V, int THREADS, int SUB, int MIN_BLOCKS>
+static void launch_variant(cudaStream_t s, uint32_t tiles, const UpdateItem* items, uint32_t n_items,
+                           unsigned long long* status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch)
+{
+    k_update<V, THREADS, SUB, MIN_BLOCKS><<<tiles, THREADS, 0, s>>>(items, n_items, tiles, status, ticket, ticket_base, epoch);
+}
+
+#define T3D_VARIANT(V, T, S, B) { "v" #V "t" #T "s" #S "b" #B, V * T * S, launch_variant<V, T, S, B> }
+static const UpdateVariant kVariants[] = {
+    T3D_VARIANT(4, 128, 4, 4), // default
+    T3D_VARIANT(4, 128, 1, 4), T3D_VARIANT(4, 128, 2, 4), T3D_VARIANT(4, 128, 8, 4), T3D_VARIANT(4, 128, 4, 6),
+    T3D_VARIANT(4, 128, 8, 6), T3D_VARIANT(4, 256, 4, 3), T3D_VARIANT(4, 256, 2, 2), T3D_VARIANT(4, 64, 8, 8),
+    T3D_VARIANT(2, 256, 4, 4), T3D_VARIANT(2, 256, 8, 4), T3D_VARIANT(2, 128, 8, 8), T3D_VARIANT(4, 128, 4, 8),
+};
+static int g_variant = -1;
+
+static const UpdateVariant& variant()
+{
+    if (g_variant < 0)
+    {
+        g_variant = 0;
+        if (const char* env = getenv("T3D_UPDATE_VARIANT"))
+            for (int i = 0; i < (int)(sizeof(kVariants) / sizeof(kVariants[0])); ++i)
+                if (!strcmp(env, kVariants[i].name)) g_variant = i;
+    }
+    return kVariants[g_variant];
+}
+
+int update_tile_size() { return variant().tile; }
+const char* update_variant_name() { return variant().name; }
+
+void launch_update(void* stream, const UpdateItem* items, uint32_t n_items, uint32_t total_tiles,
+                   unsigned long long* tile_status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch)
+{
+    variant().launch((cudaStream_t)stream, total_tiles, items, n_items, tile_status, ticket, ticket_base, epoch);
+}
+
+} // namespace t3d
