@@ -41,6 +41,15 @@ MI = 1024 * 1024
 UPDATE_BYTES, UPDATE_BYTES_ANIMATED, DRAW_BYTES, SPAWN_BYTES = 144, 160, 184, 136
 
 
+def measured_traffic():
+    """DRAM bytes per unit of each kernel from the committed ncu capture (profiles/), or {}."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -279,12 +288,14 @@ def run_cuda(args):
         upd_bytes = UPDATE_BYTES + (UPDATE_BYTES_ANIMATED - UPDATE_BYTES) * animated_frac
         per_launch_particles = local_particles if not churn else updates_done / args.steps
         roof = {}
+        traffic = measured_traffic()
         for nm, b in (("update", upd_bytes), ("draw", DRAW_BYTES)):
             ms = kern[nm]["ms_per_launch"]
             if ms:
                 ach = b * per_launch_particles / (ms * 1e-3) / 1e9
+                tr = traffic.get(nm, {}).get("bytes_per_unit") if workload == "c3" else None
                 roof[nm] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                            "traffic": None, "bytes_per_unit": b, "units_per_launch": per_launch_particles,
+                            "traffic": tr * per_launch_particles if tr else None, "bytes_per_unit": b, "units_per_launch": per_launch_particles,
                             "ms_per_launch": ms, "peak_source": peak_src}
         if churn and kern["spawn"]["ms_per_launch"]:
             ms = kern["spawn"]["ms_per_launch"]

@@ -17,6 +17,9 @@
 // design rules are coalescing, 128-bit accesses and enough bytes in flight per SM.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "t3d_device.cuh"
 #include "t3d_internal.h"
 
@@ -164,6 +167,10 @@ __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __rest
 // --------------------------------------------------------------------------------------------------
 // draw
 // --------------------------------------------------------------------------------------------------
+// OUT = 0: the tile's vertices are copied from shared memory with coalesced 128-bit streaming stores.
+// OUT = 1: one thread hands the tile to the TMA engine (cp.async.bulk shared -> global, SASS UBLKCP), which
+//          writes the nq * 144 contiguous bytes while the other warps are already gone.
+template <int OUT>
 __global__ void __launch_bounds__(kDrawThreads)
     k_draw(const DrawItem* __restrict__ items, uint32_t n_items, int rot_mode, const FrozenRotation* __restrict__ frozen)
 {
@@ -191,12 +198,12 @@ __global__ void __launch_bounds__(kDrawThreads)
     {
         const uint32_t* cols = d->c.cols;
         const size_t stride = d->c.stride;
-        auto LF = [&](int c) { return __uint_as_float(cols[(size_t)c * stride + i]); };
+        auto LF = [&](int c) { return __ldcs(reinterpret_cast<const float*>(cols + (size_t)c * stride + i)); };
         const float pos[3] = { LF(T3D_COL_POSITION), LF(T3D_COL_POSITION + 1), LF(T3D_COL_POSITION + 2) };
         const float size = LF(T3D_COL_SIZE);
         const float color[4] = { LF(T3D_COL_COLOR), LF(T3D_COL_COLOR + 1), LF(T3D_COL_COLOR + 2), LF(T3D_COL_COLOR + 3) };
         const float angle = LF(T3D_COL_ANGLE);
-        const uint32_t frame = cols[(size_t)T3D_COL_FRAME * stride + i];
+        const uint32_t frame = __ldcs(cols + (size_t)T3D_COL_FRAME * stride + i);
         const float* uv = uv_in_smem ? (s_uv + frame * 4u) : (uv_g + (size_t)frame * 4u);
         const float u1 = uv[0], v1 = uv[1], u2 = uv[2], v2 = uv[3];
 
@@ -276,13 +283,29 @@ __global__ void __launch_bounds__(kDrawThreads)
         o[7] = make_float4(p3[1], p3[2], u2, v2);
         o[8] = make_float4(color[0], color[1], color[2], color[3]);
     }
-    __syncthreads();
-
-    // Coalesced copy of the tile's vertices: nq quads * 144 B, contiguous in the emitter's vertex stream.
+    // The tile's vertices: nq quads * 144 B, contiguous in the emitter's vertex stream (16-byte aligned).
     const uint32_t nq = (N - first) < (uint32_t)kDrawThreads ? (N - first) : (uint32_t)kDrawThreads;
     float4* __restrict__ dst = reinterpret_cast<float4*>(d->c.vtx + (size_t)first * T3D_FLOATS_PER_QUAD);
-    const float4* src4 = reinterpret_cast<const float4*>(s_vtx);
-    for (uint32_t q = tid; q < nq * 9u; q += kDrawThreads) dst[q] = src4[q];
+    if (OUT == 1)
+    {
+        // Make this thread's shared-memory writes visible to the async proxy, then let one thread issue the bulk store.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0)
+        {
+            const uint32_t src = (uint32_t)__cvta_generic_to_shared(s_vtx);
+            const uint32_t bytes = nq * (uint32_t)(T3D_FLOATS_PER_QUAD * sizeof(float));
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory must outlive the read
+        }
+    }
+    else
+    {
+        __syncthreads();
+        const float4* src4 = reinterpret_cast<const float4*>(s_vtx);
+        for (uint32_t q = tid; q < nq * 9u; q += kDrawThreads) __stcs(dst + q, src4[q]);
+    }
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -339,7 +362,16 @@ void launch_spawn(void* stream, const SpawnItem* items, uint32_t n_items, uint32
 void launch_draw(void* stream, const DrawItem* items, uint32_t n_items, uint32_t total_tiles, int rot_mode,
                  const FrozenRotation* frozen)
 {
-    k_draw<<<total_tiles, kDrawThreads, 0, (cudaStream_t)stream>>>(items, n_items, rot_mode, frozen);
+    static int mode = -1;
+    if (mode < 0)
+    {
+        const char* env = getenv("T3D_DRAW_VARIANT");
+        mode = (env && !strcmp(env, "lsu")) ? 0 : 1;
+    }
+    if (mode == 1)
+        k_draw<1><<<total_tiles, kDrawThreads, 0, (cudaStream_t)stream>>>(items, n_items, rot_mode, frozen);
+    else
+        k_draw<0><<<total_tiles, kDrawThreads, 0, (cudaStream_t)stream>>>(items, n_items, rot_mode, frozen);
 }
 
 void launch_latch(void* stream, const DrawItem* items, uint32_t n_items, FrozenRotation* frozen)
