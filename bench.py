@@ -110,7 +110,7 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------------
 def build_population(ctx, workload, rank, world, particles):
     """Creates this rank's emitters and fills them.  Returns (emitters, per_emitter_particles, animated_fraction, name)."""
-    from tractor3d_b200 import abi, presets
+    from tractor3d_b200 import abi, presets, sharding
     from tractor3d_b200.emitter import ParticleEmitter
 
     emitters = []
@@ -127,7 +127,7 @@ def build_population(ctx, workload, rank, world, particles):
         if particles:
             per = max(32, particles // n_emitters)
         animated = 0
-        for eid in range(rank, n_emitters, world):
+        for eid in sharding.local_emitter_ids(n_emitters, rank, world):
             p, sprite = presets.MIXED[eid % 3]()
             p.particle_count_max = per
             p.energy_min, p.energy_max = 1.0e6, 2.0e6   # stationary population
@@ -273,15 +273,12 @@ def run_cuda(args):
         del host
 
     # ---- reduce over ranks: max time, sum of work (the only collective, after the run) ----
-    if world > 1:
-        t = torch.tensor([ms_total, t_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, t_e2e = float(t[0]), float(t[1])
-        w = torch.tensor([updates_done, e2e_units, local_particles, live_after, launches], device="cuda", dtype=torch.int64)
-        dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        updates_done, e2e_units, total_particles, live_after, launches = [int(x) for x in w]
-    else:
-        total_particles = local_particles
+    from tractor3d_b200 import sharding
+    mx, sm = sharding.reduce_stats({"ms_total": ms_total, "t_e2e": t_e2e},
+                                   {"updates": updates_done, "e2e_units": e2e_units, "particles": local_particles,
+                                    "live": live_after, "launches": launches})
+    ms_total, t_e2e = mx["ms_total"], mx["t_e2e"]
+    updates_done, e2e_units, total_particles, live_after, launches = sm["updates"], sm["e2e_units"], sm["particles"], sm["live"], sm["launches"]
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()

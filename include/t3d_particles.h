@@ -223,6 +223,8 @@ uint32_t t3d_host_sprite_frame_coords(uint32_t frame_count, int width, int heigh
 /* Number of draws one spawned particle consumes starting at draws[0] (PE.cpp:312-364); 0 if the
  * stream ends first.  Used to cut a recorded stream into per-particle offsets. */
 size_t t3d_host_particle_draws(const int32_t* draws, size_t n, int ellipsoid, uint32_t frame_random_offset);
+/* Width and height of a PNG from its header: all ParticleEmitter ever asks of its texture (PE.cpp:244-247). */
+int t3d_host_png_size(const char* path, uint32_t* width, uint32_t* height);
 /* Parses a `.particle` file into params + sprite sheet description (PE.cpp:92-184). */
 int t3d_particle_file_parse(const char* url, t3d_emitter_params* params, uint32_t* frame_count,
                             int* sprite_width, int* sprite_height, char* texture_path, size_t texture_path_len);

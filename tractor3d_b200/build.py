@@ -55,6 +55,23 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_facade_driver():
+    """Compiles the C++ ParticleEmitter facade (tractor3d_b200/host) together with tests/facade_driver.cpp against
+    the library; proves the host-side mirror of the reference interface builds and links."""
+    root = os.path.dirname(HERE)
+    out_dir = os.path.join(HERE, "host", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, "facade_driver")
+    cmd = ["g++", "-std=c++17", "-O2", "-DGP_ERRORS_AS_WARNINGS", "-o", out,
+           os.path.join(root, "tests", "facade_driver.cpp"), os.path.join(HERE, "host", "ParticleEmitter.cpp"),
+           "-L" + CSRC, "-lt3d_particles", "-Wl,-rpath,$ORIGIN/../../csrc"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building the facade driver")
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
     print(OUT)

@@ -314,6 +314,15 @@ bool png_size(const std::string& p, unsigned* w, unsigned* h)
 }
 } // namespace
 
+extern "C" int t3d_host_png_size(const char* path, uint32_t* width, uint32_t* height)
+{
+    unsigned w = 0, h = 0;
+    if (!path || !png_size(path, &w, &h)) return host_fail(T3D_ERR_IO, "Failed to create texture for particle emitter: '%s'", path ? path : "");
+    if (width) *width = w;
+    if (height) *height = h;
+    return T3D_OK;
+}
+
 extern "C" int t3d_particle_file_parse(const char* url, t3d_emitter_params* params, uint32_t* frame_count, int* sprite_width,
                                        int* sprite_height, char* texture_path, size_t texture_path_len)
 {
