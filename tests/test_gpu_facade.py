@@ -48,7 +48,7 @@ def test_cpp_facade_matches_oracle(tmp_path):
         eo.set_node_world(w.T.reshape(16))
         eo.update(S.DT)
         n_draws += eo.draw()
-    assert (count, draws) == (eo.count(), n_draws) and count > 100
+    assert (count, draws) == (eo.count(), n_draws) and count > 20
     so = eo.state()
     fa, fb = state.view(np.float32), so.view(np.float32)
     for c in abi.INT_COLUMNS:

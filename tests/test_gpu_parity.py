@@ -207,8 +207,8 @@ def test_batch_of_mixed_emitters_one_launch_per_phase():
             for _, eo in twins:
                 eo.update(S.DT); eo.draw()
         lib.ctx.sync()
-        # spawn + update + draw (+ one latch for the frozen rotation): a handful of launches per frame, not 48 x 3
-        assert lib.ctx.launch_count() - launches0 <= frames * 3 + 2
+        # spawn + update + count feedback + draw (+ one latch for the frozen rotation) per frame, not 48 x 3
+        assert lib.ctx.launch_count() - launches0 <= frames * 4 + 2
         counts = lib.ctx.batch_counts(pes)
         for k, (eg, eo) in enumerate(twins):
             assert counts[k] == eo.count(), f"emitter {k}"

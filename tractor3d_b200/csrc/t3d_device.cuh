@@ -75,10 +75,39 @@ __device__ __forceinline__ void rot_apply(const Rot3& r, float w, float& x, floa
     z = oz;
 }
 
+// Which emitter of the launch owns global tile `tile`: the last item with tile_begin <= tile.  Every step is a
+// dependent load, so the search starts from the interpolated position (exact when emitters have equal tile
+// counts: two loads) and gallops outwards before bisecting.
 template <class Item>
-__device__ __forceinline__ uint32_t find_item(const Item* __restrict__ items, uint32_t n_items, uint32_t tile)
+__device__ __forceinline__ uint32_t find_item(const Item* __restrict__ items, uint32_t n_items, uint32_t tile,
+                                              uint32_t total_tiles)
 {
-    uint32_t lo = 0, hi = n_items;
+    if (n_items == 1) return 0;
+    uint32_t lo, hi;
+    uint32_t g = (uint32_t)(((unsigned long long)tile * n_items) / (total_tiles ? total_tiles : 1u));
+    if (g >= n_items) g = n_items - 1;
+    if (items[g].tile_begin <= tile)
+    {
+        lo = g;
+        uint32_t step = 1;
+        while (lo + step < n_items && items[lo + step].tile_begin <= tile)
+        {
+            lo += step;
+            step <<= 1;
+        }
+        hi = lo + step < n_items ? lo + step : n_items;
+    }
+    else
+    {
+        hi = g;
+        uint32_t step = 1;
+        while (hi > step && items[hi - step].tile_begin > tile)
+        {
+            hi -= step;
+            step <<= 1;
+        }
+        lo = hi > step ? hi - step : 0;
+    }
     while (hi - lo > 1)
     {
         uint32_t mid = (lo + hi) >> 1;

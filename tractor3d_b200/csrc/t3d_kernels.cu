@@ -45,7 +45,7 @@ struct DrawSource
 __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __restrict__ items, uint32_t n_items)
 {
     const uint32_t tile = blockIdx.x;
-    const SpawnItem& it = items[find_item(items, n_items, tile)];
+    const SpawnItem& it = items[find_item(items, n_items, tile, gridDim.x)];
     EmitterDev* d = it.dev;
     const uint32_t parity = it.parity;
     const uint32_t count0 = d->cnt[parity].count;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kDrawThreads)
     __shared__ float s_uv[kMaxSmemFrames * 4];
 
     const uint32_t tile = blockIdx.x;
-    const DrawItem& it = items[find_item(items, n_items, tile)];
+    const DrawItem& it = items[find_item(items, n_items, tile, gridDim.x)];
     const EmitterDev* d = it.dev;
     const uint32_t N = d->cnt[it.parity].count;
     const uint32_t first = (tile - it.tile_begin) * kDrawThreads;

@@ -144,6 +144,21 @@ struct t3d_ctx
     float kernel_ms_last[3]{ 0, 0, 0 };
     bool timing_enabled{ true };
 
+    // Asynchronous count feedback: after every update launch the new live counts are copied to pinned memory
+    // without waiting; when a copy has landed, it tightens the host's upper bounds (which size the next grids).
+    struct Feedback
+    {
+        std::vector<t3d_emitter*> es;
+        std::vector<uint64_t> emitted_mark; // emitter's emitted_total when the launch was enqueued
+        uint32_t* host{ nullptr };
+        uint32_t* dev{ nullptr };
+        size_t cap{ 0 };
+        cudaEvent_t done{ nullptr };
+        bool in_flight{ false };
+    };
+    Feedback feedback[4];
+    int feedback_next{ 0 };
+
     uint32_t* readback_host{ nullptr }; // pinned scratch for counts
     size_t readback_cap{ 0 };
     uint32_t* readback_dev{ nullptr };
@@ -184,6 +199,7 @@ struct t3d_emitter
     bool count_exact{ true };
     bool queued{ false };
     bool last_draw_empty{ true }; // the last draw() submitted no quads (inactive or no particles)
+    uint64_t emitted_total{ 0 };  // particles ever asked to spawn (upper bound of those spawned)
 };
 
 constexpr uint32_t kDevChunk = 4096;
@@ -501,12 +517,66 @@ static int launch_spawns(t3d_ctx* c)
     return T3D_OK;
 }
 
+static void poll_feedback(t3d_ctx* c)
+{
+    for (t3d_ctx::Feedback& fb : c->feedback)
+    {
+        if (!fb.in_flight || cudaEventQuery(fb.done) != cudaSuccess) continue;
+        for (size_t i = 0; i < fb.es.size(); ++i)
+        {
+            t3d_emitter* e = fb.es[i];
+            if (!e) continue;
+            const uint64_t ub = (uint64_t)fb.host[2 * i] + (e->emitted_total - fb.emitted_mark[i]);
+            if (ub < e->count_ub) e->count_ub = (uint32_t)ub;
+        }
+        fb.in_flight = false;
+    }
+}
+
+// Enqueues the read-back of the counts the update launch just produced; never waits.
+static int submit_feedback(t3d_ctx* c, const CountQuery* dev_queries)
+{
+    t3d_ctx::Feedback& fb = c->feedback[c->feedback_next];
+    if (fb.in_flight) return T3D_OK; // all slots busy: skip this frame's feedback
+    c->feedback_next = (c->feedback_next + 1) % 4;
+    const size_t n = c->pending.size();
+    if (fb.cap < n)
+    {
+        if (fb.host) cudaFreeHost(fb.host);
+        if (fb.dev) cudaFree(fb.dev);
+        fb.host = fb.dev = nullptr;
+        const size_t cap = std::max<size_t>(n * 2, 64);
+        T3D_CUDA(cudaMallocHost((void**)&fb.host, cap * 2 * sizeof(uint32_t)));
+        T3D_CUDA(cudaMalloc((void**)&fb.dev, cap * 2 * sizeof(uint32_t)));
+        fb.cap = cap;
+    }
+    if (!fb.done) T3D_CUDA(cudaEventCreateWithFlags(&fb.done, cudaEventDisableTiming));
+    fb.es.resize(n);
+    fb.emitted_mark.resize(n);
+    for (size_t i = 0; i < n; ++i)
+    {
+        fb.es[i] = c->pending[i].e;
+        fb.emitted_mark[i] = c->pending[i].e->emitted_total;
+    }
+    launch_gather_counts(c->stream, dev_queries, (uint32_t)n, fb.dev);
+    T3D_CUDA(cudaGetLastError());
+    c->launches++;
+    T3D_CUDA(cudaMemcpyAsync(fb.host, fb.dev, n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    T3D_CUDA(cudaEventRecord(fb.done, c->stream));
+    c->d2h_bytes += n * 2 * sizeof(uint32_t);
+    fb.in_flight = true;
+    return T3D_OK;
+}
+
 static int launch_updates(t3d_ctx* c)
 {
     const uint32_t n_items = (uint32_t)c->pending.size();
     StagingSlot* slot;
-    T3D_TRY(staging_acquire(c, sizeof(UpdateItem) * n_items, &slot));
+    const size_t items_bytes = align_up(sizeof(UpdateItem) * n_items, 16);
+    const size_t total_bytes = items_bytes + sizeof(CountQuery) * n_items;
+    T3D_TRY(staging_acquire(c, total_bytes, &slot));
     UpdateItem* items = reinterpret_cast<UpdateItem*>(slot->host);
+    CountQuery* queries = reinterpret_cast<CountQuery*>(slot->host + items_bytes);
     uint32_t tiles = 0;
     const uint32_t tile_size = (uint32_t)update_tile_size();
     for (uint32_t k = 0; k < n_items; ++k)
@@ -521,6 +591,9 @@ static int launch_updates(t3d_ctx* c)
         e->parity ^= 1u;
         it.tile_begin = tiles;
         it.pad = 0;
+        queries[k].dev = e->dev;
+        queries[k].parity = e->parity; // where this launch leaves the new count
+        queries[k].pad = 0;
         // At least one tile per emitter: tile 0 republishes the count into the other parity slot.
         tiles += std::max(1u, (e->count_ub + tile_size - 1) / tile_size);
     }
@@ -542,7 +615,7 @@ static int launch_updates(t3d_ctx* c)
         T3D_CUDA(cudaMemsetAsync(c->tile_status, 0, c->tile_status_cap * sizeof(unsigned long long), c->stream));
         c->epoch = 1;
     }
-    T3D_TRY(staging_submit(c, slot, sizeof(UpdateItem) * n_items));
+    T3D_TRY(staging_submit(c, slot, total_bytes));
     T3D_TRY(time_begin(c, KERNEL_UPDATE));
     launch_update(c->stream, reinterpret_cast<const UpdateItem*>(slot->dev), n_items, tiles, c->tile_status, c->ticket,
                   c->ticket_base, c->epoch);
@@ -550,6 +623,7 @@ static int launch_updates(t3d_ctx* c)
     T3D_TRY(time_end(c, KERNEL_UPDATE));
     c->ticket_base += tiles;
     c->launches++;
+    T3D_TRY(submit_feedback(c, reinterpret_cast<const CountQuery*>(slot->dev + items_bytes)));
     T3D_TRY(staging_release(c, slot));
     return T3D_OK;
 }
@@ -624,6 +698,7 @@ static int flush(t3d_ctx* c)
         return T3D_OK;
     }
     T3D_TRY(use_device(c));
+    poll_feedback(c);
     int rc = T3D_OK;
     if (c->phase == PHASE_EMIT)
         rc = launch_spawns(c);
@@ -695,7 +770,15 @@ static int refresh_counts(t3d_ctx* c, t3d_emitter* const* es, size_t n, uint32_t
 
 static int exact_count(t3d_emitter* e, uint32_t* out)
 {
-    if (!e->count_exact) T3D_TRY(refresh_counts(e->ctx, &e, 1, nullptr, nullptr));
+    if (!e->count_exact)
+    {
+        // One read-back serves every emitter whose count is stale: a loop over many stopped-but-live emitters
+        // (isActive needs `count > 0`, PE.cpp:283) then costs one sync per phase, not one per emitter.
+        std::vector<t3d_emitter*> stale;
+        for (t3d_emitter* o : e->ctx->emitters)
+            if (!o->count_exact) stale.push_back(o);
+        T3D_TRY(refresh_counts(e->ctx, stale.data(), stale.size(), nullptr, nullptr));
+    }
     *out = e->count_ub;
     return T3D_OK;
 }
@@ -801,6 +884,7 @@ static int prepare_emit(t3d_emitter* e, uint32_t n, PendingOp* op)
     {
         // The kernel clamps against the live count it reads (PE.cpp:293-296); the host keeps an upper bound.
         op->emit_n = n;
+        e->emitted_total += n;
         const uint64_t ub = (uint64_t)e->count_ub + n;
         e->count_ub = (uint32_t)std::min<uint64_t>(ub, cap);
         return T3D_OK;
@@ -817,6 +901,7 @@ static int prepare_emit(t3d_emitter* e, uint32_t n, PendingOp* op)
     {
         T3D_TRY(collect_host_draws(e, n, op));
         e->count_ub += n;
+        e->emitted_total += n;
     }
     return T3D_OK;
 }
@@ -891,6 +976,12 @@ int t3d_ctx_destroy(t3d_ctx* c)
     if (c->frozen_dev) cudaFree(c->frozen_dev);
     if (c->readback_host) cudaFreeHost(c->readback_host);
     if (c->readback_dev) cudaFree(c->readback_dev);
+    for (t3d_ctx::Feedback& fb : c->feedback)
+    {
+        if (fb.host) cudaFreeHost(fb.host);
+        if (fb.dev) cudaFree(fb.dev);
+        if (fb.done) cudaEventDestroy(fb.done);
+    }
     for (int k = 0; k < 3; ++k)
         for (auto& p : c->ev_pending[k]) c->ev_free.push_back(p);
     for (auto& p : c->ev_free)
@@ -1072,6 +1163,9 @@ int t3d_emitter_destroy(t3d_emitter* e)
     if (e->queued) flush(c);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (t3d_ctx::Feedback& fb : c->feedback)
+        for (t3d_emitter*& o : fb.es)
+            if (o == e) o = nullptr;
     if (e->uv_dev) cudaFree(e->uv_dev);
     if (e->dev) c->dev_free.push_back(e->dev);
     Slab& s = c->slabs[e->slab];
@@ -1422,6 +1516,7 @@ int t3d_emitter_upload_state(t3d_emitter* e, const uint32_t* in, size_t stride, 
     c->h2d_bytes += (size_t)count * T3D_NUM_COLUMNS * sizeof(uint32_t) + sizeof(uint32_t);
     e->count_ub = count;
     e->count_exact = true;
+    e->emitted_total += count; // keeps count feedback still in flight a valid upper bound
     // Uploaded particles may carry any rotation state.
     e->may_rotate = e->may_spin = true;
     e->const_dirty = true;

@@ -171,6 +171,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[SUB][WARPS];
     __shared__ uint32_t s_excl;
+    // Slots of this tile that receive a moved particle, indexed by the dead particle's rank inside the tile
+    // (offset from the tile's first slot; kNoMove: nothing to copy).
+    __shared__ unsigned short s_move[TILE];
+    constexpr unsigned short kNoMove = 0xFFFFu;
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u, warp = tid >> 5;
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     const uint32_t tile = s_tile;
     if (tile >= total_tiles) return;
 
-    const UpdateItem& it = items[find_item(items, n_items, tile)];
+    const UpdateItem& it = items[find_item(items, n_items, tile, total_tiles)];
     EmitterDev* d = it.dev;
     const uint32_t parity = it.parity;
     const uint32_t N = d->cnt[parity].count;
@@ -272,6 +276,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         base[s] = before + incl[s] - cnt[s];
     }
 
+    for (uint32_t r = tid; r < tile_dead; r += THREADS) s_move[r] = kNoMove;
+
     // ---- decoupled look-back over the preceding tiles of this emitter ----
     const unsigned long long tag = (unsigned long long)epoch << 34;
     unsigned long long* my_status = tile_status + tile;
@@ -332,6 +338,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         auto col = [&](int c) -> uint32_t* { return gbase + (size_t)c * stride; };
 
         // which originals the reference's loop examines, and what lands in each slot
+        // all_store: every slot of the group is examined, so the whole group is stored with vector stores --
+        // the dead ones with don't-care values, overwritten after the barrier below by the particle moved in.
         bool valid[V], alive[V], examined[V];
         uint32_t D[V];
         bool all_store = true;
@@ -344,8 +352,14 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 alive[l] = valid[l] && !((dead_bits >> (s * V + l)) & 1u);
                 D[l] = run;
                 examined[l] = valid[l] && (k0 + l + run < N);
+                if (examined[l] && !alive[l])
+                {
+                    // PE.cpp:825-828: the last live particle, untouched this frame, takes the dead one's place.
+                    const uint32_t src = N - 1u - run;
+                    if (src != k0 + l) s_move[run - tile_excl] = (unsigned short)(k0 + l - first);
+                }
                 run += (valid[l] && !alive[l]) ? 1u : 0u;
-                all_store = all_store && examined[l] && alive[l];
+                all_store = all_store && examined[l];
             }
         }
 
@@ -471,21 +485,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                     col(T3D_COL_FRAME)[l] = (uint32_t)a.fr[l];
                 }
             }
-            // PE.cpp:825-828: the last live particle, untouched this frame, takes a dead one's place.  Sources lie
-            // beyond every examined slot, so no thread writes what is read here.
-#pragma unroll
-            for (int l = 0; l < V; ++l)
-            {
-                if (!examined[l] || alive[l]) continue;
-                const uint32_t src = N - 1u - D[l];
-                const uint32_t dst = k0 + l;
-                if (src != dst)
-                {
-#pragma unroll 2
-                    for (int c = 0; c < T3D_NUM_COLUMNS; ++c)
-                        cols[(size_t)c * stride + dst] = cols[(size_t)c * stride + src];
-                }
-            }
         }
 
         // the last examined original publishes the new count (PE.cpp:829)
@@ -502,6 +501,28 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             }
         }
         compiler_fence();
+    }
+
+    // ---- the moves, cooperatively: rank r of this tile's dead particles pulls original N-1-(tile_excl+r) into its
+    // slot.  Column-major task order: consecutive threads read consecutive sources (contiguous at the end of the
+    // live range) of one column.  Sources lie beyond every examined slot, so nothing read here is written by anyone.
+    if (tile_dead)
+    {
+        __syncthreads(); // s_move complete; this CTA's stores to the dead slots are ordered before the moves
+        const uint32_t tasks = tile_dead * (uint32_t)T3D_NUM_COLUMNS;
+        const uint32_t src_last = N - 1u - tile_excl;
+#pragma unroll 4
+        for (uint32_t t = tid; t < tasks; t += THREADS)
+        {
+            const uint32_t c = t / tile_dead;
+            const uint32_t r = t - c * tile_dead;
+            const unsigned short off = s_move[r];
+            if (off != kNoMove)
+            {
+                uint32_t* column = cols + (size_t)c * stride;
+                column[first + off] = column[src_last - r];
+            }
+        }
     }
 }
 
