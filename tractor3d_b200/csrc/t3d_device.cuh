@@ -75,6 +75,22 @@ __device__ __forceinline__ void rot_apply(const Rot3& r, float w, float& x, floa
     z = oz;
 }
 
+// Address of particle i's word in column 0 of an emitter; its word in column c lies c * stride words further.
+//   block_shift == 0  plain struct-of-arrays: stride = slab capacity.
+//   block_shift == k  blocked struct-of-arrays: 2^k consecutive particles keep their 34 columns in one contiguous
+//                     chunk (stride = 2^k), so a tile's working set is one contiguous region of HBM.
+// Groups of 4 consecutive particles (index multiple of 4) never straddle a block.
+__device__ __forceinline__ uint32_t* particle_base(uint32_t* cols, uint32_t block_shift, uint32_t i)
+{
+    if (block_shift == 0) return cols + i;
+    const uint32_t blk = i >> block_shift, lane = i & ((1u << block_shift) - 1u);
+    return cols + ((size_t)blk * T3D_NUM_COLUMNS << block_shift) + lane;
+}
+__device__ __forceinline__ const uint32_t* particle_base(const uint32_t* cols, uint32_t block_shift, uint32_t i)
+{
+    return particle_base(const_cast<uint32_t*>(cols), block_shift, i);
+}
+
 // Which emitter of the launch owns global tile `tile`: the last item with tile_begin <= tile.  Every step is a
 // dependent load, so the search starts from the interpolated position (exact when emitters have equal tile
 // counts: two loads) and gallops outwards before bisecting.

@@ -60,7 +60,8 @@ struct EmitterConst
     uint32_t* cols;   // column 0 of this emitter's segment; column c starts at cols + c * stride
     float* vtx;       // vertex stream of this emitter: 36 floats per quad
     const float* uv;  // frame_count * 4 floats (u1, v1, u2, v2)
-    uint32_t stride;  // words between columns (slab capacity)
+    uint32_t stride;  // words between columns: the slab capacity (plain SoA) or the block size (blocked SoA)
+    uint32_t block_shift; // 0: plain SoA.  k > 0: blocked SoA, 2^k particles x 34 columns contiguous per block
     uint32_t capacity;
     uint32_t flags;
     uint32_t frame_count;
@@ -80,10 +81,18 @@ struct EmitterDev
 struct UpdateItem
 {
     EmitterDev* dev;
+    uint32_t* cols;       // copied from the emitter's record so a CTA can start loading after ONE dependent fetch
     float elapsed_ms;
-    uint32_t parity; // which cnt[] copy is current on entry
+    uint32_t parity;      // which cnt[] copy is current on entry
     uint32_t tile_begin;
-    uint32_t pad;
+    uint32_t stride;
+    uint32_t block_shift;
+    uint32_t seg_capacity; // padded segment size: any slot below it lies inside the slab and may be read
+    uint32_t flags;
+    uint32_t frame_count;
+    float percent_per_frame;
+    float frame_duration_secs;
+    uint32_t pad[2];
 };
 
 struct SpawnItem
@@ -130,6 +139,11 @@ struct CountQuery
 };
 // out[2*i] = live count, out[2*i+1] = quads written by the last draw, for each query.
 void launch_gather_counts(void* stream, const CountQuery* q, uint32_t n, uint32_t* out);
+// Device layout <-> the ABI's exchange layout (T3D_NUM_COLUMNS columns of `host_stride` words).
+void launch_export_state(void* stream, const uint32_t* cols, uint32_t stride, uint32_t block_shift, uint32_t n, uint32_t* out,
+                         uint32_t host_stride);
+void launch_import_state(void* stream, uint32_t* cols, uint32_t stride, uint32_t block_shift, uint32_t n, const uint32_t* in,
+                         uint32_t host_stride);
 
 // The counter-based generator of T3D_RNG_DEVICE (host + device).
 #if defined(__CUDACC__)

@@ -133,9 +133,9 @@ __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __rest
     uint32_t frame = 0; // :357-364
     if (P.frame_random_offset > 0) frame = (uint32_t)src.next() % P.frame_random_offset;
 
-    uint32_t* cols = d->c.cols;
     const size_t stride = d->c.stride;
-    const size_t slot = count0 + i;
+    uint32_t* const cols = particle_base(d->c.cols, d->c.block_shift, count0 + i); // this particle's word of column 0
+    const size_t slot = 0;
     auto F = [&](int c, float v) { cols[(size_t)c * stride + slot] = __float_as_uint(v); };
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -196,14 +196,14 @@ __global__ void __launch_bounds__(kDrawThreads)
     const uint32_t i = first + tid;
     if (i < N)
     {
-        const uint32_t* cols = d->c.cols;
+        const uint32_t* cols = particle_base(d->c.cols, d->c.block_shift, i);
         const size_t stride = d->c.stride;
-        auto LF = [&](int c) { return __ldcs(reinterpret_cast<const float*>(cols + (size_t)c * stride + i)); };
+        auto LF = [&](int c) { return __ldcs(reinterpret_cast<const float*>(cols + (size_t)c * stride)); };
         const float pos[3] = { LF(T3D_COL_POSITION), LF(T3D_COL_POSITION + 1), LF(T3D_COL_POSITION + 2) };
         const float size = LF(T3D_COL_SIZE);
         const float color[4] = { LF(T3D_COL_COLOR), LF(T3D_COL_COLOR + 1), LF(T3D_COL_COLOR + 2), LF(T3D_COL_COLOR + 3) };
         const float angle = LF(T3D_COL_ANGLE);
-        const uint32_t frame = __ldcs(cols + (size_t)T3D_COL_FRAME * stride + i);
+        const uint32_t frame = __ldcs(cols + (size_t)T3D_COL_FRAME * stride);
         const float* uv = uv_in_smem ? (s_uv + frame * 4u) : (uv_g + (size_t)frame * 4u);
         const float u1 = uv[0], v1 = uv[1], u2 = uv[2], v2 = uv[3];
 
@@ -323,13 +323,15 @@ __global__ void __launch_bounds__(256) k_latch(const DrawItem* __restrict__ item
         const EmitterDev* d = it.dev;
         if (!(d->c.flags & kFlagMaySpin)) continue;
         const uint32_t N = d->cnt[it.parity].count;
-        const uint32_t* ang = d->c.cols + (size_t)T3D_COL_ANGLE * d->c.stride;
+        const uint32_t* ang0 = d->c.cols + (size_t)T3D_COL_ANGLE * d->c.stride;
+        const uint32_t shift = d->c.block_shift;
+        auto ANG = [&](uint32_t i) { return __uint_as_float(*particle_base(ang0, shift, i)); };
         for (uint32_t base = 0; base < N; base += 256)
         {
             if (threadIdx.x == 0) s_min = 0xffffffffu;
             __syncthreads();
             const uint32_t i = base + threadIdx.x;
-            if (i < N && __uint_as_float(ang[i]) != 0.0f) atomicMin(&s_min, i);
+            if (i < N && ANG(i) != 0.0f) atomicMin(&s_min, i);
             __syncthreads();
             const uint32_t m = s_min;
             __syncthreads();
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(256) k_latch(const DrawItem* __restrict__ item
                     frozen->m[0] = (r[1] * u[2]) - (r[2] * u[1]);
                     frozen->m[1] = (r[2] * u[0]) - (r[0] * u[2]);
                     frozen->m[2] = (r[0] * u[1]) - (r[1] * u[0]);
-                    frozen->m[3] = __uint_as_float(ang[m]);
+                    frozen->m[3] = ANG(m);
                     frozen->latched = 2; // 2 = axis/angle found, matrix pending on the host
                 }
                 return;
@@ -390,6 +392,36 @@ __global__ void k_gather_counts(const CountQuery* __restrict__ q, uint32_t n, ui
 void launch_gather_counts(void* stream, const CountQuery* q, uint32_t n, uint32_t* out)
 {
     k_gather_counts<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(q, n, out);
+}
+
+// Exchange with the ABI's layout (download_state / upload_state): one thread per particle, all columns.
+template <bool EXPORT>
+__global__ void k_exchange_state(uint32_t* cols, uint32_t stride, uint32_t block_shift, uint32_t n, uint32_t* host_layout,
+                                 uint32_t host_stride)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t* p = particle_base(cols, block_shift, i);
+#pragma unroll 2
+    for (int c = 0; c < T3D_NUM_COLUMNS; ++c)
+    {
+        if (EXPORT)
+            host_layout[(size_t)c * host_stride + i] = p[(size_t)c * stride];
+        else
+            p[(size_t)c * stride] = host_layout[(size_t)c * host_stride + i];
+    }
+}
+
+void launch_export_state(void* stream, const uint32_t* cols, uint32_t stride, uint32_t block_shift, uint32_t n, uint32_t* out,
+                         uint32_t host_stride)
+{
+    if (n) k_exchange_state<true><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(const_cast<uint32_t*>(cols), stride, block_shift, n, out, host_stride);
+}
+
+void launch_import_state(void* stream, uint32_t* cols, uint32_t stride, uint32_t block_shift, uint32_t n, const uint32_t* in,
+                         uint32_t host_stride)
+{
+    if (n) k_exchange_state<false><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(cols, stride, block_shift, n, const_cast<uint32_t*>(in), host_stride);
 }
 
 } // namespace t3d

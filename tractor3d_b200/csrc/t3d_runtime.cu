@@ -108,6 +108,7 @@ struct t3d_ctx
 
     std::vector<Slab> slabs;
     uint32_t next_slab_particles{ 1u << 20 };
+    uint32_t block_shift{ 0 }; // particle storage layout: 0 plain SoA, k blocked SoA with 2^k-particle blocks
 
     std::vector<EmitterDev*> dev_chunks; // arena of device records, kDevChunk per allocation
     uint32_t dev_used{ 0 };
@@ -253,7 +254,8 @@ static int staging_release(t3d_ctx* c, StagingSlot* s)
 
 static int alloc_segment(t3d_ctx* c, uint32_t capacity, int* slab_out, uint32_t* offset_out, uint32_t* padded_out)
 {
-    uint32_t padded = (std::max(capacity, 1u) + kSegmentAlign - 1) / kSegmentAlign * kSegmentAlign;
+    const uint32_t align = std::max<uint32_t>(kSegmentAlign, c->block_shift ? (1u << c->block_shift) : 0u);
+    uint32_t padded = (std::max(capacity, 1u) + align - 1) / align * align;
     for (size_t i = 0; i < c->slabs.size(); ++i)
     {
         Slab& s = c->slabs[i];
@@ -268,7 +270,8 @@ static int alloc_segment(t3d_ctx* c, uint32_t capacity, int* slab_out, uint32_t*
         }
     }
     uint64_t want = std::max<uint64_t>(padded, c->next_slab_particles);
-    want = (want + 1023) / 1024 * 1024;
+    const uint64_t gran = std::max<uint64_t>(1024, c->block_shift ? (1ull << c->block_shift) : 0ull);
+    want = (want + gran - 1) / gran * gran;
     if (want > 0x7fffffffull) return fail(T3D_ERR_CAPACITY, "emitter capacity %u exceeds the 2^31 particle slab limit", capacity);
     Slab s;
     s.capacity = (uint32_t)want;
@@ -352,10 +355,12 @@ static void fill_const(const t3d_emitter* e, EmitterConst* k)
     const t3d_ctx* c = e->ctx;
     const Slab& s = c->slabs[e->slab];
     memset(k, 0, sizeof(*k));
-    k->cols = s.cols + e->seg_offset;
+    // blocked SoA: segment offsets are whole blocks, and a block holds all 34 columns of its particles
+    k->cols = c->block_shift ? s.cols + (size_t)e->seg_offset * T3D_NUM_COLUMNS : s.cols + e->seg_offset;
+    k->block_shift = c->block_shift;
     k->vtx = s.vtx ? s.vtx + (size_t)e->seg_offset * T3D_FLOATS_PER_QUAD : nullptr;
     k->uv = e->uv_dev;
-    k->stride = s.capacity;
+    k->stride = c->block_shift ? (1u << c->block_shift) : s.capacity;
     k->capacity = e->p.particle_count_max;
     k->flags = (e->p.sprite_animated ? kFlagAnimated : 0u) | (e->p.sprite_looped ? kFlagLooped : 0u) |
                (e->may_rotate ? kFlagMayRotate : 0u) | (e->may_spin ? kFlagMaySpin : 0u);
@@ -585,12 +590,22 @@ static int launch_updates(t3d_ctx* c)
         t3d_emitter* e = op.e;
         T3D_TRY(sync_const(e));
         UpdateItem& it = items[k];
+        EmitterConst ec;
+        fill_const(e, &ec);
+        memset(&it, 0, sizeof(it));
         it.dev = e->dev;
+        it.cols = ec.cols;
+        it.stride = ec.stride;
+        it.block_shift = ec.block_shift;
+        it.seg_capacity = e->seg_capacity;
+        it.flags = ec.flags;
+        it.frame_count = ec.frame_count;
+        it.percent_per_frame = ec.percent_per_frame;
+        it.frame_duration_secs = ec.frame_duration_secs;
         it.elapsed_ms = op.elapsed_ms;
         it.parity = e->parity;
         e->parity ^= 1u;
         it.tile_begin = tiles;
-        it.pad = 0;
         queries[k].dev = e->dev;
         queries[k].parity = e->parity; // where this launch leaves the new count
         queries[k].pad = 0;
@@ -948,6 +963,13 @@ int t3d_ctx_create(int device, void* cuda_stream, t3d_ctx** out)
         return fail(T3D_ERR_CUDA, "t3d_ctx_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     memset(c->frozen_m, 0, sizeof(c->frozen_m));
+    // T3D_LAYOUT_BLOCK=2^k selects the blocked struct-of-arrays layout (measured equal to plain SoA on B200).
+    if (const char* env = getenv("T3D_LAYOUT_BLOCK"))
+    {
+        const int b = atoi(env);
+        for (uint32_t k = 5; k <= 12; ++k)
+            if (b == (1 << k)) c->block_shift = k;
+    }
     *out = c;
     return T3D_OK;
 }
@@ -1492,9 +1514,26 @@ int t3d_emitter_download_state(t3d_emitter* e, uint32_t* out, size_t stride, uin
     if (!out || n == 0) return T3D_OK;
     if (stride < n) return fail(T3D_ERR_INVALID, "download_state: stride %zu < live count %u", stride, n);
     const Slab& s = c->slabs[e->slab];
-    T3D_CUDA(cudaMemcpy2DAsync(out, stride * sizeof(uint32_t), s.cols + e->seg_offset, (size_t)s.capacity * sizeof(uint32_t),
-                               (size_t)n * sizeof(uint32_t), T3D_NUM_COLUMNS, cudaMemcpyDeviceToHost, c->stream));
-    T3D_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->block_shift == 0)
+    {
+        T3D_CUDA(cudaMemcpy2DAsync(out, stride * sizeof(uint32_t), s.cols + e->seg_offset, (size_t)s.capacity * sizeof(uint32_t),
+                                   (size_t)n * sizeof(uint32_t), T3D_NUM_COLUMNS, cudaMemcpyDeviceToHost, c->stream));
+        T3D_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    else
+    {
+        EmitterConst k;
+        fill_const(e, &k);
+        uint32_t* tmp = nullptr;
+        T3D_CUDA(cudaMalloc((void**)&tmp, (size_t)n * T3D_NUM_COLUMNS * sizeof(uint32_t)));
+        launch_export_state(c->stream, k.cols, k.stride, k.block_shift, n, tmp, n);
+        c->launches++;
+        cudaError_t err = cudaMemcpy2DAsync(out, stride * sizeof(uint32_t), tmp, (size_t)n * sizeof(uint32_t), (size_t)n * sizeof(uint32_t),
+                                            T3D_NUM_COLUMNS, cudaMemcpyDeviceToHost, c->stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(c->stream);
+        cudaFree(tmp);
+        if (err != cudaSuccess) return fail(T3D_ERR_CUDA, "download_state: %s", cudaGetErrorString(err));
+    }
     c->d2h_bytes += (size_t)n * T3D_NUM_COLUMNS * sizeof(uint32_t);
     return T3D_OK;
 }
@@ -1508,11 +1547,28 @@ int t3d_emitter_upload_state(t3d_emitter* e, const uint32_t* in, size_t stride, 
     T3D_TRY(flush(c));
     T3D_TRY(use_device(c));
     const Slab& s = c->slabs[e->slab];
-    if (count)
+    uint32_t* tmp = nullptr;
+    if (count && c->block_shift == 0)
         T3D_CUDA(cudaMemcpy2DAsync(s.cols + e->seg_offset, (size_t)s.capacity * sizeof(uint32_t), in, stride * sizeof(uint32_t),
                                    (size_t)count * sizeof(uint32_t), T3D_NUM_COLUMNS, cudaMemcpyHostToDevice, c->stream));
+    else if (count)
+    {
+        EmitterConst k;
+        fill_const(e, &k);
+        T3D_CUDA(cudaMalloc((void**)&tmp, (size_t)count * T3D_NUM_COLUMNS * sizeof(uint32_t)));
+        cudaError_t err = cudaMemcpy2DAsync(tmp, (size_t)count * sizeof(uint32_t), in, stride * sizeof(uint32_t),
+                                            (size_t)count * sizeof(uint32_t), T3D_NUM_COLUMNS, cudaMemcpyHostToDevice, c->stream);
+        if (err != cudaSuccess)
+        {
+            cudaFree(tmp);
+            return fail(T3D_ERR_CUDA, "upload_state: %s", cudaGetErrorString(err));
+        }
+        launch_import_state(c->stream, k.cols, k.stride, k.block_shift, count, tmp, count);
+        c->launches++;
+    }
     T3D_CUDA(cudaMemcpyAsync(&e->dev->cnt[e->parity].count, &count, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
     T3D_CUDA(cudaStreamSynchronize(c->stream));
+    if (tmp) cudaFree(tmp);
     c->h2d_bytes += (size_t)count * T3D_NUM_COLUMNS * sizeof(uint32_t) + sizeof(uint32_t);
     e->count_ub = count;
     e->count_exact = true;

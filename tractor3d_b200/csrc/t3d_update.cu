@@ -94,6 +94,66 @@ struct Vec<1>
     static __device__ __forceinline__ void st(uint32_t* p, const int* a) { __stcs(reinterpret_cast<int*>(p), a[0]); }
 };
 
+// ---- register-free prefetch (ASYNC variants) -----------------------------------------------------------
+// Each thread copies the 16 bytes it owns of every input column straight from global to shared memory with
+// cp.async (LDGSTS), one commit group per particle group, two groups in flight per thread.  The bytes in flight
+// per SM are then bounded by shared memory (2 CTAs x 2 stages x 48 KB), not by registers.  A thread only ever
+// reads back its own 16-byte slots, so no block barrier is needed: cp.async.wait_group is the only sync.
+enum : int
+{
+    RC_EST = 0, RC_POS = 1, RC_VEL = 4, RC_ACC = 7, RC_SPIN = 10, RC_ANGLE = 11, RC_CS = 12, RC_CE = 16, RC_SS = 20,
+    RC_SE = 21, RC_TF = 22, RC_FRAME = 23, RC_COUNT = 24
+};
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// slot(c): this thread's float4 of ring column c in the given stage
+template <int THREADS>
+struct Ring
+{
+    float4* base; // [2][RC_COUNT][THREADS]
+    uint32_t tid;
+    __device__ __forceinline__ float4* slot(int stage, int c) const { return base + ((size_t)(stage * RC_COUNT + c) * THREADS + tid); }
+    __device__ __forceinline__ void issue(int stage, const uint32_t* g, size_t stride, bool animated) const
+    {
+        auto G = [&](int col) { return g + (size_t)col * stride; };
+        cp_async16(slot(stage, RC_EST), G(T3D_COL_ENERGY_START));
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            cp_async16(slot(stage, RC_POS + k), G(T3D_COL_POSITION + k));
+            cp_async16(slot(stage, RC_VEL + k), G(T3D_COL_VELOCITY + k));
+            cp_async16(slot(stage, RC_ACC + k), G(T3D_COL_ACCELERATION + k));
+        }
+        cp_async16(slot(stage, RC_SPIN), G(T3D_COL_ROT_PER_PARTICLE_SPEED));
+        cp_async16(slot(stage, RC_ANGLE), G(T3D_COL_ANGLE));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            cp_async16(slot(stage, RC_CS + k), G(T3D_COL_COLOR_START + k));
+            cp_async16(slot(stage, RC_CE + k), G(T3D_COL_COLOR_END + k));
+        }
+        cp_async16(slot(stage, RC_SS), G(T3D_COL_SIZE_START));
+        cp_async16(slot(stage, RC_SE), G(T3D_COL_SIZE_END));
+        if (animated)
+        {
+            cp_async16(slot(stage, RC_TF), G(T3D_COL_TIME_ON_FRAME));
+            cp_async16(slot(stage, RC_FRAME), G(T3D_COL_FRAME));
+        }
+    }
+};
+__device__ __forceinline__ void unpack4(const float4& v, float* a) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+__device__ __forceinline__ void unpack4(const float4& v, int* a)
+{
+    a[0] = __float_as_int(v.x); a[1] = __float_as_int(v.y); a[2] = __float_as_int(v.z); a[3] = __float_as_int(v.w);
+}
+
 // What one thread holds of one V-particle group.  The record is processed in two halves -- motion (position,
 // velocity, acceleration, angle) and appearance (colour, size, sprite frame) -- each loaded, computed and stored
 // before the other is touched, so that only half of the record occupies registers at a time and more CTAs fit
@@ -118,13 +178,24 @@ struct Motion
         Vec<V>::ld(col(T3D_COL_ACCELERATION + 2), az);
         Vec<V>::ld(col(T3D_COL_ROT_PER_PARTICLE_SPEED), spin);
         Vec<V>::ld(col(T3D_COL_ANGLE), ang);
-        if (may_rotate)
-        {
-            Vec<V>::ld(col(T3D_COL_ROTATION_AXIS + 0), rx);
-            Vec<V>::ld(col(T3D_COL_ROTATION_AXIS + 1), ry);
-            Vec<V>::ld(col(T3D_COL_ROTATION_AXIS + 2), rz);
-            Vec<V>::ld(col(T3D_COL_ROTATION_SPEED), rs);
-        }
+        if (may_rotate) load_rotation(base, stride);
+    }
+    __device__ __forceinline__ void load_rotation(const uint32_t* base, size_t stride)
+    {
+        auto col = [&](int c) -> const uint32_t* { return base + (size_t)c * stride; };
+        Vec<V>::ld(col(T3D_COL_ROTATION_AXIS + 0), rx);
+        Vec<V>::ld(col(T3D_COL_ROTATION_AXIS + 1), ry);
+        Vec<V>::ld(col(T3D_COL_ROTATION_AXIS + 2), rz);
+        Vec<V>::ld(col(T3D_COL_ROTATION_SPEED), rs);
+    }
+    template <int THREADS>
+    __device__ __forceinline__ void load_ring(const Ring<THREADS>& r, int stage) // V == 4
+    {
+        unpack4(*r.slot(stage, RC_POS + 0), px); unpack4(*r.slot(stage, RC_POS + 1), py); unpack4(*r.slot(stage, RC_POS + 2), pz);
+        unpack4(*r.slot(stage, RC_VEL + 0), vx); unpack4(*r.slot(stage, RC_VEL + 1), vy); unpack4(*r.slot(stage, RC_VEL + 2), vz);
+        unpack4(*r.slot(stage, RC_ACC + 0), ax); unpack4(*r.slot(stage, RC_ACC + 1), ay); unpack4(*r.slot(stage, RC_ACC + 2), az);
+        unpack4(*r.slot(stage, RC_SPIN), spin);
+        unpack4(*r.slot(stage, RC_ANGLE), ang);
     }
 };
 template <int V>
@@ -153,13 +224,31 @@ struct Appearance
             Vec<V>::ld(col(T3D_COL_FRAME), fr);
         }
     }
+    template <int THREADS>
+    __device__ __forceinline__ void load_ring(const Ring<THREADS>& r, int stage, bool animated) // V == 4
+    {
+        unpack4(*r.slot(stage, RC_EST), est);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+        {
+            unpack4(*r.slot(stage, RC_CS + c), cs[c]);
+            unpack4(*r.slot(stage, RC_CE + c), ce[c]);
+        }
+        unpack4(*r.slot(stage, RC_SS), ss);
+        unpack4(*r.slot(stage, RC_SE), se);
+        if (animated)
+        {
+            unpack4(*r.slot(stage, RC_TF), tf);
+            unpack4(*r.slot(stage, RC_FRAME), fr);
+        }
+    }
 };
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
 
 // V = particles per thread per group, THREADS per CTA, SUB = groups per thread: a tile is V*THREADS*SUB
 // consecutive particles of one emitter and costs one look-back, so the scan frontier only has to advance
 // one tile per V*THREADS*SUB particles streamed.
-template <int V, int THREADS, int SUB, int MIN_BLOCKS>
+template <int V, int THREADS, int SUB, int MIN_BLOCKS, bool ASYNC, bool TICKET>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     k_update(const UpdateItem* __restrict__ items, uint32_t n_items, uint32_t total_tiles,
              unsigned long long* __restrict__ tile_status, uint32_t* __restrict__ ticket, uint32_t ticket_base,
@@ -175,20 +264,71 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     // (offset from the tile's first slot; kNoMove: nothing to copy).
     __shared__ unsigned short s_move[TILE];
     constexpr unsigned short kNoMove = 0xFFFFu;
+    // Per-thread results of phase A (decremented energies, dead particles preceding each group), parked in shared
+    // memory so that phase B can be a rolled loop: unrolling it SUB times overflowed the instruction cache.
+    __shared__ __align__(16) int s_en[SUB * THREADS * V];
+    __shared__ uint32_t s_base[SUB * THREADS];
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    // Tile order = block order.  The look-back below only ever waits for tiles with a smaller id; like CUB's
+    // single-pass scan this relies on CTAs being dispatched in increasing blockIdx order.  TICKET hands the ids out
+    // with an atomic instead (an extra round trip and a barrier before the first load can be issued).
+    uint32_t tile = blockIdx.x;
+    if (TICKET)
+    {
+        if (tid == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
+        __syncthreads();
+        tile = s_tile;
+    }
     if (tile >= total_tiles) return;
 
+    // One dependent fetch (the launch descriptor) and the loads can start; the live count is fetched in parallel.
     const UpdateItem& it = items[find_item(items, n_items, tile, total_tiles)];
-    EmitterDev* d = it.dev;
+    EmitterDev* const d = it.dev;
     const uint32_t parity = it.parity;
-    const uint32_t N = d->cnt[parity].count;
+    uint32_t* const cols = it.cols;
+    const size_t stride = it.stride;
+    const uint32_t bshift = it.block_shift;
+    const uint32_t cap = it.seg_capacity;
     const uint32_t jt = tile - it.tile_begin; // tile index inside the emitter
     const uint32_t first = jt * TILE;
+    const uint32_t flags = it.flags;
+    const bool animated = (flags & kFlagAnimated) != 0;
+    const bool looped = (flags & kFlagLooped) != 0;
+    const bool may_rotate = (flags & kFlagMayRotate) != 0;
+    const float elapsed_ms = it.elapsed_ms;
+    const float secs = elapsed_ms * 0.001f; // PE.cpp:727
+    const uint32_t N = d->cnt[parity].count;
+
+    // ---- phase A: the energy column of the whole tile -> dead flags (PE.cpp:753-755: `long -= float`, `> 0`) ----
+    // Issued before the live count has arrived: every slot below the padded segment size is safe to read.
+    int en[SUB][V];
+#pragma unroll
+    for (int s = 0; s < SUB; ++s)
+    {
+        const uint32_t k0 = first + s * GROUP + tid * V;
+        if (k0 < cap) Vec<V>::ld(particle_base(cols, bshift, k0) + (size_t)T3D_COL_ENERGY * stride, en[s]);
+    }
+    // The first group(s) are requested now so that they are in flight while the scan and look-back run.
+    Motion<V> m;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    Ring<THREADS> ring{ reinterpret_cast<float4*>(dyn_smem), tid };
+    if (ASYNC)
+    {
+#pragma unroll
+        for (int s = 0; s < (SUB < 2 ? SUB : 2); ++s)
+        {
+            const uint32_t k0 = first + s * GROUP + tid * V;
+            if (k0 < cap) ring.issue(s, particle_base(cols, bshift, k0), stride, animated);
+            cp_async_commit();
+        }
+    }
+    else
+    {
+        const uint32_t k0 = first + tid * V;
+        if (k0 < cap) m.load(particle_base(cols, bshift, k0), stride, may_rotate);
+    }
     if (first >= N)
     {
         if (jt == 0 && tid == 0)
@@ -198,31 +338,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         }
         return;
     }
-
-    const float elapsed_ms = it.elapsed_ms;
-    const float secs = elapsed_ms * 0.001f; // PE.cpp:727
-    const uint32_t flags = d->c.flags;
-    const bool animated = (flags & kFlagAnimated) != 0;
-    const bool looped = (flags & kFlagLooped) != 0;
-    const bool may_rotate = (flags & kFlagMayRotate) != 0;
-    uint32_t* const cols = d->c.cols;
-    const size_t stride = d->c.stride;
-
-    // ---- phase A: the energy column of the whole tile -> dead flags (PE.cpp:753-755: `long -= float`, `> 0`) ----
-    int en[SUB][V];
-#pragma unroll
-    for (int s = 0; s < SUB; ++s)
-    {
-        const uint32_t k0 = first + s * GROUP + tid * V;
-        if (k0 < N) Vec<V>::ld(cols + (size_t)T3D_COL_ENERGY * stride + k0, en[s]);
-    }
-    // The motion half of the first group is requested now so that it is in flight while the scan and look-back run.
-    Motion<V> m;
-    {
-        const uint32_t k0 = first + tid * V;
-        if (k0 < N) m.load(cols + k0, stride, may_rotate);
-    }
-    uint32_t dead_bits = 0; // bit s*V+l: particle is valid and dead
     uint32_t cnt[SUB];
 #pragma unroll
     for (int s = 0; s < SUB; ++s)
@@ -235,11 +350,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             if (k0 + l < N)
             {
                 en[s][l] = __float2int_rz((float)en[s][l] - elapsed_ms);
-                if (!(en[s][l] > 0))
-                {
-                    dead_bits |= 1u << (s * V + l);
-                    cnt[s]++;
-                }
+                if (!(en[s][l] > 0)) cnt[s]++;
             }
         }
     }
@@ -274,6 +385,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             tile_dead += v;
         }
         base[s] = before + incl[s] - cnt[s];
+        s_base[s * THREADS + tid] = base[s];
+#pragma unroll
+        for (int l = 0; l < V; ++l) s_en[(s * THREADS + tid) * V + l] = en[s][l];
     }
 
     for (uint32_t r = tid; r < tile_dead; r += THREADS) s_move[r] = kNoMove;
@@ -326,15 +440,19 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     const uint32_t tile_excl = s_excl;
 
     // ---- phase B: stream the groups ----
-    const float ppf = d->c.percent_per_frame;
-    const float dur = d->c.frame_duration_secs;
-    const uint32_t frame_count = d->c.frame_count;
-#pragma unroll
+    const float ppf = it.percent_per_frame;
+    const float dur = it.frame_duration_secs;
+    const uint32_t frame_count = it.frame_count;
+#pragma unroll 1
     for (int s = 0; s < SUB; ++s)
     {
         const uint32_t k0 = first + s * GROUP + tid * V;
         if (k0 >= N) break;
-        uint32_t* const gbase = cols + k0;
+        int e4[V];
+#pragma unroll
+        for (int l = 0; l < V; ++l) e4[l] = s_en[(s * THREADS + tid) * V + l];
+        const uint32_t base_s = s_base[s * THREADS + tid];
+        uint32_t* const gbase = particle_base(cols, bshift, k0);
         auto col = [&](int c) -> uint32_t* { return gbase + (size_t)c * stride; };
 
         // which originals the reference's loop examines, and what lands in each slot
@@ -344,12 +462,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         uint32_t D[V];
         bool all_store = true;
         {
-            uint32_t run = tile_excl + base[s];
+            uint32_t run = tile_excl + base_s;
 #pragma unroll
             for (int l = 0; l < V; ++l)
             {
                 valid[l] = k0 + l < N;
-                alive[l] = valid[l] && !((dead_bits >> (s * V + l)) & 1u);
+                alive[l] = valid[l] && e4[l] > 0;
                 D[l] = run;
                 examined[l] = valid[l] && (k0 + l + run < N);
                 if (examined[l] && !alive[l])
@@ -364,7 +482,17 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         }
 
         // -- motion half: PE.cpp:757-774 --
-        if (s > 0) m.load(gbase, stride, may_rotate);
+        if (ASYNC)
+        {
+            if (s + 1 < SUB)
+                cp_async_wait<1>(); // group s has landed; group s+1 may still be in flight
+            else
+                cp_async_wait<0>();
+            m.load_ring(ring, s & 1);
+            if (may_rotate) m.load_rotation(gbase, stride);
+        }
+        else if (s > 0)
+            m.load(gbase, stride, may_rotate);
 #pragma unroll
         for (int l = 0; l < V; ++l)
         {
@@ -425,13 +553,25 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 
         // -- appearance half: PE.cpp:777-819 --
         Appearance<V> a;
-        a.load(gbase, stride, animated);
+        if (ASYNC)
+        {
+            a.load_ring(ring, s & 1, animated);
+            // This stage's slots are consumed: refill them with the group after next.
+            if (s + 2 < SUB)
+            {
+                const uint32_t kn = first + (s + 2) * GROUP + tid * V;
+                if (kn < N) ring.issue(s & 1, particle_base(cols, bshift, kn), stride, animated);
+                cp_async_commit();
+            }
+        }
+        else
+            a.load(gbase, stride, animated);
         float col_out[4][V], size_out[V];
 #pragma unroll
         for (int l = 0; l < V; ++l)
         {
             if (!alive[l]) continue;
-            const float percent = 1.0f - ((float)en[s][l] / (float)a.est[l]); // :777
+            const float percent = 1.0f - ((float)e4[l] / (float)a.est[l]); // :777
 #pragma unroll
             for (int c = 0; c < 4; ++c) col_out[c][l] = a.cs[c][l] + (a.ce[c][l] - a.cs[c][l]) * percent; // :779-782
             size_out[l] = a.ss[l] + (a.se[l] - a.ss[l]) * percent;                                          // :784
@@ -458,7 +598,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         }
         if (all_store)
         {
-            Vec<V>::st(col(T3D_COL_ENERGY), en[s]);
+            Vec<V>::st(col(T3D_COL_ENERGY), e4);
 #pragma unroll
             for (int c = 0; c < 4; ++c) Vec<V>::st(col(T3D_COL_COLOR + c), col_out[c]);
             Vec<V>::st(col(T3D_COL_SIZE), size_out);
@@ -475,7 +615,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             {
                 if (!(examined[l] && alive[l])) continue;
                 auto S = [&](int c, float v) { col(c)[l] = __float_as_uint(v); };
-                col(T3D_COL_ENERGY)[l] = (uint32_t)en[s][l];
+                col(T3D_COL_ENERGY)[l] = (uint32_t)e4[l];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) S(T3D_COL_COLOR + c, col_out[c][l]);
                 S(T3D_COL_SIZE, size_out[l]);
@@ -518,10 +658,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             const uint32_t r = t - c * tile_dead;
             const unsigned short off = s_move[r];
             if (off != kNoMove)
-            {
-                uint32_t* column = cols + (size_t)c * stride;
-                column[first + off] = column[src_last - r];
-            }
+                particle_base(cols, bshift, first + off)[(size_t)c * stride] = particle_base(cols, bshift, src_last - r)[(size_t)c * stride];
         }
     }
 }
@@ -537,19 +674,51 @@ struct UpdateVariant
     void (*launch)(cudaStream_t, uint32_t, const UpdateItem*, uint32_t, unsigned long long*, uint32_t*, uint32_t, uint32_t);
 };
 
+// T3D_UPDATE_TICKET=1: hand tile ids out with an atomic ticket instead of relying on block dispatch order.
+static bool use_ticket()
+{
+    static int v = -1;
+    if (v < 0)
+    {
+        const char* env = getenv("T3D_UPDATE_TICKET");
+        v = (env && env[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 template <int V, int THREADS, int SUB, int MIN_BLOCKS>
 static void launch_variant(cudaStream_t s, uint32_t tiles, const UpdateItem* items, uint32_t n_items,
                            unsigned long long* status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch)
 {
-    k_update<V, THREADS, SUB, MIN_BLOCKS><<<tiles, THREADS, 0, s>>>(items, n_items, tiles, status, ticket, ticket_base, epoch);
+    if (use_ticket())
+        k_update<V, THREADS, SUB, MIN_BLOCKS, false, true><<<tiles, THREADS, 0, s>>>(items, n_items, tiles, status, ticket, ticket_base, epoch);
+    else
+        k_update<V, THREADS, SUB, MIN_BLOCKS, false, false><<<tiles, THREADS, 0, s>>>(items, n_items, tiles, status, ticket, ticket_base, epoch);
+}
+
+template <int THREADS, int SUB, int MIN_BLOCKS>
+static void launch_async(cudaStream_t s, uint32_t tiles, const UpdateItem* items, uint32_t n_items,
+                         unsigned long long* status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch)
+{
+    constexpr size_t smem = 2 * (size_t)RC_COUNT * THREADS * sizeof(float4);
+    static bool configured = false;
+    if (!configured)
+    {
+        cudaFuncSetAttribute(k_update<4, THREADS, SUB, MIN_BLOCKS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    k_update<4, THREADS, SUB, MIN_BLOCKS, true, false><<<tiles, THREADS, smem, s>>>(items, n_items, tiles, status, ticket, ticket_base, epoch);
 }
 
 #define T3D_VARIANT(V, T, S, B) { "v" #V "t" #T "s" #S "b" #B, V * T * S, launch_variant<V, T, S, B> }
+#define T3D_ASYNC(T, S, B) { "a4t" #T "s" #S "b" #B, 4 * T * S, launch_async<T, S, B> }
 static const UpdateVariant kVariants[] = {
     T3D_VARIANT(4, 128, 4, 4), // default
-    T3D_VARIANT(4, 128, 1, 4), T3D_VARIANT(4, 128, 2, 4), T3D_VARIANT(4, 128, 8, 4), T3D_VARIANT(4, 128, 4, 6),
-    T3D_VARIANT(4, 128, 8, 6), T3D_VARIANT(4, 256, 4, 3), T3D_VARIANT(4, 256, 2, 2), T3D_VARIANT(4, 64, 8, 8),
-    T3D_VARIANT(2, 256, 4, 4), T3D_VARIANT(2, 256, 8, 4), T3D_VARIANT(2, 128, 8, 8), T3D_VARIANT(4, 128, 4, 8),
+    T3D_ASYNC(128, 4, 2), T3D_ASYNC(128, 8, 2), T3D_ASYNC(64, 8, 4), T3D_ASYNC(64, 16, 4), T3D_ASYNC(64, 8, 5),
+    T3D_ASYNC(256, 4, 1), T3D_ASYNC(96, 8, 3), T3D_ASYNC(32, 16, 9),
+    T3D_VARIANT(4, 128, 1, 4), T3D_VARIANT(4, 128, 2, 4), T3D_VARIANT(4, 128, 8, 4), T3D_VARIANT(4, 128, 4, 5),
+    T3D_VARIANT(4, 128, 4, 3), T3D_VARIANT(4, 256, 4, 2), T3D_VARIANT(4, 256, 2, 2), T3D_VARIANT(4, 64, 8, 8),
+    T3D_VARIANT(2, 256, 4, 4), T3D_VARIANT(2, 256, 8, 4), T3D_VARIANT(4, 64, 4, 8),
 };
 static int g_variant = -1;
 
