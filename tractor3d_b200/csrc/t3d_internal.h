@@ -110,8 +110,15 @@ struct SpawnItem
 struct DrawItem
 {
     EmitterDev* dev;
+    const uint32_t* cols; // copied from the emitter's record: one dependent fetch, then the loads can start
+    float* vtx;
+    const float* uv;
     uint32_t parity;
     uint32_t tile_begin;
+    uint32_t stride;
+    uint32_t block_shift;
+    uint32_t seg_capacity;
+    uint32_t frame_count;
     float right[3];
     float up[3];
 };

@@ -178,32 +178,41 @@ __global__ void __launch_bounds__(kDrawThreads)
     __shared__ float s_uv[kMaxSmemFrames * 4];
 
     const uint32_t tile = blockIdx.x;
+    const uint32_t tid = threadIdx.x;
     const DrawItem& it = items[find_item(items, n_items, tile, gridDim.x)];
     const EmitterDev* d = it.dev;
-    const uint32_t N = d->cnt[it.parity].count;
     const uint32_t first = (tile - it.tile_begin) * kDrawThreads;
-    const uint32_t tid = threadIdx.x;
-    if (first == 0 && tid == 0) const_cast<EmitterDev*>(d)->cnt[0].drawn = N;
-    if (first >= N) return;
+    const uint32_t i = first + tid;
+    const uint32_t N = d->cnt[it.parity].count;
 
-    const uint32_t frame_count = d->c.frame_count;
-    const float* __restrict__ uv_g = d->c.uv;
+    // This thread's particle, requested before the live count has arrived (any slot below the padded segment
+    // size is inside the slab and safe to read).
+    float pos[3] = { 0.0f, 0.0f, 0.0f }, color[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+    float size = 0.0f, angle = 0.0f;
+    uint32_t frame = 0;
+    if (i < it.seg_capacity)
+    {
+        const uint32_t* cols = particle_base(it.cols, it.block_shift, i);
+        const size_t stride = it.stride;
+        auto LF = [&](int c) { return __ldcs(reinterpret_cast<const float*>(cols + (size_t)c * stride)); };
+        pos[0] = LF(T3D_COL_POSITION); pos[1] = LF(T3D_COL_POSITION + 1); pos[2] = LF(T3D_COL_POSITION + 2);
+        size = LF(T3D_COL_SIZE);
+        color[0] = LF(T3D_COL_COLOR); color[1] = LF(T3D_COL_COLOR + 1); color[2] = LF(T3D_COL_COLOR + 2); color[3] = LF(T3D_COL_COLOR + 3);
+        angle = LF(T3D_COL_ANGLE);
+        frame = __ldcs(cols + (size_t)T3D_COL_FRAME * stride);
+    }
+
+    const uint32_t frame_count = it.frame_count;
+    const float* __restrict__ uv_g = it.uv;
     const bool uv_in_smem = frame_count <= (uint32_t)kMaxSmemFrames;
     if (uv_in_smem)
         for (uint32_t q = tid; q < frame_count * 4u; q += kDrawThreads) s_uv[q] = uv_g[q];
+    if (first == 0 && tid == 0) const_cast<EmitterDev*>(d)->cnt[0].drawn = N;
+    if (first >= N) return;
     __syncthreads();
 
-    const uint32_t i = first + tid;
     if (i < N)
     {
-        const uint32_t* cols = particle_base(d->c.cols, d->c.block_shift, i);
-        const size_t stride = d->c.stride;
-        auto LF = [&](int c) { return __ldcs(reinterpret_cast<const float*>(cols + (size_t)c * stride)); };
-        const float pos[3] = { LF(T3D_COL_POSITION), LF(T3D_COL_POSITION + 1), LF(T3D_COL_POSITION + 2) };
-        const float size = LF(T3D_COL_SIZE);
-        const float color[4] = { LF(T3D_COL_COLOR), LF(T3D_COL_COLOR + 1), LF(T3D_COL_COLOR + 2), LF(T3D_COL_COLOR + 3) };
-        const float angle = LF(T3D_COL_ANGLE);
-        const uint32_t frame = __ldcs(cols + (size_t)T3D_COL_FRAME * stride);
         const float* uv = uv_in_smem ? (s_uv + frame * 4u) : (uv_g + (size_t)frame * 4u);
         const float u1 = uv[0], v1 = uv[1], u2 = uv[2], v2 = uv[3];
 
@@ -285,7 +294,7 @@ __global__ void __launch_bounds__(kDrawThreads)
     }
     // The tile's vertices: nq quads * 144 B, contiguous in the emitter's vertex stream (16-byte aligned).
     const uint32_t nq = (N - first) < (uint32_t)kDrawThreads ? (N - first) : (uint32_t)kDrawThreads;
-    float4* __restrict__ dst = reinterpret_cast<float4*>(d->c.vtx + (size_t)first * T3D_FLOATS_PER_QUAD);
+    float4* __restrict__ dst = reinterpret_cast<float4*>(it.vtx + (size_t)first * T3D_FLOATS_PER_QUAD);
     if (OUT == 1)
     {
         // Make this thread's shared-memory writes visible to the async proxy, then let one thread issue the bulk store.

@@ -668,7 +668,17 @@ static int launch_draws(t3d_ctx* c)
         t3d_emitter* e = op.e;
         T3D_TRY(sync_const(e));
         DrawItem& it = items[k];
+        EmitterConst ec;
+        fill_const(e, &ec);
+        memset(&it, 0, sizeof(it));
         it.dev = e->dev;
+        it.cols = ec.cols;
+        it.vtx = ec.vtx;
+        it.uv = ec.uv;
+        it.stride = ec.stride;
+        it.block_shift = ec.block_shift;
+        it.seg_capacity = e->seg_capacity;
+        it.frame_count = ec.frame_count;
         it.parity = e->parity;
         it.tile_begin = tiles;
         memcpy(it.right, op.right, 12);

@@ -312,8 +312,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     }
     // The first group(s) are requested now so that they are in flight while the scan and look-back run.
     Motion<V> m;
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    Ring<THREADS> ring{ reinterpret_cast<float4*>(dyn_smem), tid };
+    // The ring starts on a 128-byte boundary so that a warp's 512-byte cp.async destination covers whole lines.
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    Ring<THREADS> ring{ reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(dyn_smem) + 127) & ~uintptr_t(127)), tid };
     if (ASYNC)
     {
 #pragma unroll
@@ -700,7 +701,7 @@ template <int THREADS, int SUB, int MIN_BLOCKS>
 static void launch_async(cudaStream_t s, uint32_t tiles, const UpdateItem* items, uint32_t n_items,
                          unsigned long long* status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch)
 {
-    constexpr size_t smem = 2 * (size_t)RC_COUNT * THREADS * sizeof(float4);
+    constexpr size_t smem = 2 * (size_t)RC_COUNT * THREADS * sizeof(float4) + 128;
     static bool configured = false;
     if (!configured)
     {
@@ -713,12 +714,13 @@ static void launch_async(cudaStream_t s, uint32_t tiles, const UpdateItem* items
 #define T3D_VARIANT(V, T, S, B) { "v" #V "t" #T "s" #S "b" #B, V * T * S, launch_variant<V, T, S, B> }
 #define T3D_ASYNC(T, S, B) { "a4t" #T "s" #S "b" #B, 4 * T * S, launch_async<T, S, B> }
 static const UpdateVariant kVariants[] = {
-    T3D_VARIANT(4, 128, 4, 4), // default
-    T3D_ASYNC(128, 4, 2), T3D_ASYNC(128, 8, 2), T3D_ASYNC(64, 8, 4), T3D_ASYNC(64, 16, 4), T3D_ASYNC(64, 8, 5),
-    T3D_ASYNC(256, 4, 1), T3D_ASYNC(96, 8, 3), T3D_ASYNC(32, 16, 9),
-    T3D_VARIANT(4, 128, 1, 4), T3D_VARIANT(4, 128, 2, 4), T3D_VARIANT(4, 128, 8, 4), T3D_VARIANT(4, 128, 4, 5),
-    T3D_VARIANT(4, 128, 4, 3), T3D_VARIANT(4, 256, 4, 2), T3D_VARIANT(4, 256, 2, 2), T3D_VARIANT(4, 64, 8, 8),
-    T3D_VARIANT(2, 256, 4, 4), T3D_VARIANT(2, 256, 8, 4), T3D_VARIANT(4, 64, 4, 8),
+    // default: 96 threads x 4 particles x 11 groups = 4 224-particle tiles, cp.async ring, 2 CTAs/SM (shared-memory
+    // bound; 12 groups no longer fit twice).  Measured on B200 (profiles/r1_update_variant_sweep*.txt).
+    T3D_ASYNC(96, 11, 2),
+    T3D_ASYNC(96, 6, 2), T3D_ASYNC(96, 8, 2), T3D_ASYNC(96, 9, 2), T3D_ASYNC(96, 10, 2), T3D_ASYNC(96, 12, 2), T3D_ASYNC(64, 10, 3),
+    T3D_ASYNC(64, 8, 3), T3D_ASYNC(128, 7, 1), T3D_ASYNC(64, 4, 3), T3D_ASYNC(96, 4, 2),
+    T3D_VARIANT(4, 128, 4, 4), T3D_VARIANT(4, 128, 1, 4), T3D_VARIANT(4, 128, 2, 4), T3D_VARIANT(4, 128, 8, 4),
+    T3D_VARIANT(4, 128, 4, 3), T3D_VARIANT(4, 256, 4, 2), T3D_VARIANT(4, 64, 8, 8), T3D_VARIANT(2, 256, 4, 4),
 };
 static int g_variant = -1;
 
