@@ -207,6 +207,12 @@ int t3d_batch_set_transforms(t3d_emitter* const* emitters, size_t n, const float
  * reads the quad count back. */
 int t3d_emitter_vertices(t3d_emitter* e, const t3d_sprite_vertex** device_ptr, uint32_t* n_quads);
 int t3d_emitter_download_vertices(t3d_emitter* e, float* out, size_t max_quads, uint32_t* n_quads);
+/* The index buffer MeshBatch builds for n_quads billboards (TRIANGLE_STRIP, MB.cpp:117-141): quad 0 contributes
+ * {0,1,2,3}; every later quad i the degenerate pair {4(i-1)+3, 4i} and then {4i..4i+3}: 6*n_quads-2 indices.
+ * 32-bit (the reference's unsigned short indices cap a batch at 10 922 quads, MB.cpp:213-220).  The buffer is
+ * cached by the context, device-resident, and valid until the next call that asks for more quads. */
+int t3d_ctx_strip_indices(t3d_ctx* ctx, uint32_t n_quads, const uint32_t** device_ptr, uint64_t* n_indices);
+int t3d_ctx_download_strip_indices(t3d_ctx* ctx, uint32_t n_quads, uint32_t* out, uint64_t max_indices, uint64_t* n_indices);
 /* Live particles as T3D_NUM_COLUMNS columns of `stride` words each: out[c*stride + i] for i < *count. */
 int t3d_emitter_download_state(t3d_emitter* e, uint32_t* out, size_t stride, uint32_t* count);
 int t3d_emitter_upload_state(t3d_emitter* e, const uint32_t* in, size_t stride, uint32_t count);

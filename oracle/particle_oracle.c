@@ -628,6 +628,29 @@ int orc_emitter_set_state(orc_emitter* e, const uint32_t* in, size_t stride, uin
 }
 
 /* =====================================================================================
+ * MeshBatch index stitching (MB.cpp:87-148): every SpriteBatch::draw adds 4 vertices with indices {0,1,2,3}.
+ * ===================================================================================== */
+uint64_t orc_strip_indices(uint32_t n_quads, uint32_t* out)
+{
+    static const uint32_t quad[4] = { 0, 1, 2, 3 }; /* SB.cpp:361 */
+    uint64_t index_count = 0;
+    uint32_t vertex_count = 0;
+    for (uint32_t q = 0; q < n_quads; ++q) {
+        if (vertex_count == 0) {
+            for (int i = 0; i < 4; ++i) out[index_count + i] = quad[i];        /* MB.cpp:118-122 */
+        } else {
+            out[index_count] = out[index_count - 1];                           /* MB.cpp:126-133: degenerate triangle */
+            out[index_count + 1] = vertex_count;
+            index_count += 2;
+            for (int i = 0; i < 4; ++i) out[index_count + i] = quad[i] + vertex_count; /* MB.cpp:137-141 */
+        }
+        index_count += 4;
+        vertex_count += 4;
+    }
+    return index_count;
+}
+
+/* =====================================================================================
  * Timing loops.
  * ===================================================================================== */
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }

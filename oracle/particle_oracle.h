@@ -70,6 +70,10 @@ uint32_t orc_emitter_get_state(orc_emitter* e, uint32_t* out, size_t stride);
 int orc_emitter_set_state(orc_emitter* e, const uint32_t* in, size_t stride, uint32_t n);
 uint32_t orc_emitter_get_vertices(orc_emitter* e, float* out, size_t max_quads);
 
+/* MeshBatch::add's index stitching for n quads appended one by one (MB.cpp:87-148, TRIANGLE_STRIP, indexed), with
+ * 32-bit indices.  Returns the number of indices written (6n-2).  Restated, not reference-pinned (MeshBatch.cpp needs GL). */
+uint64_t orc_strip_indices(uint32_t n_quads, uint32_t* out);
+
 /* ---- timing loops (seconds) for bench.py's cpu_baseline "port" leg ---- */
 double orc_time_update(orc_emitter* e, float elapsed_ms, int frames);
 double orc_time_draw(orc_emitter* e, int frames);

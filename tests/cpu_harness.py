@@ -95,6 +95,7 @@ class CpuLib:
             proto("set_frozen_rotation", None, [_P(C.c_float), C.c_float])
             proto("get_frozen_rotation", C.c_int, [_P(C.c_float)])
             proto("emitter_set_device_rng", None, [_vp, C.c_int, C.c_uint64])
+            proto("strip_indices", C.c_uint64, [C.c_uint32, _P(C.c_uint32)])
         else:
             proto("emitter_create_from_file", _vp, [C.c_char_p])
             proto("emitter_clone", _vp, [_vp])

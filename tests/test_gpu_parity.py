@@ -296,3 +296,14 @@ def test_large_population_properties():
         assert prev == 0
     finally:
         lib.close()
+
+
+def test_strip_index_pattern_matches_meshbatch_restatement(gpu):
+    # the index pattern MeshBatch::add stitches per quad (MB.cpp:117-141), 32-bit.
+    O = H.oracle()
+    for n in (0, 1, 2, 3, 7, 1000, 10923, 100_001):
+        got = gpu.ctx.strip_indices(n)
+        want = np.zeros(max(6 * n - 2, 1), dtype=np.uint32)
+        cnt = O.strip_indices(n, want.ctypes.data_as(H._P(C.c_uint32)))
+        assert cnt == (6 * n - 2 if n else 0) == got.size
+        assert np.array_equal(got, want[:cnt]), n

@@ -403,6 +403,29 @@ void launch_gather_counts(void* stream, const CountQuery* q, uint32_t n, uint32_
     k_gather_counts<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(q, n, out);
 }
 
+// MB.cpp:117-141: the first quad's four indices, then per quad two degenerate indices (previous last, next first)
+// stitching the strips, then its four.
+__global__ void k_strip_indices(uint32_t* __restrict__ out, uint64_t n_indices)
+{
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_indices) return;
+    uint32_t v;
+    if (p < 4)
+        v = (uint32_t)p;
+    else
+    {
+        const uint64_t q = (p - 4) / 6 + 1; // quad
+        const uint32_t r = (uint32_t)((p - 4) % 6);
+        v = r == 0 ? (uint32_t)(4 * (q - 1) + 3) : r == 1 ? (uint32_t)(4 * q) : (uint32_t)(4 * q + (r - 2));
+    }
+    out[p] = v;
+}
+
+void launch_strip_indices(void* stream, uint32_t* out, uint64_t n_indices)
+{
+    if (n_indices) k_strip_indices<<<(unsigned)((n_indices + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n_indices);
+}
+
 // Exchange with the ABI's layout (download_state / upload_state): one thread per particle, all columns.
 template <bool EXPORT>
 __global__ void k_exchange_state(uint32_t* cols, uint32_t stride, uint32_t block_shift, uint32_t n, uint32_t* host_layout,

@@ -160,6 +160,9 @@ struct t3d_ctx
     Feedback feedback[4];
     int feedback_next{ 0 };
 
+    uint32_t* strip_indices{ nullptr }; // cached MeshBatch index pattern
+    uint32_t strip_quads{ 0 };
+
     uint32_t* readback_host{ nullptr }; // pinned scratch for counts
     size_t readback_cap{ 0 };
     uint32_t* readback_dev{ nullptr };
@@ -1008,6 +1011,7 @@ int t3d_ctx_destroy(t3d_ctx* c)
     if (c->frozen_dev) cudaFree(c->frozen_dev);
     if (c->readback_host) cudaFreeHost(c->readback_host);
     if (c->readback_dev) cudaFree(c->readback_dev);
+    if (c->strip_indices) cudaFree(c->strip_indices);
     for (t3d_ctx::Feedback& fb : c->feedback)
     {
         if (fb.host) cudaFreeHost(fb.host);
@@ -1493,6 +1497,49 @@ int t3d_emitter_vertices(t3d_emitter* e, const t3d_sprite_vertex** device_ptr, u
     if (device_ptr)
         *device_ptr = s.vtx ? reinterpret_cast<const t3d_sprite_vertex*>(s.vtx + (size_t)e->seg_offset * T3D_FLOATS_PER_QUAD) : nullptr;
     if (n_quads) *n_quads = (s.vtx && !e->last_draw_empty) ? drawn : 0;
+    return T3D_OK;
+}
+
+int t3d_ctx_strip_indices(t3d_ctx* c, uint32_t n_quads, const uint32_t** device_ptr, uint64_t* n_indices)
+{
+    if (!c) return fail(T3D_ERR_INVALID, "null context");
+    T3D_TRY(use_device(c));
+    const uint64_t n = n_quads ? 6ull * n_quads - 2ull : 0ull;
+    if (n_quads > c->strip_quads)
+    {
+        if (c->strip_indices)
+        {
+            T3D_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(c->strip_indices);
+            c->strip_indices = nullptr;
+            c->strip_quads = 0;
+        }
+        const uint32_t cap = std::max<uint32_t>(n_quads, 1024);
+        const uint64_t cap_idx = 6ull * cap - 2ull;
+        T3D_CUDA(cudaMalloc((void**)&c->strip_indices, cap_idx * sizeof(uint32_t)));
+        launch_strip_indices(c->stream, c->strip_indices, cap_idx); // the pattern of n quads is a prefix of any longer one
+        T3D_CUDA(cudaGetLastError());
+        c->launches++;
+        c->strip_quads = cap;
+    }
+    if (device_ptr) *device_ptr = c->strip_indices;
+    if (n_indices) *n_indices = n;
+    return T3D_OK;
+}
+
+int t3d_ctx_download_strip_indices(t3d_ctx* c, uint32_t n_quads, uint32_t* out, uint64_t max_indices, uint64_t* n_indices)
+{
+    const uint32_t* dev = nullptr;
+    uint64_t n = 0;
+    T3D_TRY(t3d_ctx_strip_indices(c, n_quads, &dev, &n));
+    if (n_indices) *n_indices = n;
+    const uint64_t m = std::min<uint64_t>(n, max_indices);
+    if (out && m)
+    {
+        T3D_CUDA(cudaMemcpyAsync(out, dev, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        T3D_CUDA(cudaStreamSynchronize(c->stream));
+        c->d2h_bytes += m * sizeof(uint32_t);
+    }
     return T3D_OK;
 }
 

@@ -82,6 +82,13 @@ class Context:
         _check(self.lib, self.lib.t3d_ctx_kernel_time(self.h, which, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def strip_indices(self, n_quads):
+        """MeshBatch's triangle-strip index pattern for n_quads quads (uint32 numpy copy)."""
+        n = C.c_uint64()
+        out = np.zeros(max(6 * n_quads - 2, 1), dtype=np.uint32)
+        _check(self.lib, self.lib.t3d_ctx_download_strip_indices(self.h, n_quads, out.ctypes.data_as(_P(C.c_uint32)), out.size, C.byref(n)))
+        return out[: n.value]
+
     def launch_count(self):
         n = C.c_uint64()
         _check(self.lib, self.lib.t3d_ctx_launch_count(self.h, C.byref(n)))
