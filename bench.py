@@ -294,6 +294,14 @@ def run_cuda(args):
                 roof[nm] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                             "traffic": tr * per_launch_particles if tr else None, "bytes_per_unit": b, "units_per_launch": per_launch_particles,
                             "ms_per_launch": ms, "peak_source": peak_src}
+        if churn and "update" in roof:
+            # compaction: every particle that dies pulls one in from the end of the array, 2 x 136 B;
+            # in steady state deaths per frame = spawns per frame
+            moved = spawn_per_frame * len(emitters)
+            r = roof["update"]
+            r["moved_per_launch"] = moved
+            r["achieved"] = (upd_bytes * per_launch_particles + 2 * SPAWN_BYTES * moved) / (r["ms_per_launch"] * 1e-3) / 1e9
+            r["frac"] = r["achieved"] / peak
         if churn and kern["spawn"]["ms_per_launch"]:
             ms = kern["spawn"]["ms_per_launch"]
             ach = SPAWN_BYTES * spawn_per_frame * len(emitters) / (ms * 1e-3) / 1e9

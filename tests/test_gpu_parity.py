@@ -71,6 +71,40 @@ def test_gpu_device_rng_matches_oracle(factory):
         lib.close()
 
 
+def test_c1_fire_600_frames_every_frame(gpu):
+    # BASELINE configs[0]: the browser sample's fire.particle, 1/60 s steps, 600 frames of update + draw, at the
+    # stock rate (~280 live) and at 1000/s (~870 live); live count compared EVERY frame, full state and vertex
+    # stream every 50th, against the oracle on the same recorded draw stream.
+    for rate in (None, 1000):
+        sc = S.fire(frames=1, rate=rate)
+        O = H.oracle(fresh=True)
+        O.rand_seed(1234)
+        eo = S.new_emitter(O, sc)
+        eg = S.new_emitter(gpu, sc)
+        cam = np.eye(4, dtype=np.float32); cam[:3, 3] = (0.22, 2.7, 13.3)
+        for e in (eo, eg):
+            e.set_camera_world(cam.T.reshape(16))
+            e.start()
+        updates = 0
+        for f in range(600):
+            O.rand_record(1)
+            eo.update(S.DT)
+            eg.feed_draws(O.recorded())
+            eg.update(S.DT)
+            assert eo.draw() == eg.draw() == 1
+            n = eo.count()
+            updates += n
+            if f % 50 == 49:
+                assert eg.count() == n, f"frame {f}"
+                assert np.array_equal(eg.state(), eo.state()), f"frame {f}"
+                assert np.array_equal(eg.vertices().view(np.uint32), eo.vertices().view(np.uint32)), f"frame {f}"
+        assert eg.count() == eo.count()
+        assert eg.pe.pending_draws() == 0
+        assert (250 < eo.count() < 320) if rate is None else (800 < eo.count() < 950)
+        assert updates > 150_000
+        gpu.ctx.reset_statics()
+
+
 def test_gpu_libc_rand_mode_matches_oracle():
     # T3D_RNG_LIBC: the library calls rand() itself in the reference's order; replay the same libc stream into the oracle.
     from gpu_adapter import GpuLib
