@@ -150,6 +150,42 @@ def build_population(ctx, workload, rank, world, particles):
     raise SystemExit(f"unknown workload {workload}")
 
 
+def quick_measure(ctx, stream, workload, steps, torch):
+    """A short extra measurement of another single-GPU workload on the same context (reported under `also`)."""
+    emitters, per, animated_frac, wl_name = build_population(ctx, workload, 0, 1, 0)
+    handles = ctx._handles(emitters)
+    n = int(ctx.batch_counts(emitters, handles).sum())
+    for _ in range(5):
+        ctx.batch_update(emitters, DT, handles)
+        ctx.batch_draw(emitters, handles)
+    ctx.sync()
+    t0 = [ctx.kernel_time(k) for k in range(3)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(steps):
+            ctx.batch_update(emitters, DT, handles)
+            ctx.batch_draw(emitters, handles)
+        ctx.flush()
+        ev1.record(stream)
+    ctx.sync()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    t1 = [ctx.kernel_time(k) for k in range(3)]
+    peak, _ = measured_peak_gbs()
+    upd_b = UPDATE_BYTES + (UPDATE_BYTES_ANIMATED - UPDATE_BYTES) * animated_frac
+    out = {"workload": wl_name, "particles": n, "steps": steps, "ms_per_step": ms / steps, "value": n * steps / (ms * 1e-3),
+           "unit": "particles/s"}
+    for k, nm, b in ((1, "update", upd_b), (2, "draw", DRAW_BYTES)):
+        dn = t1[k][1] - t0[k][1]
+        if dn:
+            ms_l = (t1[k][0] - t0[k][0]) / dn
+            out[nm] = {"ms_per_launch": ms_l, "achieved_gbs": b * n / (ms_l * 1e-3) / 1e9, "frac": b * n / (ms_l * 1e-3) / 1e9 / peak}
+    for e in emitters:
+        e.release()
+    return out
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -193,7 +229,9 @@ def run_cuda(args):
 
     counts0 = ctx.batch_counts(emitters, handles)
     local_particles = int(counts0.sum())
-    for _ in range(max(3, args.warmup)):
+    # churn needs ~25 frames (the longest lifetime) before the live population is stationary
+    n_warm = max(30 if churn else 3, args.warmup)
+    for _ in range(n_warm):
         frame()
     barrier()
 
@@ -311,7 +349,7 @@ def run_cuda(args):
         value = updates_done / (ms_total * 1e-3)
         line = {
             "metric": "particle updates/s (one step = update + billboard draw of every live particle; quads/s is the same number)",
-            "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong" if workload in ("c4", "c2") else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -332,6 +370,12 @@ def run_cuda(args):
             "e2e_vertices_to_host": e2e_v,
             "clocks": clocks,
         }
+        if world == 1 and workload == "c3" and not args.no_also:
+            # BASELINE configs[1] (1 024 emitters x 4 Ki, mixed parameter sets) measured beside the headline workload
+            for e in emitters:
+                e.release()
+            emitters = []
+            line["also"] = {"c2": quick_measure(ctx, stream, "c2", 50, torch)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single_core(args.cpu_particles)
         print(json.dumps(line), flush=True)
@@ -427,6 +471,7 @@ def main():
     ap.add_argument("--particles", type=int, default=0, help="override the population size of the workload")
     ap.add_argument("--cpu-particles", type=int, default=2 * MI, help="population of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the extra c2 measurement")
     ap.add_argument("--vertices-to-host", action="store_true", help="also time frames with the vertex stream copied to pinned host memory")
     args = ap.parse_args()
     if args.impl == "reference":

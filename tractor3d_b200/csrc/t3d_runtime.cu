@@ -204,6 +204,10 @@ struct t3d_emitter
     bool queued{ false };
     bool last_draw_empty{ true }; // the last draw() submitted no quads (inactive or no particles)
     uint64_t emitted_total{ 0 };  // particles ever asked to spawn (upper bound of those spawned)
+    // Milliseconds for which at least one particle is GUARANTEED to be alive: a particle that certainly spawned
+    // starts with energy >= floor(min(energyMin, energyMax)) (PE.cpp:316) and every update takes at most
+    // elapsed + 1 off it (PE.cpp:753 truncates).  While positive, isActive() of a stopped emitter needs no read-back.
+    double alive_budget_ms{ 0 };
 };
 
 constexpr uint32_t kDevChunk = 4096;
@@ -914,6 +918,8 @@ static int prepare_emit(t3d_emitter* e, uint32_t n, PendingOp* op)
         op->emit_n = n;
         e->emitted_total += n;
         const uint64_t ub = (uint64_t)e->count_ub + n;
+        if (n && ub <= cap) // all of them fit for sure
+            e->alive_budget_ms = std::max(e->alive_budget_ms, (double)std::floor(std::min(e->p.energy_min, e->p.energy_max)));
         e->count_ub = (uint32_t)std::min<uint64_t>(ub, cap);
         return T3D_OK;
     }
@@ -930,6 +936,7 @@ static int prepare_emit(t3d_emitter* e, uint32_t n, PendingOp* op)
         T3D_TRY(collect_host_draws(e, n, op));
         e->count_ub += n;
         e->emitted_total += n;
+        e->alive_budget_ms = std::max(e->alive_budget_ms, (double)std::floor(std::min(e->p.energy_min, e->p.energy_max)));
     }
     return T3D_OK;
 }
@@ -1364,6 +1371,11 @@ static int is_active(t3d_emitter* e, bool* out)
         *out = false;
         return T3D_OK;
     }
+    if (e->alive_budget_ms > 0) // some particle cannot have died yet: `_particleCount > 0` without asking the device
+    {
+        *out = true;
+        return T3D_OK;
+    }
     uint32_t cnt;
     T3D_TRY(exact_count(e, &cnt));
     *out = cnt > 0;
@@ -1411,6 +1423,7 @@ int t3d_emitter_update(t3d_emitter* e, float elapsed_time)
         if (emit_count) T3D_TRY(prepare_emit(e, emit_count, &op));                                            // PE.cpp:744
     }
     if (e->count_ub > 0) e->count_exact = false; // particles may die in the kernel; the bound stays valid
+    e->alive_budget_ms -= (double)elapsed_ms + 1.0;
     return enqueue(c, PHASE_UPDATE, op);
 }
 
@@ -1630,6 +1643,7 @@ int t3d_emitter_upload_state(t3d_emitter* e, const uint32_t* in, size_t stride, 
     e->count_ub = count;
     e->count_exact = true;
     e->emitted_total += count; // keeps count feedback still in flight a valid upper bound
+    e->alive_budget_ms = 0;
     // Uploaded particles may carry any rotation state.
     e->may_rotate = e->may_spin = true;
     e->const_dirty = true;
