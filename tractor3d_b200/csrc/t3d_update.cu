@@ -645,21 +645,41 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     }
 
     // ---- the moves, cooperatively: rank r of this tile's dead particles pulls original N-1-(tile_excl+r) into its
-    // slot.  Column-major task order: consecutive threads read consecutive sources (contiguous at the end of the
-    // live range) of one column.  Sources lie beyond every examined slot, so nothing read here is written by anyone.
+    // slot.  Each warp takes whole columns; its lanes walk the ranks, so 32 consecutive sources (contiguous at the end
+    // of the live range) are one 128-byte read.  Loads are issued in batches of 8 per lane before any store: the
+    // moves are latency-bound, not bandwidth-bound.  Sources lie beyond every examined slot: nothing read here is
+    // written by anyone.
     if (tile_dead)
     {
         __syncthreads(); // s_move complete; this CTA's stores to the dead slots are ordered before the moves
-        const uint32_t tasks = tile_dead * (uint32_t)T3D_NUM_COLUMNS;
         const uint32_t src_last = N - 1u - tile_excl;
-#pragma unroll 4
-        for (uint32_t t = tid; t < tasks; t += THREADS)
+        constexpr int BATCH = 8;
+        for (uint32_t c = warp; c < (uint32_t)T3D_NUM_COLUMNS; c += WARPS)
         {
-            const uint32_t c = t / tile_dead;
-            const uint32_t r = t - c * tile_dead;
-            const unsigned short off = s_move[r];
-            if (off != kNoMove)
-                particle_base(cols, bshift, first + off)[(size_t)c * stride] = particle_base(cols, bshift, src_last - r)[(size_t)c * stride];
+            const size_t coff = (size_t)c * stride;
+            for (uint32_t r0 = lane; r0 < tile_dead; r0 += 32u * BATCH)
+            {
+                uint32_t val[BATCH];
+                uint32_t* dst[BATCH];
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j)
+                {
+                    const uint32_t r = r0 + 32u * j;
+                    dst[j] = nullptr;
+                    if (r < tile_dead)
+                    {
+                        const unsigned short off = s_move[r];
+                        if (off != kNoMove)
+                        {
+                            dst[j] = particle_base(cols, bshift, first + off) + coff;
+                            val[j] = *(particle_base(cols, bshift, src_last - r) + coff);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j)
+                    if (dst[j]) *dst[j] = val[j];
+            }
         }
     }
 }
