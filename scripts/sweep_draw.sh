@@ -1,7 +1,8 @@
 #!/bin/bash
-# Compares the draw-kernel output paths on the c3 workload (run on the GPU box).
-P=${1:-67108864}
-for v in lsu tma; do
-  T3D_DRAW_VARIANT=$v python bench.py --steps 20 --warmup 3 --particles $P --no-cpu-baseline 2>/dev/null | \
-    python -c "import sys,json; d=json.loads(sys.stdin.read()); k=d['kernels']; r=d['rooflines']; print('$v', 'update ms %.3f (%.0f GB/s, %.3f)' % (k['update']['ms_per_launch'], r['update']['achieved'], r['update']['frac']), 'draw ms %.3f (%.0f GB/s, %.3f)' % (k['draw']['ms_per_launch'], r['draw']['achieved'], r['draw']['frac']), 'value %.3g' % d['value'])"
+# Sweeps sub-tiles per draw CTA on two workloads (GPU box).
+for w in c3 c4 c2; do
+  for d in 1 2 4 8; do
+    echo -n "$w draw_sub=$d: "
+    T3D_DRAW_SUB=$d python bench.py --workload $w --steps 20 --warmup 3 --no-cpu-baseline --no-also 2>/dev/null | scripts/bench_summary.py | head -1 | sed 's/ e2e=.*//'
+  done
 done

@@ -12,6 +12,8 @@ namespace t3d
 // Particles per tile of the update kernel = particles per thread x threads per CTA of the selected variant
 // (t3d_update.cu).
 int update_tile_size();
+int draw_sub(uint32_t n_items);
+int draw_tile_size(uint32_t n_items); // quads per draw CTA for a launch over n_items emitters
 const char* update_variant_name();
 // Spawn and draw: one particle per thread.
 constexpr int kSpawnThreads = 256;

@@ -170,47 +170,76 @@ __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __rest
 // OUT = 0: the tile's vertices are copied from shared memory with coalesced 128-bit streaming stores.
 // OUT = 1: one thread hands the tile to the TMA engine (cp.async.bulk shared -> global, SASS UBLKCP), which
 //          writes the nq * 144 contiguous bytes while the other warps are already gone.
-template <int OUT>
+template <int OUT, int DSUB>
 __global__ void __launch_bounds__(kDrawThreads)
     k_draw(const DrawItem* __restrict__ items, uint32_t n_items, int rot_mode, const FrozenRotation* __restrict__ frozen)
 {
-    __shared__ __align__(16) float s_vtx[kDrawThreads * T3D_FLOATS_PER_QUAD];
+    __shared__ __align__(128) float s_vtx[kDrawThreads * T3D_FLOATS_PER_QUAD];
     __shared__ float s_uv[kMaxSmemFrames * 4];
 
+    // One CTA draws DSUB consecutive sub-tiles of kDrawThreads quads: the descriptor fetch, the uv table and the
+    // live count are paid once per DSUB * 256 quads, and the next sub-tile's particles are requested before the
+    // current one is expanded.
     const uint32_t tile = blockIdx.x;
     const uint32_t tid = threadIdx.x;
     const DrawItem& it = items[find_item(items, n_items, tile, gridDim.x)];
     const EmitterDev* d = it.dev;
-    const uint32_t first = (tile - it.tile_begin) * kDrawThreads;
-    const uint32_t i = first + tid;
+    const uint32_t first_tile = (tile - it.tile_begin) * (kDrawThreads * DSUB);
     const uint32_t N = d->cnt[it.parity].count;
+    const uint32_t seg_capacity = it.seg_capacity;
+    const uint32_t* const cols0 = it.cols;
+    const uint32_t bshift = it.block_shift;
+    const size_t stride = it.stride;
 
-    // This thread's particle, requested before the live count has arrived (any slot below the padded segment
-    // size is inside the slab and safe to read).
-    float pos[3] = { 0.0f, 0.0f, 0.0f }, color[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
-    float size = 0.0f, angle = 0.0f;
-    uint32_t frame = 0;
-    if (i < it.seg_capacity)
+    struct Quad
     {
-        const uint32_t* cols = particle_base(it.cols, it.block_shift, i);
-        const size_t stride = it.stride;
-        auto LF = [&](int c) { return __ldcs(reinterpret_cast<const float*>(cols + (size_t)c * stride)); };
-        pos[0] = LF(T3D_COL_POSITION); pos[1] = LF(T3D_COL_POSITION + 1); pos[2] = LF(T3D_COL_POSITION + 2);
-        size = LF(T3D_COL_SIZE);
-        color[0] = LF(T3D_COL_COLOR); color[1] = LF(T3D_COL_COLOR + 1); color[2] = LF(T3D_COL_COLOR + 2); color[3] = LF(T3D_COL_COLOR + 3);
-        angle = LF(T3D_COL_ANGLE);
-        frame = __ldcs(cols + (size_t)T3D_COL_FRAME * stride);
-    }
+        float pos[3], color[4], size, angle;
+        uint32_t frame;
+    };
+    // Requested before the live count has arrived: any slot below the padded segment size is inside the slab.
+    auto load = [&](uint32_t i, Quad& q)
+    {
+        if (i < seg_capacity)
+        {
+            const uint32_t* cols = particle_base(cols0, bshift, i);
+            auto LF = [&](int c) { return __ldcs(reinterpret_cast<const float*>(cols + (size_t)c * stride)); };
+            q.pos[0] = LF(T3D_COL_POSITION); q.pos[1] = LF(T3D_COL_POSITION + 1); q.pos[2] = LF(T3D_COL_POSITION + 2);
+            q.size = LF(T3D_COL_SIZE);
+            q.color[0] = LF(T3D_COL_COLOR); q.color[1] = LF(T3D_COL_COLOR + 1); q.color[2] = LF(T3D_COL_COLOR + 2); q.color[3] = LF(T3D_COL_COLOR + 3);
+            q.angle = LF(T3D_COL_ANGLE);
+            q.frame = __ldcs(cols + (size_t)T3D_COL_FRAME * stride);
+        }
+    };
+    Quad cur = {};
+    load(first_tile + tid, cur);
 
     const uint32_t frame_count = it.frame_count;
     const float* __restrict__ uv_g = it.uv;
     const bool uv_in_smem = frame_count <= (uint32_t)kMaxSmemFrames;
     if (uv_in_smem)
         for (uint32_t q = tid; q < frame_count * 4u; q += kDrawThreads) s_uv[q] = uv_g[q];
-    if (first == 0 && tid == 0) const_cast<EmitterDev*>(d)->cnt[0].drawn = N;
-    if (first >= N) return;
+    if (first_tile == 0 && tid == 0) const_cast<EmitterDev*>(d)->cnt[0].drawn = N;
+    if (first_tile >= N) return;
     __syncthreads();
 
+#pragma unroll 1
+    for (int sub = 0; sub < DSUB; ++sub)
+    {
+    const uint32_t first = first_tile + sub * kDrawThreads;
+    if (first >= N) break;
+    const uint32_t i = first + tid;
+    Quad nxt = {};
+    if (sub + 1 < DSUB) load(i + kDrawThreads, nxt);
+    if (sub > 0)
+    {
+        // s_vtx is reused: the previous sub-tile's bulk store must have finished reading it
+        if (OUT == 1 && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
+    }
+    const float* pos = cur.pos;
+    const float* color = cur.color;
+    const float size = cur.size, angle = cur.angle;
+    const uint32_t frame = cur.frame;
     if (i < N)
     {
         const float* uv = uv_in_smem ? (s_uv + frame * 4u) : (uv_g + (size_t)frame * 4u);
@@ -292,7 +321,7 @@ __global__ void __launch_bounds__(kDrawThreads)
         o[7] = make_float4(p3[1], p3[2], u2, v2);
         o[8] = make_float4(color[0], color[1], color[2], color[3]);
     }
-    // The tile's vertices: nq quads * 144 B, contiguous in the emitter's vertex stream (16-byte aligned).
+    // The sub-tile's vertices: nq quads * 144 B, contiguous in the emitter's vertex stream (16-byte aligned).
     const uint32_t nq = (N - first) < (uint32_t)kDrawThreads ? (N - first) : (uint32_t)kDrawThreads;
     float4* __restrict__ dst = reinterpret_cast<float4*>(it.vtx + (size_t)first * T3D_FLOATS_PER_QUAD);
     if (OUT == 1)
@@ -306,7 +335,6 @@ __global__ void __launch_bounds__(kDrawThreads)
             const uint32_t bytes = nq * (uint32_t)(T3D_FLOATS_PER_QUAD * sizeof(float));
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory must outlive the read
         }
     }
     else
@@ -315,6 +343,10 @@ __global__ void __launch_bounds__(kDrawThreads)
         const float4* src4 = reinterpret_cast<const float4*>(s_vtx);
         for (uint32_t q = tid; q < nq * 9u; q += kDrawThreads) __stcs(dst + q, src4[q]);
     }
+    cur = nxt;
+    }
+    // shared memory must outlive the last bulk store's read
+    if (OUT == 1 && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -373,17 +405,49 @@ void launch_spawn(void* stream, const SpawnItem* items, uint32_t n_items, uint32
 void launch_draw(void* stream, const DrawItem* items, uint32_t n_items, uint32_t total_tiles, int rot_mode,
                  const FrozenRotation* frozen)
 {
+    const int sub = draw_sub(n_items);
     static int mode = -1;
     if (mode < 0)
     {
         const char* env = getenv("T3D_DRAW_VARIANT");
         mode = (env && !strcmp(env, "lsu")) ? 0 : 1;
     }
+    cudaStream_t st = (cudaStream_t)stream;
     if (mode == 1)
-        k_draw<1><<<total_tiles, kDrawThreads, 0, (cudaStream_t)stream>>>(items, n_items, rot_mode, frozen);
+    {
+        if (sub == 1) k_draw<1, 1><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen);
+        else if (sub == 2) k_draw<1, 2><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen);
+        else if (sub == 4) k_draw<1, 4><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen);
+        else k_draw<1, 8><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen);
+    }
     else
-        k_draw<0><<<total_tiles, kDrawThreads, 0, (cudaStream_t)stream>>>(items, n_items, rot_mode, frozen);
+    {
+        if (sub == 1) k_draw<0, 1><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen);
+        else if (sub == 2) k_draw<0, 2><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen);
+        else if (sub == 4) k_draw<0, 4><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen);
+        else k_draw<0, 8><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen);
+    }
 }
+
+// Sub-tiles of 256 quads per draw CTA.  Measured on B200 (profiles/r1_draw_subtile_sweep.txt): 4 is best when the
+// launch covers many emitters (the per-CTA descriptor/uv/count prologue is amortised: 8 192 x 32 Ki draws 9 % faster),
+// 2 when it covers a few large ones.  T3D_DRAW_SUB = 1, 2, 4 or 8 overrides for experiments.
+int draw_sub(uint32_t n_items)
+{
+    static int forced = -1;
+    if (forced < 0)
+    {
+        forced = 0;
+        if (const char* env = getenv("T3D_DRAW_SUB"))
+        {
+            const int v = atoi(env);
+            if (v == 1 || v == 2 || v == 4 || v == 8) forced = v;
+        }
+    }
+    if (forced) return forced;
+    return n_items > 8 ? 4 : 2;
+}
+int draw_tile_size(uint32_t n_items) { return kDrawThreads * draw_sub(n_items); }
 
 void launch_latch(void* stream, const DrawItem* items, uint32_t n_items, FrozenRotation* frozen)
 {

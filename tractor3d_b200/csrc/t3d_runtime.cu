@@ -669,6 +669,7 @@ static int launch_draws(t3d_ctx* c)
     DrawItem* items = reinterpret_cast<DrawItem*>(slot->host);
     uint32_t tiles = 0;
     bool any_spin = false;
+    const uint32_t draw_tile = (uint32_t)draw_tile_size(n_items);
     for (uint32_t k = 0; k < n_items; ++k)
     {
         PendingOp& op = c->pending[k];
@@ -690,7 +691,7 @@ static int launch_draws(t3d_ctx* c)
         it.tile_begin = tiles;
         memcpy(it.right, op.right, 12);
         memcpy(it.up, op.up, 12);
-        tiles += std::max(1u, (e->count_ub + kDrawThreads - 1) / kDrawThreads);
+        tiles += std::max(1u, (e->count_ub + draw_tile - 1) / draw_tile);
         any_spin = any_spin || e->may_spin;
     }
     T3D_TRY(staging_submit(c, slot, sizeof(DrawItem) * n_items));
