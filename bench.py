@@ -227,13 +227,13 @@ def run_cuda(args):
         if world > 1:
             dist.barrier()
 
-    counts0 = ctx.batch_counts(emitters, handles)
-    local_particles = int(counts0.sum())
     # churn needs ~25 frames (the longest lifetime) before the live population is stationary
     n_warm = max(30 if churn else 3, args.warmup)
     for _ in range(n_warm):
         frame()
     barrier()
+    counts0 = ctx.batch_counts(emitters, handles)   # live population at the start of the timed region
+    local_particles = int(counts0.sum())
 
     # ---- timed region: K frames back to back, device time on the launching stream ----
     sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(local_rank), "uuid", None))

@@ -208,6 +208,7 @@ struct t3d_emitter
     // starts with energy >= floor(min(energyMin, energyMax)) (PE.cpp:316) and every update takes at most
     // elapsed + 1 off it (PE.cpp:753 truncates).  While positive, isActive() of a stopped emitter needs no read-back.
     double alive_budget_ms{ 0 };
+    EmitterConst hc{}; // host copy of the device constants as last uploaded (launch descriptors are cut from it)
 };
 
 constexpr uint32_t kDevChunk = 4096;
@@ -417,11 +418,10 @@ static int sync_const(t3d_emitter* e)
     }
     if (e->const_dirty)
     {
-        EmitterConst k;
-        fill_const(e, &k);
-        // Pageable source: the runtime stages it before returning, so `k` may go out of scope.
-        T3D_CUDA(cudaMemcpyAsync(&e->dev->c, &k, sizeof(k), cudaMemcpyHostToDevice, c->stream));
-        c->h2d_bytes += sizeof(k);
+        fill_const(e, &e->hc);
+        // Pageable source: the runtime stages it before returning.
+        T3D_CUDA(cudaMemcpyAsync(&e->dev->c, &e->hc, sizeof(e->hc), cudaMemcpyHostToDevice, c->stream));
+        c->h2d_bytes += sizeof(e->hc);
         e->const_dirty = false;
     }
     return T3D_OK;
@@ -597,8 +597,7 @@ static int launch_updates(t3d_ctx* c)
         t3d_emitter* e = op.e;
         T3D_TRY(sync_const(e));
         UpdateItem& it = items[k];
-        EmitterConst ec;
-        fill_const(e, &ec);
+        const EmitterConst& ec = e->hc; // current: sync_const ran just above
         memset(&it, 0, sizeof(it));
         it.dev = e->dev;
         it.cols = ec.cols;
@@ -676,8 +675,7 @@ static int launch_draws(t3d_ctx* c)
         t3d_emitter* e = op.e;
         T3D_TRY(sync_const(e));
         DrawItem& it = items[k];
-        EmitterConst ec;
-        fill_const(e, &ec);
+        const EmitterConst& ec = e->hc; // current: sync_const ran just above
         memset(&it, 0, sizeof(it));
         it.dev = e->dev;
         it.cols = ec.cols;
