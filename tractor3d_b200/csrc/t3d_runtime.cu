@@ -453,7 +453,8 @@ static int resolve_timing(t3d_ctx* c, int k, bool wait)
 static int time_begin(t3d_ctx* c, int k)
 {
     if (!c->timing_enabled) return T3D_OK;
-    if (c->ev_pending[k].size() >= 256) T3D_TRY(resolve_timing(c, k, true));
+    if (c->ev_pending[k].size() >= 64) T3D_TRY(resolve_timing(c, k, false)); // recycle finished pairs without waiting
+    if (c->ev_pending[k].size() >= 1024) T3D_TRY(resolve_timing(c, k, true));
     t3d_ctx::EventPair p;
     if (!c->ev_free.empty())
     {

@@ -644,41 +644,30 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         compiler_fence();
     }
 
-    // ---- the moves, cooperatively: rank r of this tile's dead particles pulls original N-1-(tile_excl+r) into its
-    // slot.  Each warp takes whole columns; its lanes walk the ranks, so 32 consecutive sources (contiguous at the end
-    // of the live range) are one 128-byte read.  Loads are issued in batches of 8 per lane before any store: the
-    // moves are latency-bound, not bandwidth-bound.  Sources lie beyond every examined slot: nothing read here is
+    // ---- the moves: rank r of this tile's dead particles pulls original N-1-(tile_excl+r) into its slot.  One thread
+    // per move (consecutive lanes read consecutive sources, contiguous at the end of the live range, so each column
+    // is a coalesced read); the 34 words are fetched in two batches of 17 independent loads before they are stored --
+    // the moves are latency-bound, not bandwidth-bound.  Sources lie beyond every examined slot: nothing read here is
     // written by anyone.
     if (tile_dead)
     {
         __syncthreads(); // s_move complete; this CTA's stores to the dead slots are ordered before the moves
         const uint32_t src_last = N - 1u - tile_excl;
-        constexpr int BATCH = 8;
-        for (uint32_t c = warp; c < (uint32_t)T3D_NUM_COLUMNS; c += WARPS)
+        constexpr int BATCH = T3D_NUM_COLUMNS / 2;
+        for (uint32_t r = tid; r < tile_dead; r += THREADS)
         {
-            const size_t coff = (size_t)c * stride;
-            for (uint32_t r0 = lane; r0 < tile_dead; r0 += 32u * BATCH)
+            const unsigned short off = s_move[r];
+            if (off == kNoMove) continue;
+            uint32_t* const dst = particle_base(cols, bshift, first + off);
+            const uint32_t* const src = particle_base(cols, bshift, src_last - r);
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
             {
                 uint32_t val[BATCH];
-                uint32_t* dst[BATCH];
 #pragma unroll
-                for (int j = 0; j < BATCH; ++j)
-                {
-                    const uint32_t r = r0 + 32u * j;
-                    dst[j] = nullptr;
-                    if (r < tile_dead)
-                    {
-                        const unsigned short off = s_move[r];
-                        if (off != kNoMove)
-                        {
-                            dst[j] = particle_base(cols, bshift, first + off) + coff;
-                            val[j] = *(particle_base(cols, bshift, src_last - r) + coff);
-                        }
-                    }
-                }
+                for (int j = 0; j < BATCH; ++j) val[j] = src[(size_t)(half * BATCH + j) * stride];
 #pragma unroll
-                for (int j = 0; j < BATCH; ++j)
-                    if (dst[j]) *dst[j] = val[j];
+                for (int j = 0; j < BATCH; ++j) dst[(size_t)(half * BATCH + j) * stride] = val[j];
             }
         }
     }
