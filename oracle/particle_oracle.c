@@ -71,15 +71,21 @@ static uint64_t splitmix64_next(uint64_t* s)
     return z ^ (z >> 31);
 }
 
-/* Specification of T3D_RNG_DEVICE: draw j of particle `serial` under `seed` is the top 31 bits of a
- * splitmix64 finaliser over a key that mixes the three counters. */
+/* Specification of T3D_RNG_DEVICE, restated: a 32-bit hash of (seed, particle serial, draw index).  The seed and the
+ * serial are folded into a per-particle key with odd multipliers; draw j is key + (j+1)*0x165667B1 pushed through the
+ * "lowbias32" finaliser (xor-shift 16, *0x7FEB352D, xor-shift 15, *0x846CA68B, xor-shift 16); the top 31 bits are the draw. */
 int32_t orc_device_rng_draw(uint64_t seed, uint64_t serial, uint32_t j)
 {
-    uint64_t z = seed + serial * 0xD1342543DE82EF95ULL + ((uint64_t)j + 1ULL) * 0x9E3779B97F4A7C15ULL;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    z = z ^ (z >> 31);
-    return (int32_t)(z >> 33);
+    uint32_t seed_lo = (uint32_t)(seed & 0xFFFFFFFFu), seed_hi = (uint32_t)(seed >> 32);
+    uint32_t ser_lo = (uint32_t)(serial & 0xFFFFFFFFu), ser_hi = (uint32_t)(serial >> 32);
+    uint32_t key = (seed_lo * 2654435761u) ^ (seed_hi * 2246822519u) ^ (ser_lo * 3266489917u) ^ (ser_hi * 668265263u);
+    uint32_t x = key + (j + 1u) * 374761393u;
+    x ^= x >> 16;
+    x *= 2146121005u;
+    x ^= x >> 15;
+    x *= 2221713035u;
+    x ^= x >> 16;
+    return (int32_t)(x >> 1);
 }
 
 static void record(int32_t r)

@@ -156,17 +156,33 @@ void launch_export_state(void* stream, const uint32_t* cols, uint32_t stride, ui
 void launch_import_state(void* stream, uint32_t* cols, uint32_t stride, uint32_t block_shift, uint32_t n, const uint32_t* in,
                          uint32_t host_stride);
 
-// The counter-based generator of T3D_RNG_DEVICE (host + device).
+// The counter-based generator of T3D_RNG_DEVICE (host + device): 32-bit integer hash of (seed, particle serial,
+// draw index).  key = the part that is constant per particle; one draw = key + (j+1)*C through the lowbias32
+// finaliser (two multiplies, three xor-shifts), top 31 bits.  Cheap on purpose: a particle consumes ~30 draws and
+// the spawn kernel is bound by exactly this arithmetic.
 #if defined(__CUDACC__)
-__host__ __device__
+#define T3D_HD __host__ __device__
+#else
+#define T3D_HD
 #endif
-inline int32_t device_rng_draw(uint64_t seed, uint64_t serial, uint32_t j)
+T3D_HD inline uint32_t device_rng_key(uint64_t seed, uint64_t serial)
 {
-    uint64_t z = seed + serial * 0xD1342543DE82EF95ULL + ((uint64_t)j + 1ULL) * 0x9E3779B97F4A7C15ULL;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    z = z ^ (z >> 31);
-    return (int32_t)(z >> 33);
+    const uint32_t k = ((uint32_t)seed * 0x9E3779B1u) ^ ((uint32_t)(seed >> 32) * 0x85EBCA77u);
+    return k ^ ((uint32_t)serial * 0xC2B2AE3Du) ^ ((uint32_t)(serial >> 32) * 0x27D4EB2Fu);
+}
+T3D_HD inline int32_t device_rng_from_key(uint32_t key, uint32_t j)
+{
+    uint32_t x = key + (j + 1u) * 0x165667B1u;
+    x ^= x >> 16;
+    x *= 0x7FEB352Du;
+    x ^= x >> 15;
+    x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return (int32_t)(x >> 1);
+}
+T3D_HD inline int32_t device_rng_draw(uint64_t seed, uint64_t serial, uint32_t j)
+{
+    return device_rng_from_key(device_rng_key(seed, serial), j);
 }
 
 } // namespace t3d

@@ -32,11 +32,11 @@ namespace t3d
 struct DrawSource
 {
     const int32_t* p; // recorded stream positioned at this particle's first draw, or nullptr
-    uint64_t seed, serial;
+    uint32_t key;     // device generator: the per-particle part of the hash
     uint32_t j;
     __device__ __forceinline__ int32_t next()
     {
-        int32_t r = p ? p[j] : device_rng_draw(seed, serial, j);
+        int32_t r = p ? p[j] : device_rng_from_key(key, j);
         ++j;
         return r;
     }
@@ -65,8 +65,7 @@ __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __rest
     const SpawnParams& P = d->c.sp;
     DrawSource src;
     src.p = it.draws ? it.draws + (it.offsets ? it.offsets[i] : i * it.draw_stride) : nullptr;
-    src.seed = P.rng_seed;
-    src.serial = serial0 + i;
+    src.key = device_rng_key(P.rng_seed, serial0 + i);
     src.j = 0;
 
     // PE.cpp:312-313 -> :669-679: x, y, z, w, one draw each.
