@@ -238,7 +238,9 @@ __global__ void __launch_bounds__(kDrawThreads)
     const float* pos = cur.pos;
     const float* color = cur.color;
     const float size = cur.size, angle = cur.angle;
-    const uint32_t frame = cur.frame;
+    // A frame index past the table (frameRandomOffset > frameCount set by hand: the reference then reads past its
+    // array) is clamped instead of faulting.
+    const uint32_t frame = cur.frame < frame_count ? cur.frame : frame_count - 1u;
     if (i < N)
     {
         const float* uv = uv_in_smem ? (s_uv + frame * 4u) : (uv_g + (size_t)frame * 4u);
