@@ -212,6 +212,10 @@ int t3d_emitter_download_vertices(t3d_emitter* e, float* out, size_t max_quads, 
  * 32-bit (the reference's unsigned short indices cap a batch at 10 922 quads, MB.cpp:213-220).  The buffer is
  * cached by the context, device-resident, and valid until the next call that asks for more quads. */
 int t3d_ctx_strip_indices(t3d_ctx* ctx, uint32_t n_quads, const uint32_t** device_ptr, uint64_t* n_indices);
+/* The same quads as an indexed triangle LIST for renderers without strips: {4i, 4i+1, 4i+2, 4i+2, 4i+1, 4i+3} per quad
+ * = the two non-degenerate triangles of quad i's strip with the strip's winding (6*n_quads indices, 32-bit). */
+int t3d_ctx_triangle_indices(t3d_ctx* ctx, uint32_t n_quads, const uint32_t** device_ptr, uint64_t* n_indices);
+int t3d_ctx_download_triangle_indices(t3d_ctx* ctx, uint32_t n_quads, uint32_t* out, uint64_t max_indices, uint64_t* n_indices);
 int t3d_ctx_download_strip_indices(t3d_ctx* ctx, uint32_t n_quads, uint32_t* out, uint64_t max_indices, uint64_t* n_indices);
 /* Live particles as T3D_NUM_COLUMNS columns of `stride` words each: out[c*stride + i] for i < *count. */
 int t3d_emitter_download_state(t3d_emitter* e, uint32_t* out, size_t stride, uint32_t* count);

@@ -341,3 +341,19 @@ def test_strip_index_pattern_matches_meshbatch_restatement(gpu):
         cnt = O.strip_indices(n, want.ctypes.data_as(H._P(C.c_uint32)))
         assert cnt == (6 * n - 2 if n else 0) == got.size
         assert np.array_equal(got, want[:cnt]), n
+
+
+def test_triangle_list_is_the_strip_without_its_degenerate_triangles(gpu):
+    # Decompose the MeshBatch strip (winding flips on odd triangles), drop the degenerate stitches, compare.
+    for n in (1, 2, 5, 333):
+        strip = gpu.ctx.strip_indices(n)
+        tris = []
+        for k in range(len(strip) - 2):
+            a, b, c = (int(x) for x in strip[k:k + 3])
+            if a == b or b == c or a == c:
+                continue
+            tris.append((a, b, c) if k % 2 == 0 else (b, a, c))
+        got = gpu.ctx.triangle_indices(n).reshape(-1, 3)
+        assert got.shape == (2 * n, 3)
+        canon = lambda t: min((t[0], t[1], t[2]), (t[1], t[2], t[0]), (t[2], t[0], t[1]))   # same winding, any start
+        assert [canon(t) for t in tris] == [canon(tuple(int(x) for x in t)) for t in got]

@@ -150,6 +150,7 @@ struct CountQuery
 void launch_gather_counts(void* stream, const CountQuery* q, uint32_t n, uint32_t* out);
 // MeshBatch's triangle-strip index pattern for n_quads quads (MB.cpp:117-141), 6*n_quads-2 indices.
 void launch_strip_indices(void* stream, uint32_t* out, uint64_t n_indices);
+void launch_triangle_indices(void* stream, uint32_t* out, uint64_t n_indices);
 // Device layout <-> the ABI's exchange layout (T3D_NUM_COLUMNS columns of `host_stride` words).
 void launch_export_state(void* stream, const uint32_t* cols, uint32_t stride, uint32_t block_shift, uint32_t n, uint32_t* out,
                          uint32_t host_stride);

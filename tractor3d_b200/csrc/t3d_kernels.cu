@@ -486,6 +486,19 @@ __global__ void k_strip_indices(uint32_t* __restrict__ out, uint64_t n_indices)
     out[p] = v;
 }
 
+__global__ void k_triangle_indices(uint32_t* __restrict__ out, uint64_t n_indices)
+{
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_indices) return;
+    const uint32_t corner[6] = { 0, 1, 2, 2, 1, 3 }; // strip (a,b,c,d) = triangles (a,b,c), (c,b,d)
+    out[p] = (uint32_t)(4 * (p / 6)) + corner[p % 6];
+}
+
+void launch_triangle_indices(void* stream, uint32_t* out, uint64_t n_indices)
+{
+    if (n_indices) k_triangle_indices<<<(unsigned)((n_indices + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n_indices);
+}
+
 void launch_strip_indices(void* stream, uint32_t* out, uint64_t n_indices)
 {
     if (n_indices) k_strip_indices<<<(unsigned)((n_indices + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n_indices);

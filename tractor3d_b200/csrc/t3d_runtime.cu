@@ -162,6 +162,8 @@ struct t3d_ctx
 
     uint32_t* strip_indices{ nullptr }; // cached MeshBatch index pattern
     uint32_t strip_quads{ 0 };
+    uint32_t* tri_indices{ nullptr };   // cached triangle-list pattern
+    uint32_t tri_quads{ 0 };
 
     uint32_t* readback_host{ nullptr }; // pinned scratch for counts
     size_t readback_cap{ 0 };
@@ -1019,6 +1021,7 @@ int t3d_ctx_destroy(t3d_ctx* c)
     if (c->readback_host) cudaFreeHost(c->readback_host);
     if (c->readback_dev) cudaFree(c->readback_dev);
     if (c->strip_indices) cudaFree(c->strip_indices);
+    if (c->tri_indices) cudaFree(c->tri_indices);
     for (t3d_ctx::Feedback& fb : c->feedback)
     {
         if (fb.host) cudaFreeHost(fb.host);
@@ -1537,6 +1540,47 @@ int t3d_ctx_strip_indices(t3d_ctx* c, uint32_t n_quads, const uint32_t** device_
     }
     if (device_ptr) *device_ptr = c->strip_indices;
     if (n_indices) *n_indices = n;
+    return T3D_OK;
+}
+
+int t3d_ctx_triangle_indices(t3d_ctx* c, uint32_t n_quads, const uint32_t** device_ptr, uint64_t* n_indices)
+{
+    if (!c) return fail(T3D_ERR_INVALID, "null context");
+    T3D_TRY(use_device(c));
+    if (n_quads > c->tri_quads)
+    {
+        if (c->tri_indices)
+        {
+            T3D_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(c->tri_indices);
+            c->tri_indices = nullptr;
+            c->tri_quads = 0;
+        }
+        const uint32_t cap = std::max<uint32_t>(n_quads, 1024);
+        T3D_CUDA(cudaMalloc((void**)&c->tri_indices, 6ull * cap * sizeof(uint32_t)));
+        launch_triangle_indices(c->stream, c->tri_indices, 6ull * cap);
+        T3D_CUDA(cudaGetLastError());
+        c->launches++;
+        c->tri_quads = cap;
+    }
+    if (device_ptr) *device_ptr = c->tri_indices;
+    if (n_indices) *n_indices = 6ull * n_quads;
+    return T3D_OK;
+}
+
+int t3d_ctx_download_triangle_indices(t3d_ctx* c, uint32_t n_quads, uint32_t* out, uint64_t max_indices, uint64_t* n_indices)
+{
+    const uint32_t* dev = nullptr;
+    uint64_t n = 0;
+    T3D_TRY(t3d_ctx_triangle_indices(c, n_quads, &dev, &n));
+    if (n_indices) *n_indices = n;
+    const uint64_t m = std::min<uint64_t>(n, max_indices);
+    if (out && m)
+    {
+        T3D_CUDA(cudaMemcpyAsync(out, dev, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        T3D_CUDA(cudaStreamSynchronize(c->stream));
+        c->d2h_bytes += m * sizeof(uint32_t);
+    }
     return T3D_OK;
 }
 

@@ -89,6 +89,13 @@ class Context:
         _check(self.lib, self.lib.t3d_ctx_download_strip_indices(self.h, n_quads, out.ctypes.data_as(_P(C.c_uint32)), out.size, C.byref(n)))
         return out[: n.value]
 
+    def triangle_indices(self, n_quads):
+        """Triangle-list indices for n_quads quads (uint32 numpy copy)."""
+        n = C.c_uint64()
+        out = np.zeros(max(6 * n_quads, 1), dtype=np.uint32)
+        _check(self.lib, self.lib.t3d_ctx_download_triangle_indices(self.h, n_quads, out.ctypes.data_as(_P(C.c_uint32)), out.size, C.byref(n)))
+        return out[: n.value]
+
     def launch_count(self):
         n = C.c_uint64()
         _check(self.lib, self.lib.t3d_ctx_launch_count(self.h, C.byref(n)))
