@@ -437,8 +437,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             s_excl = excl;
         }
     }
-    __syncthreads();
-    const uint32_t tile_excl = s_excl;
+    // A tile in the first half of the emitter needs no prefix to know that every slot of it is examined:
+    // D(k) <= k, so k + D(k) <= 2k < N.  Its warps start streaming at once; the prefix (resolved by warp 0 above,
+    // which then joins them) is only needed for the sources of the moves, after the barrier at the end.
+    const bool certain = 2ull * ((unsigned long long)first + TILE) <= (unsigned long long)N;
+    if (!certain) __syncthreads();
+    const uint32_t tile_excl = certain ? 0u : s_excl; // certain: ranks below are tile-local
 
     // ---- phase B: stream the groups ----
     const float ppf = it.percent_per_frame;
@@ -470,12 +474,13 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 valid[l] = k0 + l < N;
                 alive[l] = valid[l] && e4[l] > 0;
                 D[l] = run;
-                examined[l] = valid[l] && (k0 + l + run < N);
+                examined[l] = valid[l] && (certain || k0 + l + run < N);
                 if (examined[l] && !alive[l])
                 {
-                    // PE.cpp:825-828: the last live particle, untouched this frame, takes the dead one's place.
+                    // PE.cpp:825-828: the last live particle, untouched this frame, takes the dead one's place
+                    // (unless the dead one IS the last: only possible in an uncertain tile).
                     const uint32_t src = N - 1u - run;
-                    if (src != k0 + l) s_move[run - tile_excl] = (unsigned short)(k0 + l - first);
+                    if (certain || src != k0 + l) s_move[run - tile_excl] = (unsigned short)(k0 + l - first);
                 }
                 run += (valid[l] && !alive[l]) ? 1u : 0u;
                 all_store = all_store && examined[l];
@@ -628,11 +633,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             }
         }
 
-        // the last examined original publishes the new count (PE.cpp:829)
+        // the last examined original publishes the new count (PE.cpp:829); it never lies in a certain tile
 #pragma unroll
         for (int l = 0; l < V; ++l)
         {
-            if (!examined[l]) continue;
+            if (certain || !examined[l]) continue;
             const uint32_t dead_l = alive[l] ? 0u : 1u;
             const bool next_examined = (k0 + l + 1u) + D[l] + dead_l < N;
             if (!next_examined)
@@ -652,7 +657,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     if (tile_dead)
     {
         __syncthreads(); // s_move complete; this CTA's stores to the dead slots are ordered before the moves
-        const uint32_t src_last = N - 1u - tile_excl;
+        const uint32_t src_last = N - 1u - s_excl; // the emitter-wide prefix, visible to all after the barrier
         constexpr int BATCH = T3D_NUM_COLUMNS / 2;
         for (uint32_t r = tid; r < tile_dead; r += THREADS)
         {
