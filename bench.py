@@ -159,7 +159,7 @@ def quick_measure(ctx, stream, workload, steps, torch):
         ctx.batch_update(emitters, DT, handles)
         ctx.batch_draw(emitters, handles)
     ctx.sync()
-    t0 = [ctx.kernel_time(k) for k in range(3)]
+    t0 = [ctx.kernel_time(k) for k in range(4)]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         ev0.record(stream)
@@ -171,12 +171,12 @@ def quick_measure(ctx, stream, workload, steps, torch):
     ctx.sync()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
-    t1 = [ctx.kernel_time(k) for k in range(3)]
+    t1 = [ctx.kernel_time(k) for k in range(4)]
     peak, _ = measured_peak_gbs()
     upd_b = UPDATE_BYTES + (UPDATE_BYTES_ANIMATED - UPDATE_BYTES) * animated_frac
     out = {"workload": wl_name, "particles": n, "steps": steps, "ms_per_step": ms / steps, "value": n * steps / (ms * 1e-3),
            "unit": "particles/s"}
-    for k, nm, b in ((1, "update", upd_b), (2, "draw", DRAW_BYTES)):
+    for k, nm, b in ((1, "update", upd_b), (2, "draw", DRAW_BYTES), (3, "update_draw", upd_b + DRAW_BYTES - 40)):
         dn = t1[k][1] - t0[k][1]
         if dn:
             ms_l = (t1[k][0] - t0[k][0]) / dn
@@ -238,7 +238,7 @@ def run_cuda(args):
     # ---- timed region: K frames back to back, device time on the launching stream ----
     sampler = ClockSampler(local_rank, getattr(torch.cuda.get_device_properties(local_rank), "uuid", None))
     sampler.start()
-    t_before = [ctx.kernel_time(k) for k in range(3)]
+    t_before = [ctx.kernel_time(k) for k in range(4)]
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
@@ -250,15 +250,17 @@ def run_cuda(args):
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.result()
-    t_after = [ctx.kernel_time(k) for k in range(3)]
+    t_after = [ctx.kernel_time(k) for k in range(4)]
     launches = ctx.launch_count() - launches0
     counts1 = ctx.batch_counts(emitters, handles)
     live_after = int(counts1.sum())
     updates_done = (local_particles if not churn else int((counts0.sum() + counts1.sum()) // 2)) * args.steps
 
     kern = {}
-    for k, nm in enumerate(("spawn", "update", "draw")):
+    for k, nm in enumerate(("spawn", "update", "draw", "update_draw")):
         dms, dn = t_after[k][0] - t_before[k][0], t_after[k][1] - t_before[k][1]
+        if nm == "update_draw" and not dn:
+            continue   # the fused launch only exists with T3D_FUSED=1
         kern[nm] = {"ms_per_launch": (dms / dn) if dn else None, "launches": int(dn), "ms_total": dms}
 
     # ---- e2e: the same frames through the per-emitter public calls, host inputs in, host results out, every frame ----
@@ -324,8 +326,10 @@ def run_cuda(args):
         per_launch_particles = local_particles if not churn else updates_done / args.steps
         roof = {}
         traffic = measured_traffic()
-        for nm, b in (("update", upd_bytes), ("draw", DRAW_BYTES)):
-            ms = kern[nm]["ms_per_launch"]
+        # fused: the draw's 40 B re-read of position/colour/size/angle/frame disappears (the frame index is read once)
+        fused_bytes = upd_bytes + DRAW_BYTES - 40 + (0 if animated_frac == 1.0 else 4 * (1 - animated_frac))
+        for nm, b in (("update", upd_bytes), ("draw", DRAW_BYTES), ("update_draw", fused_bytes)):
+            ms = kern.get(nm, {}).get("ms_per_launch")
             if ms:
                 ach = b * per_launch_particles / (ms * 1e-3) / 1e9
                 tr = traffic.get(nm, {}).get("bytes_per_unit") if workload == "c3" else None

@@ -141,7 +141,7 @@ int t3d_ctx_get_frozen_rotation(t3d_ctx* ctx, float m[16], int* latched);
  * accumulator (PE.cpp:720) and the latched rotation (SB.cpp:339) -- i.e. "a fresh process". */
 int t3d_ctx_reset_statics(t3d_ctx* ctx);
 /* Device time in ms of the last flushed launch of each kind (CUDA events on the context's stream):
- * which = 0 spawn, 1 update, 2 draw.  Waits for that launch to finish. */
+ * which = 0 spawn, 1 update, 2 draw, 3 fused update+draw (T3D_FUSED=1).  Waits for that launch to finish. */
 int t3d_ctx_last_kernel_ms(t3d_ctx* ctx, int which, float* ms);
 /* Cumulative device time (ms) and number of launches of one kind since the context was created; every
  * launch is bracketed by its own event pair, so a caller can difference two readings around a timed region. */

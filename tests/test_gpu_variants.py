@@ -1,6 +1,7 @@
 """The alternative code paths kept in the library (selected by environment variables read once per process)
 must stay parity-green too: the plain-LDG update kernel, ticket-ordered tiles, the blocked struct-of-arrays
-layout, the LSU copy-out of the draw kernel.  Each runs a slice of the parity suite in a fresh process."""
+layout, the LSU copy-out of the draw kernel, the fused update+draw launch.  Each runs a slice of the parity suite
+in a fresh process."""
 import os
 import subprocess
 import sys
@@ -17,6 +18,9 @@ CASES = [
     {"T3D_LAYOUT_BLOCK": "512"},
     {"T3D_LAYOUT_BLOCK": "256", "T3D_UPDATE_VARIANT": "v2t256s4b4"},
     {"T3D_DRAW_VARIANT": "lsu"},
+    {"T3D_FUSED": "1"},
+    {"T3D_FUSED": "1", "T3D_FUSED_VARIANT": "f4t64s10b2"},
+    {"T3D_FUSED": "1", "T3D_FUSED_VARIANT": "g4t128s8b2", "T3D_LAYOUT_BLOCK": "512"},
 ]
 
 
@@ -28,3 +32,31 @@ def test_alternative_paths_stay_bit_exact(env):
            "-k", "golden or multi_tile or batch_of_mixed or device_rng"]
     res = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+
+
+FUSED_PROBE = """
+import numpy as np
+from tractor3d_b200 import abi, presets
+from tractor3d_b200.emitter import Context, ParticleEmitter
+ctx = Context(0)
+p, sprite = presets.fire()
+es = [ParticleEmitter.create(ctx, p, sprite, (abi.RNG_DEVICE, 5 + k)) for k in range(3)]
+ctx.batch_emit_once(es, [1000] * 3)
+for _ in range(6):
+    ctx.batch_update(es, 16.0)
+    ctx.batch_draw(es)
+ctx.sync()
+print("FUSED_LAUNCHES", ctx.kernel_time(3)[1], "SEPARATE", ctx.kernel_time(1)[1], ctx.kernel_time(2)[1])
+"""
+
+
+def test_fused_launch_is_what_runs_when_enabled():
+    """update(set) directly followed by draw(same set) goes out as ONE launch with T3D_FUSED=1, as two without."""
+    for fused, expect in (("1", lambda f, u, d: f >= 5 and d <= 1), ("0", lambda f, u, d: f == 0 and u == 6 and d == 6)):
+        e = dict(os.environ)
+        e["T3D_FUSED"] = fused
+        res = subprocess.run([sys.executable, "-c", FUSED_PROBE], env=e, capture_output=True, text=True, timeout=300, cwd=ROOT)
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+        line = [l for l in res.stdout.splitlines() if l.startswith("FUSED_LAUNCHES")][0].split()
+        f, u, d = int(line[1]), int(line[3]), int(line[4])
+        assert expect(f, u, d), (fused, line)

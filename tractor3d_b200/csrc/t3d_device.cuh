@@ -75,6 +75,92 @@ __device__ __forceinline__ void rot_apply(const Rot3& r, float w, float& x, floa
     z = oz;
 }
 
+// The latched rotation (3x3 part), fetched once per thread.
+__device__ __forceinline__ Rot3 load_frozen(const FrozenRotation* __restrict__ f)
+{
+    Rot3 r;
+    r.m0 = f->m[0]; r.m1 = f->m[1]; r.m2 = f->m[2];
+    r.m4 = f->m[4]; r.m5 = f->m[5]; r.m6 = f->m[6];
+    r.m8 = f->m[8]; r.m9 = f->m[9]; r.m10 = f->m[10];
+    return r;
+}
+
+// One billboard quad in SpriteBatch's vertex layout (SB.cpp:292-363 through PE.cpp:866-882): 4 vertices x
+// {position, uv, colour} = 36 floats written as nine float4.  rotationPoint = (0.5, 0.5) (PE.cpp:855).
+// get_frozen() yields the latched rotation; it is only called for a rotated quad in T3D_ROT_FROZEN mode.
+template <class GetFrozen>
+__device__ __forceinline__ void expand_quad(const float pos[3], const float color[4], float size, float angle, float u1,
+                                            float v1, float u2, float v2, const float right[3], const float up[3],
+                                            int rot_mode, GetFrozen get_frozen, float4* __restrict__ o)
+{
+    const float width = size, height = size;
+    // SB.cpp:306-324
+    float p0[3], p1[3], p2[3], p3[3], tfw[3];
+    const float hw = width * 0.5f, hh = height * 0.5f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+        const float tr = right[k] * hw;
+        const float tf = up[k] * hh;
+        p0[k] = pos[k];
+        p0[k] -= tr;
+        p0[k] -= tf;
+        p1[k] = pos[k];
+        p1[k] += tr;
+        p1[k] -= tf;
+        tfw[k] = up[k] * height;
+        p2[k] = p0[k] + tfw[k];
+        p3[k] = p1[k] + tfw[k];
+    }
+    if (angle != 0) // SB.cpp:327
+    {
+        float rp[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            const float tr = right[k] * (width * 0.5f); // rotationPoint.x = 0.5 (PE.cpp:855)
+            const float tf = tfw[k] * 0.5f;
+            rp[k] = p0[k];
+            rp[k] += tr;
+            rp[k] += tf;
+        }
+        Rot3 r;
+        if (rot_mode == T3D_ROT_FROZEN)
+            r = get_frozen(); // SB.cpp:339: the matrix latched by the first rotated quad of the process
+        else
+        {
+            // MathUtil.h:216-225
+            const float ux = (right[1] * up[2]) - (right[2] * up[1]);
+            const float uy = (right[2] * up[0]) - (right[0] * up[2]);
+            const float uz = (right[0] * up[1]) - (right[1] * up[0]);
+            r = create_rotation(ux, uy, uz, angle);
+        }
+        float* ps[4] = { p0, p1, p2, p3 };
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+            float* p = ps[q];
+            p[0] -= rp[0];
+            p[1] -= rp[1];
+            p[2] -= rp[2];
+            rot_apply(r, 0.0f, p[0], p[1], p[2]); // Vector3 *= Matrix: transformVector, w = 0
+            p[0] += rp[0];
+            p[1] += rp[1];
+            p[2] += rp[2];
+        }
+    }
+    // SB.cpp:355-359: v0=(p0,u1,v1) v1=(p1,u2,v1) v2=(p2,u1,v2) v3=(p3,u2,v2), particle colour on all four.
+    o[0] = make_float4(p0[0], p0[1], p0[2], u1);
+    o[1] = make_float4(v1, color[0], color[1], color[2]);
+    o[2] = make_float4(color[3], p1[0], p1[1], p1[2]);
+    o[3] = make_float4(u2, v1, color[0], color[1]);
+    o[4] = make_float4(color[2], color[3], p2[0], p2[1]);
+    o[5] = make_float4(p2[2], u1, v2, color[0]);
+    o[6] = make_float4(color[1], color[2], color[3], p3[0]);
+    o[7] = make_float4(p3[1], p3[2], u2, v2);
+    o[8] = make_float4(color[0], color[1], color[2], color[3]);
+}
+
 // Address of particle i's word in column 0 of an emitter; its word in column c lies c * stride words further.
 //   block_shift == 0  plain struct-of-arrays: stride = slab capacity.
 //   block_shift == k  blocked struct-of-arrays: 2^k consecutive particles keep their 34 columns in one contiguous

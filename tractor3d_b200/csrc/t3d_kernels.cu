@@ -248,79 +248,8 @@ __global__ void __launch_bounds__(kDrawThreads)
 
         const float right[3] = { it.right[0], it.right[1], it.right[2] };
         const float up[3] = { it.up[0], it.up[1], it.up[2] };
-        const float width = size, height = size;
-
-        // SB.cpp:306-324
-        float p0[3], p1[3], p2[3], p3[3], tfw[3];
-        const float hw = width * 0.5f, hh = height * 0.5f;
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-        {
-            const float tr = right[k] * hw;
-            const float tf = up[k] * hh;
-            p0[k] = pos[k];
-            p0[k] -= tr;
-            p0[k] -= tf;
-            p1[k] = pos[k];
-            p1[k] += tr;
-            p1[k] -= tf;
-            tfw[k] = up[k] * height;
-            p2[k] = p0[k] + tfw[k];
-            p3[k] = p1[k] + tfw[k];
-        }
-        if (angle != 0) // SB.cpp:327
-        {
-            float rp[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-            {
-                const float tr = right[k] * (width * 0.5f); // rotationPoint.x = 0.5 (PE.cpp:855)
-                const float tf = tfw[k] * 0.5f;
-                rp[k] = p0[k];
-                rp[k] += tr;
-                rp[k] += tf;
-            }
-            Rot3 r;
-            if (rot_mode == T3D_ROT_FROZEN)
-            {
-                // SB.cpp:339: the matrix latched by the first rotated quad of the process.
-                r.m0 = frozen->m[0]; r.m1 = frozen->m[1]; r.m2 = frozen->m[2];
-                r.m4 = frozen->m[4]; r.m5 = frozen->m[5]; r.m6 = frozen->m[6];
-                r.m8 = frozen->m[8]; r.m9 = frozen->m[9]; r.m10 = frozen->m[10];
-            }
-            else
-            {
-                // MathUtil.h:216-225
-                const float ux = (right[1] * up[2]) - (right[2] * up[1]);
-                const float uy = (right[2] * up[0]) - (right[0] * up[2]);
-                const float uz = (right[0] * up[1]) - (right[1] * up[0]);
-                r = create_rotation(ux, uy, uz, angle);
-            }
-            float* ps[4] = { p0, p1, p2, p3 };
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-            {
-                float* p = ps[q];
-                p[0] -= rp[0];
-                p[1] -= rp[1];
-                p[2] -= rp[2];
-                rot_apply(r, 0.0f, p[0], p[1], p[2]); // Vector3 *= Matrix: transformVector, w = 0
-                p[0] += rp[0];
-                p[1] += rp[1];
-                p[2] += rp[2];
-            }
-        }
-        // SB.cpp:355-359: v0=(p0,u1,v1) v1=(p1,u2,v1) v2=(p2,u1,v2) v3=(p3,u2,v2), particle colour on all four.
-        float4* o = reinterpret_cast<float4*>(s_vtx + tid * T3D_FLOATS_PER_QUAD);
-        o[0] = make_float4(p0[0], p0[1], p0[2], u1);
-        o[1] = make_float4(v1, color[0], color[1], color[2]);
-        o[2] = make_float4(color[3], p1[0], p1[1], p1[2]);
-        o[3] = make_float4(u2, v1, color[0], color[1]);
-        o[4] = make_float4(color[2], color[3], p2[0], p2[1]);
-        o[5] = make_float4(p2[2], u1, v2, color[0]);
-        o[6] = make_float4(color[1], color[2], color[3], p3[0]);
-        o[7] = make_float4(p3[1], p3[2], u2, v2);
-        o[8] = make_float4(color[0], color[1], color[2], color[3]);
+        expand_quad(pos, color, size, angle, u1, v1, u2, v2, right, up, rot_mode, [&] { return load_frozen(frozen); },
+                    reinterpret_cast<float4*>(s_vtx + tid * T3D_FLOATS_PER_QUAD));
     }
     // The sub-tile's vertices: nq quads * 144 B, contiguous in the emitter's vertex stream (16-byte aligned).
     const uint32_t nq = (N - first) < (uint32_t)kDrawThreads ? (N - first) : (uint32_t)kDrawThreads;

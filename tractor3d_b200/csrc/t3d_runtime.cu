@@ -64,7 +64,7 @@ namespace
 {
 
 enum Phase { PHASE_NONE = 0, PHASE_EMIT = 1, PHASE_UPDATE = 2, PHASE_DRAW = 3 };
-enum { KERNEL_SPAWN = 0, KERNEL_UPDATE = 1, KERNEL_DRAW = 2 };
+enum { KERNEL_SPAWN = 0, KERNEL_UPDATE = 1, KERNEL_DRAW = 2, KERNEL_UPDATE_DRAW = 3, KERNEL_KINDS = 4 };
 
 struct Slab
 {
@@ -132,6 +132,9 @@ struct t3d_ctx
 
     int phase{ PHASE_NONE };
     std::vector<PendingOp> pending;
+    // Updates whose launch is deferred because a draw phase was opened right behind them: if the draws turn out to
+    // cover the same emitters in the same order, both become one fused launch (T3D_FUSED=1).
+    std::vector<PendingOp> held;
     std::vector<int32_t> pending_draws;
     std::vector<uint32_t> pending_offsets;
 
@@ -139,10 +142,10 @@ struct t3d_ctx
     // Per-kind launch timing: every launch is bracketed by a pair of events on the stream; pairs are
     // resolved (and recycled) lazily when somebody asks for the totals.
     struct EventPair { cudaEvent_t start, stop; };
-    std::vector<EventPair> ev_pending[3], ev_free;
-    double kernel_ms_total[3]{ 0, 0, 0 };
-    uint64_t kernel_launches[3]{ 0, 0, 0 };
-    float kernel_ms_last[3]{ 0, 0, 0 };
+    std::vector<EventPair> ev_pending[KERNEL_KINDS], ev_free;
+    double kernel_ms_total[KERNEL_KINDS]{ 0, 0, 0, 0 };
+    uint64_t kernel_launches[KERNEL_KINDS]{ 0, 0, 0, 0 };
+    float kernel_ms_last[KERNEL_KINDS]{ 0, 0, 0, 0 };
     bool timing_enabled{ true };
 
     // Asynchronous count feedback: after every update launch the new live counts are copied to pinned memory
@@ -204,6 +207,7 @@ struct t3d_emitter
     uint32_t count_ub{ 0 };     // upper bound of the live count (exact when count_exact)
     bool count_exact{ true };
     bool queued{ false };
+    bool held{ false }; // has an update in ctx->held (launch deferred, see flush)
     bool last_draw_empty{ true }; // the last draw() submitted no quads (inactive or no particles)
     uint64_t emitted_total{ 0 };  // particles ever asked to spawn (upper bound of those spawned)
     // Milliseconds for which at least one particle is GUARANTEED to be alive: a particle that certainly spawned
@@ -549,12 +553,12 @@ static void poll_feedback(t3d_ctx* c)
 }
 
 // Enqueues the read-back of the counts the update launch just produced; never waits.
-static int submit_feedback(t3d_ctx* c, const CountQuery* dev_queries)
+static int submit_feedback(t3d_ctx* c, const std::vector<PendingOp>& ops, const CountQuery* dev_queries)
 {
     t3d_ctx::Feedback& fb = c->feedback[c->feedback_next];
     if (fb.in_flight) return T3D_OK; // all slots busy: skip this frame's feedback
     c->feedback_next = (c->feedback_next + 1) % 4;
-    const size_t n = c->pending.size();
+    const size_t n = ops.size();
     if (fb.cap < n)
     {
         if (fb.host) cudaFreeHost(fb.host);
@@ -570,8 +574,8 @@ static int submit_feedback(t3d_ctx* c, const CountQuery* dev_queries)
     fb.emitted_mark.resize(n);
     for (size_t i = 0; i < n; ++i)
     {
-        fb.es[i] = c->pending[i].e;
-        fb.emitted_mark[i] = c->pending[i].e->emitted_total;
+        fb.es[i] = ops[i].e;
+        fb.emitted_mark[i] = ops[i].e->emitted_total;
     }
     launch_gather_counts(c->stream, dev_queries, (uint32_t)n, fb.dev);
     T3D_CUDA(cudaGetLastError());
@@ -583,24 +587,16 @@ static int submit_feedback(t3d_ctx* c, const CountQuery* dev_queries)
     return T3D_OK;
 }
 
-static int launch_updates(t3d_ctx* c)
+// Cuts the update descriptors (and the count queries of the feedback) of `ops`; advances each emitter's parity.
+static void build_update_items(std::vector<PendingOp>& ops, UpdateItem* items, CountQuery* queries, uint32_t tile_size, uint32_t* tiles_out)
 {
-    const uint32_t n_items = (uint32_t)c->pending.size();
-    StagingSlot* slot;
-    const size_t items_bytes = align_up(sizeof(UpdateItem) * n_items, 16);
-    const size_t total_bytes = items_bytes + sizeof(CountQuery) * n_items;
-    T3D_TRY(staging_acquire(c, total_bytes, &slot));
-    UpdateItem* items = reinterpret_cast<UpdateItem*>(slot->host);
-    CountQuery* queries = reinterpret_cast<CountQuery*>(slot->host + items_bytes);
     uint32_t tiles = 0;
-    const uint32_t tile_size = (uint32_t)update_tile_size();
-    for (uint32_t k = 0; k < n_items; ++k)
+    for (size_t k = 0; k < ops.size(); ++k)
     {
-        PendingOp& op = c->pending[k];
+        PendingOp& op = ops[k];
         t3d_emitter* e = op.e;
-        T3D_TRY(sync_const(e));
         UpdateItem& it = items[k];
-        const EmitterConst& ec = e->hc; // current: sync_const ran just above
+        const EmitterConst& ec = e->hc; // current: sync_const ran just before
         memset(&it, 0, sizeof(it));
         it.dev = e->dev;
         it.cols = ec.cols;
@@ -621,6 +617,11 @@ static int launch_updates(t3d_ctx* c)
         // At least one tile per emitter: tile 0 republishes the count into the other parity slot.
         tiles += std::max(1u, (e->count_ub + tile_size - 1) / tile_size);
     }
+    *tiles_out = tiles;
+}
+
+static int begin_scan_epoch(t3d_ctx* c, uint32_t tiles)
+{
     if (c->tile_status_cap < tiles)
     {
         if (c->tile_status)
@@ -639,6 +640,22 @@ static int launch_updates(t3d_ctx* c)
         T3D_CUDA(cudaMemsetAsync(c->tile_status, 0, c->tile_status_cap * sizeof(unsigned long long), c->stream));
         c->epoch = 1;
     }
+    return T3D_OK;
+}
+
+static int launch_updates(t3d_ctx* c, std::vector<PendingOp>& ops)
+{
+    const uint32_t n_items = (uint32_t)ops.size();
+    if (!n_items) return T3D_OK;
+    for (PendingOp& op : ops) T3D_TRY(sync_const(op.e));
+    StagingSlot* slot;
+    const size_t items_bytes = align_up(sizeof(UpdateItem) * n_items, 16);
+    const size_t total_bytes = items_bytes + sizeof(CountQuery) * n_items;
+    T3D_TRY(staging_acquire(c, total_bytes, &slot));
+    uint32_t tiles = 0;
+    build_update_items(ops, reinterpret_cast<UpdateItem*>(slot->host), reinterpret_cast<CountQuery*>(slot->host + items_bytes),
+                       (uint32_t)update_tile_size(), &tiles);
+    T3D_TRY(begin_scan_epoch(c, tiles));
     T3D_TRY(staging_submit(c, slot, total_bytes));
     T3D_TRY(time_begin(c, KERNEL_UPDATE));
     launch_update(c->stream, reinterpret_cast<const UpdateItem*>(slot->dev), n_items, tiles, c->tile_status, c->ticket,
@@ -647,16 +664,15 @@ static int launch_updates(t3d_ctx* c)
     T3D_TRY(time_end(c, KERNEL_UPDATE));
     c->ticket_base += tiles;
     c->launches++;
-    T3D_TRY(submit_feedback(c, reinterpret_cast<const CountQuery*>(slot->dev + items_bytes)));
+    T3D_TRY(submit_feedback(c, ops, reinterpret_cast<const CountQuery*>(slot->dev + items_bytes)));
     T3D_TRY(staging_release(c, slot));
     return T3D_OK;
 }
 
-static int launch_draws(t3d_ctx* c)
+// Vertex storage is allocated per slab the first time one of its emitters is drawn.
+static int ensure_vertex_storage(t3d_ctx* c, std::vector<PendingOp>& ops)
 {
-    const uint32_t n_items = (uint32_t)c->pending.size();
-    // Vertex storage is allocated per slab the first time one of its emitters is drawn.
-    for (PendingOp& op : c->pending)
+    for (PendingOp& op : ops)
     {
         Slab& s = c->slabs[op.e->slab];
         if (!s.vtx)
@@ -666,19 +682,20 @@ static int launch_draws(t3d_ctx* c)
                 if (o->slab == op.e->slab) o->const_dirty = true;
         }
     }
-    StagingSlot* slot;
-    T3D_TRY(staging_acquire(c, sizeof(DrawItem) * n_items, &slot));
-    DrawItem* items = reinterpret_cast<DrawItem*>(slot->host);
+    for (PendingOp& op : ops) T3D_TRY(sync_const(op.e));
+    return T3D_OK;
+}
+
+static void build_draw_items(std::vector<PendingOp>& ops, DrawItem* items, uint32_t draw_tile, uint32_t* tiles_out, bool* any_spin_out)
+{
     uint32_t tiles = 0;
     bool any_spin = false;
-    const uint32_t draw_tile = (uint32_t)draw_tile_size(n_items);
-    for (uint32_t k = 0; k < n_items; ++k)
+    for (size_t k = 0; k < ops.size(); ++k)
     {
-        PendingOp& op = c->pending[k];
+        PendingOp& op = ops[k];
         t3d_emitter* e = op.e;
-        T3D_TRY(sync_const(e));
         DrawItem& it = items[k];
-        const EmitterConst& ec = e->hc; // current: sync_const ran just above
+        const EmitterConst& ec = e->hc; // current: sync_const ran just before
         memset(&it, 0, sizeof(it));
         it.dev = e->dev;
         it.cols = ec.cols;
@@ -695,6 +712,19 @@ static int launch_draws(t3d_ctx* c)
         tiles += std::max(1u, (e->count_ub + draw_tile - 1) / draw_tile);
         any_spin = any_spin || e->may_spin;
     }
+    *tiles_out = tiles;
+    *any_spin_out = any_spin;
+}
+
+static int launch_draws(t3d_ctx* c)
+{
+    const uint32_t n_items = (uint32_t)c->pending.size();
+    T3D_TRY(ensure_vertex_storage(c, c->pending));
+    StagingSlot* slot;
+    T3D_TRY(staging_acquire(c, sizeof(DrawItem) * n_items, &slot));
+    uint32_t tiles = 0;
+    bool any_spin = false;
+    build_draw_items(c->pending, reinterpret_cast<DrawItem*>(slot->host), (uint32_t)draw_tile_size(n_items), &tiles, &any_spin);
     T3D_TRY(staging_submit(c, slot, sizeof(DrawItem) * n_items));
     if (c->rot_mode == T3D_ROT_FROZEN && !c->frozen_latched && any_spin)
     {
@@ -724,26 +754,109 @@ static int launch_draws(t3d_ctx* c)
     return T3D_OK;
 }
 
-static int flush(t3d_ctx* c)
+// The held updates and the pending draws cover the same emitters in the same order, and no rotation matrix has to
+// be latched between them: one launch does both (k_update<..., FUSED>).
+static bool can_fuse(const t3d_ctx* c)
+{
+    if (c->held.empty() || c->held.size() != c->pending.size()) return false;
+    bool any_spin = false;
+    for (size_t k = 0; k < c->held.size(); ++k)
+    {
+        if (c->held[k].e != c->pending[k].e) return false;
+        any_spin = any_spin || c->held[k].e->may_spin;
+    }
+    if (c->rot_mode == T3D_ROT_FROZEN && !c->frozen_latched && any_spin) return false;
+    return true;
+}
+
+static int launch_fused_frame(t3d_ctx* c)
+{
+    const uint32_t n_items = (uint32_t)c->held.size();
+    T3D_TRY(ensure_vertex_storage(c, c->pending));
+    StagingSlot* slot;
+    const size_t items_bytes = align_up(sizeof(UpdateItem) * n_items, 16);
+    const size_t queries_bytes = align_up(sizeof(CountQuery) * n_items, 16);
+    const size_t total_bytes = items_bytes + queries_bytes + sizeof(DrawItem) * n_items;
+    T3D_TRY(staging_acquire(c, total_bytes, &slot));
+    uint32_t tiles = 0, draw_tiles = 0;
+    bool any_spin = false;
+    const uint32_t tile_size = (uint32_t)fused_tile_size();
+    build_update_items(c->held, reinterpret_cast<UpdateItem*>(slot->host), reinterpret_cast<CountQuery*>(slot->host + items_bytes),
+                       tile_size, &tiles);
+    build_draw_items(c->pending, reinterpret_cast<DrawItem*>(slot->host + items_bytes + queries_bytes), tile_size, &draw_tiles, &any_spin);
+    T3D_TRY(begin_scan_epoch(c, tiles));
+    T3D_TRY(staging_submit(c, slot, total_bytes));
+    T3D_TRY(time_begin(c, KERNEL_UPDATE_DRAW));
+    launch_update_draw(c->stream, reinterpret_cast<const UpdateItem*>(slot->dev),
+                       reinterpret_cast<const DrawItem*>(slot->dev + items_bytes + queries_bytes), n_items, tiles, c->tile_status,
+                       c->epoch, c->rot_mode, c->frozen_dev);
+    T3D_CUDA(cudaGetLastError());
+    T3D_TRY(time_end(c, KERNEL_UPDATE_DRAW));
+    c->launches++;
+    T3D_TRY(submit_feedback(c, c->held, reinterpret_cast<const CountQuery*>(slot->dev + items_bytes)));
+    T3D_TRY(staging_release(c, slot));
+    return T3D_OK;
+}
+
+static int launch_held(t3d_ctx* c)
+{
+    if (c->held.empty()) return T3D_OK;
+    const int rc = launch_updates(c, c->held);
+    for (PendingOp& op : c->held) op.e->held = false;
+    c->held.clear();
+    return rc;
+}
+
+// Launches what is queued.  next_phase is the phase the caller is about to open: updates directly followed by draws
+// are held back one step so that both can go out as one fused launch when they cover the same emitters.
+static int flush(t3d_ctx* c, int next_phase = PHASE_NONE)
 {
     if (c->phase == PHASE_NONE || c->pending.empty())
     {
         c->phase = PHASE_NONE;
+        if (next_phase != PHASE_DRAW && !c->held.empty())
+        {
+            T3D_TRY(use_device(c));
+            return launch_held(c);
+        }
         return T3D_OK;
     }
     T3D_TRY(use_device(c));
     poll_feedback(c);
     int rc = T3D_OK;
+    bool hold = false;
     if (c->phase == PHASE_EMIT)
-        rc = launch_spawns(c);
+    {
+        rc = launch_held(c);
+        if (rc == T3D_OK) rc = launch_spawns(c);
+    }
     else if (c->phase == PHASE_UPDATE)
     {
-        rc = launch_spawns(c);
-        if (rc == T3D_OK) rc = launch_updates(c);
+        rc = launch_held(c);
+        if (rc == T3D_OK) rc = launch_spawns(c);
+        hold = rc == T3D_OK && next_phase == PHASE_DRAW && fused_enabled();
+        if (rc == T3D_OK && !hold) rc = launch_updates(c, c->pending);
     }
     else if (c->phase == PHASE_DRAW)
-        rc = launch_draws(c);
+    {
+        if (can_fuse(c))
+        {
+            rc = launch_fused_frame(c);
+            for (PendingOp& op : c->held) op.e->held = false;
+            c->held.clear();
+        }
+        else
+        {
+            rc = launch_held(c);
+            if (rc == T3D_OK) rc = launch_draws(c);
+        }
+    }
     for (PendingOp& op : c->pending) op.e->queued = false;
+    if (hold)
+    {
+        c->held.swap(c->pending);
+        for (PendingOp& op : c->held) op.e->held = true;
+    }
     c->pending.clear();
     c->pending_draws.clear();
     c->pending_offsets.clear();
@@ -753,7 +866,7 @@ static int flush(t3d_ctx* c)
 
 static int enqueue(t3d_ctx* c, int phase, const PendingOp& op)
 {
-    if (c->phase != phase || op.e->queued) T3D_TRY(flush(c));
+    if (c->phase != phase || op.e->queued) T3D_TRY(flush(c, phase));
     c->phase = phase;
     c->pending.push_back(op);
     op.e->queued = true;
@@ -1028,7 +1141,7 @@ int t3d_ctx_destroy(t3d_ctx* c)
         if (fb.dev) cudaFree(fb.dev);
         if (fb.done) cudaEventDestroy(fb.done);
     }
-    for (int k = 0; k < 3; ++k)
+    for (int k = 0; k < KERNEL_KINDS; ++k)
         for (auto& p : c->ev_pending[k]) c->ev_free.push_back(p);
     for (auto& p : c->ev_free)
     {
@@ -1095,7 +1208,7 @@ int t3d_ctx_reset_statics(t3d_ctx* c)
 
 int t3d_ctx_last_kernel_ms(t3d_ctx* c, int which, float* ms)
 {
-    if (!c || which < 0 || which > 2 || !ms) return fail(T3D_ERR_INVALID, "bad argument");
+    if (!c || which < 0 || which >= KERNEL_KINDS || !ms) return fail(T3D_ERR_INVALID, "bad argument");
     T3D_TRY(flush(c));
     T3D_TRY(resolve_timing(c, which, true));
     if (!c->kernel_launches[which]) return fail(T3D_ERR_INVALID, "no launch of kind %d has been recorded", which);
@@ -1105,7 +1218,7 @@ int t3d_ctx_last_kernel_ms(t3d_ctx* c, int which, float* ms)
 
 int t3d_ctx_kernel_time(t3d_ctx* c, int which, double* total_ms, uint64_t* n_launches)
 {
-    if (!c || which < 0 || which > 2) return fail(T3D_ERR_INVALID, "bad argument");
+    if (!c || which < 0 || which >= KERNEL_KINDS) return fail(T3D_ERR_INVALID, "bad argument");
     T3D_TRY(flush(c));
     T3D_TRY(resolve_timing(c, which, true));
     if (total_ms) *total_ms = c->kernel_ms_total[which];
@@ -1206,7 +1319,7 @@ int t3d_emitter_destroy(t3d_emitter* e)
 {
     if (!e) return T3D_OK;
     t3d_ctx* c = e->ctx;
-    if (e->queued) flush(c);
+    if (e->queued || e->held) flush(c);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (t3d_ctx::Feedback& fb : c->feedback)
@@ -1237,7 +1350,7 @@ int t3d_emitter_set_params(t3d_emitter* e, const t3d_emitter_params* p)
     if (p->particle_count_max > e->p.particle_count_max)
         return fail(T3D_ERR_CAPACITY, "particle_count_max cannot grow past the %u fixed at create (asked %u)",
                     e->p.particle_count_max, p->particle_count_max);
-    if (e->queued) T3D_TRY(flush(e->ctx));
+    if (e->queued || e->held) T3D_TRY(flush(e->ctx));
     apply_params(e, p);
     return T3D_OK;
 }
@@ -1268,7 +1381,7 @@ static int install_tex_coords(t3d_emitter* e, uint32_t frame_count)
 int t3d_emitter_set_sprite_tex_coords(t3d_emitter* e, uint32_t frame_count, const float* tex_coords)
 {
     if (!e || !frame_count || !tex_coords) return fail(T3D_ERR_INVALID, "setSpriteTexCoords: bad argument (PE.cpp:514-515)");
-    if (e->queued) T3D_TRY(flush(e->ctx));
+    if (e->queued || e->held) T3D_TRY(flush(e->ctx));
     e->tex_coords.assign(tex_coords, tex_coords + (size_t)frame_count * 4);
     return install_tex_coords(e, frame_count);
 }
@@ -1276,7 +1389,7 @@ int t3d_emitter_set_sprite_tex_coords(t3d_emitter* e, uint32_t frame_count, cons
 int t3d_emitter_set_sprite_frame_rects(t3d_emitter* e, uint32_t frame_count, const float* rects)
 {
     if (!e || !frame_count || !rects) return fail(T3D_ERR_INVALID, "setSpriteFrameCoords: bad argument (PE.cpp:528-529)");
-    if (e->queued) T3D_TRY(flush(e->ctx));
+    if (e->queued || e->held) T3D_TRY(flush(e->ctx));
     e->tex_coords.resize((size_t)frame_count * 4);
     t3d_host_sprite_rect_coords(frame_count, rects, e->tex_w_ratio, e->tex_h_ratio, e->tex_coords.data());
     return install_tex_coords(e, frame_count);
@@ -1285,7 +1398,7 @@ int t3d_emitter_set_sprite_frame_rects(t3d_emitter* e, uint32_t frame_count, con
 int t3d_emitter_set_sprite_frame_coords(t3d_emitter* e, uint32_t frame_count, int width, int height)
 {
     if (!e || !frame_count || !width || !height) return fail(T3D_ERR_INVALID, "setSpriteFrameCoords: bad argument (PE.cpp:552-553)");
-    if (e->queued) T3D_TRY(flush(e->ctx));
+    if (e->queued || e->held) T3D_TRY(flush(e->ctx));
     e->tex_coords.resize((size_t)frame_count * 4);
     t3d_host_sprite_frame_coords(frame_count, width, height, e->p.texture_width, e->p.texture_height, e->tex_coords.data());
     return install_tex_coords(e, frame_count);
@@ -1302,7 +1415,7 @@ int t3d_emitter_get_sprite_tex_coords(t3d_emitter* e, uint32_t* frame_count, flo
 int t3d_emitter_set_rng(t3d_emitter* e, int mode, uint64_t seed)
 {
     if (!e || mode < T3D_RNG_LIBC || mode > T3D_RNG_DEVICE) return fail(T3D_ERR_INVALID, "bad rng mode %d", mode);
-    if (e->queued) T3D_TRY(flush(e->ctx));
+    if (e->queued || e->held) T3D_TRY(flush(e->ctx));
     e->rng_mode = mode;
     e->rng_seed = seed;
     e->const_dirty = true;

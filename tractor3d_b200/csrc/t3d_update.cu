@@ -120,7 +120,8 @@ struct Ring
     float4* base; // [2][RC_COUNT][THREADS]
     uint32_t tid;
     __device__ __forceinline__ float4* slot(int stage, int c) const { return base + ((size_t)(stage * RC_COUNT + c) * THREADS + tid); }
-    __device__ __forceinline__ void issue(int stage, const uint32_t* g, size_t stride, bool animated) const
+    // animated: the sprite-step inputs; need_frame: the frame index alone (the fused draw reads it for the uv lookup)
+    __device__ __forceinline__ void issue(int stage, const uint32_t* g, size_t stride, bool animated, bool need_frame = false) const
     {
         auto G = [&](int col) { return g + (size_t)col * stride; };
         cp_async16(slot(stage, RC_EST), G(T3D_COL_ENERGY_START));
@@ -141,11 +142,8 @@ struct Ring
         }
         cp_async16(slot(stage, RC_SS), G(T3D_COL_SIZE_START));
         cp_async16(slot(stage, RC_SE), G(T3D_COL_SIZE_END));
-        if (animated)
-        {
-            cp_async16(slot(stage, RC_TF), G(T3D_COL_TIME_ON_FRAME));
-            cp_async16(slot(stage, RC_FRAME), G(T3D_COL_FRAME));
-        }
+        if (animated) cp_async16(slot(stage, RC_TF), G(T3D_COL_TIME_ON_FRAME));
+        if (animated || need_frame) cp_async16(slot(stage, RC_FRAME), G(T3D_COL_FRAME));
     }
 };
 __device__ __forceinline__ void unpack4(const float4& v, float* a) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
@@ -206,7 +204,7 @@ struct Appearance
     float cs[4][V], ce[4][V];
     float tf[V];
     int fr[V];
-    __device__ __forceinline__ void load(const uint32_t* base, size_t stride, bool animated)
+    __device__ __forceinline__ void load(const uint32_t* base, size_t stride, bool animated, bool need_frame = false)
     {
         auto col = [&](int c) -> const uint32_t* { return base + (size_t)c * stride; };
         Vec<V>::ld(col(T3D_COL_ENERGY_START), est);
@@ -218,14 +216,11 @@ struct Appearance
         }
         Vec<V>::ld(col(T3D_COL_SIZE_START), ss);
         Vec<V>::ld(col(T3D_COL_SIZE_END), se);
-        if (animated)
-        {
-            Vec<V>::ld(col(T3D_COL_TIME_ON_FRAME), tf);
-            Vec<V>::ld(col(T3D_COL_FRAME), fr);
-        }
+        if (animated) Vec<V>::ld(col(T3D_COL_TIME_ON_FRAME), tf);
+        if (animated || need_frame) Vec<V>::ld(col(T3D_COL_FRAME), fr);
     }
     template <int THREADS>
-    __device__ __forceinline__ void load_ring(const Ring<THREADS>& r, int stage, bool animated) // V == 4
+    __device__ __forceinline__ void load_ring(const Ring<THREADS>& r, int stage, bool animated, bool need_frame = false) // V == 4
     {
         unpack4(*r.slot(stage, RC_EST), est);
 #pragma unroll
@@ -236,11 +231,8 @@ struct Appearance
         }
         unpack4(*r.slot(stage, RC_SS), ss);
         unpack4(*r.slot(stage, RC_SE), se);
-        if (animated)
-        {
-            unpack4(*r.slot(stage, RC_TF), tf);
-            unpack4(*r.slot(stage, RC_FRAME), fr);
-        }
+        if (animated) unpack4(*r.slot(stage, RC_TF), tf);
+        if (animated || need_frame) unpack4(*r.slot(stage, RC_FRAME), fr);
     }
 };
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
@@ -248,12 +240,25 @@ __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory")
 // V = particles per thread per group, THREADS per CTA, SUB = groups per thread: a tile is V*THREADS*SUB
 // consecutive particles of one emitter and costs one look-back, so the scan frontier only has to advance
 // one tile per V*THREADS*SUB particles streamed.
-template <int V, int THREADS, int SUB, int MIN_BLOCKS, bool ASYNC, bool TICKET>
+//
+// FUSED (with ASYNC, V = 4): the same pass also emits the frame's billboard quads (what k_draw would produce from
+// the state this kernel leaves), so position/colour/size/angle/frame never make the round trip through HBM
+// between update and draw: 304 B per particle per frame instead of 344.  Each thread expands the 4 particles of
+// its group into the warp's piece of shared memory (128 consecutive quads, 18 KB), and one lane hands that piece to
+// the TMA engine with a cp.async.bulk -- warp-level sync only on the vertex path.  Slots that receive a moved
+// particle get their quad in the move pass; slots that are not examined lie beyond the new live count and are not
+// part of the frame's vertex stream.
+template <int V, int THREADS, int SUB, int MIN_BLOCKS, bool ASYNC, bool TICKET, bool FUSED = false>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     k_update(const UpdateItem* __restrict__ items, uint32_t n_items, uint32_t total_tiles,
              unsigned long long* __restrict__ tile_status, uint32_t* __restrict__ ticket, uint32_t ticket_base,
-             uint32_t epoch)
+             uint32_t epoch, const DrawItem* __restrict__ ditems = nullptr, int rot_mode = 0,
+             const FrozenRotation* __restrict__ frozen = nullptr)
 {
+    static_assert(!FUSED || V == 4, "the fused variant stages 4 quads per thread");
+    constexpr int kQuadBytes = T3D_FLOATS_PER_QUAD * 4;
+    constexpr int kStageWarp = 32 * 4 * kQuadBytes; // bytes of vertex staging per warp: its 128 consecutive quads
+    __shared__ float s_uv[FUSED ? kMaxSmemFrames * 4 : 1];
     constexpr int GROUP = V * THREADS;  // particles per sub-tile
     constexpr int TILE = GROUP * SUB;
     constexpr int WARPS = THREADS / 32;
@@ -284,7 +289,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     if (tile >= total_tiles) return;
 
     // One dependent fetch (the launch descriptor) and the loads can start; the live count is fetched in parallel.
-    const UpdateItem& it = items[find_item(items, n_items, tile, total_tiles)];
+    const uint32_t item_index = find_item(items, n_items, tile, total_tiles);
+    const UpdateItem& it = items[item_index];
     EmitterDev* const d = it.dev;
     const uint32_t parity = it.parity;
     uint32_t* const cols = it.cols;
@@ -313,15 +319,17 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     // The first group(s) are requested now so that they are in flight while the scan and look-back run.
     Motion<V> m;
     // The ring starts on a 128-byte boundary so that a warp's 512-byte cp.async destination covers whole lines.
+    // (The offset is added to the array itself so that the compiler keeps addressing it as shared memory.)
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    Ring<THREADS> ring{ reinterpret_cast<float4*>((reinterpret_cast<uintptr_t>(dyn_smem) + 127) & ~uintptr_t(127)), tid };
+    unsigned char* const ring_bytes = dyn_smem + ((128u - ((uint32_t)__cvta_generic_to_shared(dyn_smem) & 127u)) & 127u);
+    Ring<THREADS> ring{ reinterpret_cast<float4*>(ring_bytes), tid };
     if (ASYNC)
     {
 #pragma unroll
         for (int s = 0; s < (SUB < 2 ? SUB : 2); ++s)
         {
             const uint32_t k0 = first + s * GROUP + tid * V;
-            if (k0 < cap) ring.issue(s, particle_base(cols, bshift, k0), stride, animated);
+            if (k0 < cap) ring.issue(s, particle_base(cols, bshift, k0), stride, animated, FUSED);
             cp_async_commit();
         }
     }
@@ -336,8 +344,32 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         {
             d->cnt[parity ^ 1].count = 0;
             d->cnt[parity ^ 1].serial = d->cnt[parity].serial;
+            if (FUSED) d->cnt[0].drawn = 0;
         }
         return;
+    }
+    // the draw side of the launch descriptor (FUSED)
+    float right[3] = { 0, 0, 0 }, up[3] = { 0, 0, 0 };
+    float* vtx = nullptr;
+    const float* uv_g = nullptr;
+    bool uv_in_smem = false;
+    unsigned char* stage_warp = ring_bytes + (ASYNC ? 2 * (size_t)RC_COUNT * THREADS * sizeof(float4) : 0) + (size_t)warp * kStageWarp;
+    Rot3 frozen_rot = {};
+    if (FUSED)
+    {
+        frozen_rot = load_frozen(frozen);
+        const DrawItem& di = ditems[item_index];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            right[k] = di.right[k];
+            up[k] = di.up[k];
+        }
+        vtx = di.vtx;
+        uv_g = di.uv;
+        uv_in_smem = it.frame_count <= (uint32_t)kMaxSmemFrames;
+        if (uv_in_smem)
+            for (uint32_t q = tid; q < it.frame_count * 4u; q += THREADS) s_uv[q] = uv_g[q]; // visible after the scan's barrier
     }
     uint32_t cnt[SUB];
 #pragma unroll
@@ -452,7 +484,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     for (int s = 0; s < SUB; ++s)
     {
         const uint32_t k0 = first + s * GROUP + tid * V;
-        if (k0 >= N) break;
+        // (FUSED: warps leave together -- the vertex staging below is warp-collective)
+        if ((FUSED ? first + s * GROUP + (tid & ~31u) * V : k0) >= N) break;
         int e4[V];
 #pragma unroll
         for (int l = 0; l < V; ++l) e4[l] = s_en[(s * THREADS + tid) * V + l];
@@ -561,17 +594,17 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         Appearance<V> a;
         if (ASYNC)
         {
-            a.load_ring(ring, s & 1, animated);
+            a.load_ring(ring, s & 1, animated, FUSED);
             // This stage's slots are consumed: refill them with the group after next.
             if (s + 2 < SUB)
             {
                 const uint32_t kn = first + (s + 2) * GROUP + tid * V;
-                if (kn < N) ring.issue(s & 1, particle_base(cols, bshift, kn), stride, animated);
+                if (kn < N) ring.issue(s & 1, particle_base(cols, bshift, kn), stride, animated, FUSED);
                 cp_async_commit();
             }
         }
         else
-            a.load(gbase, stride, animated);
+            a.load(gbase, stride, animated, FUSED);
         float col_out[4][V], size_out[V];
 #pragma unroll
         for (int l = 0; l < V; ++l)
@@ -633,6 +666,43 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             }
         }
 
+        if (FUSED)
+        {
+            // -- the quads of this group: PE.cpp:866-882 + SB.cpp:292-363 on the values just computed --
+            // Examined slots form a prefix of the group (k + D(k) is increasing); the rest lie beyond the new count.
+            uint32_t n_quads = 0;
+#pragma unroll
+            for (int l = 0; l < V; ++l) n_quads += examined[l] ? 1u : 0u;
+            const uint32_t warp_quads = __reduce_add_sync(0xffffffffu, n_quads);
+            if (warp_quads)
+            {
+                // the warp's piece of shared memory is reused: its previous bulk store must have read it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+#pragma unroll
+                for (int l = 0; l < V; ++l)
+                {
+                    if (!(examined[l] && alive[l])) continue; // dead: the move pass writes this quad
+                    const uint32_t frame = (uint32_t)a.fr[l] < frame_count ? (uint32_t)a.fr[l] : frame_count - 1u;
+                    const float* uv = uv_in_smem ? (s_uv + frame * 4u) : (uv_g + (size_t)frame * 4u);
+                    const float pos[3] = { m.px[l], m.py[l], m.pz[l] };
+                    const float rgba[4] = { col_out[0][l], col_out[1][l], col_out[2][l], col_out[3][l] };
+                    expand_quad(pos, rgba, size_out[l], m.ang[l], uv[0], uv[1], uv[2], uv[3], right, up, rot_mode, [&] { return frozen_rot; },
+                                reinterpret_cast<float4*>(stage_warp + (lane * V + l) * kQuadBytes));
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0)
+                {
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage_warp);
+                    const uint32_t bytes = warp_quads * (uint32_t)kQuadBytes;
+                    float* dst = vtx + (size_t)(first + s * GROUP + warp * 32u * V) * T3D_FLOATS_PER_QUAD;
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        }
+
         // the last examined original publishes the new count (PE.cpp:829); it never lies in a certain tile
 #pragma unroll
         for (int l = 0; l < V; ++l)
@@ -644,9 +714,17 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             {
                 d->cnt[parity ^ 1].count = N - D[l] - dead_l;
                 d->cnt[parity ^ 1].serial = d->cnt[parity].serial;
+                if (FUSED) d->cnt[0].drawn = N - D[l] - dead_l;
             }
         }
         compiler_fence();
+    }
+    // shared memory must outlive the bulk stores, and their writes must have landed before the move pass overwrites
+    // the quads of the slots it fills
+    if (FUSED && lane == 0)
+    {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
     }
 
     // ---- the moves: rank r of this tile's dead particles pulls original N-1-(tile_excl+r) into its slot.  One thread
@@ -665,6 +743,26 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             if (off == kNoMove) continue;
             uint32_t* const dst = particle_base(cols, bshift, first + off);
             const uint32_t* const src = particle_base(cols, bshift, src_last - r);
+            if (FUSED)
+            {
+                // the whole record is needed at once: the moved particle is drawn as it stands (PE.cpp:866-882)
+                uint32_t val[T3D_NUM_COLUMNS];
+#pragma unroll
+                for (int j = 0; j < T3D_NUM_COLUMNS; ++j) val[j] = src[(size_t)j * stride];
+#pragma unroll
+                for (int j = 0; j < T3D_NUM_COLUMNS; ++j) dst[(size_t)j * stride] = val[j];
+                auto F = [&](int c) { return __uint_as_float(val[c]); };
+                const uint32_t frame = val[T3D_COL_FRAME] < frame_count ? val[T3D_COL_FRAME] : frame_count - 1u;
+                const float* uv = uv_in_smem ? (s_uv + frame * 4u) : (uv_g + (size_t)frame * 4u);
+                const float pos[3] = { F(T3D_COL_POSITION), F(T3D_COL_POSITION + 1), F(T3D_COL_POSITION + 2) };
+                const float rgba[4] = { F(T3D_COL_COLOR), F(T3D_COL_COLOR + 1), F(T3D_COL_COLOR + 2), F(T3D_COL_COLOR + 3) };
+                float4 q[9];
+                expand_quad(pos, rgba, F(T3D_COL_SIZE), F(T3D_COL_ANGLE), uv[0], uv[1], uv[2], uv[3], right, up, rot_mode, [&] { return frozen_rot; }, q);
+                float4* const o = reinterpret_cast<float4*>(vtx + (size_t)(first + off) * T3D_FLOATS_PER_QUAD);
+#pragma unroll
+                for (int j = 0; j < 9; ++j) __stcs(o + j, q[j]);
+                continue;
+            }
 #pragma unroll
             for (int half = 0; half < 2; ++half)
             {
@@ -747,6 +845,82 @@ static const UpdateVariant& variant()
                 if (!strcmp(env, kVariants[i].name)) g_variant = i;
     }
     return kVariants[g_variant];
+}
+
+// ---- fused update + draw ----------------------------------------------------------------------------------
+struct FusedVariant
+{
+    const char* name;
+    int tile;
+    void (*launch)(cudaStream_t, uint32_t, const UpdateItem*, const DrawItem*, uint32_t, unsigned long long*, uint32_t, int,
+                   const FrozenRotation*);
+};
+template <int THREADS, int SUB, int MIN_BLOCKS>
+static void launch_fused(cudaStream_t s, uint32_t tiles, const UpdateItem* items, const DrawItem* ditems, uint32_t n_items,
+                         unsigned long long* status, uint32_t epoch, int rot_mode, const FrozenRotation* frozen)
+{
+    // ring + vertex staging (4 quads per thread, contiguous per warp)
+    constexpr size_t smem = 2 * (size_t)RC_COUNT * THREADS * sizeof(float4) + (size_t)THREADS * (4 * T3D_FLOATS_PER_QUAD * 4) + 128;
+    static bool configured = false;
+    if (!configured)
+    {
+        cudaFuncSetAttribute(k_update<4, THREADS, SUB, MIN_BLOCKS, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    k_update<4, THREADS, SUB, MIN_BLOCKS, true, false, true><<<tiles, THREADS, smem, s>>>(items, n_items, tiles, status, nullptr, 0u, epoch,
+                                                                                          ditems, rot_mode, frozen);
+}
+// the same without the cp.async ring: loads through registers, more warps per SM
+template <int THREADS, int SUB, int MIN_BLOCKS>
+static void launch_fused_lsu(cudaStream_t s, uint32_t tiles, const UpdateItem* items, const DrawItem* ditems, uint32_t n_items,
+                             unsigned long long* status, uint32_t epoch, int rot_mode, const FrozenRotation* frozen)
+{
+    constexpr size_t smem = (size_t)THREADS * (4 * T3D_FLOATS_PER_QUAD * 4) + 128;
+    static bool configured = false;
+    if (!configured)
+    {
+        cudaFuncSetAttribute(k_update<4, THREADS, SUB, MIN_BLOCKS, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    k_update<4, THREADS, SUB, MIN_BLOCKS, false, false, true><<<tiles, THREADS, smem, s>>>(items, n_items, tiles, status, nullptr, 0u, epoch,
+                                                                                           ditems, rot_mode, frozen);
+}
+#define T3D_FUSED(T, S, B) { "f4t" #T "s" #S "b" #B, 4 * T * S, launch_fused<T, S, B> }
+#define T3D_FUSED_LSU(T, S, B) { "g4t" #T "s" #S "b" #B, 4 * T * S, launch_fused_lsu<T, S, B> }
+static const FusedVariant kFused[] = {
+    // Measured on B200 (profiles/r1_fused_sweep.txt): none beats the two separate launches -- the fused pass carries
+    // ~1 400 non-FMA instructions per 128 particles and the vertex staging (18 KB per warp) caps an SM at 8 warps, so
+    // it is issue/latency-bound at 0.82 of the HBM peak.  Kept as an opt-in, parity-tested path (T3D_FUSED=1).
+    T3D_FUSED_LSU(256, 4, 1), T3D_FUSED_LSU(128, 8, 2), T3D_FUSED(64, 10, 2),
+};
+static const FusedVariant& fused_variant()
+{
+    static int v = -1;
+    if (v < 0)
+    {
+        v = 0;
+        if (const char* env = getenv("T3D_FUSED_VARIANT"))
+            for (int i = 0; i < (int)(sizeof(kFused) / sizeof(kFused[0])); ++i)
+                if (!strcmp(env, kFused[i].name)) v = i;
+    }
+    return kFused[v];
+}
+int fused_tile_size() { return fused_variant().tile; }
+// T3D_FUSED=1: an update of a set of emitters directly followed by the draw of the same set becomes one launch.
+bool fused_enabled()
+{
+    static int v = -1;
+    if (v < 0)
+    {
+        const char* env = getenv("T3D_FUSED");
+        v = (env && env[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+void launch_update_draw(void* stream, const UpdateItem* items, const DrawItem* ditems, uint32_t n_items, uint32_t total_tiles,
+                        unsigned long long* tile_status, uint32_t epoch, int rot_mode, const FrozenRotation* frozen)
+{
+    fused_variant().launch((cudaStream_t)stream, total_tiles, items, ditems, n_items, tile_status, epoch, rot_mode, frozen);
 }
 
 int update_tile_size() { return variant().tile; }
