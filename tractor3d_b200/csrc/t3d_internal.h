@@ -140,7 +140,7 @@ void launch_update(void* stream, const UpdateItem* items, uint32_t n_items, uint
 void launch_draw(void* stream, const DrawItem* items, uint32_t n_items, uint32_t total_tiles, int rot_mode,
                  const FrozenRotation* frozen);
 int fused_tile_size();
-bool fused_enabled();
+int fused_mode(); // 1 always, 0 never, -1 automatic
 void launch_update_draw(void* stream, const UpdateItem* items, const DrawItem* ditems, uint32_t n_items, uint32_t total_tiles,
                         unsigned long long* tile_status, uint32_t epoch, int rot_mode, const FrozenRotation* frozen);
 void launch_latch(void* stream, const DrawItem* items, uint32_t n_items, FrozenRotation* frozen);

@@ -91,6 +91,7 @@ struct PendingOp
     uint32_t emit_n;      // particles to spawn before the update (or the whole op for PHASE_EMIT)
     size_t draws_begin;   // into ctx->pending_draws, when the draws come from the host
     size_t draws_count;
+    uint32_t spawned;     // update: particles asked to spawn since the emitter's previous update (churn estimate)
     size_t offsets_begin; // into ctx->pending_offsets (ellipsoid), or SIZE_MAX for constant stride
     uint32_t draw_stride;
     bool host_draws;
@@ -210,6 +211,7 @@ struct t3d_emitter
     bool held{ false }; // has an update in ctx->held (launch deferred, see flush)
     bool last_draw_empty{ true }; // the last draw() submitted no quads (inactive or no particles)
     uint64_t emitted_total{ 0 };  // particles ever asked to spawn (upper bound of those spawned)
+    uint64_t emitted_at_update{ 0 }; // emitted_total when the previous update was queued
     // Milliseconds for which at least one particle is GUARANTEED to be alive: a particle that certainly spawned
     // starts with energy >= floor(min(energyMin, energyMax)) (PE.cpp:316) and every update takes at most
     // elapsed + 1 off it (PE.cpp:753 truncates).  While positive, isActive() of a stopped emitter needs no read-back.
@@ -798,6 +800,26 @@ static int launch_fused_frame(t3d_ctx* c)
     return T3D_OK;
 }
 
+// Should the pending updates wait for the draws that are about to be queued?  Automatic mode holds them when the
+// fused launch is expected to pay (measured on B200, profiles/r1_fused_sweep.txt):
+//  - enough particles per emitter that the frame is bound by the GPU, not by the per-emitter host work
+//    (1 024 x 4 Ki: 0.319 ms fused against 0.294 ms separate, both host-bound);
+//  - little churn: a slot that receives a moved particle costs the fused pass an extra scattered 144-byte quad
+//    (1 Mi of 14 Mi particles replaced per frame: 1.42 ms fused against 1.20 ms separate).  Deaths are not known
+//    on the host; spawns since the previous update stand in for them (equal in steady state).
+static bool hold_for_fusion(const t3d_ctx* c)
+{
+    const int mode = fused_mode();
+    if (mode >= 0) return mode == 1;
+    uint64_t particles = 0, spawned = 0;
+    for (const PendingOp& op : c->pending)
+    {
+        particles += op.e->count_ub;
+        spawned += op.spawned;
+    }
+    return particles >= (uint64_t)8192 * c->pending.size() && spawned * 32 <= particles;
+}
+
 static int launch_held(t3d_ctx* c)
 {
     if (c->held.empty()) return T3D_OK;
@@ -834,7 +856,7 @@ static int flush(t3d_ctx* c, int next_phase = PHASE_NONE)
     {
         rc = launch_held(c);
         if (rc == T3D_OK) rc = launch_spawns(c);
-        hold = rc == T3D_OK && next_phase == PHASE_DRAW && fused_enabled();
+        hold = rc == T3D_OK && next_phase == PHASE_DRAW && hold_for_fusion(c);
         if (rc == T3D_OK && !hold) rc = launch_updates(c, c->pending);
     }
     else if (c->phase == PHASE_DRAW)
@@ -1540,6 +1562,8 @@ int t3d_emitter_update(t3d_emitter* e, float elapsed_time)
     }
     if (e->count_ub > 0) e->count_exact = false; // particles may die in the kernel; the bound stays valid
     e->alive_budget_ms -= (double)elapsed_ms + 1.0;
+    op.spawned = (uint32_t)std::min<uint64_t>(e->emitted_total - e->emitted_at_update, UINT32_MAX);
+    e->emitted_at_update = e->emitted_total;
     return enqueue(c, PHASE_UPDATE, op);
 }
 

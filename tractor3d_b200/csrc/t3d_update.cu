@@ -255,9 +255,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
              uint32_t epoch, const DrawItem* __restrict__ ditems = nullptr, int rot_mode = 0,
              const FrozenRotation* __restrict__ frozen = nullptr)
 {
-    static_assert(!FUSED || V == 4, "the fused variant stages 4 quads per thread");
+    static_assert(!FUSED || !ASYNC || V == 4, "the cp.async ring moves 4 particles per thread");
+    static_assert(V * THREADS * SUB < 65535, "tile-local offsets and ranks are kept as 16-bit values");
     constexpr int kQuadBytes = T3D_FLOATS_PER_QUAD * 4;
-    constexpr int kStageWarp = 32 * 4 * kQuadBytes; // bytes of vertex staging per warp: its 128 consecutive quads
+    constexpr int kStageWarp = 32 * V * kQuadBytes; // bytes of vertex staging per warp: its 32 * V consecutive quads
     __shared__ float s_uv[FUSED ? kMaxSmemFrames * 4 : 1];
     constexpr int GROUP = V * THREADS;  // particles per sub-tile
     constexpr int TILE = GROUP * SUB;
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     // Per-thread results of phase A (decremented energies, dead particles preceding each group), parked in shared
     // memory so that phase B can be a rolled loop: unrolling it SUB times overflowed the instruction cache.
     __shared__ __align__(16) int s_en[SUB * THREADS * V];
-    __shared__ uint32_t s_base[SUB * THREADS];
+    __shared__ unsigned short s_base[SUB * THREADS]; // < TILE
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u, warp = tid >> 5;
@@ -333,10 +334,18 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             cp_async_commit();
         }
     }
-    else
+    // With one or two particles per thread the whole record fits in registers twice: both halves are requested at
+    // once and one group ahead (one exposed round trip to HBM per tile instead of two per group).
+    constexpr bool kWholeRecord = FUSED && !ASYNC && V <= 2;
+    Appearance<V> a_cur;
+    if (!ASYNC)
     {
         const uint32_t k0 = first + tid * V;
-        if (k0 < cap) m.load(particle_base(cols, bshift, k0), stride, may_rotate);
+        if (k0 < cap)
+        {
+            m.load(particle_base(cols, bshift, k0), stride, may_rotate);
+            if (kWholeRecord) a_cur.load(particle_base(cols, bshift, k0), stride, animated, FUSED);
+        }
     }
     if (first >= N)
     {
@@ -418,7 +427,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             tile_dead += v;
         }
         base[s] = before + incl[s] - cnt[s];
-        s_base[s * THREADS + tid] = base[s];
+        s_base[s * THREADS + tid] = (unsigned short)base[s];
 #pragma unroll
         for (int l = 0; l < V; ++l) s_en[(s * THREADS + tid) * V + l] = en[s][l];
     }
@@ -480,6 +489,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     const float ppf = it.percent_per_frame;
     const float dur = it.frame_duration_secs;
     const uint32_t frame_count = it.frame_count;
+    // With one or two particles per thread the whole record fits in registers twice: both halves are requested at
+    // once and one group ahead (one exposed round trip to HBM per tile instead of two per group).
 #pragma unroll 1
     for (int s = 0; s < SUB; ++s)
     {
@@ -520,6 +531,23 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             }
         }
 
+        // kWholeRecord: this group's record is already in registers; the next group's is requested now, so that it
+        // travels while this one is computed and expanded.
+        Appearance<V> a;
+        Motion<V> m_nxt;
+        Appearance<V> a_nxt;
+        if (kWholeRecord)
+        {
+            a = a_cur;
+            const uint32_t kn = k0 + GROUP;
+            if (s + 1 < SUB && kn < cap)
+            {
+                const uint32_t* nbase = particle_base(cols, bshift, kn);
+                m_nxt.load(nbase, stride, may_rotate);
+                a_nxt.load(nbase, stride, animated, FUSED);
+            }
+        }
+
         // -- motion half: PE.cpp:757-774 --
         if (ASYNC)
         {
@@ -530,7 +558,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             m.load_ring(ring, s & 1);
             if (may_rotate) m.load_rotation(gbase, stride);
         }
-        else if (s > 0)
+        else if (!kWholeRecord && s > 0)
             m.load(gbase, stride, may_rotate);
 #pragma unroll
         for (int l = 0; l < V; ++l)
@@ -588,10 +616,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 }
             }
         }
-        compiler_fence();
+        if (!kWholeRecord) compiler_fence();
 
         // -- appearance half: PE.cpp:777-819 --
-        Appearance<V> a;
         if (ASYNC)
         {
             a.load_ring(ring, s & 1, animated, FUSED);
@@ -603,7 +630,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 cp_async_commit();
             }
         }
-        else
+        else if (!kWholeRecord)
             a.load(gbase, stride, animated, FUSED);
         float col_out[4][V], size_out[V];
 #pragma unroll
@@ -717,14 +744,24 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 if (FUSED) d->cnt[0].drawn = N - D[l] - dead_l;
             }
         }
+        if (kWholeRecord)
+        {
+            m = m_nxt;
+            a_cur = a_nxt;
+        }
         compiler_fence();
     }
     // shared memory must outlive the bulk stores, and their writes must have landed before the move pass overwrites
     // the quads of the slots it fills
     if (FUSED && lane == 0)
     {
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async;" ::: "memory");
+        if (tile_dead)
+        {
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        else // nothing is overwritten afterwards: it is enough that the staging memory has been read
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 
     // ---- the moves: rank r of this tile's dead particles pulls original N-1-(tile_excl+r) into its slot.  One thread
@@ -871,27 +908,30 @@ static void launch_fused(cudaStream_t s, uint32_t tiles, const UpdateItem* items
                                                                                           ditems, rot_mode, frozen);
 }
 // the same without the cp.async ring: loads through registers, more warps per SM
-template <int THREADS, int SUB, int MIN_BLOCKS>
+template <int V, int THREADS, int SUB, int MIN_BLOCKS>
 static void launch_fused_lsu(cudaStream_t s, uint32_t tiles, const UpdateItem* items, const DrawItem* ditems, uint32_t n_items,
                              unsigned long long* status, uint32_t epoch, int rot_mode, const FrozenRotation* frozen)
 {
-    constexpr size_t smem = (size_t)THREADS * (4 * T3D_FLOATS_PER_QUAD * 4) + 128;
+    constexpr size_t smem = (size_t)THREADS * (V * T3D_FLOATS_PER_QUAD * 4) + 128;
     static bool configured = false;
     if (!configured)
     {
-        cudaFuncSetAttribute(k_update<4, THREADS, SUB, MIN_BLOCKS, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_update<V, THREADS, SUB, MIN_BLOCKS, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    k_update<4, THREADS, SUB, MIN_BLOCKS, false, false, true><<<tiles, THREADS, smem, s>>>(items, n_items, tiles, status, nullptr, 0u, epoch,
+    k_update<V, THREADS, SUB, MIN_BLOCKS, false, false, true><<<tiles, THREADS, smem, s>>>(items, n_items, tiles, status, nullptr, 0u, epoch,
                                                                                            ditems, rot_mode, frozen);
 }
 #define T3D_FUSED(T, S, B) { "f4t" #T "s" #S "b" #B, 4 * T * S, launch_fused<T, S, B> }
-#define T3D_FUSED_LSU(T, S, B) { "g4t" #T "s" #S "b" #B, 4 * T * S, launch_fused_lsu<T, S, B> }
+#define T3D_FUSED_LSU(V, T, S, B) { "g" #V "t" #T "s" #S "b" #B, V * T * S, launch_fused_lsu<V, T, S, B> }
 static const FusedVariant kFused[] = {
-    // Measured on B200 (profiles/r1_fused_sweep.txt): none beats the two separate launches -- the fused pass carries
-    // ~1 400 non-FMA instructions per 128 particles and the vertex staging (18 KB per warp) caps an SM at 8 warps, so
-    // it is issue/latency-bound at 0.82 of the HBM peak.  Kept as an opt-in, parity-tested path (T3D_FUSED=1).
-    T3D_FUSED_LSU(256, 4, 1), T3D_FUSED_LSU(128, 8, 2), T3D_FUSED(64, 10, 2),
+    // default: 2 particles per thread, whole record in registers one group ahead, 192 threads x 12 groups = 4 608-particle
+    // tiles, 2 CTAs/SM.  Measured on B200 (profiles/r1_fused_sweep.txt): 3.30 ms for 64 Mi particles (0.95 of the HBM
+    // peak on 304 B/particle) against 1.69 + 1.83 ms for the two separate launches.  The 4-particle variants (f4: with the
+    // cp.async ring, g4: without) are capped at 4-8 warps per SM by their vertex staging and lose.
+    T3D_FUSED_LSU(2, 192, 12, 2),
+    T3D_FUSED_LSU(2, 192, 8, 2), T3D_FUSED_LSU(2, 384, 6, 1), T3D_FUSED_LSU(2, 256, 8, 1), T3D_FUSED_LSU(1, 512, 8, 1),
+    T3D_FUSED_LSU(4, 256, 4, 1), T3D_FUSED_LSU(4, 128, 8, 2), T3D_FUSED(64, 10, 2),
 };
 static const FusedVariant& fused_variant()
 {
@@ -906,16 +946,17 @@ static const FusedVariant& fused_variant()
     return kFused[v];
 }
 int fused_tile_size() { return fused_variant().tile; }
-// T3D_FUSED=1: an update of a set of emitters directly followed by the draw of the same set becomes one launch.
-bool fused_enabled()
+// An update of a set of emitters directly followed by the draw of the same set can go out as one launch.
+// T3D_FUSED=1 always, T3D_FUSED=0 never, unset: when the runtime expects it to pay (see hold_for_fusion()).
+int fused_mode()
 {
-    static int v = -1;
-    if (v < 0)
+    static int v = -2;
+    if (v == -2)
     {
         const char* env = getenv("T3D_FUSED");
-        v = (env && env[0] == '1') ? 1 : 0;
+        v = !env ? -1 : (env[0] == '1' ? 1 : 0);
     }
-    return v == 1;
+    return v;
 }
 void launch_update_draw(void* stream, const UpdateItem* items, const DrawItem* ditems, uint32_t n_items, uint32_t total_tiles,
                         unsigned long long* tile_status, uint32_t epoch, int rot_mode, const FrozenRotation* frozen)
