@@ -210,7 +210,9 @@ def run_cuda(args):
     workload = args.workload or ("c3" if world == 1 else "c4")
     stream = torch.cuda.Stream()
     ctx = Context(local_rank, stream.cuda_stream)
-    emitters, per, animated_frac, wl_name = build_population(ctx, workload, rank, world, args.particles)
+    # T3D_BENCH_EMULATE_WORLD=N (experiments only): rank 0's share of an N-GPU run on one GPU
+    pop_world = int(os.environ.get("T3D_BENCH_EMULATE_WORLD", world)) if world == 1 else world
+    emitters, per, animated_frac, wl_name = build_population(ctx, workload, rank, pop_world, args.particles)
     handles = Context._handles(emitters)
     churn = workload == "c5"
     spawn_per_frame = (MI // world) // len(emitters) if churn else 0
@@ -382,7 +384,7 @@ def run_cuda(args):
             line["also"] = {"c2": quick_measure(ctx, stream, "c2", 50, torch)}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single_core(args.cpu_particles)
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -479,10 +481,26 @@ def run_reference(args):
                          "sample": f"{cores} processes x {n_particles} particles x {frames} frames of update()+draw() per step"},
         "e2e": {"value": value, "unit": "particles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
+
+
+_RESULT_OUT = None
+
+
+def emit_line(line):
+    """The ONE JSON line of the contract, written to the process's original stdout."""
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    # Libraries write banners to file descriptor 1 (NCCL prints its version there at communicator creation): keep
+    # stdout for the result line alone and send everything else to stderr.
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)

@@ -81,6 +81,7 @@ struct StagingSlot
     char* dev{ nullptr };
     size_t cap{ 0 };
     cudaEvent_t done{ nullptr };
+    cudaEvent_t uploaded{ nullptr };
     bool in_flight{ false };
 };
 
@@ -117,6 +118,9 @@ struct t3d_ctx
 
     StagingSlot staging[8];
     int staging_next{ 0 };
+    // Launch descriptors travel on a stream of their own, so that the upload for the next launch overlaps the kernel
+    // of the current one; the launching stream waits for the slot's `uploaded` event.  (T3D_COPY_STREAM=0: same stream.)
+    cudaStream_t copy_stream{ nullptr };
 
     unsigned long long* tile_status{ nullptr };
     size_t tile_status_cap{ 0 };
@@ -240,6 +244,7 @@ static int staging_acquire(t3d_ctx* c, size_t bytes, StagingSlot** out)
         s.in_flight = false;
     }
     if (!s.done) T3D_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    if (!s.uploaded) T3D_CUDA(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
     if (s.cap < bytes)
     {
         if (s.host) cudaFreeHost(s.host);
@@ -256,7 +261,15 @@ static int staging_acquire(t3d_ctx* c, size_t bytes, StagingSlot** out)
 
 static int staging_submit(t3d_ctx* c, StagingSlot* s, size_t bytes)
 {
-    T3D_CUDA(cudaMemcpyAsync(s->dev, s->host, bytes, cudaMemcpyHostToDevice, c->stream));
+    if (c->copy_stream)
+    {
+        // The slot's device buffer is free: staging_acquire waited for the last launch that read it.
+        T3D_CUDA(cudaMemcpyAsync(s->dev, s->host, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+        T3D_CUDA(cudaEventRecord(s->uploaded, c->copy_stream));
+        T3D_CUDA(cudaStreamWaitEvent(c->stream, s->uploaded, 0));
+    }
+    else
+        T3D_CUDA(cudaMemcpyAsync(s->dev, s->host, bytes, cudaMemcpyHostToDevice, c->stream));
     c->h2d_bytes += bytes;
     return T3D_OK;
 }
@@ -1120,6 +1133,11 @@ int t3d_ctx_create(int device, void* cuda_stream, t3d_ctx** out)
         return fail(T3D_ERR_CUDA, "t3d_ctx_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     memset(c->frozen_m, 0, sizeof(c->frozen_m));
+    {
+        const char* env = getenv("T3D_COPY_STREAM");
+        if (!(env && env[0] == '0') && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+            c->copy_stream = nullptr; // descriptors then travel on the launching stream
+    }
     // T3D_LAYOUT_BLOCK=2^k selects the blocked struct-of-arrays layout (measured equal to plain SoA on B200).
     if (const char* env = getenv("T3D_LAYOUT_BLOCK"))
     {
@@ -1149,7 +1167,9 @@ int t3d_ctx_destroy(t3d_ctx* c)
         if (s.host) cudaFreeHost(s.host);
         if (s.dev) cudaFree(s.dev);
         if (s.done) cudaEventDestroy(s.done);
+        if (s.uploaded) cudaEventDestroy(s.uploaded);
     }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->tile_status) cudaFree(c->tile_status);
     if (c->ticket) cudaFree(c->ticket);
     if (c->frozen_dev) cudaFree(c->frozen_dev);
