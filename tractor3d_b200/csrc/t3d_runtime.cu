@@ -778,6 +778,7 @@ static bool can_fuse(const t3d_ctx* c)
     for (size_t k = 0; k < c->held.size(); ++k)
     {
         if (c->held[k].e != c->pending[k].e) return false;
+        if (c->held[k].e->frame_count > (uint32_t)kMaxSmemFrames) return false; // the fused pass reads uv from shared memory only
         any_spin = any_spin || c->held[k].e->may_spin;
     }
     if (c->rot_mode == T3D_ROT_FROZEN && !c->frozen_latched && any_spin) return false;

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     static_assert(V * THREADS * SUB < 65535, "tile-local offsets and ranks are kept as 16-bit values");
     constexpr int kQuadBytes = T3D_FLOATS_PER_QUAD * 4;
     constexpr int kStageWarp = 32 * V * kQuadBytes; // bytes of vertex staging per warp: its 32 * V consecutive quads
-    __shared__ float s_uv[FUSED ? kMaxSmemFrames * 4 : 1];
+    __shared__ __align__(16) float s_uv[FUSED ? kMaxSmemFrames * 4 : 4];
     constexpr int GROUP = V * THREADS;  // particles per sub-tile
     constexpr int TILE = GROUP * SUB;
     constexpr int WARPS = THREADS / 32;
@@ -360,8 +360,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     // the draw side of the launch descriptor (FUSED)
     float right[3] = { 0, 0, 0 }, up[3] = { 0, 0, 0 };
     float* vtx = nullptr;
-    const float* uv_g = nullptr;
-    bool uv_in_smem = false;
     unsigned char* stage_warp = ring_bytes + (ASYNC ? 2 * (size_t)RC_COUNT * THREADS * sizeof(float4) : 0) + (size_t)warp * kStageWarp;
     Rot3 frozen_rot = {};
     if (FUSED)
@@ -375,10 +373,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             up[k] = di.up[k];
         }
         vtx = di.vtx;
-        uv_g = di.uv;
-        uv_in_smem = it.frame_count <= (uint32_t)kMaxSmemFrames;
-        if (uv_in_smem)
-            for (uint32_t q = tid; q < it.frame_count * 4u; q += THREADS) s_uv[q] = uv_g[q]; // visible after the scan's barrier
+        // the host only fuses emitters whose uv table fits (frame_count <= kMaxSmemFrames)
+        const float* uv_g = di.uv;
+        const uint32_t uv_words = (it.frame_count < (uint32_t)kMaxSmemFrames ? it.frame_count : (uint32_t)kMaxSmemFrames) * 4u;
+        for (uint32_t q = tid; q < uv_words; q += THREADS) s_uv[q] = uv_g[q]; // visible after the scan's barrier
     }
     uint32_t cnt[SUB];
 #pragma unroll
@@ -486,9 +484,31 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     const uint32_t tile_excl = certain ? 0u : s_excl; // certain: ranks below are tile-local
 
     // ---- phase B: stream the groups ----
-    const float ppf = it.percent_per_frame;
-    const float dur = it.frame_duration_secs;
-    const uint32_t frame_count = it.frame_count;
+    float ppf = it.percent_per_frame;
+    float dur = it.frame_duration_secs;
+    uint32_t frame_count = it.frame_count;
+    if (kWholeRecord)
+    {
+        // The group loop keeps a whole record of loads in flight.  A value that is still "a pending load" when the loop
+        // is entered would make its consumers inside the loop wait on the scoreboard those loads share (ptxas puts
+        // nearly all of them on one), i.e. for the record that was just requested.  Passing the per-tile constants
+        // through one ALU instruction here settles them before the loop (the operand is 0 in this launch, unknown to
+        // the compiler).
+        auto settle_f = [&](float& v) { v = __uint_as_float(__float_as_uint(v) ^ ticket_base); };
+        auto settle_u = [&](uint32_t& v) { v ^= ticket_base; };
+        settle_f(ppf);
+        settle_f(dur);
+        settle_u(frame_count);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            settle_f(right[k]);
+            settle_f(up[k]);
+        }
+        settle_f(frozen_rot.m0); settle_f(frozen_rot.m1); settle_f(frozen_rot.m2);
+        settle_f(frozen_rot.m4); settle_f(frozen_rot.m5); settle_f(frozen_rot.m6);
+        settle_f(frozen_rot.m8); settle_f(frozen_rot.m9); settle_f(frozen_rot.m10);
+    }
     // With one or two particles per thread the whole record fits in registers twice: both halves are requested at
     // once and one group ahead (one exposed round trip to HBM per tile instead of two per group).
 #pragma unroll 1
@@ -711,10 +731,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 {
                     if (!(examined[l] && alive[l])) continue; // dead: the move pass writes this quad
                     const uint32_t frame = (uint32_t)a.fr[l] < frame_count ? (uint32_t)a.fr[l] : frame_count - 1u;
-                    const float* uv = uv_in_smem ? (s_uv + frame * 4u) : (uv_g + (size_t)frame * 4u);
+                    // (always from shared memory: a global load here would share a scoreboard with the record in flight)
+                    const float4 uv = *reinterpret_cast<const float4*>(s_uv + frame * 4u);
                     const float pos[3] = { m.px[l], m.py[l], m.pz[l] };
                     const float rgba[4] = { col_out[0][l], col_out[1][l], col_out[2][l], col_out[3][l] };
-                    expand_quad(pos, rgba, size_out[l], m.ang[l], uv[0], uv[1], uv[2], uv[3], right, up, rot_mode, [&] { return frozen_rot; },
+                    expand_quad(pos, rgba, size_out[l], m.ang[l], uv.x, uv.y, uv.z, uv.w, right, up, rot_mode, [&] { return frozen_rot; },
                                 reinterpret_cast<float4*>(stage_warp + (lane * V + l) * kQuadBytes));
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -790,11 +811,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 for (int j = 0; j < T3D_NUM_COLUMNS; ++j) dst[(size_t)j * stride] = val[j];
                 auto F = [&](int c) { return __uint_as_float(val[c]); };
                 const uint32_t frame = val[T3D_COL_FRAME] < frame_count ? val[T3D_COL_FRAME] : frame_count - 1u;
-                const float* uv = uv_in_smem ? (s_uv + frame * 4u) : (uv_g + (size_t)frame * 4u);
+                const float4 uv = *reinterpret_cast<const float4*>(s_uv + frame * 4u);
                 const float pos[3] = { F(T3D_COL_POSITION), F(T3D_COL_POSITION + 1), F(T3D_COL_POSITION + 2) };
                 const float rgba[4] = { F(T3D_COL_COLOR), F(T3D_COL_COLOR + 1), F(T3D_COL_COLOR + 2), F(T3D_COL_COLOR + 3) };
                 float4 q[9];
-                expand_quad(pos, rgba, F(T3D_COL_SIZE), F(T3D_COL_ANGLE), uv[0], uv[1], uv[2], uv[3], right, up, rot_mode, [&] { return frozen_rot; }, q);
+                expand_quad(pos, rgba, F(T3D_COL_SIZE), F(T3D_COL_ANGLE), uv.x, uv.y, uv.z, uv.w, right, up, rot_mode, [&] { return frozen_rot; }, q);
                 float4* const o = reinterpret_cast<float4*>(vtx + (size_t)(first + off) * T3D_FLOATS_PER_QUAD);
 #pragma unroll
                 for (int j = 0; j < 9; ++j) __stcs(o + j, q[j]);
