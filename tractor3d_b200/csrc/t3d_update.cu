@@ -787,21 +787,47 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 
     // ---- the moves: rank r of this tile's dead particles pulls original N-1-(tile_excl+r) into its slot.  One thread
     // per move (consecutive lanes read consecutive sources, contiguous at the end of the live range, so each column
-    // is a coalesced read); the 34 words are fetched in two batches of 17 independent loads before they are stored --
-    // the moves are latency-bound, not bandwidth-bound.  Sources lie beyond every examined slot: nothing read here is
-    // written by anyone.
+    // is a coalesced read).  The moves are latency-bound, not bandwidth-bound: a thread requests the 34 words of two
+    // moves (68 independent loads) before it stores any, so a tile with up to 2 x THREADS dead particles pays one round
+    // trip.  Sources lie beyond every examined slot: nothing read here is written by anyone.
     if (tile_dead)
     {
         __syncthreads(); // s_move complete; this CTA's stores to the dead slots are ordered before the moves
         const uint32_t src_last = N - 1u - s_excl; // the emitter-wide prefix, visible to all after the barrier
-        constexpr int BATCH = T3D_NUM_COLUMNS / 2;
-        for (uint32_t r = tid; r < tile_dead; r += THREADS)
+        if (!FUSED)
+        {
+            constexpr int PER = 2;
+            for (uint32_t r0 = tid; r0 < tile_dead; r0 += PER * THREADS)
+            {
+                uint32_t val[PER][T3D_NUM_COLUMNS];
+                uint32_t* dst[PER];
+#pragma unroll
+                for (int p = 0; p < PER; ++p)
+                {
+                    const uint32_t r = r0 + p * THREADS;
+                    const unsigned short off = r < tile_dead ? s_move[r] : kNoMove;
+                    dst[p] = nullptr;
+                    if (off == kNoMove) continue;
+                    dst[p] = particle_base(cols, bshift, first + off);
+                    const uint32_t* const src = particle_base(cols, bshift, src_last - r);
+#pragma unroll
+                    for (int j = 0; j < T3D_NUM_COLUMNS; ++j) val[p][j] = src[(size_t)j * stride];
+                }
+#pragma unroll
+                for (int p = 0; p < PER; ++p)
+                {
+                    if (!dst[p]) continue;
+#pragma unroll
+                    for (int j = 0; j < T3D_NUM_COLUMNS; ++j) dst[p][(size_t)j * stride] = val[p][j];
+                }
+            }
+        }
+        for (uint32_t r = tid; FUSED && r < tile_dead; r += THREADS)
         {
             const unsigned short off = s_move[r];
             if (off == kNoMove) continue;
             uint32_t* const dst = particle_base(cols, bshift, first + off);
             const uint32_t* const src = particle_base(cols, bshift, src_last - r);
-            if (FUSED)
             {
                 // the whole record is needed at once: the moved particle is drawn as it stands (PE.cpp:866-882)
                 uint32_t val[T3D_NUM_COLUMNS];
@@ -819,16 +845,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 float4* const o = reinterpret_cast<float4*>(vtx + (size_t)(first + off) * T3D_FLOATS_PER_QUAD);
 #pragma unroll
                 for (int j = 0; j < 9; ++j) __stcs(o + j, q[j]);
-                continue;
-            }
-#pragma unroll
-            for (int half = 0; half < 2; ++half)
-            {
-                uint32_t val[BATCH];
-#pragma unroll
-                for (int j = 0; j < BATCH; ++j) val[j] = src[(size_t)(half * BATCH + j) * stride];
-#pragma unroll
-                for (int j = 0; j < BATCH; ++j) dst[(size_t)(half * BATCH + j) * stride] = val[j];
             }
         }
     }
