@@ -39,14 +39,16 @@ import sys
 import numpy as np
 from tractor3d_b200 import abi, presets
 from tractor3d_b200.emitter import Context, ParticleEmitter
-n_emitters, per = int(sys.argv[1]), int(sys.argv[2])
+n_emitters, per, emit_per_frame = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 ctx = Context(0)
 p, sprite = presets.fire()
-p.particle_count_max = per
+p.particle_count_max = per + 6 * emit_per_frame
 p.energy_min, p.energy_max = 1.0e5, 2.0e5
 es = [ParticleEmitter.create(ctx, p, sprite, (abi.RNG_DEVICE, 5 + k)) for k in range(n_emitters)]
 ctx.batch_emit_once(es, [per] * n_emitters)
 for _ in range(6):
+    if emit_per_frame:
+        ctx.batch_emit_once(es, [emit_per_frame] * n_emitters)
     ctx.batch_update(es, 16.0)
     ctx.batch_draw(es)
 ctx.sync()
@@ -54,13 +56,13 @@ print("FUSED_LAUNCHES", ctx.kernel_time(3)[1], "SEPARATE", ctx.kernel_time(1)[1]
 """
 
 
-def _probe(fused, n_emitters, per):
+def _probe(fused, n_emitters, per, emit_per_frame=0):
     e = dict(os.environ)
     e.pop("T3D_FUSED", None)
     if fused is not None:
         e["T3D_FUSED"] = fused
-    res = subprocess.run([sys.executable, "-c", FUSED_PROBE, str(n_emitters), str(per)], env=e, capture_output=True, text=True,
-                         timeout=300, cwd=ROOT)
+    res = subprocess.run([sys.executable, "-c", FUSED_PROBE, str(n_emitters), str(per), str(emit_per_frame)], env=e,
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     line = [l for l in res.stdout.splitlines() if l.startswith("FUSED_LAUNCHES")][0].split()
     return int(line[1]), int(line[3]), int(line[4])
@@ -68,13 +70,15 @@ def _probe(fused, n_emitters, per):
 
 def test_fused_launch_policy():
     """update(set) directly followed by draw(same set): one launch with T3D_FUSED=1, two with T3D_FUSED=0; left alone,
-    the runtime fuses large stationary populations and keeps small ones (host-bound) on the two-launch path."""
+    the runtime fuses unless many particles are being replaced per frame (spawns stand in for deaths)."""
     # (the very first frame stays apart: the rotation latch has to look at the updated angles before the draw, SB.cpp:339)
     f, u, d = _probe("1", 3, 1000)
     assert f >= 5 and u == 6 - f and d == 6 - f, (f, u, d)
     f, u, d = _probe("0", 3, 1000)
     assert f == 0 and u == 6 and d == 6, (f, u, d)
     f, u, d = _probe(None, 3, 1000)
+    assert f >= 5 and u == 6 - f and d == 6 - f, (f, u, d)
+    f, u, d = _probe(None, 3, 1000, emit_per_frame=200)   # 200 of ~1 000-2 000 replaced per frame: high churn
     assert f == 0 and u == 6 and d == 6, (f, u, d)
-    f, u, d = _probe(None, 2, 40000)
+    f, u, d = _probe(None, 3, 20000, emit_per_frame=100)  # 100 of 20 000: low churn
     assert f >= 5 and u == 6 - f and d == 6 - f, (f, u, d)

@@ -247,13 +247,22 @@ static int staging_acquire(t3d_ctx* c, size_t bytes, StagingSlot** out)
     if (!s.uploaded) T3D_CUDA(cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
     if (s.cap < bytes)
     {
-        if (s.host) cudaFreeHost(s.host);
-        if (s.dev) cudaFree(s.dev);
-        s.host = s.dev = nullptr;
-        size_t cap = std::max<size_t>(bytes + bytes / 2, 1 << 16);
-        T3D_CUDA(cudaMallocHost((void**)&s.host, cap));
-        T3D_CUDA(cudaMalloc((void**)&s.dev, cap));
-        s.cap = cap;
+        // All slots grow together (one pause now instead of one per slot over the next frames): wait for the
+        // launches that still read them, then reallocate the ring.
+        T3D_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->copy_stream) T3D_CUDA(cudaStreamSynchronize(c->copy_stream));
+        const size_t cap = std::max<size_t>(bytes + bytes / 2, 1 << 16);
+        for (StagingSlot& o : c->staging)
+        {
+            if (o.host) cudaFreeHost(o.host);
+            if (o.dev) cudaFree(o.dev);
+            o.host = o.dev = nullptr;
+            o.cap = 0;
+            o.in_flight = false;
+            T3D_CUDA(cudaMallocHost((void**)&o.host, cap));
+            T3D_CUDA(cudaMalloc((void**)&o.dev, cap));
+            o.cap = cap;
+        }
     }
     *out = &s;
     return T3D_OK;
@@ -814,13 +823,11 @@ static int launch_fused_frame(t3d_ctx* c)
     return T3D_OK;
 }
 
-// Should the pending updates wait for the draws that are about to be queued?  Automatic mode holds them when the
-// fused launch is expected to pay (measured on B200, profiles/r1_fused_sweep.txt):
-//  - enough particles per emitter that the frame is bound by the GPU, not by the per-emitter host work
-//    (1 024 x 4 Ki: 0.319 ms fused against 0.294 ms separate, both host-bound);
-//  - little churn: a slot that receives a moved particle costs the fused pass an extra scattered 144-byte quad
-//    (1 Mi of 14 Mi particles replaced per frame: 1.42 ms fused against 1.20 ms separate).  Deaths are not known
-//    on the host; spawns since the previous update stand in for them (equal in steady state).
+// Should the pending updates wait for the draws that are about to be queued?  Automatic mode holds them unless the
+// churn is high: a slot that receives a moved particle costs the fused pass an extra scattered 144-byte quad, and
+// with 1 Mi of 14 Mi particles replaced per frame the fused frame takes 1.42 ms against 1.20 ms for two launches
+// (B200, profiles/r1_fused_sweep.txt).  Deaths are not known on the host; the particles spawned since the previous
+// update stand in for them (equal in steady state).
 static bool hold_for_fusion(const t3d_ctx* c)
 {
     const int mode = fused_mode();
@@ -831,7 +838,7 @@ static bool hold_for_fusion(const t3d_ctx* c)
         particles += op.e->count_ub;
         spawned += op.spawned;
     }
-    return particles >= (uint64_t)8192 * c->pending.size() && spawned * 32 <= particles;
+    return spawned * 32 <= particles;
 }
 
 static int launch_held(t3d_ctx* c)
