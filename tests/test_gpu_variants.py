@@ -18,6 +18,7 @@ CASES = [
     {"T3D_LAYOUT_BLOCK": "512"},
     {"T3D_LAYOUT_BLOCK": "256", "T3D_UPDATE_VARIANT": "v2t256s4b4"},
     {"T3D_DRAW_VARIANT": "lsu"},
+    {"T3D_FUSED": "0"},
     {"T3D_FUSED": "1"},
     {"T3D_FUSED": "1", "T3D_FUSED_VARIANT": "f4t64s10b2"},
     {"T3D_FUSED": "1", "T3D_FUSED_VARIANT": "g4t128s8b2", "T3D_LAYOUT_BLOCK": "512"},
@@ -82,3 +83,14 @@ def test_fused_launch_policy():
     assert f == 0 and u == 6 and d == 6, (f, u, d)
     f, u, d = _probe(None, 3, 20000, emit_per_frame=100)  # 100 of 20 000: low churn
     assert f >= 5 and u == 6 - f and d == 6 - f, (f, u, d)
+
+
+def test_fuzz_with_forced_fusion():
+    """The randomised API sequences again with every eligible update+draw pair fused (the emitters there churn too much
+    for the automatic policy to pick the fused launch often)."""
+    e = dict(os.environ)
+    e["T3D_FUSED"] = "1"
+    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_fuzz.py"), os.path.join(ROOT, "tests", "test_gpu_facade.py"),
+           "-x", "-q"]
+    res = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
