@@ -214,6 +214,42 @@ def test_multi_tile_update_and_removal_order(gpu, n):
     assert np.array_equal(eg.vertices().view(np.uint32), eo.vertices().view(np.uint32))
 
 
+@pytest.mark.parametrize("n,energy", [(4607, (20.0, 400.0)), (4609, (20.0, 400.0)), (9216, (20.0, 120.0)), (200_003, (20.0, 400.0)),
+                                      (50_001, (1.0e5, 2.0e5))])
+def test_multi_tile_update_draw_frames(gpu, n, energy):
+    # The game loop's update() + draw() over an emitter of many tiles, with particles dying every frame: this is the
+    # sequence the runtime sends out as ONE fused launch (unless T3D_FUSED=0), so the vertices of every frame -- those of
+    # the particles moved into dead slots included -- and the state must match the sequential reference.
+    import os
+    p, sprite = presets.headline_64m(capacity=n + 5)
+    p.energy_min, p.energy_max = energy
+    # started, one particle per second: isActive() then needs no live count (nothing splits the frame) and the 14 frames
+    # below end before the first emission is due
+    p.emission_rate = 1
+    O = H.oracle(fresh=True)
+    eo = O.emitter(p); eo.set_sprite_frame_coords(*sprite)
+    eg = gpu.emitter(p); eg.set_sprite_frame_coords(*sprite)
+    cols = _big_population(n, seed=n + 7, energy=energy)
+    eo.set_state(cols); eg.pe.upload_state(cols)
+    eo.start(); eg.start()
+    fused0 = gpu.ctx.kernel_time(3)[1]
+    frames = 0
+    for f in range(14):
+        eo.update(S.DT); eo.draw()
+        eg.update(S.DT); eg.draw()
+        frames += 1
+        vo, vg = eo.vertices(), eg.vertices()
+        assert vo.shape == vg.shape, f"frame {f}"
+        assert np.array_equal(vg.view(np.uint32), vo.view(np.uint32)), f"frame {f}"
+        if f % 3 == 2:
+            assert eg.count() == eo.count(), f"frame {f}"
+            assert np.array_equal(eg.state(), eo.state()), f"frame {f}"
+    assert eg.count() == eo.count()
+    if os.environ.get("T3D_FUSED") != "0":
+        # all frames but the first two (the upload counts as churn; the rotation latch needs the first drawn frame apart)
+        assert gpu.ctx.kernel_time(3)[1] - fused0 >= frames - 2
+
+
 def test_batch_of_mixed_emitters_one_launch_per_phase():
     # BASELINE configs[1] in miniature: many independent emitters with mixed fire/smoke/explosion parameter sets,
     # updated and drawn through the batch calls; every emitter must match its own oracle twin.

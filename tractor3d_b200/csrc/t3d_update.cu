@@ -1,9 +1,11 @@
-// t3d_update.cu -- the fused update + dead-particle removal kernel (replaces the per-particle loop of
-// ParticleEmitter::update, PE.cpp:750-831 of the reference).
+// t3d_update.cu -- the update + dead-particle removal kernel (replaces the per-particle loop of
+// ParticleEmitter::update, PE.cpp:750-831 of the reference) and its FUSED form, which also expands the frame's
+// billboard quads (ParticleEmitter::draw + SpriteBatch::draw, PE.cpp:866-882, SB.cpp:292-363) in the same pass.
 //
 // One thread owns V consecutive particles of one emitter and reads/writes every column with one V x 32-bit
 // access, so a warp touches 32 x V x 4 contiguous bytes per column per instruction.  The kernel is a pure
-// HBM stream: 144 B per particle (160 B with sprite animation, +28 B with axis rotation), no reuse.
+// HBM stream: 144 B per particle (160 B with sprite animation, +28 B with axis rotation), no reuse; the fused
+// form adds the 144 B of vertices and saves the draw kernel's 40-byte re-read.
 //
 // removal.  The reference walks i = 0.. and, when particle i is dead, copies the LAST live particle into
 // slot i, shrinks the count and moves on WITHOUT examining the particle it just moved (PE.cpp:821-830 and
@@ -15,8 +17,9 @@
 //     new count                     =    N - D(K), K = number of examined originals
 // Sources (>= new count, never examined, never written) and destinations (< K) are disjoint, so the fill is
 // race-free in place.  D(k) is one exclusive scan: within a tile by warp shuffles, across the tiles of an
-// emitter by decoupled look-back over per-tile status words (tile ids are handed out by an atomic ticket,
-// so every predecessor of a running tile is itself running or finished).
+// emitter by decoupled look-back over per-tile status words.  Tile order = block order (a tile only ever waits
+// for tiles with a smaller block index, which were dispatched before it); T3D_UPDATE_TICKET=1 hands the ids out
+// with an atomic ticket instead.
 //
 // Numerics: --fmad=false, reference evaluation order (see t3d_kernels.cu).
 #include <cuda_runtime.h>
