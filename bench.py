@@ -108,6 +108,11 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------------
 # workloads
 # --------------------------------------------------------------------------------------------------
+# c5 (churn) knobs; --churn-spawn / --churn-energy change them for experiments
+CHURN_SPAWN = MI
+CHURN_ENERGY = (50.0, 400.0)
+
+
 def build_population(ctx, workload, rank, world, particles):
     """Creates this rank's emitters and fills them.  Returns (emitters, per_emitter_particles, animated_fraction, name)."""
     from tractor3d_b200 import abi, presets, sharding
@@ -142,10 +147,11 @@ def build_population(ctx, workload, rank, world, particles):
         n_em, cap = 8, (particles or 64 * MI) // 8
         for k in range(n_em):
             p, sprite = presets.headline_64m(capacity=cap)
-            p.energy_min, p.energy_max = 50.0, 400.0
+            p.energy_min, p.energy_max = CHURN_ENERGY
             e = ParticleEmitter.create(ctx, p, sprite, (abi.RNG_DEVICE, 77 + rank * n_em + k))
             emitters.append(e)
-        name = f"c5: {n_em} emitters/GPU, {MI // world} particles spawned per frame per GPU, energies 50..400 ms"
+        name = (f"c5: {n_em} emitters/GPU, {CHURN_SPAWN // world} particles spawned per frame per GPU, "
+                f"energies {CHURN_ENERGY[0]:g}..{CHURN_ENERGY[1]:g} ms")
         return emitters, cap, 1.0, name
     raise SystemExit(f"unknown workload {workload}")
 
@@ -215,7 +221,7 @@ def run_cuda(args):
     emitters, per, animated_frac, wl_name = build_population(ctx, workload, rank, pop_world, args.particles)
     handles = Context._handles(emitters)
     churn = workload == "c5"
-    spawn_per_frame = (MI // world) // len(emitters) if churn else 0
+    spawn_per_frame = (CHURN_SPAWN // world) // len(emitters) if churn else 0
 
     def frame():
         if churn:
@@ -511,8 +517,15 @@ def main():
     ap.add_argument("--cpu-particles", type=int, default=2 * MI, help="population of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the extra c2 measurement")
+    ap.add_argument("--churn-spawn", type=int, default=None, help="c5: particles spawned per frame (all GPUs)")
+    ap.add_argument("--churn-energy", default=None, help="c5: energy range in ms, e.g. 500,2000")
     ap.add_argument("--vertices-to-host", action="store_true", help="also time frames with the vertex stream copied to pinned host memory")
     args = ap.parse_args()
+    global CHURN_SPAWN, CHURN_ENERGY
+    if args.churn_spawn:
+        CHURN_SPAWN = args.churn_spawn
+    if args.churn_energy:
+        CHURN_ENERGY = tuple(float(x) for x in args.churn_energy.split(","))
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 3
         args.warmup = args.warmup if args.warmup is not None else 1

@@ -250,6 +250,47 @@ def test_multi_tile_update_draw_frames(gpu, n, energy):
         assert gpu.ctx.kernel_time(3)[1] - fused0 >= frames - 2
 
 
+def test_churn_at_scale_matches_oracle():
+    # Several emitters, 20 000 particles spawned per emitter per frame by the device generator, update + draw every frame
+    # through the batch calls, until the launch is wider than one wave of CTAs (4 x 400 K particles); live counts are read
+    # back only every 10 frames, so the asynchronous count feedback sizes the grids in between.  Caught a race between the
+    # initialisation of the move list and its writers in tiles that skip the look-back barrier (4 particles lost now and then).
+    from gpu_adapter import GpuLib
+    from tractor3d_b200.emitter import Context
+    K, spawn, frames = 4, 20000, 40
+    O = H.oracle(fresh=True)
+    lib = GpuLib(rng_mode=abi.RNG_DEVICE, seed=0)
+    try:
+        eos, egs = [], []
+        for k in range(K):
+            p, sprite = presets.headline_64m(capacity=spawn * 64)
+            p.energy_min, p.energy_max = 100.0, 600.0
+            eo = O.emitter(p); eo.set_sprite_frame_coords(*sprite)
+            O.emitter_set_device_rng(eo.h, 1, 100 + k)
+            eg = lib.emitter(p); eg.set_sprite_frame_coords(*sprite)
+            eg.pe.set_rng(abi.RNG_DEVICE, 100 + k)
+            eos.append(eo); egs.append(eg)
+        pes = [e.pe for e in egs]
+        h = Context._handles(pes)
+        for f in range(frames):
+            for eo in eos:
+                eo.emit_once(spawn)
+            for eo in eos:
+                eo.update(S.DT)
+            for eo in eos:
+                eo.draw()
+            lib.ctx.batch_emit_once(pes, [spawn] * K, h)
+            lib.ctx.batch_update(pes, S.DT, h)
+            lib.ctx.batch_draw(pes, h)
+            if f % 10 == 9:
+                assert list(map(int, lib.ctx.batch_counts(pes, h))) == [eo.count() for eo in eos], f"frame {f}"
+        for k in range(K):
+            assert np.array_equal(egs[k].state(), eos[k].state()), k
+            assert np.array_equal(egs[k].vertices().view(np.uint32), eos[k].vertices().view(np.uint32)), k
+    finally:
+        lib.close()
+
+
 def test_batch_of_mixed_emitters_one_launch_per_phase():
     # BASELINE configs[1] in miniature: many independent emitters with mixed fire/smoke/explosion parameter sets,
     # updated and drawn through the batch calls; every emitter must match its own oracle twin.

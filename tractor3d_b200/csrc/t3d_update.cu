@@ -433,7 +433,15 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         for (int l = 0; l < V; ++l) s_en[(s * THREADS + tid) * V + l] = en[s][l];
     }
 
-    for (uint32_t r = tid; r < tile_dead; r += THREADS) s_move[r] = kNoMove;
+    // A tile in the first half of the emitter needs no prefix to know that every slot of it is examined:
+    // D(k) <= k, so k + D(k) <= 2k < N.  Its warps start streaming at once; the prefix (resolved by warp 0 below,
+    // which then joins them) is only needed for the sources of the moves, after the barrier at the end.
+    const bool certain = 2ull * ((unsigned long long)first + TILE) <= (unsigned long long)N;
+    // Ranks whose dead particle turns out not to be examined (or to be the last one) keep kNoMove.  Only an uncertain
+    // tile can have such ranks, and only there a barrier separates this initialisation from the writes of phase B:
+    // in a certain tile every rank is written in phase B, and initialising it here would race with that write.
+    if (!certain)
+        for (uint32_t r = tid; r < tile_dead; r += THREADS) s_move[r] = kNoMove;
 
     // ---- decoupled look-back over the preceding tiles of this emitter ----
     const unsigned long long tag = (unsigned long long)epoch << 34;
@@ -479,10 +487,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             s_excl = excl;
         }
     }
-    // A tile in the first half of the emitter needs no prefix to know that every slot of it is examined:
-    // D(k) <= k, so k + D(k) <= 2k < N.  Its warps start streaming at once; the prefix (resolved by warp 0 above,
-    // which then joins them) is only needed for the sources of the moves, after the barrier at the end.
-    const bool certain = 2ull * ((unsigned long long)first + TILE) <= (unsigned long long)N;
     if (!certain) __syncthreads();
     const uint32_t tile_excl = certain ? 0u : s_excl; // certain: ranks below are tile-local
 
@@ -825,27 +829,38 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 }
             }
         }
-        for (uint32_t r = tid; FUSED && r < tile_dead; r += THREADS)
+        // FUSED: the same two moves per thread; the moved particle is also drawn, as it stands (PE.cpp:866-882)
+        for (uint32_t r0 = tid; FUSED && r0 < tile_dead; r0 += 2 * THREADS)
         {
-            const unsigned short off = s_move[r];
-            if (off == kNoMove) continue;
-            uint32_t* const dst = particle_base(cols, bshift, first + off);
-            const uint32_t* const src = particle_base(cols, bshift, src_last - r);
+            uint32_t val[2][T3D_NUM_COLUMNS];
+            uint32_t slot[2];
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
             {
-                // the whole record is needed at once: the moved particle is drawn as it stands (PE.cpp:866-882)
-                uint32_t val[T3D_NUM_COLUMNS];
+                const uint32_t r = r0 + p * THREADS;
+                const unsigned short off = r < tile_dead ? s_move[r] : kNoMove;
+                slot[p] = 0xffffffffu;
+                if (off == kNoMove) continue;
+                slot[p] = first + off;
+                const uint32_t* const src = particle_base(cols, bshift, src_last - r);
 #pragma unroll
-                for (int j = 0; j < T3D_NUM_COLUMNS; ++j) val[j] = src[(size_t)j * stride];
+                for (int j = 0; j < T3D_NUM_COLUMNS; ++j) val[p][j] = src[(size_t)j * stride];
+            }
 #pragma unroll
-                for (int j = 0; j < T3D_NUM_COLUMNS; ++j) dst[(size_t)j * stride] = val[j];
-                auto F = [&](int c) { return __uint_as_float(val[c]); };
-                const uint32_t frame = val[T3D_COL_FRAME] < frame_count ? val[T3D_COL_FRAME] : frame_count - 1u;
+            for (int p = 0; p < 2; ++p)
+            {
+                if (slot[p] == 0xffffffffu) continue;
+                uint32_t* const dst = particle_base(cols, bshift, slot[p]);
+#pragma unroll
+                for (int j = 0; j < T3D_NUM_COLUMNS; ++j) dst[(size_t)j * stride] = val[p][j];
+                auto F = [&](int c) { return __uint_as_float(val[p][c]); };
+                const uint32_t frame = val[p][T3D_COL_FRAME] < frame_count ? val[p][T3D_COL_FRAME] : frame_count - 1u;
                 const float4 uv = *reinterpret_cast<const float4*>(s_uv + frame * 4u);
                 const float pos[3] = { F(T3D_COL_POSITION), F(T3D_COL_POSITION + 1), F(T3D_COL_POSITION + 2) };
                 const float rgba[4] = { F(T3D_COL_COLOR), F(T3D_COL_COLOR + 1), F(T3D_COL_COLOR + 2), F(T3D_COL_COLOR + 3) };
                 float4 q[9];
                 expand_quad(pos, rgba, F(T3D_COL_SIZE), F(T3D_COL_ANGLE), uv.x, uv.y, uv.z, uv.w, right, up, rot_mode, [&] { return frozen_rot; }, q);
-                float4* const o = reinterpret_cast<float4*>(vtx + (size_t)(first + off) * T3D_FLOATS_PER_QUAD);
+                float4* const o = reinterpret_cast<float4*>(vtx + (size_t)slot[p] * T3D_FLOATS_PER_QUAD);
 #pragma unroll
                 for (int j = 0; j < 9; ++j) __stcs(o + j, q[j]);
             }
