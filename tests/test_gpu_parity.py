@@ -215,7 +215,7 @@ def test_multi_tile_update_and_removal_order(gpu, n):
 
 
 @pytest.mark.parametrize("n,energy", [(4607, (20.0, 400.0)), (4609, (20.0, 400.0)), (9216, (20.0, 120.0)), (200_003, (20.0, 400.0)),
-                                      (50_001, (1.0e5, 2.0e5))])
+                                      (50_001, (1.0e5, 2.0e5)), (1_500_003, (20.0, 300.0))])  # the last: wider than one wave of CTAs
 def test_multi_tile_update_draw_frames(gpu, n, energy):
     # The game loop's update() + draw() over an emitter of many tiles, with particles dying every frame: this is the
     # sequence the runtime sends out as ONE fused launch (unless T3D_FUSED=0), so the vertices of every frame -- those of

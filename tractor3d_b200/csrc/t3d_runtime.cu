@@ -823,11 +823,12 @@ static int launch_fused_frame(t3d_ctx* c)
     return T3D_OK;
 }
 
-// Should the pending updates wait for the draws that are about to be queued?  Automatic mode holds them unless the
-// churn is high: a slot that receives a moved particle costs the fused pass an extra scattered 144-byte quad, and
-// with 1 Mi of 14 Mi particles replaced per frame the fused frame takes 1.42 ms against 1.20 ms for two launches
-// (B200, profiles/r1_fused_sweep.txt).  Deaths are not known on the host; the particles spawned since the previous
-// update stand in for them (equal in steady state).
+// Should the pending updates wait for the draws that are about to be queued?  Automatic mode holds them while the
+// churn is low.  A slot that receives a moved particle costs the fused pass an extra scattered 144-byte quad on top of the
+// move, and its tiles drain their bulk stores before the move pass; measured on B200 with 38 M live particles
+// (profiles/r1_churn_crossover.txt) the fused frame is 7.7 % faster with no particle replaced per frame, 2.9 % faster at
+// 0.17 %, 1.8 % slower at 0.34 %, 8-12 % slower at 0.7-2.7 %.  Deaths are not known on the host; the particles spawned
+// since the previous update stand in for them (equal in steady state).
 static bool hold_for_fusion(const t3d_ctx* c)
 {
     const int mode = fused_mode();
@@ -838,7 +839,7 @@ static bool hold_for_fusion(const t3d_ctx* c)
         particles += op.e->count_ub;
         spawned += op.spawned;
     }
-    return spawned * 32 <= particles;
+    return spawned * 400 <= particles; // <= 0.25 % replaced per frame
 }
 
 static int launch_held(t3d_ctx* c)
