@@ -42,7 +42,9 @@ typedef enum t3d_status {
     T3D_ERR_CAPACITY = 3,     /* growth beyond the capacity fixed at create (PE.h:237 rewrites the field only) */
     T3D_ERR_RNG_UNDERFLOW = 4,/* T3D_RNG_STREAM: not enough recorded draws were fed for this emit */
     T3D_ERR_IO = 5,           /* .particle file missing or malformed (PE.cpp:79-83, 94-115) */
-    T3D_ERR_NO_NODE = 6       /* emitOnce/draw before a node world matrix was supplied (PE.cpp:289, 858) */
+    T3D_ERR_NO_NODE = 6,      /* emitOnce/draw before a node world matrix was supplied (PE.cpp:289, 858) */
+    T3D_ERR_INTERNAL = 7      /* a kernel found its grid too small for the live count it read: the host's upper bound was
+                                 wrong (a bug in this library); the context refuses further work instead of dropping particles */
 } t3d_status;
 
 typedef struct t3d_ctx t3d_ctx;         /* one per GPU */

@@ -94,3 +94,30 @@ def test_fuzz_with_forced_fusion():
            "-x", "-q"]
     res = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+
+
+FAULT_PROBE = """
+from tractor3d_b200 import abi, presets
+from tractor3d_b200.emitter import Context, ParticleEmitter, T3DError
+ctx = Context(0)
+p, sprite = presets.headline_64m(capacity=30000)
+e = ParticleEmitter.create(ctx, p, sprite, (abi.RNG_DEVICE, 9))
+e.emitOnce(20000)
+e.update(16.0)
+try:
+    n = e.getParticlesCount()
+    print("NO_FAULT", n)
+except T3DError as err:
+    print("FAULT", err.code, str(err)[:120])
+"""
+
+
+def test_a_grid_smaller_than_the_live_count_is_reported_not_ignored():
+    """The kernels check that the tiles the host launched cover the live count they read; with the test hook that drops
+    the last tile of every emitter, the next call that talks to the device must fail with T3D_ERR_INTERNAL."""
+    for shrink, expect in (("1", "FAULT 7"), ("0", "NO_FAULT 20000")):
+        e = dict(os.environ)
+        e["T3D_DEBUG_SHRINK_GRID"] = shrink
+        res = subprocess.run([sys.executable, "-c", FAULT_PROBE], env=e, capture_output=True, text=True, timeout=300, cwd=ROOT)
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+        assert expect in res.stdout, res.stdout[-500:]

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libt3d_particles.so")
 
 # t3d_status
-OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_RNG_UNDERFLOW, ERR_IO, ERR_NO_NODE = range(7)
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_RNG_UNDERFLOW, ERR_IO, ERR_NO_NODE, ERR_INTERNAL = range(8)
 # blend modes (reference ParticleEmitter.h:157-163)
 BLEND_NONE, BLEND_ALPHA, BLEND_ADDITIVE, BLEND_MULTIPLIED = range(4)
 # draw sources

@@ -94,7 +94,8 @@ struct UpdateItem
     uint32_t frame_count;
     float percent_per_frame;
     float frame_duration_secs;
-    uint32_t pad[2];
+    uint32_t n_tiles;     // tiles of this launch that belong to the emitter (the kernel checks that they cover the live count)
+    uint32_t pad;
 };
 
 struct SpawnItem
@@ -123,6 +124,8 @@ struct DrawItem
     uint32_t frame_count;
     float right[3];
     float up[3];
+    uint32_t n_tiles;     // as in UpdateItem
+    uint32_t pad;
 };
 
 // Process-wide billboard rotation of the reference (SB.cpp:339), kept on the device.
@@ -135,14 +138,17 @@ struct FrozenRotation
 
 // ---- launch wrappers (t3d_kernels.cu) ----
 void launch_spawn(void* stream, const SpawnItem* items, uint32_t n_items, uint32_t total_tiles);
+// `fault`: device word the kernels OR into when a grid does not cover the live count it finds (kFaultUpdateGrid ...).
+constexpr uint32_t kFaultUpdateGrid = 1u, kFaultDrawGrid = 2u;
 void launch_update(void* stream, const UpdateItem* items, uint32_t n_items, uint32_t total_tiles,
-                   unsigned long long* tile_status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch);
+                   unsigned long long* tile_status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch, uint32_t* fault);
 void launch_draw(void* stream, const DrawItem* items, uint32_t n_items, uint32_t total_tiles, int rot_mode,
-                 const FrozenRotation* frozen);
+                 const FrozenRotation* frozen, uint32_t* fault);
 int fused_tile_size();
 int fused_mode(); // 1 always, 0 never, -1 automatic
 void launch_update_draw(void* stream, const UpdateItem* items, const DrawItem* ditems, uint32_t n_items, uint32_t total_tiles,
-                        unsigned long long* tile_status, uint32_t epoch, int rot_mode, const FrozenRotation* frozen);
+                        unsigned long long* tile_status, uint32_t epoch, int rot_mode, const FrozenRotation* frozen,
+                        uint32_t* fault);
 void launch_latch(void* stream, const DrawItem* items, uint32_t n_items, FrozenRotation* frozen);
 struct CountQuery
 {
@@ -151,7 +157,8 @@ struct CountQuery
     uint32_t pad;
 };
 // out[2*i] = live count, out[2*i+1] = quads written by the last draw, for each query.
-void launch_gather_counts(void* stream, const CountQuery* q, uint32_t n, uint32_t* out);
+// out[2*n] = the context's fault word.
+void launch_gather_counts(void* stream, const CountQuery* q, uint32_t n, uint32_t* out, const uint32_t* fault);
 // MeshBatch's triangle-strip index pattern for n_quads quads (MB.cpp:117-141), 6*n_quads-2 indices.
 void launch_strip_indices(void* stream, uint32_t* out, uint64_t n_indices);
 void launch_triangle_indices(void* stream, uint32_t* out, uint64_t n_indices);

@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __rest
 //          writes the nq * 144 contiguous bytes while the other warps are already gone.
 template <int OUT, int DSUB>
 __global__ void __launch_bounds__(kDrawThreads)
-    k_draw(const DrawItem* __restrict__ items, uint32_t n_items, int rot_mode, const FrozenRotation* __restrict__ frozen)
+    k_draw(const DrawItem* __restrict__ items, uint32_t n_items, int rot_mode, const FrozenRotation* __restrict__ frozen,
+           uint32_t* __restrict__ fault)
 {
     __shared__ __align__(128) float s_vtx[kDrawThreads * T3D_FLOATS_PER_QUAD];
     __shared__ float s_uv[kMaxSmemFrames * 4];
@@ -217,7 +218,12 @@ __global__ void __launch_bounds__(kDrawThreads)
     const bool uv_in_smem = frame_count <= (uint32_t)kMaxSmemFrames;
     if (uv_in_smem)
         for (uint32_t q = tid; q < frame_count * 4u; q += kDrawThreads) s_uv[q] = uv_g[q];
-    if (first_tile == 0 && tid == 0) const_cast<EmitterDev*>(d)->cnt[0].drawn = N;
+    if (first_tile == 0 && tid == 0)
+    {
+        const_cast<EmitterDev*>(d)->cnt[0].drawn = N;
+        // (see k_update: the grid was sized from the host's upper bound of the live count)
+        if ((unsigned long long)N > (unsigned long long)it.n_tiles * (kDrawThreads * DSUB)) atomicOr(fault, kFaultDrawGrid);
+    }
     if (first_tile >= N) return;
     __syncthreads();
 
@@ -333,7 +339,7 @@ void launch_spawn(void* stream, const SpawnItem* items, uint32_t n_items, uint32
 }
 
 void launch_draw(void* stream, const DrawItem* items, uint32_t n_items, uint32_t total_tiles, int rot_mode,
-                 const FrozenRotation* frozen)
+                 const FrozenRotation* frozen, uint32_t* fault)
 {
     const int sub = draw_sub(n_items);
     static int mode = -1;
@@ -345,17 +351,17 @@ void launch_draw(void* stream, const DrawItem* items, uint32_t n_items, uint32_t
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 1)
     {
-        if (sub == 1) k_draw<1, 1><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen);
-        else if (sub == 2) k_draw<1, 2><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen);
-        else if (sub == 4) k_draw<1, 4><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen);
-        else k_draw<1, 8><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen);
+        if (sub == 1) k_draw<1, 1><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
+        else if (sub == 2) k_draw<1, 2><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
+        else if (sub == 4) k_draw<1, 4><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
+        else k_draw<1, 8><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
     }
     else
     {
-        if (sub == 1) k_draw<0, 1><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen);
-        else if (sub == 2) k_draw<0, 2><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen);
-        else if (sub == 4) k_draw<0, 4><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen);
-        else k_draw<0, 8><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen);
+        if (sub == 1) k_draw<0, 1><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
+        else if (sub == 2) k_draw<0, 2><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
+        else if (sub == 4) k_draw<0, 4><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
+        else k_draw<0, 8><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
     }
 }
 
@@ -384,17 +390,19 @@ void launch_latch(void* stream, const DrawItem* items, uint32_t n_items, FrozenR
     k_latch<<<1, 256, 0, (cudaStream_t)stream>>>(items, n_items, frozen);
 }
 
-__global__ void k_gather_counts(const CountQuery* __restrict__ q, uint32_t n, uint32_t* __restrict__ out)
+__global__ void k_gather_counts(const CountQuery* __restrict__ q, uint32_t n, uint32_t* __restrict__ out,
+                                const uint32_t* __restrict__ fault)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) out[2 * n] = *fault;
     if (i >= n) return;
     out[2 * i] = q[i].dev->cnt[q[i].parity].count;
     out[2 * i + 1] = q[i].dev->cnt[0].drawn;
 }
 
-void launch_gather_counts(void* stream, const CountQuery* q, uint32_t n, uint32_t* out)
+void launch_gather_counts(void* stream, const CountQuery* q, uint32_t n, uint32_t* out, const uint32_t* fault)
 {
-    k_gather_counts<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(q, n, out);
+    k_gather_counts<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(q, n, out, fault);
 }
 
 // MB.cpp:117-141: the first quad's four indices, then per quad two degenerate indices (previous last, next first)

@@ -173,6 +173,11 @@ struct t3d_ctx
     uint32_t* tri_indices{ nullptr };   // cached triangle-list pattern
     uint32_t tri_quads{ 0 };
 
+    // Device word the kernels OR into when they find their grid too small for the live count (the host's upper bound was
+    // wrong); it rides back with every count read-back and turns into T3D_ERR_INTERNAL on the next call.
+    uint32_t* fault_dev{ nullptr };
+    uint32_t fault{ 0 };
+
     uint32_t* readback_host{ nullptr }; // pinned scratch for counts
     size_t readback_cap{ 0 };
     uint32_t* readback_dev{ nullptr };
@@ -570,6 +575,7 @@ static void poll_feedback(t3d_ctx* c)
             t3d_emitter* e = fb.es[i];
             if (!e) continue;
             const uint64_t ub = (uint64_t)fb.host[2 * i] + (e->emitted_total - fb.emitted_mark[i]);
+            if (i == 0) c->fault |= fb.host[2 * fb.es.size()];
             if (ub < e->count_ub) e->count_ub = (uint32_t)ub;
         }
         fb.in_flight = false;
@@ -589,8 +595,8 @@ static int submit_feedback(t3d_ctx* c, const std::vector<PendingOp>& ops, const 
         if (fb.dev) cudaFree(fb.dev);
         fb.host = fb.dev = nullptr;
         const size_t cap = std::max<size_t>(n * 2, 64);
-        T3D_CUDA(cudaMallocHost((void**)&fb.host, cap * 2 * sizeof(uint32_t)));
-        T3D_CUDA(cudaMalloc((void**)&fb.dev, cap * 2 * sizeof(uint32_t)));
+        T3D_CUDA(cudaMallocHost((void**)&fb.host, (cap * 2 + 1) * sizeof(uint32_t)));
+        T3D_CUDA(cudaMalloc((void**)&fb.dev, (cap * 2 + 1) * sizeof(uint32_t)));
         fb.cap = cap;
     }
     if (!fb.done) T3D_CUDA(cudaEventCreateWithFlags(&fb.done, cudaEventDisableTiming));
@@ -601,14 +607,26 @@ static int submit_feedback(t3d_ctx* c, const std::vector<PendingOp>& ops, const 
         fb.es[i] = ops[i].e;
         fb.emitted_mark[i] = ops[i].e->emitted_total;
     }
-    launch_gather_counts(c->stream, dev_queries, (uint32_t)n, fb.dev);
+    launch_gather_counts(c->stream, dev_queries, (uint32_t)n, fb.dev, c->fault_dev);
     T3D_CUDA(cudaGetLastError());
     c->launches++;
-    T3D_CUDA(cudaMemcpyAsync(fb.host, fb.dev, n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    T3D_CUDA(cudaMemcpyAsync(fb.host, fb.dev, (n * 2 + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     T3D_CUDA(cudaEventRecord(fb.done, c->stream));
     c->d2h_bytes += n * 2 * sizeof(uint32_t);
     fb.in_flight = true;
     return T3D_OK;
+}
+
+// T3D_DEBUG_SHRINK_GRID=1 (tests only): every update launch leaves the last tile of each emitter out.
+static bool debug_shrink_grid()
+{
+    static int v = -1;
+    if (v < 0)
+    {
+        const char* env = getenv("T3D_DEBUG_SHRINK_GRID");
+        v = (env && env[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
 }
 
 // Cuts the update descriptors (and the count queries of the feedback) of `ops`; advances each emitter's parity.
@@ -639,7 +657,9 @@ static void build_update_items(std::vector<PendingOp>& ops, UpdateItem* items, C
         queries[k].parity = e->parity; // where this launch leaves the new count
         queries[k].pad = 0;
         // At least one tile per emitter: tile 0 republishes the count into the other parity slot.
-        tiles += std::max(1u, (e->count_ub + tile_size - 1) / tile_size);
+        it.n_tiles = std::max(1u, (e->count_ub + tile_size - 1) / tile_size);
+        if (debug_shrink_grid() && it.n_tiles > 1) it.n_tiles -= 1; // test hook: proves that the kernel's check fires
+        tiles += it.n_tiles;
     }
     *tiles_out = tiles;
 }
@@ -683,7 +703,7 @@ static int launch_updates(t3d_ctx* c, std::vector<PendingOp>& ops)
     T3D_TRY(staging_submit(c, slot, total_bytes));
     T3D_TRY(time_begin(c, KERNEL_UPDATE));
     launch_update(c->stream, reinterpret_cast<const UpdateItem*>(slot->dev), n_items, tiles, c->tile_status, c->ticket,
-                  c->ticket_base, c->epoch);
+                  c->ticket_base, c->epoch, c->fault_dev);
     T3D_CUDA(cudaGetLastError());
     T3D_TRY(time_end(c, KERNEL_UPDATE));
     c->ticket_base += tiles;
@@ -733,7 +753,8 @@ static void build_draw_items(std::vector<PendingOp>& ops, DrawItem* items, uint3
         it.tile_begin = tiles;
         memcpy(it.right, op.right, 12);
         memcpy(it.up, op.up, 12);
-        tiles += std::max(1u, (e->count_ub + draw_tile - 1) / draw_tile);
+        it.n_tiles = std::max(1u, (e->count_ub + draw_tile - 1) / draw_tile);
+        tiles += it.n_tiles;
         any_spin = any_spin || e->may_spin;
     }
     *tiles_out = tiles;
@@ -770,7 +791,7 @@ static int launch_draws(t3d_ctx* c)
         }
     }
     T3D_TRY(time_begin(c, KERNEL_DRAW));
-    launch_draw(c->stream, reinterpret_cast<const DrawItem*>(slot->dev), n_items, tiles, c->rot_mode, c->frozen_dev);
+    launch_draw(c->stream, reinterpret_cast<const DrawItem*>(slot->dev), n_items, tiles, c->rot_mode, c->frozen_dev, c->fault_dev);
     T3D_CUDA(cudaGetLastError());
     T3D_TRY(time_end(c, KERNEL_DRAW));
     c->launches++;
@@ -814,7 +835,7 @@ static int launch_fused_frame(t3d_ctx* c)
     T3D_TRY(time_begin(c, KERNEL_UPDATE_DRAW));
     launch_update_draw(c->stream, reinterpret_cast<const UpdateItem*>(slot->dev),
                        reinterpret_cast<const DrawItem*>(slot->dev + items_bytes + queries_bytes), n_items, tiles, c->tile_status,
-                       c->epoch, c->rot_mode, c->frozen_dev);
+                       c->epoch, c->rot_mode, c->frozen_dev, c->fault_dev);
     T3D_CUDA(cudaGetLastError());
     T3D_TRY(time_end(c, KERNEL_UPDATE_DRAW));
     c->launches++;
@@ -842,6 +863,15 @@ static bool hold_for_fusion(const t3d_ctx* c)
     return spawned * 400 <= particles; // <= 0.25 % replaced per frame
 }
 
+static int check_fault(const t3d_ctx* c)
+{
+    if (c->fault)
+        return fail(T3D_ERR_INTERNAL, "a kernel found its grid too small for the live count (%s%s): the host's upper bound was wrong; "
+                                      "particles were left out of a frame", (c->fault & kFaultUpdateGrid) ? "update " : "",
+                    (c->fault & kFaultDrawGrid) ? "draw" : "");
+    return T3D_OK;
+}
+
 static int launch_held(t3d_ctx* c)
 {
     if (c->held.empty()) return T3D_OK;
@@ -867,6 +897,7 @@ static int flush(t3d_ctx* c, int next_phase = PHASE_NONE)
     }
     T3D_TRY(use_device(c));
     poll_feedback(c);
+    T3D_TRY(check_fault(c));
     int rc = T3D_OK;
     bool hold = false;
     if (c->phase == PHASE_EMIT)
@@ -928,8 +959,8 @@ static int refresh_counts(t3d_ctx* c, t3d_emitter* const* es, size_t n, uint32_t
         if (c->readback_host) cudaFreeHost(c->readback_host);
         if (c->readback_dev) cudaFree(c->readback_dev);
         size_t cap = std::max<size_t>(n * 2, 256);
-        T3D_CUDA(cudaMallocHost((void**)&c->readback_host, cap * 2 * sizeof(uint32_t)));
-        T3D_CUDA(cudaMalloc((void**)&c->readback_dev, cap * 2 * sizeof(uint32_t)));
+        T3D_CUDA(cudaMallocHost((void**)&c->readback_host, (cap * 2 + 1) * sizeof(uint32_t)));
+        T3D_CUDA(cudaMalloc((void**)&c->readback_dev, (cap * 2 + 1) * sizeof(uint32_t)));
         c->readback_cap = cap;
     }
     StagingSlot* slot;
@@ -942,13 +973,15 @@ static int refresh_counts(t3d_ctx* c, t3d_emitter* const* es, size_t n, uint32_t
         q[i].pad = 0;
     }
     T3D_TRY(staging_submit(c, slot, sizeof(CountQuery) * n));
-    launch_gather_counts(c->stream, reinterpret_cast<const CountQuery*>(slot->dev), (uint32_t)n, c->readback_dev);
+    launch_gather_counts(c->stream, reinterpret_cast<const CountQuery*>(slot->dev), (uint32_t)n, c->readback_dev, c->fault_dev);
     T3D_CUDA(cudaGetLastError());
     c->launches++;
-    T3D_CUDA(cudaMemcpyAsync(c->readback_host, c->readback_dev, n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    T3D_CUDA(cudaMemcpyAsync(c->readback_host, c->readback_dev, (n * 2 + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     T3D_TRY(staging_release(c, slot));
     T3D_CUDA(cudaStreamSynchronize(c->stream));
     c->d2h_bytes += n * 2 * sizeof(uint32_t);
+    c->fault |= c->readback_host[2 * n];
+    T3D_TRY(check_fault(c));
     for (size_t i = 0; i < n; ++i)
     {
         es[i]->count_ub = c->readback_host[2 * i];
@@ -1136,6 +1169,8 @@ int t3d_ctx_create(int device, void* cuda_stream, t3d_ctx** out)
     if (cudaMalloc((void**)&c->ticket, sizeof(uint32_t)) != cudaSuccess ||
         cudaMemsetAsync(c->ticket, 0, sizeof(uint32_t), c->stream) != cudaSuccess ||
         cudaMalloc((void**)&c->frozen_dev, sizeof(FrozenRotation)) != cudaSuccess ||
+        cudaMalloc((void**)&c->fault_dev, sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemsetAsync(c->fault_dev, 0, sizeof(uint32_t), c->stream) != cudaSuccess ||
         cudaMemsetAsync(c->frozen_dev, 0, sizeof(FrozenRotation), c->stream) != cudaSuccess)
     {
         delete c;
@@ -1182,6 +1217,7 @@ int t3d_ctx_destroy(t3d_ctx* c)
     if (c->tile_status) cudaFree(c->tile_status);
     if (c->ticket) cudaFree(c->ticket);
     if (c->frozen_dev) cudaFree(c->frozen_dev);
+    if (c->fault_dev) cudaFree(c->fault_dev);
     if (c->readback_host) cudaFreeHost(c->readback_host);
     if (c->readback_dev) cudaFree(c->readback_dev);
     if (c->strip_indices) cudaFree(c->strip_indices);

@@ -255,7 +255,7 @@ template <int V, int THREADS, int SUB, int MIN_BLOCKS, bool ASYNC, bool TICKET, 
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     k_update(const UpdateItem* __restrict__ items, uint32_t n_items, uint32_t total_tiles,
              unsigned long long* __restrict__ tile_status, uint32_t* __restrict__ ticket, uint32_t ticket_base,
-             uint32_t epoch, const DrawItem* __restrict__ ditems = nullptr, int rot_mode = 0,
+             uint32_t epoch, uint32_t* __restrict__ fault, const DrawItem* __restrict__ ditems = nullptr, int rot_mode = 0,
              const FrozenRotation* __restrict__ frozen = nullptr)
 {
     static_assert(!FUSED || !ASYNC || V == 4, "the cp.async ring moves 4 particles per thread");
@@ -350,8 +350,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             if (kWholeRecord) a_cur.load(particle_base(cols, bshift, k0), stride, animated, FUSED);
         }
     }
+    // The host sized this emitter's share of the grid from an upper bound of its live count; if the bound was wrong,
+    // say so instead of silently leaving particles out of the frame.
+    if (jt == 0 && tid == 0 && (unsigned long long)N > (unsigned long long)it.n_tiles * TILE) atomicOr(fault, kFaultUpdateGrid);
     if (first >= N)
     {
+        if (ASYNC) cp_async_wait<0>(); // nothing of this thread may still be landing in shared memory when the CTA retires
         if (jt == 0 && tid == 0)
         {
             d->cnt[parity ^ 1].count = 0;
@@ -779,6 +783,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         }
         compiler_fence();
     }
+    // (threads that left the loop early still have their first ring groups in flight)
+    if (ASYNC) cp_async_wait<0>();
     // shared memory must outlive the bulk stores, and their writes must have landed before the move pass overwrites
     // the quads of the slots it fills
     if (FUSED && lane == 0)
@@ -876,7 +882,7 @@ struct UpdateVariant
 {
     const char* name;
     int tile;
-    void (*launch)(cudaStream_t, uint32_t, const UpdateItem*, uint32_t, unsigned long long*, uint32_t*, uint32_t, uint32_t);
+    void (*launch)(cudaStream_t, uint32_t, const UpdateItem*, uint32_t, unsigned long long*, uint32_t*, uint32_t, uint32_t, uint32_t*);
 };
 
 // T3D_UPDATE_TICKET=1: hand tile ids out with an atomic ticket instead of relying on block dispatch order.
@@ -893,17 +899,17 @@ static bool use_ticket()
 
 template <int V, int THREADS, int SUB, int MIN_BLOCKS>
 static void launch_variant(cudaStream_t s, uint32_t tiles, const UpdateItem* items, uint32_t n_items,
-                           unsigned long long* status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch)
+                           unsigned long long* status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch, uint32_t* fault)
 {
     if (use_ticket())
-        k_update<V, THREADS, SUB, MIN_BLOCKS, false, true><<<tiles, THREADS, 0, s>>>(items, n_items, tiles, status, ticket, ticket_base, epoch);
+        k_update<V, THREADS, SUB, MIN_BLOCKS, false, true><<<tiles, THREADS, 0, s>>>(items, n_items, tiles, status, ticket, ticket_base, epoch, fault);
     else
-        k_update<V, THREADS, SUB, MIN_BLOCKS, false, false><<<tiles, THREADS, 0, s>>>(items, n_items, tiles, status, ticket, ticket_base, epoch);
+        k_update<V, THREADS, SUB, MIN_BLOCKS, false, false><<<tiles, THREADS, 0, s>>>(items, n_items, tiles, status, ticket, ticket_base, epoch, fault);
 }
 
 template <int THREADS, int SUB, int MIN_BLOCKS>
 static void launch_async(cudaStream_t s, uint32_t tiles, const UpdateItem* items, uint32_t n_items,
-                         unsigned long long* status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch)
+                         unsigned long long* status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch, uint32_t* fault)
 {
     constexpr size_t smem = 2 * (size_t)RC_COUNT * THREADS * sizeof(float4) + 128;
     static bool configured = false;
@@ -912,7 +918,7 @@ static void launch_async(cudaStream_t s, uint32_t tiles, const UpdateItem* items
         cudaFuncSetAttribute(k_update<4, THREADS, SUB, MIN_BLOCKS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
-    k_update<4, THREADS, SUB, MIN_BLOCKS, true, false><<<tiles, THREADS, smem, s>>>(items, n_items, tiles, status, ticket, ticket_base, epoch);
+    k_update<4, THREADS, SUB, MIN_BLOCKS, true, false><<<tiles, THREADS, smem, s>>>(items, n_items, tiles, status, ticket, ticket_base, epoch, fault);
 }
 
 #define T3D_VARIANT(V, T, S, B) { "v" #V "t" #T "s" #S "b" #B, V * T * S, launch_variant<V, T, S, B> }
@@ -945,11 +951,11 @@ struct FusedVariant
     const char* name;
     int tile;
     void (*launch)(cudaStream_t, uint32_t, const UpdateItem*, const DrawItem*, uint32_t, unsigned long long*, uint32_t, int,
-                   const FrozenRotation*);
+                   const FrozenRotation*, uint32_t*);
 };
 template <int THREADS, int SUB, int MIN_BLOCKS>
 static void launch_fused(cudaStream_t s, uint32_t tiles, const UpdateItem* items, const DrawItem* ditems, uint32_t n_items,
-                         unsigned long long* status, uint32_t epoch, int rot_mode, const FrozenRotation* frozen)
+                         unsigned long long* status, uint32_t epoch, int rot_mode, const FrozenRotation* frozen, uint32_t* fault)
 {
     // ring + vertex staging (4 quads per thread, contiguous per warp)
     constexpr size_t smem = 2 * (size_t)RC_COUNT * THREADS * sizeof(float4) + (size_t)THREADS * (4 * T3D_FLOATS_PER_QUAD * 4) + 128;
@@ -960,12 +966,12 @@ static void launch_fused(cudaStream_t s, uint32_t tiles, const UpdateItem* items
         configured = true;
     }
     k_update<4, THREADS, SUB, MIN_BLOCKS, true, false, true><<<tiles, THREADS, smem, s>>>(items, n_items, tiles, status, nullptr, 0u, epoch,
-                                                                                          ditems, rot_mode, frozen);
+                                                                                          fault, ditems, rot_mode, frozen);
 }
 // the same without the cp.async ring: loads through registers, more warps per SM
 template <int V, int THREADS, int SUB, int MIN_BLOCKS>
 static void launch_fused_lsu(cudaStream_t s, uint32_t tiles, const UpdateItem* items, const DrawItem* ditems, uint32_t n_items,
-                             unsigned long long* status, uint32_t epoch, int rot_mode, const FrozenRotation* frozen)
+                             unsigned long long* status, uint32_t epoch, int rot_mode, const FrozenRotation* frozen, uint32_t* fault)
 {
     constexpr size_t smem = (size_t)THREADS * (V * T3D_FLOATS_PER_QUAD * 4) + 128;
     static bool configured = false;
@@ -975,7 +981,7 @@ static void launch_fused_lsu(cudaStream_t s, uint32_t tiles, const UpdateItem* i
         configured = true;
     }
     k_update<V, THREADS, SUB, MIN_BLOCKS, false, false, true><<<tiles, THREADS, smem, s>>>(items, n_items, tiles, status, nullptr, 0u, epoch,
-                                                                                           ditems, rot_mode, frozen);
+                                                                                           fault, ditems, rot_mode, frozen);
 }
 #define T3D_FUSED(T, S, B) { "f4t" #T "s" #S "b" #B, 4 * T * S, launch_fused<T, S, B> }
 #define T3D_FUSED_LSU(V, T, S, B) { "g" #V "t" #T "s" #S "b" #B, V * T * S, launch_fused_lsu<V, T, S, B> }
@@ -1014,18 +1020,18 @@ int fused_mode()
     return v;
 }
 void launch_update_draw(void* stream, const UpdateItem* items, const DrawItem* ditems, uint32_t n_items, uint32_t total_tiles,
-                        unsigned long long* tile_status, uint32_t epoch, int rot_mode, const FrozenRotation* frozen)
+                        unsigned long long* tile_status, uint32_t epoch, int rot_mode, const FrozenRotation* frozen, uint32_t* fault)
 {
-    fused_variant().launch((cudaStream_t)stream, total_tiles, items, ditems, n_items, tile_status, epoch, rot_mode, frozen);
+    fused_variant().launch((cudaStream_t)stream, total_tiles, items, ditems, n_items, tile_status, epoch, rot_mode, frozen, fault);
 }
 
 int update_tile_size() { return variant().tile; }
 const char* update_variant_name() { return variant().name; }
 
 void launch_update(void* stream, const UpdateItem* items, uint32_t n_items, uint32_t total_tiles,
-                   unsigned long long* tile_status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch)
+                   unsigned long long* tile_status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch, uint32_t* fault)
 {
-    variant().launch((cudaStream_t)stream, total_tiles, items, n_items, tile_status, ticket, ticket_base, epoch);
+    variant().launch((cudaStream_t)stream, total_tiles, items, n_items, tile_status, ticket, ticket_base, epoch, fault);
 }
 
 } // namespace t3d
