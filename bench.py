@@ -263,6 +263,7 @@ def run_cuda(args):
     counts1 = ctx.batch_counts(emitters, handles)
     live_after = int(counts1.sum())
     updates_done = (local_particles if not churn else int((counts0.sum() + counts1.sum()) // 2)) * args.steps
+    local_updates_done = updates_done   # this rank's share: the per-launch rooflines below are rank 0's kernels
 
     kern = {}
     for k, nm in enumerate(("spawn", "update", "draw", "update_draw")):
@@ -331,7 +332,7 @@ def run_cuda(args):
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         upd_bytes = UPDATE_BYTES + (UPDATE_BYTES_ANIMATED - UPDATE_BYTES) * animated_frac
-        per_launch_particles = local_particles if not churn else updates_done / args.steps
+        per_launch_particles = local_particles if not churn else local_updates_done / args.steps
         roof = {}
         traffic = measured_traffic()
         # fused: the draw's 40 B re-read of position/colour/size/angle/frame disappears (the frame index is read once)

@@ -190,7 +190,9 @@ int t3d_emitter_is_started(t3d_emitter* e, int* out);    /* PE.h:279 */
 int t3d_emitter_is_active(t3d_emitter* e, int* out);     /* PE.cpp:277-284 (may read the count back) */
 int t3d_emitter_emit_once(t3d_emitter* e, uint32_t particle_count);   /* PE.cpp:287-369 */
 int t3d_emitter_update(t3d_emitter* e, float elapsed_ms);             /* PE.cpp:713-832 */
-/* PE.cpp:835-888.  *draw_calls receives what the reference returns (0 if inactive, else 1). */
+/* PE.cpp:835-888.  *draw_calls receives what the reference returns (0 if inactive, else 1); for a stopped emitter
+ * that may need the live count from the device.  Pass NULL (as t3d_batch_draw does) when the value is not needed:
+ * the draw is then queued without waiting, and writes no quads if every particle has died. */
 int t3d_emitter_draw(t3d_emitter* e, uint32_t* draw_calls);
 int t3d_emitter_get_count(t3d_emitter* e, uint32_t* count);           /* PE.h:306; flushes + reads back */
 

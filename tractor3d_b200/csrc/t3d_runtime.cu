@@ -1561,7 +1561,8 @@ int t3d_emitter_is_started(t3d_emitter* e, int* out)
     return T3D_OK;
 }
 
-static int is_active(t3d_emitter* e, bool* out)
+// need_exact = false: the caller can live with "maybe" (answered as active) when only a read-back could tell.
+static int is_active(t3d_emitter* e, bool* out, bool need_exact = true)
 {
     // PE.cpp:277-284
     if (e->started)
@@ -1575,6 +1576,11 @@ static int is_active(t3d_emitter* e, bool* out)
         return T3D_OK;
     }
     if (e->alive_budget_ms > 0) // some particle cannot have died yet: `_particleCount > 0` without asking the device
+    {
+        *out = true;
+        return T3D_OK;
+    }
+    if (!need_exact && !e->count_exact)
     {
         *out = true;
         return T3D_OK;
@@ -1637,8 +1643,11 @@ int t3d_emitter_draw(t3d_emitter* e, uint32_t* draw_calls)
     if (!e) return fail(T3D_ERR_INVALID, "null emitter");
     t3d_ctx* c = e->ctx;
     if (draw_calls) *draw_calls = 0;
+    // The return value (PE.cpp:837: 0 when inactive) is the only thing that needs the exact live count of a stopped
+    // emitter; a caller that does not ask for it (the batch call) is not made to wait for the device -- a draw of an
+    // emitter whose particles have all died writes no quads either way.
     bool active;
-    T3D_TRY(is_active(e, &active));
+    T3D_TRY(is_active(e, &active, draw_calls != nullptr));
     e->last_draw_empty = true;
     if (!active) return T3D_OK; // PE.cpp:837
     if (draw_calls) *draw_calls = 1;
