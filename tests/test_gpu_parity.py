@@ -342,6 +342,26 @@ def test_empty_and_inactive_emitters(gpu):
     assert eg.count() == 0
 
 
+def test_batch_draw_of_a_drained_emitter_draws_nothing():
+    # A stopped emitter whose particles have all died: the batch draw (which does not ask for the reference's return
+    # value) is queued without reading the live count back, and the frame then holds no quads.
+    from gpu_adapter import GpuLib
+    lib = GpuLib(rng_mode=abi.RNG_DEVICE, seed=5)
+    try:
+        p, sprite = presets.headline_64m(capacity=5000)
+        p.energy_min, p.energy_max = 10.0, 30.0
+        eg = lib.emitter(p); eg.set_sprite_frame_coords(*sprite)
+        eg.emit_once(3000)
+        for _ in range(40):   # (a particle moved into a dead slot skips a frame, so extinction takes a while)
+            lib.ctx.batch_update([eg.pe], S.DT)
+            lib.ctx.batch_draw([eg.pe])
+        assert eg.vertices().shape[0] == 0
+        assert eg.count() == 0 and not eg.is_active()
+        assert eg.draw() == 0      # PE.cpp:837, now with the exact answer
+    finally:
+        lib.close()
+
+
 def test_errors_are_codes_not_exits(gpu):
     from tractor3d_b200.emitter import T3DError
     p, _ = presets.smoke()
