@@ -230,6 +230,10 @@ int t3d_emitter_upload_state(t3d_emitter* e, const uint32_t* in, size_t stride, 
 int32_t t3d_device_rng_draw(uint64_t seed, uint64_t serial, uint32_t j);
 /* PE.cpp:720-725: the process-wide update rate cap.  Returns 1 and sets *elapsed_ms when the update proceeds. */
 int t3d_host_rate_cap(double* running_time, float elapsed_time, float* elapsed_ms);
+/* The runtime's launch policy (not in the reference): should update() of a set of emitters wait for the draw() that
+ * follows, to go out as one fused launch?  particles = their live particles (upper bound), spawned = particles asked to
+ * spawn since their previous update (stands in for deaths).  1 while at most 0.25 % are replaced per frame. */
+int t3d_host_fuse_policy(uint64_t particles, uint64_t spawned);
 /* PE.cpp:732-743: advances *emit_time and returns how many particles to emit this frame. */
 uint32_t t3d_host_emission_count(float* emit_time, float time_per_emission, float elapsed_ms);
 /* PE.cpp:526-582: uv table for a grid of width x height frames on a tex_w x tex_h texture. Returns frames written. */

@@ -82,6 +82,17 @@ def test_rate_cap_and_emission_count_follow_the_oracle():
             assert np.float32(emit_time.value) == np.float32(eo.emit_time())
 
 
+def test_fuse_policy_follows_the_measured_crossover():
+    # update+draw go out as one fused launch while at most 0.25 % of the particles are replaced per frame
+    # (profiles/r1_churn_crossover.txt: fused wins at 0 and 0.17 %, loses at 0.34 % and beyond).
+    lib = abi.load()
+    assert lib.t3d_host_fuse_policy(64 << 20, 0) == 1                 # C3/C4: stationary
+    assert lib.t3d_host_fuse_policy(38_500_000, 65_536) == 1          # 0.17 %
+    assert lib.t3d_host_fuse_policy(38_500_000, 131_072) == 0         # 0.34 %
+    assert lib.t3d_host_fuse_policy(14_300_000, 1 << 20) == 0         # C5: 7 %
+    assert lib.t3d_host_fuse_policy(0, 0) == 1 and lib.t3d_host_fuse_policy(0, 1) == 0
+
+
 def test_sprite_frame_coords_follow_the_oracle():
     lib, O = abi.load(), H.oracle()
     for tw, th, n, w, h in ((1024, 256, 3, 256, 256), (256, 256, 16, 64, 64), (64, 64, 1, 64, 64), (300, 200, 7, 100, 50),

@@ -170,6 +170,7 @@ PROTOTYPES = {
     "t3d_emitter_download_state": (C.c_int, [_vp, _P(C.c_uint32), C.c_size_t, _P(C.c_uint32)]),
     "t3d_emitter_upload_state": (C.c_int, [_vp, _P(C.c_uint32), C.c_size_t, C.c_uint32]),
     "t3d_device_rng_draw": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_uint32]),
+    "t3d_host_fuse_policy": (C.c_int, [C.c_uint64, C.c_uint64]),
     "t3d_host_rate_cap": (C.c_int, [_P(C.c_double), C.c_float, _P(C.c_float)]),
     "t3d_host_emission_count": (C.c_uint32, [_P(C.c_float), C.c_float, C.c_float]),
     "t3d_host_sprite_frame_coords": (C.c_uint32, [C.c_uint32, C.c_int, C.c_int, C.c_float, C.c_float, _P(C.c_float)]),

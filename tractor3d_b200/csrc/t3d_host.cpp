@@ -72,6 +72,13 @@ void t3d_emitter_params_default(t3d_emitter_params* p)
 
 int32_t t3d_device_rng_draw(uint64_t seed, uint64_t serial, uint32_t j) { return t3d::device_rng_draw(seed, serial, j); }
 
+int t3d_host_fuse_policy(uint64_t particles, uint64_t spawned)
+{
+    // Measured crossover on B200 (profiles/r1_churn_crossover.txt): the fused frame wins up to ~0.25 % of the particles
+    // replaced per frame and loses beyond (every moved particle costs it an extra scattered 144-byte quad).
+    return spawned * 400 <= particles ? 1 : 0;
+}
+
 int t3d_host_rate_cap(double* running_time, float elapsed_time, float* elapsed_ms)
 {
     // PE.cpp:720-725: PARTICLE_UPDATE_RATE_MAX = 8 ms.

@@ -860,7 +860,7 @@ static bool hold_for_fusion(const t3d_ctx* c)
         particles += op.e->count_ub;
         spawned += op.spawned;
     }
-    return spawned * 400 <= particles; // <= 0.25 % replaced per frame
+    return t3d_host_fuse_policy(particles, spawned) != 0; // <= 0.25 % replaced per frame
 }
 
 static int check_fault(const t3d_ctx* c)
