@@ -991,8 +991,8 @@ static const FusedVariant kFused[] = {
     // peak on 304 B/particle) against 1.69 + 1.83 ms for the two separate launches.  The 4-particle variants (f4: with the
     // cp.async ring, g4: without) are capped at 4-8 warps per SM by their vertex staging and lose.
     T3D_FUSED_LSU(2, 192, 12, 2),
-    T3D_FUSED_LSU(2, 192, 8, 2), T3D_FUSED_LSU(2, 384, 6, 1), T3D_FUSED_LSU(2, 256, 8, 1), T3D_FUSED_LSU(1, 512, 8, 1),
-    T3D_FUSED_LSU(4, 256, 4, 1), T3D_FUSED_LSU(4, 128, 8, 2), T3D_FUSED(64, 10, 2),
+    // alternatives kept for experiments and for the parity tests of the other code paths (tests/test_gpu_variants.py)
+    T3D_FUSED_LSU(2, 192, 8, 2), T3D_FUSED_LSU(2, 384, 6, 1), T3D_FUSED_LSU(4, 128, 8, 2), T3D_FUSED(64, 10, 2),
 };
 static const FusedVariant& fused_variant()
 {
