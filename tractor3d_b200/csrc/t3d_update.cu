@@ -885,6 +885,14 @@ struct UpdateVariant
     void (*launch)(cudaStream_t, uint32_t, const UpdateItem*, uint32_t, unsigned long long*, uint32_t*, uint32_t, uint32_t, uint32_t*);
 };
 
+constexpr int kMaxDevices = 64;
+static int current_device()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+
 // T3D_UPDATE_TICKET=1: hand tile ids out with an atomic ticket instead of relying on block dispatch order.
 static bool use_ticket()
 {
@@ -912,11 +920,13 @@ static void launch_async(cudaStream_t s, uint32_t tiles, const UpdateItem* items
                          unsigned long long* status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch, uint32_t* fault)
 {
     constexpr size_t smem = 2 * (size_t)RC_COUNT * THREADS * sizeof(float4) + 128;
-    static bool configured = false;
-    if (!configured)
+    // the opt-in to more than 48 KB of dynamic shared memory is per device: once for each device this process launches on
+    static bool configured[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!configured[dev])
     {
         cudaFuncSetAttribute(k_update<4, THREADS, SUB, MIN_BLOCKS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+        configured[dev] = true;
     }
     k_update<4, THREADS, SUB, MIN_BLOCKS, true, false><<<tiles, THREADS, smem, s>>>(items, n_items, tiles, status, ticket, ticket_base, epoch, fault);
 }
@@ -959,11 +969,13 @@ static void launch_fused(cudaStream_t s, uint32_t tiles, const UpdateItem* items
 {
     // ring + vertex staging (4 quads per thread, contiguous per warp)
     constexpr size_t smem = 2 * (size_t)RC_COUNT * THREADS * sizeof(float4) + (size_t)THREADS * (4 * T3D_FLOATS_PER_QUAD * 4) + 128;
-    static bool configured = false;
-    if (!configured)
+    // the opt-in to more than 48 KB of dynamic shared memory is per device: once for each device this process launches on
+    static bool configured[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!configured[dev])
     {
         cudaFuncSetAttribute(k_update<4, THREADS, SUB, MIN_BLOCKS, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+        configured[dev] = true;
     }
     k_update<4, THREADS, SUB, MIN_BLOCKS, true, false, true><<<tiles, THREADS, smem, s>>>(items, n_items, tiles, status, nullptr, 0u, epoch,
                                                                                           fault, ditems, rot_mode, frozen);
@@ -974,11 +986,13 @@ static void launch_fused_lsu(cudaStream_t s, uint32_t tiles, const UpdateItem* i
                              unsigned long long* status, uint32_t epoch, int rot_mode, const FrozenRotation* frozen, uint32_t* fault)
 {
     constexpr size_t smem = (size_t)THREADS * (V * T3D_FLOATS_PER_QUAD * 4) + 128;
-    static bool configured = false;
-    if (!configured)
+    // the opt-in to more than 48 KB of dynamic shared memory is per device: once for each device this process launches on
+    static bool configured[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!configured[dev])
     {
         cudaFuncSetAttribute(k_update<V, THREADS, SUB, MIN_BLOCKS, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+        configured[dev] = true;
     }
     k_update<V, THREADS, SUB, MIN_BLOCKS, false, false, true><<<tiles, THREADS, smem, s>>>(items, n_items, tiles, status, nullptr, 0u, epoch,
                                                                                            fault, ditems, rot_mode, frozen);
