@@ -429,6 +429,40 @@ def test_large_population_properties():
         lib.close()
 
 
+def test_fused_and_separate_frames_agree_at_scale():
+    # Two emitters with the same seed and parameters in one context, 3 Mi particles each (several waves of CTAs), heavy
+    # dying.  A is driven update(); draw() -- the fused launch; B is driven update(); getParticlesCount(); draw() -- the
+    # count forces its update out on its own, so B takes the two separate kernels.  Same arithmetic, same removal order:
+    # state and vertices must be bit-identical, at a size the CPU oracle is not needed for.
+    import os
+    from gpu_adapter import GpuLib
+    if os.environ.get("T3D_FUSED") == "0":
+        pytest.skip("fusion disabled by the environment")
+    lib = GpuLib(rng_mode=abi.RNG_DEVICE, seed=1234)
+    try:
+        n = 3 * 1024 * 1024
+        p, sprite = presets.headline_64m(capacity=n)
+        p.energy_min, p.energy_max = 40.0, 300.0
+        p.emission_rate = 1
+        a = lib.emitter(p); a.set_sprite_frame_coords(*sprite)
+        b = lib.emitter(p); b.set_sprite_frame_coords(*sprite)
+        a.emit_once(n); b.emit_once(n)
+        a.start(); b.start()        # started: isActive() needs no read-back, nothing splits A's frames
+        k0 = [lib.ctx.kernel_time(i)[1] for i in range(4)]
+        for f in range(8):
+            a.update(S.DT); a.draw()
+            b.update(S.DT); cb = b.count(); b.draw()
+            if f % 2 == 1:
+                assert a.count() == cb, f"frame {f}"
+                assert np.array_equal(a.state(), b.state()), f"frame {f}"
+                assert np.array_equal(a.vertices().view(np.uint32), b.vertices().view(np.uint32)), f"frame {f}"
+        k1 = [lib.ctx.kernel_time(i)[1] for i in range(4)]
+        assert k1[3] - k0[3] >= 6 and k1[1] - k0[1] >= 8, (k0, k1)   # A fused (but for the latch frame), B separate
+        assert 0 < a.count() < n
+    finally:
+        lib.close()
+
+
 def test_strip_index_pattern_matches_meshbatch_restatement(gpu):
     # the index pattern MeshBatch::add stitches per quad (MB.cpp:117-141), 32-bit.
     O = H.oracle()
