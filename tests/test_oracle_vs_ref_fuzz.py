@@ -77,3 +77,28 @@ def test_random_api_sequences_oracle_equals_reference(seed, rotate):
             check()
     check()
     assert O.rand_calls() == R.rand_calls()   # both consumed the shared stream to the same position
+
+
+@pytest.mark.parametrize("n", [4609, 200_003])
+def test_uploaded_populations_with_heavy_dying_oracle_equals_reference(n):
+    # The multi-tile GPU tests upload a synthetic live population and let it die out frame by frame: the removal order
+    # (swap-with-last, the moved particle skipped for a frame) is what they check.  Same populations, oracle against the
+    # unmodified reference, state and vertices after every frame.
+    from test_gpu_parity import _big_population
+    from tractor3d_b200 import presets
+    p, sprite = presets.headline_64m(capacity=n + 5)
+    p.energy_min, p.energy_max = 20.0, 400.0
+    O, R = H.oracle(fresh=True), H.ref(fresh=True)
+    eo, er = O.emitter(p), R.emitter(p)
+    eo.set_sprite_frame_coords(*sprite); er.set_sprite_frame_coords(*sprite)
+    cols = _big_population(n, seed=n + 7)
+    eo.set_state(cols); er.set_state(cols)
+    for f in range(14):
+        eo.update(S.DT); er.update(S.DT)
+        assert eo.count() == er.count(), f"frame {f}"
+        assert np.array_equal(eo.state(), er.state()), f"frame {f}"
+        assert eo.draw() == er.draw()
+        va, vb = eo.vertices(), er.vertices()
+        assert va.shape == vb.shape and np.array_equal(va.view(np.uint32), vb.view(np.uint32)), f"frame {f}"
+        if eo.count() == 0:
+            break
