@@ -216,6 +216,8 @@ def run_cuda(args):
     workload = args.workload or ("c3" if world == 1 else "c4")
     stream = torch.cuda.Stream()
     ctx = Context(local_rank, stream.cuda_stream)
+    if args.rotation == "per-particle":
+        ctx.set_rotation_mode(abi.ROT_PER_PARTICLE)
     # T3D_BENCH_EMULATE_WORLD=N (experiments only): rank 0's share of an N-GPU run on one GPU
     pop_world = int(os.environ.get("T3D_BENCH_EMULATE_WORLD", world)) if world == 1 else world
     emitters, per, animated_frac, wl_name = build_population(ctx, workload, rank, pop_world, args.particles)
@@ -368,7 +370,8 @@ def run_cuda(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl_name, "particles_total": total_particles, "live_after": live_after,
                        "dt_ms": DT, "rng": "device counter-based generator (T3D_RNG_DEVICE)",
-                       "rotation_mode": "frozen (reference-identical, SB.cpp:339)",
+                       "rotation_mode": "frozen (reference-identical, SB.cpp:339)" if args.rotation == "frozen"
+                                        else "per particle (createRotation(right x up, angle_i) for every quad; not what the reference does)",
                        "l2": "inputs larger than L2 (state + vertex stream >> 126 MB), no flush needed" if total_particles // world * 280 > 512 * MI
                              else "working set may fit L2; no flush",
                        "parallelism": f"emitter-ownership sharding x{world}, no per-frame collective"},
@@ -518,6 +521,8 @@ def main():
     ap.add_argument("--cpu-particles", type=int, default=2 * MI, help="population of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the extra c2 measurement")
+    ap.add_argument("--rotation", default="frozen", choices=["frozen", "per-particle"],
+                    help="billboard rotation: the reference's frozen matrix (default) or a matrix per quad (experiments)")
     ap.add_argument("--churn-spawn", type=int, default=None, help="c5: particles spawned per frame (all GPUs)")
     ap.add_argument("--churn-energy", default=None, help="c5: energy range in ms, e.g. 500,2000")
     ap.add_argument("--vertices-to-host", action="store_true", help="also time frames with the vertex stream copied to pinned host memory")
