@@ -10,7 +10,12 @@ A step is one frame over the whole population: `update(1000/60 ms)` then `draw()
     c4  8 192 emitters x 32 Ki = 256 Mi particles, mixed fire/smoke/explosion sets, emitter e owned by rank e mod N
         (N > 1 default; strong scaling, no per-frame collective; NCCL only gathers the end-of-run counters)
     c2  1 024 emitters x 4 Ki (4 Mi particles), mixed sets
-    c5  high churn: 8 emitters per GPU, 1 Mi spawned per frame in total, energies 50..400 ms
+    c5  high churn: 8 emitters per GPU, 1 Mi spawned per frame PER GPU, energies 50..400 ms (7 % of the live set replaced
+        per frame: spawn- and compaction-bound)
+    c3d the c3 emitter with deaths: 1 Mi spawned per frame, energies 500..1500 ms (1.7 % replaced per frame, ~63 M live)
+The N = 1 line also carries short measurements of c2, c3d, c4 and c5 under `also` (every BASELINE.json config on one
+GPU; `also.c4` is the N = 1 point of the strong-scaling curve the N > 1 lines continue, `also.c5` that of the churn
+workload, which is weak-scaled: 1 Mi spawned per frame per GPU).
 One JSON line is printed by rank 0.  `value` = particles x steps / device time of the timed region with all
 state resident in HBM; `e2e` = the same frames driven call by call through the public ParticleEmitter
 interface with the per-frame host inputs (node and camera matrices, elapsed time) coming from host memory and
@@ -44,7 +49,7 @@ UPDATE_BYTES, UPDATE_BYTES_ANIMATED, DRAW_BYTES, SPAWN_BYTES = 144, 160, 184, 13
 def measured_traffic():
     """DRAM bytes per unit of each kernel from the committed ncu capture (profiles/), or {}."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             return json.load(f)
     except Exception:
         return {}
@@ -108,9 +113,9 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------------
 # workloads
 # --------------------------------------------------------------------------------------------------
-# c5 (churn) knobs; --churn-spawn / --churn-energy change them for experiments
-CHURN_SPAWN = MI
-CHURN_ENERGY = (50.0, 400.0)
+# churn knobs (particles spawned per frame PER GPU, energy range in ms); --churn-spawn / --churn-energy change c5's
+CHURN = {"c5": {"spawn": MI, "energy": (50.0, 400.0), "emitters": 8, "warm": 30},
+         "c3d": {"spawn": MI, "energy": (500.0, 1500.0), "emitters": 1, "warm": 100}}
 
 
 def build_population(ctx, workload, rank, world, particles):
@@ -143,52 +148,140 @@ def build_population(ctx, workload, rank, world, particles):
         name = (f"{workload}: {n_emitters} emitters x {per} particles, fire/smoke/explosion parameter sets round-robin, "
                 f"emitter e owned by rank e mod {world}")
         return emitters, per, animated / max(1, len(emitters)), name
-    if workload == "c5":
-        n_em, cap = 8, (particles or 64 * MI) // 8
-        for k in range(n_em):
+    if workload in CHURN:
+        k = CHURN[workload]
+        n_em, cap = k["emitters"], (particles or 64 * MI) // k["emitters"]
+        for j in range(n_em):
             p, sprite = presets.headline_64m(capacity=cap)
-            p.energy_min, p.energy_max = CHURN_ENERGY
-            e = ParticleEmitter.create(ctx, p, sprite, (abi.RNG_DEVICE, 77 + rank * n_em + k))
+            p.energy_min, p.energy_max = k["energy"]
+            e = ParticleEmitter.create(ctx, p, sprite, (abi.RNG_DEVICE, 77 + rank * n_em + j))
             emitters.append(e)
-        name = (f"c5: {n_em} emitters/GPU, {CHURN_SPAWN // world} particles spawned per frame per GPU, "
-                f"energies {CHURN_ENERGY[0]:g}..{CHURN_ENERGY[1]:g} ms")
+        name = (f"{workload}: {n_em} emitter(s)/GPU, {k['spawn']} particles spawned per frame per GPU, "
+                f"energies {k['energy'][0]:g}..{k['energy'][1]:g} ms")
         return emitters, cap, 1.0, name
     raise SystemExit(f"unknown workload {workload}")
 
 
-def quick_measure(ctx, stream, workload, steps, torch):
-    """A short extra measurement of another single-GPU workload on the same context (reported under `also`)."""
-    emitters, per, animated_frac, wl_name = build_population(ctx, workload, 0, 1, 0)
+def kernel_rooflines(kern, particles_per_launch, animated_frac, moved_per_launch=0, spawned_per_launch=0, traffic=None):
+    """Per-kernel roofline objects from average launch times (CUDA events on the launching stream)."""
+    peak, peak_src = measured_peak_gbs()
+    upd_b = UPDATE_BYTES + (UPDATE_BYTES_ANIMATED - UPDATE_BYTES) * animated_frac
+    # fused: the draw's 40 B re-read of position/colour/size/angle/frame disappears (the frame index is read once)
+    fused_b = upd_b + DRAW_BYTES - 40 + (0 if animated_frac == 1.0 else 4 * (1 - animated_frac))
+    # compaction: every particle that dies pulls one in from the end of the array, 2 x 136 B (SURVEY §8(d))
+    move_bytes = 2 * SPAWN_BYTES * moved_per_launch
+    roof = {}
+    for nm, b, extra, units in (("update", upd_b, move_bytes, particles_per_launch), ("draw", DRAW_BYTES, 0, particles_per_launch),
+                                ("update_draw", fused_b, move_bytes, particles_per_launch), ("spawn", SPAWN_BYTES, 0, spawned_per_launch)):
+        ms = kern.get(nm, {}).get("ms_per_launch")
+        if not ms or not units:
+            continue
+        ach = (b * units + extra) / (ms * 1e-3) / 1e9
+        tr = (traffic or {}).get(nm, {}).get("bytes_per_unit")
+        roof[nm] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": tr * units if tr else None, "bytes_per_unit": b, "units_per_launch": units, "ms_per_launch": ms,
+                    "peak_source": peak_src}
+        if extra:
+            roof[nm]["moved_per_launch"] = moved_per_launch
+    return roof
+
+
+def kernel_deltas(t0, t1):
+    """{kernel: ms per launch, launches, total ms} between two readings of the context's per-kind event timers."""
+    out = {}
+    for k, nm in enumerate(("spawn", "update", "draw", "update_draw")):
+        dms, dn = t1[k][0] - t0[k][0], t1[k][1] - t0[k][1]
+        if dn:
+            out[nm] = {"ms_per_launch": dms / dn, "launches": int(dn), "ms_total": dms}
+    return out
+
+
+def quick_measure(ctx, stream, workload, steps, torch, rank=0, world=1):
+    """A short extra measurement of another workload on the same context (reported under `also`)."""
+    emitters, per, animated_frac, wl_name = build_population(ctx, workload, rank, world, 0)
     handles = ctx._handles(emitters)
-    n = int(ctx.batch_counts(emitters, handles).sum())
-    for _ in range(5):
+    churn = CHURN.get(workload)
+    spawn_each = churn["spawn"] // len(emitters) if churn else 0
+
+    def frame():
+        if churn:
+            ctx.batch_emit_once(emitters, [spawn_each] * len(emitters), handles)
         ctx.batch_update(emitters, DT, handles)
         ctx.batch_draw(emitters, handles)
+
+    for _ in range(churn["warm"] if churn else 5):
+        frame()
     ctx.sync()
+    n0 = int(ctx.batch_counts(emitters, handles).sum())
     t0 = [ctx.kernel_time(k) for k in range(4)]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         ev0.record(stream)
         for _ in range(steps):
-            ctx.batch_update(emitters, DT, handles)
-            ctx.batch_draw(emitters, handles)
+            frame()
         ctx.flush()
         ev1.record(stream)
     ctx.sync()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
     t1 = [ctx.kernel_time(k) for k in range(4)]
-    peak, _ = measured_peak_gbs()
-    upd_b = UPDATE_BYTES + (UPDATE_BYTES_ANIMATED - UPDATE_BYTES) * animated_frac
+    n1 = int(ctx.batch_counts(emitters, handles).sum())
+    n = (n0 + n1) // 2
+    kern = kernel_deltas(t0, t1)
+    moved = spawn_each * len(emitters)   # steady state: deaths per frame = spawns per frame
     out = {"workload": wl_name, "particles": n, "steps": steps, "ms_per_step": ms / steps, "value": n * steps / (ms * 1e-3),
-           "unit": "particles/s"}
-    for k, nm, b in ((1, "update", upd_b), (2, "draw", DRAW_BYTES), (3, "update_draw", upd_b + DRAW_BYTES - 40)):
-        dn = t1[k][1] - t0[k][1]
-        if dn:
-            ms_l = (t1[k][0] - t0[k][0]) / dn
-            out[nm] = {"ms_per_launch": ms_l, "achieved_gbs": b * n / (ms_l * 1e-3) / 1e9, "frac": b * n / (ms_l * 1e-3) / 1e9 / peak}
+           "unit": "particles/s", "kernels": kern,
+           "rooflines": kernel_rooflines(kern, n, animated_frac, moved, moved, measured_traffic().get(workload))}
+    if churn:
+        out["replaced_per_frame"] = moved / max(1, n)
     for e in emitters:
         e.release()
+    return out
+
+
+def vertices_to_host(ctx, e, n, torch, reps=3):
+    """Frames whose vertex stream is delivered to pinned host memory: drawn into one of two device buffers
+    (t3d_emitter_draw_to), copied out on the context's download stream while the next frame is computed."""
+    quad_bytes = 144
+    try:
+        avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+    except Exception:
+        avail = 0
+    n_host = 2 if avail > 6 * n * quad_bytes else 1
+    try:
+        dev = [torch.empty(n * 36, dtype=torch.float32, device="cuda") for _ in range(2)]
+        host = [torch.empty(n * 36, dtype=torch.float32, pin_memory=True) for _ in range(n_host)]
+    except Exception as err:   # not enough pinnable memory on this box: say so instead of failing the run
+        return {"unavailable": f"could not allocate the buffers: {err}"}
+    nbytes = n * quad_bytes
+    # PCIe roofline of this box: one plain copy of the same size
+    ctx.sync()
+    t0 = time.perf_counter()
+    ctx.copy_wait(ctx.copy_to_host_async(host[0].data_ptr(), dev[0].data_ptr(), nbytes))
+    pcie_gbs = nbytes / (time.perf_counter() - t0) / 1e9
+    tickets = [None, None]
+    t0 = time.perf_counter()
+    for k in range(reps):
+        b = k & 1
+        if tickets[b] is not None:
+            ctx.copy_wait(tickets[b])      # buffer b's previous frame has left the device: it may be redrawn
+        if n_host == 1 and tickets[b ^ 1] is not None:
+            ctx.copy_wait(tickets[b ^ 1])  # (one host buffer only: the previous frame must have landed before it is overwritten)
+            tickets[b ^ 1] = None
+        e.update(DT)
+        e.draw_to(dev[b].data_ptr(), n)
+        tickets[b] = ctx.copy_to_host_async(host[b % n_host].data_ptr(), dev[b].data_ptr(), nbytes)
+    for t in tickets:
+        if t is not None:
+            ctx.copy_wait(t)
+    dt = time.perf_counter() - t0
+    out = {"value": n * reps / dt, "unit": "particles/s", "d2h_bytes_per_step": nbytes, "steps": reps,
+           "pcie_d2h_gbs_measured": pcie_gbs, "pcie_roofline_particles_per_s": pcie_gbs * 1e9 / quad_bytes,
+           "frac_of_pcie": (n * reps / dt) / (pcie_gbs * 1e9 / quad_bytes), "host_buffers": n_host,
+           "what": "update + draw_to(device buffer k mod 2) + asynchronous copy of the 144 B/quad vertex stream to pinned host "
+                   "memory, overlapped with the next frame; bound by the PCIe link, not by the kernels"}
+    del dev, host
+    torch.cuda.empty_cache()
     return out
 
 
@@ -222,8 +315,8 @@ def run_cuda(args):
     pop_world = int(os.environ.get("T3D_BENCH_EMULATE_WORLD", world)) if world == 1 else world
     emitters, per, animated_frac, wl_name = build_population(ctx, workload, rank, pop_world, args.particles)
     handles = Context._handles(emitters)
-    churn = workload == "c5"
-    spawn_per_frame = (CHURN_SPAWN // world) // len(emitters) if churn else 0
+    churn = workload in CHURN
+    spawn_per_frame = CHURN[workload]["spawn"] // len(emitters) if churn else 0
 
     def frame():
         if churn:
@@ -238,7 +331,7 @@ def run_cuda(args):
             dist.barrier()
 
     # churn needs ~25 frames (the longest lifetime) before the live population is stationary
-    n_warm = max(30 if churn else 3, args.warmup)
+    n_warm = max(CHURN[workload]["warm"] if churn else 3, args.warmup)
     for _ in range(n_warm):
         frame()
     barrier()
@@ -267,12 +360,7 @@ def run_cuda(args):
     updates_done = (local_particles if not churn else int((counts0.sum() + counts1.sum()) // 2)) * args.steps
     local_updates_done = updates_done   # this rank's share: the per-launch rooflines below are rank 0's kernels
 
-    kern = {}
-    for k, nm in enumerate(("spawn", "update", "draw", "update_draw")):
-        dms, dn = t_after[k][0] - t_before[k][0], t_after[k][1] - t_before[k][1]
-        if nm == "update_draw" and not dn:
-            continue   # the fused launch only exists with T3D_FUSED=1
-        kern[nm] = {"ms_per_launch": (dms / dn) if dn else None, "launches": int(dn), "ms_total": dms}
+    kern = kernel_deltas(t_before, t_after)
 
     # ---- e2e: the same frames through the per-emitter public calls, host inputs in, host results out, every frame ----
     import numpy as np
@@ -307,21 +395,13 @@ def run_cuda(args):
     h2d1, d2h1 = ctx.transfer_bytes()
     matrix_bytes = 2 * 64 * len(emitters)   # the two float[16] the caller hands over per emitter per frame
 
-    # ---- e2e with the vertex stream copied to pinned host memory as well (PCIe-bound; reported for transparency) ----
+    # ---- e2e with the vertex stream delivered to pinned HOST memory every frame: what a renderer that submits from client
+    #      arrays (the reference's glDrawElements path, MeshBatch.cpp:299-303) would need.  Frame k is drawn straight into
+    #      device buffer k mod 2 (t3d_emitter_draw_to) and travels over PCIe on the download stream while frame k + 1 is
+    #      computed; the figure is PCIe-bound (144 B per quad). ----
     e2e_v = None
-    if args.vertices_to_host and workload == "c3":
-        n = local_particles
-        host = torch.empty((n, 4, 9), dtype=torch.float32, pin_memory=True).numpy()
-        barrier()
-        t0 = time.perf_counter()
-        reps = 2
-        for _ in range(reps):
-            emitters[0].update(DT)
-            emitters[0].draw()
-            emitters[0].vertices(out=host)
-        t_v = time.perf_counter() - t0
-        e2e_v = {"value": n * reps / t_v, "unit": "particles/s", "d2h_bytes_per_step": n * 144, "steps": reps}
-        del host
+    if not args.no_vertices_to_host and workload == "c3" and world == 1:
+        e2e_v = vertices_to_host(ctx, emitters[0], local_particles, torch)
 
     # ---- reduce over ranks: max time, sum of work (the only collective, after the run) ----
     from tractor3d_b200 import sharding
@@ -332,40 +412,18 @@ def run_cuda(args):
     updates_done, e2e_units, total_particles, live_after, launches = sm["updates"], sm["e2e_units"], sm["particles"], sm["live"], sm["launches"]
 
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        upd_bytes = UPDATE_BYTES + (UPDATE_BYTES_ANIMATED - UPDATE_BYTES) * animated_frac
         per_launch_particles = local_particles if not churn else local_updates_done / args.steps
-        roof = {}
-        traffic = measured_traffic()
-        # fused: the draw's 40 B re-read of position/colour/size/angle/frame disappears (the frame index is read once)
-        fused_bytes = upd_bytes + DRAW_BYTES - 40 + (0 if animated_frac == 1.0 else 4 * (1 - animated_frac))
-        for nm, b in (("update", upd_bytes), ("draw", DRAW_BYTES), ("update_draw", fused_bytes)):
-            ms = kern.get(nm, {}).get("ms_per_launch")
-            if ms:
-                ach = b * per_launch_particles / (ms * 1e-3) / 1e9
-                tr = traffic.get(nm, {}).get("bytes_per_unit") if workload == "c3" else None
-                roof[nm] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                            "traffic": tr * per_launch_particles if tr else None, "bytes_per_unit": b, "units_per_launch": per_launch_particles,
-                            "ms_per_launch": ms, "peak_source": peak_src}
-        if churn and "update" in roof:
-            # compaction: every particle that dies pulls one in from the end of the array, 2 x 136 B;
-            # in steady state deaths per frame = spawns per frame
-            moved = spawn_per_frame * len(emitters)
-            r = roof["update"]
-            r["moved_per_launch"] = moved
-            r["achieved"] = (upd_bytes * per_launch_particles + 2 * SPAWN_BYTES * moved) / (r["ms_per_launch"] * 1e-3) / 1e9
-            r["frac"] = r["achieved"] / peak
-        if churn and kern["spawn"]["ms_per_launch"]:
-            ms = kern["spawn"]["ms_per_launch"]
-            ach = SPAWN_BYTES * spawn_per_frame * len(emitters) / (ms * 1e-3) / 1e9
-            roof["spawn"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                             "bytes_per_unit": SPAWN_BYTES, "units_per_launch": spawn_per_frame * len(emitters), "ms_per_launch": ms}
+        moved = spawn_per_frame * len(emitters) if churn else 0
+        roof = kernel_rooflines(kern, per_launch_particles, animated_frac, moved, moved, measured_traffic().get(workload))
         dominant = max(roof, key=lambda k: kern[k]["ms_total"]) if roof else None
         value = updates_done / (ms_total * 1e-3)
         line = {
             "metric": "particle updates/s (one step = update + billboard draw of every live particle; quads/s is the same number)",
             "value": value, "unit": "particles/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            # c4 / c2: a fixed population split by emitter ownership (strong); c3 / c3d: one emitter per GPU, replicas only;
+            # c5: 1 Mi spawned per frame per GPU (weak).  The default N > 1 workload is c4: its N = 1 point is `also.c4`
+            # of the N = 1 line (the N = 1 headline is c3, the configuration the metric is quoted on).
             "scaling": "strong" if workload in ("c4", "c2") else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl_name, "particles_total": total_particles, "live_after": live_after,
@@ -382,16 +440,36 @@ def run_cuda(args):
                     "h2d_bytes_per_step": (h2d1 - h2d0) / e2e_steps + matrix_bytes, "d2h_bytes_per_step": (d2h1 - d2h0) / e2e_steps,
                     "steps": e2e_steps,
                     "what": "per-emitter set_node_world/set_camera_world/update/draw calls + live counts read back every frame; "
-                            "the vertex stream stays in HBM for the renderer (the reference hands it to GL, MeshBatch.cpp:299-303)"},
+                            "the vertex stream stays in HBM for a renderer that takes the device pointer or a mapped interop "
+                            "buffer (t3d_emitter_vertices / t3d_emitter_draw_to); see e2e_vertices_to_host for the host-buffer figure"},
             "e2e_vertices_to_host": e2e_v,
             "clocks": clocks,
         }
-        if world == 1 and workload == "c3" and not args.no_also:
-            # BASELINE configs[1] (1 024 emitters x 4 Ki, mixed parameter sets) measured beside the headline workload
-            for e in emitters:
-                e.release()
-            emitters = []
-            line["also"] = {"c2": quick_measure(ctx, stream, "c2", 50, torch)}
+        also_plan = []
+        if not args.no_also and workload == "c3" and world == 1:
+            also_plan = [("c2", 50), ("c3d", 30), ("c5", 40), ("c4", 12)]     # every BASELINE config on one GPU
+    else:
+        also_plan = []
+    if world > 1 and not args.no_also and workload == "c4":
+        also_plan = [("c5", 40)]                                              # 1 Mi spawned per frame PER GPU
+    also = {}
+    if also_plan:
+        for e in emitters:
+            e.release()
+        emitters = []
+        for wl, st in also_plan:
+            barrier()
+            r = quick_measure(ctx, stream, wl, st, torch, rank, world)
+            if world > 1:
+                mx, sm = sharding.reduce_stats({"ms": r["ms_per_step"]}, {"particles": r["particles"]})
+                r["ms_per_step_max_over_ranks"] = mx["ms"]
+                r["particles_all_ranks"] = sm["particles"]
+                r["value"] = sm["particles"] / (mx["ms"] * 1e-3)
+                r["note"] = "value = live particles of all ranks / slowest rank's step time; kernels and rooflines are rank 0's"
+            also[wl] = r
+    if rank == 0:
+        if also:
+            line["also"] = also
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single_core(args.cpu_particles)
         emit_line(line)
@@ -516,22 +594,23 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default=None, choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default=None, choices=["c2", "c3", "c3d", "c4", "c5"])
     ap.add_argument("--particles", type=int, default=0, help="override the population size of the workload")
     ap.add_argument("--cpu-particles", type=int, default=2 * MI, help="population of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the extra c2 measurement")
     ap.add_argument("--rotation", default="frozen", choices=["frozen", "per-particle"],
                     help="billboard rotation: the reference's frozen matrix (default) or a matrix per quad (experiments)")
-    ap.add_argument("--churn-spawn", type=int, default=None, help="c5: particles spawned per frame (all GPUs)")
+    ap.add_argument("--churn-spawn", type=int, default=None, help="c5: particles spawned per frame per GPU")
     ap.add_argument("--churn-energy", default=None, help="c5: energy range in ms, e.g. 500,2000")
-    ap.add_argument("--vertices-to-host", action="store_true", help="also time frames with the vertex stream copied to pinned host memory")
+    ap.add_argument("--no-vertices-to-host", action="store_true",
+                    help="skip the frames that also stream the vertices to pinned host memory (PCIe-bound e2e figure)")
     args = ap.parse_args()
-    global CHURN_SPAWN, CHURN_ENERGY
     if args.churn_spawn:
-        CHURN_SPAWN = args.churn_spawn
+        CHURN["c5"]["spawn"] = args.churn_spawn
     if args.churn_energy:
-        CHURN_ENERGY = tuple(float(x) for x in args.churn_energy.split(","))
+        CHURN["c5"]["energy"] = tuple(float(x) for x in args.churn_energy.split(","))
+        CHURN["c5"]["warm"] = max(30, int(CHURN["c5"]["energy"][1] / DT) + 10)
     if args.impl == "reference":
         args.steps = args.steps if args.steps is not None else 3
         args.warmup = args.warmup if args.warmup is not None else 1

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define T3D_ABI_VERSION 1
+#define T3D_ABI_VERSION 2
 
 typedef enum t3d_status {
     T3D_OK = 0,
@@ -65,6 +65,13 @@ enum {
 enum {
     T3D_ROT_FROZEN = 0,      /* reference-identical: one rotation matrix per process, latched from the first rotated quad (SB.cpp:339) */
     T3D_ROT_PER_PARTICLE = 1 /* intended behaviour: createRotation(right x up, angle_i) for every quad */
+};
+
+/* What draw writes per vertex. */
+enum {
+    T3D_VERTEX_WORLD = 0, /* SpriteBatch::SpriteVertex in world space, as the reference hands it to MeshBatch (SB.cpp:355-362) */
+    T3D_VERTEX_CLIP = 1   /* t3d_clip_vertex: position already multiplied by the node's view-projection matrix, i.e. the
+                             vertex shader's one line (res/shaders/sprite.vert:19, matrix set at PE.cpp:846-849) */
 };
 
 /* Emitter configuration = the reference's private configuration members, PE.h:824-877, in the
@@ -122,6 +129,10 @@ enum {
  * ({4i..4i+3} stitched by two degenerate indices) and is not materialised per frame. */
 typedef struct t3d_sprite_vertex { float x, y, z, u, v, r, g, b, a; } t3d_sprite_vertex;
 #define T3D_FLOATS_PER_QUAD 36
+/* T3D_VERTEX_CLIP: gl_Position = u_projectionMatrix * vec4(a_position, 1) (sprite.vert:19) evaluated per vertex,
+ * each component as the left-to-right sum x*m[r] + y*m[4+r] + z*m[8+r] + 1*m[12+r] (MathUtil.h:195-200). */
+typedef struct t3d_clip_vertex { float x, y, z, w, u, v, r, g, b, a; } t3d_clip_vertex;
+#define T3D_FLOATS_PER_CLIP_QUAD 40
 
 /* ---- library / context ------------------------------------------------------------------ */
 int t3d_abi_version(void);
@@ -134,6 +145,9 @@ int t3d_ctx_destroy(t3d_ctx* ctx);
 int t3d_ctx_flush(t3d_ctx* ctx);  /* launch everything queued; does not wait */
 int t3d_ctx_sync(t3d_ctx* ctx);   /* flush, then wait for the stream */
 int t3d_ctx_set_rotation_mode(t3d_ctx* ctx, int mode);            /* T3D_ROT_*; default FROZEN */
+/* T3D_VERTEX_*; default WORLD.  In CLIP mode draw() multiplies every vertex by the matrix given with
+ * t3d_emitter_set_view_projection (update and draw then go out as two launches: the fused pass writes SpriteVertex). */
+int t3d_ctx_set_vertex_mode(t3d_ctx* ctx, int mode);
 /* Latches the process-wide billboard rotation explicitly, as if the first rotated quad ever drawn
  * had axis u = right x up and this angle (SB.cpp:337-339). */
 int t3d_ctx_set_frozen_rotation(t3d_ctx* ctx, const float u[3], float angle);
@@ -183,6 +197,10 @@ int t3d_emitter_set_node_world(t3d_emitter* e, const float world[16]);
 /* getWorldMatrix() of the active camera's node (PE.cpp:860-864); only right=(m0,m1,m2), up=(m4,m5,m6) are used. */
 int t3d_emitter_set_camera_world(t3d_emitter* e, const float camera_world[16]);
 
+/* Node::getViewProjectionMatrix() of the emitter's node (PE.cpp:846-849); identity until set.  Used by
+ * T3D_VERTEX_CLIP draws and by the frustum test of t3d_emitter_set_culling. */
+int t3d_emitter_set_view_projection(t3d_emitter* e, const float view_projection[16]);
+
 /* ---- the hot path ------------------------------------------------------------------------- */
 int t3d_emitter_start(t3d_emitter* e);                   /* PE.cpp:270-274 */
 int t3d_emitter_stop(t3d_emitter* e);                    /* PE.h:272 */
@@ -195,6 +213,12 @@ int t3d_emitter_update(t3d_emitter* e, float elapsed_ms);             /* PE.cpp:
  * the draw is then queued without waiting, and writes no quads if every particle has died. */
 int t3d_emitter_draw(t3d_emitter* e, uint32_t* draw_calls);
 int t3d_emitter_get_count(t3d_emitter* e, uint32_t* count);           /* PE.h:306; flushes + reads back */
+/* draw() with the quads written straight into the caller's device buffer instead of the emitter's own vertex stream:
+ * a mapped graphics-interop buffer (cudaGraphicsResourceGetMappedPointer of a GL/Vulkan vertex buffer) or any device
+ * allocation.  `device_dst` must be 16-byte aligned and hold `dst_quads` quads of the context's vertex layout; the call
+ * fails with T3D_ERR_CAPACITY when the emitter may hold more live particles than that.  Quad i of the frame lands at
+ * quad index i, exactly as in t3d_emitter_vertices(); nothing is written beyond the frame's quads. */
+int t3d_emitter_draw_to(t3d_emitter* e, void* device_dst, size_t dst_quads, uint32_t* draw_calls);
 
 /* ---- batches: the same calls over many emitters, one launch per phase --------------------- */
 int t3d_batch_update(t3d_emitter* const* emitters, size_t n, float elapsed_ms);
@@ -211,6 +235,20 @@ int t3d_batch_set_transforms(t3d_emitter* const* emitters, size_t n, const float
  * reads the quad count back. */
 int t3d_emitter_vertices(t3d_emitter* e, const t3d_sprite_vertex** device_ptr, uint32_t* n_quads);
 int t3d_emitter_download_vertices(t3d_emitter* e, float* out, size_t max_quads, uint32_t* n_quads);
+/* Copies `bytes` from device memory to (pinned) host memory on the context's download stream, ordered after everything
+ * enqueued on the context so far, without blocking later launches: frame k's vertices travel over PCIe while frame k+1
+ * is computed (alternate between two t3d_emitter_draw_to buffers).  t3d_ctx_copy_wait blocks until that copy has landed. */
+int t3d_ctx_copy_to_host_async(t3d_ctx* ctx, void* host_dst, const void* device_src, size_t bytes, uint64_t* ticket);
+int t3d_ctx_copy_wait(t3d_ctx* ctx, uint64_t ticket);
+/* Bounding box of the emitter's live particles as the last update() left them: min / max over pos -+ size per axis (the
+ * engine leaves this out: "TODO: bounds ignore particle emitters", src/scene/Node.cpp:777-780).  Reduced inside the
+ * update kernel while the particle is in registers; enable it before the update whose box is wanted.  *valid = 0 when
+ * no update has run since enabling or no particle is live. */
+int t3d_emitter_enable_bounds(t3d_emitter* e, int on);
+int t3d_emitter_bounds(t3d_emitter* e, float lo[3], float hi[3], int* valid);
+/* on: draw() of this emitter is skipped (no quads, returns what the reference returns) while its last bounding box lies
+ * entirely outside the clip volume of its view-projection matrix.  Implies t3d_emitter_enable_bounds. */
+int t3d_emitter_set_culling(t3d_emitter* e, int on);
 /* The index buffer MeshBatch builds for n_quads billboards (TRIANGLE_STRIP, MB.cpp:117-141): quad 0 contributes
  * {0,1,2,3}; every later quad i the degenerate pair {4(i-1)+3, 4i} and then {4i..4i+3}: 6*n_quads-2 indices.
  * 32-bit (the reference's unsigned short indices cap a batch at 10 922 quads, MB.cpp:213-220).  The buffer is

@@ -1,6 +1,6 @@
 """The alternative code paths kept in the library (selected by environment variables read once per process)
-must stay parity-green too: the plain-LDG update kernel, ticket-ordered tiles, the blocked struct-of-arrays
-layout, the LSU copy-out of the draw kernel, the fused update+draw launch.  Each runs a slice of the parity suite
+must stay parity-green too: other tile shapes of the update kernel (2 or 4 particles per thread), ticket-ordered
+tiles, the LSU copy-out of the draw kernel, the fused update+draw launch on and off.  Each runs a slice of the parity suite
 in a fresh process."""
 import os
 import subprocess
@@ -12,16 +12,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 CASES = [
-    {"T3D_UPDATE_VARIANT": "v4t128s4b3"},
-    {"T3D_UPDATE_VARIANT": "v4t128s4b3", "T3D_UPDATE_TICKET": "1"},
-    {"T3D_UPDATE_VARIANT": "a4t64s8b3"},
-    {"T3D_LAYOUT_BLOCK": "512"},
-    {"T3D_LAYOUT_BLOCK": "256", "T3D_UPDATE_VARIANT": "v2t256s4b4"},
+    {"T3D_UPDATE_VARIANT": "u2t256s8b2"},
+    {"T3D_UPDATE_VARIANT": "u2t128s12b4", "T3D_UPDATE_TICKET": "1"},
+    {"T3D_UPDATE_VARIANT": "u4t128s8b2"},
     {"T3D_DRAW_VARIANT": "lsu"},
     {"T3D_FUSED": "0"},
     {"T3D_FUSED": "1"},
-    {"T3D_FUSED": "1", "T3D_FUSED_VARIANT": "f4t64s10b2"},
-    {"T3D_FUSED": "1", "T3D_FUSED_VARIANT": "g4t128s8b2", "T3D_LAYOUT_BLOCK": "512"},
+    {"T3D_FUSED": "1", "T3D_UPDATE_TICKET": "1"},
+    {"T3D_FUSED": "1", "T3D_FUSED_VARIANT": "f2t192s6b2"},
+    {"T3D_FUSED": "1", "T3D_FUSED_VARIANT": "f2t128s12b3"},
 ]
 
 

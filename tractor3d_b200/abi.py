@@ -18,6 +18,9 @@ BLEND_NONE, BLEND_ALPHA, BLEND_ADDITIVE, BLEND_MULTIPLIED = range(4)
 RNG_LIBC, RNG_STREAM, RNG_DEVICE = range(3)
 # billboard rotation modes
 ROT_FROZEN, ROT_PER_PARTICLE = range(2)
+# vertex layouts of draw
+VERTEX_WORLD, VERTEX_CLIP = range(2)
+FLOATS_PER_CLIP_QUAD = 40
 
 # column order of the struct-of-arrays particle record
 COL_COLOR_START, COL_COLOR_END, COL_COLOR = 0, 4, 8
@@ -125,6 +128,9 @@ PROTOTYPES = {
     "t3d_ctx_flush": (C.c_int, [_vp]),
     "t3d_ctx_sync": (C.c_int, [_vp]),
     "t3d_ctx_set_rotation_mode": (C.c_int, [_vp, C.c_int]),
+    "t3d_ctx_set_vertex_mode": (C.c_int, [_vp, C.c_int]),
+    "t3d_ctx_copy_to_host_async": (C.c_int, [_vp, _vp, _vp, C.c_size_t, _P(C.c_uint64)]),
+    "t3d_ctx_copy_wait": (C.c_int, [_vp, C.c_uint64]),
     "t3d_ctx_set_frozen_rotation": (C.c_int, [_vp, _P(C.c_float), C.c_float]),
     "t3d_ctx_get_frozen_rotation": (C.c_int, [_vp, _P(C.c_float), _P(C.c_int)]),
     "t3d_ctx_reset_statics": (C.c_int, [_vp]),
@@ -148,6 +154,11 @@ PROTOTYPES = {
     "t3d_emitter_pending_draws": (C.c_int, [_vp, _P(C.c_size_t)]),
     "t3d_emitter_set_node_world": (C.c_int, [_vp, _P(C.c_float)]),
     "t3d_emitter_set_camera_world": (C.c_int, [_vp, _P(C.c_float)]),
+    "t3d_emitter_set_view_projection": (C.c_int, [_vp, _P(C.c_float)]),
+    "t3d_emitter_draw_to": (C.c_int, [_vp, _vp, C.c_size_t, _P(C.c_uint32)]),
+    "t3d_emitter_enable_bounds": (C.c_int, [_vp, C.c_int]),
+    "t3d_emitter_bounds": (C.c_int, [_vp, _P(C.c_float), _P(C.c_float), _P(C.c_int)]),
+    "t3d_emitter_set_culling": (C.c_int, [_vp, C.c_int]),
     "t3d_emitter_start": (C.c_int, [_vp]),
     "t3d_emitter_stop": (C.c_int, [_vp]),
     "t3d_emitter_is_started": (C.c_int, [_vp, _P(C.c_int)]),

@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstring>
+
 #include "t3d_internal.h"
 
 namespace t3d
@@ -85,17 +87,16 @@ __device__ __forceinline__ Rot3 load_frozen(const FrozenRotation* __restrict__ f
     return r;
 }
 
-// One billboard quad in SpriteBatch's vertex layout (SB.cpp:292-363 through PE.cpp:866-882): 4 vertices x
-// {position, uv, colour} = 36 floats written as nine float4.  rotationPoint = (0.5, 0.5) (PE.cpp:855).
-// get_frozen() yields the latched rotation; it is only called for a rotated quad in T3D_ROT_FROZEN mode.
+// The four corners of one billboard (SB.cpp:292-352 through PE.cpp:866-882), in world space.
+// rotationPoint = (0.5, 0.5) (PE.cpp:855).  get_frozen() yields the latched rotation; it is only called for a rotated
+// quad in T3D_ROT_FROZEN mode.
 template <class GetFrozen>
-__device__ __forceinline__ void expand_quad(const float pos[3], const float color[4], float size, float angle, float u1,
-                                            float v1, float u2, float v2, const float right[3], const float up[3],
-                                            int rot_mode, GetFrozen get_frozen, float4* __restrict__ o)
+__device__ __forceinline__ void quad_corners(const float pos[3], float size, float angle, const float right[3], const float up[3],
+                                             int rot_mode, GetFrozen get_frozen, float p0[3], float p1[3], float p2[3], float p3[3])
 {
     const float width = size, height = size;
     // SB.cpp:306-324
-    float p0[3], p1[3], p2[3], p3[3], tfw[3];
+    float tfw[3];
     const float hw = width * 0.5f, hh = height * 0.5f;
 #pragma unroll
     for (int k = 0; k < 3; ++k)
@@ -149,7 +150,17 @@ __device__ __forceinline__ void expand_quad(const float pos[3], const float colo
             p[2] += rp[2];
         }
     }
-    // SB.cpp:355-359: v0=(p0,u1,v1) v1=(p1,u2,v1) v2=(p2,u1,v2) v3=(p3,u2,v2), particle colour on all four.
+}
+
+// One billboard quad in SpriteBatch's vertex layout: 4 vertices x {position, uv, colour} = 36 floats written as nine
+// float4.  SB.cpp:355-359: v0=(p0,u1,v1) v1=(p1,u2,v1) v2=(p2,u1,v2) v3=(p3,u2,v2), particle colour on all four.
+template <class GetFrozen>
+__device__ __forceinline__ void expand_quad(const float pos[3], const float color[4], float size, float angle, float u1,
+                                            float v1, float u2, float v2, const float right[3], const float up[3],
+                                            int rot_mode, GetFrozen get_frozen, float4* __restrict__ o)
+{
+    float p0[3], p1[3], p2[3], p3[3];
+    quad_corners(pos, size, angle, right, up, rot_mode, get_frozen, p0, p1, p2, p3);
     o[0] = make_float4(p0[0], p0[1], p0[2], u1);
     o[1] = make_float4(v1, color[0], color[1], color[2]);
     o[2] = make_float4(color[3], p1[0], p1[1], p1[2]);
@@ -161,20 +172,146 @@ __device__ __forceinline__ void expand_quad(const float pos[3], const float colo
     o[8] = make_float4(color[0], color[1], color[2], color[3]);
 }
 
-// Address of particle i's word in column 0 of an emitter; its word in column c lies c * stride words further.
-//   block_shift == 0  plain struct-of-arrays: stride = slab capacity.
-//   block_shift == k  blocked struct-of-arrays: 2^k consecutive particles keep their 34 columns in one contiguous
-//                     chunk (stride = 2^k), so a tile's working set is one contiguous region of HBM.
-// Groups of 4 consecutive particles (index multiple of 4) never straddle a block.
-__device__ __forceinline__ uint32_t* particle_base(uint32_t* cols, uint32_t block_shift, uint32_t i)
+// The same quad with the vertex shader's projection already applied (res/shaders/sprite.vert:19:
+// gl_Position = u_projectionMatrix * vec4(a_position, 1), the matrix being the node's view-projection matrix,
+// PE.cpp:846-849): 4 vertices x {x, y, z, w, u, v, r, g, b, a} = 40 floats written as ten float4.  Each component is
+// the left-to-right sum of MathUtil::transformVector4 (MathUtil.h:195-200) with w = 1.
+template <class GetFrozen>
+__device__ __forceinline__ void expand_quad_clip(const float pos[3], const float color[4], float size, float angle, float u1,
+                                                 float v1, float u2, float v2, const float right[3], const float up[3],
+                                                 int rot_mode, GetFrozen get_frozen, const float* __restrict__ vp,
+                                                 float4* __restrict__ o)
 {
-    if (block_shift == 0) return cols + i;
-    const uint32_t blk = i >> block_shift, lane = i & ((1u << block_shift) - 1u);
-    return cols + ((size_t)blk * T3D_NUM_COLUMNS << block_shift) + lane;
+    float p[4][3];
+    quad_corners(pos, size, angle, right, up, rot_mode, get_frozen, p[0], p[1], p[2], p[3]);
+    float c[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+    {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            c[q][r] = p[q][0] * vp[r] + p[q][1] * vp[4 + r] + p[q][2] * vp[8 + r] + 1.0f * vp[12 + r];
+    }
+    o[0] = make_float4(c[0][0], c[0][1], c[0][2], c[0][3]);
+    o[1] = make_float4(u1, v1, color[0], color[1]);
+    o[2] = make_float4(color[2], color[3], c[1][0], c[1][1]);
+    o[3] = make_float4(c[1][2], c[1][3], u2, v1);
+    o[4] = make_float4(color[0], color[1], color[2], color[3]);
+    o[5] = make_float4(c[2][0], c[2][1], c[2][2], c[2][3]);
+    o[6] = make_float4(u1, v2, color[0], color[1]);
+    o[7] = make_float4(color[2], color[3], c[3][0], c[3][1]);
+    o[8] = make_float4(c[3][2], c[3][3], u2, v2);
+    o[9] = make_float4(color[0], color[1], color[2], color[3]);
 }
-__device__ __forceinline__ const uint32_t* particle_base(const uint32_t* cols, uint32_t block_shift, uint32_t i)
+
+// V x 32-bit streaming accesses (evict-first: every byte of the particle state is touched once per frame).
+template <int V>
+struct Vec;
+template <>
+struct Vec<4>
 {
-    return particle_base(const_cast<uint32_t*>(cols), block_shift, i);
+    static __device__ __forceinline__ void ld(const uint32_t* p, float* a)
+    {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(p));
+        a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+    }
+    static __device__ __forceinline__ void ld(const uint32_t* p, int* a)
+    {
+        const int4 v = __ldcs(reinterpret_cast<const int4*>(p));
+        a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+    }
+    static __device__ __forceinline__ void st(uint32_t* p, const float* a)
+    {
+        __stcs(reinterpret_cast<float4*>(p), make_float4(a[0], a[1], a[2], a[3]));
+    }
+    static __device__ __forceinline__ void st(uint32_t* p, const int* a)
+    {
+        __stcs(reinterpret_cast<int4*>(p), make_int4(a[0], a[1], a[2], a[3]));
+    }
+};
+template <>
+struct Vec<2>
+{
+    static __device__ __forceinline__ void ld(const uint32_t* p, float* a)
+    {
+        const float2 v = __ldcs(reinterpret_cast<const float2*>(p));
+        a[0] = v.x; a[1] = v.y;
+    }
+    static __device__ __forceinline__ void ld(const uint32_t* p, int* a)
+    {
+        const int2 v = __ldcs(reinterpret_cast<const int2*>(p));
+        a[0] = v.x; a[1] = v.y;
+    }
+    static __device__ __forceinline__ void st(uint32_t* p, const float* a) { __stcs(reinterpret_cast<float2*>(p), make_float2(a[0], a[1])); }
+    static __device__ __forceinline__ void st(uint32_t* p, const int* a) { __stcs(reinterpret_cast<int2*>(p), make_int2(a[0], a[1])); }
+};
+__device__ __forceinline__ float ld_f(const uint32_t* p) { return __uint_as_float(__ldcs(p)); }
+__device__ __forceinline__ int ld_i(const uint32_t* p) { return (int)__ldcs(p); }
+
+// ---- asynchronous copies -------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+{
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Life records in shared memory.  A warp owns 32 * V consecutive particles; lane t's V records form row t of the
+// warp's stage (V * 64 bytes).  The warp fetches the 32 * V * 64 contiguous bytes cooperatively (chunk g = 16 bytes, lane j copies
+// chunks j, j + 32, ...: 512 contiguous bytes per cp.async instruction) and every lane reads its own row back.  Rows are
+// a multiple of the 128-byte bank period apart, so chunk p of a row is stored at position p ^ (row & 7): the eight lanes
+// of a quarter-warp then hit eight different bank groups on both sides.
+template <int V>
+__device__ __forceinline__ uint32_t rec_chunk_offset(uint32_t row, uint32_t p)
+{
+    return row * (V * 64u) + ((p ^ (row & 7u)) << 4);
+}
+// issue: the warp's `n` records starting at `rec_g` (n <= 32 * V; records past n are not fetched)
+template <int V>
+__device__ __forceinline__ void rec_issue(unsigned char* stage_warp, const uint32_t* rec_g, uint32_t n, uint32_t lane)
+{
+#pragma unroll
+    for (int i = 0; i < V * 4; ++i)
+    {
+        const uint32_t g = (uint32_t)i * 32u + lane; // chunk of the warp's run
+        if ((g >> 2) < n) cp_async16(stage_warp + rec_chunk_offset<V>(g / (V * 4u), g % (V * 4u)), rec_g + g * 4u);
+    }
+}
+// read back: record l of this lane's row, as 16 words
+template <int V>
+__device__ __forceinline__ void rec_read(const unsigned char* stage_warp, uint32_t lane, int l, uint32_t* w)
+{
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+    {
+        const uint4 v = *reinterpret_cast<const uint4*>(stage_warp + rec_chunk_offset<V>(lane, (uint32_t)(l * 4 + c)));
+        w[c * 4 + 0] = v.x; w[c * 4 + 1] = v.y; w[c * 4 + 2] = v.z; w[c * 4 + 3] = v.w;
+    }
+}
+
+// Order-preserving map of a float onto an unsigned integer (for atomic min / max of bounding boxes).
+__device__ __host__ __forceinline__ uint32_t float_order(float f)
+{
+#if defined(__CUDA_ARCH__)
+    const uint32_t b = __float_as_uint(f);
+#else
+    uint32_t b;
+    memcpy(&b, &f, 4);
+#endif
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __host__ __forceinline__ float float_unorder(uint32_t u)
+{
+    const uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
 }
 
 // Which emitter of the launch owns global tile `tile`: the last item with tile_begin <= tile.  Every step is a

@@ -9,19 +9,42 @@
 namespace t3d
 {
 
-// Particles per tile of the update kernel = particles per thread x threads per CTA of the selected variant
+// Particles per tile of the update kernel = particles per thread x threads per CTA x groups of the selected variant
 // (t3d_update.cu).
 int update_tile_size();
 int draw_sub(uint32_t n_items);
 int draw_tile_size(uint32_t n_items); // quads per draw CTA for a launch over n_items emitters
 const char* update_variant_name();
-// Spawn and draw: one particle per thread.
-constexpr int kSpawnThreads = 256;
+constexpr int kSpawnThreads = 256; // spawn and draw: one particle per thread
 constexpr int kDrawThreads = 256;
 constexpr int kMaxSmemFrames = 256; // sprite uv tables up to this many frames are staged in shared memory
 
-// Segment alignment inside a slab, in particles (128 B per column).
-constexpr uint32_t kSegmentAlign = 32;
+// Segment alignment inside a slab, in particles (a warp of the update kernel copies the life records of 64
+// consecutive particles as one 4 KB run).
+constexpr uint32_t kSegmentAlign = 64;
+
+// ---- particle storage in HBM (private to the library; the ABI exchanges the 34 T3D_COL_* columns) ----------
+// The 34 words of ParticleEmitter::Particle (PE.h:792-822) are split by how the frame touches them:
+//   rw  : 15 columns of `stride` words, struct-of-arrays -- everything update() rewrites (or draw() reads) every frame.
+//         A thread owns consecutive particles, so every access is a unit-stride vector access.
+//   rec : one 64-byte LIFE RECORD per particle, array-of-structs -- the 15 words a particle is born with and keeps
+//         (colour and size end points, acceleration, spin, initial energy).  The update streams them with warp-wide
+//         contiguous copies; swap-with-last removal (PE.cpp:821-830) moves a record as two full 32-byte sectors
+//         instead of 15 scattered words that each cost a sector fill and a write-back.
+//   rot : one 16-byte record per particle: rotation axis and speed, only read by emitters that can rotate
+//         (PE.cpp:757-763; no stock .particle file sets them).
+enum : int
+{
+    RW_ENERGY = 0, RW_POS = 1, RW_VEL = 4, RW_ANGLE = 7, RW_COLOR = 8, RW_SIZE = 12, RW_TIME_ON_FRAME = 13, RW_FRAME = 14,
+    RW_COUNT = 15
+};
+enum : int
+{
+    REC_COLOR_START = 0, REC_COLOR_END = 4, REC_ACC = 8, REC_SPIN = 11, REC_ENERGY_START = 12, REC_SIZE_START = 13,
+    REC_SIZE_END = 14, REC_PAD = 15, REC_WORDS = 16
+};
+enum : int { ROT_AXIS = 0, ROT_SPEED = 3, ROT_WORDS = 4 };
+constexpr uint32_t kBytesPerParticle = (RW_COUNT + REC_WORDS + ROT_WORDS) * 4; // 140
 
 // Live count and spawn serial of one emitter.  Two copies: a kernel reads cnt[parity] and writes
 // cnt[parity ^ 1], so no CTA of a launch can observe the value another CTA of the same launch writes.
@@ -36,8 +59,9 @@ enum : uint32_t
 {
     kFlagAnimated = 1u,   // _spriteAnimated
     kFlagLooped = 2u,     // _spriteLooped
-    kFlagMayRotate = 4u,  // some live particle may have rotationSpeed != 0: axis/rotSpeed columns are read
+    kFlagMayRotate = 4u,  // some live particle may have rotationSpeed != 0: the rotation records are read
     kFlagMaySpin = 8u,    // some live particle may have angle != 0 (used by the frozen-rotation latch)
+    kFlagBounds = 16u,    // the update also reduces the emitter's bounding box (t3d_emitter_bounds)
 };
 
 // Spawn-time configuration: the float members of t3d_emitter_params the spawn kernel needs.
@@ -56,25 +80,43 @@ struct SpawnParams
     uint64_t rng_seed;
 };
 
+// Where one emitter's particles live: its segment of the slab's three arrays.
+struct Storage
+{
+    uint32_t* rw;    // column 0 of the segment; column c starts at rw + c * stride
+    uint32_t* rec;   // life record of particle i: the REC_WORDS words at rec + REC_WORDS * i (64-byte aligned)
+    uint32_t* rot;   // rotation record of particle i: the ROT_WORDS words at rot + ROT_WORDS * i (16-byte aligned)
+    uint32_t stride; // words between rw columns: the slab capacity
+    uint32_t seg_capacity; // padded segment size: any particle index below it lies inside the slab and may be read
+};
+
 // Host-written part of the per-emitter device record.
 struct EmitterConst
 {
-    uint32_t* cols;   // column 0 of this emitter's segment; column c starts at cols + c * stride
+    Storage st;
     float* vtx;       // vertex stream of this emitter: 36 floats per quad
     const float* uv;  // frame_count * 4 floats (u1, v1, u2, v2)
-    uint32_t stride;  // words between columns: the slab capacity (plain SoA) or the block size (blocked SoA)
-    uint32_t block_shift; // 0: plain SoA.  k > 0: blocked SoA, 2^k particles x 34 columns contiguous per block
     uint32_t capacity;
     uint32_t flags;
     uint32_t frame_count;
     float percent_per_frame;
     float frame_duration_secs;
+    uint32_t pad;
     SpawnParams sp;
+};
+
+// Bounding box of the live particles after an update, reduced by the update kernel with 64-bit atomicMax on
+// (launch epoch << 32 | order-preserving float bits): a newer launch's first contribution overrides whatever an older
+// launch left, so nothing has to be reset between frames.  lo[] holds the complement of the encoding (max = min).
+struct EmitterBounds
+{
+    unsigned long long lo[3], hi[3];
 };
 
 struct EmitterDev
 {
     EmitterCounts cnt[2]; // device-owned
+    EmitterBounds bounds; // device-owned
     EmitterConst c;       // host-owned, re-uploaded when dirty
 };
 
@@ -83,19 +125,15 @@ struct EmitterDev
 struct UpdateItem
 {
     EmitterDev* dev;
-    uint32_t* cols;       // copied from the emitter's record so a CTA can start loading after ONE dependent fetch
+    Storage st;           // copied from the emitter's record so a CTA can start loading after ONE dependent fetch
     float elapsed_ms;
     uint32_t parity;      // which cnt[] copy is current on entry
     uint32_t tile_begin;
-    uint32_t stride;
-    uint32_t block_shift;
-    uint32_t seg_capacity; // padded segment size: any slot below it lies inside the slab and may be read
     uint32_t flags;
     uint32_t frame_count;
     float percent_per_frame;
     float frame_duration_secs;
     uint32_t n_tiles;     // tiles of this launch that belong to the emitter (the kernel checks that they cover the live count)
-    uint32_t pad;
 };
 
 struct SpawnItem
@@ -113,19 +151,18 @@ struct SpawnItem
 struct DrawItem
 {
     EmitterDev* dev;
-    const uint32_t* cols; // copied from the emitter's record: one dependent fetch, then the loads can start
-    float* vtx;
+    const uint32_t* rw;   // copied from the emitter's record: one dependent fetch, then the loads can start
+    float* vtx;           // where this draw's quads go: the emitter's own stream, or the caller's buffer (t3d_emitter_draw_to)
     const float* uv;
     uint32_t parity;
     uint32_t tile_begin;
     uint32_t stride;
-    uint32_t block_shift;
     uint32_t seg_capacity;
     uint32_t frame_count;
+    uint32_t n_tiles;     // as in UpdateItem
     float right[3];
     float up[3];
-    uint32_t n_tiles;     // as in UpdateItem
-    uint32_t pad;
+    float vp[16];         // view-projection matrix (PE.cpp:846-849); only read by the clip-space draw (T3D_VERTEX_CLIP)
 };
 
 // Process-wide billboard rotation of the reference (SB.cpp:339), kept on the device.
@@ -136,19 +173,31 @@ struct FrozenRotation
     int pad[3];
 };
 
-// ---- launch wrappers (t3d_kernels.cu) ----
+// ---- launch wrappers (t3d_kernels.cu, t3d_update.cu) ----
 void launch_spawn(void* stream, const SpawnItem* items, uint32_t n_items, uint32_t total_tiles);
 // `fault`: device word the kernels OR into when a grid does not cover the live count it finds (kFaultUpdateGrid ...).
 constexpr uint32_t kFaultUpdateGrid = 1u, kFaultDrawGrid = 2u;
-void launch_update(void* stream, const UpdateItem* items, uint32_t n_items, uint32_t total_tiles,
-                   unsigned long long* tile_status, uint32_t* ticket, uint32_t ticket_base, uint32_t epoch, uint32_t* fault);
+struct UpdateLaunch
+{
+    const UpdateItem* items;
+    const DrawItem* ditems; // fused launches only
+    uint32_t n_items, total_tiles;
+    unsigned long long* tile_status;
+    uint32_t* ticket;
+    uint32_t ticket_base;
+    uint32_t epoch;
+    uint32_t* fault;
+    int rot_mode;
+    const FrozenRotation* frozen;
+    bool bounds; // some emitter of the launch wants its bounding box
+};
+void launch_update(void* stream, const UpdateLaunch& L);
+void launch_update_draw(void* stream, const UpdateLaunch& L);
+// vertex_mode: T3D_VERTEX_WORLD (SpriteVertex, 36 floats per quad) or T3D_VERTEX_CLIP (40 floats per quad)
 void launch_draw(void* stream, const DrawItem* items, uint32_t n_items, uint32_t total_tiles, int rot_mode,
-                 const FrozenRotation* frozen, uint32_t* fault);
+                 const FrozenRotation* frozen, uint32_t* fault, int vertex_mode);
 int fused_tile_size();
 int fused_mode(); // 1 always, 0 never, -1 automatic
-void launch_update_draw(void* stream, const UpdateItem* items, const DrawItem* ditems, uint32_t n_items, uint32_t total_tiles,
-                        unsigned long long* tile_status, uint32_t epoch, int rot_mode, const FrozenRotation* frozen,
-                        uint32_t* fault);
 void launch_latch(void* stream, const DrawItem* items, uint32_t n_items, FrozenRotation* frozen);
 struct CountQuery
 {
@@ -162,11 +211,9 @@ void launch_gather_counts(void* stream, const CountQuery* q, uint32_t n, uint32_
 // MeshBatch's triangle-strip index pattern for n_quads quads (MB.cpp:117-141), 6*n_quads-2 indices.
 void launch_strip_indices(void* stream, uint32_t* out, uint64_t n_indices);
 void launch_triangle_indices(void* stream, uint32_t* out, uint64_t n_indices);
-// Device layout <-> the ABI's exchange layout (T3D_NUM_COLUMNS columns of `host_stride` words).
-void launch_export_state(void* stream, const uint32_t* cols, uint32_t stride, uint32_t block_shift, uint32_t n, uint32_t* out,
-                         uint32_t host_stride);
-void launch_import_state(void* stream, uint32_t* cols, uint32_t stride, uint32_t block_shift, uint32_t n, const uint32_t* in,
-                         uint32_t host_stride);
+// Device storage <-> the ABI's exchange layout (T3D_NUM_COLUMNS columns of `host_stride` words).
+void launch_export_state(void* stream, const Storage& st, uint32_t n, uint32_t* out, uint32_t host_stride);
+void launch_import_state(void* stream, const Storage& st, uint32_t n, const uint32_t* in, uint32_t host_stride);
 
 // The counter-based generator of T3D_RNG_DEVICE (host + device): 32-bit integer hash of (seed, particle serial,
 // draw index).  key = the part that is constant per particle; one draw = key + (j+1)*C through the lowbias32

@@ -44,6 +44,11 @@ struct DrawSource
 
 __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __restrict__ items, uint32_t n_items)
 {
+    // The tile's life records and rotation records are assembled in shared memory and leave as two contiguous bulk
+    // stores (the appended range [count0, count0 + n) is contiguous in both arrays); the rw words go out column by
+    // column, one coalesced 128-byte line per warp per column.
+    __shared__ __align__(128) uint32_t s_rec[kSpawnThreads * REC_WORDS];
+    __shared__ __align__(128) uint32_t s_rot[kSpawnThreads * ROT_WORDS];
     const uint32_t tile = blockIdx.x;
     const SpawnItem& it = items[find_item(items, n_items, tile, gridDim.x)];
     EmitterDev* d = it.dev;
@@ -54,14 +59,18 @@ __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __rest
     // PE.cpp:293-296: never go over particleCountMax.
     const uint32_t room = cap - count0;
     const uint32_t n = it.request < room ? it.request : room;
-    const uint32_t i = (tile - it.tile_begin) * kSpawnThreads + threadIdx.x;
+    const uint32_t tile_first = (tile - it.tile_begin) * kSpawnThreads;
+    const uint32_t i = tile_first + threadIdx.x;
     if (i == 0)
     {
         d->cnt[parity ^ 1].count = count0 + n;
         d->cnt[parity ^ 1].serial = serial0 + n;
     }
-    if (i >= n) return;
+    if (tile_first >= n) return;
+    const Storage st = d->c.st;
 
+    if (i < n)
+    {
     const SpawnParams& P = d->c.sp;
     DrawSource src;
     src.p = it.draws ? it.draws + (it.offsets ? it.offsets[i] : i * it.draw_stride) : nullptr;
@@ -132,35 +141,45 @@ __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __rest
     uint32_t frame = 0; // :357-364
     if (P.frame_random_offset > 0) frame = (uint32_t)src.next() % P.frame_random_offset;
 
-    const size_t stride = d->c.stride;
-    uint32_t* const cols = particle_base(d->c.cols, d->c.block_shift, count0 + i); // this particle's word of column 0
-    const size_t slot = 0;
-    auto F = [&](int c, float v) { cols[(size_t)c * stride + slot] = __float_as_uint(v); };
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-    {
-        F(T3D_COL_COLOR_START + k, cs[k]);
-        F(T3D_COL_COLOR_END + k, ce[k]);
-        F(T3D_COL_COLOR + k, cs[k]); // :314
-    }
+    // what update() rewrites every frame: 15 rw columns
+    uint32_t* const rw = st.rw + (count0 + i);
+    const size_t stride = st.stride;
+    auto F = [&](int c, float v) { rw[(size_t)c * stride] = __float_as_uint(v); };
+    rw[(size_t)RW_ENERGY * stride] = (uint32_t)energy;
 #pragma unroll
     for (int k = 0; k < 3; ++k)
     {
-        F(T3D_COL_POSITION + k, pos[k]);
-        F(T3D_COL_VELOCITY + k, vel[k]);
-        F(T3D_COL_ACCELERATION + k, acc[k]);
-        F(T3D_COL_ROTATION_AXIS + k, axis[k]);
+        F(RW_POS + k, pos[k]);
+        F(RW_VEL + k, vel[k]);
     }
-    cols[(size_t)T3D_COL_ENERGY_START * stride + slot] = (uint32_t)energy;
-    cols[(size_t)T3D_COL_ENERGY * stride + slot] = (uint32_t)energy;
-    F(T3D_COL_SIZE_START, size_start);
-    F(T3D_COL_SIZE_END, size_end);
-    F(T3D_COL_SIZE, size_start);
-    F(T3D_COL_ROT_PER_PARTICLE_SPEED, spin);
-    F(T3D_COL_ROTATION_SPEED, rot_speed);
-    F(T3D_COL_ANGLE, angle);
-    F(T3D_COL_TIME_ON_FRAME, 0.0f); // :365
-    cols[(size_t)T3D_COL_FRAME * stride + slot] = frame;
+    F(RW_ANGLE, angle);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) F(RW_COLOR + k, cs[k]); // :314
+    F(RW_SIZE, size_start);
+    F(RW_TIME_ON_FRAME, 0.0f); // :365
+    rw[(size_t)RW_FRAME * stride] = frame;
+    // what the particle keeps for life: the 64-byte record and the rotation record, through shared memory
+    uint4* const r4 = reinterpret_cast<uint4*>(s_rec + threadIdx.x * REC_WORDS);
+    auto U = [](float v) { return __float_as_uint(v); };
+    r4[0] = make_uint4(U(cs[0]), U(cs[1]), U(cs[2]), U(cs[3]));
+    r4[1] = make_uint4(U(ce[0]), U(ce[1]), U(ce[2]), U(ce[3]));
+    r4[2] = make_uint4(U(acc[0]), U(acc[1]), U(acc[2]), U(spin));
+    r4[3] = make_uint4((uint32_t)energy, U(size_start), U(size_end), 0u);
+    *reinterpret_cast<uint4*>(s_rot + threadIdx.x * ROT_WORDS) = make_uint4(U(axis[0]), U(axis[1]), U(axis[2]), U(rot_speed));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const uint32_t nt = (n - tile_first) < (uint32_t)kSpawnThreads ? (n - tile_first) : (uint32_t)kSpawnThreads;
+        const size_t p0 = (size_t)count0 + tile_first;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(st.rec + p0 * REC_WORDS),
+                     "r"((uint32_t)__cvta_generic_to_shared(s_rec)), "r"(nt * (uint32_t)(REC_WORDS * 4)) : "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(st.rot + p0 * ROT_WORDS),
+                     "r"((uint32_t)__cvta_generic_to_shared(s_rot)), "r"(nt * (uint32_t)(ROT_WORDS * 4)) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory must outlive the stores' reads
+    }
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -169,13 +188,16 @@ __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __rest
 // OUT = 0: the tile's vertices are copied from shared memory with coalesced 128-bit streaming stores.
 // OUT = 1: one thread hands the tile to the TMA engine (cp.async.bulk shared -> global, SASS UBLKCP), which
 //          writes the nq * 144 contiguous bytes while the other warps are already gone.
-template <int OUT, int DSUB>
+// CLIP:    vertices carry the projected position (sprite.vert:19 applied; 40 floats per quad) instead of SpriteVertex.
+template <int OUT, int DSUB, bool CLIP>
 __global__ void __launch_bounds__(kDrawThreads)
     k_draw(const DrawItem* __restrict__ items, uint32_t n_items, int rot_mode, const FrozenRotation* __restrict__ frozen,
            uint32_t* __restrict__ fault)
 {
-    __shared__ __align__(128) float s_vtx[kDrawThreads * T3D_FLOATS_PER_QUAD];
+    constexpr int QF = CLIP ? T3D_FLOATS_PER_CLIP_QUAD : T3D_FLOATS_PER_QUAD;
+    __shared__ __align__(128) float s_vtx[kDrawThreads * QF];
     __shared__ float s_uv[kMaxSmemFrames * 4];
+    __shared__ float s_vp[16];
 
     // One CTA draws DSUB consecutive sub-tiles of kDrawThreads quads: the descriptor fetch, the uv table and the
     // live count are paid once per DSUB * 256 quads, and the next sub-tile's particles are requested before the
@@ -187,8 +209,7 @@ __global__ void __launch_bounds__(kDrawThreads)
     const uint32_t first_tile = (tile - it.tile_begin) * (kDrawThreads * DSUB);
     const uint32_t N = d->cnt[it.parity].count;
     const uint32_t seg_capacity = it.seg_capacity;
-    const uint32_t* const cols0 = it.cols;
-    const uint32_t bshift = it.block_shift;
+    const uint32_t* const rw = it.rw;
     const size_t stride = it.stride;
 
     struct Quad
@@ -201,13 +222,13 @@ __global__ void __launch_bounds__(kDrawThreads)
     {
         if (i < seg_capacity)
         {
-            const uint32_t* cols = particle_base(cols0, bshift, i);
+            const uint32_t* cols = rw + i;
             auto LF = [&](int c) { return __ldcs(reinterpret_cast<const float*>(cols + (size_t)c * stride)); };
-            q.pos[0] = LF(T3D_COL_POSITION); q.pos[1] = LF(T3D_COL_POSITION + 1); q.pos[2] = LF(T3D_COL_POSITION + 2);
-            q.size = LF(T3D_COL_SIZE);
-            q.color[0] = LF(T3D_COL_COLOR); q.color[1] = LF(T3D_COL_COLOR + 1); q.color[2] = LF(T3D_COL_COLOR + 2); q.color[3] = LF(T3D_COL_COLOR + 3);
-            q.angle = LF(T3D_COL_ANGLE);
-            q.frame = __ldcs(cols + (size_t)T3D_COL_FRAME * stride);
+            q.pos[0] = LF(RW_POS); q.pos[1] = LF(RW_POS + 1); q.pos[2] = LF(RW_POS + 2);
+            q.size = LF(RW_SIZE);
+            q.color[0] = LF(RW_COLOR); q.color[1] = LF(RW_COLOR + 1); q.color[2] = LF(RW_COLOR + 2); q.color[3] = LF(RW_COLOR + 3);
+            q.angle = LF(RW_ANGLE);
+            q.frame = __ldcs(cols + (size_t)RW_FRAME * stride);
         }
     };
     Quad cur = {};
@@ -218,6 +239,7 @@ __global__ void __launch_bounds__(kDrawThreads)
     const bool uv_in_smem = frame_count <= (uint32_t)kMaxSmemFrames;
     if (uv_in_smem)
         for (uint32_t q = tid; q < frame_count * 4u; q += kDrawThreads) s_uv[q] = uv_g[q];
+    if (CLIP && tid < 16) s_vp[tid] = it.vp[tid];
     if (first_tile == 0 && tid == 0)
     {
         const_cast<EmitterDev*>(d)->cnt[0].drawn = N;
@@ -254,12 +276,16 @@ __global__ void __launch_bounds__(kDrawThreads)
 
         const float right[3] = { it.right[0], it.right[1], it.right[2] };
         const float up[3] = { it.up[0], it.up[1], it.up[2] };
-        expand_quad(pos, color, size, angle, u1, v1, u2, v2, right, up, rot_mode, [&] { return load_frozen(frozen); },
-                    reinterpret_cast<float4*>(s_vtx + tid * T3D_FLOATS_PER_QUAD));
+        if (CLIP)
+            expand_quad_clip(pos, color, size, angle, u1, v1, u2, v2, right, up, rot_mode, [&] { return load_frozen(frozen); }, s_vp,
+                             reinterpret_cast<float4*>(s_vtx + tid * QF));
+        else
+            expand_quad(pos, color, size, angle, u1, v1, u2, v2, right, up, rot_mode, [&] { return load_frozen(frozen); },
+                        reinterpret_cast<float4*>(s_vtx + tid * QF));
     }
-    // The sub-tile's vertices: nq quads * 144 B, contiguous in the emitter's vertex stream (16-byte aligned).
+    // The sub-tile's vertices: nq quads, contiguous in the emitter's vertex stream (16-byte aligned).
     const uint32_t nq = (N - first) < (uint32_t)kDrawThreads ? (N - first) : (uint32_t)kDrawThreads;
-    float4* __restrict__ dst = reinterpret_cast<float4*>(it.vtx + (size_t)first * T3D_FLOATS_PER_QUAD);
+    float4* __restrict__ dst = reinterpret_cast<float4*>(it.vtx + (size_t)first * QF);
     if (OUT == 1)
     {
         // Make this thread's shared-memory writes visible to the async proxy, then let one thread issue the bulk store.
@@ -268,7 +294,7 @@ __global__ void __launch_bounds__(kDrawThreads)
         if (tid == 0)
         {
             const uint32_t src = (uint32_t)__cvta_generic_to_shared(s_vtx);
-            const uint32_t bytes = nq * (uint32_t)(T3D_FLOATS_PER_QUAD * sizeof(float));
+            const uint32_t bytes = nq * (uint32_t)(QF * sizeof(float));
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -277,7 +303,7 @@ __global__ void __launch_bounds__(kDrawThreads)
     {
         __syncthreads();
         const float4* src4 = reinterpret_cast<const float4*>(s_vtx);
-        for (uint32_t q = tid; q < nq * 9u; q += kDrawThreads) __stcs(dst + q, src4[q]);
+        for (uint32_t q = tid; q < nq * (uint32_t)(QF / 4); q += kDrawThreads) __stcs(dst + q, src4[q]);
     }
     cur = nxt;
     }
@@ -300,9 +326,8 @@ __global__ void __launch_bounds__(256) k_latch(const DrawItem* __restrict__ item
         const EmitterDev* d = it.dev;
         if (!(d->c.flags & kFlagMaySpin)) continue;
         const uint32_t N = d->cnt[it.parity].count;
-        const uint32_t* ang0 = d->c.cols + (size_t)T3D_COL_ANGLE * d->c.stride;
-        const uint32_t shift = d->c.block_shift;
-        auto ANG = [&](uint32_t i) { return __uint_as_float(*particle_base(ang0, shift, i)); };
+        const uint32_t* ang0 = it.rw + (size_t)RW_ANGLE * it.stride;
+        auto ANG = [&](uint32_t i) { return __uint_as_float(ang0[i]); };
         for (uint32_t base = 0; base < N; base += 256)
         {
             if (threadIdx.x == 0) s_min = 0xffffffffu;
@@ -338,8 +363,18 @@ void launch_spawn(void* stream, const SpawnItem* items, uint32_t n_items, uint32
     k_spawn<<<total_tiles, kSpawnThreads, 0, (cudaStream_t)stream>>>(items, n_items);
 }
 
+template <int OUT, bool CLIP>
+static void launch_draw_sub(cudaStream_t st, int sub, uint32_t total_tiles, const DrawItem* items, uint32_t n_items, int rot_mode,
+                            const FrozenRotation* frozen, uint32_t* fault)
+{
+    if (sub == 1) k_draw<OUT, 1, CLIP><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
+    else if (sub == 2) k_draw<OUT, 2, CLIP><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
+    else if (sub == 4) k_draw<OUT, 4, CLIP><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
+    else k_draw<OUT, 8, CLIP><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
+}
+
 void launch_draw(void* stream, const DrawItem* items, uint32_t n_items, uint32_t total_tiles, int rot_mode,
-                 const FrozenRotation* frozen, uint32_t* fault)
+                 const FrozenRotation* frozen, uint32_t* fault, int vertex_mode)
 {
     const int sub = draw_sub(n_items);
     static int mode = -1;
@@ -349,20 +384,12 @@ void launch_draw(void* stream, const DrawItem* items, uint32_t n_items, uint32_t
         mode = (env && !strcmp(env, "lsu")) ? 0 : 1;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == 1)
-    {
-        if (sub == 1) k_draw<1, 1><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
-        else if (sub == 2) k_draw<1, 2><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
-        else if (sub == 4) k_draw<1, 4><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
-        else k_draw<1, 8><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
-    }
+    if (vertex_mode == T3D_VERTEX_CLIP)
+        launch_draw_sub<1, true>(st, sub, total_tiles, items, n_items, rot_mode, frozen, fault);
+    else if (mode == 1)
+        launch_draw_sub<1, false>(st, sub, total_tiles, items, n_items, rot_mode, frozen, fault);
     else
-    {
-        if (sub == 1) k_draw<0, 1><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
-        else if (sub == 2) k_draw<0, 2><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
-        else if (sub == 4) k_draw<0, 4><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
-        else k_draw<0, 8><<<total_tiles, kDrawThreads, 0, st>>>(items, n_items, rot_mode, frozen, fault);
-    }
+        launch_draw_sub<0, false>(st, sub, total_tiles, items, n_items, rot_mode, frozen, fault);
 }
 
 // Sub-tiles of 256 quads per draw CTA.  Measured on B200 (profiles/r1_draw_subtile_sweep.txt): 4 is best when the
@@ -441,34 +468,60 @@ void launch_strip_indices(void* stream, uint32_t* out, uint64_t n_indices)
     if (n_indices) k_strip_indices<<<(unsigned)((n_indices + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n_indices);
 }
 
-// Exchange with the ABI's layout (download_state / upload_state): one thread per particle, all columns.
+// Exchange with the ABI's layout (download_state / upload_state): one thread per particle, the 34 T3D_COL_* columns
+// on one side, the rw columns and the two records on the other.
+__device__ __forceinline__ uint32_t* storage_word(const Storage& st, uint32_t i, int c)
+{
+    // where word T3D_COL_* c of particle i lives
+    auto RW = [&](int col) { return st.rw + (size_t)col * st.stride + i; };
+    auto REC = [&](int w) { return st.rec + (size_t)i * REC_WORDS + w; };
+    auto ROT = [&](int w) { return st.rot + (size_t)i * ROT_WORDS + w; };
+    if (c < T3D_COL_COLOR_END) return REC(REC_COLOR_START + (c - T3D_COL_COLOR_START));
+    if (c < T3D_COL_COLOR) return REC(REC_COLOR_END + (c - T3D_COL_COLOR_END));
+    if (c < T3D_COL_POSITION) return RW(RW_COLOR + (c - T3D_COL_COLOR));
+    if (c < T3D_COL_VELOCITY) return RW(RW_POS + (c - T3D_COL_POSITION));
+    if (c < T3D_COL_ACCELERATION) return RW(RW_VEL + (c - T3D_COL_VELOCITY));
+    if (c < T3D_COL_ROTATION_AXIS) return REC(REC_ACC + (c - T3D_COL_ACCELERATION));
+    if (c < T3D_COL_ENERGY_START) return ROT(ROT_AXIS + (c - T3D_COL_ROTATION_AXIS));
+    switch (c)
+    {
+    case T3D_COL_ENERGY_START: return REC(REC_ENERGY_START);
+    case T3D_COL_ENERGY: return RW(RW_ENERGY);
+    case T3D_COL_SIZE_START: return REC(REC_SIZE_START);
+    case T3D_COL_SIZE_END: return REC(REC_SIZE_END);
+    case T3D_COL_SIZE: return RW(RW_SIZE);
+    case T3D_COL_ROT_PER_PARTICLE_SPEED: return REC(REC_SPIN);
+    case T3D_COL_ROTATION_SPEED: return ROT(ROT_SPEED);
+    case T3D_COL_ANGLE: return RW(RW_ANGLE);
+    case T3D_COL_TIME_ON_FRAME: return RW(RW_TIME_ON_FRAME);
+    default: return RW(RW_FRAME);
+    }
+}
 template <bool EXPORT>
-__global__ void k_exchange_state(uint32_t* cols, uint32_t stride, uint32_t block_shift, uint32_t n, uint32_t* host_layout,
-                                 uint32_t host_stride)
+__global__ void k_exchange_state(Storage st, uint32_t n, uint32_t* host_layout, uint32_t host_stride)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t* p = particle_base(cols, block_shift, i);
-#pragma unroll 2
+#pragma unroll
     for (int c = 0; c < T3D_NUM_COLUMNS; ++c)
     {
+        uint32_t* w = storage_word(st, i, c);
         if (EXPORT)
-            host_layout[(size_t)c * host_stride + i] = p[(size_t)c * stride];
+            host_layout[(size_t)c * host_stride + i] = *w;
         else
-            p[(size_t)c * stride] = host_layout[(size_t)c * host_stride + i];
+            *w = host_layout[(size_t)c * host_stride + i];
     }
+    if (!EXPORT) st.rec[(size_t)i * REC_WORDS + REC_PAD] = 0u;
 }
 
-void launch_export_state(void* stream, const uint32_t* cols, uint32_t stride, uint32_t block_shift, uint32_t n, uint32_t* out,
-                         uint32_t host_stride)
+void launch_export_state(void* stream, const Storage& st, uint32_t n, uint32_t* out, uint32_t host_stride)
 {
-    if (n) k_exchange_state<true><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(const_cast<uint32_t*>(cols), stride, block_shift, n, out, host_stride);
+    if (n) k_exchange_state<true><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(st, n, out, host_stride);
 }
 
-void launch_import_state(void* stream, uint32_t* cols, uint32_t stride, uint32_t block_shift, uint32_t n, const uint32_t* in,
-                         uint32_t host_stride)
+void launch_import_state(void* stream, const Storage& st, uint32_t n, const uint32_t* in, uint32_t host_stride)
 {
-    if (n) k_exchange_state<false><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(cols, stride, block_shift, n, const_cast<uint32_t*>(in), host_stride);
+    if (n) k_exchange_state<false><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(st, n, const_cast<uint32_t*>(in), host_stride);
 }
 
 } // namespace t3d

@@ -22,6 +22,7 @@
 #include <string>
 #include <vector>
 
+#include "t3d_device.cuh"
 #include "t3d_host.h"
 #include "t3d_internal.h"
 
@@ -68,11 +69,18 @@ enum { KERNEL_SPAWN = 0, KERNEL_UPDATE = 1, KERNEL_DRAW = 2, KERNEL_UPDATE_DRAW 
 
 struct Slab
 {
-    uint32_t* cols{ nullptr }; // T3D_NUM_COLUMNS * capacity words
-    float* vtx{ nullptr };     // capacity * 36 floats, allocated at the first draw that needs it
+    // one allocation: RW_COUNT columns of `capacity` words, then `capacity` 64-byte life records, then `capacity`
+    // 16-byte rotation records (t3d_internal.h)
+    uint32_t* base{ nullptr };
+    float* vtx{ nullptr };     // capacity * vtx_floats floats, allocated at the first draw that needs it
+    uint32_t vtx_floats{ 0 };  // floats per quad the vertex storage was sized for (36 world, 40 clip)
     uint32_t capacity{ 0 };
-    uint32_t used{ 0 };
+    uint32_t used{ 0 };        // high-water mark: [used, capacity) has never been handed out
     uint32_t live_emitters{ 0 };
+    std::vector<std::pair<uint32_t, uint32_t>> free_ranges; // (offset, particles) returned by destroyed emitters, sorted, coalesced
+    uint32_t* rw() const { return base; }
+    uint32_t* rec() const { return base + (size_t)RW_COUNT * capacity; }
+    uint32_t* rot() const { return base + (size_t)(RW_COUNT + REC_WORDS) * capacity; }
 };
 
 struct StagingSlot
@@ -98,6 +106,8 @@ struct PendingOp
     bool host_draws;
     float world[16];
     float right[3], up[3];
+    float vp[16];         // draw: the node's view-projection matrix (clip-space vertices)
+    float* draw_dst;      // draw: the caller's device buffer (t3d_emitter_draw_to), or nullptr for the emitter's own stream
 };
 
 } // namespace
@@ -110,7 +120,6 @@ struct t3d_ctx
 
     std::vector<Slab> slabs;
     uint32_t next_slab_particles{ 1u << 20 };
-    uint32_t block_shift{ 0 }; // particle storage layout: 0 plain SoA, k blocked SoA with 2^k-particle blocks
 
     std::vector<EmitterDev*> dev_chunks; // arena of device records, kDevChunk per allocation
     uint32_t dev_used{ 0 };
@@ -132,6 +141,7 @@ struct t3d_ctx
     bool frozen_latched{ false };
     float frozen_m[16];
     int rot_mode{ T3D_ROT_FROZEN };
+    int vertex_mode{ T3D_VERTEX_WORLD };
 
     double running_time{ 0 }; // PE.cpp:720, one per process in the reference, one per context here
 
@@ -178,6 +188,12 @@ struct t3d_ctx
     uint32_t* fault_dev{ nullptr };
     uint32_t fault{ 0 };
 
+    // Downloads that overlap the next frame (t3d_ctx_copy_to_host_async): a stream of their own, one event per copy.
+    cudaStream_t download_stream{ nullptr };
+    cudaEvent_t download_fence{ nullptr };
+    std::vector<cudaEvent_t> download_done; // ticket t (1-based) -> download_done[t - 1]
+    uint64_t download_waited{ 0 };          // every ticket <= this has been waited for
+
     uint32_t* readback_host{ nullptr }; // pinned scratch for counts
     size_t readback_cap{ 0 };
     uint32_t* readback_dev{ nullptr };
@@ -214,11 +230,16 @@ struct t3d_emitter
     uint32_t parity{ 0 };
     bool const_dirty{ true }, uv_dirty{ true };
     bool may_rotate{ false }, may_spin{ false };
+    bool want_bounds{ false }, culling{ false };
+    uint32_t bounds_epoch{ 0 }; // launch epoch of the last update that reduced this emitter's box (0: none yet)
+    bool has_vp{ false };
+    float view_projection[16];
     uint32_t count_ub{ 0 };     // upper bound of the live count (exact when count_exact)
     bool count_exact{ true };
     bool queued{ false };
     bool held{ false }; // has an update in ctx->held (launch deferred, see flush)
-    bool last_draw_empty{ true }; // the last draw() submitted no quads (inactive or no particles)
+    bool last_draw_empty{ true }; // the last draw() submitted no quads (inactive, no particles, or culled)
+    float* last_draw_dst{ nullptr }; // where the last draw's quads went when not into the emitter's own stream (t3d_emitter_draw_to)
     uint64_t emitted_total{ 0 };  // particles ever asked to spawn (upper bound of those spawned)
     uint64_t emitted_at_update{ 0 }; // emitted_total when the previous update was queued
     // Milliseconds for which at least one particle is GUARANTEED to be alive: a particle that certainly spawned
@@ -297,36 +318,84 @@ static int staging_release(t3d_ctx* c, StagingSlot* s)
 
 static int alloc_segment(t3d_ctx* c, uint32_t capacity, int* slab_out, uint32_t* offset_out, uint32_t* padded_out)
 {
-    const uint32_t align = std::max<uint32_t>(kSegmentAlign, c->block_shift ? (1u << c->block_shift) : 0u);
+    const uint32_t align = kSegmentAlign;
     uint32_t padded = (std::max(capacity, 1u) + align - 1) / align * align;
+    *padded_out = padded;
+    // first fit: a range a destroyed emitter gave back, else the untouched tail of a slab
     for (size_t i = 0; i < c->slabs.size(); ++i)
     {
         Slab& s = c->slabs[i];
-        if (s.cols && s.capacity - s.used >= padded)
+        if (!s.base) continue;
+        for (size_t r = 0; r < s.free_ranges.size(); ++r)
+        {
+            if (s.free_ranges[r].second < padded) continue;
+            *slab_out = (int)i;
+            *offset_out = s.free_ranges[r].first;
+            s.free_ranges[r].first += padded;
+            s.free_ranges[r].second -= padded;
+            if (!s.free_ranges[r].second) s.free_ranges.erase(s.free_ranges.begin() + (ptrdiff_t)r);
+            s.live_emitters++;
+            return T3D_OK;
+        }
+        if (s.capacity - s.used >= padded)
         {
             *slab_out = (int)i;
             *offset_out = s.used;
-            *padded_out = padded;
             s.used += padded;
             s.live_emitters++;
             return T3D_OK;
         }
     }
     uint64_t want = std::max<uint64_t>(padded, c->next_slab_particles);
-    const uint64_t gran = std::max<uint64_t>(1024, c->block_shift ? (1ull << c->block_shift) : 0ull);
-    want = (want + gran - 1) / gran * gran;
+    want = (want + 1023) / 1024 * 1024;
     if (want > 0x7fffffffull) return fail(T3D_ERR_CAPACITY, "emitter capacity %u exceeds the 2^31 particle slab limit", capacity);
     Slab s;
     s.capacity = (uint32_t)want;
-    T3D_CUDA(cudaMalloc((void**)&s.cols, (size_t)T3D_NUM_COLUMNS * s.capacity * sizeof(uint32_t)));
+    T3D_CUDA(cudaMalloc((void**)&s.base, (size_t)kBytesPerParticle * s.capacity));
     s.used = padded;
     s.live_emitters = 1;
-    c->slabs.push_back(s);
+    // reuse the table entry of a slab that was given back
+    size_t idx = c->slabs.size();
+    for (size_t i = 0; i < c->slabs.size(); ++i)
+        if (!c->slabs[i].base) idx = i;
+    if (idx == c->slabs.size()) c->slabs.push_back(s);
+    else c->slabs[idx] = s;
     if (c->next_slab_particles < (1u << 26)) c->next_slab_particles *= 2;
-    *slab_out = (int)c->slabs.size() - 1;
+    *slab_out = (int)idx;
     *offset_out = 0;
-    *padded_out = padded;
     return T3D_OK;
+}
+
+// Returns an emitter's segment to its slab: merged with neighbouring free ranges; a range that reaches the high-water
+// mark lowers it instead.  The last emitter of a slab gives the whole allocation back.
+static void free_segment(t3d_ctx* c, int slab, uint32_t offset, uint32_t padded)
+{
+    Slab& s = c->slabs[slab];
+    if (--s.live_emitters == 0)
+    {
+        if (s.base) cudaFree(s.base);
+        if (s.vtx) cudaFree(s.vtx);
+        s = Slab();
+        return;
+    }
+    auto& fr = s.free_ranges;
+    auto it = std::lower_bound(fr.begin(), fr.end(), std::make_pair(offset, 0u));
+    it = fr.insert(it, std::make_pair(offset, padded));
+    if (it + 1 != fr.end() && it->first + it->second == (it + 1)->first)
+    {
+        it->second += (it + 1)->second;
+        fr.erase(it + 1);
+    }
+    if (it != fr.begin() && (it - 1)->first + (it - 1)->second == it->first)
+    {
+        (it - 1)->second += it->second;
+        it = fr.erase(it) - 1;
+    }
+    if (it->first + it->second == s.used)
+    {
+        s.used = it->first;
+        fr.erase(it);
+    }
 }
 
 static int alloc_dev_record(t3d_ctx* c, EmitterDev** out)
@@ -398,15 +467,16 @@ static void fill_const(const t3d_emitter* e, EmitterConst* k)
     const t3d_ctx* c = e->ctx;
     const Slab& s = c->slabs[e->slab];
     memset(k, 0, sizeof(*k));
-    // blocked SoA: segment offsets are whole blocks, and a block holds all 34 columns of its particles
-    k->cols = c->block_shift ? s.cols + (size_t)e->seg_offset * T3D_NUM_COLUMNS : s.cols + e->seg_offset;
-    k->block_shift = c->block_shift;
-    k->vtx = s.vtx ? s.vtx + (size_t)e->seg_offset * T3D_FLOATS_PER_QUAD : nullptr;
+    k->st.rw = s.rw() + e->seg_offset;
+    k->st.rec = s.rec() + (size_t)e->seg_offset * REC_WORDS;
+    k->st.rot = s.rot() + (size_t)e->seg_offset * ROT_WORDS;
+    k->st.stride = s.capacity;
+    k->st.seg_capacity = e->seg_capacity;
+    k->vtx = s.vtx ? s.vtx + (size_t)e->seg_offset * s.vtx_floats : nullptr;
     k->uv = e->uv_dev;
-    k->stride = c->block_shift ? (1u << c->block_shift) : s.capacity;
     k->capacity = e->p.particle_count_max;
     k->flags = (e->p.sprite_animated ? kFlagAnimated : 0u) | (e->p.sprite_looped ? kFlagLooped : 0u) |
-               (e->may_rotate ? kFlagMayRotate : 0u) | (e->may_spin ? kFlagMaySpin : 0u);
+               (e->may_rotate ? kFlagMayRotate : 0u) | (e->may_spin ? kFlagMaySpin : 0u) | (e->want_bounds ? kFlagBounds : 0u);
     k->frame_count = e->frame_count;
     k->percent_per_frame = e->percent_per_frame;
     k->frame_duration_secs = e->frame_duration_secs;
@@ -641,10 +711,7 @@ static void build_update_items(std::vector<PendingOp>& ops, UpdateItem* items, C
         const EmitterConst& ec = e->hc; // current: sync_const ran just before
         memset(&it, 0, sizeof(it));
         it.dev = e->dev;
-        it.cols = ec.cols;
-        it.stride = ec.stride;
-        it.block_shift = ec.block_shift;
-        it.seg_capacity = e->seg_capacity;
+        it.st = ec.st;
         it.flags = ec.flags;
         it.frame_count = ec.frame_count;
         it.percent_per_frame = ec.percent_per_frame;
@@ -687,6 +754,19 @@ static int begin_scan_epoch(t3d_ctx* c, uint32_t tiles)
     return T3D_OK;
 }
 
+// Emitters of the launch that want their bounding box: remembers the epoch their box will carry.
+static bool mark_bounds(t3d_ctx* c, std::vector<PendingOp>& ops)
+{
+    bool any = false;
+    for (PendingOp& op : ops)
+        if (op.e->want_bounds)
+        {
+            op.e->bounds_epoch = c->epoch;
+            any = true;
+        }
+    return any;
+}
+
 static int launch_updates(t3d_ctx* c, std::vector<PendingOp>& ops)
 {
     const uint32_t n_items = (uint32_t)ops.size();
@@ -702,8 +782,17 @@ static int launch_updates(t3d_ctx* c, std::vector<PendingOp>& ops)
     T3D_TRY(begin_scan_epoch(c, tiles));
     T3D_TRY(staging_submit(c, slot, total_bytes));
     T3D_TRY(time_begin(c, KERNEL_UPDATE));
-    launch_update(c->stream, reinterpret_cast<const UpdateItem*>(slot->dev), n_items, tiles, c->tile_status, c->ticket,
-                  c->ticket_base, c->epoch, c->fault_dev);
+    UpdateLaunch L{};
+    L.items = reinterpret_cast<const UpdateItem*>(slot->dev);
+    L.n_items = n_items;
+    L.total_tiles = tiles;
+    L.tile_status = c->tile_status;
+    L.ticket = c->ticket;
+    L.ticket_base = c->ticket_base;
+    L.epoch = c->epoch;
+    L.fault = c->fault_dev;
+    L.bounds = mark_bounds(c, ops);
+    launch_update(c->stream, L);
     T3D_CUDA(cudaGetLastError());
     T3D_TRY(time_end(c, KERNEL_UPDATE));
     c->ticket_base += tiles;
@@ -713,18 +802,26 @@ static int launch_updates(t3d_ctx* c, std::vector<PendingOp>& ops)
     return T3D_OK;
 }
 
-// Vertex storage is allocated per slab the first time one of its emitters is drawn.
+// Vertex storage is allocated per slab the first time one of its emitters is drawn into it (draws into a caller's
+// buffer need none); a later switch to the wider clip-space vertex reallocates it.
 static int ensure_vertex_storage(t3d_ctx* c, std::vector<PendingOp>& ops)
 {
+    const uint32_t want = c->vertex_mode == T3D_VERTEX_CLIP ? T3D_FLOATS_PER_CLIP_QUAD : T3D_FLOATS_PER_QUAD;
     for (PendingOp& op : ops)
     {
+        if (op.draw_dst) continue;
         Slab& s = c->slabs[op.e->slab];
-        if (!s.vtx)
+        if (s.vtx && s.vtx_floats >= want) continue;
+        if (s.vtx)
         {
-            T3D_CUDA(cudaMalloc((void**)&s.vtx, (size_t)s.capacity * T3D_FLOATS_PER_QUAD * sizeof(float)));
-            for (t3d_emitter* o : c->emitters)
-                if (o->slab == op.e->slab) o->const_dirty = true;
+            T3D_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(s.vtx);
+            s.vtx = nullptr;
         }
+        T3D_CUDA(cudaMalloc((void**)&s.vtx, (size_t)s.capacity * want * sizeof(float)));
+        s.vtx_floats = want;
+        for (t3d_emitter* o : c->emitters)
+            if (o->slab == op.e->slab) o->const_dirty = true;
     }
     for (PendingOp& op : ops) T3D_TRY(sync_const(op.e));
     return T3D_OK;
@@ -742,13 +839,13 @@ static void build_draw_items(std::vector<PendingOp>& ops, DrawItem* items, uint3
         const EmitterConst& ec = e->hc; // current: sync_const ran just before
         memset(&it, 0, sizeof(it));
         it.dev = e->dev;
-        it.cols = ec.cols;
-        it.vtx = ec.vtx;
+        it.rw = ec.st.rw;
+        it.vtx = op.draw_dst ? op.draw_dst : ec.vtx;
         it.uv = ec.uv;
-        it.stride = ec.stride;
-        it.block_shift = ec.block_shift;
-        it.seg_capacity = e->seg_capacity;
+        it.stride = ec.st.stride;
+        it.seg_capacity = ec.st.seg_capacity;
         it.frame_count = ec.frame_count;
+        memcpy(it.vp, op.vp, sizeof(it.vp));
         it.parity = e->parity;
         it.tile_begin = tiles;
         memcpy(it.right, op.right, 12);
@@ -791,7 +888,8 @@ static int launch_draws(t3d_ctx* c)
         }
     }
     T3D_TRY(time_begin(c, KERNEL_DRAW));
-    launch_draw(c->stream, reinterpret_cast<const DrawItem*>(slot->dev), n_items, tiles, c->rot_mode, c->frozen_dev, c->fault_dev);
+    launch_draw(c->stream, reinterpret_cast<const DrawItem*>(slot->dev), n_items, tiles, c->rot_mode, c->frozen_dev, c->fault_dev,
+                c->vertex_mode);
     T3D_CUDA(cudaGetLastError());
     T3D_TRY(time_end(c, KERNEL_DRAW));
     c->launches++;
@@ -804,6 +902,7 @@ static int launch_draws(t3d_ctx* c)
 static bool can_fuse(const t3d_ctx* c)
 {
     if (c->held.empty() || c->held.size() != c->pending.size()) return false;
+    if (c->vertex_mode != T3D_VERTEX_WORLD) return false; // the fused pass writes SpriteVertex
     bool any_spin = false;
     for (size_t k = 0; k < c->held.size(); ++k)
     {
@@ -833,10 +932,22 @@ static int launch_fused_frame(t3d_ctx* c)
     T3D_TRY(begin_scan_epoch(c, tiles));
     T3D_TRY(staging_submit(c, slot, total_bytes));
     T3D_TRY(time_begin(c, KERNEL_UPDATE_DRAW));
-    launch_update_draw(c->stream, reinterpret_cast<const UpdateItem*>(slot->dev),
-                       reinterpret_cast<const DrawItem*>(slot->dev + items_bytes + queries_bytes), n_items, tiles, c->tile_status,
-                       c->epoch, c->rot_mode, c->frozen_dev, c->fault_dev);
+    UpdateLaunch L{};
+    L.items = reinterpret_cast<const UpdateItem*>(slot->dev);
+    L.ditems = reinterpret_cast<const DrawItem*>(slot->dev + items_bytes + queries_bytes);
+    L.n_items = n_items;
+    L.total_tiles = tiles;
+    L.tile_status = c->tile_status;
+    L.ticket = c->ticket;
+    L.ticket_base = c->ticket_base;
+    L.epoch = c->epoch;
+    L.fault = c->fault_dev;
+    L.rot_mode = c->rot_mode;
+    L.frozen = c->frozen_dev;
+    L.bounds = mark_bounds(c, c->held);
+    launch_update_draw(c->stream, L);
     T3D_CUDA(cudaGetLastError());
+    c->ticket_base += tiles;
     T3D_TRY(time_end(c, KERNEL_UPDATE_DRAW));
     c->launches++;
     T3D_TRY(submit_feedback(c, c->held, reinterpret_cast<const CountQuery*>(slot->dev + items_bytes)));
@@ -1182,13 +1293,6 @@ int t3d_ctx_create(int device, void* cuda_stream, t3d_ctx** out)
         if (!(env && env[0] == '0') && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
             c->copy_stream = nullptr; // descriptors then travel on the launching stream
     }
-    // T3D_LAYOUT_BLOCK=2^k selects the blocked struct-of-arrays layout (measured equal to plain SoA on B200).
-    if (const char* env = getenv("T3D_LAYOUT_BLOCK"))
-    {
-        const int b = atoi(env);
-        for (uint32_t k = 5; k <= 12; ++k)
-            if (b == (1 << k)) c->block_shift = k;
-    }
     *out = c;
     return T3D_OK;
 }
@@ -1202,9 +1306,13 @@ int t3d_ctx_destroy(t3d_ctx* c)
     for (t3d_emitter* e : es) t3d_emitter_destroy(e);
     for (Slab& s : c->slabs)
     {
-        if (s.cols) cudaFree(s.cols);
+        if (s.base) cudaFree(s.base);
         if (s.vtx) cudaFree(s.vtx);
     }
+    if (c->download_stream) cudaStreamDestroy(c->download_stream);
+    if (c->download_fence) cudaEventDestroy(c->download_fence);
+    for (cudaEvent_t ev : c->download_done)
+        if (ev) cudaEventDestroy(ev);
     for (EmitterDev* d : c->dev_chunks) cudaFree(d);
     for (StagingSlot& s : c->staging)
     {
@@ -1328,6 +1436,49 @@ int t3d_ctx_transfer_bytes(t3d_ctx* c, uint64_t* h2d, uint64_t* d2h)
     return T3D_OK;
 }
 
+int t3d_ctx_set_vertex_mode(t3d_ctx* c, int mode)
+{
+    if (!c || (mode != T3D_VERTEX_WORLD && mode != T3D_VERTEX_CLIP)) return fail(T3D_ERR_INVALID, "bad vertex mode %d", mode);
+    T3D_TRY(flush(c));
+    c->vertex_mode = mode;
+    return T3D_OK;
+}
+
+int t3d_ctx_copy_to_host_async(t3d_ctx* c, void* host_dst, const void* device_src, size_t bytes, uint64_t* ticket)
+{
+    if (!c || !host_dst || !device_src || !ticket) return fail(T3D_ERR_INVALID, "copy_to_host_async: null argument");
+    T3D_TRY(flush(c));
+    T3D_TRY(use_device(c));
+    if (!c->download_stream) T3D_CUDA(cudaStreamCreateWithFlags(&c->download_stream, cudaStreamNonBlocking));
+    if (!c->download_fence) T3D_CUDA(cudaEventCreateWithFlags(&c->download_fence, cudaEventDisableTiming));
+    // after everything the context has enqueued so far, beside whatever it enqueues next
+    T3D_CUDA(cudaEventRecord(c->download_fence, c->stream));
+    T3D_CUDA(cudaStreamWaitEvent(c->download_stream, c->download_fence, 0));
+    T3D_CUDA(cudaMemcpyAsync(host_dst, device_src, bytes, cudaMemcpyDeviceToHost, c->download_stream));
+    cudaEvent_t done;
+    T3D_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    T3D_CUDA(cudaEventRecord(done, c->download_stream));
+    // The launching stream must not overwrite the source before the copy has read it: a later launch that reuses the
+    // buffer is the caller's to order (alternate two buffers and wait for ticket k before redrawing into buffer k).
+    c->download_done.push_back(done);
+    c->d2h_bytes += bytes;
+    *ticket = c->download_done.size();
+    return T3D_OK;
+}
+
+int t3d_ctx_copy_wait(t3d_ctx* c, uint64_t ticket)
+{
+    if (!c || ticket == 0 || ticket > c->download_done.size()) return fail(T3D_ERR_INVALID, "copy_wait: unknown ticket");
+    cudaEvent_t& ev = c->download_done[ticket - 1];
+    if (ev)
+    {
+        T3D_CUDA(cudaEventSynchronize(ev));
+        cudaEventDestroy(ev);
+        ev = nullptr;
+    }
+    return T3D_OK;
+}
+
 // ---- lifecycle ----
 static void apply_params(t3d_emitter* e, const t3d_emitter_params* p)
 {
@@ -1372,6 +1523,8 @@ int t3d_emitter_create(t3d_ctx* c, const t3d_emitter_params* p, t3d_emitter** ou
     apply_params(e, p);
     memset(e->node_world, 0, sizeof(e->node_world));
     memset(e->camera_world, 0, sizeof(e->camera_world));
+    memset(e->view_projection, 0, sizeof(e->view_projection));
+    e->view_projection[0] = e->view_projection[5] = e->view_projection[10] = e->view_projection[15] = 1.0f;
     c->emitters.push_back(e);
     *out = e;
     return T3D_OK;
@@ -1414,16 +1567,7 @@ int t3d_emitter_destroy(t3d_emitter* e)
             if (o == e) o = nullptr;
     if (e->uv_dev) cudaFree(e->uv_dev);
     if (e->dev) c->dev_free.push_back(e->dev);
-    Slab& s = c->slabs[e->slab];
-    if (--s.live_emitters == 0)
-    {
-        // Last emitter of the slab: give the memory back.
-        if (s.cols) cudaFree(s.cols);
-        if (s.vtx) cudaFree(s.vtx);
-        s.cols = nullptr;
-        s.vtx = nullptr;
-        s.capacity = s.used = 0;
-    }
+    free_segment(c, e->slab, e->seg_offset, e->seg_capacity);
     c->emitters.erase(std::remove(c->emitters.begin(), c->emitters.end(), e), c->emitters.end());
     delete e;
     return T3D_OK;
@@ -1539,6 +1683,64 @@ int t3d_emitter_set_camera_world(t3d_emitter* e, const float m[16])
     return T3D_OK;
 }
 
+int t3d_emitter_set_view_projection(t3d_emitter* e, const float m[16])
+{
+    if (!e || !m) return fail(T3D_ERR_INVALID, "null argument");
+    memcpy(e->view_projection, m, sizeof(e->view_projection));
+    e->has_vp = true;
+    return T3D_OK;
+}
+
+int t3d_emitter_enable_bounds(t3d_emitter* e, int on)
+{
+    if (!e) return fail(T3D_ERR_INVALID, "null emitter");
+    if (e->queued || e->held) T3D_TRY(flush(e->ctx));
+    if (e->want_bounds != (on != 0))
+    {
+        e->want_bounds = on != 0;
+        e->const_dirty = true;
+        if (!on) e->bounds_epoch = 0;
+    }
+    return T3D_OK;
+}
+
+static int read_bounds(t3d_emitter* e, float lo[3], float hi[3], int* valid)
+{
+    t3d_ctx* c = e->ctx;
+    *valid = 0;
+    if (!e->want_bounds) return T3D_OK;
+    if (e->queued || e->held) T3D_TRY(flush(c));
+    if (!e->bounds_epoch) return T3D_OK;
+    T3D_TRY(use_device(c));
+    EmitterBounds b;
+    T3D_CUDA(cudaMemcpyAsync(&b, &e->dev->bounds, sizeof(b), cudaMemcpyDeviceToHost, c->stream));
+    T3D_CUDA(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += sizeof(b);
+    for (int k = 0; k < 3; ++k)
+    {
+        // a word of an older launch: no particle contributed on this axis in the last update, i.e. none is live
+        if ((uint32_t)(b.lo[k] >> 32) != e->bounds_epoch || (uint32_t)(b.hi[k] >> 32) != e->bounds_epoch) return T3D_OK;
+        lo[k] = float_unorder(~(uint32_t)b.lo[k]);
+        hi[k] = float_unorder((uint32_t)b.hi[k]);
+    }
+    *valid = 1;
+    return T3D_OK;
+}
+
+int t3d_emitter_bounds(t3d_emitter* e, float lo[3], float hi[3], int* valid)
+{
+    if (!e || !lo || !hi || !valid) return fail(T3D_ERR_INVALID, "null argument");
+    return read_bounds(e, lo, hi, valid);
+}
+
+int t3d_emitter_set_culling(t3d_emitter* e, int on)
+{
+    if (!e) return fail(T3D_ERR_INVALID, "null emitter");
+    if (on) T3D_TRY(t3d_emitter_enable_bounds(e, 1));
+    e->culling = on != 0;
+    return T3D_OK;
+}
+
 // ---- the path ----
 int t3d_emitter_start(t3d_emitter* e)
 {
@@ -1638,9 +1840,30 @@ int t3d_emitter_update(t3d_emitter* e, float elapsed_time)
     return enqueue(c, PHASE_UPDATE, op);
 }
 
-int t3d_emitter_draw(t3d_emitter* e, uint32_t* draw_calls)
+// Is the emitter's last bounding box entirely outside the clip volume of its view-projection matrix?  Conservative:
+// only "all eight corners beyond the same plane" culls (clip-space test -w <= x, y, z <= w).
+static bool outside_frustum(const float* vp, const float lo[3], const float hi[3])
 {
-    if (!e) return fail(T3D_ERR_INVALID, "null emitter");
+    float cx[8][4];
+    for (int k = 0; k < 8; ++k)
+    {
+        const float x = (k & 1) ? hi[0] : lo[0], y = (k & 2) ? hi[1] : lo[1], z = (k & 4) ? hi[2] : lo[2];
+        for (int r = 0; r < 4; ++r) cx[k][r] = x * vp[r] + y * vp[4 + r] + z * vp[8 + r] + vp[12 + r];
+    }
+    for (int axis = 0; axis < 3; ++axis)
+        for (int side = 0; side < 2; ++side)
+        {
+            bool all_out = true;
+            for (int k = 0; k < 8 && all_out; ++k) all_out = side ? (cx[k][axis] > cx[k][3]) : (cx[k][axis] < -cx[k][3]);
+            if (all_out) return true;
+        }
+    return false;
+}
+
+static int read_bounds(t3d_emitter* e, float lo[3], float hi[3], int* valid);
+
+static int draw_common(t3d_emitter* e, float* dst, size_t dst_quads, uint32_t* draw_calls)
+{
     t3d_ctx* c = e->ctx;
     if (draw_calls) *draw_calls = 0;
     // The return value (PE.cpp:837: 0 when inactive) is the only thing that needs the exact live count of a stopped
@@ -1649,19 +1872,50 @@ int t3d_emitter_draw(t3d_emitter* e, uint32_t* draw_calls)
     bool active;
     T3D_TRY(is_active(e, &active, draw_calls != nullptr));
     e->last_draw_empty = true;
+    e->last_draw_dst = nullptr;
     if (!active) return T3D_OK; // PE.cpp:837
     if (draw_calls) *draw_calls = 1;
     if (e->count_ub == 0) return T3D_OK; // PE.cpp:839
     if (!e->has_node || !e->has_camera)
         return fail(T3D_ERR_NO_NODE, "draw: the emitter needs a node and an active camera node (PE.cpp:858-859)");
+    if (dst)
+    {
+        if (reinterpret_cast<uintptr_t>(dst) & 15u) return fail(T3D_ERR_INVALID, "draw_to: the destination must be 16-byte aligned");
+        if ((size_t)e->count_ub > dst_quads)
+            return fail(T3D_ERR_CAPACITY, "draw_to: the destination holds %zu quads but the emitter may have %u live particles", dst_quads,
+                        e->count_ub);
+    }
+    if (e->culling)
+    {
+        // the box the last update left (one frame old when update and draw of this frame are still queued together)
+        float lo[3], hi[3];
+        int valid = 0;
+        T3D_TRY(read_bounds(e, lo, hi, &valid));
+        if (valid && outside_frustum(e->view_projection, lo, hi)) return T3D_OK; // nothing of it can reach the screen
+    }
     PendingOp op{};
     op.e = e;
     op.offsets_begin = SIZE_MAX;
     // PE.cpp:860-864: right = (m0, m1, m2), up = (m4, m5, m6) of the camera node's world matrix.
     op.right[0] = e->camera_world[0]; op.right[1] = e->camera_world[1]; op.right[2] = e->camera_world[2];
     op.up[0] = e->camera_world[4]; op.up[1] = e->camera_world[5]; op.up[2] = e->camera_world[6];
+    memcpy(op.vp, e->view_projection, sizeof(op.vp)); // PE.cpp:846-849
+    op.draw_dst = dst;
     e->last_draw_empty = false;
+    e->last_draw_dst = dst;
     return enqueue(c, PHASE_DRAW, op);
+}
+
+int t3d_emitter_draw(t3d_emitter* e, uint32_t* draw_calls)
+{
+    if (!e) return fail(T3D_ERR_INVALID, "null emitter");
+    return draw_common(e, nullptr, 0, draw_calls);
+}
+
+int t3d_emitter_draw_to(t3d_emitter* e, void* device_dst, size_t dst_quads, uint32_t* draw_calls)
+{
+    if (!e || !device_dst) return fail(T3D_ERR_INVALID, "draw_to: null argument");
+    return draw_common(e, static_cast<float*>(device_dst), dst_quads, draw_calls);
 }
 
 int t3d_emitter_get_count(t3d_emitter* e, uint32_t* count)
@@ -1721,9 +1975,10 @@ int t3d_emitter_vertices(t3d_emitter* e, const t3d_sprite_vertex** device_ptr, u
     uint32_t cnt, drawn;
     T3D_TRY(refresh_counts(c, &e, 1, &cnt, &drawn));
     const Slab& s = c->slabs[e->slab];
-    if (device_ptr)
-        *device_ptr = s.vtx ? reinterpret_cast<const t3d_sprite_vertex*>(s.vtx + (size_t)e->seg_offset * T3D_FLOATS_PER_QUAD) : nullptr;
-    if (n_quads) *n_quads = (s.vtx && !e->last_draw_empty) ? drawn : 0;
+    const float* own = s.vtx ? s.vtx + (size_t)e->seg_offset * s.vtx_floats : nullptr;
+    const float* where = e->last_draw_dst ? e->last_draw_dst : own; // (t3d_clip_vertex in T3D_VERTEX_CLIP mode)
+    if (device_ptr) *device_ptr = reinterpret_cast<const t3d_sprite_vertex*>(where);
+    if (n_quads) *n_quads = (where && !e->last_draw_empty) ? drawn : 0;
     return T3D_OK;
 }
 
@@ -1822,9 +2077,10 @@ int t3d_emitter_download_vertices(t3d_emitter* e, float* out, size_t max_quads, 
     if (out && m)
     {
         t3d_ctx* c = e->ctx;
-        T3D_CUDA(cudaMemcpyAsync(out, dev, m * T3D_FLOATS_PER_QUAD * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        const size_t quad_bytes = (c->vertex_mode == T3D_VERTEX_CLIP ? T3D_FLOATS_PER_CLIP_QUAD : T3D_FLOATS_PER_QUAD) * sizeof(float);
+        T3D_CUDA(cudaMemcpyAsync(out, dev, m * quad_bytes, cudaMemcpyDeviceToHost, c->stream));
         T3D_CUDA(cudaStreamSynchronize(c->stream));
-        c->d2h_bytes += m * T3D_FLOATS_PER_QUAD * sizeof(float);
+        c->d2h_bytes += m * quad_bytes;
     }
     return T3D_OK;
 }
@@ -1838,20 +2094,13 @@ int t3d_emitter_download_state(t3d_emitter* e, uint32_t* out, size_t stride, uin
     if (count) *count = n;
     if (!out || n == 0) return T3D_OK;
     if (stride < n) return fail(T3D_ERR_INVALID, "download_state: stride %zu < live count %u", stride, n);
-    const Slab& s = c->slabs[e->slab];
-    if (c->block_shift == 0)
     {
-        T3D_CUDA(cudaMemcpy2DAsync(out, stride * sizeof(uint32_t), s.cols + e->seg_offset, (size_t)s.capacity * sizeof(uint32_t),
-                                   (size_t)n * sizeof(uint32_t), T3D_NUM_COLUMNS, cudaMemcpyDeviceToHost, c->stream));
-        T3D_CUDA(cudaStreamSynchronize(c->stream));
-    }
-    else
-    {
+        // the device keeps rw columns + records: a kernel rearranges them into the 34 exchange columns
         EmitterConst k;
         fill_const(e, &k);
         uint32_t* tmp = nullptr;
         T3D_CUDA(cudaMalloc((void**)&tmp, (size_t)n * T3D_NUM_COLUMNS * sizeof(uint32_t)));
-        launch_export_state(c->stream, k.cols, k.stride, k.block_shift, n, tmp, n);
+        launch_export_state(c->stream, k.st, n, tmp, n);
         c->launches++;
         cudaError_t err = cudaMemcpy2DAsync(out, stride * sizeof(uint32_t), tmp, (size_t)n * sizeof(uint32_t), (size_t)n * sizeof(uint32_t),
                                             T3D_NUM_COLUMNS, cudaMemcpyDeviceToHost, c->stream);
@@ -1871,12 +2120,8 @@ int t3d_emitter_upload_state(t3d_emitter* e, const uint32_t* in, size_t stride, 
     t3d_ctx* c = e->ctx;
     T3D_TRY(flush(c));
     T3D_TRY(use_device(c));
-    const Slab& s = c->slabs[e->slab];
     uint32_t* tmp = nullptr;
-    if (count && c->block_shift == 0)
-        T3D_CUDA(cudaMemcpy2DAsync(s.cols + e->seg_offset, (size_t)s.capacity * sizeof(uint32_t), in, stride * sizeof(uint32_t),
-                                   (size_t)count * sizeof(uint32_t), T3D_NUM_COLUMNS, cudaMemcpyHostToDevice, c->stream));
-    else if (count)
+    if (count)
     {
         EmitterConst k;
         fill_const(e, &k);
@@ -1888,7 +2133,7 @@ int t3d_emitter_upload_state(t3d_emitter* e, const uint32_t* in, size_t stride, 
             cudaFree(tmp);
             return fail(T3D_ERR_CUDA, "upload_state: %s", cudaGetErrorString(err));
         }
-        launch_import_state(c->stream, k.cols, k.stride, k.block_shift, count, tmp, count);
+        launch_import_state(c->stream, k.st, count, tmp, count);
         c->launches++;
     }
     T3D_CUDA(cudaMemcpyAsync(&e->dev->cnt[e->parity].count, &count, sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));

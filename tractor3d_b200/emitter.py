@@ -37,6 +37,7 @@ class Context:
         self.h = C.c_void_p()
         _check(self.lib, self.lib.t3d_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self.h)))
         self.device = device
+        self.vertex_mode = abi.VERTEX_WORLD
 
     def close(self):
         if self.h:
@@ -57,6 +58,20 @@ class Context:
 
     def set_rotation_mode(self, mode):
         _check(self.lib, self.lib.t3d_ctx_set_rotation_mode(self.h, mode))
+
+    def set_vertex_mode(self, mode):
+        """abi.VERTEX_WORLD (SpriteVertex, default) or abi.VERTEX_CLIP (position already projected, sprite.vert:19)."""
+        _check(self.lib, self.lib.t3d_ctx_set_vertex_mode(self.h, mode))
+        self.vertex_mode = mode
+
+    def copy_to_host_async(self, host_ptr, device_ptr, nbytes):
+        """Device -> pinned host copy on the context's download stream, beside the launches that follow.  Returns a ticket."""
+        t = C.c_uint64()
+        _check(self.lib, self.lib.t3d_ctx_copy_to_host_async(self.h, C.c_void_p(host_ptr), C.c_void_p(device_ptr), nbytes, C.byref(t)))
+        return t.value
+
+    def copy_wait(self, ticket):
+        _check(self.lib, self.lib.t3d_ctx_copy_wait(self.h, ticket))
 
     def set_frozen_rotation(self, u, angle):
         a = np.ascontiguousarray(u, dtype=np.float32)
@@ -298,6 +313,23 @@ class ParticleEmitter:
         a = np.ascontiguousarray(m, dtype=np.float32).reshape(16)
         _check(self.lib, self.lib.t3d_emitter_set_camera_world(self.h, _fptr(a)))
 
+    def set_view_projection(self, m):
+        """Node::getViewProjectionMatrix() of the emitter's node (PE.cpp:846-849)."""
+        a = np.ascontiguousarray(m, dtype=np.float32).reshape(16)
+        _check(self.lib, self.lib.t3d_emitter_set_view_projection(self.h, _fptr(a)))
+
+    def enable_bounds(self, on=True):
+        _check(self.lib, self.lib.t3d_emitter_enable_bounds(self.h, int(bool(on))))
+
+    def bounds(self):
+        """(lo, hi) of pos -+ size over the live particles as the last update() left them, or None."""
+        lo, hi, ok = np.zeros(3, np.float32), np.zeros(3, np.float32), C.c_int()
+        _check(self.lib, self.lib.t3d_emitter_bounds(self.h, _fptr(lo), _fptr(hi), C.byref(ok)))
+        return (lo, hi) if ok.value else None
+
+    def set_culling(self, on=True):
+        _check(self.lib, self.lib.t3d_emitter_set_culling(self.h, int(bool(on))))
+
     # -- the path --
     def start(self):
         _check(self.lib, self.lib.t3d_emitter_start(self.h))
@@ -326,6 +358,12 @@ class ParticleEmitter:
         _check(self.lib, self.lib.t3d_emitter_draw(self.h, C.byref(v)))
         return v.value
 
+    def draw_to(self, device_ptr, capacity_quads):
+        """draw() with the quads written into the caller's device buffer (e.g. a mapped interop vertex buffer)."""
+        v = C.c_uint32()
+        _check(self.lib, self.lib.t3d_emitter_draw_to(self.h, C.c_void_p(device_ptr), capacity_quads, C.byref(v)))
+        return v.value
+
     def getParticlesCount(self):
         v = C.c_uint32()
         _check(self.lib, self.lib.t3d_emitter_get_count(self.h, C.byref(v)))
@@ -351,9 +389,10 @@ class ParticleEmitter:
         return ptr.value, n.value
 
     def vertices(self, out=None):
-        """(n_quads, 4, 9) float32 copy of the vertex stream of the last draw()."""
+        """(n_quads, 4, 9) float32 copy of the vertex stream of the last draw() -- (n_quads, 4, 10) in clip-space mode."""
         _, n = self.vertices_device()
-        buf = out if out is not None else np.zeros((max(n, 1), 4, 9), dtype=np.float32)
+        per = 10 if self.ctx.vertex_mode == abi.VERTEX_CLIP else 9
+        buf = out if out is not None else np.zeros((max(n, 1), 4, per), dtype=np.float32)
         got = C.c_uint32()
         _check(self.lib, self.lib.t3d_emitter_download_vertices(self.h, _fptr(buf), buf.shape[0], C.byref(got)))
         return buf[: min(got.value, buf.shape[0])]
