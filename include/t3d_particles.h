@@ -270,7 +270,8 @@ int32_t t3d_device_rng_draw(uint64_t seed, uint64_t serial, uint32_t j);
 int t3d_host_rate_cap(double* running_time, float elapsed_time, float* elapsed_ms);
 /* The runtime's launch policy (not in the reference): should update() of a set of emitters wait for the draw() that
  * follows, to go out as one fused launch?  particles = their live particles (upper bound), spawned = particles asked to
- * spawn since their previous update (stands in for deaths).  1 while at most 0.25 % are replaced per frame. */
+ * spawn since their previous update (stands in for deaths).  Always 1 with the current kernels (the fused frame wins at
+ * every measured churn level); kept as the one place the decision lives. */
 int t3d_host_fuse_policy(uint64_t particles, uint64_t spawned);
 /* PE.cpp:732-743: advances *emit_time and returns how many particles to emit this frame. */
 uint32_t t3d_host_emission_count(float* emit_time, float time_per_emission, float elapsed_ms);

@@ -565,6 +565,41 @@ uint32_t orc_emitter_get_vertices(orc_emitter* e, float* out, size_t max_quads)
     return (uint32_t)e->vertex_quads;
 }
 
+/* The vertex shader's one line applied on the CPU (res/shaders/sprite.vert:19: gl_Position = u_projectionMatrix *
+ * vec4(a_position, 1), with the matrix ParticleEmitter::draw hands the batch at PE.cpp:846-849): every captured vertex
+ * becomes {x, y, z, w, u, v, r, g, b, a}.  RESTATED, not reference-pinned (the reference leaves this to the GPU); each
+ * component is summed in MathUtil::transformVector4's order (MathUtil.h:195-200). */
+uint32_t orc_emitter_get_clip_vertices(orc_emitter* e, const float vp[16], float* out, size_t max_quads)
+{
+    size_t n = e->vertex_quads < max_quads ? e->vertex_quads : max_quads;
+    for (size_t q = 0; out && q < n; ++q)
+        for (int k = 0; k < 4; ++k) {
+            const float* v = e->vertices + (q * 4 + (size_t)k) * 9;
+            float* o = out + (q * 4 + (size_t)k) * 10;
+            transform_vector4(vp, v[0], v[1], v[2], 1.0f, o); /* writes o[0..2] */
+            o[3] = v[0] * vp[3] + v[1] * vp[7] + v[2] * vp[11] + 1.0f * vp[15];
+            memcpy(o + 4, v + 3, 6 * sizeof(float));
+        }
+    return (uint32_t)e->vertex_quads;
+}
+
+/* Bounding box of the live particles: min / max over position -+ size per axis (the engine has a TODO here,
+ * src/scene/Node.cpp:777-780).  RESTATED definition of t3d_emitter_bounds.  Returns 0 when no particle is live. */
+int orc_emitter_bounds(orc_emitter* e, float lo[3], float hi[3])
+{
+    if (!e->particle_count) return 0;
+    for (int k = 0; k < 3; ++k) { lo[k] = 3.402823466e38f; hi[k] = -3.402823466e38f; }
+    for (size_t i = 0; i < e->particle_count; ++i) {
+        const orc_particle* p = &e->particles[i];
+        for (int k = 0; k < 3; ++k) {
+            const float a = p->position[k] - p->size, b = p->position[k] + p->size;
+            if (a < lo[k]) lo[k] = a;
+            if (b > hi[k]) hi[k] = b;
+        }
+    }
+    return 1;
+}
+
 /* =====================================================================================
  * State exchange in the column layout of include/t3d_particles.h.
  * ===================================================================================== */

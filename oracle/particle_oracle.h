@@ -69,6 +69,10 @@ uint32_t orc_emitter_get_count(orc_emitter* e);
 uint32_t orc_emitter_get_state(orc_emitter* e, uint32_t* out, size_t stride);
 int orc_emitter_set_state(orc_emitter* e, const uint32_t* in, size_t stride, uint32_t n);
 uint32_t orc_emitter_get_vertices(orc_emitter* e, float* out, size_t max_quads);
+/* T3D_VERTEX_CLIP restated: the captured vertices with sprite.vert:19 applied (10 floats per vertex). */
+uint32_t orc_emitter_get_clip_vertices(orc_emitter* e, const float vp[16], float* out, size_t max_quads);
+/* t3d_emitter_bounds restated: min / max of position -+ size over the live particles; returns 0 when none is live. */
+int orc_emitter_bounds(orc_emitter* e, float lo[3], float hi[3]);
 
 /* MeshBatch::add's index stitching for n quads appended one by one (MB.cpp:87-148, TRIANGLE_STRIP, indexed), with
  * 32-bit indices.  Returns the number of indices written (6n-2).  Restated, not reference-pinned (MeshBatch.cpp needs GL). */

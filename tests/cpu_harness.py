@@ -96,6 +96,8 @@ class CpuLib:
             proto("get_frozen_rotation", C.c_int, [_P(C.c_float)])
             proto("emitter_set_device_rng", None, [_vp, C.c_int, C.c_uint64])
             proto("strip_indices", C.c_uint64, [C.c_uint32, _P(C.c_uint32)])
+            proto("emitter_get_clip_vertices", C.c_uint32, [_vp, _P(C.c_float), _P(C.c_float), C.c_size_t])
+            proto("emitter_bounds", C.c_int, [_vp, _P(C.c_float), _P(C.c_float)])
         else:
             proto("emitter_create_from_file", _vp, [C.c_char_p])
             proto("emitter_clone", _vp, [_vp])
@@ -229,6 +231,21 @@ class CpuEmitter:
         if n:
             self.L.emitter_get_vertices(self.h, out.ctypes.data_as(_P(C.c_float)), n)
         return out[:n]
+
+
+    def clip_vertices(self, vp):
+        """(n_quads, 4, 10) float32: the last draw()'s vertices with sprite.vert:19 applied (oracle port only)."""
+        m = np.ascontiguousarray(vp, dtype=np.float32).reshape(16)
+        n = self.L.emitter_get_clip_vertices(self.h, m.ctypes.data_as(_P(C.c_float)), None, 0)
+        out = np.zeros((max(n, 1), 4, 10), dtype=np.float32)
+        if n:
+            self.L.emitter_get_clip_vertices(self.h, m.ctypes.data_as(_P(C.c_float)), out.ctypes.data_as(_P(C.c_float)), n)
+        return out[:n]
+
+    def bounds(self):
+        lo, hi = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        ok = self.L.emitter_bounds(self.h, lo.ctypes.data_as(_P(C.c_float)), hi.ctypes.data_as(_P(C.c_float)))
+        return (lo, hi) if ok else None
 
 
 _oracle = None

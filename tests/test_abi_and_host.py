@@ -82,15 +82,12 @@ def test_rate_cap_and_emission_count_follow_the_oracle():
             assert np.float32(emit_time.value) == np.float32(eo.emit_time())
 
 
-def test_fuse_policy_follows_the_measured_crossover():
-    # update+draw go out as one fused launch while at most 0.25 % of the particles are replaced per frame
-    # (profiles/r1_churn_crossover.txt: fused wins at 0 and 0.17 %, loses at 0.34 % and beyond).
+def test_fuse_policy_follows_the_measurements():
+    # profiles/r2_churn.txt: with moves folded into the stream the fused frame wins from 0 to 7 % of the particles replaced
+    # per frame, so update() always waits for the draw() behind it
     lib = abi.load()
-    assert lib.t3d_host_fuse_policy(64 << 20, 0) == 1                 # C3/C4: stationary
-    assert lib.t3d_host_fuse_policy(38_500_000, 65_536) == 1          # 0.17 %
-    assert lib.t3d_host_fuse_policy(38_500_000, 131_072) == 0         # 0.34 %
-    assert lib.t3d_host_fuse_policy(14_300_000, 1 << 20) == 0         # C5: 7 %
-    assert lib.t3d_host_fuse_policy(0, 0) == 1 and lib.t3d_host_fuse_policy(0, 1) == 0
+    for particles, spawned in ((64 << 20, 0), (38_500_000, 131_072), (19_300_000, 262_144), (14_300_000, 1 << 20), (0, 0), (0, 1)):
+        assert lib.t3d_host_fuse_policy(particles, spawned) == 1
 
 
 def test_sprite_frame_coords_follow_the_oracle():

@@ -70,7 +70,7 @@ def _probe(fused, n_emitters, per, emit_per_frame=0):
 
 def test_fused_launch_policy():
     """update(set) directly followed by draw(same set): one launch with T3D_FUSED=1, two with T3D_FUSED=0; left alone,
-    the runtime fuses unless many particles are being replaced per frame (spawns stand in for deaths)."""
+    the runtime fuses (t3d_host_fuse_policy: the fused frame wins at every measured churn level)."""
     # (the very first frame stays apart: the rotation latch has to look at the updated angles before the draw, SB.cpp:339)
     f, u, d = _probe("1", 3, 1000)
     assert f >= 5 and u == 6 - f and d == 6 - f, (f, u, d)
@@ -78,9 +78,7 @@ def test_fused_launch_policy():
     assert f == 0 and u == 6 and d == 6, (f, u, d)
     f, u, d = _probe(None, 3, 1000)
     assert f >= 5 and u == 6 - f and d == 6 - f, (f, u, d)
-    f, u, d = _probe(None, 3, 1000, emit_per_frame=20)    # 20 of ~1 000 replaced per frame (2 %): too much churn
-    assert f == 0 and u == 6 and d == 6, (f, u, d)
-    f, u, d = _probe(None, 3, 80000, emit_per_frame=100)  # 100 of 80 000 (0.125 %): low churn
+    f, u, d = _probe(None, 3, 1000, emit_per_frame=20)    # 2 % of the particles replaced per frame: still fused
     assert f >= 5 and u == 6 - f and d == 6 - f, (f, u, d)
 
 

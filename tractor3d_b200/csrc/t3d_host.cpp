@@ -74,9 +74,13 @@ int32_t t3d_device_rng_draw(uint64_t seed, uint64_t serial, uint32_t j) { return
 
 int t3d_host_fuse_policy(uint64_t particles, uint64_t spawned)
 {
-    // Measured crossover on B200 (profiles/r1_churn_crossover.txt): the fused frame wins up to ~0.25 % of the particles
-    // replaced per frame and loses beyond (every moved particle costs it an extra scattered 144-byte quad).
-    return spawned * 400 <= particles ? 1 : 0;
+    // Measured on B200 (profiles/r2_churn.txt): since a moved particle leaves with its destination group's vector stores
+    // and its quad with the warp's bulk store, the fused frame beats the two launches at every churn level -- by 8 % with
+    // nothing replaced per frame, 9 % at 0.34 %, 8 % at 1.3-1.7 %, 4 % at 7 % -- so update() always waits for the draw()
+    // behind it.  (Round 1's kernel paid a scattered 144-byte quad per moved particle and lost beyond 0.25 %.)
+    (void)particles;
+    (void)spawned;
+    return 1;
 }
 
 int t3d_host_rate_cap(double* running_time, float elapsed_time, float* elapsed_ms)

@@ -11,7 +11,7 @@ namespace t3d
 
 // Particles per tile of the update kernel = particles per thread x threads per CTA x groups of the selected variant
 // (t3d_update.cu).
-int update_tile_size();
+int update_tile_size(int shape = 0);
 int draw_sub(uint32_t n_items);
 int draw_tile_size(uint32_t n_items); // quads per draw CTA for a launch over n_items emitters
 const char* update_variant_name();
@@ -191,12 +191,14 @@ struct UpdateLaunch
     const FrozenRotation* frozen;
     bool bounds; // some emitter of the launch wants its bounding box
 };
-void launch_update(void* stream, const UpdateLaunch& L);
-void launch_update_draw(void* stream, const UpdateLaunch& L);
+// shape: 0 = the variant's own tiles, 1 = half-size tiles (pick_tile_shape decides; narrow launches lose less to their tail)
+void launch_update(void* stream, const UpdateLaunch& L, int shape);
+void launch_update_draw(void* stream, const UpdateLaunch& L, int shape);
+int pick_tile_shape(uint64_t tiles_big, uint64_t tiles_small, uint32_t slots);
 // vertex_mode: T3D_VERTEX_WORLD (SpriteVertex, 36 floats per quad) or T3D_VERTEX_CLIP (40 floats per quad)
 void launch_draw(void* stream, const DrawItem* items, uint32_t n_items, uint32_t total_tiles, int rot_mode,
                  const FrozenRotation* frozen, uint32_t* fault, int vertex_mode);
-int fused_tile_size();
+int fused_tile_size(int shape = 0);
 int fused_mode(); // 1 always, 0 never, -1 automatic
 void launch_latch(void* stream, const DrawItem* items, uint32_t n_items, FrozenRotation* frozen);
 struct CountQuery
@@ -206,8 +208,9 @@ struct CountQuery
     uint32_t pad;
 };
 // out[2*i] = live count, out[2*i+1] = quads written by the last draw, for each query.
-// out[2*n] = the context's fault word.
-void launch_gather_counts(void* stream, const CountQuery* q, uint32_t n, uint32_t* out, const uint32_t* fault);
+// out[2*n] = the context's fault word.  boxes (optional): the six bounding-box words of each query's emitter.
+void launch_gather_counts(void* stream, const CountQuery* q, uint32_t n, uint32_t* out, const uint32_t* fault,
+                          unsigned long long* boxes);
 // MeshBatch's triangle-strip index pattern for n_quads quads (MB.cpp:117-141), 6*n_quads-2 indices.
 void launch_strip_indices(void* stream, uint32_t* out, uint64_t n_indices);
 void launch_triangle_indices(void* stream, uint32_t* out, uint64_t n_indices);

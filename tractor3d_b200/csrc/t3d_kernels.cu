@@ -418,18 +418,27 @@ void launch_latch(void* stream, const DrawItem* items, uint32_t n_items, FrozenR
 }
 
 __global__ void k_gather_counts(const CountQuery* __restrict__ q, uint32_t n, uint32_t* __restrict__ out,
-                                const uint32_t* __restrict__ fault)
+                                const uint32_t* __restrict__ fault, unsigned long long* __restrict__ boxes)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) out[2 * n] = *fault;
     if (i >= n) return;
     out[2 * i] = q[i].dev->cnt[q[i].parity].count;
     out[2 * i + 1] = q[i].dev->cnt[0].drawn;
+    if (boxes)
+    {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            boxes[6 * i + k] = q[i].dev->bounds.lo[k];
+            boxes[6 * i + 3 + k] = q[i].dev->bounds.hi[k];
+        }
+    }
 }
 
-void launch_gather_counts(void* stream, const CountQuery* q, uint32_t n, uint32_t* out, const uint32_t* fault)
+void launch_gather_counts(void* stream, const CountQuery* q, uint32_t n, uint32_t* out, const uint32_t* fault, unsigned long long* boxes)
 {
-    k_gather_counts<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(q, n, out, fault);
+    k_gather_counts<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(q, n, out, fault, boxes);
 }
 
 // MB.cpp:117-141: the first quad's four indices, then per quad two degenerate indices (previous last, next first)

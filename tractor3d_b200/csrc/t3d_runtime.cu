@@ -142,6 +142,7 @@ struct t3d_ctx
     float frozen_m[16];
     int rot_mode{ T3D_ROT_FROZEN };
     int vertex_mode{ T3D_VERTEX_WORLD };
+    uint32_t cta_slots{ 296 }; // CTAs of the update kernel the device runs at once (2 per SM)
 
     double running_time{ 0 }; // PE.cpp:720, one per process in the reference, one per context here
 
@@ -169,6 +170,8 @@ struct t3d_ctx
     {
         std::vector<t3d_emitter*> es;
         std::vector<uint64_t> emitted_mark; // emitter's emitted_total when the launch was enqueued
+        std::vector<uint32_t> box_epoch;    // the epoch this launch's bounding box carries (0: the emitter does not ask for one)
+        bool boxes{ false };                // the six box words of every emitter ride behind the counts
         uint32_t* host{ nullptr };
         uint32_t* dev{ nullptr };
         size_t cap{ 0 };
@@ -232,6 +235,9 @@ struct t3d_emitter
     bool may_rotate{ false }, may_spin{ false };
     bool want_bounds{ false }, culling{ false };
     uint32_t bounds_epoch{ 0 }; // launch epoch of the last update that reduced this emitter's box (0: none yet)
+    // the last box that has reached the host (count feedback or t3d_emitter_bounds): what culling tests against
+    bool box_known{ false }, box_empty{ true };
+    float box_lo[3], box_hi[3];
     bool has_vp{ false };
     float view_projection[16];
     uint32_t count_ub{ 0 };     // upper bound of the live count (exact when count_exact)
@@ -635,6 +641,19 @@ static int launch_spawns(t3d_ctx* c)
     return T3D_OK;
 }
 
+// Six words as the update kernel leaves them -> a box; false when no particle contributed in the launch of `epoch`.
+static bool decode_box(const unsigned long long* w, uint32_t epoch, float lo[3], float hi[3])
+{
+    for (int k = 0; k < 3; ++k)
+    {
+        // a word of an older launch: no particle contributed on this axis in that update, i.e. none is live
+        if ((uint32_t)(w[k] >> 32) != epoch || (uint32_t)(w[3 + k] >> 32) != epoch) return false;
+        lo[k] = float_unorder(~(uint32_t)w[k]);
+        hi[k] = float_unorder((uint32_t)w[3 + k]);
+    }
+    return true;
+}
+
 static void poll_feedback(t3d_ctx* c)
 {
     for (t3d_ctx::Feedback& fb : c->feedback)
@@ -647,6 +666,12 @@ static void poll_feedback(t3d_ctx* c)
             const uint64_t ub = (uint64_t)fb.host[2 * i] + (e->emitted_total - fb.emitted_mark[i]);
             if (i == 0) c->fault |= fb.host[2 * fb.es.size()];
             if (ub < e->count_ub) e->count_ub = (uint32_t)ub;
+            if (fb.boxes && fb.box_epoch[i] && fb.box_epoch[i] == e->bounds_epoch) // (not superseded by a later update's box)
+            {
+                const unsigned long long* w = reinterpret_cast<const unsigned long long*>(fb.host + 2 * fb.cap + 2) + 6 * i;
+                e->box_empty = !decode_box(w, fb.box_epoch[i], e->box_lo, e->box_hi);
+                e->box_known = true;
+            }
         }
         fb.in_flight = false;
     }
@@ -659,30 +684,45 @@ static int submit_feedback(t3d_ctx* c, const std::vector<PendingOp>& ops, const 
     if (fb.in_flight) return T3D_OK; // all slots busy: skip this frame's feedback
     c->feedback_next = (c->feedback_next + 1) % 4;
     const size_t n = ops.size();
+    // layout: counts (2 words per emitter) + the fault word, padded to `cap` emitters; then 6 x 64-bit box words per emitter
+    auto words = [](size_t cap) { return 2 * cap + 2 + 12 * cap; };
     if (fb.cap < n)
     {
         if (fb.host) cudaFreeHost(fb.host);
         if (fb.dev) cudaFree(fb.dev);
         fb.host = fb.dev = nullptr;
         const size_t cap = std::max<size_t>(n * 2, 64);
-        T3D_CUDA(cudaMallocHost((void**)&fb.host, (cap * 2 + 1) * sizeof(uint32_t)));
-        T3D_CUDA(cudaMalloc((void**)&fb.dev, (cap * 2 + 1) * sizeof(uint32_t)));
+        T3D_CUDA(cudaMallocHost((void**)&fb.host, words(cap) * sizeof(uint32_t)));
+        T3D_CUDA(cudaMalloc((void**)&fb.dev, words(cap) * sizeof(uint32_t)));
         fb.cap = cap;
     }
     if (!fb.done) T3D_CUDA(cudaEventCreateWithFlags(&fb.done, cudaEventDisableTiming));
     fb.es.resize(n);
     fb.emitted_mark.resize(n);
+    fb.box_epoch.assign(n, 0);
+    fb.boxes = false;
     for (size_t i = 0; i < n; ++i)
     {
         fb.es[i] = ops[i].e;
         fb.emitted_mark[i] = ops[i].e->emitted_total;
+        if (ops[i].e->want_bounds)
+        {
+            fb.box_epoch[i] = ops[i].e->bounds_epoch;
+            fb.boxes = true;
+        }
     }
-    launch_gather_counts(c->stream, dev_queries, (uint32_t)n, fb.dev, c->fault_dev);
+    unsigned long long* dev_boxes = fb.boxes ? reinterpret_cast<unsigned long long*>(fb.dev + 2 * fb.cap + 2) : nullptr;
+    launch_gather_counts(c->stream, dev_queries, (uint32_t)n, fb.dev, c->fault_dev, dev_boxes);
     T3D_CUDA(cudaGetLastError());
     c->launches++;
     T3D_CUDA(cudaMemcpyAsync(fb.host, fb.dev, (n * 2 + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    T3D_CUDA(cudaEventRecord(fb.done, c->stream));
     c->d2h_bytes += n * 2 * sizeof(uint32_t);
+    if (fb.boxes)
+    {
+        T3D_CUDA(cudaMemcpyAsync(fb.host + 2 * fb.cap + 2, dev_boxes, n * 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        c->d2h_bytes += n * 6 * sizeof(unsigned long long);
+    }
+    T3D_CUDA(cudaEventRecord(fb.done, c->stream));
     fb.in_flight = true;
     return T3D_OK;
 }
@@ -697,6 +737,19 @@ static bool debug_shrink_grid()
         v = (env && env[0] == '1') ? 1 : 0;
     }
     return v == 1;
+}
+
+// Half-size tiles for a launch that is only a few waves wide (see pick_tile_shape).
+static int choose_shape(const t3d_ctx* c, const std::vector<PendingOp>& ops, uint32_t tile_big, uint32_t tile_small)
+{
+    if (tile_small >= tile_big) return 0;
+    uint64_t big = 0, small_ = 0;
+    for (const PendingOp& op : ops)
+    {
+        big += std::max(1u, (op.e->count_ub + tile_big - 1) / tile_big);
+        small_ += std::max(1u, (op.e->count_ub + tile_small - 1) / tile_small);
+    }
+    return pick_tile_shape(big, small_, c->cta_slots);
 }
 
 // Cuts the update descriptors (and the count queries of the feedback) of `ops`; advances each emitter's parity.
@@ -777,8 +830,9 @@ static int launch_updates(t3d_ctx* c, std::vector<PendingOp>& ops)
     const size_t total_bytes = items_bytes + sizeof(CountQuery) * n_items;
     T3D_TRY(staging_acquire(c, total_bytes, &slot));
     uint32_t tiles = 0;
+    const int shape = choose_shape(c, ops, (uint32_t)update_tile_size(0), (uint32_t)update_tile_size(1));
     build_update_items(ops, reinterpret_cast<UpdateItem*>(slot->host), reinterpret_cast<CountQuery*>(slot->host + items_bytes),
-                       (uint32_t)update_tile_size(), &tiles);
+                       (uint32_t)update_tile_size(shape), &tiles);
     T3D_TRY(begin_scan_epoch(c, tiles));
     T3D_TRY(staging_submit(c, slot, total_bytes));
     T3D_TRY(time_begin(c, KERNEL_UPDATE));
@@ -792,7 +846,7 @@ static int launch_updates(t3d_ctx* c, std::vector<PendingOp>& ops)
     L.epoch = c->epoch;
     L.fault = c->fault_dev;
     L.bounds = mark_bounds(c, ops);
-    launch_update(c->stream, L);
+    launch_update(c->stream, L, shape);
     T3D_CUDA(cudaGetLastError());
     T3D_TRY(time_end(c, KERNEL_UPDATE));
     c->ticket_base += tiles;
@@ -925,7 +979,8 @@ static int launch_fused_frame(t3d_ctx* c)
     T3D_TRY(staging_acquire(c, total_bytes, &slot));
     uint32_t tiles = 0, draw_tiles = 0;
     bool any_spin = false;
-    const uint32_t tile_size = (uint32_t)fused_tile_size();
+    const int shape = choose_shape(c, c->held, (uint32_t)fused_tile_size(0), (uint32_t)fused_tile_size(1));
+    const uint32_t tile_size = (uint32_t)fused_tile_size(shape);
     build_update_items(c->held, reinterpret_cast<UpdateItem*>(slot->host), reinterpret_cast<CountQuery*>(slot->host + items_bytes),
                        tile_size, &tiles);
     build_draw_items(c->pending, reinterpret_cast<DrawItem*>(slot->host + items_bytes + queries_bytes), tile_size, &draw_tiles, &any_spin);
@@ -945,7 +1000,7 @@ static int launch_fused_frame(t3d_ctx* c)
     L.rot_mode = c->rot_mode;
     L.frozen = c->frozen_dev;
     L.bounds = mark_bounds(c, c->held);
-    launch_update_draw(c->stream, L);
+    launch_update_draw(c->stream, L, shape);
     T3D_CUDA(cudaGetLastError());
     c->ticket_base += tiles;
     T3D_TRY(time_end(c, KERNEL_UPDATE_DRAW));
@@ -1084,7 +1139,7 @@ static int refresh_counts(t3d_ctx* c, t3d_emitter* const* es, size_t n, uint32_t
         q[i].pad = 0;
     }
     T3D_TRY(staging_submit(c, slot, sizeof(CountQuery) * n));
-    launch_gather_counts(c->stream, reinterpret_cast<const CountQuery*>(slot->dev), (uint32_t)n, c->readback_dev, c->fault_dev);
+    launch_gather_counts(c->stream, reinterpret_cast<const CountQuery*>(slot->dev), (uint32_t)n, c->readback_dev, c->fault_dev, nullptr);
     T3D_CUDA(cudaGetLastError());
     c->launches++;
     T3D_CUDA(cudaMemcpyAsync(c->readback_host, c->readback_dev, (n * 2 + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -1288,6 +1343,10 @@ int t3d_ctx_create(int device, void* cuda_stream, t3d_ctx** out)
         return fail(T3D_ERR_CUDA, "t3d_ctx_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     memset(c->frozen_m, 0, sizeof(c->frozen_m));
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) c->cta_slots = 2u * (uint32_t)sms;
+    }
     {
         const char* env = getenv("T3D_COPY_STREAM");
         if (!(env && env[0] == '0') && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -1699,7 +1758,11 @@ int t3d_emitter_enable_bounds(t3d_emitter* e, int on)
     {
         e->want_bounds = on != 0;
         e->const_dirty = true;
-        if (!on) e->bounds_epoch = 0;
+        if (!on)
+        {
+            e->bounds_epoch = 0;
+            e->box_known = false;
+        }
     }
     return T3D_OK;
 }
@@ -1716,13 +1779,12 @@ static int read_bounds(t3d_emitter* e, float lo[3], float hi[3], int* valid)
     T3D_CUDA(cudaMemcpyAsync(&b, &e->dev->bounds, sizeof(b), cudaMemcpyDeviceToHost, c->stream));
     T3D_CUDA(cudaStreamSynchronize(c->stream));
     c->d2h_bytes += sizeof(b);
-    for (int k = 0; k < 3; ++k)
-    {
-        // a word of an older launch: no particle contributed on this axis in the last update, i.e. none is live
-        if ((uint32_t)(b.lo[k] >> 32) != e->bounds_epoch || (uint32_t)(b.hi[k] >> 32) != e->bounds_epoch) return T3D_OK;
-        lo[k] = float_unorder(~(uint32_t)b.lo[k]);
-        hi[k] = float_unorder((uint32_t)b.hi[k]);
-    }
+    unsigned long long w[6] = { b.lo[0], b.lo[1], b.lo[2], b.hi[0], b.hi[1], b.hi[2] };
+    e->box_empty = !decode_box(w, e->bounds_epoch, e->box_lo, e->box_hi);
+    e->box_known = true;
+    if (e->box_empty) return T3D_OK;
+    memcpy(lo, e->box_lo, sizeof(e->box_lo));
+    memcpy(hi, e->box_hi, sizeof(e->box_hi));
     *valid = 1;
     return T3D_OK;
 }
@@ -1860,8 +1922,6 @@ static bool outside_frustum(const float* vp, const float lo[3], const float hi[3
     return false;
 }
 
-static int read_bounds(t3d_emitter* e, float lo[3], float hi[3], int* valid);
-
 static int draw_common(t3d_emitter* e, float* dst, size_t dst_quads, uint32_t* draw_calls)
 {
     t3d_ctx* c = e->ctx;
@@ -1885,14 +1945,10 @@ static int draw_common(t3d_emitter* e, float* dst, size_t dst_quads, uint32_t* d
             return fail(T3D_ERR_CAPACITY, "draw_to: the destination holds %zu quads but the emitter may have %u live particles", dst_quads,
                         e->count_ub);
     }
-    if (e->culling)
-    {
-        // the box the last update left (one frame old when update and draw of this frame are still queued together)
-        float lo[3], hi[3];
-        int valid = 0;
-        T3D_TRY(read_bounds(e, lo, hi, &valid));
-        if (valid && outside_frustum(e->view_projection, lo, hi)) return T3D_OK; // nothing of it can reach the screen
-    }
+    // Culling tests the last box that has reached the host -- it rides back with the asynchronous count feedback, so it
+    // is a frame or two old unless t3d_emitter_bounds was just called -- and never waits for the device.
+    if (e->culling && e->box_known && !e->box_empty && outside_frustum(e->view_projection, e->box_lo, e->box_hi))
+        return T3D_OK; // nothing of it can reach the screen
     PendingOp op{};
     op.e = e;
     op.offsets_begin = SIZE_MAX;

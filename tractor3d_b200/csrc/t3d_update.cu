@@ -65,6 +65,7 @@ struct RwIn
 };
 
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // V = particles per thread per group, THREADS per CTA, SUB = groups per thread: a tile is V*THREADS*SUB
 // consecutive particles of one emitter and costs one look-back, so the scan frontier only has to advance
@@ -186,6 +187,16 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         if (animated) r.tf[l] = ld_f(col(RW_TIME_ON_FRAME) + i);
         if (need_frame) r.fr[l] = ld_i(col(RW_FRAME) + i);
     };
+    auto prefetch_mover = [&](uint32_t i)
+    {
+        prefetch_l2(rec + (size_t)i * REC_WORDS);
+        prefetch_l2(rot + (size_t)i * ROT_WORDS);
+        prefetch_l2(col(RW_ENERGY) + i);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) prefetch_l2(col(RW_COLOR + c) + i);
+        prefetch_l2(col(RW_SIZE) + i);
+        if (!animated) prefetch_l2(col(RW_TIME_ON_FRAME) + i);
+    };
     RwIn<V> cur;
     {
         const uint32_t k0 = first + tid * V;
@@ -298,29 +309,44 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     else if (warp == 0)
     {
         if (lane == 0) st_status(my_status, tag | kStatusAggregate | tile_dead);
+        // Every round inspects the 32 * kLook nearest predecessors not yet accounted for: each lane requests kLook status
+        // words at once (the windows further back travel while the nearest one is examined), so a tile that starts in the
+        // middle of a wave of ~300 concurrent tiles resolves its prefix in two or three L2 round trips instead of ten.
+        constexpr int kLook = 4;
         uint32_t excl = 0;
         int look = (int)jt - 1; // nearest predecessor, as a tile index inside the emitter
-        while (true)
+        bool resolved = false;
+        while (!resolved)
         {
-            const int idx = look - (int)lane;
-            unsigned long long s = tag | kStatusPrefix; // before the emitter's first tile: prefix 0
-            if (idx >= 0)
-            {
-                const unsigned long long* sp = tile_status + (it.tile_begin + (uint32_t)idx);
-                do
-                {
-                    s = ld_status(sp);
-                } while ((s >> 34) != (unsigned long long)epoch || ((s >> 32) & 3ull) == 0ull);
-            }
-            const bool is_prefix = ((s >> 32) & 3ull) == 2ull;
-            const unsigned pmask = __ballot_sync(0xffffffffu, is_prefix);
-            const int first_p = __ffs((int)pmask) - 1;
-            uint32_t contrib = (pmask == 0u || (int)lane <= first_p) ? (uint32_t)s : 0u;
+            unsigned long long st[kLook];
+            const unsigned long long* sp[kLook];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-            excl += contrib;
-            if (pmask != 0u) break;
-            look -= 32;
+            for (int w = 0; w < kLook; ++w)
+            {
+                const int idx = look - (int)lane - 32 * w;
+                sp[w] = idx >= 0 ? tile_status + (it.tile_begin + (uint32_t)idx) : nullptr;
+                st[w] = sp[w] ? ld_status(sp[w]) : (tag | kStatusPrefix); // before the emitter's first tile: prefix 0
+            }
+#pragma unroll
+            for (int w = 0; w < kLook; ++w)
+            {
+                if (resolved) break;
+                while (true) // until this window's 32 tiles have all published something in this launch
+                {
+                    const bool ready = (st[w] >> 34) == (unsigned long long)epoch && ((st[w] >> 32) & 3ull) != 0ull;
+                    if (__all_sync(0xffffffffu, ready)) break;
+                    if (!ready) st[w] = ld_status(sp[w]);
+                }
+                const bool is_prefix = ((st[w] >> 32) & 3ull) == 2ull;
+                const unsigned pmask = __ballot_sync(0xffffffffu, is_prefix);
+                const int first_p = __ffs((int)pmask) - 1;
+                uint32_t contrib = (pmask == 0u || (int)lane <= first_p) ? (uint32_t)st[w] : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                excl += contrib;
+                resolved = pmask != 0u;
+            }
+            look -= 32 * kLook;
         }
         if (lane == 0)
         {
@@ -463,7 +489,13 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 else
                 {
 #pragma unroll
-                    for (int l = 0; l < V; ++l) load_one(pn.mover[l] ? pn.src[l] : kn + l, nxt, l);
+                    for (int l = 0; l < V; ++l)
+                    {
+                        load_one(pn.mover[l] ? pn.src[l] : kn + l, nxt, l);
+                        // the rest of the mover (two records, energy, colour, size) is only needed once the slot is written:
+                        // ask L2 for it now, so that the loads of the next iteration find it there
+                        if (pn.mover[l]) prefetch_mover(pn.src[l]);
+                    }
                 }
             }
         }
@@ -821,8 +853,17 @@ static const Variant& pick(const Variant (&table)[N], const char* env_name, int&
 static int g_update_variant = -1, g_fused_variant = -1;
 static const Variant& variant() { return pick(kUpdate, "T3D_UPDATE_VARIANT", g_update_variant); }
 static const Variant& fused_variant() { return pick(kFused, "T3D_FUSED_VARIANT", g_fused_variant); }
+// A launch that is only a few waves of CTAs wide loses the idle part of its last wave; with half-size tiles the tail is
+// half as long (at ~3 % more per-tile overhead).  shape 0 = the variant above, shape 1 = its half-size sibling; only the
+// default variant has one (an explicit T3D_*_VARIANT is taken as is).
+static const Variant kUpdateSmall = T3D_UPDATE_SHAPE(2, 192, 6, 2);
+static const Variant kFusedSmall = T3D_FUSED_SHAPE(2, 192, 6, 2);
+static const Variant& shaped(const Variant& v, const Variant* table, const Variant& small_one, int shape)
+{
+    return (shape == 1 && &v == table) ? small_one : v;
+}
 
-int fused_tile_size() { return fused_variant().tile; }
+int fused_tile_size(int shape) { return shaped(fused_variant(), kFused, kFusedSmall, shape).tile; }
 // An update of a set of emitters directly followed by the draw of the same set can go out as one launch.
 // T3D_FUSED=1 always, T3D_FUSED=0 never, unset: when the runtime expects it to pay (see hold_for_fusion()).
 int fused_mode()
@@ -835,10 +876,26 @@ int fused_mode()
     }
     return v;
 }
-void launch_update_draw(void* stream, const UpdateLaunch& L) { fused_variant().launch((cudaStream_t)stream, L); }
+void launch_update_draw(void* stream, const UpdateLaunch& L, int shape)
+{
+    shaped(fused_variant(), kFused, kFusedSmall, shape).launch((cudaStream_t)stream, L);
+}
 
-int update_tile_size() { return variant().tile; }
+int update_tile_size(int shape) { return shaped(variant(), kUpdate, kUpdateSmall, shape).tile; }
 const char* update_variant_name() { return variant().name; }
-void launch_update(void* stream, const UpdateLaunch& L) { variant().launch((cudaStream_t)stream, L); }
+void launch_update(void* stream, const UpdateLaunch& L, int shape)
+{
+    shaped(variant(), kUpdate, kUpdateSmall, shape).launch((cudaStream_t)stream, L);
+}
+
+// 1 when the half-size tiles are expected to finish the launch sooner: tiles_big / tiles_small = tiles of the launch
+// with either shape, slots = CTAs the device runs at once.
+int pick_tile_shape(uint64_t tiles_big, uint64_t tiles_small, uint32_t slots)
+{
+    if (!slots || tiles_big >= 16ull * slots) return 0; // many waves: the tail does not matter
+    auto cost = [&](uint64_t tiles, double tile_cost) { return (double)((tiles + slots - 1) / slots) * tile_cost; };
+    // a half-size tile costs a little more than half a big one (per-tile prologue, look-back)
+    return cost(tiles_small, 0.53) < cost(tiles_big, 1.0) ? 1 : 0;
+}
 
 } // namespace t3d
