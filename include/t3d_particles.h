@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define T3D_ABI_VERSION 2
+#define T3D_ABI_VERSION 3
 
 typedef enum t3d_status {
     T3D_OK = 0,
@@ -77,7 +77,7 @@ enum {
 /* Emitter configuration = the reference's private configuration members, PE.h:824-877, in the
  * numeric types the reference stores them in (energy bounds are float there, PE.h:840-841). */
 typedef struct t3d_emitter_params {
-    uint32_t particle_count_max;   /* _particleCountMax; fixed at create */
+    uint32_t particle_count_max;   /* _particleCountMax; storage is sized for the value at create: it may be lowered (and raised back) later, never grown */
     uint32_t emission_rate;        /* _emissionRate, particles/s (PE.cpp:262-267) */
     int32_t ellipsoid;             /* _ellipsoid */
     float size_start_min, size_start_max, size_end_min, size_end_max;
@@ -175,6 +175,9 @@ int t3d_emitter_create(t3d_ctx* ctx, const t3d_emitter_params* params, t3d_emitt
  * The texture is not decoded; only the PNG header is read for width/height (PE.cpp:244-247). */
 int t3d_emitter_create_from_file(t3d_ctx* ctx, const char* url, t3d_emitter** out);
 /* Replaces ParticleEmitter::clone (PE.cpp:891-932): same configuration, no particles. */
+/* Replaces ParticleEmitter::create(Properties*) (PE.cpp:92-211, the overload src/scene/SceneLoader.cpp:320 calls):
+ * `particle` is a namespace named "particle" whose first child namespace is "sprite" (t3d_properties below). */
+int t3d_emitter_create_from_properties(t3d_ctx* ctx, const struct t3d_properties* particle, t3d_emitter** out);
 int t3d_emitter_clone(t3d_emitter* e, t3d_emitter** out);
 int t3d_emitter_destroy(t3d_emitter* e);
 
@@ -182,6 +185,10 @@ int t3d_emitter_destroy(t3d_emitter* e);
 int t3d_emitter_set_params(t3d_emitter* e, const t3d_emitter_params* params); /* capacity must not grow */
 int t3d_emitter_get_params(t3d_emitter* e, t3d_emitter_params* params);
 int t3d_emitter_set_emission_rate(t3d_emitter* e, uint32_t rate);                   /* PE.cpp:262-267 */
+/* Replaces ParticleEmitter::setTexture(Texture*, BlendMode) (PE.cpp:229-252) minus the GL objects: the new texture's size
+ * re-derives the texel ratios and the sprite table is reset to ONE frame covering the whole texture -- also when the size
+ * did not change (PE.cpp:249-251).  Nothing on the device depends on the texture size (particles carry a frame index). */
+int t3d_emitter_set_texture_size(t3d_emitter* e, uint32_t width, uint32_t height, int blend_mode);
 int t3d_emitter_set_sprite_tex_coords(t3d_emitter* e, uint32_t frame_count, const float* tex_coords); /* PE.cpp:512-523 */
 /* rects = frame_count x {x, y, width, height} in texels (PE.cpp:526-547) */
 int t3d_emitter_set_sprite_frame_rects(t3d_emitter* e, uint32_t frame_count, const float* rects);
@@ -282,6 +289,37 @@ uint32_t t3d_host_sprite_frame_coords(uint32_t frame_count, int width, int heigh
 size_t t3d_host_particle_draws(const int32_t* draws, size_t n, int ellipsoid, uint32_t frame_random_offset);
 /* Width and height of a PNG from its header: all ParticleEmitter ever asks of its texture (PE.cpp:244-247). */
 int t3d_host_png_size(const char* path, uint32_t* width, uint32_t* height);
+/* ---- Properties: the slice of tractor::Properties (include/scene/Properties.h, src/scene/Properties.cpp) that
+ * ParticleEmitter::create reads -- nested namespaces `name [id] { ... }` holding `key = value` strings, typed getters with
+ * the reference's conversions.  A handle names one namespace; the root returned by _load / _new owns the whole tree and
+ * is the only handle to free.  This is how a caller that already holds a parsed tree (SceneLoader.cpp:318-324) hands a
+ * `particle` namespace over without going through a file. */
+typedef struct t3d_properties t3d_properties;
+int t3d_properties_load(const char* url, t3d_properties** out);                       /* Properties::create(url) */
+int t3d_properties_new(const char* name_space, const char* id, t3d_properties** out); /* an empty root namespace */
+void t3d_properties_free(t3d_properties* root);
+int t3d_properties_set(t3d_properties* p, const char* key, const char* value);        /* Properties::setString */
+int t3d_properties_add_namespace(t3d_properties* p, const char* name_space, const char* id, t3d_properties** child);
+const char* t3d_properties_namespace(const t3d_properties* p);                        /* Properties::getNamespace() */
+const char* t3d_properties_id(const t3d_properties* p);                               /* Properties::getId() */
+size_t t3d_properties_namespace_count(const t3d_properties* p);
+t3d_properties* t3d_properties_get_namespace(t3d_properties* p, size_t index);        /* the walk of getNextNamespace() */
+size_t t3d_properties_count(const t3d_properties* p);
+const char* t3d_properties_key(const t3d_properties* p, size_t index);                /* the walk of getNextProperty() */
+const char* t3d_properties_value(const t3d_properties* p, size_t index);
+const char* t3d_properties_get(const t3d_properties* p, const char* key);             /* getString; NULL when absent */
+int t3d_properties_get_bool(const t3d_properties* p, const char* key, int default_value); /* Properties.cpp:940-944 */
+int t3d_properties_get_int(const t3d_properties* p, const char* key);                 /* :947-962 */
+long long t3d_properties_get_long(const t3d_properties* p, const char* key);          /* :981-994 */
+float t3d_properties_get_float(const t3d_properties* p, const char* key);             /* :965-978 */
+/* getVector3 / getVector4 (:1214-1251): dim = 3 or 4; returns 1 when the key held a well-formed vector, else 0 and zeros. */
+int t3d_properties_get_vector(const t3d_properties* p, const char* key, float* out, int dim);
+/* getPath: the value as it stands when that file exists, else relative to the directory of the file the tree was loaded
+ * from; T3D_ERR_IO when neither exists. */
+int t3d_properties_get_path(const t3d_properties* p, const char* key, char* out, size_t out_len);
+/* PE.cpp:92-184 on a `particle` namespace: params + sprite sheet description. */
+int t3d_particle_properties_parse(const t3d_properties* particle, t3d_emitter_params* params, uint32_t* frame_count,
+                                  int* sprite_width, int* sprite_height, char* texture_path, size_t texture_path_len);
 /* Parses a `.particle` file into params + sprite sheet description (PE.cpp:92-184). */
 int t3d_particle_file_parse(const char* url, t3d_emitter_params* params, uint32_t* frame_count,
                             int* sprite_width, int* sprite_height, char* texture_path, size_t texture_path_len);

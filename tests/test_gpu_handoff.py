@@ -178,6 +178,7 @@ def test_culling_skips_the_draw_of_an_emitter_outside_the_frustum():
         eg.update(S.DT); eo.update(S.DT)
         assert eg.pe.bounds() is not None
         assert eg.draw() == 1 and eg.vertices().shape[0] == n          # in view (the emitter sits at the origin)
+        eo.draw()   # (the reference latches its process-wide billboard rotation at the first quad it ever draws, SB.cpp:339)
         # move the whole view away: every corner of the box is beyond the right clip plane
         away = vp.copy().reshape(4, 4)   # rows of the column-major array = columns of the matrix
         away[3, 0] -= 1000.0 * 1.0       # clip.x = ... - 1000 * w for w ~ 9: far left of -w

@@ -279,6 +279,33 @@ __device__ __forceinline__ void rec_issue(unsigned char* stage_warp, const uint3
         if ((g >> 2) < n) cp_async16(stage_warp + rec_chunk_offset<V>(g / (V * 4u), g % (V * 4u)), rec_g + g * 4u);
     }
 }
+// The same copy when some slots of the group receive a mover (PE.cpp:825-828): idx[l] = the particle whose record belongs
+// in slot l of this lane's row -- the slot's own index, or the source of the move.  Every chunk of the stage is still
+// written by exactly one copy, so the mover's record simply arrives in place of the dead particle's.
+template <int V>
+__device__ __forceinline__ void rec_issue_indexed(unsigned char* stage_warp, const uint32_t* rec, uint32_t n, uint32_t lane,
+                                                  const uint32_t* idx)
+{
+#pragma unroll
+    for (int i = 0; i < V * 4; ++i)
+    {
+        const uint32_t g = (uint32_t)i * 32u + lane; // chunk of the warp's run
+        const uint32_t row = g / (V * 4u), p = g % (V * 4u);
+        uint32_t src = 0;
+#pragma unroll
+        for (int l = 0; l < V; ++l)
+        {
+            const uint32_t t = __shfl_sync(0xffffffffu, idx[l], (int)row);
+            if ((uint32_t)l == (p >> 2)) src = t;
+        }
+        if ((g >> 2) < n) cp_async16(stage_warp + rec_chunk_offset<V>(row, p), rec + (size_t)src * REC_WORDS + (p & 3u) * 4u);
+    }
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem)
+{
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
 // read back: record l of this lane's row, as 16 words
 template <int V>
 __device__ __forceinline__ void rec_read(const unsigned char* stage_warp, uint32_t lane, int l, uint32_t* w)

@@ -334,15 +334,20 @@ extern "C" int t3d_host_png_size(const char* path, uint32_t* width, uint32_t* he
     return T3D_OK;
 }
 
-extern "C" int t3d_particle_file_parse(const char* url, t3d_emitter_params* params, uint32_t* frame_count, int* sprite_width,
-                                       int* sprite_height, char* texture_path, size_t texture_path_len)
+// A parsed (or hand-built) namespace tree handed across the ABI.  The root owns the whole tree.
+struct t3d_properties
 {
-    if (!url || !params) return host_fail(T3D_ERR_INVALID, "t3d_particle_file_parse: null argument");
-    Ns root;
-    std::string err;
-    if (!parse_file(url, &root, &err)) return host_fail(T3D_ERR_IO, "Failed to create particle emitter from file: %s", err.c_str());
-    // PE.cpp:85-86, 94: the (first) top-level namespace must be `particle`.
-    const Ns* particle = root.children.empty() ? nullptr : root.children.front().get();
+    Ns* ns{ nullptr };          // this namespace
+    std::string dir;            // directory of the file it came from ("" for hand-built trees): relative paths resolve here
+    std::unique_ptr<Ns> owned;  // set on roots
+    std::vector<std::unique_ptr<t3d_properties>> views; // child handles given out, kept alive with the root
+    t3d_properties* root{ nullptr };
+};
+
+// PE.cpp:92-211 on a `particle` namespace: its first child must be `sprite`; conversions as Properties.cpp's getters.
+static int params_from_namespace(const Ns* particle, const std::string& dir, t3d_emitter_params* params, uint32_t* frame_count,
+                                 int* sprite_width, int* sprite_height, char* texture_path, size_t texture_path_len)
+{
     if (!particle || particle->name != "particle")
         return host_fail(T3D_ERR_IO, "Properties object must be non-null and have namespace equal to 'particle'.");
     // PE.cpp:101-106: the first child namespace must be `sprite`.
@@ -356,10 +361,7 @@ extern "C" int t3d_particle_file_parse(const char* url, t3d_emitter_params* para
     std::string tex = *path;
     if (!file_exists(tex))
     {
-        std::string dir(url);
-        const auto slash = dir.find_last_of('/');
-        dir = slash == std::string::npos ? "" : dir.substr(0, slash + 1);
-        if (file_exists(dir + tex))
+        if (!dir.empty() && file_exists(dir + tex))
             tex = dir + tex;
         else
             return host_fail(T3D_ERR_IO, "Failed to load particle emitter: required image file path ('path') is missing.");
@@ -389,22 +391,17 @@ extern "C" int t3d_particle_file_parse(const char* url, t3d_emitter_params* para
     p.size_end_max = get_float(particle, "sizeEndMax");
     p.energy_min = (float)get_long(particle, "energyMin"); // long -> setEnergy(long, long) -> float members, PE.cpp:150-151, 381-385
     p.energy_max = (float)get_long(particle, "energyMax");
-    get_vec(particle, "colorStart", p.color_start, 4);
-    get_vec(particle, "colorStartVar", p.color_start_var, 4);
-    get_vec(particle, "colorEnd", p.color_end, 4);
-    get_vec(particle, "colorEndVar", p.color_end_var, 4);
-    get_vec(particle, "position", p.position, 3);
-    get_vec(particle, "positionVar", p.position_var, 3);
-    get_vec(particle, "velocity", p.velocity, 3);
-    get_vec(particle, "velocityVar", p.velocity_var, 3);
-    get_vec(particle, "acceleration", p.acceleration, 3);
-    get_vec(particle, "accelerationVar", p.acceleration_var, 3);
+    struct { const char* key; float* dst; int dim; } vecs[] = {
+        { "colorStart", p.color_start, 4 }, { "colorStartVar", p.color_start_var, 4 }, { "colorEnd", p.color_end, 4 },
+        { "colorEndVar", p.color_end_var, 4 }, { "position", p.position, 3 }, { "positionVar", p.position_var, 3 },
+        { "velocity", p.velocity, 3 }, { "velocityVar", p.velocity_var, 3 }, { "acceleration", p.acceleration, 3 },
+        { "accelerationVar", p.acceleration_var, 3 }, { "rotationAxis", p.rotation_axis, 3 }, { "rotationAxisVar", p.rotation_axis_var, 3 },
+    };
+    for (auto& v : vecs) get_vec(particle, v.key, v.dst, v.dim);
     p.rotation_per_particle_speed_min = get_float(particle, "rotationPerParticleSpeedMin");
     p.rotation_per_particle_speed_max = get_float(particle, "rotationPerParticleSpeedMax");
     p.rotation_speed_min = get_float(particle, "rotationSpeedMin");
     p.rotation_speed_max = get_float(particle, "rotationSpeedMax");
-    get_vec(particle, "rotationAxis", p.rotation_axis, 3);
-    get_vec(particle, "rotationAxisVar", p.rotation_axis_var, 3);
     p.orbit_position = get_bool(particle, "orbitPosition");
     p.orbit_velocity = get_bool(particle, "orbitVelocity");
     p.orbit_acceleration = get_bool(particle, "orbitAcceleration");
@@ -417,6 +414,164 @@ extern "C" int t3d_particle_file_parse(const char* url, t3d_emitter_params* para
     if (texture_path && texture_path_len) snprintf(texture_path, texture_path_len, "%s", tex.c_str());
     return T3D_OK;
 }
+
+static std::string directory_of(const char* url)
+{
+    std::string dir(url);
+    const auto slash = dir.find_last_of('/');
+    return slash == std::string::npos ? "" : dir.substr(0, slash + 1);
+}
+
+extern "C" int t3d_particle_file_parse(const char* url, t3d_emitter_params* params, uint32_t* frame_count, int* sprite_width,
+                                       int* sprite_height, char* texture_path, size_t texture_path_len)
+{
+    if (!url || !params) return host_fail(T3D_ERR_INVALID, "t3d_particle_file_parse: null argument");
+    Ns root;
+    std::string err;
+    if (!parse_file(url, &root, &err)) return host_fail(T3D_ERR_IO, "Failed to create particle emitter from file: %s", err.c_str());
+    // PE.cpp:85-86, 94: the (first) top-level namespace must be `particle`.
+    const Ns* particle = root.children.empty() ? nullptr : root.children.front().get();
+    return params_from_namespace(particle, directory_of(url), params, frame_count, sprite_width, sprite_height, texture_path, texture_path_len);
+}
+
+// ---- t3d_properties: the slice of tractor::Properties (src/scene/Properties.cpp) the particle path reads ----
+static t3d_properties* view_of(t3d_properties* root, Ns* ns)
+{
+    for (auto& v : root->views)
+        if (v->ns == ns) return v.get();
+    auto v = std::make_unique<t3d_properties>();
+    v->ns = ns;
+    v->dir = root->dir;
+    v->root = root;
+    root->views.push_back(std::move(v));
+    return root->views.back().get();
+}
+
+extern "C" {
+
+int t3d_properties_load(const char* url, t3d_properties** out)
+{
+    if (!url || !out) return host_fail(T3D_ERR_INVALID, "t3d_properties_load: null argument");
+    *out = nullptr;
+    auto root = std::make_unique<t3d_properties>();
+    root->owned = std::make_unique<Ns>();
+    std::string err;
+    if (!parse_file(url, root->owned.get(), &err)) return host_fail(T3D_ERR_IO, "Failed to load properties from '%s': %s", url, err.c_str());
+    root->ns = root->owned.get();
+    root->dir = directory_of(url);
+    root->root = root.get();
+    *out = root.release();
+    return T3D_OK;
+}
+
+int t3d_properties_new(const char* name_space, const char* id, t3d_properties** out)
+{
+    if (!out) return host_fail(T3D_ERR_INVALID, "t3d_properties_new: null argument");
+    auto root = std::make_unique<t3d_properties>();
+    root->owned = std::make_unique<Ns>();
+    root->owned->name = name_space ? name_space : "";
+    root->owned->id = id ? id : "";
+    root->ns = root->owned.get();
+    root->root = root.get();
+    *out = root.release();
+    return T3D_OK;
+}
+
+void t3d_properties_free(t3d_properties* root)
+{
+    if (root && root->root == root) delete root;
+}
+
+int t3d_properties_set(t3d_properties* p, const char* key, const char* value)
+{
+    if (!p || !key) return host_fail(T3D_ERR_INVALID, "t3d_properties_set: null argument");
+    for (auto& kv : p->ns->props)
+        if (kv.first == key)
+        {
+            kv.second = value ? value : "";
+            return T3D_OK;
+        }
+    p->ns->props.emplace_back(key, value ? value : "");
+    return T3D_OK;
+}
+
+int t3d_properties_add_namespace(t3d_properties* p, const char* name_space, const char* id, t3d_properties** child)
+{
+    if (!p || !name_space) return host_fail(T3D_ERR_INVALID, "t3d_properties_add_namespace: null argument");
+    auto ns = std::make_unique<Ns>();
+    ns->name = name_space;
+    ns->id = id ? id : "";
+    Ns* raw = ns.get();
+    p->ns->children.push_back(std::move(ns));
+    if (child) *child = view_of(p->root, raw);
+    return T3D_OK;
+}
+
+const char* t3d_properties_namespace(const t3d_properties* p) { return p ? p->ns->name.c_str() : ""; }
+const char* t3d_properties_id(const t3d_properties* p) { return p ? p->ns->id.c_str() : ""; }
+size_t t3d_properties_namespace_count(const t3d_properties* p) { return p ? p->ns->children.size() : 0; }
+t3d_properties* t3d_properties_get_namespace(t3d_properties* p, size_t index)
+{
+    if (!p || index >= p->ns->children.size()) return nullptr;
+    return view_of(p->root, p->ns->children[index].get());
+}
+size_t t3d_properties_count(const t3d_properties* p) { return p ? p->ns->props.size() : 0; }
+const char* t3d_properties_key(const t3d_properties* p, size_t index)
+{
+    return (p && index < p->ns->props.size()) ? p->ns->props[index].first.c_str() : nullptr;
+}
+const char* t3d_properties_value(const t3d_properties* p, size_t index)
+{
+    return (p && index < p->ns->props.size()) ? p->ns->props[index].second.c_str() : nullptr;
+}
+const char* t3d_properties_get(const t3d_properties* p, const char* key)
+{
+    if (!p || !key) return nullptr;
+    const std::string* v = p->ns->find(key);
+    return v ? v->c_str() : nullptr;
+}
+
+int t3d_properties_get_bool(const t3d_properties* p, const char* key, int default_value)
+{
+    if (!p || !key) return default_value;
+    const std::string* v = p->ns->find(key);
+    return (v && !v->empty()) ? (*v == "true") : default_value; // Properties.cpp:940-944
+}
+int t3d_properties_get_int(const t3d_properties* p, const char* key) { return (p && key) ? get_int(p->ns, key) : 0; }
+long long t3d_properties_get_long(const t3d_properties* p, const char* key) { return (p && key) ? get_long(p->ns, key) : 0; }
+float t3d_properties_get_float(const t3d_properties* p, const char* key) { return (p && key) ? get_float(p->ns, key) : 0.0f; }
+int t3d_properties_get_vector(const t3d_properties* p, const char* key, float* out, int dim)
+{
+    if (!p || !key || !out || (dim != 3 && dim != 4)) return 0;
+    const std::string* v = p->ns->find(key);
+    get_vec(p->ns, key, out, dim);
+    if (!v || v->empty()) return 0;
+    float t[4];
+    return (dim == 3 ? sscanf(v->c_str(), "%f,%f,%f", &t[0], &t[1], &t[2]) : sscanf(v->c_str(), "%f,%f,%f,%f", &t[0], &t[1], &t[2], &t[3])) == dim;
+}
+int t3d_properties_get_path(const t3d_properties* p, const char* key, char* out, size_t out_len)
+{
+    if (!p || !key || !out || !out_len) return host_fail(T3D_ERR_INVALID, "t3d_properties_get_path: null argument");
+    const std::string* v = p->ns->find(key);
+    if (!v || v->empty()) return host_fail(T3D_ERR_IO, "no property '%s'", key);
+    std::string path = *v;
+    if (!file_exists(path))
+    {
+        if (p->dir.empty() || !file_exists(p->dir + path)) return host_fail(T3D_ERR_IO, "'%s' does not name an existing file", v->c_str());
+        path = p->dir + path;
+    }
+    snprintf(out, out_len, "%s", path.c_str());
+    return T3D_OK;
+}
+
+int t3d_particle_properties_parse(const t3d_properties* particle, t3d_emitter_params* params, uint32_t* frame_count, int* sprite_width,
+                                  int* sprite_height, char* texture_path, size_t texture_path_len)
+{
+    if (!particle || !params) return host_fail(T3D_ERR_INVALID, "t3d_particle_properties_parse: null argument");
+    return params_from_namespace(particle->ns, particle->dir, params, frame_count, sprite_width, sprite_height, texture_path, texture_path_len);
+}
+
+} // extern "C"
 
 extern "C" int t3d_particle_file_save(const char* url, const char* name, const t3d_emitter_params* p, uint32_t frame_count,
                                       int sprite_width, int sprite_height, const char* texture_path)

@@ -17,7 +17,8 @@ int draw_tile_size(uint32_t n_items); // quads per draw CTA for a launch over n_
 const char* update_variant_name();
 constexpr int kSpawnThreads = 256; // spawn and draw: one particle per thread
 constexpr int kDrawThreads = 256;
-constexpr int kMaxSmemFrames = 256; // sprite uv tables up to this many frames are staged in shared memory
+constexpr int kMaxSmemFrames = 256; // sprite uv tables up to this many frames are staged in shared memory (k_draw)
+constexpr int kMaxFusedFrames = 64; // the fused update + draw pass has 1 KB for the table; larger sheets take the two launches
 
 // Segment alignment inside a slab, in particles (a warp of the update kernel copies the life records of 64
 // consecutive particles as one 4 KB run).

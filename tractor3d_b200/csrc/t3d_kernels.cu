@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __rest
     const uint64_t serial0 = d->cnt[parity].serial;
     const uint32_t cap = d->c.capacity;
     // PE.cpp:293-296: never go over particleCountMax.
-    const uint32_t room = cap - count0;
+    const uint32_t room = cap > count0 ? cap - count0 : 0u; // (the cap may have been lowered below the live count: nothing spawns)
     const uint32_t n = it.request < room ? it.request : room;
     const uint32_t tile_first = (tile - it.tile_begin) * kSpawnThreads;
     const uint32_t i = tile_first + threadIdx.x;

@@ -228,6 +228,7 @@ struct t3d_emitter
     EmitterDev* dev{ nullptr };
     int slab{ -1 };
     uint32_t seg_offset{ 0 }, seg_capacity{ 0 };
+    uint32_t alloc_capacity{ 0 }; // particleCountMax at create: what the storage holds; p.particle_count_max may be set lower
     float* uv_dev{ nullptr };
     uint32_t uv_cap{ 0 };
     uint32_t parity{ 0 };
@@ -961,7 +962,7 @@ static bool can_fuse(const t3d_ctx* c)
     for (size_t k = 0; k < c->held.size(); ++k)
     {
         if (c->held[k].e != c->pending[k].e) return false;
-        if (c->held[k].e->frame_count > (uint32_t)kMaxSmemFrames) return false; // the fused pass reads uv from shared memory only
+        if (c->held[k].e->frame_count > (uint32_t)kMaxFusedFrames) return false; // the fused pass reads uv from shared memory only
         any_spin = any_spin || c->held[k].e->may_spin;
     }
     if (c->rot_mode == T3D_ROT_FROZEN && !c->frozen_latched && any_spin) return false;
@@ -1278,7 +1279,9 @@ static int prepare_emit(t3d_emitter* e, uint32_t n, PendingOp* op)
         const uint64_t ub = (uint64_t)e->count_ub + n;
         if (n && ub <= cap) // all of them fit for sure
             e->alive_budget_ms = std::max(e->alive_budget_ms, (double)std::floor(std::min(e->p.energy_min, e->p.energy_max)));
-        e->count_ub = (uint32_t)std::min<uint64_t>(ub, cap);
+        // (a cap lowered below the live count spawns nothing -- the reference's unsigned `max - count` would overrun its
+        // array there -- and must not pull the bound under the particles that are already alive)
+        e->count_ub = std::max(e->count_ub, (uint32_t)std::min<uint64_t>(ub, cap));
         return T3D_OK;
     }
     // Host draws: the reference consumes draws only for particles that fit, so the clamp must be exact here.
@@ -1286,7 +1289,7 @@ static int prepare_emit(t3d_emitter* e, uint32_t n, PendingOp* op)
     {
         uint32_t cnt;
         T3D_TRY(exact_count(e, &cnt));
-        if ((uint64_t)cnt + n > cap) n = cap - cnt;
+        if ((uint64_t)cnt + n > cap) n = cap > cnt ? cap - cnt : 0;
     }
     op->emit_n = n;
     if (n)
@@ -1541,7 +1544,9 @@ int t3d_ctx_copy_wait(t3d_ctx* c, uint64_t ticket)
 // ---- lifecycle ----
 static void apply_params(t3d_emitter* e, const t3d_emitter_params* p)
 {
-    const uint32_t cap = e->p.particle_count_max;
+    // PE.h:237 only rewrites the field; the storage keeps the size it got at create, so the field may go down (the spawn
+    // clamp of PE.cpp:293-296 then uses the lower value) and back up to that size, never beyond (t3d_emitter_set_params)
+    const uint32_t cap = std::min(p->particle_count_max, e->alloc_capacity);
     const float tw = e->p.texture_width, th = e->p.texture_height;
     e->p = *p;
     e->p.particle_count_max = cap;
@@ -1564,6 +1569,7 @@ int t3d_emitter_create(t3d_ctx* c, const t3d_emitter_params* p, t3d_emitter** ou
     t3d_emitter* e = new t3d_emitter();
     e->ctx = c;
     e->p = *p;
+    e->alloc_capacity = p->particle_count_max;
     int rc = alloc_segment(c, p->particle_count_max, &e->slab, &e->seg_offset, &e->seg_capacity);
     if (rc == T3D_OK) rc = alloc_dev_record(c, &e->dev);
     if (rc != T3D_OK)
@@ -1603,6 +1609,19 @@ int t3d_emitter_create_from_file(t3d_ctx* c, const char* url, t3d_emitter** out)
     return t3d_emitter_set_sprite_frame_coords(*out, frame_count, sw, sh);
 }
 
+int t3d_emitter_create_from_properties(t3d_ctx* c, const t3d_properties* particle, t3d_emitter** out)
+{
+    if (!c || !particle || !out) return fail(T3D_ERR_INVALID, "t3d_emitter_create_from_properties: null argument");
+    t3d_emitter_params p;
+    uint32_t frame_count = 0;
+    int sw = 0, sh = 0;
+    char tex[1024];
+    int rc = t3d_particle_properties_parse(particle, &p, &frame_count, &sw, &sh, tex, sizeof(tex));
+    if (rc != T3D_OK) return fail(rc, "%s", t3d_host_last_error());
+    T3D_TRY(t3d_emitter_create(c, &p, out));
+    return t3d_emitter_set_sprite_frame_coords(*out, frame_count, sw, sh); // PE.cpp:207
+}
+
 int t3d_emitter_clone(t3d_emitter* e, t3d_emitter** out)
 {
     if (!e || !out) return fail(T3D_ERR_INVALID, "null argument");
@@ -1637,9 +1656,10 @@ int t3d_emitter_set_params(t3d_emitter* e, const t3d_emitter_params* p)
 {
     if (!e || !p) return fail(T3D_ERR_INVALID, "null argument");
     if (p->emission_rate == 0) return fail(T3D_ERR_INVALID, "emission_rate must be > 0 (PE.cpp:264)");
-    if (p->particle_count_max > e->p.particle_count_max)
-        return fail(T3D_ERR_CAPACITY, "particle_count_max cannot grow past the %u fixed at create (asked %u)",
-                    e->p.particle_count_max, p->particle_count_max);
+    if (p->particle_count_max > e->alloc_capacity)
+        return fail(T3D_ERR_CAPACITY, "particle_count_max cannot grow past the %u the storage was sized for at create (asked %u)",
+                    e->alloc_capacity, p->particle_count_max);
+    if (p->particle_count_max == 0) return fail(T3D_ERR_INVALID, "particle_count_max must be > 0");
     if (e->queued || e->held) T3D_TRY(flush(e->ctx));
     apply_params(e, p);
     return T3D_OK;
@@ -1658,6 +1678,20 @@ int t3d_emitter_set_emission_rate(t3d_emitter* e, uint32_t rate)
     e->p.emission_rate = rate;
     e->time_per_emission = 1000.0f / (float)rate;
     return T3D_OK;
+}
+
+int t3d_emitter_set_texture_size(t3d_emitter* e, uint32_t width, uint32_t height, int blend_mode)
+{
+    if (!e || !width || !height) return fail(T3D_ERR_INVALID, "setTexture: the texture must have a size (PE.cpp:244-247)");
+    if (blend_mode < T3D_BLEND_NONE || blend_mode > T3D_BLEND_MULTIPLIED) return fail(T3D_ERR_INVALID, "Unsupported blend mode (%d).", blend_mode);
+    if (e->queued || e->held) T3D_TRY(flush(e->ctx));
+    e->p.blend_mode = blend_mode;           // PE.cpp:243
+    e->p.texture_width = (float)width;      // PE.cpp:244-247
+    e->p.texture_height = (float)height;
+    e->tex_w_ratio = 1.0f / (float)width;
+    e->tex_h_ratio = 1.0f / (float)height;
+    const float full[4] = { 0.0f, 0.0f, (float)width, (float)height }; // PE.cpp:249-251: one frame, the whole texture
+    return t3d_emitter_set_sprite_frame_rects(e, 1, full);
 }
 
 static int install_tex_coords(t3d_emitter* e, uint32_t frame_count)

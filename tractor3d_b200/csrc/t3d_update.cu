@@ -33,6 +33,7 @@
 // Numerics: --fmad=false, reference evaluation order (see t3d_kernels.cu).
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -91,10 +92,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     constexpr int WG = 32 * V;                  // particles per warp per group
     constexpr int kRecWarp = WG * REC_WORDS * 4; // bytes of life records per warp per group
     constexpr int kStageWarp = WG * kQuadBytes;  // bytes of vertex staging per warp: its 32 * V consecutive quads
+    constexpr int kSideLane = 48;                // bytes per lane of the mover side stage: rotation record + 6 rw words
+    constexpr int kSideWarp = 32 * kSideLane;
     constexpr int GROUP = V * THREADS;  // particles per group
     constexpr int TILE = GROUP * SUB;
     constexpr int WARPS = THREADS / 32;
-    __shared__ __align__(16) float s_uv[FUSED ? kMaxSmemFrames * 4 : 4];
+    __shared__ __align__(16) float s_uv[FUSED ? kMaxFusedFrames * 4 : 4];
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warp[SUB][WARPS];
     __shared__ uint32_t s_excl;
@@ -145,6 +148,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     unsigned char* const dyn = dyn_smem + ((128u - ((uint32_t)__cvta_generic_to_shared(dyn_smem) & 127u)) & 127u);
     unsigned char* const rec_warp = dyn + (size_t)warp * kRecWarp;
     unsigned char* const stage_warp = dyn + (size_t)WARPS * kRecWarp + (size_t)warp * kStageWarp;
+    // the words of a mover that the slot's thread only passes on (rotation record, energy, colour, size) land here,
+    // requested one group ahead like everything else: [0,16) rotation record, [16,40) energy, colour x 4, size
+    unsigned char* const side_lane = dyn + (size_t)WARPS * (kRecWarp + (FUSED ? kStageWarp : 0)) + (size_t)warp * kSideWarp + lane * kSideLane;
 
     // ---- phase A: the energy column of the whole tile -> dead flags (PE.cpp:753-755: `long -= float`, `> 0`) ----
     // Issued before the live count has arrived: every slot below the padded segment size is safe to read.
@@ -184,8 +190,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         r.vy[l] = ld_f(col(RW_VEL + 1) + i);
         r.vz[l] = ld_f(col(RW_VEL + 2) + i);
         r.ang[l] = ld_f(col(RW_ANGLE) + i);
-        if (animated) r.tf[l] = ld_f(col(RW_TIME_ON_FRAME) + i);
-        if (need_frame) r.fr[l] = ld_i(col(RW_FRAME) + i);
+        r.tf[l] = ld_f(col(RW_TIME_ON_FRAME) + i); // (a mover brings these two along even when the emitter does not animate)
+        r.fr[l] = ld_i(col(RW_FRAME) + i);
     };
     auto prefetch_mover = [&](uint32_t i)
     {
@@ -195,7 +201,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 #pragma unroll
         for (int c = 0; c < 4; ++c) prefetch_l2(col(RW_COLOR + c) + i);
         prefetch_l2(col(RW_SIZE) + i);
-        if (!animated) prefetch_l2(col(RW_TIME_ON_FRAME) + i);
     };
     RwIn<V> cur;
     {
@@ -231,9 +236,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             up[k] = di.up[k];
         }
         vtx = di.vtx;
-        // the host only fuses emitters whose uv table fits (frame_count <= kMaxSmemFrames)
+        // the host only fuses emitters whose uv table fits (frame_count <= kMaxFusedFrames)
         const float* uv_g = di.uv;
-        const uint32_t uv_words = (it.frame_count < (uint32_t)kMaxSmemFrames ? it.frame_count : (uint32_t)kMaxSmemFrames) * 4u;
+        const uint32_t uv_words = (it.frame_count < (uint32_t)kMaxFusedFrames ? it.frame_count : (uint32_t)kMaxFusedFrames) * 4u;
         for (uint32_t q = tid; q < uv_words; q += THREADS) s_uv[q] = uv_g[q]; // visible after the scan's barrier
     }
     if (BOUNDS && tid < 6) s_box[tid] = tid < 3 ? 0xffffffffu : 0u; // min of nothing, max of nothing (ordered encoding)
@@ -442,7 +447,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             {
 #pragma unroll
                 for (int l = 0; l < V; ++l)
-                    if (p0.mover[l]) load_one(p0.src[l], cur, l);
+                    if (p0.mover[l])
+                    {
+                        load_one(p0.src[l], cur, l);
+                        prefetch_mover(p0.src[l]); // the rest is fetched when the slot is written (group 0 only)
+                    }
             }
         }
     }
@@ -458,50 +467,111 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         Plan p;
         make_plan(s, k0, p);
 
-        // -- the warp's life records of this group have landed: every lane takes its own, then the warp requests the
-        //    next group's into the same stage --
+        // -- the warp's life records of this group have landed: every lane takes its own.  A slot that receives a mover
+        //    (PE.cpp:825-828) finds the MOVER's record there: it was requested in the dead particle's place, one group
+        //    ahead (below); the words of the mover that this thread only passes on came through the side stage.  Group 0
+        //    was requested before the prefix was known: its movers are fetched directly, further down. --
+        const bool staged = s > 0;
+        bool fastm[V]; // the thread's first mover of the group: the side stage holds one particle's extras per lane
+        {
+            bool taken = false;
+#pragma unroll
+            for (int l = 0; l < V; ++l)
+            {
+                fastm[l] = staged && p.mover[l] && !taken;
+                taken = taken || p.mover[l];
+            }
+        }
         uint32_t rc[V][REC_WORDS];
+        float col_out[4][V], size_out[V];
         cp_async_wait<0>();
         __syncwarp();
 #pragma unroll
         for (int l = 0; l < V; ++l) rec_read<V>(rec_warp, lane, l, rc[l]);
-        __syncwarp();
-        const uint32_t wn = w0 + GROUP;
-        if (s + 1 < SUB && wn < N)
-            rec_issue<V>(rec_warp, rec + (size_t)wn * REC_WORDS, cap - wn < (uint32_t)WG ? cap - wn : (uint32_t)WG, lane);
-        cp_async_commit();
-
-        // -- the next group's rw words: the slot's own, or (dead slot) those of the original that takes its place --
-        RwIn<V> nxt;
+        if (staged && p.any_mover)
         {
-            const uint32_t kn = k0 + GROUP;
-            if (s + 1 < SUB && kn < cap)
-            {
-                bool plain = true;
-                Plan pn;
-                if (need_prefix && kn < N)
-                {
-                    make_plan(s + 1, kn, pn);
-                    plain = !pn.any_mover;
-                }
-                if (plain)
-                    load_own(kn, nxt);
-                else
-                {
 #pragma unroll
-                    for (int l = 0; l < V; ++l)
-                    {
-                        load_one(pn.mover[l] ? pn.src[l] : kn + l, nxt, l);
-                        // the rest of the mover (two records, energy, colour, size) is only needed once the slot is written:
-                        // ask L2 for it now, so that the loads of the next iteration find it there
-                        if (pn.mover[l]) prefetch_mover(pn.src[l]);
-                    }
+            for (int l = 0; l < V; ++l)
+            {
+                if (!p.mover[l]) continue;
+                uint4* rdst = reinterpret_cast<uint4*>(rec + (size_t)(k0 + l) * REC_WORDS);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) rdst[c] = make_uint4(rc[l][c * 4], rc[l][c * 4 + 1], rc[l][c * 4 + 2], rc[l][c * 4 + 3]);
+                if (!fastm[l]) continue;
+                const uint4 ro = *reinterpret_cast<const uint4*>(side_lane);
+                const uint4 w0s = *reinterpret_cast<const uint4*>(side_lane + 16);
+                const uint2 w1s = *reinterpret_cast<const uint2*>(side_lane + 32);
+                *reinterpret_cast<uint4*>(rot + (size_t)(k0 + l) * ROT_WORDS) = ro;
+                p.e[l] = (int)w0s.x;
+                col_out[0][l] = __uint_as_float(w0s.y);
+                col_out[1][l] = __uint_as_float(w0s.z);
+                col_out[2][l] = __uint_as_float(w0s.w);
+                col_out[3][l] = __uint_as_float(w1s.x);
+                size_out[l] = __uint_as_float(w1s.y);
+            }
+        }
+        __syncwarp();
+
+        // -- the next group: its plan, its records (movers' in place of the dead), its rw words (the slot's own, or those
+        //    of the original that takes its place) --
+        const bool more = s + 1 < SUB;
+        const uint32_t wn = w0 + GROUP, kn = k0 + GROUP;
+        Plan pn;
+        bool mv_next = false;
+        if (more && need_prefix && kn < N)
+        {
+            make_plan(s + 1, kn, pn);
+            mv_next = pn.any_mover;
+        }
+        const bool warp_mv = need_prefix && __any_sync(0xffffffffu, mv_next);
+        if (more && wn < N)
+        {
+            const uint32_t nrec = cap - wn < (uint32_t)WG ? cap - wn : (uint32_t)WG;
+            if (!warp_mv)
+                rec_issue<V>(rec_warp, rec + (size_t)wn * REC_WORDS, nrec, lane);
+            else
+            {
+                uint32_t idx[V];
+#pragma unroll
+                for (int l = 0; l < V; ++l) idx[l] = (mv_next && pn.mover[l]) ? pn.src[l] : kn + l;
+                rec_issue_indexed<V>(rec_warp, rec, nrec, lane, idx);
+            }
+        }
+        if (mv_next)
+        {
+            bool taken = false;
+#pragma unroll
+            for (int l = 0; l < V; ++l)
+            {
+                if (!pn.mover[l]) continue;
+                const uint32_t i = pn.src[l];
+                if (!taken)
+                {
+                    cp_async16(side_lane, rot + (size_t)i * ROT_WORDS);
+                    cp_async4(side_lane + 16, col(RW_ENERGY) + i);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) cp_async4(side_lane + 20 + 4 * c, col(RW_COLOR + c) + i);
+                    cp_async4(side_lane + 36, col(RW_SIZE) + i);
                 }
+                else
+                    prefetch_mover(i); // a second mover in the same thread is fetched when its slot is written: ask L2 for it now
+                taken = true;
+            }
+        }
+        cp_async_commit();
+        RwIn<V> nxt;
+        if (more && kn < cap)
+        {
+            if (!mv_next)
+                load_own(kn, nxt);
+            else
+            {
+#pragma unroll
+                for (int l = 0; l < V; ++l) load_one(pn.mover[l] ? pn.src[l] : kn + l, nxt, l);
             }
         }
 
         // -- PE.cpp:757-819 on the particles that are alive --
-        float col_out[4][V], size_out[V];
         float ax[V], ay[V], az[V];
 #pragma unroll
         for (int l = 0; l < V; ++l)
@@ -574,25 +644,28 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             }
         }
 
-        // -- PE.cpp:825-828: a dead slot takes over the mover as it stands.  Its motion words came with the prefetch; the
-        //    rest of the particle -- energy, colour, size and its two records -- is fetched here (contiguous whole-sector
-        //    copies for the records).  This wait only costs the threads that own a dead slot. --
+        // -- movers that did not come through the stages: those of group 0 (requested before the prefix was known) and a
+        //    thread's second mover of a group.  Their motion words came with the prefetch; the rest is fetched here, from
+        //    L2 where the prefetch got there in time. --
         if (p.any_mover)
         {
 #pragma unroll
             for (int l = 0; l < V; ++l)
             {
-                if (!p.mover[l]) continue;
+                if (!p.mover[l] || fastm[l]) continue;
                 const uint32_t i = p.src[l];
-                const uint4* rsrc = reinterpret_cast<const uint4*>(rec + (size_t)i * REC_WORDS);
-                const uint4 r0 = rsrc[0], r1 = rsrc[1], r2 = rsrc[2], r3 = rsrc[3];
+                if (!staged)
+                {
+                    const uint4* rsrc = reinterpret_cast<const uint4*>(rec + (size_t)i * REC_WORDS);
+                    const uint4 r0 = rsrc[0], r1 = rsrc[1], r2 = rsrc[2], r3 = rsrc[3];
+                    uint4* rdst = reinterpret_cast<uint4*>(rec + (size_t)(k0 + l) * REC_WORDS);
+                    rdst[0] = r0; rdst[1] = r1; rdst[2] = r2; rdst[3] = r3;
+                }
                 const uint4 ro = *reinterpret_cast<const uint4*>(rot + (size_t)i * ROT_WORDS);
                 p.e[l] = ld_i(col(RW_ENERGY) + i);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) col_out[c][l] = ld_f(col(RW_COLOR + c) + i);
                 size_out[l] = ld_f(col(RW_SIZE) + i);
-                uint4* rdst = reinterpret_cast<uint4*>(rec + (size_t)(k0 + l) * REC_WORDS);
-                rdst[0] = r0; rdst[1] = r1; rdst[2] = r2; rdst[3] = r3;
                 *reinterpret_cast<uint4*>(rot + (size_t)(k0 + l) * ROT_WORDS) = ro;
             }
         }
@@ -679,9 +752,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 for (int l = 0; l < V; ++l)
                 {
                     if (!p.mover[l]) continue;
-                    col(RW_TIME_ON_FRAME)[k0 + l] = __ldcs(col(RW_TIME_ON_FRAME) + p.src[l]);
-                    if (!need_frame) col(RW_FRAME)[k0 + l] = __ldcs(col(RW_FRAME) + p.src[l]);
-                    else col(RW_FRAME)[k0 + l] = (uint32_t)cur.fr[l];
+                    col(RW_TIME_ON_FRAME)[k0 + l] = __float_as_uint(cur.tf[l]);
+                    col(RW_FRAME)[k0 + l] = (uint32_t)cur.fr[l];
                 }
             }
         }
@@ -711,9 +783,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 }
                 else if (p.mover[l])
                 {
-                    col(RW_TIME_ON_FRAME)[k] = __ldcs(col(RW_TIME_ON_FRAME) + p.src[l]);
-                    if (!need_frame) col(RW_FRAME)[k] = __ldcs(col(RW_FRAME) + p.src[l]);
-                    else col(RW_FRAME)[k] = (uint32_t)cur.fr[l];
+                    S(RW_TIME_ON_FRAME, cur.tf[l]);
+                    col(RW_FRAME)[k] = (uint32_t)cur.fr[l];
                 }
             }
         }
@@ -790,7 +861,7 @@ template <int V, int THREADS, int SUB, int MIN_BLOCKS, bool TICKET, bool FUSED, 
 static void launch_one(cudaStream_t s, const UpdateLaunch& L)
 {
     // life records of one group (+ the group's vertex staging) + alignment slack
-    constexpr size_t smem = (size_t)THREADS * V * (REC_WORDS * 4 + (FUSED ? T3D_FLOATS_PER_QUAD * 4 : 0)) + 128;
+    constexpr size_t smem = (size_t)THREADS * V * (REC_WORDS * 4 + (FUSED ? T3D_FLOATS_PER_QUAD * 4 : 0)) + (size_t)THREADS * 48 + 128;
     auto kernel = k_update<V, THREADS, SUB, MIN_BLOCKS, TICKET, FUSED, BOUNDS>;
     // the opt-in to more than 48 KB of dynamic shared memory is per device: once for each device this process launches on
     static bool configured[kMaxDevices] = {};
@@ -800,6 +871,12 @@ static void launch_one(cudaStream_t s, const UpdateLaunch& L)
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured[dev] = true;
+        // the shapes are tuned for MIN_BLOCKS resident CTAs per SM; shared memory is within 4 KB of that limit, so say so
+        // loudly if a change ever pushes a variant over it (the kernel would still be correct, at half the speed)
+        int resident = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, THREADS, smem) == cudaSuccess && resident < MIN_BLOCKS)
+            fprintf(stderr, "t3d: k_update<%d,%d,%d,%d,fused=%d>: %d resident CTA(s) per SM instead of %d (shared memory %zu B dynamic)\n", V,
+                    THREADS, SUB, MIN_BLOCKS, (int)FUSED, resident, MIN_BLOCKS, smem);
     }
     kernel<<<L.total_tiles, THREADS, smem, s>>>(L.items, L.n_items, L.total_tiles, L.tile_status, L.ticket, L.ticket_base, L.epoch, L.fault, 0u,
                                                 L.ditems, L.rot_mode, L.frozen);

@@ -2,8 +2,10 @@
 // Each method cites the reference member it stands for; PE.cpp = Tractor3Dlib/src/graphics/ParticleEmitter.cpp.
 #include "ParticleEmitter.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <memory>
 
 namespace tractor
 {
@@ -38,37 +40,139 @@ void ParticleEmitter::setRotationMode(int mode) { if (context()) t3d_ctx_set_rot
 ParticleEmitter::~ParticleEmitter()
 {
     if (_h) t3d_emitter_destroy(_h); // PE.cpp:35-40: the emitter owns its particle storage
+    if (_texture) _texture->release();
 }
 
-// PE.cpp:76-211
+// PE.cpp:76-89
 ParticleEmitter* ParticleEmitter::create(const std::string& url)
 {
-    t3d_ctx* ctx = context();
-    if (!ctx) return nullptr;
-    t3d_emitter* h = nullptr;
-    if (t3d_emitter_create_from_file(ctx, url.c_str(), &h) != T3D_OK)
+    auto properties = std::unique_ptr<Properties>(Properties::create(url));
+    if (!properties)
     {
-        GP_ERROR("Failed to create particle emitter from file: %s", t3d_last_error());
+        GP_ERROR("Failed to create particle emitter from file.");
         return nullptr;
     }
-    ParticleEmitter* e = new ParticleEmitter();
-    e->_h = h;
-    return e;
+    return create(properties->getNamespace().length() > 0 ? properties.get() : properties->getNextNamespace());
 }
 
-// PE.cpp:43-60: the texture is loaded only to learn its size.
+// PE.cpp:92-211, getter by getter: whatever Properties class this is built against (the engine's, or compat.h's view of
+// the library's own parser) does the conversions.
+ParticleEmitter* ParticleEmitter::create(Properties* properties)
+{
+    if (!properties || properties->getNamespace() != "particle")
+    {
+        GP_ERROR("Properties object must be non-null and have namespace equal to 'particle'.");
+        return nullptr;
+    }
+    properties->rewind();
+    Properties* sprite = properties->getNextNamespace();
+    if (!sprite || sprite->getNamespace() != "sprite")
+    {
+        GP_ERROR("Failed to load particle emitter: required namespace 'sprite' is missing.");
+        return nullptr;
+    }
+    std::string texturePath;
+    if (!sprite->getPath("path", texturePath))
+    {
+        GP_ERROR("Failed to load particle emitter: required image file path ('path') is missing.");
+        return nullptr;
+    }
+    std::string blendModeString = sprite->getString("blendMode");
+    if (blendModeString.empty()) blendModeString = sprite->getString("blending"); // the old naming
+    const BlendMode blendMode = getBlendModeFromString(blendModeString);
+    const int spriteWidth = sprite->getInt("width");
+    const int spriteHeight = sprite->getInt("height");
+    const bool spriteAnimated = sprite->getBool("animated");
+    const bool spriteLooped = sprite->getBool("looped");
+    const int spriteFrameCount = sprite->getInt("frameCount");
+    const int spriteFrameRandomOffset = std::min(sprite->getInt("frameRandomOffset"), spriteFrameCount);
+    const float spriteFrameDuration = sprite->getFloat("frameDuration");
+
+    unsigned int particleCountMax = (unsigned int)properties->getInt("particleCountMax");
+    if (particleCountMax == 0) particleCountMax = 100; // PARTICLE_COUNT_MAX, PE.cpp:12
+    unsigned int emissionRate = (unsigned int)properties->getInt("emissionRate");
+    if (emissionRate == 0) emissionRate = 10;          // PARTICLE_EMISSION_RATE, PE.cpp:13
+    const bool ellipsoid = properties->getBool("ellipsoid");
+    const float sizeStartMin = properties->getFloat("sizeStartMin");
+    const float sizeStartMax = properties->getFloat("sizeStartMax");
+    const float sizeEndMin = properties->getFloat("sizeEndMin");
+    const float sizeEndMax = properties->getFloat("sizeEndMax");
+    const long energyMin = properties->getLong("energyMin");
+    const long energyMax = properties->getLong("energyMax");
+    Vector4 colorStart, colorStartVar, colorEnd, colorEndVar;
+    properties->getVector4("colorStart", &colorStart);
+    properties->getVector4("colorStartVar", &colorStartVar);
+    properties->getVector4("colorEnd", &colorEnd);
+    properties->getVector4("colorEndVar", &colorEndVar);
+    Vector3 position, positionVar, velocity, velocityVar, acceleration, accelerationVar, rotationAxis, rotationAxisVar;
+    properties->getVector3("position", &position);
+    properties->getVector3("positionVar", &positionVar);
+    properties->getVector3("velocity", &velocity);
+    properties->getVector3("velocityVar", &velocityVar);
+    properties->getVector3("acceleration", &acceleration);
+    properties->getVector3("accelerationVar", &accelerationVar);
+    const float rotationPerParticleSpeedMin = properties->getFloat("rotationPerParticleSpeedMin");
+    const float rotationPerParticleSpeedMax = properties->getFloat("rotationPerParticleSpeedMax");
+    const float rotationSpeedMin = properties->getFloat("rotationSpeedMin");
+    const float rotationSpeedMax = properties->getFloat("rotationSpeedMax");
+    properties->getVector3("rotationAxis", &rotationAxis);
+    properties->getVector3("rotationAxisVar", &rotationAxisVar);
+    const bool orbitPosition = properties->getBool("orbitPosition");
+    const bool orbitVelocity = properties->getBool("orbitVelocity");
+    const bool orbitAcceleration = properties->getBool("orbitAcceleration");
+
+    ParticleEmitter* emitter = ParticleEmitter::create(texturePath, blendMode, particleCountMax);
+    if (!emitter)
+    {
+        GP_ERROR("Failed to create particle emitter.");
+        return nullptr;
+    }
+    emitter->setEmissionRate(emissionRate);
+    emitter->setEllipsoid(ellipsoid);
+    emitter->setSize(sizeStartMin, sizeStartMax, sizeEndMin, sizeEndMax);
+    emitter->setEnergy(energyMin, energyMax);
+    emitter->setColor(colorStart, colorStartVar, colorEnd, colorEndVar);
+    emitter->setPosition(position, positionVar);
+    emitter->setVelocity(velocity, velocityVar);
+    emitter->setAcceleration(acceleration, accelerationVar);
+    emitter->setRotationPerParticle(rotationPerParticleSpeedMin, rotationPerParticleSpeedMax);
+    emitter->setRotation(rotationSpeedMin, rotationSpeedMax, rotationAxis, rotationAxisVar);
+    emitter->setSpriteAnimated(spriteAnimated);
+    emitter->setSpriteLooped(spriteLooped);
+    emitter->setSpriteFrameRandomOffset(spriteFrameRandomOffset);
+    emitter->setSpriteFrameDuration((long)spriteFrameDuration);
+    emitter->setSpriteFrameCoords(spriteFrameCount, spriteWidth, spriteHeight);
+    emitter->setOrbit(orbitPosition, orbitVelocity, orbitAcceleration);
+    return emitter;
+}
+
+// PE.cpp:43-60: the texture is loaded (here: its header is read) and handed on.
 ParticleEmitter* ParticleEmitter::create(const std::string& texturePath, BlendMode blendMode, unsigned int particleCountMax)
 {
-    uint32_t w = 0, h = 0;
-    if (t3d_host_png_size(texturePath.c_str(), &w, &h) != T3D_OK)
+    Texture* texture = Texture::create(texturePath, true);
+    if (!texture)
     {
         GP_ERROR("Failed to create texture for particle emitter.");
         return nullptr;
     }
-    return create(w, h, blendMode, particleCountMax);
+    ParticleEmitter* emitter = ParticleEmitter::create(texture, blendMode, particleCountMax);
+    texture->release();
+    return emitter;
 }
 
 // PE.cpp:63-73
+ParticleEmitter* ParticleEmitter::create(Texture* texture, BlendMode blendMode, unsigned int particleCountMax)
+{
+    ParticleEmitter* emitter = create(texture->getWidth(), texture->getHeight(), blendMode, particleCountMax);
+    if (emitter)
+    {
+        texture->addRef();
+        emitter->_texture = texture;
+    }
+    return emitter;
+}
+
+// The same without a Texture object: the size is all the path needs (getTexture() then returns nullptr).
 ParticleEmitter* ParticleEmitter::create(unsigned int textureWidth, unsigned int textureHeight, BlendMode blendMode,
                                          unsigned int particleCountMax)
 {
@@ -91,22 +195,36 @@ ParticleEmitter* ParticleEmitter::create(unsigned int textureWidth, unsigned int
     return e;
 }
 
-// PE.cpp:214-226.  The capacity-sized storage and the uv table depend on the texture size, which is fixed at
-// create in this backend; a different texture of the same size only changes the blend mode here.
+// PE.cpp:214-226
 void ParticleEmitter::setTexture(const std::string& texturePath, BlendMode blendMode)
 {
-    uint32_t w = 0, h = 0;
-    if (t3d_host_png_size(texturePath.c_str(), &w, &h) != T3D_OK)
+    Texture* texture = Texture::create(texturePath, true);
+    if (texture)
+    {
+        setTexture(texture, blendMode);
+        texture->release();
+    }
+    else
     {
         GP_WARN("Failed set new texture on particle emitter: %s", texturePath.c_str());
+    }
+}
+
+// PE.cpp:229-252: the new texture's size re-derives the texel ratios and the sprite table goes back to one frame
+// covering the whole texture.  (New reference taken before the old one is dropped: it may be the same texture.)
+void ParticleEmitter::setTexture(Texture* texture, BlendMode blendMode)
+{
+    if (t3d_emitter_set_texture_size(_h, texture->getWidth(), texture->getHeight(), (int)blendMode) != T3D_OK)
+    {
+        GP_ERROR("setTexture: %s", t3d_last_error());
         return;
     }
-    const t3d_emitter_params p = params();
-    if ((float)w != p.texture_width || (float)h != p.texture_height)
-        GP_WARN("setTexture: the new texture is %ux%u but the emitter was created for %gx%g; the size is kept", w, h,
-                p.texture_width, p.texture_height);
-    setBlendMode(blendMode);
+    texture->addRef();
+    if (_texture) _texture->release();
+    _texture = texture;
 }
+
+Texture* ParticleEmitter::getTexture() const { return _texture; } // PE.cpp:255-259
 
 t3d_emitter_params ParticleEmitter::params() const
 {
@@ -123,13 +241,10 @@ void ParticleEmitter::apply(const t3d_emitter_params& p)
 void ParticleEmitter::setParticleCountMax(unsigned int max)
 {
     t3d_emitter_params p = params();
-    if (max > p.particle_count_max)
-    {
-        GP_WARN("setParticleCountMax(%u): the particle storage was sized for %u at create and cannot grow", max, p.particle_count_max);
-        return;
-    }
+    // PE.h:237 rewrites the field; the storage keeps the size it was created with, so the field may go down (and back up
+    // to that size): the library refuses anything beyond it
     p.particle_count_max = max;
-    apply(p);
+    if (t3d_emitter_set_params(_h, &p) != T3D_OK) GP_WARN("setParticleCountMax(%u): %s", max, t3d_last_error());
 }
 unsigned int ParticleEmitter::getParticleCountMax() const { return params().particle_count_max; }
 
@@ -352,6 +467,11 @@ Drawable* ParticleEmitter::clone(NodeCloneContext&) // PE.cpp:891-932
     }
     ParticleEmitter* e = new ParticleEmitter();
     e->_h = h;
+    if (_texture) // PE.cpp:894: the clone shares the texture
+    {
+        _texture->addRef();
+        e->_texture = _texture;
+    }
     return e;
 }
 

@@ -5,13 +5,14 @@
 // Same names, same argument meaning, same units (milliseconds, particles per second), same ownership
 // convention (Ref: created with one reference, release() to drop it), same error behaviour (GP_ERROR /
 // GP_WARN, create*() return nullptr on failure).  What differs, by design:
-//   * there is no SpriteBatch / Texture object: the texture is only ever asked for its size
-//     (PE.cpp:244-247) and the vertex stream stays on the device -- getVertexStream() hands the renderer
-//     the device pointer where the reference handed MeshBatch a client-side array;
+//   * there is no SpriteBatch: the texture is only ever asked for its size (PE.cpp:244-247; getTexture() hands back
+//     the object setTexture() was given) and the vertex stream stays on the device -- getVertexStream() hands the
+//     renderer the device pointer where the reference handed MeshBatch a client-side array;
 //   * update()/draw() enqueue; calls on many emitters coalesce into one launch per phase.  flush()/sync()
 //     on the shared context (or any getter that needs a result) make them run;
-//   * setParticleCountMax() cannot grow the emitter (the reference only rewrites the field and would
-//     overrun its array, PE.h:237): growth is refused with GP_WARN.
+//   * setParticleCountMax() cannot grow the emitter beyond the size it was created with (the reference only rewrites
+//     the field and would overrun its array, PE.h:237): growth is refused with GP_WARN; lowering it works as there.
+// Builds against compat.h's stand-ins or, with -DT3D_WITH_ENGINE_HEADERS, against the engine's own headers.
 #pragma once
 
 #include <cstdint>
@@ -39,6 +40,7 @@ class ParticleEmitter : public Ref, public Drawable
     static void setRotationMode(int t3d_rot_mode);
 
     static ParticleEmitter* create(const std::string& url);                                    // PE.cpp:76
+    static ParticleEmitter* create(Properties* properties);                                    // PE.cpp:92 (SceneLoader.cpp:320)
     static ParticleEmitter* create(const std::string& texturePath, BlendMode blendMode,
                                    unsigned int particleCountMax);                             // PE.cpp:43
     // No engine Texture here: the size is all the path needs.
@@ -46,6 +48,8 @@ class ParticleEmitter : public Ref, public Drawable
                                    unsigned int particleCountMax);
 
     void setTexture(const std::string& texturePath, BlendMode blendMode);                      // PE.cpp:214
+    void setTexture(Texture* texture, BlendMode blendMode);                                    // PE.cpp:229
+    Texture* getTexture() const;                                                               // PE.cpp:255
     void setParticleCountMax(unsigned int max);
     unsigned int getParticleCountMax() const;
     void setEmissionRate(unsigned int rate);
@@ -131,8 +135,10 @@ class ParticleEmitter : public Ref, public Drawable
     void apply(const t3d_emitter_params& p);
     bool pushTransforms();
     static BlendMode getBlendModeFromString(const std::string& str);
+    static ParticleEmitter* create(Texture* texture, BlendMode blendMode, unsigned int particleCountMax); // PE.cpp:63 (PE.h:760)
 
     t3d_emitter* _h{ nullptr };
+    Texture* _texture{ nullptr }; // what the reference keeps inside its SpriteBatch's sampler (PE.cpp:255-259)
 };
 
 } // namespace tractor
