@@ -49,6 +49,7 @@ typedef enum t3d_status {
 
 typedef struct t3d_ctx t3d_ctx;         /* one per GPU */
 typedef struct t3d_emitter t3d_emitter; /* replaces one tractor::ParticleEmitter */
+typedef struct t3d_properties t3d_properties; /* one namespace of a tractor::Properties tree (see "Properties" below) */
 
 /* Blend modes, PE.h:157-163.  Carried for API fidelity; rasterisation is out of scope. */
 enum { T3D_BLEND_NONE = 0, T3D_BLEND_ALPHA = 1, T3D_BLEND_ADDITIVE = 2, T3D_BLEND_MULTIPLIED = 3 };
@@ -177,7 +178,7 @@ int t3d_emitter_create_from_file(t3d_ctx* ctx, const char* url, t3d_emitter** ou
 /* Replaces ParticleEmitter::clone (PE.cpp:891-932): same configuration, no particles. */
 /* Replaces ParticleEmitter::create(Properties*) (PE.cpp:92-211, the overload src/scene/SceneLoader.cpp:320 calls):
  * `particle` is a namespace named "particle" whose first child namespace is "sprite" (t3d_properties below). */
-int t3d_emitter_create_from_properties(t3d_ctx* ctx, const struct t3d_properties* particle, t3d_emitter** out);
+int t3d_emitter_create_from_properties(t3d_ctx* ctx, const t3d_properties* particle, t3d_emitter** out);
 int t3d_emitter_clone(t3d_emitter* e, t3d_emitter** out);
 int t3d_emitter_destroy(t3d_emitter* e);
 
@@ -294,7 +295,6 @@ int t3d_host_png_size(const char* path, uint32_t* width, uint32_t* height);
  * the reference's conversions.  A handle names one namespace; the root returned by _load / _new owns the whole tree and
  * is the only handle to free.  This is how a caller that already holds a parsed tree (SceneLoader.cpp:318-324) hands a
  * `particle` namespace over without going through a file. */
-typedef struct t3d_properties t3d_properties;
 int t3d_properties_load(const char* url, t3d_properties** out);                       /* Properties::create(url) */
 int t3d_properties_new(const char* name_space, const char* id, t3d_properties** out); /* an empty root namespace */
 void t3d_properties_free(t3d_properties* root);

@@ -33,6 +33,7 @@ typedef struct orc_particle {
 struct orc_emitter {
     t3d_emitter_params p;              /* PE.h:824-877 */
     orc_particle* particles;           /* PE.cpp:31 */
+    unsigned int alloc_max;            /* particleCountMax at create: the size of `particles` */
     unsigned int particle_count;
     int started;
     int has_node;
@@ -264,10 +265,12 @@ uint32_t orc_emitter_get_sprite_tex_coords(orc_emitter* e, float* out, size_t ma
 
 void orc_emitter_set_params(orc_emitter* e, const t3d_emitter_params* p)
 {
-    uint32_t cap = e->p.particle_count_max;
+    /* setParticleCountMax (PE.h:237) only rewrites the field; the array keeps the size it got at create (PE.cpp:31), so
+     * the field may be lowered -- the clamp of PE.cpp:293-296 then uses the lower value -- and raised back, never beyond */
+    uint32_t cap = (p->particle_count_max && p->particle_count_max <= e->alloc_max) ? p->particle_count_max : e->p.particle_count_max;
     float tw = e->p.texture_width, th = e->p.texture_height;
     e->p = *p;
-    e->p.particle_count_max = cap; /* storage is sized once, PE.cpp:31 */
+    e->p.particle_count_max = cap;
     e->p.texture_width = tw; e->p.texture_height = th;
     orc_emitter_set_emission_rate(e, p->emission_rate);
     e->frame_duration_secs = (float)p->sprite_frame_duration / 1000.0f; /* PE.cpp:491-495 */
@@ -279,6 +282,7 @@ orc_emitter* orc_emitter_create(const t3d_emitter_params* p)
 {
     orc_emitter* e = (orc_emitter*)calloc(1, sizeof(orc_emitter));
     e->p = *p;
+    e->alloc_max = p->particle_count_max;
     e->particles = (orc_particle*)calloc(p->particle_count_max ? p->particle_count_max : 1, sizeof(orc_particle));
     identity(e->node_world);
     identity(e->camera_world);

@@ -15,7 +15,7 @@ class MaterialParameter
 class Material : public RenderState
 {
   public:
-    static Material* create(Effect* effect) { Material* m = new Material(); m->_effect = effect; return m; }
+    static Material* create(Effect* effect) { Material* m = new Material(); m->_effect = effect; if (effect) effect->addRef(); return m; } // shares the effect, as the engine's does
     ~Material() { if (_effect) _effect->release(); }
     MaterialParameter* getParameter(const std::string&) { return &_param; }
   private:

@@ -145,6 +145,7 @@ namespace
 struct RefEmitter
 {
     ParticleEmitter* pe{ nullptr };
+    unsigned int alloc_max{ 0 }; // _particleCountMax at create = the size of the _particles array (PE.cpp:31)
     Node node;       // the emitter's node (identity by default)
     Node cameraNode; // the active camera's node
     Camera camera;
@@ -153,6 +154,7 @@ struct RefEmitter
 
 void wire(RefEmitter* r)
 {
+    r->alloc_max = r->pe->_particleCountMax;
     r->camera._node = &r->cameraNode;
     r->scene._camera = &r->camera;
     r->node._scene = &r->scene;
@@ -251,7 +253,13 @@ void t3dref_emitter_destroy(void* h)
     delete r;
 }
 
-void t3dref_emitter_set_params(void* h, const t3d_emitter_params* p) { apply_params(((RefEmitter*)h)->pe, p); }
+void t3dref_emitter_set_params(void* h, const t3d_emitter_params* p)
+{
+    RefEmitter* r = (RefEmitter*)h;
+    apply_params(r->pe, p);
+    // setParticleCountMax (PE.h:237) only rewrites the field: going beyond the array allocated at create would overrun it
+    if (p->particle_count_max && p->particle_count_max <= r->alloc_max) r->pe->setParticleCountMax(p->particle_count_max);
+}
 
 void t3dref_emitter_get_params(void* h, t3d_emitter_params* p)
 {

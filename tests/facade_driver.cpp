@@ -1,9 +1,10 @@
 // facade_driver.cpp -- drives the C++ ParticleEmitter facade the way ParticlesSample drives the reference
 // class (create from a .particle file, attach to a node, start, update/draw per frame) and dumps the result
 // for the Python test to compare with the oracle.
-//   facade_driver <file.particle> <frames> <seed> <out.bin> [emit_once_n]
+//   facade_driver <file.particle> <frames> <seed> <out.bin> [emit_once_n] [props]
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "../tractor3d_b200/host/ParticleEmitter.h"
@@ -17,7 +18,18 @@ int main(int argc, char** argv)
     const uint64_t seed = std::strtoull(argv[3], nullptr, 10);
     const unsigned burst = argc > 5 ? (unsigned)std::atoi(argv[5]) : 0;
 
-    ParticleEmitter* e = ParticleEmitter::create(argv[1]);
+    ParticleEmitter* e = nullptr;
+    if (argc > 6 && std::string(argv[6]) == "props")
+    {
+        // the way src/scene/SceneLoader.cpp:318-324 gets its emitter: a parsed Properties tree, one namespace of it handed over
+        Properties* file = Properties::create(argv[1]);
+        if (!file) return 3;
+        e = ParticleEmitter::create(file->getNamespace().length() > 0 ? file : file->getNextNamespace());
+        delete file;
+        if (!e->getTexture() || e->getTexture()->getWidth() == 0) return 9; // PE.cpp:255-259
+    }
+    else
+        e = ParticleEmitter::create(argv[1]);
     if (!e) return 3;
     // A missing file must come back as nullptr, not as an exit (built with GP_ERRORS_AS_WARNINGS).
     if (ParticleEmitter::create("/nonexistent/none.particle") != nullptr) return 4;

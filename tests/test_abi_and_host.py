@@ -249,3 +249,69 @@ def test_stock_particle_files_parse_like_the_reference(name):
     table = np.zeros(fc * 4, dtype=np.float32)
     lib.t3d_host_sprite_frame_coords(fc, sw, sh, p.texture_width, p.texture_height, table.ctypes.data_as(C.POINTER(C.c_float)))
     assert np.array_equal(table.view(np.uint32), er.sprite_tex_coords().reshape(-1).view(np.uint32))
+
+
+def test_properties_tree_is_what_create_from_properties_reads(tmp_path):
+    # t3d_properties: the slice of tractor::Properties the path reads.  A tree loaded from a file and the same tree built
+    # by hand (what a caller holding its own parsed scene file would do, SceneLoader.cpp:318-324) give the parameters the
+    # file parser gives -- and those are pinned to the reference's own Properties class by test_oracle_vs_ref.
+    lib = abi.load()
+    _write_png(str(tmp_path / "sheet.png"), 96, 32)
+    f = tmp_path / "sparks.particle"
+    f.write_text(PARTICLE_TEXT)
+    rc, want, fc, sw, sh, tex = _parse(lib, str(f))
+    assert rc == abi.OK
+
+    def parse_tree(node):
+        p = abi.EmitterParams()
+        n, w, h = C.c_uint32(), C.c_int(), C.c_int()
+        buf = C.create_string_buffer(1024)
+        rc = lib.t3d_particle_properties_parse(node, C.byref(p), C.byref(n), C.byref(w), C.byref(h), buf, 1024)
+        return rc, p, n.value, w.value, h.value, buf.value.decode()
+
+    root = C.c_void_p()
+    assert lib.t3d_properties_load(str(f).encode(), C.byref(root)) == abi.OK
+    try:
+        assert lib.t3d_properties_namespace(root) == b"" and lib.t3d_properties_namespace_count(root) == 1
+        particle = lib.t3d_properties_get_namespace(root, 0)
+        assert lib.t3d_properties_namespace(particle) == b"particle" and lib.t3d_properties_id(particle) == b"sparks"
+        sprite = lib.t3d_properties_get_namespace(particle, 0)
+        assert lib.t3d_properties_namespace(sprite) == b"sprite"
+        # typed getters, Properties.cpp's conversions
+        assert lib.t3d_properties_get_int(sprite, b"frameCount") == 6 and lib.t3d_properties_get_int(sprite, b"missing") == 0
+        assert lib.t3d_properties_get_float(sprite, b"frameDuration") == np.float32(33.7)
+        assert lib.t3d_properties_get_bool(sprite, b"animated", 0) == 1 and lib.t3d_properties_get_bool(sprite, b"missing", 1) == 1
+        assert lib.t3d_properties_get_long(particle, b"energyMax") == 1250
+        assert lib.t3d_properties_get_float(particle, b"sizeStartMax") == 10.0
+        v = (C.c_float * 4)()
+        assert lib.t3d_properties_get_vector(particle, b"colorStart", v, 4) == 1 and list(v) == [1, 0.5, 0.25, 1]
+        assert lib.t3d_properties_get_vector(particle, b"colorStart", v, 3) == 1 and list(v)[:3] == [1, 0.5, 0.25]
+        assert lib.t3d_properties_get_vector(particle, b"nothing", v, 3) == 0 and list(v)[:3] == [0, 0, 0]
+        buf = C.create_string_buffer(1024)
+        assert lib.t3d_properties_get_path(sprite, b"path", buf, 1024) == abi.OK and buf.value.decode() == tex
+        assert lib.t3d_properties_get_path(sprite, b"width", buf, 1024) == abi.ERR_IO
+        keys = [lib.t3d_properties_key(sprite, i) for i in range(lib.t3d_properties_count(sprite))]
+        assert keys[:3] == [b"path", b"width", b"height"] and lib.t3d_properties_key(sprite, 99) is None
+        rc, got, fc2, sw2, sh2, tex2 = parse_tree(particle)
+        assert rc == abi.OK and (fc2, sw2, sh2, tex2) == (fc, sw, sh, tex) and got.as_dict() == want.as_dict()
+        # the root (an unnamed namespace) is not a particle
+        assert parse_tree(root)[0] == abi.ERR_IO
+        # ... and the same tree built by hand, key by key
+        mine = C.c_void_p()
+        assert lib.t3d_properties_new(b"particle", b"copy", C.byref(mine)) == abi.OK
+        try:
+            child = C.c_void_p()
+            assert lib.t3d_properties_add_namespace(mine, b"sprite", None, C.byref(child)) == abi.OK
+            for src, dst in ((sprite, child), (particle, mine)):
+                for i in range(lib.t3d_properties_count(src)):
+                    k, val = lib.t3d_properties_key(src, i), lib.t3d_properties_value(src, i)
+                    if k == b"path":
+                        val = tex.encode()          # a hand-built tree has no directory to resolve against
+                    assert lib.t3d_properties_set(dst, k, val) == abi.OK
+            assert lib.t3d_properties_set(mine, b"emissionRate", b"1") == abi.OK and lib.t3d_properties_set(mine, b"emissionRate", b"55") == abi.OK
+            rc, got, fc3, sw3, sh3, _ = parse_tree(mine)
+            assert rc == abi.OK and (fc3, sw3, sh3) == (fc, sw, sh) and got.as_dict() == want.as_dict()
+        finally:
+            lib.t3d_properties_free(mine)
+    finally:
+        lib.t3d_properties_free(root)

@@ -128,6 +128,28 @@ def test_burst_until_extinction_swap_with_last_order():
     assert not er.is_active() and not eo.is_active()
 
 
+def test_lowered_particle_count_max_clamps_emit_once():
+    # setParticleCountMax (PE.h:237) only rewrites the field the clamp of PE.cpp:293-296 reads; the array keeps its size.
+    params = abi.default_params(particle_count_max=1000, energy_min=5000.0, energy_max=6000.0, velocity_var=[1, 1, 1])
+    O, R, eo, er = make_pair(params, None, seed=17)
+    eo.emit_once(300); er.emit_once(300)
+    for e in (eo, er):
+        q = e.params(); q.particle_count_max = 450; e.set_params(q)
+        assert e.params().particle_count_max == 450
+    eo.emit_once(400); er.emit_once(400)
+    assert eo.count() == er.count() == 450
+    for e in (eo, er):
+        q = e.params(); q.particle_count_max = 1000; e.set_params(q)      # back up to the size at create
+    eo.emit_once(700); er.emit_once(700)
+    assert eo.count() == er.count() == 1000
+    for e in (eo, er):
+        q = e.params(); q.particle_count_max = 5000; e.set_params(q)      # beyond the array: the harnesses refuse
+        assert e.params().particle_count_max == 1000
+    for f in range(3):
+        eo.update(DT); er.update(DT)
+    assert_same(eo, er, "after lowering and raising the cap")
+
+
 def test_sprite_animation_looped_and_not():
     for looped in (0, 1):
         params, sprite = presets.explosion()

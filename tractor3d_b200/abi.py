@@ -188,6 +188,28 @@ PROTOTYPES = {
     "t3d_host_particle_draws": (C.c_size_t, [_P(C.c_int32), C.c_size_t, C.c_int, C.c_uint32]),
     "t3d_host_png_size": (C.c_int, [C.c_char_p, _P(C.c_uint32), _P(C.c_uint32)]),
     "t3d_particle_file_parse": (C.c_int, [C.c_char_p, _P(EmitterParams), _P(C.c_uint32), _P(C.c_int), _P(C.c_int), C.c_char_p, C.c_size_t]),
+    "t3d_emitter_create_from_properties": (C.c_int, [_vp, _vp, _P(_vp)]),
+    "t3d_emitter_set_texture_size": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_int]),
+    "t3d_properties_load": (C.c_int, [C.c_char_p, _P(_vp)]),
+    "t3d_properties_new": (C.c_int, [C.c_char_p, C.c_char_p, _P(_vp)]),
+    "t3d_properties_free": (None, [_vp]),
+    "t3d_properties_set": (C.c_int, [_vp, C.c_char_p, C.c_char_p]),
+    "t3d_properties_add_namespace": (C.c_int, [_vp, C.c_char_p, C.c_char_p, _P(_vp)]),
+    "t3d_properties_namespace": (C.c_char_p, [_vp]),
+    "t3d_properties_id": (C.c_char_p, [_vp]),
+    "t3d_properties_namespace_count": (C.c_size_t, [_vp]),
+    "t3d_properties_get_namespace": (_vp, [_vp, C.c_size_t]),
+    "t3d_properties_count": (C.c_size_t, [_vp]),
+    "t3d_properties_key": (C.c_char_p, [_vp, C.c_size_t]),
+    "t3d_properties_value": (C.c_char_p, [_vp, C.c_size_t]),
+    "t3d_properties_get": (C.c_char_p, [_vp, C.c_char_p]),
+    "t3d_properties_get_bool": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "t3d_properties_get_int": (C.c_int, [_vp, C.c_char_p]),
+    "t3d_properties_get_long": (C.c_longlong, [_vp, C.c_char_p]),
+    "t3d_properties_get_float": (C.c_float, [_vp, C.c_char_p]),
+    "t3d_properties_get_vector": (C.c_int, [_vp, C.c_char_p, _P(C.c_float), C.c_int]),
+    "t3d_properties_get_path": (C.c_int, [_vp, C.c_char_p, C.c_char_p, C.c_size_t]),
+    "t3d_particle_properties_parse": (C.c_int, [_vp, _P(EmitterParams), _P(C.c_uint32), _P(C.c_int), _P(C.c_int), C.c_char_p, C.c_size_t]),
     "t3d_particle_file_save": (C.c_int, [C.c_char_p, C.c_char_p, _P(EmitterParams), C.c_uint32, C.c_int, C.c_int, C.c_char_p]),
 }
 

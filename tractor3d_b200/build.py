@@ -72,6 +72,60 @@ def build_facade_driver():
     return out
 
 
+REFERENCE = os.environ.get("T3D_REFERENCE", "/root/reference")
+
+
+def engine_caller_paths():
+    root = os.path.dirname(HERE)
+    return (os.path.join(root, "oracle", "_ref", "engine_caller_ref"), os.path.join(HERE, "host", "_build", "engine_caller_b200"))
+
+
+def build_engine_callers():
+    """tests/engine_caller.cpp -- application code written against the ENGINE's headers (what SceneLoader and
+    ParticlesSample do with a ParticleEmitter) -- compiled twice: against the reference's own class and objects
+    (oracle/_ref/engine_caller_ref), and with -DT3D_WITH_ENGINE_HEADERS against the facade
+    (host/_build/engine_caller_b200: the engine's math / Ref / Properties objects + libt3d_particles.so).  Needs the
+    reference tree and the objects `make -C oracle ref` leaves behind; returns None where the tree is absent (the GPU box
+    runs the prebuilt programs)."""
+    root = os.path.dirname(HERE)
+    ref_inc = os.path.join(REFERENCE, "Tractor3Dlib", "include")
+    obj_dir = os.path.join(root, "oracle", "_ref", "obj")
+    if not os.path.isdir(ref_inc) or not os.path.isdir(obj_dir):
+        return None
+    out_ref, out_b200 = engine_caller_paths()
+    tmp_ref = os.path.join(root, "oracle", "_ref", "engine")
+    tmp_b200 = os.path.join(HERE, "host", "_build", "engine")
+    os.makedirs(tmp_ref, exist_ok=True)
+    os.makedirs(tmp_b200, exist_ok=True)
+    overlay = ["-I" + os.path.join(root, "oracle", "ref_build", "overlay"), "-I" + os.path.join(root, "oracle", "ref_build", "shim"),
+               "-I" + ref_inc, "-I" + os.path.join(root, "include")]
+    cxx = ["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-w"]
+    objs = []
+    for dirpath, _, files in os.walk(obj_dir):
+        objs += [os.path.join(dirpath, f) for f in files if f.endswith(".o") and f != "ref_capi.o"]
+    objs.sort()
+
+    def run(cmd):
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+            raise RuntimeError("building the engine-header callers failed")
+
+    caller, support = os.path.join(root, "tests", "engine_caller.cpp"), os.path.join(root, "tests", "engine_support.cpp")
+    run(cxx + overlay + ["-c", support, "-o", os.path.join(tmp_ref, "support.o")])
+    # (1) the reference's own class
+    run(cxx + overlay + ["-c", caller, "-o", os.path.join(tmp_ref, "caller.o")])
+    run(["g++", "-o", out_ref, os.path.join(tmp_ref, "caller.o"), os.path.join(tmp_ref, "support.o")] + objs)
+    # (2) the facade, found first on the include path as graphics/ParticleEmitter.h
+    shim = ["-DT3D_WITH_ENGINE_HEADERS", "-I" + os.path.join(HERE, "host", "engine")]
+    run(cxx + shim + overlay + ["-c", caller, "-o", os.path.join(tmp_b200, "caller.o")])
+    run(cxx + shim + overlay + ["-c", os.path.join(HERE, "host", "ParticleEmitter.cpp"), "-o", os.path.join(tmp_b200, "facade.o")])
+    engine_objs = [o for o in objs if os.path.basename(o) not in ("ParticleEmitter.o", "SpriteBatch.o")]
+    run(["g++", "-o", out_b200, os.path.join(tmp_b200, "caller.o"), os.path.join(tmp_b200, "facade.o"), os.path.join(tmp_ref, "support.o")]
+        + engine_objs + ["-L" + CSRC, "-lt3d_particles", "-Wl,-rpath,$ORIGIN/../../csrc"])
+    return out_ref, out_b200
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
     print(OUT)

@@ -187,6 +187,15 @@ class ParticleEmitter:
         e.set_rng(*rng)
         return e
 
+    @classmethod
+    def create_from_properties(cls, ctx, particle_namespace, rng=(abi.RNG_LIBC, 0)):
+        """ParticleEmitter::create(Properties*) (PE.cpp:92-211): `particle_namespace` is a t3d_properties handle."""
+        h = C.c_void_p()
+        _check(ctx.lib, ctx.lib.t3d_emitter_create_from_properties(ctx.h, particle_namespace, C.byref(h)))
+        e = cls(ctx, h)
+        e.set_rng(*rng)
+        return e
+
     def clone(self):
         h = C.c_void_p()
         _check(self.lib, self.lib.t3d_emitter_clone(self.h, C.byref(h)))
@@ -218,6 +227,14 @@ class ParticleEmitter:
 
     def getParticleCountMax(self):
         return self.params().particle_count_max
+
+    def setParticleCountMax(self, n):
+        # PE.h:237 rewrites the field only: lowering it (and raising it back up to the size at create) is all that works
+        self._edit(particle_count_max=int(n))
+
+    def setTextureSize(self, width, height, blend_mode):
+        """setTexture(Texture*, BlendMode) (PE.cpp:229-252): new texel ratios, sprite table reset to one full frame."""
+        _check(self.lib, self.lib.t3d_emitter_set_texture_size(self.h, width, height, blend_mode))
 
     def setEmissionRate(self, rate):
         _check(self.lib, self.lib.t3d_emitter_set_emission_rate(self.h, rate))
