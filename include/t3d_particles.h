@@ -168,6 +168,18 @@ int t3d_ctx_launch_count(t3d_ctx* ctx, uint64_t* n);
 /* Bytes staged host->device / device->host by the library since creation. */
 int t3d_ctx_transfer_bytes(t3d_ctx* ctx, uint64_t* h2d, uint64_t* d2h);
 
+/* Host time in seconds, since the context was created, that calls on this context have spent inside the library, split
+ * by what it went into (each slot exclusive of the others); the batch calls and everything behind flush / read-backs are
+ * counted, the per-emitter setters are not.  For finding where a frame's host time goes (scripts/host_cost.py). */
+enum {
+    T3D_HOST_ENQUEUE = 0, /* t3d_batch_* calls: the per-emitter host logic (isActive, rate cap, emission count) and queueing */
+    T3D_HOST_BUILD = 1,   /* cutting launch descriptors and the bookkeeping around a launch */
+    T3D_HOST_SUBMIT = 2,  /* inside CUDA calls that enqueue work: descriptor uploads, launches, event records */
+    T3D_HOST_WAIT = 3,    /* blocked on the device: count read-backs, t3d_ctx_sync, a full staging ring */
+    T3D_HOST_PROFILE_SLOTS = 4
+};
+int t3d_ctx_host_profile(t3d_ctx* ctx, double seconds[T3D_HOST_PROFILE_SLOTS]);
+
 /* ---- emitter lifecycle (PE.cpp:43-211) --------------------------------------------------- */
 /* Replaces ParticleEmitter::create(texture, blendMode, particleCountMax) + the 16 setters
  * (PE.cpp:63-73, 193-208).  Installs one full-texture sprite frame like setTexture (PE.cpp:249-251). */

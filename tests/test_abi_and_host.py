@@ -315,3 +315,13 @@ def test_properties_tree_is_what_create_from_properties_reads(tmp_path):
             lib.t3d_properties_free(mine)
     finally:
         lib.t3d_properties_free(root)
+
+
+def test_ellipsoid_acceptance_needs_no_square_root():
+    # The spawn kernel tests `x*x + y*y + z*z > 1 + 2^-23` where the reference tests `sqrtf(...) > 1.0f`
+    # (Vector3::length() in generateVectorInEllipsoid, PE.cpp:629-650): identical for every float.
+    thr = np.uint32(0x3F800001).view(np.float32)
+    near_one = np.arange(0x3F000000, 0x40000000, dtype=np.uint32).view(np.float32)       # every float in [0.5, 2)
+    assert np.array_equal(np.sqrt(near_one) > np.float32(1.0), near_one > thr)
+    sweep = np.arange(0, 0x7F800000, 61, dtype=np.uint32).view(np.float32)              # and a sweep of all positive floats
+    assert np.array_equal(np.sqrt(sweep) > np.float32(1.0), sweep > thr)

@@ -137,6 +137,7 @@ PROTOTYPES = {
     "t3d_ctx_last_kernel_ms": (C.c_int, [_vp, C.c_int, _P(C.c_float)]),
     "t3d_ctx_kernel_time": (C.c_int, [_vp, C.c_int, _P(C.c_double), _P(C.c_uint64)]),
     "t3d_ctx_launch_count": (C.c_int, [_vp, _P(C.c_uint64)]),
+    "t3d_ctx_host_profile": (C.c_int, [_vp, _P(C.c_double)]),
     "t3d_ctx_transfer_bytes": (C.c_int, [_vp, _P(C.c_uint64), _P(C.c_uint64)]),
     "t3d_emitter_create": (C.c_int, [_vp, _P(EmitterParams), _P(_vp)]),
     "t3d_emitter_create_from_file": (C.c_int, [_vp, C.c_char_p, _P(_vp)]),

@@ -175,7 +175,8 @@ struct FrozenRotation
 };
 
 // ---- launch wrappers (t3d_kernels.cu, t3d_update.cu) ----
-void launch_spawn(void* stream, const SpawnItem* items, uint32_t n_items, uint32_t total_tiles);
+// host_draws: some item reads recorded draws (otherwise the launch is the device generator's specialisation)
+void launch_spawn(void* stream, const SpawnItem* items, uint32_t n_items, uint32_t total_tiles, bool host_draws);
 // `fault`: device word the kernels OR into when a grid does not cover the live count it finds (kFaultUpdateGrid ...).
 constexpr uint32_t kFaultUpdateGrid = 1u, kFaultDrawGrid = 2u;
 struct UpdateLaunch

@@ -29,6 +29,10 @@ namespace t3d
 // --------------------------------------------------------------------------------------------------
 // spawn
 // --------------------------------------------------------------------------------------------------
+// STREAM: some emitter of the launch reads recorded draws (T3D_RNG_STREAM / T3D_RNG_LIBC); otherwise every draw is the
+// counter-based hash and the kernel carries no second path (it is bound by instruction issue, not by HBM: ~30 hash
+// evaluations per particle).
+template <bool STREAM>
 struct DrawSource
 {
     const int32_t* p; // recorded stream positioned at this particle's first draw, or nullptr
@@ -36,12 +40,13 @@ struct DrawSource
     uint32_t j;
     __device__ __forceinline__ int32_t next()
     {
-        int32_t r = p ? p[j] : device_rng_from_key(key, j);
+        const int32_t r = (STREAM && p) ? p[j] : device_rng_from_key(key, j);
         ++j;
         return r;
     }
 };
 
+template <bool STREAM>
 __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __restrict__ items, uint32_t n_items)
 {
     // The tile's life records and rotation records are assembled in shared memory and leave as two contiguous bulk
@@ -72,8 +77,8 @@ __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __rest
     if (i < n)
     {
     const SpawnParams& P = d->c.sp;
-    DrawSource src;
-    src.p = it.draws ? it.draws + (it.offsets ? it.offsets[i] : i * it.draw_stride) : nullptr;
+    DrawSource<STREAM> src;
+    src.p = (STREAM && it.draws) ? it.draws + (it.offsets ? it.offsets[i] : i * it.draw_stride) : nullptr;
     src.key = device_rng_key(P.rng_seed, serial0 + i);
     src.j = 0;
 
@@ -101,7 +106,10 @@ __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __rest
             x = u11(src.next());
             y = u11(src.next());
             z = u11(src.next());
-        } while (sqrtf(x * x + y * y + z * z) > 1.0f);
+            // Vector3::length() > 1.0f (PE.cpp:640).  The correctly rounded square root of s exceeds 1 exactly when s exceeds
+            // 1 + 2^-23 (sqrt(1 + 2^-23) = 1 + 2^-24 - ... rounds down to 1), so the comparison needs no square root
+            // (checked against sqrtf over every float in [0.5, 2) by tests/test_abi_and_host.py).
+        } while ((x * x + y * y + z * z) > 1.00000011920928955078125f);
         pos[0] = x * P.position_var[0];
         pos[1] = y * P.position_var[1];
         pos[2] = z * P.position_var[2];
@@ -358,9 +366,10 @@ __global__ void __launch_bounds__(256) k_latch(const DrawItem* __restrict__ item
 // --------------------------------------------------------------------------------------------------
 // launch wrappers
 // --------------------------------------------------------------------------------------------------
-void launch_spawn(void* stream, const SpawnItem* items, uint32_t n_items, uint32_t total_tiles)
+void launch_spawn(void* stream, const SpawnItem* items, uint32_t n_items, uint32_t total_tiles, bool host_draws)
 {
-    k_spawn<<<total_tiles, kSpawnThreads, 0, (cudaStream_t)stream>>>(items, n_items);
+    if (host_draws) k_spawn<true><<<total_tiles, kSpawnThreads, 0, (cudaStream_t)stream>>>(items, n_items);
+    else k_spawn<false><<<total_tiles, kSpawnThreads, 0, (cudaStream_t)stream>>>(items, n_items);
 }
 
 template <int OUT, bool CLIP>

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -155,6 +156,9 @@ struct t3d_ctx
     std::vector<uint32_t> pending_offsets;
 
     uint64_t launches{ 0 }, h2d_bytes{ 0 }, d2h_bytes{ 0 };
+    // Host time spent inside the library, by what it was spent on (t3d_ctx_host_profile): seconds since creation.
+    double host_s[T3D_HOST_PROFILE_SLOTS]{};
+    double host_child_s{ 0 }; // time already attributed by scopes nested inside the one that is open
     // Per-kind launch timing: every launch is bracketed by a pair of events on the stream; pairs are
     // resolved (and recycled) lazily when somebody asks for the totals.
     struct EventPair { cudaEvent_t start, stop; };
@@ -170,6 +174,7 @@ struct t3d_ctx
     {
         std::vector<t3d_emitter*> es;
         std::vector<uint64_t> emitted_mark; // emitter's emitted_total when the launch was enqueued
+        std::vector<uint64_t> version_mark; // emitter's launch_version right after that launch
         std::vector<uint32_t> box_epoch;    // the epoch this launch's bounding box carries (0: the emitter does not ask for one)
         bool boxes{ false };                // the six box words of every emitter ride behind the counts
         uint32_t* host{ nullptr };
@@ -232,6 +237,7 @@ struct t3d_emitter
     float* uv_dev{ nullptr };
     uint32_t uv_cap{ 0 };
     uint32_t parity{ 0 };
+    uint64_t launch_version{ 0 }; // bumped by every launch that writes this emitter's counts (spawn, update, draw, upload)
     bool const_dirty{ true }, uv_dirty{ true };
     bool may_rotate{ false }, may_spin{ false };
     bool want_bounds{ false }, culling{ false };
@@ -258,6 +264,26 @@ struct t3d_emitter
 
 constexpr uint32_t kDevChunk = 4096;
 
+// Adds the wall time of a scope to one slot of the context's host profile.
+struct HostTimer
+{
+    t3d_ctx* c;
+    int which;
+    double outer_children;
+    std::chrono::steady_clock::time_point t0;
+    HostTimer(t3d_ctx* ctx, int w) : c(ctx), which(w), outer_children(ctx ? ctx->host_child_s : 0.0), t0(std::chrono::steady_clock::now())
+    {
+        if (c) c->host_child_s = 0.0;
+    }
+    ~HostTimer()
+    {
+        if (!c) return;
+        const double total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        c->host_s[which] += total - c->host_child_s; // exclusive of the scopes that ran inside this one
+        c->host_child_s = outer_children + total;
+    }
+};
+
 // --------------------------------------------------------------------------------------------------
 // context plumbing
 // --------------------------------------------------------------------------------------------------
@@ -269,6 +295,7 @@ static int use_device(t3d_ctx* c)
 
 static int staging_acquire(t3d_ctx* c, size_t bytes, StagingSlot** out)
 {
+    HostTimer ht(c, T3D_HOST_WAIT); // (waits only when all eight slots are still being read by launches in flight)
     StagingSlot& s = c->staging[c->staging_next];
     c->staging_next = (c->staging_next + 1) % 8;
     if (s.in_flight)
@@ -303,6 +330,7 @@ static int staging_acquire(t3d_ctx* c, size_t bytes, StagingSlot** out)
 
 static int staging_submit(t3d_ctx* c, StagingSlot* s, size_t bytes)
 {
+    HostTimer ht(c, T3D_HOST_SUBMIT);
     if (c->copy_stream)
     {
         // The slot's device buffer is free: staging_acquire waited for the last launch that read it.
@@ -318,6 +346,7 @@ static int staging_submit(t3d_ctx* c, StagingSlot* s, size_t bytes)
 
 static int staging_release(t3d_ctx* c, StagingSlot* s)
 {
+    HostTimer ht(c, T3D_HOST_SUBMIT);
     T3D_CUDA(cudaEventRecord(s->done, c->stream));
     s->in_flight = true;
     return T3D_OK;
@@ -564,6 +593,7 @@ static int resolve_timing(t3d_ctx* c, int k, bool wait)
 }
 static int time_begin(t3d_ctx* c, int k)
 {
+    HostTimer ht(c, T3D_HOST_SUBMIT);
     if (!c->timing_enabled) return T3D_OK;
     if (c->ev_pending[k].size() >= 64) T3D_TRY(resolve_timing(c, k, false)); // recycle finished pairs without waiting
     if (c->ev_pending[k].size() >= 1024) T3D_TRY(resolve_timing(c, k, true));
@@ -584,6 +614,7 @@ static int time_begin(t3d_ctx* c, int k)
 }
 static int time_end(t3d_ctx* c, int k)
 {
+    HostTimer ht(c, T3D_HOST_SUBMIT);
     if (!c->timing_enabled) return T3D_OK;
     T3D_CUDA(cudaEventRecord(c->ev_pending[k].back().stop, c->stream));
     return T3D_OK;
@@ -611,11 +642,13 @@ static int launch_spawns(t3d_ctx* c)
     if (draws_bytes) memcpy(slot->host + items_bytes + offs_bytes, c->pending_draws.data(), draws_bytes);
 
     uint32_t tiles = 0, k = 0;
+    bool any_host_draws = false;
     for (PendingOp& op : c->pending)
     {
         if (!op.emit_n) continue;
         t3d_emitter* e = op.e;
         T3D_TRY(sync_const(e));
+        any_host_draws = any_host_draws || op.host_draws;
         SpawnItem& it = items[k++];
         memset(&it, 0, sizeof(it));
         it.dev = e->dev;
@@ -628,13 +661,14 @@ static int launch_spawns(t3d_ctx* c)
         it.request = op.emit_n;
         it.parity = e->parity;
         e->parity ^= 1u;
+        e->launch_version++;
         it.tile_begin = tiles;
         memcpy(it.world, op.world, sizeof(it.world));
         tiles += (op.emit_n + kSpawnThreads - 1) / kSpawnThreads;
     }
     T3D_TRY(staging_submit(c, slot, total));
     T3D_TRY(time_begin(c, KERNEL_SPAWN));
-    launch_spawn(c->stream, reinterpret_cast<const SpawnItem*>(slot->dev), n_items, tiles);
+    launch_spawn(c->stream, reinterpret_cast<const SpawnItem*>(slot->dev), n_items, tiles, any_host_draws);
     T3D_CUDA(cudaGetLastError());
     T3D_TRY(time_end(c, KERNEL_SPAWN));
     c->launches++;
@@ -655,11 +689,10 @@ static bool decode_box(const unsigned long long* w, uint32_t epoch, float lo[3],
     return true;
 }
 
-static void poll_feedback(t3d_ctx* c)
+// A feedback copy has landed: tighten the bounds it speaks for.
+static void absorb_feedback(t3d_ctx* c, t3d_ctx::Feedback& fb)
 {
-    for (t3d_ctx::Feedback& fb : c->feedback)
     {
-        if (!fb.in_flight || cudaEventQuery(fb.done) != cudaSuccess) continue;
         for (size_t i = 0; i < fb.es.size(); ++i)
         {
             t3d_emitter* e = fb.es[i];
@@ -676,6 +709,12 @@ static void poll_feedback(t3d_ctx* c)
         }
         fb.in_flight = false;
     }
+}
+
+static void poll_feedback(t3d_ctx* c)
+{
+    for (t3d_ctx::Feedback& fb : c->feedback)
+        if (fb.in_flight && cudaEventQuery(fb.done) == cudaSuccess) absorb_feedback(c, fb);
 }
 
 // Enqueues the read-back of the counts the update launch just produced; never waits.
@@ -700,12 +739,14 @@ static int submit_feedback(t3d_ctx* c, const std::vector<PendingOp>& ops, const 
     if (!fb.done) T3D_CUDA(cudaEventCreateWithFlags(&fb.done, cudaEventDisableTiming));
     fb.es.resize(n);
     fb.emitted_mark.resize(n);
+    fb.version_mark.resize(n);
     fb.box_epoch.assign(n, 0);
     fb.boxes = false;
     for (size_t i = 0; i < n; ++i)
     {
         fb.es[i] = ops[i].e;
         fb.emitted_mark[i] = ops[i].e->emitted_total;
+        fb.version_mark[i] = ops[i].e->launch_version;
         if (ops[i].e->want_bounds)
         {
             fb.box_epoch[i] = ops[i].e->bounds_epoch;
@@ -773,6 +814,7 @@ static void build_update_items(std::vector<PendingOp>& ops, UpdateItem* items, C
         it.elapsed_ms = op.elapsed_ms;
         it.parity = e->parity;
         e->parity ^= 1u;
+        e->launch_version++;
         it.tile_begin = tiles;
         queries[k].dev = e->dev;
         queries[k].parity = e->parity; // where this launch leaves the new count
@@ -901,6 +943,7 @@ static void build_draw_items(std::vector<PendingOp>& ops, DrawItem* items, uint3
         it.seg_capacity = ec.st.seg_capacity;
         it.frame_count = ec.frame_count;
         memcpy(it.vp, op.vp, sizeof(it.vp));
+        e->launch_version++; // (a draw rewrites the emitter's quad count)
         it.parity = e->parity;
         it.tile_begin = tiles;
         memcpy(it.right, op.right, 12);
@@ -1052,6 +1095,7 @@ static int launch_held(t3d_ctx* c)
 // are held back one step so that both can go out as one fused launch when they cover the same emitters.
 static int flush(t3d_ctx* c, int next_phase = PHASE_NONE)
 {
+    HostTimer ht(c, T3D_HOST_BUILD);
     if (c->phase == PHASE_NONE || c->pending.empty())
     {
         c->phase = PHASE_NONE;
@@ -1121,6 +1165,32 @@ static int refresh_counts(t3d_ctx* c, t3d_emitter* const* es, size_t n, uint32_t
     T3D_TRY(flush(c));
     T3D_TRY(use_device(c));
     if (n == 0) return T3D_OK;
+    {
+        // The counts of the newest launch are already on their way back (submit_feedback): when nothing has touched these
+        // emitters since and the question is about exactly that launch's emitters, wait for that copy instead of asking again.
+        t3d_ctx::Feedback& fb = c->feedback[(c->feedback_next + 3) % 4];
+        bool same = fb.in_flight && fb.es.size() == n;
+        for (size_t i = 0; same && i < n; ++i) same = fb.es[i] == es[i] && fb.version_mark[i] == es[i]->launch_version;
+        if (same)
+        {
+            {
+                HostTimer ht(c, T3D_HOST_WAIT);
+                T3D_CUDA(cudaEventSynchronize(fb.done));
+            }
+            poll_feedback(c); // older copies first (they can only loosen nothing), then this one
+            if (fb.in_flight) absorb_feedback(c, fb);
+            c->fault |= fb.host[2 * n];
+            T3D_TRY(check_fault(c));
+            for (size_t i = 0; i < n; ++i)
+            {
+                es[i]->count_ub = fb.host[2 * i];
+                es[i]->count_exact = true;
+                if (counts) counts[i] = fb.host[2 * i];
+                if (drawn) drawn[i] = fb.host[2 * i + 1];
+            }
+            return T3D_OK;
+        }
+    }
     if (c->readback_cap < n)
     {
         if (c->readback_host) cudaFreeHost(c->readback_host);
@@ -1145,7 +1215,10 @@ static int refresh_counts(t3d_ctx* c, t3d_emitter* const* es, size_t n, uint32_t
     c->launches++;
     T3D_CUDA(cudaMemcpyAsync(c->readback_host, c->readback_dev, (n * 2 + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     T3D_TRY(staging_release(c, slot));
-    T3D_CUDA(cudaStreamSynchronize(c->stream));
+    {
+        HostTimer ht(c, T3D_HOST_WAIT);
+        T3D_CUDA(cudaStreamSynchronize(c->stream));
+    }
     c->d2h_bytes += n * 2 * sizeof(uint32_t);
     c->fault |= c->readback_host[2 * n];
     T3D_TRY(check_fault(c));
@@ -1421,6 +1494,7 @@ int t3d_ctx_sync(t3d_ctx* c)
     if (!c) return fail(T3D_ERR_INVALID, "null context");
     T3D_TRY(flush(c));
     T3D_TRY(use_device(c));
+    HostTimer ht(c, T3D_HOST_WAIT);
     T3D_CUDA(cudaStreamSynchronize(c->stream));
     return T3D_OK;
 }
@@ -1487,6 +1561,13 @@ int t3d_ctx_launch_count(t3d_ctx* c, uint64_t* n)
 {
     if (!c || !n) return fail(T3D_ERR_INVALID, "null argument");
     *n = c->launches;
+    return T3D_OK;
+}
+
+int t3d_ctx_host_profile(t3d_ctx* c, double seconds[T3D_HOST_PROFILE_SLOTS])
+{
+    if (!c || !seconds) return fail(T3D_ERR_INVALID, "null argument");
+    for (int k = 0; k < T3D_HOST_PROFILE_SLOTS; ++k) seconds[k] = c->host_s[k];
     return T3D_OK;
 }
 
@@ -2018,6 +2099,7 @@ int t3d_emitter_get_count(t3d_emitter* e, uint32_t* count)
 int t3d_batch_update(t3d_emitter* const* es, size_t n, float elapsed_ms)
 {
     if (!es && n) return fail(T3D_ERR_INVALID, "null argument");
+    HostTimer ht(n ? es[0]->ctx : nullptr, T3D_HOST_ENQUEUE);
     for (size_t i = 0; i < n; ++i) T3D_TRY(t3d_emitter_update(es[i], elapsed_ms));
     return T3D_OK;
 }
@@ -2025,6 +2107,7 @@ int t3d_batch_update(t3d_emitter* const* es, size_t n, float elapsed_ms)
 int t3d_batch_draw(t3d_emitter* const* es, size_t n)
 {
     if (!es && n) return fail(T3D_ERR_INVALID, "null argument");
+    HostTimer ht(n ? es[0]->ctx : nullptr, T3D_HOST_ENQUEUE);
     for (size_t i = 0; i < n; ++i) T3D_TRY(t3d_emitter_draw(es[i], nullptr));
     return T3D_OK;
 }
@@ -2032,6 +2115,7 @@ int t3d_batch_draw(t3d_emitter* const* es, size_t n)
 int t3d_batch_emit_once(t3d_emitter* const* es, size_t n, const uint32_t* counts)
 {
     if ((!es || !counts) && n) return fail(T3D_ERR_INVALID, "null argument");
+    HostTimer ht(n ? es[0]->ctx : nullptr, T3D_HOST_ENQUEUE);
     for (size_t i = 0; i < n; ++i) T3D_TRY(t3d_emitter_emit_once(es[i], counts[i]));
     return T3D_OK;
 }
@@ -2049,6 +2133,7 @@ int t3d_batch_get_counts(t3d_emitter* const* es, size_t n, uint32_t* counts)
 int t3d_batch_set_transforms(t3d_emitter* const* es, size_t n, const float* node_worlds, const float* camera_world)
 {
     if (!es && n) return fail(T3D_ERR_INVALID, "null argument");
+    HostTimer ht(n ? es[0]->ctx : nullptr, T3D_HOST_ENQUEUE);
     for (size_t i = 0; i < n; ++i)
     {
         if (node_worlds) T3D_TRY(t3d_emitter_set_node_world(es[i], node_worlds + 16 * i));
@@ -2230,6 +2315,7 @@ int t3d_emitter_upload_state(t3d_emitter* e, const uint32_t* in, size_t stride, 
     T3D_CUDA(cudaStreamSynchronize(c->stream));
     if (tmp) cudaFree(tmp);
     c->h2d_bytes += (size_t)count * T3D_NUM_COLUMNS * sizeof(uint32_t) + sizeof(uint32_t);
+    e->launch_version++;
     e->count_ub = count;
     e->count_exact = true;
     e->emitted_total += count; // keeps count feedback still in flight a valid upper bound

@@ -116,6 +116,12 @@ class Context:
         _check(self.lib, self.lib.t3d_ctx_launch_count(self.h, C.byref(n)))
         return n.value
 
+    def host_profile(self):
+        """Seconds the library has spent on the host: {enqueue, build, submit, wait} (t3d_ctx_host_profile)."""
+        out = (C.c_double * 4)()
+        _check(self.lib, self.lib.t3d_ctx_host_profile(self.h, out))
+        return dict(zip(("enqueue", "build", "submit", "wait"), out))
+
     def transfer_bytes(self):
         a, b = C.c_uint64(), C.c_uint64()
         _check(self.lib, self.lib.t3d_ctx_transfer_bytes(self.h, C.byref(a), C.byref(b)))
