@@ -155,8 +155,14 @@ int t3d_ctx_set_frozen_rotation(t3d_ctx* ctx, const float u[3], float angle);
 /* Returns the latched matrix (column-major 4x4) and whether it is latched yet. */
 int t3d_ctx_get_frozen_rotation(t3d_ctx* ctx, float m[16], int* latched);
 /* Forgets the function-local statics the reference keeps per process: the update rate-cap
- * accumulator (PE.cpp:720) and the latched rotation (SB.cpp:339) -- i.e. "a fresh process". */
+ * accumulator (PE.cpp:720) and the latched rotation (SB.cpp:339) -- i.e. "a fresh process".
+ * These two live ONCE PER PROCESS here as well: all contexts of a process (one per GPU) share them, so a host that drives
+ * N contexts from its game thread gets the reference's results however the emitters are split over the GPUs. */
 int t3d_ctx_reset_statics(t3d_ctx* ctx);
+/* on: this context keeps its own copy of those statics (fresh at the switch) instead of the process-wide one -- for hosts
+ * that drive their contexts from different threads (the shared copy is not synchronised), at the price that results with
+ * update steps under 8 ms, and the frame that latches the rotation, then depend on the split.  Off by default. */
+int t3d_ctx_set_private_statics(t3d_ctx* ctx, int on);
 /* Device time in ms of the last flushed launch of each kind (CUDA events on the context's stream):
  * which = 0 spawn, 1 update, 2 draw, 3 fused update+draw (T3D_FUSED=1).  Waits for that launch to finish. */
 int t3d_ctx_last_kernel_ms(t3d_ctx* ctx, int which, float* ms);

@@ -13,6 +13,9 @@ class GpuLib:
 
     def __init__(self, rng_mode=abi.RNG_STREAM, seed=0, device=0, rot_mode=abi.ROT_FROZEN):
         self.ctx = Context(device)
+        # the rate-cap accumulator and the latched rotation live once per process (like the reference's statics): a test
+        # that stands for "a fresh process" starts from fresh ones
+        self.ctx.reset_statics()
         self.ctx.set_rotation_mode(rot_mode)
         self.rng_mode, self.seed = rng_mode, seed
 

@@ -189,6 +189,7 @@ def test_create_from_a_hand_built_properties_tree(tmp_path):
     tree = C.c_void_p()
     assert lib.t3d_properties_new(b"particle", b"flame", C.byref(tree)) == abi.OK
     ctx = Context(0)
+    ctx.reset_statics()
     try:
         sprite = C.c_void_p()
         assert lib.t3d_properties_add_namespace(tree, b"sprite", None, C.byref(sprite)) == abi.OK

@@ -134,6 +134,7 @@ PROTOTYPES = {
     "t3d_ctx_set_frozen_rotation": (C.c_int, [_vp, _P(C.c_float), C.c_float]),
     "t3d_ctx_get_frozen_rotation": (C.c_int, [_vp, _P(C.c_float), _P(C.c_int)]),
     "t3d_ctx_reset_statics": (C.c_int, [_vp]),
+    "t3d_ctx_set_private_statics": (C.c_int, [_vp, C.c_int]),
     "t3d_ctx_last_kernel_ms": (C.c_int, [_vp, C.c_int, _P(C.c_float)]),
     "t3d_ctx_kernel_time": (C.c_int, [_vp, C.c_int, _P(C.c_double), _P(C.c_uint64)]),
     "t3d_ctx_launch_count": (C.c_int, [_vp, _P(C.c_uint64)]),

@@ -72,6 +72,21 @@ def build_facade_driver():
     return out
 
 
+def build_multi_ctx_driver():
+    """tests/multi_ctx_driver.cpp: one process, one thread, several contexts, through the C ABI only."""
+    root = os.path.dirname(HERE)
+    out_dir = os.path.join(HERE, "host", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, "multi_ctx_driver")
+    cmd = ["g++", "-std=c++17", "-O2", "-o", out, os.path.join(root, "tests", "multi_ctx_driver.cpp"),
+           "-L" + CSRC, "-lt3d_particles", "-Wl,-rpath,$ORIGIN/../../csrc"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building the multi-context driver")
+    return out
+
+
 REFERENCE = os.environ.get("T3D_REFERENCE", "/root/reference")
 
 

@@ -105,13 +105,28 @@ struct PendingOp
     size_t offsets_begin; // into ctx->pending_offsets (ellipsoid), or SIZE_MAX for constant stride
     uint32_t draw_stride;
     bool host_draws;
-    float world[16];
-    float right[3], up[3];
-    float vp[16];         // draw: the node's view-projection matrix (clip-space vertices)
     float* draw_dst;      // draw: the caller's device buffer (t3d_emitter_draw_to), or nullptr for the emitter's own stream
+    // (No copies of the node / camera / view-projection matrices: the setters launch whatever an emitter still has queued
+    //  before they change them, so the emitter's own copies are what the call saw when the descriptors are cut.)
 };
 
 } // namespace
+
+// What the reference keeps in function-local statics, i.e. once per PROCESS: the update rate-cap accumulator
+// (`static double runningTime`, PE.cpp:720) and the billboard rotation latched by the first rotated quad ever drawn
+// (`static Matrix rotation`, SB.cpp:339).  By default every context of the process shares one copy, like every emitter of
+// the reference process does -- a host that drives one context per GPU from its game thread gets the reference's results
+// whichever way the emitters are split over the GPUs.  t3d_ctx_set_private_statics gives a context its own copy (for
+// hosts that drive contexts from different threads: the shared copy is not synchronised).
+struct ProcessStatics
+{
+    double running_time{ 0 };
+    bool frozen_latched{ false };
+    float frozen_m[16]{};
+    uint64_t frozen_version{ 1 }; // bumped whenever the matrix or its latched state changes
+};
+static ProcessStatics g_statics;
+static std::vector<t3d_ctx*> g_contexts; // every live context of the process
 
 struct t3d_ctx
 {
@@ -139,13 +154,14 @@ struct t3d_ctx
     uint32_t epoch{ 0 };
 
     FrozenRotation* frozen_dev{ nullptr };
-    bool frozen_latched{ false };
-    float frozen_m[16];
+    uint64_t frozen_dev_version{ 0 }; // the version of the statics' matrix the device copy holds (0: none yet)
+    ProcessStatics own_statics;       // used instead of the process-wide copy when private_statics is set
+    bool private_statics{ false };
+    ProcessStatics& statics() { return private_statics ? own_statics : g_statics; }
+    const ProcessStatics& statics() const { return private_statics ? own_statics : g_statics; }
     int rot_mode{ T3D_ROT_FROZEN };
     int vertex_mode{ T3D_VERTEX_WORLD };
     uint32_t cta_slots{ 296 }; // CTAs of the update kernel the device runs at once (2 per SM)
-
-    double running_time{ 0 }; // PE.cpp:720, one per process in the reference, one per context here
 
     int phase{ PHASE_NONE };
     std::vector<PendingOp> pending;
@@ -250,6 +266,9 @@ struct t3d_emitter
     uint32_t count_ub{ 0 };     // upper bound of the live count (exact when count_exact)
     bool count_exact{ true };
     bool queued{ false };
+    // a queued spawn will read node_world / a queued draw will read camera_world and view_projection when its descriptors
+    // are cut: the setters launch it first if they are about to change what it was called with
+    bool node_in_use{ false }, camera_in_use{ false };
     bool held{ false }; // has an update in ctx->held (launch deferred, see flush)
     bool last_draw_empty{ true }; // the last draw() submitted no quads (inactive, no particles, or culled)
     float* last_draw_dst{ nullptr }; // where the last draw's quads went when not into the emitter's own stream (t3d_emitter_draw_to)
@@ -488,11 +507,20 @@ static int upload_frozen(t3d_ctx* c)
 {
     FrozenRotation f;
     memset(&f, 0, sizeof(f));
-    memcpy(f.m, c->frozen_m, sizeof(f.m));
-    f.latched = c->frozen_latched ? 1 : 0;
+    const ProcessStatics& st = c->statics();
+    memcpy(f.m, st.frozen_m, sizeof(f.m));
+    f.latched = st.frozen_latched ? 1 : 0;
     T3D_CUDA(cudaMemcpyAsync(c->frozen_dev, &f, sizeof(f), cudaMemcpyHostToDevice, c->stream));
     T3D_CUDA(cudaStreamSynchronize(c->stream)); // `f` is on the stack
+    c->frozen_dev_version = st.frozen_version;
     return T3D_OK;
+}
+
+// Before a launch that draws: the device copy of the rotation must be the one the statics hold now (another context of
+// the process may have latched it, or it may have been reset).
+static int ensure_frozen_current(t3d_ctx* c)
+{
+    return c->frozen_dev_version == c->statics().frozen_version ? T3D_OK : upload_frozen(c);
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -537,6 +565,7 @@ static void fill_const(const t3d_emitter* e, EmitterConst* k)
 
 static int sync_const(t3d_emitter* e)
 {
+    if (!e->uv_dirty && !e->const_dirty) return T3D_OK;
     t3d_ctx* c = e->ctx;
     if (e->uv_dirty)
     {
@@ -663,7 +692,7 @@ static int launch_spawns(t3d_ctx* c)
         e->parity ^= 1u;
         e->launch_version++;
         it.tile_begin = tiles;
-        memcpy(it.world, op.world, sizeof(it.world));
+        memcpy(it.world, e->node_world, sizeof(it.world)); // PE.cpp:299
         tiles += (op.emit_n + kSpawnThreads - 1) / kSpawnThreads;
     }
     T3D_TRY(staging_submit(c, slot, total));
@@ -804,7 +833,6 @@ static void build_update_items(std::vector<PendingOp>& ops, UpdateItem* items, C
         t3d_emitter* e = op.e;
         UpdateItem& it = items[k];
         const EmitterConst& ec = e->hc; // current: sync_const ran just before
-        memset(&it, 0, sizeof(it));
         it.dev = e->dev;
         it.st = ec.st;
         it.flags = ec.flags;
@@ -924,7 +952,8 @@ static int ensure_vertex_storage(t3d_ctx* c, std::vector<PendingOp>& ops)
     return T3D_OK;
 }
 
-static void build_draw_items(std::vector<PendingOp>& ops, DrawItem* items, uint32_t draw_tile, uint32_t* tiles_out, bool* any_spin_out)
+static void build_draw_items(std::vector<PendingOp>& ops, DrawItem* items, uint32_t draw_tile, uint32_t* tiles_out, bool* any_spin_out,
+                             bool clip)
 {
     uint32_t tiles = 0;
     bool any_spin = false;
@@ -934,7 +963,6 @@ static void build_draw_items(std::vector<PendingOp>& ops, DrawItem* items, uint3
         t3d_emitter* e = op.e;
         DrawItem& it = items[k];
         const EmitterConst& ec = e->hc; // current: sync_const ran just before
-        memset(&it, 0, sizeof(it));
         it.dev = e->dev;
         it.rw = ec.st.rw;
         it.vtx = op.draw_dst ? op.draw_dst : ec.vtx;
@@ -942,12 +970,13 @@ static void build_draw_items(std::vector<PendingOp>& ops, DrawItem* items, uint3
         it.stride = ec.st.stride;
         it.seg_capacity = ec.st.seg_capacity;
         it.frame_count = ec.frame_count;
-        memcpy(it.vp, op.vp, sizeof(it.vp));
+        if (clip) memcpy(it.vp, e->view_projection, sizeof(it.vp)); // PE.cpp:846-849 (only the clip-space draw reads it)
         e->launch_version++; // (a draw rewrites the emitter's quad count)
         it.parity = e->parity;
         it.tile_begin = tiles;
-        memcpy(it.right, op.right, 12);
-        memcpy(it.up, op.up, 12);
+        // PE.cpp:860-864: right = (m0, m1, m2), up = (m4, m5, m6) of the camera node's world matrix.
+        memcpy(it.right, e->camera_world, 12);
+        memcpy(it.up, e->camera_world + 4, 12);
         it.n_tiles = std::max(1u, (e->count_ub + draw_tile - 1) / draw_tile);
         tiles += it.n_tiles;
         any_spin = any_spin || e->may_spin;
@@ -960,13 +989,15 @@ static int launch_draws(t3d_ctx* c)
 {
     const uint32_t n_items = (uint32_t)c->pending.size();
     T3D_TRY(ensure_vertex_storage(c, c->pending));
+    T3D_TRY(ensure_frozen_current(c));
     StagingSlot* slot;
     T3D_TRY(staging_acquire(c, sizeof(DrawItem) * n_items, &slot));
     uint32_t tiles = 0;
     bool any_spin = false;
-    build_draw_items(c->pending, reinterpret_cast<DrawItem*>(slot->host), (uint32_t)draw_tile_size(n_items), &tiles, &any_spin);
+    build_draw_items(c->pending, reinterpret_cast<DrawItem*>(slot->host), (uint32_t)draw_tile_size(n_items), &tiles, &any_spin,
+                     c->vertex_mode == T3D_VERTEX_CLIP);
     T3D_TRY(staging_submit(c, slot, sizeof(DrawItem) * n_items));
-    if (c->rot_mode == T3D_ROT_FROZEN && !c->frozen_latched && any_spin)
+    if (c->rot_mode == T3D_ROT_FROZEN && !c->statics().frozen_latched && any_spin)
     {
         // SB.cpp:337-339: the first rotated quad of the process fixes the rotation matrix for good.  Find it on
         // the device, build the matrix on the host with the libm the reference uses, upload it.  Happens once.
@@ -980,8 +1011,10 @@ static int launch_draws(t3d_ctx* c)
         if (f.latched == 2)
         {
             const float u[3] = { f.m[0], f.m[1], f.m[2] };
-            host_create_rotation(u, f.m[3], c->frozen_m);
-            c->frozen_latched = true;
+            ProcessStatics& st = c->statics();
+            host_create_rotation(u, f.m[3], st.frozen_m);
+            st.frozen_latched = true;
+            st.frozen_version++;
             T3D_TRY(upload_frozen(c));
         }
     }
@@ -1008,7 +1041,7 @@ static bool can_fuse(const t3d_ctx* c)
         if (c->held[k].e->frame_count > (uint32_t)kMaxFusedFrames) return false; // the fused pass reads uv from shared memory only
         any_spin = any_spin || c->held[k].e->may_spin;
     }
-    if (c->rot_mode == T3D_ROT_FROZEN && !c->frozen_latched && any_spin) return false;
+    if (c->rot_mode == T3D_ROT_FROZEN && !c->statics().frozen_latched && any_spin) return false;
     return true;
 }
 
@@ -1016,6 +1049,7 @@ static int launch_fused_frame(t3d_ctx* c)
 {
     const uint32_t n_items = (uint32_t)c->held.size();
     T3D_TRY(ensure_vertex_storage(c, c->pending));
+    T3D_TRY(ensure_frozen_current(c));
     StagingSlot* slot;
     const size_t items_bytes = align_up(sizeof(UpdateItem) * n_items, 16);
     const size_t queries_bytes = align_up(sizeof(CountQuery) * n_items, 16);
@@ -1027,7 +1061,7 @@ static int launch_fused_frame(t3d_ctx* c)
     const uint32_t tile_size = (uint32_t)fused_tile_size(shape);
     build_update_items(c->held, reinterpret_cast<UpdateItem*>(slot->host), reinterpret_cast<CountQuery*>(slot->host + items_bytes),
                        tile_size, &tiles);
-    build_draw_items(c->pending, reinterpret_cast<DrawItem*>(slot->host + items_bytes + queries_bytes), tile_size, &draw_tiles, &any_spin);
+    build_draw_items(c->pending, reinterpret_cast<DrawItem*>(slot->host + items_bytes + queries_bytes), tile_size, &draw_tiles, &any_spin, false);
     T3D_TRY(begin_scan_epoch(c, tiles));
     T3D_TRY(staging_submit(c, slot, total_bytes));
     T3D_TRY(time_begin(c, KERNEL_UPDATE_DRAW));
@@ -1064,13 +1098,10 @@ static bool hold_for_fusion(const t3d_ctx* c)
 {
     const int mode = fused_mode();
     if (mode >= 0) return mode == 1;
-    uint64_t particles = 0, spawned = 0;
-    for (const PendingOp& op : c->pending)
-    {
-        particles += op.e->count_ub;
-        spawned += op.spawned;
-    }
-    return t3d_host_fuse_policy(particles, spawned) != 0; // <= 0.25 % replaced per frame
+    // (the policy no longer looks at its arguments -- the fused frame wins at every churn level measured -- so the
+    //  population is not summed up here; see t3d_host_fuse_policy)
+    (void)c;
+    return t3d_host_fuse_policy(0, 0) != 0;
 }
 
 static int check_fault(const t3d_ctx* c)
@@ -1137,7 +1168,11 @@ static int flush(t3d_ctx* c, int next_phase = PHASE_NONE)
             if (rc == T3D_OK) rc = launch_draws(c);
         }
     }
-    for (PendingOp& op : c->pending) op.e->queued = false;
+    for (PendingOp& op : c->pending)
+    {
+        op.e->queued = false;
+        op.e->node_in_use = op.e->camera_in_use = false; // spawns and draws of this phase have been cut and launched
+    }
     if (hold)
     {
         c->held.swap(c->pending);
@@ -1156,6 +1191,8 @@ static int enqueue(t3d_ctx* c, int phase, const PendingOp& op)
     c->phase = phase;
     c->pending.push_back(op);
     op.e->queued = true;
+    if (op.emit_n) op.e->node_in_use = true;
+    if (phase == PHASE_DRAW) op.e->camera_in_use = true;
     return T3D_OK;
 }
 
@@ -1339,7 +1376,6 @@ static int prepare_emit(t3d_emitter* e, uint32_t n, PendingOp* op)
         if (!e->may_spin) e->const_dirty = true;
         e->may_spin = true;
     }
-    memcpy(op->world, e->node_world, sizeof(op->world));
     op->host_draws = false;
     op->draws_begin = op->draws_count = 0;
     op->offsets_begin = SIZE_MAX;
@@ -1418,7 +1454,6 @@ int t3d_ctx_create(int device, void* cuda_stream, t3d_ctx** out)
         delete c;
         return fail(T3D_ERR_CUDA, "t3d_ctx_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    memset(c->frozen_m, 0, sizeof(c->frozen_m));
     {
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) c->cta_slots = 2u * (uint32_t)sms;
@@ -1428,6 +1463,7 @@ int t3d_ctx_create(int device, void* cuda_stream, t3d_ctx** out)
         if (!(env && env[0] == '0') && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
             c->copy_stream = nullptr; // descriptors then travel on the launching stream
     }
+    g_contexts.push_back(c);
     *out = c;
     return T3D_OK;
 }
@@ -1435,6 +1471,7 @@ int t3d_ctx_create(int device, void* cuda_stream, t3d_ctx** out)
 int t3d_ctx_destroy(t3d_ctx* c)
 {
     if (!c) return T3D_OK;
+    g_contexts.erase(std::remove(g_contexts.begin(), g_contexts.end(), c), g_contexts.end());
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     std::vector<t3d_emitter*> es = c->emitters;
@@ -1512,8 +1549,10 @@ int t3d_ctx_set_frozen_rotation(t3d_ctx* c, const float u[3], float angle)
     if (!c || !u) return fail(T3D_ERR_INVALID, "null argument");
     T3D_TRY(flush(c));
     T3D_TRY(use_device(c));
-    host_create_rotation(u, angle, c->frozen_m);
-    c->frozen_latched = true;
+    ProcessStatics& st = c->statics();
+    host_create_rotation(u, angle, st.frozen_m);
+    st.frozen_latched = true;
+    st.frozen_version++;
     return upload_frozen(c);
 }
 
@@ -1521,8 +1560,8 @@ int t3d_ctx_get_frozen_rotation(t3d_ctx* c, float m[16], int* latched)
 {
     if (!c) return fail(T3D_ERR_INVALID, "null context");
     T3D_TRY(flush(c));
-    if (m) memcpy(m, c->frozen_m, sizeof(c->frozen_m));
-    if (latched) *latched = c->frozen_latched ? 1 : 0;
+    if (m) memcpy(m, c->statics().frozen_m, sizeof(c->statics().frozen_m));
+    if (latched) *latched = c->statics().frozen_latched ? 1 : 0;
     return T3D_OK;
 }
 
@@ -1531,10 +1570,28 @@ int t3d_ctx_reset_statics(t3d_ctx* c)
     if (!c) return fail(T3D_ERR_INVALID, "null context");
     T3D_TRY(flush(c));
     T3D_TRY(use_device(c));
-    c->running_time = 0;
-    c->frozen_latched = false;
-    memset(c->frozen_m, 0, sizeof(c->frozen_m));
+    // (work other contexts of the process have queued belongs to the "old process": it goes out first)
+    if (!c->private_statics)
+        for (t3d_ctx* o : g_contexts)
+            if (o != c && !o->private_statics) T3D_TRY(flush(o));
+    T3D_TRY(use_device(c));
+    ProcessStatics& st = c->statics();
+    st.running_time = 0;
+    st.frozen_latched = false;
+    memset(st.frozen_m, 0, sizeof(st.frozen_m));
+    st.frozen_version++;
     return upload_frozen(c);
+}
+
+int t3d_ctx_set_private_statics(t3d_ctx* c, int on)
+{
+    if (!c) return fail(T3D_ERR_INVALID, "null context");
+    T3D_TRY(flush(c));
+    if ((on != 0) == c->private_statics) return T3D_OK;
+    if (on) c->own_statics = ProcessStatics(); // a fresh copy: "a process of its own"
+    c->private_statics = on != 0;
+    c->frozen_dev_version = 0;
+    return T3D_OK;
 }
 
 int t3d_ctx_last_kernel_ms(t3d_ctx* c, int which, float* ms)
@@ -1844,6 +1901,7 @@ int t3d_emitter_pending_draws(t3d_emitter* e, size_t* n)
 int t3d_emitter_set_node_world(t3d_emitter* e, const float world[16])
 {
     if (!e || !world) return fail(T3D_ERR_INVALID, "null argument");
+    if (e->node_in_use && memcmp(e->node_world, world, sizeof(e->node_world)) != 0) T3D_TRY(flush(e->ctx));
     memcpy(e->node_world, world, sizeof(e->node_world));
     e->has_node = true;
     return T3D_OK;
@@ -1852,6 +1910,7 @@ int t3d_emitter_set_node_world(t3d_emitter* e, const float world[16])
 int t3d_emitter_set_camera_world(t3d_emitter* e, const float m[16])
 {
     if (!e || !m) return fail(T3D_ERR_INVALID, "null argument");
+    if (e->camera_in_use && memcmp(e->camera_world, m, sizeof(e->camera_world)) != 0) T3D_TRY(flush(e->ctx));
     memcpy(e->camera_world, m, sizeof(e->camera_world));
     e->has_camera = true;
     return T3D_OK;
@@ -1860,6 +1919,7 @@ int t3d_emitter_set_camera_world(t3d_emitter* e, const float m[16])
 int t3d_emitter_set_view_projection(t3d_emitter* e, const float m[16])
 {
     if (!e || !m) return fail(T3D_ERR_INVALID, "null argument");
+    if (e->camera_in_use && memcmp(e->view_projection, m, sizeof(e->view_projection)) != 0) T3D_TRY(flush(e->ctx));
     memcpy(e->view_projection, m, sizeof(e->view_projection));
     e->has_vp = true;
     return T3D_OK;
@@ -1999,7 +2059,7 @@ int t3d_emitter_update(t3d_emitter* e, float elapsed_time)
     T3D_TRY(is_active(e, &active));
     if (!active) return T3D_OK; // PE.cpp:715
     float elapsed_ms;
-    if (!t3d_host_rate_cap(&c->running_time, elapsed_time, &elapsed_ms)) return T3D_OK; // PE.cpp:720-725
+    if (!t3d_host_rate_cap(&c->statics().running_time, elapsed_time, &elapsed_ms)) return T3D_OK; // PE.cpp:720-725 (process-wide)
     if (c->phase != PHASE_UPDATE || e->queued) T3D_TRY(flush(c));
     PendingOp op{};
     op.e = e;
@@ -2064,13 +2124,14 @@ static int draw_common(t3d_emitter* e, float* dst, size_t dst_quads, uint32_t* d
     // is a frame or two old unless t3d_emitter_bounds was just called -- and never waits for the device.
     if (e->culling && e->box_known && !e->box_empty && outside_frustum(e->view_projection, e->box_lo, e->box_hi))
         return T3D_OK; // nothing of it can reach the screen
+    // SB.cpp:339 latches the rotation of the first rotated quad the PROCESS ever draws.  Until that has happened, draws
+    // reach the device in call order across the contexts that share the statics: whatever the others still hold goes first.
+    if (!c->private_statics && c->rot_mode == T3D_ROT_FROZEN && !g_statics.frozen_latched && g_contexts.size() > 1)
+        for (t3d_ctx* o : g_contexts)
+            if (o != c && !o->private_statics && (!o->pending.empty() || !o->held.empty())) T3D_TRY(flush(o));
     PendingOp op{};
     op.e = e;
     op.offsets_begin = SIZE_MAX;
-    // PE.cpp:860-864: right = (m0, m1, m2), up = (m4, m5, m6) of the camera node's world matrix.
-    op.right[0] = e->camera_world[0]; op.right[1] = e->camera_world[1]; op.right[2] = e->camera_world[2];
-    op.up[0] = e->camera_world[4]; op.up[1] = e->camera_world[5]; op.up[2] = e->camera_world[6];
-    memcpy(op.vp, e->view_projection, sizeof(op.vp)); // PE.cpp:846-849
     op.draw_dst = dst;
     e->last_draw_empty = false;
     e->last_draw_dst = dst;

@@ -86,6 +86,9 @@ class Context:
     def reset_statics(self):
         _check(self.lib, self.lib.t3d_ctx_reset_statics(self.h))
 
+    def set_private_statics(self, on):
+        _check(self.lib, self.lib.t3d_ctx_set_private_statics(self.h, int(bool(on))))
+
     def last_kernel_ms(self, which):
         ms = C.c_float()
         _check(self.lib, self.lib.t3d_ctx_last_kernel_ms(self.h, which, C.byref(ms)))
