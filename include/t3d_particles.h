@@ -289,6 +289,50 @@ int t3d_ctx_download_strip_indices(t3d_ctx* ctx, uint32_t n_quads, uint32_t* out
 int t3d_emitter_download_state(t3d_emitter* e, uint32_t* out, size_t stride, uint32_t* count);
 int t3d_emitter_upload_state(t3d_emitter* e, const uint32_t* in, size_t stride, uint32_t count);
 
+/* ---- the other SpriteBatch producers -- 2-D quads ---------------------------------------------
+ * TileSet::draw (src/graphics/TileSet.cpp:179-236), Font::drawText (src/renderer/Font.cpp:242-420) and the UI controls
+ * (src/ui/Control.cpp, Container.cpp) feed SpriteBatch's 2-D overloads, one call per quad.  One t3d_sprite2d = one such
+ * call; a list of them expands on the device into the same SpriteVertex stream, in call order, culled sprites leaving no
+ * gap.  "SB.cpp" line numbers as above. */
+enum {
+    T3D_SPRITE_ROTATED = 1,  /* the overloads that take rotationPoint / rotationAngle (SB.cpp:235-289): vertices leave in the
+                                order downLeft, upLeft, downRight, upRight and turn about the pivot when the angle is not 0 */
+    T3D_SPRITE_CENTERED = 2, /* positionIsCenter (SB.cpp:248-252, :487-491) */
+    T3D_SPRITE_CLIPPED = 4   /* the overloads with a clip rectangle (SB.cpp:366-413): clipped against it by clipSprite
+                                (SB.cpp:523-597), dropped when entirely outside; not combined with T3D_SPRITE_ROTATED */
+};
+typedef struct t3d_sprite2d {
+    float x, y, z, width, height;   /* destination */
+    float u1, v1, u2, v2;           /* source, already in texture coordinates (SB.cpp:176-181 is the caller's) */
+    float color[4];
+    float rotation_point[2];        /* T3D_SPRITE_ROTATED */
+    float rotation_angle;
+    uint32_t flags;
+    float clip[4];                  /* T3D_SPRITE_CLIPPED: x, y, width, height */
+} t3d_sprite2d;
+/* Expands n sprites.  `sprites` is host memory (copied in through pinned staging) or, with sprites_on_device, a device
+ * array the caller keeps resident.  Quads go to device_dst (16-byte aligned, dst_quads quads; T3D_ERR_CAPACITY if n does
+ * not fit) or, when it is NULL, to a buffer the context owns; *device_ptr receives where.  *n_quads (may be NULL) receives
+ * the number of quads written, which waits for the device when some sprite is clipped; without clipping it is n. */
+int t3d_ctx_draw_sprites(t3d_ctx* ctx, const t3d_sprite2d* sprites, size_t n, int sprites_on_device, void* device_dst,
+                         size_t dst_quads, const t3d_sprite_vertex** device_ptr, uint32_t* n_quads);
+
+/* TileSet (include/graphics/TileSet.h): a grid of equally sized tiles cut from one texture; blank cells are skipped.  The
+ * tile table lives on the device, so a frame uploads nothing but its position. */
+typedef struct t3d_tileset t3d_tileset;
+int t3d_tileset_create(t3d_ctx* ctx, uint32_t texture_width, uint32_t texture_height, float tile_width, float tile_height,
+                       uint32_t row_count, uint32_t column_count, t3d_tileset** out);            /* TileSet.cpp:31-58: every cell blank */
+int t3d_tileset_destroy(t3d_tileset* t);
+int t3d_tileset_set_tile_source(t3d_tileset* t, uint32_t column, uint32_t row, float x, float y); /* TileSet.cpp:155-165 */
+/* all cells at once: sources = row_count * column_count * {x, y}, row-major; negative = blank (TileSet.cpp:217) */
+int t3d_tileset_set_tiles(t3d_tileset* t, const float* sources);
+/* TileSet::draw (TileSet.cpp:179-236).  position = what the function derives from its node and the active camera's node
+ * (node world translation minus the camera node's x and y, :182-205); color = _color with _opacity folded into alpha (:226).
+ * Destination as in t3d_ctx_draw_sprites; *n_quads = the number of non-blank cells (known on the host: no wait). */
+int t3d_tileset_draw(t3d_tileset* t, const float position[3], const float color[4], void* device_dst, size_t dst_quads,
+                     const t3d_sprite_vertex** device_ptr, uint32_t* n_quads);
+int t3d_ctx_download_quads(t3d_ctx* ctx, const t3d_sprite_vertex* device_ptr, uint32_t n_quads, float* out); /* tests */
+
 /* ---- pure host helpers (no GPU needed): the scalar logic of the path ----------------------- */
 /* Raw 31-bit draw j of particle `serial` for T3D_RNG_DEVICE (same function the spawn kernel evaluates). */
 int32_t t3d_device_rng_draw(uint64_t seed, uint64_t serial, uint32_t j);

@@ -696,6 +696,141 @@ uint64_t orc_strip_indices(uint32_t n_quads, uint32_t* out)
 }
 
 /* =====================================================================================
+ * SpriteBatch's 2-D overloads (SB.cpp:235-289, :366-413, :475-506, clipSprite :523-597) and TileSet::draw
+ * (src/graphics/TileSet.cpp:179-236).  Pinned bit for bit to the reference's own code by tests/test_oracle_vs_ref.py.
+ * ===================================================================================== */
+static void sprite_vertex(float* v, float x, float y, float z, float u, float t, const float* c)
+{
+    v[0] = x; v[1] = y; v[2] = z; v[3] = u; v[4] = t; v[5] = c[0]; v[6] = c[1]; v[7] = c[2]; v[8] = c[3]; /* SB.cpp:21-31 */
+}
+
+/* Vector2::rotate, src/math/Vector2.cpp:181-200.  `double sinAngle = sin(angle)` with a float argument: in C++ that is
+ * the float overload (sinf) widened afterwards; the products are then formed in double and rounded to float where the
+ * reference assigns to its float members. */
+static void rotate2(float* x, float* y, float px, float py, float angle)
+{
+    const double s = (double)sinf(angle), c = (double)cosf(angle);
+    if (px == 0.0f && py == 0.0f) {
+        const float tx = (float)(*x * c - *y * s);
+        *y = (float)(*y * c + *x * s);
+        *x = tx;
+    } else {
+        const float tx = *x - px, ty = *y - py;
+        *x = (float)(tx * c - ty * s + px);
+        *y = (float)(ty * c + tx * s + py);
+    }
+}
+
+/* SB.cpp:523-597 */
+static int clip_sprite(const float* clip, float* x, float* y, float* w, float* h, float* u1, float* v1, float* u2, float* v2)
+{
+    if (*x + *w < clip[0] || *x > clip[0] + clip[2] || *y + *h < clip[1] || *y > clip[1] + clip[3]) return 0;
+    float uvw = *u2 - *u1, uvh = *v2 - *v1;
+    if (*x < clip[0]) {
+        const float percent = (clip[0] - *x) / *w, dx = clip[0] - *x, du = uvw * percent;
+        *x = clip[0]; *w -= dx; *u1 += du; uvw -= du;
+    }
+    if (*y < clip[1]) {
+        const float percent = (clip[1] - *y) / *h, dy = clip[1] - *y, dv = uvh * percent;
+        *y = clip[1]; *h -= dy; *v1 += dv; uvh -= dv;
+    }
+    const float cx2 = clip[0] + clip[2];
+    const float x2 = *x + *w;
+    if (x2 > cx2) {
+        const float percent = (x2 - cx2) / *w;
+        *w = cx2 - *x;
+        *u2 -= uvw * percent;
+    }
+    const float cy2 = clip[1] + clip[3];
+    const float y2 = *y + *h;
+    if (y2 > cy2) {
+        const float percent = (y2 - cy2) / *h;
+        *h = cy2 - *y;
+        *v2 -= uvh * percent;
+    }
+    return 1;
+}
+
+/* One sprite -> 0 or 1 quad (36 floats at q). */
+static int sprite_quad(const t3d_sprite2d* sp, float* q)
+{
+    float x = sp->x, y = sp->y, w = sp->width, h = sp->height, u1 = sp->u1, v1 = sp->v1, u2 = sp->u2, v2 = sp->v2;
+    const float z = sp->z;
+    if (sp->flags & T3D_SPRITE_CLIPPED) {                       /* SB.cpp:394-413 */
+        if (!clip_sprite(sp->clip, &x, &y, &w, &h, &u1, &v1, &u2, &v2)) return 0;
+    } else if (sp->flags & T3D_SPRITE_CENTERED) {               /* SB.cpp:248-252, :487-491 */
+        x -= 0.5f * w;
+        y -= 0.5f * h;
+    }
+    const float x2 = x + w, y2 = y + h;
+    if ((sp->flags & T3D_SPRITE_ROTATED) && !(sp->flags & T3D_SPRITE_CLIPPED)) {  /* SB.cpp:254-288 */
+        float ulx = x, uly = y, urx = x2, ury = y, dlx = x, dly = y2, drx = x2, dry = y2;
+        if (sp->rotation_angle != 0) {
+            float px = sp->rotation_point[0], py = sp->rotation_point[1];
+            px *= w; py *= h; px += x; py += y;
+            rotate2(&ulx, &uly, px, py, sp->rotation_angle);
+            rotate2(&urx, &ury, px, py, sp->rotation_angle);
+            rotate2(&dlx, &dly, px, py, sp->rotation_angle);
+            rotate2(&drx, &dry, px, py, sp->rotation_angle);
+        }
+        sprite_vertex(q + 0, dlx, dly, z, u1, v1, sp->color);
+        sprite_vertex(q + 9, ulx, uly, z, u1, v2, sp->color);
+        sprite_vertex(q + 18, drx, dry, z, u2, v1, sp->color);
+        sprite_vertex(q + 27, urx, ury, z, u2, v2, sp->color);
+    } else {                                                    /* SB.cpp:493-505 */
+        sprite_vertex(q + 0, x, y, z, u1, v1, sp->color);
+        sprite_vertex(q + 9, x, y2, z, u1, v2, sp->color);
+        sprite_vertex(q + 18, x2, y, z, u2, v1, sp->color);
+        sprite_vertex(q + 27, x2, y2, z, u2, v2, sp->color);
+    }
+    return 1;
+}
+
+uint32_t orc_sprites_2d(const t3d_sprite2d* sp, size_t n, float* out, size_t max_quads)
+{
+    uint32_t quads = 0;
+    float scratch[36];
+    for (size_t i = 0; i < n; ++i)
+        quads += (uint32_t)sprite_quad(&sp[i], (out && quads < max_quads) ? out + (size_t)quads * 36 : scratch);
+    return quads;
+}
+
+/* TileSet::draw, TileSet.cpp:207-236, from the position the function has arrived at by line 205 (node translation minus
+ * the camera's x and y).  sources = rows * cols * {x, y}, negative = blank. */
+uint32_t orc_tileset_draw(const float* sources, uint32_t rows, uint32_t cols, float tile_w, float tile_h, float tex_w, float tex_h,
+                          const float position[3], const float color[4], float* out, size_t max_quads)
+{
+    const float wr = 1.0f / tex_w, hr = 1.0f / tex_h;          /* SB.cpp:155-156 */
+    float px = position[0], py = position[1];
+    py += tile_h * (float)(rows - 1);                            /* :208 */
+    const float x_start = px;
+    uint32_t quads = 0;
+    float scratch[36];
+    for (uint32_t row = 0; row < rows; ++row) {
+        for (uint32_t col = 0; col < cols; ++col) {
+            const float sx = sources[2 * ((size_t)row * cols + col)], sy = sources[2 * ((size_t)row * cols + col) + 1];
+            if (sx >= 0 && sy >= 0) {                            /* :217 */
+                t3d_sprite2d sp;
+                memset(&sp, 0, sizeof(sp));
+                sp.x = px; sp.y = py; sp.z = position[2]; sp.width = tile_w; sp.height = tile_h;
+                sp.u1 = wr * sx;                                 /* SB.cpp:208-211 */
+                sp.v1 = 1.0f - hr * sy;
+                sp.u2 = sp.u1 + wr * tile_w;
+                sp.v2 = sp.v1 - hr * tile_h;
+                memcpy(sp.color, color, 16);
+                sp.rotation_point[0] = sp.rotation_point[1] = 0.5f;
+                sp.flags = T3D_SPRITE_ROTATED;                   /* :223-228: the rotationPoint overload, angle 0 */
+                quads += (uint32_t)sprite_quad(&sp, (out && quads < max_quads) ? out + (size_t)quads * 36 : scratch);
+            }
+            px += tile_w;                                        /* :231 */
+        }
+        px = x_start;                                            /* :233-234 */
+        py -= tile_h;
+    }
+    return quads;
+}
+
+/* =====================================================================================
  * Timing loops.
  * ===================================================================================== */
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }

@@ -78,6 +78,12 @@ int orc_emitter_bounds(orc_emitter* e, float lo[3], float hi[3]);
  * 32-bit indices.  Returns the number of indices written (6n-2).  Restated, not reference-pinned (MeshBatch.cpp needs GL). */
 uint64_t orc_strip_indices(uint32_t n_quads, uint32_t* out);
 
+/* one SpriteBatch::draw 2-D call per t3d_sprite2d (SB.cpp:235-289, :366-413, :475-506); 36 floats per quad. */
+uint32_t orc_sprites_2d(const t3d_sprite2d* sprites, size_t n, float* out, size_t max_quads);
+/* TileSet::draw (TileSet.cpp:207-236) from the position it has computed by line 205. */
+uint32_t orc_tileset_draw(const float* sources, uint32_t rows, uint32_t cols, float tile_w, float tile_h, float tex_w, float tex_h,
+                          const float position[3], const float color[4], float* out, size_t max_quads);
+
 /* ---- timing loops (seconds) for bench.py's cpu_baseline "port" leg ---- */
 double orc_time_update(orc_emitter* e, float elapsed_ms, int frames);
 double orc_time_draw(orc_emitter* e, int frames);

@@ -11,6 +11,7 @@ class Texture : public Ref
   public:
     enum Filter { NEAREST, LINEAR, NEAREST_MIPMAP_NEAREST, LINEAR_MIPMAP_NEAREST, NEAREST_MIPMAP_LINEAR, LINEAR_MIPMAP_LINEAR };
     enum Type { TEXTURE_2D, TEXTURE_CUBE };
+    enum Wrap { REPEAT, CLAMP };
     static Texture* create(const std::string& path, bool generateMipmaps = false);
     unsigned int getWidth() const { return _width; }
     unsigned int getHeight() const { return _height; }
@@ -24,6 +25,7 @@ class Texture : public Ref
         static Sampler* create(Texture* texture) { Sampler* s = new Sampler(); s->_texture = texture; texture->addRef(); return s; }
         ~Sampler() { if (_texture) _texture->release(); }
         void setFilterMode(Filter, Filter) {}
+        void setWrapMode(Wrap, Wrap, Wrap = REPEAT) {}
         Texture* getTexture() const { return _texture; }
       private:
         Texture* _texture{ nullptr };

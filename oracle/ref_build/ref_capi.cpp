@@ -24,6 +24,7 @@
 #include "framework/Platform.h"
 #include "graphics/ParticleEmitter.h"
 #include "graphics/SpriteBatch.h"
+#include "graphics/TileSet.h"
 #include "scene/Node.h"
 #include "scene/Scene.h"
 
@@ -152,6 +153,19 @@ struct RefEmitter
     Scene scene;
 };
 
+// SpriteBatch.cpp keeps its sprite effect in a file-level static and drops it with the last batch (SB.cpp:49-65) -- but
+// the batch's material still holds a reference when that destructor runs, so the static is left dangling once the last
+// batch of the process is gone and the next SpriteBatch::create() would touch freed memory.  A harness that creates and
+// destroys batches all day keeps one alive for good.
+void keep_sprite_effect_alive()
+{
+    static SpriteBatch* keeper = nullptr;
+    if (keeper) return;
+    Texture* tex = Texture::create(std::string("@1x1"));
+    keeper = SpriteBatch::create(tex);
+    tex->release();
+}
+
 void wire(RefEmitter* r)
 {
     r->alloc_max = r->pe->_particleCountMax;
@@ -211,6 +225,7 @@ size_t t3dref_sizeof_particle(void) { return sizeof(ParticleEmitter::Particle); 
 // ---- lifecycle ----
 void* t3dref_emitter_create(const t3d_emitter_params* p)
 {
+    keep_sprite_effect_alive();
     char tex[64];
     snprintf(tex, sizeof(tex), "@%ux%u", (unsigned)p->texture_width, (unsigned)p->texture_height);
     ParticleEmitter* e = ParticleEmitter::create(std::string(tex), (ParticleEmitter::BlendMode)p->blend_mode,
@@ -225,6 +240,7 @@ void* t3dref_emitter_create(const t3d_emitter_params* p)
 
 void* t3dref_emitter_create_from_file(const char* url)
 {
+    keep_sprite_effect_alive();
     ParticleEmitter* e = ParticleEmitter::create(std::string(url));
     if (!e) return nullptr;
     RefEmitter* r = new RefEmitter();
@@ -428,6 +444,105 @@ double t3dref_time_frames(void* h, float elapsed_ms, int frames)
     for (int i = 0; i < frames; ++i) { e->update(elapsed_ms); e->draw(false); }
     auto t1 = std::chrono::steady_clock::now();
     return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---- SpriteBatch's 2-D overloads and TileSet, driven headless ----
+static uint32_t copy_captured(MeshBatch* mb, float* out, size_t max_quads)
+{
+    const size_t quads = mb->capturedVertexCount() / 4;
+    if (out)
+    {
+        size_t bytes = (quads < max_quads ? quads : max_quads) * 4 * sizeof(SpriteBatch::SpriteVertex);
+        if (bytes > mb->capturedBytes().size()) bytes = mb->capturedBytes().size();
+        memcpy(out, mb->capturedBytes().data(), bytes);
+    }
+    return (uint32_t)quads;
+}
+
+// One SpriteBatch::draw call per t3d_sprite2d, the overload the flags name; returns the quads the batch received.
+// time_s (optional): seconds spent between start() and finish().
+uint32_t t3dref_sprites_2d(const t3d_sprite2d* sp, size_t n, uint32_t tex_w, uint32_t tex_h, float* out, size_t max_quads, double* time_s)
+{
+    keep_sprite_effect_alive();
+    char name[64];
+    snprintf(name, sizeof(name), "@%ux%u", tex_w, tex_h);
+    Texture* tex = Texture::create(std::string(name));
+    if (!tex) return 0;
+    SpriteBatch* b = SpriteBatch::create(tex);
+    tex->release();
+    auto t0 = std::chrono::steady_clock::now();
+    b->start();
+    for (size_t i = 0; i < n; ++i)
+    {
+        const t3d_sprite2d& s = sp[i];
+        const Vector4 color(s.color[0], s.color[1], s.color[2], s.color[3]);
+        if (s.flags & T3D_SPRITE_CLIPPED)
+            b->draw(s.x, s.y, s.z, s.width, s.height, s.u1, s.v1, s.u2, s.v2, color, Rectangle(s.clip[0], s.clip[1], s.clip[2], s.clip[3]));
+        else if (s.flags & T3D_SPRITE_ROTATED)
+            b->draw(s.x, s.y, s.z, s.width, s.height, s.u1, s.v1, s.u2, s.v2, color, Vector2(s.rotation_point[0], s.rotation_point[1]),
+                    s.rotation_angle, (s.flags & T3D_SPRITE_CENTERED) != 0);
+        else
+            b->draw(s.x, s.y, s.z, s.width, s.height, s.u1, s.v1, s.u2, s.v2, color, (s.flags & T3D_SPRITE_CENTERED) != 0);
+    }
+    b->finish();
+    if (time_s) *time_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    const uint32_t quads = copy_captured(b->_batch.get(), out, max_quads);
+    delete b;
+    return quads;
+}
+
+namespace
+{
+struct RefTileSet
+{
+    TileSet* ts{ nullptr };
+    Node node, cameraNode;
+    Camera camera;
+    Scene scene;
+};
+} // namespace
+
+void* t3dref_tileset_create(uint32_t tex_w, uint32_t tex_h, float tile_w, float tile_h, uint32_t rows, uint32_t cols)
+{
+    keep_sprite_effect_alive();
+    char name[64];
+    snprintf(name, sizeof(name), "@%ux%u", tex_w, tex_h);
+    TileSet* ts = TileSet::create(std::string(name), tile_w, tile_h, rows, cols);
+    if (!ts) return nullptr;
+    RefTileSet* r = new RefTileSet();
+    r->ts = ts;
+    r->camera._node = &r->cameraNode;
+    r->scene._camera = &r->camera;
+    r->node._scene = &r->scene;
+    r->node.setDrawable(ts);
+    return r;
+}
+void t3dref_tileset_destroy(void* h)
+{
+    RefTileSet* r = (RefTileSet*)h;
+    if (!r) return;
+    r->node.setDrawable(nullptr);
+    r->ts->release();
+    delete r;
+}
+void t3dref_tileset_set_tile_source(void* h, uint32_t col, uint32_t row, float x, float y)
+{
+    ((RefTileSet*)h)->ts->setTileSource(col, row, Vector2(x, y));
+}
+// TileSet::draw with the node at node_t and the active camera's node at camera_t (world translations).
+uint32_t t3dref_tileset_draw(void* h, const float node_t[3], const float camera_t[3], const float color[4], float opacity, float* out,
+                             size_t max_quads)
+{
+    RefTileSet* r = (RefTileSet*)h;
+    for (int k = 0; k < 3; ++k)
+    {
+        r->node._world.m[12 + k] = node_t[k];
+        r->cameraNode._world.m[12 + k] = camera_t[k];
+    }
+    r->ts->setColor(Vector4(color[0], color[1], color[2], color[3]));
+    r->ts->setOpacity(opacity);
+    r->ts->draw(false);
+    return copy_captured(r->ts->_batch->_batch.get(), out, max_quads);
 }
 
 } // extern "C"

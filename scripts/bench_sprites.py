@@ -1,0 +1,102 @@
+#!/usr/bin/env python
+"""SURVEY 8(f3) measured: the 2-D SpriteBatch overloads as a batched expansion kernel and TileSet::draw from a
+device-resident tile table, against the reference's own SpriteBatch.cpp on one host core (oracle/_ref).
+
+    python scripts/bench_sprites.py [n_sprites] [tile rows] [tile cols]
+
+Algorithmic bytes: 84 B read + 144 B written per sprite (228 B); per tile 4 B cell index + 8 B source read + 144 B written."""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+import cpu_harness as H  # noqa: E402
+from tractor3d_b200.emitter import Context, TileSet  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+rows = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+cols = int(sys.argv[3]) if len(sys.argv) > 3 else 2048
+PEAK = 6541.1
+stream = torch.cuda.Stream()
+ctx = Context(0, stream.cuda_stream)
+
+
+def timed(fn, reps=20, warm=3):
+    for _ in range(warm):
+        fn()
+    ctx.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    ctx.sync(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, (time.perf_counter() - t0) / reps * 1e3   # device ms, wall ms
+
+
+print(f"{n} sprites; tile set {rows} x {cols}")
+for label, kw in (("plain + centred (no clipping, no rotation)", dict(clipped=False, rotated=False)),
+                  ("every overload (a third clipped, a third rotated)", dict())):
+    sp = H.random_sprites(n, 11, **kw)
+    dev_list = torch.from_numpy(sp.view(np.uint8).copy()).cuda()
+    dst = torch.empty(n * 36, dtype=torch.float32, device="cuda")
+    d_ms, w_ms = timed(lambda: ctx.draw_sprites(dev_list.data_ptr(), device_dst=dst.data_ptr(), dst_quads=n, on_device=True, n=n, want_count=False))
+    print(f"  {label}\n    list resident in HBM: {d_ms:.3f} ms per list = {n / d_ms / 1e6:.2f} G sprites/s, "
+          f"{228 * n / d_ms / 1e6:.0f} GB/s algorithmic ({228 * n / d_ms / 1e6 / PEAK:.2f} of the measured HBM peak)")
+    d_ms, w_ms = timed(lambda: ctx.draw_sprites(sp, device_dst=dst.data_ptr(), dst_quads=n, want_count=False), reps=10)
+    print(f"    list in host memory (copied through pinned staging every call, 84 B per sprite): {w_ms:.3f} ms wall per list = "
+          f"{n / w_ms / 1e6:.3f} G sprites/s; host -> device {84 * n / 1e6:.1f} MB per list")
+    R = H.ref(fresh=True)
+    m = min(n, 1 << 18)
+    t = C.c_double()
+    out = np.zeros((m, 36), dtype=np.float32)
+    R.sprites_2d(sp.ctypes.data, m, 512, 256, out.ctypes.data_as(C.POINTER(C.c_float)), m, C.byref(t))
+    R.sprites_2d(sp.ctypes.data, m, 512, 256, out.ctypes.data_as(C.POINTER(C.c_float)), m, C.byref(t))
+    print(f"    reference SpriteBatch.cpp, one host core, {m} sprites: {t.value * 1e3:.2f} ms = {m / t.value / 1e6:.2f} M sprites/s")
+
+rng = np.random.default_rng(3)
+src = np.zeros((rows, cols, 2), dtype=np.float32)
+src[..., 0] = rng.integers(0, 8, (rows, cols)) * 32.0
+src[..., 1] = rng.integers(0, 4, (rows, cols)) * 32.0
+src[rng.random((rows, cols)) < 0.1] = -1.0
+ts = TileSet(ctx, 256, 128, 16.0, 16.0, rows, cols)
+ts.set_tiles(src)
+cells = int((src[..., 0] >= 0).sum())
+dst = torch.empty(cells * 36, dtype=torch.float32, device="cuda")
+color = (1.0, 1.0, 1.0, 0.8)
+frame = [0]
+
+
+def draw_tiles():
+    frame[0] += 1
+    ts.draw((0.25 * frame[0], -0.5 * frame[0], 0.0), color, device_dst=dst.data_ptr(), dst_quads=cells)
+
+
+d_ms, w_ms = timed(draw_tiles)
+print(f"  tile set, {cells} non-blank cells, table resident in HBM, ({cols} + {rows}) x 4 B uploaded per frame:\n"
+      f"    {d_ms:.3f} ms device, {w_ms:.3f} ms wall per frame = {cells / d_ms / 1e6:.2f} G tiles/s, "
+      f"{156 * cells / d_ms / 1e6:.0f} GB/s algorithmic ({156 * cells / d_ms / 1e6 / PEAK:.2f} of the measured HBM peak)")
+R = H.ref(fresh=True)
+r2, c2 = min(rows, 512), min(cols, 512)
+h = R.tileset_create(256, 128, 16.0, 16.0, r2, c2)
+for r in range(r2):
+    for c in range(c2):
+        if src[r, c, 0] >= 0:
+            R.tileset_set_tile_source(h, c, r, float(src[r, c, 0]), float(src[r, c, 1]))
+z3 = np.zeros(3, dtype=np.float32); col = np.ones(4, dtype=np.float32)
+fpp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+R.tileset_draw(h, fpp(z3), fpp(z3), fpp(col), 0.8, None, 0)
+t0 = time.perf_counter()
+for _ in range(3):
+    nq = R.tileset_draw(h, fpp(z3), fpp(z3), fpp(col), 0.8, None, 0)
+t = (time.perf_counter() - t0) / 3
+print(f"    reference TileSet.cpp, one host core, {r2} x {c2} grid ({nq} tiles): {t * 1e3:.2f} ms per frame = {nq / t / 1e6:.2f} M tiles/s")
+ctx.close()

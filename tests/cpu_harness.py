@@ -89,6 +89,9 @@ class CpuLib:
         proto("time_draw", C.c_double, [_vp, C.c_int])
         proto("time_frames", C.c_double, [_vp, C.c_float, C.c_int])
         if self.kind == "port":
+            proto("sprites_2d", C.c_uint32, [_vp, C.c_size_t, _P(C.c_float), C.c_size_t])
+            proto("tileset_draw", C.c_uint32, [_P(C.c_float), C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float,
+                                               _P(C.c_float), _P(C.c_float), _P(C.c_float), C.c_size_t])
             proto("device_rng_draw", C.c_int32, [C.c_uint64, C.c_uint64, C.c_uint32])
             proto("reset_statics", None, [])
             proto("set_rotation_mode", None, [C.c_int])
@@ -99,6 +102,11 @@ class CpuLib:
             proto("emitter_get_clip_vertices", C.c_uint32, [_vp, _P(C.c_float), _P(C.c_float), C.c_size_t])
             proto("emitter_bounds", C.c_int, [_vp, _P(C.c_float), _P(C.c_float)])
         else:
+            proto("sprites_2d", C.c_uint32, [_vp, C.c_size_t, C.c_uint32, C.c_uint32, _P(C.c_float), C.c_size_t, _P(C.c_double)])
+            proto("tileset_create", _vp, [C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_uint32, C.c_uint32])
+            proto("tileset_destroy", None, [_vp])
+            proto("tileset_set_tile_source", None, [_vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float])
+            proto("tileset_draw", C.c_uint32, [_vp, _P(C.c_float), _P(C.c_float), _P(C.c_float), C.c_float, _P(C.c_float), C.c_size_t])
             proto("emitter_create_from_file", _vp, [C.c_char_p])
             proto("emitter_clone", _vp, [_vp])
             proto("set_quiet", None, [C.c_int])
@@ -279,3 +287,33 @@ def ref(fresh=False):
         _ref = CpuLib(REF_SO, "t3dref_")
         _ref.set_quiet(1)
     return _ref
+
+
+# -- 2-D sprites and tile sets --
+def random_sprites(n, seed, clipped=True, rotated=True):
+    """n t3d_sprite2d records (numpy structured array) covering every overload: plain, centred, rotated (angle 0 and not,
+    zero and non-zero pivots), clipped (inside, straddling every edge, outside)."""
+    rng = np.random.default_rng(seed)
+    s = np.zeros(n, dtype=abi.SPRITE2D_DTYPE)
+    s["x"] = rng.uniform(-50, 800, n); s["y"] = rng.uniform(-50, 600, n); s["z"] = rng.uniform(0, 1, n)
+    s["width"] = rng.uniform(1, 120, n); s["height"] = rng.uniform(1, 90, n)
+    s["u1"] = rng.uniform(0, 0.5, n); s["u2"] = s["u1"] + rng.uniform(0.01, 0.5, n)
+    s["v1"] = rng.uniform(0.5, 1, n); s["v2"] = s["v1"] - rng.uniform(0.01, 0.5, n)
+    s["color"] = rng.uniform(0, 1, (n, 4))
+    kind = rng.integers(0, 6, n)
+    flags = np.zeros(n, dtype=np.uint32)
+    flags[kind == 1] = abi.SPRITE_CENTERED
+    if rotated:
+        flags[kind == 2] = abi.SPRITE_ROTATED
+        flags[kind == 3] = abi.SPRITE_ROTATED | abi.SPRITE_CENTERED
+        s["rotation_point"] = rng.uniform(0, 1, (n, 2))
+        s["rotation_point"][rng.random(n) < 0.2] = 0.0            # pivot (0, 0) with the sprite at the origin: Vector2::rotate's other branch
+        at_origin = rng.random(n) < 0.1
+        s["x"][at_origin] = 0; s["y"][at_origin] = 0
+        s["rotation_angle"] = np.where(rng.random(n) < 0.3, 0.0, rng.uniform(-7, 7, n))
+    if clipped:
+        flags[kind >= 4] = abi.SPRITE_CLIPPED
+        s["clip"][:, 0] = rng.uniform(0, 300, n); s["clip"][:, 1] = rng.uniform(0, 200, n)
+        s["clip"][:, 2] = rng.uniform(50, 400, n); s["clip"][:, 3] = rng.uniform(50, 300, n)
+    s["flags"] = flags
+    return s

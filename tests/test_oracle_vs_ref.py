@@ -3,6 +3,7 @@
 vertex stream after every frame.  Needs /root/reference at build time, so these tests skip where the
 reference library was never built; tests/test_golden.py covers the same ground from committed vectors.
 """
+import ctypes as C
 import numpy as np
 import pytest
 
@@ -229,3 +230,52 @@ def test_sprite_tex_coord_tables():
     rects = np.array([[0, 0, 10, 20], [13, 7, 100, 50.5]], dtype=np.float32)
     eo.set_sprite_frame_rects(rects); er.set_sprite_frame_rects(rects)
     assert np.array_equal(eo.sprite_tex_coords(), er.sprite_tex_coords())
+
+
+# ---- the 2-D SpriteBatch overloads and TileSet::draw ------------------------------------------------
+def test_sprites_2d_every_overload_matches_the_reference():
+    # One SpriteBatch::draw call per record through the reference's own SpriteBatch.cpp (plain, centred, rotated about
+    # zero and non-zero pivots, clipped and culled), against the plain-C restatement: bit for bit, including the quads
+    # the clip rectangle drops.
+    O, R = H.oracle(fresh=True), H.ref(fresh=True)
+    for n, seed in ((1, 1), (257, 2), (20000, 3)):
+        sp = H.random_sprites(n, seed)
+        want = np.zeros((n, 36), dtype=np.float32)
+        got = np.zeros((n, 36), dtype=np.float32)
+        nr = R.sprites_2d(sp.ctypes.data, n, 512, 256, want.ctypes.data_as(C.POINTER(C.c_float)), n, None)
+        no = O.sprites_2d(sp.ctypes.data, n, got.ctypes.data_as(C.POINTER(C.c_float)), n)
+        assert no == nr and (n < 100 or 0 < nr < n)          # some sprites lie outside their clip rectangle
+        assert np.array_equal(got[:no].view(np.uint32), want[:nr].view(np.uint32))
+
+
+def test_tileset_draw_matches_the_reference():
+    # TileSet::draw (TileSet.cpp:179-236) on a grid with blank cells, node and camera away from the origin, tile sizes
+    # that do not add up exactly in binary (the row / column positions are running float sums).
+    O, R = H.oracle(fresh=True), H.ref(fresh=True)
+    rng = np.random.default_rng(5)
+    for rows, cols, tw, th in ((1, 1, 16.0, 16.0), (7, 13, 0.1, 0.3), (64, 96, 33.3, 17.7)):
+        src = np.zeros((rows, cols, 2), dtype=np.float32)
+        src[..., 0] = rng.integers(0, 8, (rows, cols)) * 32.0
+        src[..., 1] = rng.integers(0, 4, (rows, cols)) * 32.0
+        src[rng.random((rows, cols)) < 0.3] = -1.0            # blank cells (TileSet.cpp:217)
+        h = R.tileset_create(256, 128, tw, th, rows, cols)
+        for r in range(rows):
+            for c in range(cols):
+                if src[r, c, 0] >= 0:
+                    R.tileset_set_tile_source(h, c, r, float(src[r, c, 0]), float(src[r, c, 1]))
+        node = np.array([12.25, -3.5, 0.75], dtype=np.float32)
+        cam = np.array([100.1, 50.7, 9.0], dtype=np.float32)
+        color = np.array([0.9, 0.8, 0.7, 0.6], dtype=np.float32)
+        opacity = np.float32(0.35)
+        n_cells = rows * cols
+        want = np.zeros((n_cells, 36), dtype=np.float32)
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        nr = R.tileset_draw(h, fp(node), fp(cam), fp(color), opacity, fp(want), n_cells)
+        R.tileset_destroy(h)
+        # what TileSet::draw has made of the two translations by line 205, and of colour and opacity at line 226
+        pos = np.array([np.float32(0) - cam[0] + node[0], np.float32(0) - cam[1] + node[1], np.float32(0) + node[2]], dtype=np.float32)
+        col = color.copy(); col[3] = color[3] * opacity
+        got = np.zeros((n_cells, 36), dtype=np.float32)
+        no = O.tileset_draw(fp(src), rows, cols, tw, th, 256.0, 128.0, fp(pos), fp(col), fp(got), n_cells)
+        assert no == nr == int((src[..., 0] >= 0).sum())
+        assert np.array_equal(got[:no].view(np.uint32), want[:nr].view(np.uint32))

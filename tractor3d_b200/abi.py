@@ -115,6 +115,18 @@ def default_params(**overrides):
     return EmitterParams.from_dict(d)
 
 
+class Sprite2D(C.Structure):
+    """t3d_sprite2d: one SpriteBatch::draw 2-D call (include/t3d_particles.h)."""
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float), ("width", C.c_float), ("height", C.c_float),
+                ("u1", C.c_float), ("v1", C.c_float), ("u2", C.c_float), ("v2", C.c_float), ("color", C.c_float * 4),
+                ("rotation_point", C.c_float * 2), ("rotation_angle", C.c_float), ("flags", C.c_uint32), ("clip", C.c_float * 4)]
+
+
+SPRITE_ROTATED, SPRITE_CENTERED, SPRITE_CLIPPED = 1, 2, 4
+# numpy view of an array of t3d_sprite2d (21 words each)
+SPRITE2D_DTYPE = [("x", "f4"), ("y", "f4"), ("z", "f4"), ("width", "f4"), ("height", "f4"), ("u1", "f4"), ("v1", "f4"), ("u2", "f4"),
+                  ("v2", "f4"), ("color", "f4", 4), ("rotation_point", "f4", 2), ("rotation_angle", "f4"), ("flags", "u4"), ("clip", "f4", 4)]
+
 _P = C.POINTER
 _vp = C.c_void_p
 
@@ -182,6 +194,13 @@ PROTOTYPES = {
     "t3d_emitter_download_vertices": (C.c_int, [_vp, _P(C.c_float), C.c_size_t, _P(C.c_uint32)]),
     "t3d_emitter_download_state": (C.c_int, [_vp, _P(C.c_uint32), C.c_size_t, _P(C.c_uint32)]),
     "t3d_emitter_upload_state": (C.c_int, [_vp, _P(C.c_uint32), C.c_size_t, C.c_uint32]),
+    "t3d_ctx_draw_sprites": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, _vp, C.c_size_t, _P(_vp), _P(C.c_uint32)]),
+    "t3d_tileset_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_uint32, C.c_uint32, _P(_vp)]),
+    "t3d_tileset_destroy": (C.c_int, [_vp]),
+    "t3d_tileset_set_tile_source": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float]),
+    "t3d_tileset_set_tiles": (C.c_int, [_vp, _P(C.c_float)]),
+    "t3d_tileset_draw": (C.c_int, [_vp, _P(C.c_float), _P(C.c_float), _vp, C.c_size_t, _P(_vp), _P(C.c_uint32)]),
+    "t3d_ctx_download_quads": (C.c_int, [_vp, _vp, C.c_uint32, _P(C.c_float)]),
     "t3d_device_rng_draw": (C.c_int32, [C.c_uint64, C.c_uint64, C.c_uint32]),
     "t3d_host_fuse_policy": (C.c_int, [C.c_uint64, C.c_uint64]),
     "t3d_host_rate_cap": (C.c_int, [_P(C.c_double), C.c_float, _P(C.c_float)]),

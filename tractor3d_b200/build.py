@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libt3d_particles.so")
-SOURCES = ["t3d_kernels.cu", "t3d_update.cu", "t3d_runtime.cu", "t3d_host.cpp"]
+SOURCES = ["t3d_kernels.cu", "t3d_update.cu", "t3d_sprites.cu", "t3d_runtime.cu", "t3d_host.cpp"]
 HEADERS = ["t3d_internal.h", "t3d_device.cuh", "t3d_host.h", os.path.join("..", "..", "include", "t3d_particles.h")]
 
 NVCC_FLAGS = [
@@ -135,7 +135,7 @@ def build_engine_callers():
     shim = ["-DT3D_WITH_ENGINE_HEADERS", "-I" + os.path.join(HERE, "host", "engine")]
     run(cxx + shim + overlay + ["-c", caller, "-o", os.path.join(tmp_b200, "caller.o")])
     run(cxx + shim + overlay + ["-c", os.path.join(HERE, "host", "ParticleEmitter.cpp"), "-o", os.path.join(tmp_b200, "facade.o")])
-    engine_objs = [o for o in objs if os.path.basename(o) not in ("ParticleEmitter.o", "SpriteBatch.o")]
+    engine_objs = [o for o in objs if os.path.basename(o) not in ("ParticleEmitter.o", "SpriteBatch.o", "TileSet.o")]
     run(["g++", "-o", out_b200, os.path.join(tmp_b200, "caller.o"), os.path.join(tmp_b200, "facade.o"), os.path.join(tmp_ref, "support.o")]
         + engine_objs + ["-L" + CSRC, "-lt3d_particles", "-Wl,-rpath,$ORIGIN/../../csrc"])
     return out_ref, out_b200

@@ -220,6 +220,14 @@ void launch_triangle_indices(void* stream, uint32_t* out, uint64_t n_indices);
 void launch_export_state(void* stream, const Storage& st, uint32_t n, uint32_t* out, uint32_t host_stride);
 void launch_import_state(void* stream, const Storage& st, uint32_t n, const uint32_t* in, uint32_t host_stride);
 
+// ---- 2-D sprites and tile sets (t3d_sprites.cu) ----
+uint32_t sprite_tiles(uint32_t n); // CTAs (tiles of 256 sprites) a list of n sprites takes
+// tile_scratch: sprite_tiles(n) + 1 words when some sprite may be culled by its clip rectangle (ordered compaction; the
+// last word receives the number of quads written), nullptr when sprite i simply becomes quad i.
+void launch_sprites(void* stream, const t3d_sprite2d* sprites, uint32_t n, uint32_t* tile_scratch, float* dst);
+void launch_tileset(void* stream, const uint32_t* cells, uint32_t n_quads, const float* tiles_xy, uint32_t cols, const float* xs,
+                    const float* ys, float z, float tile_w, float tile_h, float wr, float hr, const float color[4], float* dst);
+
 // The counter-based generator of T3D_RNG_DEVICE (host + device): 32-bit integer hash of (seed, particle serial,
 // draw index).  key = the part that is constant per particle; one draw = key + (j+1)*C through the lowbias32
 // finaliser (two multiplies, three xor-shifts), top 31 bits.  Cheap on purpose: a particle consumes ~30 draws and

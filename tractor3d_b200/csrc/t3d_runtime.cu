@@ -218,6 +218,25 @@ struct t3d_ctx
     std::vector<cudaEvent_t> download_done; // ticket t (1-based) -> download_done[t - 1]
     uint64_t download_waited{ 0 };          // every ticket <= this has been waited for
 
+    // 2-D sprites (t3d_ctx_draw_sprites, t3d_tileset_draw): two pinned/device buffer pairs for lists that arrive from the
+    // host (the copy of list k + 1 is filled while list k is still in flight), the context-owned vertex buffer, the
+    // per-tile scratch of the ordered compaction
+    struct SpriteStage
+    {
+        char* host{ nullptr };
+        char* dev{ nullptr };
+        size_t cap{ 0 };
+        cudaEvent_t done{ nullptr };
+        bool in_flight{ false };
+    };
+    SpriteStage sprite_stage[2];
+    int sprite_stage_next{ 0 };
+    float* sprite_vtx{ nullptr };
+    size_t sprite_vtx_quads{ 0 };
+    uint32_t* sprite_scratch{ nullptr };
+    size_t sprite_scratch_words{ 0 };
+    std::vector<struct t3d_tileset*> tilesets;
+
     uint32_t* readback_host{ nullptr }; // pinned scratch for counts
     size_t readback_cap{ 0 };
     uint32_t* readback_dev{ nullptr };
@@ -1502,6 +1521,18 @@ int t3d_ctx_destroy(t3d_ctx* c)
     if (c->readback_dev) cudaFree(c->readback_dev);
     if (c->strip_indices) cudaFree(c->strip_indices);
     if (c->tri_indices) cudaFree(c->tri_indices);
+    {
+        std::vector<t3d_tileset*> ts = c->tilesets;
+        for (t3d_tileset* t : ts) t3d_tileset_destroy(t);
+    }
+    for (t3d_ctx::SpriteStage& st : c->sprite_stage)
+    {
+        if (st.host) cudaFreeHost(st.host);
+        if (st.dev) cudaFree(st.dev);
+        if (st.done) cudaEventDestroy(st.done);
+    }
+    if (c->sprite_vtx) cudaFree(c->sprite_vtx);
+    if (c->sprite_scratch) cudaFree(c->sprite_scratch);
     for (t3d_ctx::Feedback& fb : c->feedback)
     {
         if (fb.host) cudaFreeHost(fb.host);
@@ -2384,6 +2415,279 @@ int t3d_emitter_upload_state(t3d_emitter* e, const uint32_t* in, size_t stride, 
     // Uploaded particles may carry any rotation state.
     e->may_rotate = e->may_spin = true;
     e->const_dirty = true;
+    return T3D_OK;
+}
+
+// --------------------------------------------------------------------------------------------------
+// 2-D sprites and tile sets
+// --------------------------------------------------------------------------------------------------
+} // extern "C"
+
+struct t3d_tileset
+{
+    t3d_ctx* ctx{ nullptr };
+    uint32_t rows{ 0 }, cols{ 0 };
+    float tile_w{ 0 }, tile_h{ 0 }, tex_w_ratio{ 0 }, tex_h_ratio{ 0 };
+    std::vector<float> tiles;      // rows * cols * {x, y}; negative = blank (TileSet.cpp:41-42 fills the table with -1)
+    float* tiles_dev{ nullptr };
+    uint32_t* cells_dev{ nullptr }; // indices of the non-blank cells, row-major
+    uint32_t n_quads{ 0 };
+    bool dirty{ true };
+};
+
+// Where a list's quads go: the caller's buffer, or the context's own (grown on demand).
+static int sprite_destination(t3d_ctx* c, size_t quads, void* device_dst, size_t dst_quads, float** out)
+{
+    if (device_dst)
+    {
+        if (reinterpret_cast<uintptr_t>(device_dst) & 15u) return fail(T3D_ERR_INVALID, "the destination must be 16-byte aligned");
+        if (quads > dst_quads) return fail(T3D_ERR_CAPACITY, "the destination holds %zu quads, the list may write %zu", dst_quads, quads);
+        *out = static_cast<float*>(device_dst);
+        return T3D_OK;
+    }
+    if (c->sprite_vtx_quads < quads)
+    {
+        if (c->sprite_vtx)
+        {
+            T3D_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(c->sprite_vtx);
+            c->sprite_vtx = nullptr;
+        }
+        const size_t cap = std::max<size_t>(quads + quads / 2, 4096);
+        T3D_CUDA(cudaMalloc((void**)&c->sprite_vtx, cap * T3D_FLOATS_PER_QUAD * sizeof(float)));
+        c->sprite_vtx_quads = cap;
+    }
+    *out = c->sprite_vtx;
+    return T3D_OK;
+}
+
+extern "C" {
+
+int t3d_ctx_draw_sprites(t3d_ctx* c, const t3d_sprite2d* sprites, size_t n, int sprites_on_device, void* device_dst, size_t dst_quads,
+                         const t3d_sprite_vertex** device_ptr, uint32_t* n_quads)
+{
+    if (!c || (!sprites && n)) return fail(T3D_ERR_INVALID, "t3d_ctx_draw_sprites: null argument");
+    if (n > 0xfffffff0u) return fail(T3D_ERR_INVALID, "t3d_ctx_draw_sprites: too many sprites");
+    T3D_TRY(use_device(c));
+    float* dst = nullptr;
+    T3D_TRY(sprite_destination(c, n, device_dst, dst_quads, &dst));
+    if (device_ptr) *device_ptr = reinterpret_cast<const t3d_sprite_vertex*>(dst);
+    if (n_quads) *n_quads = 0;
+    if (n == 0) return T3D_OK;
+    const t3d_sprite2d* dev_list = sprites;
+    bool may_cull = true; // a device-resident list is not inspected here
+    t3d_ctx::SpriteStage* stage = nullptr;
+    if (!sprites_on_device)
+    {
+        stage = &c->sprite_stage[c->sprite_stage_next];
+        c->sprite_stage_next ^= 1;
+        if (stage->in_flight)
+        {
+            HostTimer ht(c, T3D_HOST_WAIT);
+            T3D_CUDA(cudaEventSynchronize(stage->done));
+            stage->in_flight = false;
+        }
+        const size_t bytes = n * sizeof(t3d_sprite2d);
+        if (stage->cap < bytes)
+        {
+            if (stage->host) cudaFreeHost(stage->host);
+            if (stage->dev) cudaFree(stage->dev);
+            stage->host = stage->dev = nullptr;
+            const size_t cap = std::max<size_t>(bytes + bytes / 2, 1 << 16);
+            T3D_CUDA(cudaMallocHost((void**)&stage->host, cap));
+            T3D_CUDA(cudaMalloc((void**)&stage->dev, cap));
+            stage->cap = cap;
+        }
+        if (!stage->done) T3D_CUDA(cudaEventCreateWithFlags(&stage->done, cudaEventDisableTiming));
+        {
+            HostTimer ht(c, T3D_HOST_BUILD);
+            memcpy(stage->host, sprites, bytes);
+            may_cull = false;
+            for (size_t i = 0; i < n && !may_cull; ++i) may_cull = (sprites[i].flags & T3D_SPRITE_CLIPPED) != 0;
+        }
+        T3D_CUDA(cudaMemcpyAsync(stage->dev, stage->host, bytes, cudaMemcpyHostToDevice, c->stream));
+        c->h2d_bytes += bytes;
+        dev_list = reinterpret_cast<const t3d_sprite2d*>(stage->dev);
+    }
+    else if (reinterpret_cast<uintptr_t>(sprites) & 15u)
+        return fail(T3D_ERR_INVALID, "t3d_ctx_draw_sprites: a device-resident list must be 16-byte aligned");
+    uint32_t* scratch = nullptr;
+    const uint32_t tiles = sprite_tiles((uint32_t)n);
+    if (may_cull)
+    {
+        if (c->sprite_scratch_words < (size_t)tiles + 1)
+        {
+            if (c->sprite_scratch)
+            {
+                T3D_CUDA(cudaStreamSynchronize(c->stream));
+                cudaFree(c->sprite_scratch);
+            }
+            const size_t cap = std::max<size_t>((size_t)tiles * 2 + 1, 1024);
+            T3D_CUDA(cudaMalloc((void**)&c->sprite_scratch, cap * sizeof(uint32_t)));
+            c->sprite_scratch_words = cap;
+        }
+        scratch = c->sprite_scratch;
+    }
+    launch_sprites(c->stream, dev_list, (uint32_t)n, scratch, dst);
+    T3D_CUDA(cudaGetLastError());
+    c->launches += scratch ? 3 : 1;
+    if (stage)
+    {
+        T3D_CUDA(cudaEventRecord(stage->done, c->stream));
+        stage->in_flight = true;
+    }
+    if (n_quads)
+    {
+        if (!scratch)
+            *n_quads = (uint32_t)n;
+        else
+        {
+            // culling is decided on the device: the quad count has to come back
+            uint32_t total = 0;
+            T3D_CUDA(cudaMemcpyAsync(&total, scratch + tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            {
+                HostTimer ht(c, T3D_HOST_WAIT);
+                T3D_CUDA(cudaStreamSynchronize(c->stream));
+            }
+            c->d2h_bytes += sizeof(uint32_t);
+            *n_quads = total;
+        }
+    }
+    return T3D_OK;
+}
+
+int t3d_tileset_create(t3d_ctx* c, uint32_t texture_width, uint32_t texture_height, float tile_width, float tile_height, uint32_t row_count,
+                       uint32_t column_count, t3d_tileset** out)
+{
+    if (!c || !out) return fail(T3D_ERR_INVALID, "t3d_tileset_create: null argument");
+    *out = nullptr;
+    if (!texture_width || !texture_height) return fail(T3D_ERR_INVALID, "the texture must have a size");
+    if (!(tile_width > 0) || !(tile_height > 0)) return fail(T3D_ERR_INVALID, "tile width and height must be positive (TileSet.cpp:36)");
+    if (!row_count || !column_count) return fail(T3D_ERR_INVALID, "row and column counts must be positive (TileSet.cpp:37)");
+    if ((uint64_t)row_count * column_count > 0x7fffffffull) return fail(T3D_ERR_INVALID, "too many cells");
+    T3D_TRY(use_device(c));
+    t3d_tileset* t = new t3d_tileset();
+    t->ctx = c;
+    t->rows = row_count;
+    t->cols = column_count;
+    t->tile_w = tile_width;
+    t->tile_h = tile_height;
+    t->tex_w_ratio = 1.0f / (float)texture_width;   // SB.cpp:155-156
+    t->tex_h_ratio = 1.0f / (float)texture_height;
+    t->tiles.assign((size_t)row_count * column_count * 2, -1.0f);
+    const size_t cells = (size_t)row_count * column_count;
+    if (cudaMalloc((void**)&t->tiles_dev, cells * 2 * sizeof(float)) != cudaSuccess ||
+        cudaMalloc((void**)&t->cells_dev, cells * sizeof(uint32_t)) != cudaSuccess)
+    {
+        if (t->tiles_dev) cudaFree(t->tiles_dev);
+        delete t;
+        return fail(T3D_ERR_CUDA, "t3d_tileset_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    c->tilesets.push_back(t);
+    *out = t;
+    return T3D_OK;
+}
+
+int t3d_tileset_destroy(t3d_tileset* t)
+{
+    if (!t) return T3D_OK;
+    t3d_ctx* c = t->ctx;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(t->tiles_dev);
+    cudaFree(t->cells_dev);
+    c->tilesets.erase(std::remove(c->tilesets.begin(), c->tilesets.end(), t), c->tilesets.end());
+    delete t;
+    return T3D_OK;
+}
+
+int t3d_tileset_set_tile_source(t3d_tileset* t, uint32_t column, uint32_t row, float x, float y)
+{
+    if (!t || column >= t->cols || row >= t->rows) return fail(T3D_ERR_INVALID, "setTileSource: cell out of range (TileSet.cpp:157-158)");
+    float* cell = &t->tiles[2 * ((size_t)row * t->cols + column)];
+    cell[0] = x;
+    cell[1] = y;
+    t->dirty = true;
+    return T3D_OK;
+}
+
+int t3d_tileset_set_tiles(t3d_tileset* t, const float* sources)
+{
+    if (!t || !sources) return fail(T3D_ERR_INVALID, "null argument");
+    memcpy(t->tiles.data(), sources, t->tiles.size() * sizeof(float));
+    t->dirty = true;
+    return T3D_OK;
+}
+
+int t3d_tileset_draw(t3d_tileset* t, const float position[3], const float color[4], void* device_dst, size_t dst_quads,
+                     const t3d_sprite_vertex** device_ptr, uint32_t* n_quads)
+{
+    if (!t || !position || !color) return fail(T3D_ERR_INVALID, "t3d_tileset_draw: null argument");
+    t3d_ctx* c = t->ctx;
+    T3D_TRY(use_device(c));
+    const size_t cells = (size_t)t->rows * t->cols;
+    if (t->dirty)
+    {
+        // the table changed: upload it and the list of non-blank cells (TileSet.cpp:217) in draw order
+        std::vector<uint32_t> live;
+        live.reserve(cells);
+        for (size_t k = 0; k < cells; ++k)
+            if (t->tiles[2 * k] >= 0 && t->tiles[2 * k + 1] >= 0) live.push_back((uint32_t)k);
+        T3D_CUDA(cudaStreamSynchronize(c->stream)); // (a draw in flight may still read the old table)
+        T3D_CUDA(cudaMemcpy(t->tiles_dev, t->tiles.data(), cells * 2 * sizeof(float), cudaMemcpyHostToDevice));
+        if (!live.empty()) T3D_CUDA(cudaMemcpy(t->cells_dev, live.data(), live.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        c->h2d_bytes += cells * 2 * sizeof(float) + live.size() * sizeof(uint32_t);
+        t->n_quads = (uint32_t)live.size();
+        t->dirty = false;
+    }
+    float* dst = nullptr;
+    T3D_TRY(sprite_destination(c, t->n_quads, device_dst, dst_quads, &dst));
+    if (device_ptr) *device_ptr = reinterpret_cast<const t3d_sprite_vertex*>(dst);
+    if (n_quads) *n_quads = t->n_quads;
+    if (!t->n_quads) return T3D_OK;
+    // TileSet.cpp:207-235: the loop's running position -- sequential float additions, one per column and per row -- is the
+    // only per-frame input: cols + rows floats
+    StagingSlot* slot;
+    const size_t bytes = ((size_t)t->cols + t->rows) * sizeof(float);
+    T3D_TRY(staging_acquire(c, bytes, &slot));
+    {
+        HostTimer ht(c, T3D_HOST_BUILD);
+        float* xs = reinterpret_cast<float*>(slot->host);
+        float* ys = xs + t->cols;
+        float x = position[0];
+        for (uint32_t col = 0; col < t->cols; ++col)
+        {
+            xs[col] = x;
+            x += t->tile_w; // :231
+        }
+        float y = position[1];
+        y += t->tile_h * (float)(t->rows - 1); // :208
+        for (uint32_t row = 0; row < t->rows; ++row)
+        {
+            ys[row] = y;
+            y -= t->tile_h; // :234
+        }
+    }
+    T3D_TRY(staging_submit(c, slot, bytes));
+    const float* xs_dev = reinterpret_cast<const float*>(slot->dev);
+    launch_tileset(c->stream, t->cells_dev, t->n_quads, t->tiles_dev, t->cols, xs_dev, xs_dev + t->cols, position[2], t->tile_w, t->tile_h,
+                   t->tex_w_ratio, t->tex_h_ratio, color, dst);
+    T3D_CUDA(cudaGetLastError());
+    c->launches++;
+    T3D_TRY(staging_release(c, slot));
+    return T3D_OK;
+}
+
+int t3d_ctx_download_quads(t3d_ctx* c, const t3d_sprite_vertex* device_ptr, uint32_t n_quads, float* out)
+{
+    if (!c || (!device_ptr && n_quads) || (!out && n_quads)) return fail(T3D_ERR_INVALID, "null argument");
+    T3D_TRY(flush(c));
+    T3D_TRY(use_device(c));
+    if (!n_quads) return T3D_OK;
+    const size_t bytes = (size_t)n_quads * T3D_FLOATS_PER_QUAD * sizeof(float);
+    T3D_CUDA(cudaMemcpyAsync(out, device_ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    T3D_CUDA(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += bytes;
     return T3D_OK;
 }
 

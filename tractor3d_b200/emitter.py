@@ -119,6 +119,25 @@ class Context:
         _check(self.lib, self.lib.t3d_ctx_launch_count(self.h, C.byref(n)))
         return n.value
 
+    def draw_sprites(self, sprites, device_dst=None, dst_quads=0, on_device=False, n=None, want_count=True):
+        """One SpriteBatch::draw 2-D call per record (numpy array of abi.SPRITE2D_DTYPE, or a device pointer with
+        on_device=True and n).  Returns (device pointer of the quads, quads written or None)."""
+        if on_device:
+            src, count = C.c_void_p(sprites), n
+        else:
+            a = np.ascontiguousarray(sprites)
+            assert a.dtype.itemsize == C.sizeof(abi.Sprite2D)
+            src, count = C.c_void_p(a.ctypes.data), a.size
+        ptr, nq = C.c_void_p(), C.c_uint32()
+        _check(self.lib, self.lib.t3d_ctx_draw_sprites(self.h, src, count, int(on_device), C.c_void_p(device_dst) if device_dst else None,
+                                                       dst_quads, C.byref(ptr), C.byref(nq) if want_count else None))
+        return ptr.value, (nq.value if want_count else None)
+
+    def download_quads(self, device_ptr, n_quads):
+        out = np.zeros((n_quads, 4, 9), dtype=np.float32)
+        _check(self.lib, self.lib.t3d_ctx_download_quads(self.h, C.c_void_p(device_ptr), n_quads, _fptr(out.reshape(-1)) if n_quads else None))
+        return out
+
     def host_profile(self):
         """Seconds the library has spent on the host: {enqueue, build, submit, wait} (t3d_ctx_host_profile)."""
         out = (C.c_double * 4)()
@@ -162,6 +181,39 @@ class Context:
         out = np.zeros(len(h), dtype=np.uint32)
         _check(self.lib, self.lib.t3d_batch_get_counts(h, len(h), out.ctypes.data_as(_P(C.c_uint32))))
         return out
+
+
+class TileSet:
+    """tractor::TileSet's draw path (include/graphics/TileSet.h) with the tile table resident on the device."""
+
+    def __init__(self, ctx, texture_width, texture_height, tile_width, tile_height, row_count, column_count):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.rows, self.cols = row_count, column_count
+        self.h = C.c_void_p()
+        _check(self.lib, self.lib.t3d_tileset_create(ctx.h, texture_width, texture_height, tile_width, tile_height, row_count, column_count,
+                                                     C.byref(self.h)))
+
+    def setTileSource(self, column, row, source):
+        _check(self.lib, self.lib.t3d_tileset_set_tile_source(self.h, column, row, source[0], source[1]))
+
+    def set_tiles(self, sources):
+        a = np.ascontiguousarray(sources, dtype=np.float32).reshape(-1)
+        assert a.size == self.rows * self.cols * 2
+        _check(self.lib, self.lib.t3d_tileset_set_tiles(self.h, _fptr(a)))
+
+    def draw(self, position, color, device_dst=None, dst_quads=0):
+        """Returns (device pointer, quads).  position / color as TileSet::draw has them by TileSet.cpp:205 / :226."""
+        p = np.ascontiguousarray(position, dtype=np.float32)
+        c = np.ascontiguousarray(color, dtype=np.float32)
+        ptr, n = C.c_void_p(), C.c_uint32()
+        _check(self.lib, self.lib.t3d_tileset_draw(self.h, _fptr(p), _fptr(c), C.c_void_p(device_dst) if device_dst else None, dst_quads,
+                                                   C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def release(self):
+        if self.h:
+            self.lib.t3d_tileset_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 class ParticleEmitter:
