@@ -310,12 +310,23 @@ typedef struct t3d_sprite2d {
     uint32_t flags;
     float clip[4];                  /* T3D_SPRITE_CLIPPED: x, y, width, height */
 } t3d_sprite2d;
-/* Expands n sprites.  `sprites` is host memory (copied in through pinned staging) or, with sprites_on_device, a device
- * array the caller keeps resident.  Quads go to device_dst (16-byte aligned, dst_quads quads; T3D_ERR_CAPACITY if n does
- * not fit) or, when it is NULL, to a buffer the context owns; *device_ptr receives where.  *n_quads (may be NULL) receives
- * the number of quads written, which waits for the device when some sprite is clipped; without clipping it is n. */
-int t3d_ctx_draw_sprites(t3d_ctx* ctx, const t3d_sprite2d* sprites, size_t n, int sprites_on_device, void* device_dst,
+/* how the list arrives */
+enum {
+    T3D_SPRITES_ON_DEVICE = 1, /* `sprites` is a device array the caller keeps resident (16-byte aligned) */
+    T3D_SPRITES_NO_CLIP = 2    /* the caller promises that no sprite carries T3D_SPRITE_CLIPPED: sprite i becomes quad i, one
+                                  launch, and the list is not scanned for the flag */
+};
+/* Expands n sprites.  `sprites` is host memory -- copied through pinned staging, or, when it is the buffer
+ * t3d_ctx_map_sprites handed out, used where it lies -- or a device array (T3D_SPRITES_ON_DEVICE).  Quads go to device_dst
+ * (16-byte aligned, dst_quads quads; T3D_ERR_CAPACITY if n does not fit) or, when it is NULL, to a buffer the context
+ * owns; *device_ptr receives where.  *n_quads (may be NULL) receives the number of quads written, which waits for the
+ * device when some sprite may be clipped; otherwise it is n. */
+int t3d_ctx_draw_sprites(t3d_ctx* ctx, const t3d_sprite2d* sprites, size_t n, int list_flags, void* device_dst,
                          size_t dst_quads, const t3d_sprite_vertex** device_ptr, uint32_t* n_quads);
+/* Pinned host memory for the next list of up to n sprites: a producer (text layout, UI, a tile walk) writes its records
+ * straight into it and passes the same pointer to t3d_ctx_draw_sprites, which then uploads without a copy of its own.
+ * Two such buffers alternate, so list k + 1 can be written while list k is still on its way to the device. */
+int t3d_ctx_map_sprites(t3d_ctx* ctx, size_t n, t3d_sprite2d** host_list);
 
 /* TileSet (include/graphics/TileSet.h): a grid of equally sized tiles cut from one texture; blank cells are skipped.  The
  * tile table lives on the device, so a frame uploads nothing but its position. */

@@ -34,8 +34,10 @@ struct Record
     t3d_emitter_params p;
     uint32_t frame_count;
     int32_t sprite_w, sprite_h;
+    int32_t pad;
     uint64_t seed;
 };
+static_assert(sizeof(Record) == sizeof(t3d_emitter_params) + 24, "the layout tests/test_gpu_multi_context.py writes");
 
 struct Result
 {

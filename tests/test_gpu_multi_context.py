@@ -29,9 +29,10 @@ def _records(tmp_path):
             p.rotation_per_particle_speed_min, p.rotation_per_particle_speed_max = 0.5, 2.5
         seed = 9000 + e
         recs.append((p, sprite, seed))
-        raw += bytes(p) + np.array([sprite[0]], dtype=np.uint32).tobytes() + np.array(sprite[1:], dtype=np.int32).tobytes()
+        # struct Record of multi_ctx_driver.cpp: params, uint32, int32, int32, 4 bytes of padding, uint64
+        raw += bytes(p) + np.array([sprite[0]], dtype=np.uint32).tobytes() + np.array(sprite[1:] + (0,), dtype=np.int32).tobytes()
         raw += np.array([seed], dtype=np.uint64).tobytes()
-    assert len(raw) == K * (C.sizeof(abi.EmitterParams) + 20)
+    assert len(raw) == K * (C.sizeof(abi.EmitterParams) + 24)
     f = tmp_path / "params.bin"
     f.write_bytes(raw)
     return recs, str(f)

@@ -60,6 +60,27 @@ def test_sprite_lists_expand_like_spritebatch(n):
         ctx.close()
 
 
+def test_sprites_written_straight_into_the_mapped_staging_buffer():
+    # t3d_ctx_map_sprites: the producer fills pinned memory, the library uploads from where the list lies; two buffers
+    # alternate, so consecutive lists do not wait for each other
+    O = H.oracle(fresh=True)
+    ctx = Context(0)
+    try:
+        for k in range(5):
+            n = 10_000 + 1000 * k
+            sp = H.random_sprites(n, seed=300 + k, rotated=False, clipped=(k % 2 == 1))
+            mapped = ctx.map_sprites(n)
+            mapped[:] = sp
+            h2d0 = ctx.transfer_bytes()[0]
+            ptr, nq = ctx.draw_sprites(mapped, no_clip=(k % 2 == 0))
+            assert ctx.transfer_bytes()[0] - h2d0 == n * 84
+            want = _oracle_sprites(O, sp)
+            assert nq == want.shape[0]
+            assert np.array_equal(ctx.download_quads(ptr, nq).view(np.uint32), want.view(np.uint32)), k
+    finally:
+        ctx.close()
+
+
 def test_sprite_list_resident_on_the_device_into_a_foreign_buffer():
     import torch
     O = H.oracle(fresh=True)

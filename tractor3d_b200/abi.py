@@ -123,6 +123,7 @@ class Sprite2D(C.Structure):
 
 
 SPRITE_ROTATED, SPRITE_CENTERED, SPRITE_CLIPPED = 1, 2, 4
+SPRITES_ON_DEVICE, SPRITES_NO_CLIP = 1, 2
 # numpy view of an array of t3d_sprite2d (21 words each)
 SPRITE2D_DTYPE = [("x", "f4"), ("y", "f4"), ("z", "f4"), ("width", "f4"), ("height", "f4"), ("u1", "f4"), ("v1", "f4"), ("u2", "f4"),
                   ("v2", "f4"), ("color", "f4", 4), ("rotation_point", "f4", 2), ("rotation_angle", "f4"), ("flags", "u4"), ("clip", "f4", 4)]
@@ -195,6 +196,7 @@ PROTOTYPES = {
     "t3d_emitter_download_state": (C.c_int, [_vp, _P(C.c_uint32), C.c_size_t, _P(C.c_uint32)]),
     "t3d_emitter_upload_state": (C.c_int, [_vp, _P(C.c_uint32), C.c_size_t, C.c_uint32]),
     "t3d_ctx_draw_sprites": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, _vp, C.c_size_t, _P(_vp), _P(C.c_uint32)]),
+    "t3d_ctx_map_sprites": (C.c_int, [_vp, C.c_size_t, _P(_vp)]),
     "t3d_tileset_create": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_uint32, C.c_uint32, _P(_vp)]),
     "t3d_tileset_destroy": (C.c_int, [_vp]),
     "t3d_tileset_set_tile_source": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float]),

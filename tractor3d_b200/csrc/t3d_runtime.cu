@@ -843,8 +843,29 @@ static int choose_shape(const t3d_ctx* c, const std::vector<PendingOp>& ops, uin
 }
 
 // Cuts the update descriptors (and the count queries of the feedback) of `ops`; advances each emitter's parity.
-static void build_update_items(std::vector<PendingOp>& ops, UpdateItem* items, CountQuery* queries, uint32_t tile_size, uint32_t* tiles_out)
+// T3D_TAIL_TILES=0: every tile whole (experiments).
+static bool tail_tiles_enabled()
 {
+    static int v = -1;
+    if (v < 0)
+    {
+        const char* env = getenv("T3D_TAIL_TILES");
+        v = (env && env[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+static void build_update_items(std::vector<PendingOp>& ops, UpdateItem* items, CountQuery* queries, uint32_t tile_size, uint32_t* tiles_out,
+                               uint32_t cta_slots)
+{
+    // The work that ends a launch is cut into half tiles: while the last wave of CTAs drains, an SM that has nothing left
+    // idles for the rest of a tile's duration -- half as long with half tiles (which cost a few per cent more per particle,
+    // so only the last wave's worth is cut that way).  In whole-tile units: the tiles from tail_start on are halved.
+    uint64_t total_big = 0;
+    for (const PendingOp& op : ops) total_big += std::max(1u, (op.e->count_ub + tile_size - 1) / tile_size);
+    // (a launch narrower than one wave is left alone: choose_shape has already picked its tile size)
+    const uint64_t tail_start = (tail_tiles_enabled() && total_big > cta_slots) ? total_big - cta_slots : total_big;
+    uint64_t big_offset = 0;
     uint32_t tiles = 0;
     for (size_t k = 0; k < ops.size(); ++k)
     {
@@ -867,8 +888,23 @@ static void build_update_items(std::vector<PendingOp>& ops, UpdateItem* items, C
         queries[k].parity = e->parity; // where this launch leaves the new count
         queries[k].pad = 0;
         // At least one tile per emitter: tile 0 republishes the count into the other parity slot.
-        it.n_tiles = std::max(1u, (e->count_ub + tile_size - 1) / tile_size);
-        if (debug_shrink_grid() && it.n_tiles > 1) it.n_tiles -= 1; // test hook: proves that the kernel's check fires
+        {
+            const uint32_t big = std::max(1u, (e->count_ub + tile_size - 1) / tile_size);
+            const uint64_t before_tail = tail_start > big_offset ? tail_start - big_offset : 0;
+            it.n_big = (uint32_t)std::min<uint64_t>(before_tail, big);
+            const uint64_t covered = (uint64_t)it.n_big * tile_size;
+            const uint32_t rest = e->count_ub > covered ? (uint32_t)(e->count_ub - covered) : 0u;
+            const uint32_t half = tile_size / 2;
+            it.n_tiles = it.n_big + (rest + half - 1) / half;
+            if (it.n_tiles == 0) it.n_tiles = 1;
+            it.pad = 0;
+            big_offset += big;
+        }
+        if (debug_shrink_grid() && it.n_tiles > 1) // test hook: proves that the kernel's check fires
+        {
+            it.n_tiles -= 1;
+            it.n_big = std::min(it.n_big, it.n_tiles);
+        }
         tiles += it.n_tiles;
     }
     *tiles_out = tiles;
@@ -922,7 +958,7 @@ static int launch_updates(t3d_ctx* c, std::vector<PendingOp>& ops)
     uint32_t tiles = 0;
     const int shape = choose_shape(c, ops, (uint32_t)update_tile_size(0), (uint32_t)update_tile_size(1));
     build_update_items(ops, reinterpret_cast<UpdateItem*>(slot->host), reinterpret_cast<CountQuery*>(slot->host + items_bytes),
-                       (uint32_t)update_tile_size(shape), &tiles);
+                       (uint32_t)update_tile_size(shape), &tiles, c->cta_slots);
     T3D_TRY(begin_scan_epoch(c, tiles));
     T3D_TRY(staging_submit(c, slot, total_bytes));
     T3D_TRY(time_begin(c, KERNEL_UPDATE));
@@ -1079,7 +1115,7 @@ static int launch_fused_frame(t3d_ctx* c)
     const int shape = choose_shape(c, c->held, (uint32_t)fused_tile_size(0), (uint32_t)fused_tile_size(1));
     const uint32_t tile_size = (uint32_t)fused_tile_size(shape);
     build_update_items(c->held, reinterpret_cast<UpdateItem*>(slot->host), reinterpret_cast<CountQuery*>(slot->host + items_bytes),
-                       tile_size, &tiles);
+                       tile_size, &tiles, c->cta_slots);
     build_draw_items(c->pending, reinterpret_cast<DrawItem*>(slot->host + items_bytes + queries_bytes), tile_size, &draw_tiles, &any_spin, false);
     T3D_TRY(begin_scan_epoch(c, tiles));
     T3D_TRY(staging_submit(c, slot, total_bytes));
@@ -2463,7 +2499,43 @@ static int sprite_destination(t3d_ctx* c, size_t quads, void* device_dst, size_t
 
 extern "C" {
 
-int t3d_ctx_draw_sprites(t3d_ctx* c, const t3d_sprite2d* sprites, size_t n, int sprites_on_device, void* device_dst, size_t dst_quads,
+// The pinned / device buffer pair the next host list goes through, grown to `bytes` and no longer in flight.
+static int sprite_stage_acquire(t3d_ctx* c, size_t bytes, t3d_ctx::SpriteStage** out)
+{
+    t3d_ctx::SpriteStage* stage = &c->sprite_stage[c->sprite_stage_next];
+    if (stage->in_flight)
+    {
+        HostTimer ht(c, T3D_HOST_WAIT);
+        T3D_CUDA(cudaEventSynchronize(stage->done));
+        stage->in_flight = false;
+    }
+    if (stage->cap < bytes)
+    {
+        if (stage->host) cudaFreeHost(stage->host);
+        if (stage->dev) cudaFree(stage->dev);
+        stage->host = stage->dev = nullptr;
+        stage->cap = 0;
+        const size_t cap = std::max<size_t>(bytes + bytes / 2, 1 << 16);
+        T3D_CUDA(cudaMallocHost((void**)&stage->host, cap));
+        T3D_CUDA(cudaMalloc((void**)&stage->dev, cap));
+        stage->cap = cap;
+    }
+    if (!stage->done) T3D_CUDA(cudaEventCreateWithFlags(&stage->done, cudaEventDisableTiming));
+    *out = stage;
+    return T3D_OK;
+}
+
+int t3d_ctx_map_sprites(t3d_ctx* c, size_t n, t3d_sprite2d** host_list)
+{
+    if (!c || !host_list) return fail(T3D_ERR_INVALID, "t3d_ctx_map_sprites: null argument");
+    T3D_TRY(use_device(c));
+    t3d_ctx::SpriteStage* stage;
+    T3D_TRY(sprite_stage_acquire(c, std::max<size_t>(n, 1) * sizeof(t3d_sprite2d), &stage));
+    *host_list = reinterpret_cast<t3d_sprite2d*>(stage->host);
+    return T3D_OK;
+}
+
+int t3d_ctx_draw_sprites(t3d_ctx* c, const t3d_sprite2d* sprites, size_t n, int list_flags, void* device_dst, size_t dst_quads,
                          const t3d_sprite_vertex** device_ptr, uint32_t* n_quads)
 {
     if (!c || (!sprites && n)) return fail(T3D_ERR_INVALID, "t3d_ctx_draw_sprites: null argument");
@@ -2475,35 +2547,27 @@ int t3d_ctx_draw_sprites(t3d_ctx* c, const t3d_sprite2d* sprites, size_t n, int 
     if (n_quads) *n_quads = 0;
     if (n == 0) return T3D_OK;
     const t3d_sprite2d* dev_list = sprites;
-    bool may_cull = true; // a device-resident list is not inspected here
+    bool may_cull = !(list_flags & T3D_SPRITES_NO_CLIP); // (a device-resident list is not inspected here)
     t3d_ctx::SpriteStage* stage = nullptr;
-    if (!sprites_on_device)
+    if (!(list_flags & T3D_SPRITES_ON_DEVICE))
     {
-        stage = &c->sprite_stage[c->sprite_stage_next];
-        c->sprite_stage_next ^= 1;
-        if (stage->in_flight)
-        {
-            HostTimer ht(c, T3D_HOST_WAIT);
-            T3D_CUDA(cudaEventSynchronize(stage->done));
-            stage->in_flight = false;
-        }
         const size_t bytes = n * sizeof(t3d_sprite2d);
-        if (stage->cap < bytes)
-        {
-            if (stage->host) cudaFreeHost(stage->host);
-            if (stage->dev) cudaFree(stage->dev);
-            stage->host = stage->dev = nullptr;
-            const size_t cap = std::max<size_t>(bytes + bytes / 2, 1 << 16);
-            T3D_CUDA(cudaMallocHost((void**)&stage->host, cap));
-            T3D_CUDA(cudaMalloc((void**)&stage->dev, cap));
-            stage->cap = cap;
-        }
-        if (!stage->done) T3D_CUDA(cudaEventCreateWithFlags(&stage->done, cudaEventDisableTiming));
+        // the list may already lie in the buffer t3d_ctx_map_sprites handed out: then there is nothing to copy
+        t3d_ctx::SpriteStage* mapped = &c->sprite_stage[c->sprite_stage_next];
+        const bool in_place = mapped->host && reinterpret_cast<const char*>(sprites) == mapped->host && bytes <= mapped->cap && !mapped->in_flight;
+        if (in_place)
+            stage = mapped;
+        else
+            T3D_TRY(sprite_stage_acquire(c, bytes, &stage));
+        c->sprite_stage_next ^= 1;
         {
             HostTimer ht(c, T3D_HOST_BUILD);
-            memcpy(stage->host, sprites, bytes);
-            may_cull = false;
-            for (size_t i = 0; i < n && !may_cull; ++i) may_cull = (sprites[i].flags & T3D_SPRITE_CLIPPED) != 0;
+            if (!in_place) memcpy(stage->host, sprites, bytes);
+            if (may_cull)
+            {
+                may_cull = false;
+                for (size_t i = 0; i < n && !may_cull; ++i) may_cull = (sprites[i].flags & T3D_SPRITE_CLIPPED) != 0;
+            }
         }
         T3D_CUDA(cudaMemcpyAsync(stage->dev, stage->host, bytes, cudaMemcpyHostToDevice, c->stream));
         c->h2d_bytes += bytes;

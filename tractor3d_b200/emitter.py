@@ -119,19 +119,28 @@ class Context:
         _check(self.lib, self.lib.t3d_ctx_launch_count(self.h, C.byref(n)))
         return n.value
 
-    def draw_sprites(self, sprites, device_dst=None, dst_quads=0, on_device=False, n=None, want_count=True):
-        """One SpriteBatch::draw 2-D call per record (numpy array of abi.SPRITE2D_DTYPE, or a device pointer with
-        on_device=True and n).  Returns (device pointer of the quads, quads written or None)."""
+    def draw_sprites(self, sprites, device_dst=None, dst_quads=0, on_device=False, n=None, want_count=True, no_clip=False):
+        """One SpriteBatch::draw 2-D call per record (numpy array of abi.SPRITE2D_DTYPE -- possibly the one map_sprites
+        returned -- or a device pointer with on_device=True and n).  Returns (device pointer of the quads, quads written or None)."""
         if on_device:
             src, count = C.c_void_p(sprites), n
         else:
             a = np.ascontiguousarray(sprites)
             assert a.dtype.itemsize == C.sizeof(abi.Sprite2D)
             src, count = C.c_void_p(a.ctypes.data), a.size
+        flags = (abi.SPRITES_ON_DEVICE if on_device else 0) | (abi.SPRITES_NO_CLIP if no_clip else 0)
         ptr, nq = C.c_void_p(), C.c_uint32()
-        _check(self.lib, self.lib.t3d_ctx_draw_sprites(self.h, src, count, int(on_device), C.c_void_p(device_dst) if device_dst else None,
+        _check(self.lib, self.lib.t3d_ctx_draw_sprites(self.h, src, count, flags, C.c_void_p(device_dst) if device_dst else None,
                                                        dst_quads, C.byref(ptr), C.byref(nq) if want_count else None))
         return ptr.value, (nq.value if want_count else None)
+
+    def map_sprites(self, n):
+        """The pinned staging buffer of the next list as a numpy array of n abi.SPRITE2D_DTYPE records: fill it, then pass
+        it to draw_sprites (no further host copy)."""
+        p = C.c_void_p()
+        _check(self.lib, self.lib.t3d_ctx_map_sprites(self.h, n, C.byref(p)))
+        buf = (C.c_char * (n * C.sizeof(abi.Sprite2D))).from_address(p.value)
+        return np.frombuffer(buf, dtype=abi.SPRITE2D_DTYPE, count=n)
 
     def download_quads(self, device_ptr, n_quads):
         out = np.zeros((n_quads, 4, 9), dtype=np.float32)
