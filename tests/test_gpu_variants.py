@@ -21,8 +21,6 @@ CASES = [
     {"T3D_FUSED": "1", "T3D_UPDATE_TICKET": "1"},
     {"T3D_FUSED": "1", "T3D_FUSED_VARIANT": "f2t192s6b2"},
     {"T3D_FUSED": "1", "T3D_FUSED_VARIANT": "f2t128s12b3"},
-    {"T3D_TAIL_TILES": "0"},                               # every tile whole (the default halves the tiles that end a wide launch)
-    {"T3D_TAIL_TILES": "0", "T3D_FUSED": "0"},
 ]
 
 

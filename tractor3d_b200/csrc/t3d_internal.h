@@ -135,8 +135,6 @@ struct UpdateItem
     float percent_per_frame;
     float frame_duration_secs;
     uint32_t n_tiles;     // tiles of this launch that belong to the emitter (the kernel checks that they cover the live count)
-    uint32_t n_big;       // the first n_big of them are whole tiles, the rest half tiles (the tail of the launch is cut finer)
-    uint32_t pad;
 };
 
 struct SpawnItem

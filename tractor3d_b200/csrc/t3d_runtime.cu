@@ -843,29 +843,8 @@ static int choose_shape(const t3d_ctx* c, const std::vector<PendingOp>& ops, uin
 }
 
 // Cuts the update descriptors (and the count queries of the feedback) of `ops`; advances each emitter's parity.
-// T3D_TAIL_TILES=0: every tile whole (experiments).
-static bool tail_tiles_enabled()
+static void build_update_items(std::vector<PendingOp>& ops, UpdateItem* items, CountQuery* queries, uint32_t tile_size, uint32_t* tiles_out)
 {
-    static int v = -1;
-    if (v < 0)
-    {
-        const char* env = getenv("T3D_TAIL_TILES");
-        v = (env && env[0] == '0') ? 0 : 1;
-    }
-    return v == 1;
-}
-
-static void build_update_items(std::vector<PendingOp>& ops, UpdateItem* items, CountQuery* queries, uint32_t tile_size, uint32_t* tiles_out,
-                               uint32_t cta_slots)
-{
-    // The work that ends a launch is cut into half tiles: while the last wave of CTAs drains, an SM that has nothing left
-    // idles for the rest of a tile's duration -- half as long with half tiles (which cost a few per cent more per particle,
-    // so only the last wave's worth is cut that way).  In whole-tile units: the tiles from tail_start on are halved.
-    uint64_t total_big = 0;
-    for (const PendingOp& op : ops) total_big += std::max(1u, (op.e->count_ub + tile_size - 1) / tile_size);
-    // (a launch narrower than one wave is left alone: choose_shape has already picked its tile size)
-    const uint64_t tail_start = (tail_tiles_enabled() && total_big > cta_slots) ? total_big - cta_slots : total_big;
-    uint64_t big_offset = 0;
     uint32_t tiles = 0;
     for (size_t k = 0; k < ops.size(); ++k)
     {
@@ -888,23 +867,8 @@ static void build_update_items(std::vector<PendingOp>& ops, UpdateItem* items, C
         queries[k].parity = e->parity; // where this launch leaves the new count
         queries[k].pad = 0;
         // At least one tile per emitter: tile 0 republishes the count into the other parity slot.
-        {
-            const uint32_t big = std::max(1u, (e->count_ub + tile_size - 1) / tile_size);
-            const uint64_t before_tail = tail_start > big_offset ? tail_start - big_offset : 0;
-            it.n_big = (uint32_t)std::min<uint64_t>(before_tail, big);
-            const uint64_t covered = (uint64_t)it.n_big * tile_size;
-            const uint32_t rest = e->count_ub > covered ? (uint32_t)(e->count_ub - covered) : 0u;
-            const uint32_t half = tile_size / 2;
-            it.n_tiles = it.n_big + (rest + half - 1) / half;
-            if (it.n_tiles == 0) it.n_tiles = 1;
-            it.pad = 0;
-            big_offset += big;
-        }
-        if (debug_shrink_grid() && it.n_tiles > 1) // test hook: proves that the kernel's check fires
-        {
-            it.n_tiles -= 1;
-            it.n_big = std::min(it.n_big, it.n_tiles);
-        }
+        it.n_tiles = std::max(1u, (e->count_ub + tile_size - 1) / tile_size);
+        if (debug_shrink_grid() && it.n_tiles > 1) it.n_tiles -= 1; // test hook: proves that the kernel's check fires
         tiles += it.n_tiles;
     }
     *tiles_out = tiles;
@@ -958,7 +922,7 @@ static int launch_updates(t3d_ctx* c, std::vector<PendingOp>& ops)
     uint32_t tiles = 0;
     const int shape = choose_shape(c, ops, (uint32_t)update_tile_size(0), (uint32_t)update_tile_size(1));
     build_update_items(ops, reinterpret_cast<UpdateItem*>(slot->host), reinterpret_cast<CountQuery*>(slot->host + items_bytes),
-                       (uint32_t)update_tile_size(shape), &tiles, c->cta_slots);
+                       (uint32_t)update_tile_size(shape), &tiles);
     T3D_TRY(begin_scan_epoch(c, tiles));
     T3D_TRY(staging_submit(c, slot, total_bytes));
     T3D_TRY(time_begin(c, KERNEL_UPDATE));
@@ -1115,7 +1079,7 @@ static int launch_fused_frame(t3d_ctx* c)
     const int shape = choose_shape(c, c->held, (uint32_t)fused_tile_size(0), (uint32_t)fused_tile_size(1));
     const uint32_t tile_size = (uint32_t)fused_tile_size(shape);
     build_update_items(c->held, reinterpret_cast<UpdateItem*>(slot->host), reinterpret_cast<CountQuery*>(slot->host + items_bytes),
-                       tile_size, &tiles, c->cta_slots);
+                       tile_size, &tiles);
     build_draw_items(c->pending, reinterpret_cast<DrawItem*>(slot->host + items_bytes + queries_bytes), tile_size, &draw_tiles, &any_spin, false);
     T3D_TRY(begin_scan_epoch(c, tiles));
     T3D_TRY(staging_submit(c, slot, total_bytes));

@@ -88,7 +88,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 {
     static_assert(V == 2 || V == 4, "a thread owns 2 or 4 consecutive particles");
     static_assert(V * THREADS * SUB < 65535, "tile-local dead counts are kept as 16-bit values");
-    static_assert(SUB % 2 == 0, "the tiles at the tail of an emitter are half tiles");
     constexpr int kQuadBytes = T3D_FLOATS_PER_QUAD * 4;
     constexpr int WG = 32 * V;                  // particles per warp per group
     constexpr int kRecWarp = WG * REC_WORDS * 4; // bytes of life records per warp per group
@@ -133,13 +132,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     const size_t stride = it.st.stride;
     const uint32_t cap = it.st.seg_capacity;
     const uint32_t jt = tile - it.tile_begin; // tile index inside the emitter
-    // The emitter's first n_big tiles are whole (SUB groups), the rest half tiles (SUB / 2 groups): the host cuts the work
-    // that ends a launch finer, so that the SMs do not idle for most of a tile's duration while the last ones finish.
-    const uint32_t n_big = it.n_big;
-    const bool half_tile = jt >= n_big;
-    const int groups = half_tile ? SUB / 2 : SUB;
-    const uint32_t first = half_tile ? n_big * TILE + (jt - n_big) * (TILE / 2) : jt * TILE;
-    const uint32_t tile_len = (uint32_t)groups * GROUP;
+    const uint32_t first = jt * TILE;
     const uint32_t flags = it.flags;
     const bool animated = (flags & kFlagAnimated) != 0;
     const bool looped = (flags & kFlagLooped) != 0;
@@ -166,7 +159,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     for (int s = 0; s < SUB; ++s)
     {
         const uint32_t k0 = first + s * GROUP + tid * V;
-        if (s < groups && k0 < cap) Vec<V>::ld(col(RW_ENERGY) + k0, en[s]);
+        if (k0 < cap) Vec<V>::ld(col(RW_ENERGY) + k0, en[s]);
     }
     // Group 0 is requested now so that it is in flight while the scan and the look-back run: the warp's life records into
     // shared memory, the thread's own rw words into registers.
@@ -216,9 +209,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     }
     // The host sized this emitter's share of the grid from an upper bound of its live count; if the bound was wrong,
     // say so instead of silently leaving particles out of the frame.
-    if (jt == 0 && tid == 0 &&
-        (unsigned long long)N > (unsigned long long)n_big * TILE + (unsigned long long)(it.n_tiles - n_big) * (TILE / 2))
-        atomicOr(fault, kFaultUpdateGrid);
+    if (jt == 0 && tid == 0 && (unsigned long long)N > (unsigned long long)it.n_tiles * TILE) atomicOr(fault, kFaultUpdateGrid);
     if (first >= N)
     {
         cp_async_wait<0>(); // nothing of this thread may still be landing in shared memory when the CTA retires
@@ -260,7 +251,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 #pragma unroll
         for (int l = 0; l < V; ++l)
         {
-            if (s < groups && k0 + l < N) // (the slots past a half tile's groups belong to the next tile)
+            if (k0 + l < N)
             {
                 en[s][l] = __float2int_rz((float)en[s][l] - elapsed_ms);
                 if (!(en[s][l] > 0)) cnt[s]++;
@@ -306,7 +297,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     // count, then never lies in such a tile -- K >= N/2 examined originals, and 2 * (first + TILE) < N puts every k of
     // the tile below N/2 - 1.)  If it has no dead particle either, nothing in it depends on the emitter-wide prefix and
     // its warps start streaming at once; warp 0 still resolves and publishes the prefix for the tiles behind it.
-    const bool certain = 2ull * ((unsigned long long)first + tile_len) < (unsigned long long)N;
+    const bool certain = 2ull * ((unsigned long long)first + TILE) < (unsigned long long)N;
     const bool need_prefix = !certain || tile_dead != 0;
 
     // ---- decoupled look-back over the preceding tiles of this emitter ----
@@ -468,7 +459,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     float box_hi[3] = { -3.402823466e38f, -3.402823466e38f, -3.402823466e38f };
 
 #pragma unroll 1
-    for (int s = 0; s < groups; ++s)
+    for (int s = 0; s < SUB; ++s)
     {
         const uint32_t w0 = first + s * GROUP + warp * WG; // first particle of the warp's group
         const uint32_t k0 = w0 + lane * V;
@@ -523,7 +514,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 
         // -- the next group: its plan, its records (movers' in place of the dead), its rw words (the slot's own, or those
         //    of the original that takes its place) --
-        const bool more = s + 1 < groups;
+        const bool more = s + 1 < SUB;
         const uint32_t wn = w0 + GROUP, kn = k0 + GROUP;
         Plan pn;
         bool mv_next = false;
