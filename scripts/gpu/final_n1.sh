@@ -21,6 +21,10 @@ timeout 600 env T3D_FUSED=0 $N -k regex:"k_update|k_draw" --launch-skip 8 -c 2 -
 timeout 300 python scripts/host_cost.py c2 200 1 2>&1 | tee $O/host_cost.txt
 timeout 300 python scripts/host_cost.py c4 30 8 2>&1 | tee -a $O/host_cost.txt
 timeout 300 python scripts/bench_sprites.py 2>&1 | tee $O/sprites.txt
-for f in 1 0; do for w in "c5" "c3d" "c5 --churn-spawn 262144 --churn-energy 500,2000" "c5 --churn-spawn 131072 --churn-energy 2000,8000"; do
-  echo "== fused=$f $w ==" | tee -a $O/churn.txt; timeout 300 env T3D_FUSED=$f $B --workload $w --steps 30 2>/dev/null | scripts/bench_summary.py | tee -a $O/churn.txt; done; done
+# the reports are too big to travel (64 MiB limit): keep their raw metrics and the source-level stall summaries
+for r in $O/prof_*.ncu-rep; do
+  ncu -i $r --page raw --csv > ${r%.ncu-rep}_raw.csv 2>/dev/null
+  python scripts/ncu_top_stalls.py $r 40 > ${r%.ncu-rep}_stalls.txt 2>/dev/null
+  rm -f $r
+done
 ls -la $O
