@@ -275,6 +275,14 @@ int t3d_emitter_bounds(t3d_emitter* e, float lo[3], float hi[3], int* valid);
 /* on: draw() of this emitter is skipped (no quads, returns what the reference returns) while its last bounding box lies
  * entirely outside the clip volume of its view-projection matrix.  Implies t3d_emitter_enable_bounds. */
 int t3d_emitter_set_culling(t3d_emitter* e, int on);
+/* SURVEY 8(f4), back-to-front order for BLEND_ALPHA (the reference draws in array order, PE.cpp:866-882, which only
+ * additive blending forgives): a triangle-list index buffer (6 indices per quad, 32-bit, the pattern of
+ * t3d_ctx_triangle_indices) that walks the quads of the emitter's current particles by decreasing depth
+ * position . view_dir (x*vx + y*vy + z*vz, left to right); quads of equal depth keep their live-array order.  The indices
+ * address the vertex stream of a draw() of the same state (quad i = live particle i).  Device-resident, owned by the
+ * context, valid until the next call of this function on the context.  Flushes and reads the live count back. */
+int t3d_emitter_depth_sorted_indices(t3d_emitter* e, const float view_dir[3], const uint32_t** device_ptr, uint64_t* n_indices);
+int t3d_emitter_download_depth_sorted_indices(t3d_emitter* e, const float view_dir[3], uint32_t* out, uint64_t max_indices, uint64_t* n_indices);
 /* The index buffer MeshBatch builds for n_quads billboards (TRIANGLE_STRIP, MB.cpp:117-141): quad 0 contributes
  * {0,1,2,3}; every later quad i the degenerate pair {4(i-1)+3, 4i} and then {4i..4i+3}: 6*n_quads-2 indices.
  * 32-bit (the reference's unsigned short indices cap a batch at 10 922 quads, MB.cpp:213-220).  The buffer is

@@ -696,6 +696,42 @@ uint64_t orc_strip_indices(uint32_t n_quads, uint32_t* out)
 }
 
 /* =====================================================================================
+ * SURVEY 8(f4), restated (the reference has no depth sort): triangle-list indices that walk the live particles by
+ * decreasing position . view_dir, equal depths in live-array order.  The order is DEFINED on the integer key
+ * ~order(depth) (order() maps a float onto an unsigned integer monotonically, -0 below +0), sorted ascending and stably.
+ * ===================================================================================== */
+static uint32_t float_order_u(float f)
+{
+    uint32_t b;
+    memcpy(&b, &f, 4);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+typedef struct { uint32_t key, index; } depth_key;
+static int depth_key_cmp(const void* a, const void* b)
+{
+    const depth_key* x = (const depth_key*)a; const depth_key* y = (const depth_key*)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->index < y->index ? -1 : (x->index > y->index ? 1 : 0);   /* stable */
+}
+uint64_t orc_emitter_depth_sorted_indices(orc_emitter* e, const float view_dir[3], uint32_t* out, uint64_t max_indices)
+{
+    const uint32_t n = e->particle_count;
+    if (!out || !n) return 6ull * n;
+    depth_key* keys = (depth_key*)malloc(sizeof(depth_key) * n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const orc_particle* p = &e->particles[i];
+        const float d = p->position[0] * view_dir[0] + p->position[1] * view_dir[1] + p->position[2] * view_dir[2];
+        keys[i].key = ~float_order_u(d);
+        keys[i].index = i;
+    }
+    qsort(keys, n, sizeof(depth_key), depth_key_cmp);
+    static const uint32_t pat[6] = { 0, 1, 2, 2, 1, 3 };
+    for (uint64_t j = 0; j < 6ull * n && j < max_indices; ++j) out[j] = 4u * keys[j / 6].index + pat[j % 6];
+    free(keys);
+    return 6ull * n;
+}
+
+/* =====================================================================================
  * SpriteBatch's 2-D overloads (SB.cpp:235-289, :366-413, :475-506, clipSprite :523-597) and TileSet::draw
  * (src/graphics/TileSet.cpp:179-236).  Pinned bit for bit to the reference's own code by tests/test_oracle_vs_ref.py.
  * ===================================================================================== */

@@ -78,6 +78,8 @@ int orc_emitter_bounds(orc_emitter* e, float lo[3], float hi[3]);
  * 32-bit indices.  Returns the number of indices written (6n-2).  Restated, not reference-pinned (MeshBatch.cpp needs GL). */
 uint64_t orc_strip_indices(uint32_t n_quads, uint32_t* out);
 
+/* t3d_emitter_depth_sorted_indices restated (no reference counterpart): 6 indices per live particle, farthest first. */
+uint64_t orc_emitter_depth_sorted_indices(orc_emitter* e, const float view_dir[3], uint32_t* out, uint64_t max_indices);
 /* one SpriteBatch::draw 2-D call per t3d_sprite2d (SB.cpp:235-289, :366-413, :475-506); 36 floats per quad. */
 uint32_t orc_sprites_2d(const t3d_sprite2d* sprites, size_t n, float* out, size_t max_quads);
 /* TileSet::draw (TileSet.cpp:207-236) from the position it has computed by line 205. */

@@ -89,6 +89,7 @@ class CpuLib:
         proto("time_draw", C.c_double, [_vp, C.c_int])
         proto("time_frames", C.c_double, [_vp, C.c_float, C.c_int])
         if self.kind == "port":
+            proto("emitter_depth_sorted_indices", C.c_uint64, [_vp, _P(C.c_float), _P(C.c_uint32), C.c_uint64])
             proto("sprites_2d", C.c_uint32, [_vp, C.c_size_t, _P(C.c_float), C.c_size_t])
             proto("tileset_draw", C.c_uint32, [_P(C.c_float), C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float,
                                                _P(C.c_float), _P(C.c_float), _P(C.c_float), C.c_size_t])
@@ -248,6 +249,13 @@ class CpuEmitter:
         out = np.zeros((max(n, 1), 4, 10), dtype=np.float32)
         if n:
             self.L.emitter_get_clip_vertices(self.h, m.ctypes.data_as(_P(C.c_float)), out.ctypes.data_as(_P(C.c_float)), n)
+        return out[:n]
+
+    def depth_sorted_indices(self, view_dir):
+        v = np.ascontiguousarray(view_dir, dtype=np.float32)
+        n = self.L.emitter_depth_sorted_indices(self.h, v.ctypes.data_as(_P(C.c_float)), None, 0)
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        self.L.emitter_depth_sorted_indices(self.h, v.ctypes.data_as(_P(C.c_float)), out.ctypes.data_as(_P(C.c_uint32)), n)
         return out[:n]
 
     def bounds(self):

@@ -193,3 +193,38 @@ def test_culling_skips_the_draw_of_an_emitter_outside_the_frustum():
         assert np.array_equal(eg.vertices().view(np.uint32), eo.vertices().view(np.uint32))
     finally:
         lib.close()
+
+
+@pytest.mark.parametrize("n", [1, 777, 70_000, 1_200_000])
+def test_depth_sorted_indices_walk_the_quads_back_to_front(n):
+    # for BLEND_ALPHA the quads want to be drawn farthest first.  The order is defined on an integer key of
+    # position . view_dir, so the comparison with the restated oracle is exact -- ties (here: a block of particles forced
+    # onto the same position) keep live-array order.
+    O, lib, eo, eg = _pair(61, n, energy=(40.0, 4000.0))
+    try:
+        for f in range(3):
+            eo.update(S.DT); eg.update(S.DT)
+        so = eo.state()
+        if n > 100:                                         # make ties: 40 particles at one point, a few exactly at depth 0
+            for c in (abi.COL_POSITION, abi.COL_POSITION + 1, abi.COL_POSITION + 2):
+                so[c, 10:50] = so[c, 10]
+                so[c, 60:64] = 0
+            so[abi.COL_POSITION, 62] = np.float32(-0.0).view(np.uint32)
+            eo.set_state(so); eg.pe.upload_state(so)
+        for view in ((0.0, 0.0, -1.0), (0.3, -0.5, 0.81), (1.0, 0.0, 0.0)):
+            want = eo.depth_sorted_indices(view)
+            got = eg.pe.depth_sorted_indices(view)
+            assert want.size == got.size == 6 * eo.count()
+            assert np.array_equal(got, want), view
+            # and it IS a back-to-front walk: depths do not increase along it
+            pos = so[abi.COL_POSITION:abi.COL_POSITION + 3].view(np.float32) if n > 100 else eo.state()[abi.COL_POSITION:abi.COL_POSITION + 3].view(np.float32)
+            v = np.asarray(view, dtype=np.float32)
+            depth = pos[0] * v[0] + pos[1] * v[1] + pos[2] * v[2]
+            order = got[0::6] // 4
+            assert sorted(order.tolist()) == list(range(eo.count()))
+            assert np.all(np.diff(depth[order]) <= 0)
+        # the vertices those indices address are the ones a draw of this state writes
+        eo.draw(); eg.draw()
+        assert np.array_equal(eg.vertices().view(np.uint32), eo.vertices().view(np.uint32))
+    finally:
+        lib.close()

@@ -188,6 +188,8 @@ PROTOTYPES = {
     "t3d_batch_get_counts": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_uint32)]),
     "t3d_batch_set_transforms": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_float), _P(C.c_float)]),
     "t3d_emitter_vertices": (C.c_int, [_vp, _P(_vp), _P(C.c_uint32)]),
+    "t3d_emitter_depth_sorted_indices": (C.c_int, [_vp, _P(C.c_float), _P(_vp), _P(C.c_uint64)]),
+    "t3d_emitter_download_depth_sorted_indices": (C.c_int, [_vp, _P(C.c_float), _P(C.c_uint32), C.c_uint64, _P(C.c_uint64)]),
     "t3d_ctx_strip_indices": (C.c_int, [_vp, C.c_uint32, _P(_vp), _P(C.c_uint64)]),
     "t3d_ctx_triangle_indices": (C.c_int, [_vp, C.c_uint32, _P(_vp), _P(C.c_uint64)]),
     "t3d_ctx_download_triangle_indices": (C.c_int, [_vp, C.c_uint32, _P(C.c_uint32), C.c_uint64, _P(C.c_uint64)]),

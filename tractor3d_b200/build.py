@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(CSRC, "libt3d_particles.so")
-SOURCES = ["t3d_kernels.cu", "t3d_update.cu", "t3d_sprites.cu", "t3d_runtime.cu", "t3d_host.cpp"]
+SOURCES = ["t3d_kernels.cu", "t3d_update.cu", "t3d_sprites.cu", "t3d_sort.cu", "t3d_runtime.cu", "t3d_host.cpp"]
 HEADERS = ["t3d_internal.h", "t3d_device.cuh", "t3d_host.h", os.path.join("..", "..", "include", "t3d_particles.h")]
 
 NVCC_FLAGS = [

@@ -228,6 +228,12 @@ void launch_sprites(void* stream, const t3d_sprite2d* sprites, uint32_t n, uint3
 void launch_tileset(void* stream, const uint32_t* cells, uint32_t n_quads, const float* tiles_xy, uint32_t cols, const float* xs,
                     const float* ys, float z, float tile_w, float tile_h, float wr, float hr, const float color[4], float* dst);
 
+// ---- depth sort (t3d_sort.cu) ----
+size_t depth_sort_temp_bytes(uint32_t n);
+// scratch: 4 * n words; temp: depth_sort_temp_bytes(n) bytes; out: 6 * n indices.  Returns 0 or the cudaError_t of the sort.
+int launch_depth_sort(void* stream, const uint32_t* rw, size_t stride, uint32_t n, const float view_dir[3], uint32_t* scratch, void* temp,
+                      size_t temp_bytes, uint32_t* out);
+
 // The counter-based generator of T3D_RNG_DEVICE (host + device): 32-bit integer hash of (seed, particle serial,
 // draw index).  key = the part that is constant per particle; one draw = key + (j+1)*C through the lowbias32
 // finaliser (two multiplies, three xor-shifts), top 31 bits.  Cheap on purpose: a particle consumes ~30 draws and

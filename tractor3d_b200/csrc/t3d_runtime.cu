@@ -237,6 +237,12 @@ struct t3d_ctx
     size_t sprite_scratch_words{ 0 };
     std::vector<struct t3d_tileset*> tilesets;
 
+    // depth sort (t3d_emitter_depth_sorted_indices): keys / values / library temp / sorted indices, grown on demand
+    uint32_t* sort_scratch{ nullptr };
+    void* sort_temp{ nullptr };
+    uint32_t* sort_indices{ nullptr };
+    size_t sort_cap{ 0 }, sort_temp_cap{ 0 };
+
     uint32_t* readback_host{ nullptr }; // pinned scratch for counts
     size_t readback_cap{ 0 };
     uint32_t* readback_dev{ nullptr };
@@ -1531,6 +1537,9 @@ int t3d_ctx_destroy(t3d_ctx* c)
         if (st.dev) cudaFree(st.dev);
         if (st.done) cudaEventDestroy(st.done);
     }
+    if (c->sort_scratch) cudaFree(c->sort_scratch);
+    if (c->sort_temp) cudaFree(c->sort_temp);
+    if (c->sort_indices) cudaFree(c->sort_indices);
     if (c->sprite_vtx) cudaFree(c->sprite_vtx);
     if (c->sprite_scratch) cudaFree(c->sprite_scratch);
     for (t3d_ctx::Feedback& fb : c->feedback)
@@ -2246,6 +2255,59 @@ int t3d_emitter_vertices(t3d_emitter* e, const t3d_sprite_vertex** device_ptr, u
     const float* where = e->last_draw_dst ? e->last_draw_dst : own; // (t3d_clip_vertex in T3D_VERTEX_CLIP mode)
     if (device_ptr) *device_ptr = reinterpret_cast<const t3d_sprite_vertex*>(where);
     if (n_quads) *n_quads = (where && !e->last_draw_empty) ? drawn : 0;
+    return T3D_OK;
+}
+
+int t3d_emitter_depth_sorted_indices(t3d_emitter* e, const float view_dir[3], const uint32_t** device_ptr, uint64_t* n_indices)
+{
+    if (!e || !view_dir) return fail(T3D_ERR_INVALID, "null argument");
+    t3d_ctx* c = e->ctx;
+    uint32_t n = 0;
+    T3D_TRY(refresh_counts(c, &e, 1, &n, nullptr));
+    if (device_ptr) *device_ptr = nullptr;
+    if (n_indices) *n_indices = 0;
+    if (n == 0) return T3D_OK;
+    if (n > (1u << 30)) return fail(T3D_ERR_INVALID, "too many particles for 32-bit vertex indices");
+    const size_t temp_bytes = depth_sort_temp_bytes(n);
+    if (c->sort_cap < n || c->sort_temp_cap < temp_bytes)
+    {
+        T3D_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->sort_scratch) cudaFree(c->sort_scratch);
+        if (c->sort_temp) cudaFree(c->sort_temp);
+        if (c->sort_indices) cudaFree(c->sort_indices);
+        c->sort_scratch = c->sort_indices = nullptr;
+        c->sort_temp = nullptr;
+        c->sort_cap = c->sort_temp_cap = 0;
+        const size_t cap = std::max<size_t>((size_t)n + n / 4, 4096);
+        const size_t tcap = std::max(depth_sort_temp_bytes((uint32_t)cap), temp_bytes);
+        T3D_CUDA(cudaMalloc((void**)&c->sort_scratch, cap * 4 * sizeof(uint32_t)));
+        T3D_CUDA(cudaMalloc((void**)&c->sort_indices, cap * 6 * sizeof(uint32_t)));
+        T3D_CUDA(cudaMalloc(&c->sort_temp, std::max<size_t>(tcap, 16)));
+        c->sort_cap = cap;
+        c->sort_temp_cap = tcap;
+    }
+    const int err = launch_depth_sort(c->stream, e->hc.st.rw, e->hc.st.stride, n, view_dir, c->sort_scratch, c->sort_temp, c->sort_temp_cap,
+                                      c->sort_indices);
+    if (err) return fail(T3D_ERR_CUDA, "depth sort failed: %s", cudaGetErrorString((cudaError_t)err));
+    T3D_CUDA(cudaGetLastError());
+    c->launches += 3; // keys, indices, and the library's sort passes counted as one
+    if (device_ptr) *device_ptr = c->sort_indices;
+    if (n_indices) *n_indices = 6ull * n;
+    return T3D_OK;
+}
+
+int t3d_emitter_download_depth_sorted_indices(t3d_emitter* e, const float view_dir[3], uint32_t* out, uint64_t max_indices, uint64_t* n_indices)
+{
+    const uint32_t* dev = nullptr;
+    uint64_t n = 0;
+    T3D_TRY(t3d_emitter_depth_sorted_indices(e, view_dir, &dev, &n));
+    if (n_indices) *n_indices = n;
+    if (!out || !n) return T3D_OK;
+    t3d_ctx* c = e->ctx;
+    const uint64_t m = std::min(n, max_indices);
+    T3D_CUDA(cudaMemcpyAsync(out, dev, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    T3D_CUDA(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += m * sizeof(uint32_t);
     return T3D_OK;
 }
 

@@ -380,6 +380,15 @@ class ParticleEmitter:
         _check(self.lib, self.lib.t3d_emitter_get_sprite_tex_coords(self.h, None, _fptr(out), n))
         return out.reshape(n, 4)
 
+    def depth_sorted_indices(self, view_dir):
+        """Triangle-list indices (uint32 numpy copy) that walk the current particles' quads farthest first along view_dir."""
+        v = np.ascontiguousarray(view_dir, dtype=np.float32)
+        n = C.c_uint64()
+        _check(self.lib, self.lib.t3d_emitter_download_depth_sorted_indices(self.h, _fptr(v), None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=np.uint32)
+        _check(self.lib, self.lib.t3d_emitter_download_depth_sorted_indices(self.h, _fptr(v), out.ctypes.data_as(_P(C.c_uint32)), out.size, C.byref(n)))
+        return out[: n.value]
+
     def set_rng(self, mode, seed=0):
         _check(self.lib, self.lib.t3d_emitter_set_rng(self.h, mode, seed))
 
