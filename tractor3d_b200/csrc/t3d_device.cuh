@@ -204,6 +204,89 @@ __device__ __forceinline__ void expand_quad_clip(const float pos[3], const float
     o[9] = make_float4(color[0], color[1], color[2], color[3]);
 }
 
+// --------------------------------------------------------------------------------------------------
+// spawn: one particle of ParticleEmitter::emitOnce (PE.cpp:312-364 with the generators of :611-679), from a source of
+// raw draws.  Shared by k_spawn and by the update kernel's in-launch spawn, so both produce the same bits.
+// --------------------------------------------------------------------------------------------------
+struct SpawnedParticle
+{
+    float cs[4], ce[4];
+    int energy;
+    float size_start, size_end, spin, angle, rot_speed;
+    float pos[3], vel[3], acc[3], axis[3];
+    uint32_t frame;
+};
+// Src::next() yields the raw draws (integers in [0, 2^31-1]) in the order the reference consumes them.
+template <class Src>
+__device__ __forceinline__ SpawnedParticle spawn_particle(const SpawnParams& P, const float* __restrict__ world, Src& src)
+{
+    SpawnedParticle o;
+    // PE.cpp:312-313 -> :669-679: x, y, z, w, one draw each.
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.cs[k] = P.color_start[k] + P.color_start_var[k] * u11(src.next());
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.ce[k] = P.color_end[k] + P.color_end_var[k] * u11(src.next());
+    // PE.cpp:316: float overload (the bounds are float members), truncated into the integer field.
+    o.energy = __float2int_rz(P.energy_min + (P.energy_max - P.energy_min) * u01(src.next()));
+    o.size_start = P.size_start_min + (P.size_start_max - P.size_start_min) * u01(src.next()); // :317
+    o.size_end = P.size_end_min + (P.size_end_max - P.size_end_min) * u01(src.next());         // :318
+    o.spin = P.spin_min + (P.spin_max - P.spin_min) * u01(src.next());                          // :319-320
+    o.angle = 0.0f + (o.spin - 0.0f) * u01(src.next());                                         // :321
+    o.rot_speed = P.rot_speed_min + (P.rot_speed_max - P.rot_speed_min) * u01(src.next());      // :322
+    if (P.ellipsoid)
+    {
+        // PE.cpp:629-650: rejection-sample the unit ball, scale, translate.
+        float x, y, z;
+        do
+        {
+            x = u11(src.next());
+            y = u11(src.next());
+            z = u11(src.next());
+            // Vector3::length() > 1.0f (PE.cpp:640).  The correctly rounded square root of s exceeds 1 exactly when s exceeds
+            // 1 + 2^-23 (sqrt(1 + 2^-23) = 1 + 2^-24 - ... rounds down to 1), so the comparison needs no square root
+            // (checked against sqrtf over every float in [0.5, 2) by tests/test_abi_and_host.py).
+        } while ((x * x + y * y + z * z) > 1.00000011920928955078125f);
+        o.pos[0] = x * P.position_var[0];
+        o.pos[1] = y * P.position_var[1];
+        o.pos[2] = z * P.position_var[2];
+        o.pos[0] += P.position[0];
+        o.pos[1] += P.position[1];
+        o.pos[2] += P.position[2];
+    }
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) o.pos[k] = P.position[k] + P.position_var[k] * u11(src.next()); // :617-626
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o.vel[k] = P.velocity[k] + P.velocity_var[k] * u11(src.next());
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o.acc[k] = P.acceleration[k] + P.acceleration_var[k] * u11(src.next());
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o.axis[k] = P.rotation_axis[k] + P.rotation_axis_var[k] * u11(src.next());
+
+    // PE.cpp:298-305, 332-351: orbiting properties are rotated by the node's world matrix with its translation removed.
+    float w[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w[k] = world[k];
+    const float tx = w[12], ty = w[13], tz = w[14];
+    w[12] = 0.0f;
+    w[13] = 0.0f;
+    w[14] = 0.0f;
+    if (P.orbit_position) transform4(w, o.pos[0], o.pos[1], o.pos[2], 1.0f, o.pos[0], o.pos[1], o.pos[2]);
+    if (P.orbit_velocity) transform4(w, o.vel[0], o.vel[1], o.vel[2], 1.0f, o.vel[0], o.vel[1], o.vel[2]);
+    if (P.orbit_acceleration) transform4(w, o.acc[0], o.acc[1], o.acc[2], 1.0f, o.acc[0], o.acc[1], o.acc[2]);
+    if (o.rot_speed != 0.0f && !(o.axis[0] == 0.0f && o.axis[1] == 0.0f && o.axis[2] == 0.0f))
+        transform4(w, o.axis[0], o.axis[1], o.axis[2], 1.0f, o.axis[0], o.axis[1], o.axis[2]);
+    o.pos[0] += tx; // :354
+    o.pos[1] += ty;
+    o.pos[2] += tz;
+
+    o.frame = 0; // :357-364
+    if (P.frame_random_offset > 0) o.frame = (uint32_t)src.next() % P.frame_random_offset;
+    return o;
+}
+
 // V x 32-bit streaming accesses (evict-first: every byte of the particle state is touched once per frame).
 template <int V>
 struct Vec;

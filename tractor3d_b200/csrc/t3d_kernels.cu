@@ -81,73 +81,12 @@ __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __rest
     src.p = (STREAM && it.draws) ? it.draws + (it.offsets ? it.offsets[i] : i * it.draw_stride) : nullptr;
     src.key = device_rng_key(P.rng_seed, serial0 + i);
     src.j = 0;
-
-    // PE.cpp:312-313 -> :669-679: x, y, z, w, one draw each.
-    float cs[4], ce[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) cs[k] = P.color_start[k] + P.color_start_var[k] * u11(src.next());
-#pragma unroll
-    for (int k = 0; k < 4; ++k) ce[k] = P.color_end[k] + P.color_end_var[k] * u11(src.next());
-    // PE.cpp:316: float overload (the bounds are float members), truncated into the integer field.
-    const int energy = __float2int_rz(P.energy_min + (P.energy_max - P.energy_min) * u01(src.next()));
-    const float size_start = P.size_start_min + (P.size_start_max - P.size_start_min) * u01(src.next()); // :317
-    const float size_end = P.size_end_min + (P.size_end_max - P.size_end_min) * u01(src.next());         // :318
-    const float spin = P.spin_min + (P.spin_max - P.spin_min) * u01(src.next());                          // :319-320
-    const float angle = 0.0f + (spin - 0.0f) * u01(src.next());                                           // :321
-    const float rot_speed = P.rot_speed_min + (P.rot_speed_max - P.rot_speed_min) * u01(src.next());      // :322
-
-    float pos[3], vel[3], acc[3], axis[3];
-    if (P.ellipsoid)
-    {
-        // PE.cpp:629-650: rejection-sample the unit ball, scale, translate.
-        float x, y, z;
-        do
-        {
-            x = u11(src.next());
-            y = u11(src.next());
-            z = u11(src.next());
-            // Vector3::length() > 1.0f (PE.cpp:640).  The correctly rounded square root of s exceeds 1 exactly when s exceeds
-            // 1 + 2^-23 (sqrt(1 + 2^-23) = 1 + 2^-24 - ... rounds down to 1), so the comparison needs no square root
-            // (checked against sqrtf over every float in [0.5, 2) by tests/test_abi_and_host.py).
-        } while ((x * x + y * y + z * z) > 1.00000011920928955078125f);
-        pos[0] = x * P.position_var[0];
-        pos[1] = y * P.position_var[1];
-        pos[2] = z * P.position_var[2];
-        pos[0] += P.position[0];
-        pos[1] += P.position[1];
-        pos[2] += P.position[2];
-    }
-    else
-    {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) pos[k] = P.position[k] + P.position_var[k] * u11(src.next()); // :617-626
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) vel[k] = P.velocity[k] + P.velocity_var[k] * u11(src.next());
-#pragma unroll
-    for (int k = 0; k < 3; ++k) acc[k] = P.acceleration[k] + P.acceleration_var[k] * u11(src.next());
-#pragma unroll
-    for (int k = 0; k < 3; ++k) axis[k] = P.rotation_axis[k] + P.rotation_axis_var[k] * u11(src.next());
-
-    // PE.cpp:298-305, 332-351: orbiting properties are rotated by the node's world matrix with its translation removed.
-    float w[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) w[k] = it.world[k];
-    const float tx = w[12], ty = w[13], tz = w[14];
-    w[12] = 0.0f;
-    w[13] = 0.0f;
-    w[14] = 0.0f;
-    if (P.orbit_position) transform4(w, pos[0], pos[1], pos[2], 1.0f, pos[0], pos[1], pos[2]);
-    if (P.orbit_velocity) transform4(w, vel[0], vel[1], vel[2], 1.0f, vel[0], vel[1], vel[2]);
-    if (P.orbit_acceleration) transform4(w, acc[0], acc[1], acc[2], 1.0f, acc[0], acc[1], acc[2]);
-    if (rot_speed != 0.0f && !(axis[0] == 0.0f && axis[1] == 0.0f && axis[2] == 0.0f))
-        transform4(w, axis[0], axis[1], axis[2], 1.0f, axis[0], axis[1], axis[2]);
-    pos[0] += tx; // :354
-    pos[1] += ty;
-    pos[2] += tz;
-
-    uint32_t frame = 0; // :357-364
-    if (P.frame_random_offset > 0) frame = (uint32_t)src.next() % P.frame_random_offset;
+    const SpawnedParticle sp = spawn_particle(P, it.world, src); // PE.cpp:312-364
+    const float* cs = sp.cs; const float* ce = sp.ce; const float* pos = sp.pos; const float* vel = sp.vel; const float* acc = sp.acc;
+    const float* axis = sp.axis;
+    const int energy = sp.energy;
+    const float size_start = sp.size_start, size_end = sp.size_end, spin = sp.spin, angle = sp.angle, rot_speed = sp.rot_speed;
+    const uint32_t frame = sp.frame;
 
     // what update() rewrites every frame: 15 rw columns
     uint32_t* const rw = st.rw + (count0 + i);
