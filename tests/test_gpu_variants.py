@@ -16,11 +16,13 @@ CASES = [
     {"T3D_UPDATE_VARIANT": "u2t128s12b4", "T3D_UPDATE_TICKET": "1"},
     {"T3D_UPDATE_VARIANT": "u4t128s8b2"},
     {"T3D_DRAW_VARIANT": "lsu"},
-    {"T3D_FUSED": "0"},
     {"T3D_FUSED": "1"},
     {"T3D_FUSED": "1", "T3D_UPDATE_TICKET": "1"},
     {"T3D_FUSED": "1", "T3D_FUSED_VARIANT": "f2t192s6b2"},
     {"T3D_FUSED": "1", "T3D_FUSED_VARIANT": "f2t128s12b3"},
+    {"T3D_FUSE_SPAWN": "0"},                      # every spawn a launch of its own (the default lets the update launch do it)
+    {"T3D_FUSE_SPAWN": "0", "T3D_FUSED": "0"},
+    {"T3D_FUSED": "0"},
 ]
 
 
@@ -29,7 +31,7 @@ def test_alternative_paths_stay_bit_exact(env):
     e = dict(os.environ)
     e.update(env)
     cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-x", "-q",
-           "-k", "golden or multi_tile or batch_of_mixed or device_rng or churn_at_scale"]
+           "-k", "golden or multi_tile or batch_of_mixed or device_rng or churn_at_scale or headline_parameters"]
     res = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
 
