@@ -16,13 +16,11 @@ CASES = [
     {"T3D_UPDATE_VARIANT": "u2t128s12b4", "T3D_UPDATE_TICKET": "1"},
     {"T3D_UPDATE_VARIANT": "u4t128s8b2"},
     {"T3D_DRAW_VARIANT": "lsu"},
+    {"T3D_FUSED": "0"},
     {"T3D_FUSED": "1"},
     {"T3D_FUSED": "1", "T3D_UPDATE_TICKET": "1"},
     {"T3D_FUSED": "1", "T3D_FUSED_VARIANT": "f2t192s6b2"},
     {"T3D_FUSED": "1", "T3D_FUSED_VARIANT": "f2t128s12b3"},
-    {"T3D_FUSE_SPAWN": "0"},                      # every spawn a launch of its own (the default lets the update launch do it)
-    {"T3D_FUSE_SPAWN": "0", "T3D_FUSED": "0"},
-    {"T3D_FUSED": "0"},
 ]
 
 

@@ -135,12 +135,6 @@ struct UpdateItem
     float percent_per_frame;
     float frame_duration_secs;
     uint32_t n_tiles;     // tiles of this launch that belong to the emitter (the kernel checks that they cover the live count)
-    // spawn inside the update launch (device generator only): particles to append before the loop (PE.cpp:729-746),
-    // clamped on the device against spawn_cap (PE.cpp:293-296); the node world matrix they are spawned with (PE.cpp:299)
-    uint32_t spawn_request;
-    uint32_t spawn_cap;
-    uint32_t pad;
-    const float* spawn_world;
 };
 
 struct SpawnItem
@@ -198,7 +192,6 @@ struct UpdateLaunch
     int rot_mode;
     const FrozenRotation* frozen;
     bool bounds; // some emitter of the launch wants its bounding box
-    bool spawn;  // some emitter of the launch spawns inside it (UpdateItem::spawn_request)
 };
 // shape: 0 = the variant's own tiles, 1 = half-size tiles (pick_tile_shape decides; narrow launches lose less to their tail)
 void launch_update(void* stream, const UpdateLaunch& L, int shape);

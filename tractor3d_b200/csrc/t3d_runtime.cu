@@ -98,8 +98,7 @@ struct PendingOp
 {
     t3d_emitter* e;
     float elapsed_ms;     // update
-    uint32_t emit_n;      // particles to spawn with a launch of their own before the update (or the whole op for PHASE_EMIT)
-    uint32_t fused_spawn_n; // update: particles the update launch itself spawns before its loop (device generator; see k_update SPAWN)
+    uint32_t emit_n;      // particles to spawn before the update (or the whole op for PHASE_EMIT)
     size_t draws_begin;   // into ctx->pending_draws, when the draws come from the host
     size_t draws_count;
     uint32_t spawned;     // update: particles asked to spawn since the emitter's previous update (churn estimate)
@@ -169,7 +168,6 @@ struct t3d_ctx
     // Updates whose launch is deferred because a draw phase was opened right behind them: if the draws turn out to
     // cover the same emitters in the same order, both become one fused launch (T3D_FUSED=1).
     std::vector<PendingOp> held;
-    std::vector<t3d_emitter*> emit_held; // emitters with held_emit_n > 0 (entries may have been claimed: held_emit_n == 0)
     std::vector<int32_t> pending_draws;
     std::vector<uint32_t> pending_offsets;
 
@@ -296,8 +294,6 @@ struct t3d_emitter
     // a queued spawn will read node_world / a queued draw will read camera_world and view_projection when its descriptors
     // are cut: the setters launch it first if they are about to change what it was called with
     bool node_in_use{ false }, camera_in_use{ false };
-    // particles of emitOnce() calls whose spawn is being held for the update() expected next (it will do it in its own launch)
-    uint32_t held_emit_n{ 0 };
     bool held{ false }; // has an update in ctx->held (launch deferred, see flush)
     bool last_draw_empty{ true }; // the last draw() submitted no quads (inactive, no particles, or culled)
     float* last_draw_dst{ nullptr }; // where the last draw's quads went when not into the emitter's own stream (t3d_emitter_draw_to)
@@ -680,11 +676,11 @@ static int time_end(t3d_ctx* c, int k)
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-static int launch_spawns(t3d_ctx* c, std::vector<PendingOp>& ops)
+static int launch_spawns(t3d_ctx* c)
 {
     // Gather the ops that spawn.
     uint32_t n_items = 0;
-    for (const PendingOp& op : ops) n_items += op.emit_n > 0 ? 1u : 0u;
+    for (const PendingOp& op : c->pending) n_items += op.emit_n > 0 ? 1u : 0u;
     if (!n_items) return T3D_OK;
 
     const size_t items_bytes = align_up(sizeof(SpawnItem) * n_items, 16);
@@ -701,7 +697,7 @@ static int launch_spawns(t3d_ctx* c, std::vector<PendingOp>& ops)
 
     uint32_t tiles = 0, k = 0;
     bool any_host_draws = false;
-    for (PendingOp& op : ops)
+    for (PendingOp& op : c->pending)
     {
         if (!op.emit_n) continue;
         t3d_emitter* e = op.e;
@@ -853,9 +849,7 @@ static int choose_shape(const t3d_ctx* c, const std::vector<PendingOp>& ops, uin
 }
 
 // Cuts the update descriptors (and the count queries of the feedback) of `ops`; advances each emitter's parity.
-// worlds_host / worlds_dev: n x float[16] of staging for the node matrices of the emitters that spawn inside the launch
-static void build_update_items(std::vector<PendingOp>& ops, UpdateItem* items, CountQuery* queries, uint32_t tile_size, uint32_t* tiles_out,
-                               float* worlds_host, const float* worlds_dev)
+static void build_update_items(std::vector<PendingOp>& ops, UpdateItem* items, CountQuery* queries, uint32_t tile_size, uint32_t* tiles_out)
 {
     uint32_t tiles = 0;
     for (size_t k = 0; k < ops.size(); ++k)
@@ -871,15 +865,6 @@ static void build_update_items(std::vector<PendingOp>& ops, UpdateItem* items, C
         it.percent_per_frame = ec.percent_per_frame;
         it.frame_duration_secs = ec.frame_duration_secs;
         it.elapsed_ms = op.elapsed_ms;
-        it.spawn_request = op.fused_spawn_n;
-        it.spawn_cap = e->p.particle_count_max;
-        it.pad = 0;
-        it.spawn_world = nullptr;
-        if (op.fused_spawn_n)
-        {
-            memcpy(worlds_host + 16 * k, e->node_world, 64); // PE.cpp:299
-            it.spawn_world = worlds_dev + 16 * k;
-        }
         it.parity = e->parity;
         e->parity ^= 1u;
         e->launch_version++;
@@ -938,17 +923,12 @@ static int launch_updates(t3d_ctx* c, std::vector<PendingOp>& ops)
     for (PendingOp& op : ops) T3D_TRY(sync_const(op.e));
     StagingSlot* slot;
     const size_t items_bytes = align_up(sizeof(UpdateItem) * n_items, 16);
-    const size_t queries_bytes = align_up(sizeof(CountQuery) * n_items, 16);
-    bool any_spawn = false;
-    for (const PendingOp& op : ops) any_spawn = any_spawn || op.fused_spawn_n != 0;
-    const size_t worlds_bytes = any_spawn ? 64 * (size_t)n_items : 0;
-    const size_t total_bytes = items_bytes + queries_bytes + worlds_bytes;
+    const size_t total_bytes = items_bytes + sizeof(CountQuery) * n_items;
     T3D_TRY(staging_acquire(c, total_bytes, &slot));
     uint32_t tiles = 0;
     const int shape = choose_shape(c, ops, (uint32_t)update_tile_size(0), (uint32_t)update_tile_size(1));
     build_update_items(ops, reinterpret_cast<UpdateItem*>(slot->host), reinterpret_cast<CountQuery*>(slot->host + items_bytes),
-                       (uint32_t)update_tile_size(shape), &tiles, reinterpret_cast<float*>(slot->host + items_bytes + queries_bytes),
-                       reinterpret_cast<const float*>(slot->dev + items_bytes + queries_bytes));
+                       (uint32_t)update_tile_size(shape), &tiles);
     T3D_TRY(begin_scan_epoch(c, tiles));
     T3D_TRY(staging_submit(c, slot, total_bytes));
     T3D_TRY(time_begin(c, KERNEL_UPDATE));
@@ -962,7 +942,6 @@ static int launch_updates(t3d_ctx* c, std::vector<PendingOp>& ops)
     L.epoch = c->epoch;
     L.fault = c->fault_dev;
     L.bounds = mark_bounds(c, ops);
-    L.spawn = any_spawn;
     launch_update(c->stream, L, shape);
     T3D_CUDA(cudaGetLastError());
     T3D_TRY(time_end(c, KERNEL_UPDATE));
@@ -970,8 +949,6 @@ static int launch_updates(t3d_ctx* c, std::vector<PendingOp>& ops)
     c->launches++;
     T3D_TRY(submit_feedback(c, ops, reinterpret_cast<const CountQuery*>(slot->dev + items_bytes)));
     T3D_TRY(staging_release(c, slot));
-    for (PendingOp& op : ops)
-        if (op.fused_spawn_n) op.e->node_in_use = false; // the spawn has been cut with the matrix it was called with
     return T3D_OK;
 }
 
@@ -1101,18 +1078,14 @@ static int launch_fused_frame(t3d_ctx* c)
     StagingSlot* slot;
     const size_t items_bytes = align_up(sizeof(UpdateItem) * n_items, 16);
     const size_t queries_bytes = align_up(sizeof(CountQuery) * n_items, 16);
-    const size_t ditems_bytes = align_up(sizeof(DrawItem) * n_items, 16);
-    bool any_spawn = false;
-    for (const PendingOp& op : c->held) any_spawn = any_spawn || op.fused_spawn_n != 0;
-    const size_t total_bytes = items_bytes + queries_bytes + ditems_bytes + (any_spawn ? 64 * (size_t)n_items : 0);
+    const size_t total_bytes = items_bytes + queries_bytes + sizeof(DrawItem) * n_items;
     T3D_TRY(staging_acquire(c, total_bytes, &slot));
     uint32_t tiles = 0, draw_tiles = 0;
     bool any_spin = false;
     const int shape = choose_shape(c, c->held, (uint32_t)fused_tile_size(0), (uint32_t)fused_tile_size(1));
     const uint32_t tile_size = (uint32_t)fused_tile_size(shape);
     build_update_items(c->held, reinterpret_cast<UpdateItem*>(slot->host), reinterpret_cast<CountQuery*>(slot->host + items_bytes),
-                       tile_size, &tiles, reinterpret_cast<float*>(slot->host + items_bytes + queries_bytes + ditems_bytes),
-                       reinterpret_cast<const float*>(slot->dev + items_bytes + queries_bytes + ditems_bytes));
+                       tile_size, &tiles);
     build_draw_items(c->pending, reinterpret_cast<DrawItem*>(slot->host + items_bytes + queries_bytes), tile_size, &draw_tiles, &any_spin, false);
     T3D_TRY(begin_scan_epoch(c, tiles));
     T3D_TRY(staging_submit(c, slot, total_bytes));
@@ -1130,7 +1103,6 @@ static int launch_fused_frame(t3d_ctx* c)
     L.rot_mode = c->rot_mode;
     L.frozen = c->frozen_dev;
     L.bounds = mark_bounds(c, c->held);
-    L.spawn = any_spawn;
     launch_update_draw(c->stream, L, shape);
     T3D_CUDA(cudaGetLastError());
     c->ticket_base += tiles;
@@ -1138,8 +1110,6 @@ static int launch_fused_frame(t3d_ctx* c)
     c->launches++;
     T3D_TRY(submit_feedback(c, c->held, reinterpret_cast<const CountQuery*>(slot->dev + items_bytes)));
     T3D_TRY(staging_release(c, slot));
-    for (PendingOp& op : c->held)
-        if (op.fused_spawn_n) op.e->node_in_use = false;
     return T3D_OK;
 }
 
@@ -1179,58 +1149,9 @@ static int launch_held(t3d_ctx* c)
 
 // Launches what is queued.  next_phase is the phase the caller is about to open: updates directly followed by draws
 // are held back one step so that both can go out as one fused launch when they cover the same emitters.
-// T3D_FUSE_SPAWN=0: every spawn is a launch of its own (experiments, and the parity tests of that path).
-static bool fuse_spawn_enabled()
-{
-    static int v = -1;
-    if (v < 0)
-    {
-        const char* env = getenv("T3D_FUSE_SPAWN");
-        v = (env && env[0] == '0') ? 0 : 1;
-    }
-    return v == 1;
-}
-
-// emitOnce() calls whose spawn was held for an update() that did not come: they get their own launch after all.
-static int launch_unclaimed_emits(t3d_ctx* c)
-{
-    if (c->emit_held.empty()) return T3D_OK;
-    std::vector<PendingOp> ops;
-    for (t3d_emitter* e : c->emit_held)
-    {
-        if (!e || !e->held_emit_n) continue;
-        PendingOp op{};
-        op.e = e;
-        op.emit_n = e->held_emit_n;
-        op.offsets_begin = SIZE_MAX;
-        e->held_emit_n = 0;
-        ops.push_back(op);
-    }
-    c->emit_held.clear();
-    if (ops.empty()) return T3D_OK;
-    T3D_TRY(use_device(c));
-    const int rc = launch_spawns(c, ops);
-    for (PendingOp& op : ops) op.e->node_in_use = false;
-    return rc;
-}
-
 static int flush(t3d_ctx* c, int next_phase = PHASE_NONE)
 {
     HostTimer ht(c, T3D_HOST_BUILD);
-    // (held emits that the updates queued since did not claim; the held updates of an earlier phase go first: they were called first)
-    if (!c->emit_held.empty())
-    {
-        bool unclaimed = false;
-        for (t3d_emitter* e : c->emit_held) unclaimed = unclaimed || (e && e->held_emit_n);
-        if (unclaimed)
-        {
-            T3D_TRY(use_device(c));
-            T3D_TRY(launch_held(c));
-            T3D_TRY(launch_unclaimed_emits(c));
-        }
-        else
-            c->emit_held.clear();
-    }
     if (c->phase == PHASE_NONE || c->pending.empty())
     {
         c->phase = PHASE_NONE;
@@ -1246,29 +1167,15 @@ static int flush(t3d_ctx* c, int next_phase = PHASE_NONE)
     T3D_TRY(check_fault(c));
     int rc = T3D_OK;
     bool hold = false;
-    bool emits_held = false;
     if (c->phase == PHASE_EMIT)
     {
         rc = launch_held(c);
-        if (rc == T3D_OK && next_phase == PHASE_UPDATE && fuse_spawn_enabled())
-        {
-            // update() calls are about to follow: the update launch can spawn these itself (device generator only), so they
-            // wait for it; an emitter whose update() does not come gets its spawn launch at the next flush
-            for (PendingOp& op : c->pending)
-            {
-                if (!op.emit_n || op.host_draws) continue;
-                if (!op.e->held_emit_n) c->emit_held.push_back(op.e);
-                op.e->held_emit_n += op.emit_n;
-                op.emit_n = 0;
-                emits_held = true;
-            }
-        }
-        if (rc == T3D_OK) rc = launch_spawns(c, c->pending);
+        if (rc == T3D_OK) rc = launch_spawns(c);
     }
     else if (c->phase == PHASE_UPDATE)
     {
         rc = launch_held(c);
-        if (rc == T3D_OK) rc = launch_spawns(c, c->pending);
+        if (rc == T3D_OK) rc = launch_spawns(c);
         hold = rc == T3D_OK && next_phase == PHASE_DRAW && hold_for_fusion(c);
         if (rc == T3D_OK && !hold) rc = launch_updates(c, c->pending);
     }
@@ -1289,10 +1196,7 @@ static int flush(t3d_ctx* c, int next_phase = PHASE_NONE)
     for (PendingOp& op : c->pending)
     {
         op.e->queued = false;
-        // spawns and draws of this phase have been cut and launched -- except a spawn that waits for its update launch
-        const bool spawn_waits = (emits_held && op.e->held_emit_n) || (hold && op.fused_spawn_n);
-        if (!spawn_waits) op.e->node_in_use = false;
-        op.e->camera_in_use = false;
+        op.e->node_in_use = op.e->camera_in_use = false; // spawns and draws of this phase have been cut and launched
     }
     if (hold)
     {
@@ -1312,7 +1216,7 @@ static int enqueue(t3d_ctx* c, int phase, const PendingOp& op)
     c->phase = phase;
     c->pending.push_back(op);
     op.e->queued = true;
-    if (op.emit_n || op.fused_spawn_n) op.e->node_in_use = true;
+    if (op.emit_n) op.e->node_in_use = true;
     if (phase == PHASE_DRAW) op.e->camera_in_use = true;
     return T3D_OK;
 }
@@ -1911,14 +1815,12 @@ int t3d_emitter_destroy(t3d_emitter* e)
 {
     if (!e) return T3D_OK;
     t3d_ctx* c = e->ctx;
-    if (e->queued || e->held || e->held_emit_n) flush(c);
+    if (e->queued || e->held) flush(c);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (t3d_ctx::Feedback& fb : c->feedback)
         for (t3d_emitter*& o : fb.es)
             if (o == e) o = nullptr;
-    for (t3d_emitter*& o : c->emit_held)
-        if (o == e) o = nullptr;
     if (e->uv_dev) cudaFree(e->uv_dev);
     if (e->dev) c->dev_free.push_back(e->dev);
     free_segment(c, e->slab, e->seg_offset, e->seg_capacity);
@@ -1936,7 +1838,7 @@ int t3d_emitter_set_params(t3d_emitter* e, const t3d_emitter_params* p)
         return fail(T3D_ERR_CAPACITY, "particle_count_max cannot grow past the %u the storage was sized for at create (asked %u)",
                     e->alloc_capacity, p->particle_count_max);
     if (p->particle_count_max == 0) return fail(T3D_ERR_INVALID, "particle_count_max must be > 0");
-    if (e->queued || e->held || e->held_emit_n) T3D_TRY(flush(e->ctx));
+    if (e->queued || e->held) T3D_TRY(flush(e->ctx));
     apply_params(e, p);
     return T3D_OK;
 }
@@ -1960,7 +1862,7 @@ int t3d_emitter_set_texture_size(t3d_emitter* e, uint32_t width, uint32_t height
 {
     if (!e || !width || !height) return fail(T3D_ERR_INVALID, "setTexture: the texture must have a size (PE.cpp:244-247)");
     if (blend_mode < T3D_BLEND_NONE || blend_mode > T3D_BLEND_MULTIPLIED) return fail(T3D_ERR_INVALID, "Unsupported blend mode (%d).", blend_mode);
-    if (e->queued || e->held || e->held_emit_n) T3D_TRY(flush(e->ctx));
+    if (e->queued || e->held) T3D_TRY(flush(e->ctx));
     e->p.blend_mode = blend_mode;           // PE.cpp:243
     e->p.texture_width = (float)width;      // PE.cpp:244-247
     e->p.texture_height = (float)height;
@@ -1981,7 +1883,7 @@ static int install_tex_coords(t3d_emitter* e, uint32_t frame_count)
 int t3d_emitter_set_sprite_tex_coords(t3d_emitter* e, uint32_t frame_count, const float* tex_coords)
 {
     if (!e || !frame_count || !tex_coords) return fail(T3D_ERR_INVALID, "setSpriteTexCoords: bad argument (PE.cpp:514-515)");
-    if (e->queued || e->held || e->held_emit_n) T3D_TRY(flush(e->ctx));
+    if (e->queued || e->held) T3D_TRY(flush(e->ctx));
     e->tex_coords.assign(tex_coords, tex_coords + (size_t)frame_count * 4);
     return install_tex_coords(e, frame_count);
 }
@@ -1989,7 +1891,7 @@ int t3d_emitter_set_sprite_tex_coords(t3d_emitter* e, uint32_t frame_count, cons
 int t3d_emitter_set_sprite_frame_rects(t3d_emitter* e, uint32_t frame_count, const float* rects)
 {
     if (!e || !frame_count || !rects) return fail(T3D_ERR_INVALID, "setSpriteFrameCoords: bad argument (PE.cpp:528-529)");
-    if (e->queued || e->held || e->held_emit_n) T3D_TRY(flush(e->ctx));
+    if (e->queued || e->held) T3D_TRY(flush(e->ctx));
     e->tex_coords.resize((size_t)frame_count * 4);
     t3d_host_sprite_rect_coords(frame_count, rects, e->tex_w_ratio, e->tex_h_ratio, e->tex_coords.data());
     return install_tex_coords(e, frame_count);
@@ -1998,7 +1900,7 @@ int t3d_emitter_set_sprite_frame_rects(t3d_emitter* e, uint32_t frame_count, con
 int t3d_emitter_set_sprite_frame_coords(t3d_emitter* e, uint32_t frame_count, int width, int height)
 {
     if (!e || !frame_count || !width || !height) return fail(T3D_ERR_INVALID, "setSpriteFrameCoords: bad argument (PE.cpp:552-553)");
-    if (e->queued || e->held || e->held_emit_n) T3D_TRY(flush(e->ctx));
+    if (e->queued || e->held) T3D_TRY(flush(e->ctx));
     e->tex_coords.resize((size_t)frame_count * 4);
     t3d_host_sprite_frame_coords(frame_count, width, height, e->p.texture_width, e->p.texture_height, e->tex_coords.data());
     return install_tex_coords(e, frame_count);
@@ -2015,7 +1917,7 @@ int t3d_emitter_get_sprite_tex_coords(t3d_emitter* e, uint32_t* frame_count, flo
 int t3d_emitter_set_rng(t3d_emitter* e, int mode, uint64_t seed)
 {
     if (!e || mode < T3D_RNG_LIBC || mode > T3D_RNG_DEVICE) return fail(T3D_ERR_INVALID, "bad rng mode %d", mode);
-    if (e->queued || e->held || e->held_emit_n) T3D_TRY(flush(e->ctx));
+    if (e->queued || e->held) T3D_TRY(flush(e->ctx));
     e->rng_mode = mode;
     e->rng_seed = seed;
     e->const_dirty = true;
@@ -2066,7 +1968,7 @@ int t3d_emitter_set_view_projection(t3d_emitter* e, const float m[16])
 int t3d_emitter_enable_bounds(t3d_emitter* e, int on)
 {
     if (!e) return fail(T3D_ERR_INVALID, "null emitter");
-    if (e->queued || e->held || e->held_emit_n) T3D_TRY(flush(e->ctx));
+    if (e->queued || e->held) T3D_TRY(flush(e->ctx));
     if (e->want_bounds != (on != 0))
     {
         e->want_bounds = on != 0;
@@ -2085,7 +1987,7 @@ static int read_bounds(t3d_emitter* e, float lo[3], float hi[3], int* valid)
     t3d_ctx* c = e->ctx;
     *valid = 0;
     if (!e->want_bounds) return T3D_OK;
-    if (e->queued || e->held || e->held_emit_n) T3D_TRY(flush(c));
+    if (e->queued || e->held) T3D_TRY(flush(c));
     if (!e->bounds_epoch) return T3D_OK;
     T3D_TRY(use_device(c));
     EmitterBounds b;
@@ -2198,7 +2100,7 @@ int t3d_emitter_update(t3d_emitter* e, float elapsed_time)
     if (!active) return T3D_OK; // PE.cpp:715
     float elapsed_ms;
     if (!t3d_host_rate_cap(&c->statics().running_time, elapsed_time, &elapsed_ms)) return T3D_OK; // PE.cpp:720-725 (process-wide)
-    if (c->phase != PHASE_UPDATE || e->queued) T3D_TRY(flush(c, PHASE_UPDATE));
+    if (c->phase != PHASE_UPDATE || e->queued) T3D_TRY(flush(c));
     PendingOp op{};
     op.e = e;
     op.elapsed_ms = elapsed_ms;
@@ -2207,13 +2109,6 @@ int t3d_emitter_update(t3d_emitter* e, float elapsed_time)
     {
         const uint32_t emit_count = t3d_host_emission_count(&e->emit_time, e->time_per_emission, elapsed_ms); // PE.cpp:732-743
         if (emit_count) T3D_TRY(prepare_emit(e, emit_count, &op));                                            // PE.cpp:744
-    }
-    if (e->rng_mode == T3D_RNG_DEVICE && !op.host_draws && fuse_spawn_enabled())
-    {
-        // what this update emits, and what emitOnce() calls right before it asked for, is spawned by the update launch itself
-        op.fused_spawn_n = op.emit_n + e->held_emit_n;
-        op.emit_n = 0;
-        e->held_emit_n = 0;
     }
     if (e->count_ub > 0) e->count_exact = false; // particles may die in the kernel; the bound stays valid
     e->alive_budget_ms -= (double)elapsed_ms + 1.0;

@@ -68,59 +68,6 @@ struct RwIn
 __device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// ---- spawn inside the update launch (SPAWN) ----------------------------------------------------------------------
-// ParticleEmitter::update emits before its loop and the new particles are updated in the same call (PE.cpp:729-746); an
-// emitOnce right before an update is the same thing one call earlier.  With the device generator a new particle is a pure
-// function of (seed, serial), so the update kernel does not need it in memory: the thread that owns its slot -- or the
-// dead slot it is moved into, PE.cpp:825-828 -- generates it in registers and writes it once.  The spawn launch, its
-// 140-byte write and the update's 104-byte re-read per new particle disappear, and in a steady churn the movers (the
-// last particles of the array = the newest) are generated where they land instead of being fetched from the array's end.
-//
-// The draws of one particle are produced by the whole warp: lane j evaluates draw j, the ellipsoid rejection loop
-// (PE.cpp:629-650) tests six attempts per round in parallel, then the draws behind it.  They go to a 144-byte slot of
-// shared memory from which the requesting lane runs the same spawn_particle() k_spawn runs -- same draws, same
-// arithmetic, same bits.
-constexpr int kGenSlotWords = 36;
-__device__ __forceinline__ void coop_spawn_draws(bool ellipsoid, uint32_t key, uint32_t lane, int32_t* __restrict__ out)
-{
-    const int32_t r = device_rng_from_key(key, lane); // draws 0..31
-    if (lane < 14u) out[lane] = r;
-    uint32_t tries = 1;
-    if (ellipsoid)
-    {
-        uint32_t base = 14; // draw index held by lane 14 in this round
-        int32_t rr = r;
-        while (true)
-        {
-            const float v = u11(rr);
-            const float t = v * v;
-            const float t1 = __shfl_down_sync(0xffffffffu, t, 1), t2 = __shfl_down_sync(0xffffffffu, t, 2);
-            const bool head = lane >= 14u && lane <= 29u && (lane - 14u) % 3u == 0u; // x of attempts 0..5 of the round
-            const bool accepted = head && !((t + t1 + t2) > 1.00000011920928955078125f); // (x*x + y*y) + z*z, as spawn_particle
-            const unsigned am = __ballot_sync(0xffffffffu, accepted);
-            if (am)
-            {
-                const uint32_t h = (uint32_t)__ffs((int)am) - 1u;
-                if (lane >= h && lane < h + 3u) out[14u + (lane - h)] = rr;
-                tries = (base - 14u) / 3u + (h - 14u) / 3u + 1u;
-                break;
-            }
-            base += 18u;
-            rr = device_rng_from_key(key, base + (lane >= 14u ? lane - 14u : 0u));
-        }
-    }
-    else if (lane >= 14u && lane < 17u)
-        out[lane] = r;
-    const uint32_t b2 = 14u + 3u * tries;
-    if (lane < 10u) out[17u + lane] = device_rng_from_key(key, b2 + lane);
-}
-struct SlotDraws
-{
-    const int32_t* p;
-    int j;
-    __device__ __forceinline__ int32_t next() { return p[j++]; }
-};
-
 // V = particles per thread per group, THREADS per CTA, SUB = groups per thread: a tile is V*THREADS*SUB
 // consecutive particles of one emitter and costs one look-back, so the scan frontier only has to advance
 // one tile per V*THREADS*SUB particles streamed.
@@ -132,7 +79,7 @@ struct SlotDraws
 // not examined lie beyond the new live count and are not part of the frame's vertex stream.
 //
 // BOUNDS: also reduces the bounding box of pos +- size over the particles that are live after the update.
-template <int V, int THREADS, int SUB, int MIN_BLOCKS, bool TICKET, bool FUSED, bool BOUNDS, bool SPAWN>
+template <int V, int THREADS, int SUB, int MIN_BLOCKS, bool TICKET, bool FUSED, bool BOUNDS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     k_update(const UpdateItem* __restrict__ items, uint32_t n_items, uint32_t total_tiles,
              unsigned long long* __restrict__ tile_status, uint32_t* __restrict__ ticket, uint32_t ticket_base,
@@ -193,18 +140,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     const bool need_frame = animated || FUSED; // the fused draw reads the frame index for the uv lookup
     const float elapsed_ms = it.elapsed_ms;
     const float secs = elapsed_ms * 0.001f; // PE.cpp:727
-    // SPAWN: the particles [N_old, N) do not exist in memory yet: they are generated where they are needed (see above)
-    const uint32_t N_old = d->cnt[parity].count;
-    uint32_t n_spawn = 0;
-    uint64_t serial0 = 0;
-    if (SPAWN && it.spawn_request)
-    {
-        const uint32_t room = it.spawn_cap > N_old ? it.spawn_cap - N_old : 0u; // PE.cpp:293-296
-        n_spawn = it.spawn_request < room ? it.spawn_request : room;
-        serial0 = d->cnt[parity].serial;
-    }
-    const uint32_t N = N_old + n_spawn;
-    const uint64_t serial_out = SPAWN ? (n_spawn ? serial0 + n_spawn : d->cnt[parity].serial) : 0ull;
+    const uint32_t N = d->cnt[parity].count;
     auto col = [&](int c) -> uint32_t* { return rw + (size_t)c * stride; };
 
     extern __shared__ __align__(128) unsigned char dyn_smem[];
@@ -215,9 +151,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     // the words of a mover that the slot's thread only passes on (rotation record, energy, colour, size) land here,
     // requested one group ahead like everything else: [0,16) rotation record, [16,40) energy, colour x 4, size
     unsigned char* const side_lane = dyn + (size_t)WARPS * (kRecWarp + (FUSED ? kStageWarp : 0)) + (size_t)warp * kSideWarp + lane * kSideLane;
-    // SPAWN: 32 slots of raw draws per warp -- the warp's vertex stage while it is idle (FUSED), else a piece of its own
-    int32_t* const gen_warp = reinterpret_cast<int32_t*>(
-        FUSED ? stage_warp : dyn + (size_t)WARPS * (kRecWarp + kSideWarp) + (size_t)warp * (32 * kGenSlotWords * 4));
 
     // ---- phase A: the energy column of the whole tile -> dead flags (PE.cpp:753-755: `long -= float`, `> 0`) ----
     // Issued before the live count has arrived: every slot below the padded segment size is safe to read.
@@ -283,7 +216,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         if (jt == 0 && tid == 0)
         {
             d->cnt[parity ^ 1].count = 0;
-            d->cnt[parity ^ 1].serial = SPAWN ? serial_out : d->cnt[parity].serial;
+            d->cnt[parity ^ 1].serial = d->cnt[parity].serial;
             if (FUSED) d->cnt[0].drawn = 0;
         }
         return;
@@ -320,13 +253,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         {
             if (k0 + l < N)
             {
-                if (SPAWN && k0 + l >= N_old)
-                {
-                    // a particle spawned by this launch: its energy is draw 8 (PE.cpp:316), evaluated as spawn_particle does
-                    const SpawnParams& P = d->c.sp;
-                    const int32_t r8 = device_rng_from_key(device_rng_key(P.rng_seed, serial0 + (k0 + l - N_old)), 8u);
-                    en[s][l] = __float2int_rz(P.energy_min + (P.energy_max - P.energy_min) * u01(r8));
-                }
                 en[s][l] = __float2int_rz((float)en[s][l] - elapsed_ms);
                 if (!(en[s][l] > 0)) cnt[s]++;
             }
@@ -443,9 +369,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         bool alive[V];       // examined and alive: updated in place
         bool mover[V];       // examined and dead, and not the last particle: original src[l] takes the slot, as it stands
         bool stored[V];      // alive or mover: the slot belongs to the new live range
-        bool memm[V];        // mover that exists in memory (fetched); the others (SPAWN) were spawned by this launch: generated
-        bool genm[V];
-        bool any_memm;
         uint32_t src[V];
         bool all_examined;   // every slot of the group is examined (whole-group vector stores are safe)
         bool any_mover;
@@ -458,7 +381,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         uint32_t run = tile_excl + s_base[s * THREADS + tid];
         p.all_examined = true;
         p.any_mover = false;
-        p.any_memm = false;
         p.last_examined = false;
         p.new_count = 0;
 #pragma unroll
@@ -475,9 +397,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             p.mover[l] = examined && !live && p.src[l] != k; // (the dead one IS the last: nothing moves)
             p.stored[l] = p.alive[l] || p.mover[l];
             p.any_mover = p.any_mover || p.mover[l];
-            p.genm[l] = SPAWN && p.mover[l] && p.src[l] >= N_old;
-            p.memm[l] = p.mover[l] && !p.genm[l];
-            p.any_memm = p.any_memm || p.memm[l];
             p.all_examined = p.all_examined && examined;
             const uint32_t dead_l = (valid && !live) ? 1u : 0u;
             if (need_prefix && examined && !((k + 1u) + run + dead_l < N))
@@ -528,7 +447,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             {
 #pragma unroll
                 for (int l = 0; l < V; ++l)
-                    if (p0.mover[l] && !(SPAWN && p0.src[l] >= N_old))
+                    if (p0.mover[l])
                     {
                         load_one(p0.src[l], cur, l);
                         prefetch_mover(p0.src[l]); // the rest is fetched when the slot is written (group 0 only)
@@ -559,8 +478,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 #pragma unroll
             for (int l = 0; l < V; ++l)
             {
-                fastm[l] = staged && p.memm[l] && !taken;
-                taken = taken || p.memm[l];
+                fastm[l] = staged && p.mover[l] && !taken;
+                taken = taken || p.mover[l];
             }
         }
         uint32_t rc[V][REC_WORDS];
@@ -569,12 +488,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         __syncwarp();
 #pragma unroll
         for (int l = 0; l < V; ++l) rec_read<V>(rec_warp, lane, l, rc[l]);
-        if (staged && p.any_memm)
+        if (staged && p.any_mover)
         {
 #pragma unroll
             for (int l = 0; l < V; ++l)
             {
-                if (!p.memm[l]) continue;
+                if (!p.mover[l]) continue;
                 uint4* rdst = reinterpret_cast<uint4*>(rec + (size_t)(k0 + l) * REC_WORDS);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) rdst[c] = make_uint4(rc[l][c * 4], rc[l][c * 4 + 1], rc[l][c * 4 + 2], rc[l][c * 4 + 3]);
@@ -602,7 +521,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         if (more && need_prefix && kn < N)
         {
             make_plan(s + 1, kn, pn);
-            mv_next = pn.any_memm;
+            mv_next = pn.any_mover;
         }
         const bool warp_mv = need_prefix && __any_sync(0xffffffffu, mv_next);
         if (more && wn < N)
@@ -614,7 +533,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             {
                 uint32_t idx[V];
 #pragma unroll
-                for (int l = 0; l < V; ++l) idx[l] = (mv_next && pn.memm[l]) ? pn.src[l] : kn + l;
+                for (int l = 0; l < V; ++l) idx[l] = (mv_next && pn.mover[l]) ? pn.src[l] : kn + l;
                 rec_issue_indexed<V>(rec_warp, rec, nrec, lane, idx);
             }
         }
@@ -624,7 +543,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 #pragma unroll
             for (int l = 0; l < V; ++l)
             {
-                if (!pn.memm[l]) continue;
+                if (!pn.mover[l]) continue;
                 const uint32_t i = pn.src[l];
                 if (!taken)
                 {
@@ -648,84 +567,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             else
             {
 #pragma unroll
-                for (int l = 0; l < V; ++l) load_one(pn.memm[l] ? pn.src[l] : kn + l, nxt, l);
-            }
-        }
-
-        // -- SPAWN: the particles of this group that this launch spawns -- a new particle in its own slot (then updated
-        //    like any other, PE.cpp:729-746), or one that moves into a dead slot as it stands (PE.cpp:825-828) -- are
-        //    generated here: the warp produces each one's draws together, the requesting lanes finish them side by side --
-        if (SPAWN && n_spawn)
-        {
-            const SpawnParams& P = d->c.sp;
-#pragma unroll
-            for (int l = 0; l < V; ++l)
-            {
-                const uint32_t k = k0 + l;
-                const bool own_new = p.alive[l] && k >= N_old;
-                const bool need = p.genm[l] || own_new;
-                const unsigned m = __ballot_sync(0xffffffffu, need);
-                if (!m) continue;
-                if (FUSED)
-                {
-                    // the slots live in the warp's vertex stage: its previous bulk store must have read it
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                    __syncwarp();
-                }
-                const uint32_t mine = p.genm[l] ? p.src[l] : k;
-                const uint32_t my_slot = (uint32_t)__popc(m & ((1u << lane) - 1u));
-                const bool ellipsoid = P.ellipsoid != 0;
-                const uint64_t seed = P.rng_seed;
-                unsigned todo = m;
-                uint32_t slot = 0;
-                while (todo)
-                {
-                    const int leader = __ffs((int)todo) - 1;
-                    todo &= todo - 1u;
-                    const uint32_t idx = __shfl_sync(0xffffffffu, mine, leader);
-                    coop_spawn_draws(ellipsoid, device_rng_key(seed, serial0 + (idx - N_old)), lane, gen_warp + slot * kGenSlotWords);
-                    ++slot;
-                }
-                __syncwarp();
-                if (need)
-                {
-                    SlotDraws src{ gen_warp + my_slot * kGenSlotWords, 0 };
-                    const SpawnedParticle sp = spawn_particle(P, it.spawn_world, src);
-                    cur.px[l] = sp.pos[0]; cur.py[l] = sp.pos[1]; cur.pz[l] = sp.pos[2];
-                    cur.vx[l] = sp.vel[0]; cur.vy[l] = sp.vel[1]; cur.vz[l] = sp.vel[2];
-                    cur.ang[l] = sp.angle;
-                    cur.tf[l] = 0.0f; // PE.cpp:365
-                    cur.fr[l] = (int)sp.frame;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                    {
-                        rc[l][REC_COLOR_START + c] = __float_as_uint(sp.cs[c]);
-                        rc[l][REC_COLOR_END + c] = __float_as_uint(sp.ce[c]);
-                    }
-                    rc[l][REC_ACC + 0] = __float_as_uint(sp.acc[0]);
-                    rc[l][REC_ACC + 1] = __float_as_uint(sp.acc[1]);
-                    rc[l][REC_ACC + 2] = __float_as_uint(sp.acc[2]);
-                    rc[l][REC_SPIN] = __float_as_uint(sp.spin);
-                    rc[l][REC_ENERGY_START] = (uint32_t)sp.energy;
-                    rc[l][REC_SIZE_START] = __float_as_uint(sp.size_start);
-                    rc[l][REC_SIZE_END] = __float_as_uint(sp.size_end);
-                    rc[l][REC_PAD] = 0u;
-                    // the particle's two records are written here, once (an alive one may rewrite its acceleration below)
-                    uint4* rdst = reinterpret_cast<uint4*>(rec + (size_t)k * REC_WORDS);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) rdst[c] = make_uint4(rc[l][c * 4], rc[l][c * 4 + 1], rc[l][c * 4 + 2], rc[l][c * 4 + 3]);
-                    *reinterpret_cast<uint4*>(rot + (size_t)k * ROT_WORDS) =
-                        make_uint4(__float_as_uint(sp.axis[0]), __float_as_uint(sp.axis[1]), __float_as_uint(sp.axis[2]), __float_as_uint(sp.rot_speed));
-                    if (p.genm[l])
-                    {
-                        // a mover arrives as spawned: PE.cpp:314 colour = colorStart, :317 size = sizeStart, energy undiminished
-                        p.e[l] = sp.energy;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) col_out[c][l] = sp.cs[c];
-                        size_out[l] = sp.size_start;
-                    }
-                }
-                __syncwarp(); // the slots are reused by the next l
+                for (int l = 0; l < V; ++l) load_one(pn.mover[l] ? pn.src[l] : kn + l, nxt, l);
             }
         }
 
@@ -805,12 +647,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         // -- movers that did not come through the stages: those of group 0 (requested before the prefix was known) and a
         //    thread's second mover of a group.  Their motion words came with the prefetch; the rest is fetched here, from
         //    L2 where the prefetch got there in time. --
-        if (p.any_memm)
+        if (p.any_mover)
         {
 #pragma unroll
             for (int l = 0; l < V; ++l)
             {
-                if (!p.memm[l] || fastm[l]) continue;
+                if (!p.mover[l] || fastm[l]) continue;
                 const uint32_t i = p.src[l];
                 if (!staged)
                 {
@@ -951,7 +793,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         if (p.last_examined)
         {
             d->cnt[parity ^ 1].count = p.new_count;
-            d->cnt[parity ^ 1].serial = SPAWN ? serial_out : d->cnt[parity].serial;
+            d->cnt[parity ^ 1].serial = d->cnt[parity].serial;
             if (FUSED) d->cnt[0].drawn = p.new_count;
         }
         cur = nxt;
@@ -1015,14 +857,12 @@ static bool use_ticket()
     return v == 1;
 }
 
-template <int V, int THREADS, int SUB, int MIN_BLOCKS, bool TICKET, bool FUSED, bool BOUNDS, bool SPAWN>
+template <int V, int THREADS, int SUB, int MIN_BLOCKS, bool TICKET, bool FUSED, bool BOUNDS>
 static void launch_one(cudaStream_t s, const UpdateLaunch& L)
 {
-    // life records of one group (+ the group's vertex staging) + the movers' side stage (+ the spawn slots where there is
-    // no vertex stage to borrow) + alignment slack
-    constexpr size_t smem = (size_t)THREADS * V * (REC_WORDS * 4 + (FUSED ? T3D_FLOATS_PER_QUAD * 4 : 0)) + (size_t)THREADS * 48 +
-                            ((SPAWN && !FUSED) ? (size_t)THREADS * kGenSlotWords * 4 : 0) + 128;
-    auto kernel = k_update<V, THREADS, SUB, MIN_BLOCKS, TICKET, FUSED, BOUNDS, SPAWN>;
+    // life records of one group (+ the group's vertex staging) + alignment slack
+    constexpr size_t smem = (size_t)THREADS * V * (REC_WORDS * 4 + (FUSED ? T3D_FLOATS_PER_QUAD * 4 : 0)) + (size_t)THREADS * 48 + 128;
+    auto kernel = k_update<V, THREADS, SUB, MIN_BLOCKS, TICKET, FUSED, BOUNDS>;
     // the opt-in to more than 48 KB of dynamic shared memory is per device: once for each device this process launches on
     static bool configured[kMaxDevices] = {};
     const int dev = current_device();
@@ -1035,33 +875,26 @@ static void launch_one(cudaStream_t s, const UpdateLaunch& L)
         // loudly if a change ever pushes a variant over it (the kernel would still be correct, at half the speed)
         int resident = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, THREADS, smem) == cudaSuccess && resident < MIN_BLOCKS)
-            fprintf(stderr, "t3d: k_update<%d,%d,%d,%d,fused=%d,spawn=%d>: %d resident CTA(s) per SM instead of %d (shared memory %zu B dynamic)\n", V,
-                    THREADS, SUB, MIN_BLOCKS, (int)FUSED, (int)SPAWN, resident, MIN_BLOCKS, smem);
+            fprintf(stderr, "t3d: k_update<%d,%d,%d,%d,fused=%d>: %d resident CTA(s) per SM instead of %d (shared memory %zu B dynamic)\n", V,
+                    THREADS, SUB, MIN_BLOCKS, (int)FUSED, resident, MIN_BLOCKS, smem);
     }
     kernel<<<L.total_tiles, THREADS, smem, s>>>(L.items, L.n_items, L.total_tiles, L.tile_status, L.ticket, L.ticket_base, L.epoch, L.fault, 0u,
                                                 L.ditems, L.rot_mode, L.frozen);
 }
-template <int V, int THREADS, int SUB, int MIN_BLOCKS, bool FUSED, bool SPAWN>
-static void launch_flavour(cudaStream_t s, const UpdateLaunch& L)
+template <int V, int THREADS, int SUB, int MIN_BLOCKS, bool FUSED>
+static void launch_shape(cudaStream_t s, const UpdateLaunch& L)
 {
     const bool t = use_ticket();
     if (L.bounds)
     {
-        if (t) launch_one<V, THREADS, SUB, MIN_BLOCKS, true, FUSED, true, SPAWN>(s, L);
-        else launch_one<V, THREADS, SUB, MIN_BLOCKS, false, FUSED, true, SPAWN>(s, L);
+        if (t) launch_one<V, THREADS, SUB, MIN_BLOCKS, true, FUSED, true>(s, L);
+        else launch_one<V, THREADS, SUB, MIN_BLOCKS, false, FUSED, true>(s, L);
     }
     else
     {
-        if (t) launch_one<V, THREADS, SUB, MIN_BLOCKS, true, FUSED, false, SPAWN>(s, L);
-        else launch_one<V, THREADS, SUB, MIN_BLOCKS, false, FUSED, false, SPAWN>(s, L);
+        if (t) launch_one<V, THREADS, SUB, MIN_BLOCKS, true, FUSED, false>(s, L);
+        else launch_one<V, THREADS, SUB, MIN_BLOCKS, false, FUSED, false>(s, L);
     }
-}
-template <int V, int THREADS, int SUB, int MIN_BLOCKS, bool FUSED>
-static void launch_shape(cudaStream_t s, const UpdateLaunch& L)
-{
-    // (the spawning form is a kernel of its own: launches that spawn nothing run exactly the code they ran before)
-    if (L.spawn) launch_flavour<V, THREADS, SUB, MIN_BLOCKS, FUSED, true>(s, L);
-    else launch_flavour<V, THREADS, SUB, MIN_BLOCKS, FUSED, false>(s, L);
 }
 
 struct Variant
