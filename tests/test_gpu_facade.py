@@ -219,3 +219,53 @@ def test_create_from_a_hand_built_properties_tree(tmp_path):
     finally:
         lib.t3d_properties_free(tree)
         ctx.close()
+
+
+def test_short_lived_emitters_reuse_their_storage():
+    # A game creates and destroys explosions next to long-lived emitters: the segment of a destroyed emitter goes back
+    # to its slab and is handed out again (it used to be lost until the whole slab was empty), and an emitter
+    # that lands in recycled storage starts clean -- same particles as its oracle twin.
+    import torch
+    from gpu_adapter import GpuLib
+    from tractor3d_b200 import presets
+    lib = GpuLib(rng_mode=abi.RNG_DEVICE, seed=3)
+    try:
+        keep_p, keep_sprite = presets.fire()
+        keep = lib.emitter(keep_p); keep.set_sprite_frame_coords(*keep_sprite)
+        keep.start()
+
+        def burst(k, check):
+            p, sprite = presets.explosion()
+            p.particle_count_max = 50_000
+            eg = lib.emitter(p); eg.set_sprite_frame_coords(*sprite)
+            eg.pe.set_rng(abi.RNG_DEVICE, 500 + k)
+            eg.emit_once(40_000)
+            eo = None
+            if check:
+                O = H.oracle(fresh=True)
+                eo = O.emitter(p); eo.set_sprite_frame_coords(*sprite)
+                O.emitter_set_device_rng(eo.h, 1, 500 + k)
+                eo.emit_once(40_000)
+            for _ in range(3):
+                keep.update(S.DT); keep.draw()
+                eg.update(S.DT); eg.draw()
+                if eo:
+                    eo.update(S.DT); eo.draw()
+            if eo:
+                assert eg.count() == eo.count()
+                assert np.array_equal(eg.state(), eo.state())
+                assert np.array_equal(eg.vertices().view(np.uint32), eo.vertices().view(np.uint32))
+            eg.close()
+
+        for k in range(4):
+            burst(k, check=False)        # slabs and vertex storage reach their steady size
+        lib.ctx.sync()
+        free0 = torch.cuda.mem_get_info()[0]
+        for k in range(4, 64):
+            burst(k, check=(k % 20 == 5))
+        lib.ctx.sync()
+        free1 = torch.cuda.mem_get_info()[0]
+        assert free0 - free1 < 32 * 1024 * 1024, (free0, free1)     # 60 more explosions of 7 MB each: nothing leaked
+        assert keep.count() > 0
+    finally:
+        lib.close()
