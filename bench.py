@@ -368,6 +368,7 @@ def run_cuda(args):
     nodes = np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (len(emitters), 1))
     cam = np.eye(4, dtype=np.float32).reshape(16)
     single = len(emitters) == 1
+    e2e_counts = np.zeros(len(emitters), dtype=np.uint32)
     barrier()
     h2d0, d2h0 = ctx.transfer_bytes()
     t0 = time.perf_counter()
@@ -382,14 +383,17 @@ def run_cuda(args):
             e.update(DT)
             e.draw()
             e2e_units += e.getParticlesCount()   # device -> host: live count (= quads drawn) of this frame
-        else:
+        elif churn:
             ctx.batch_set_transforms(emitters, nodes, cam, handles)
-            if churn:
-                ctx.batch_emit_once(emitters, [spawn_per_frame] * len(emitters), handles)
+            ctx.batch_emit_once(emitters, [spawn_per_frame] * len(emitters), handles)
             ctx.batch_update(emitters, DT, handles)
             ctx.batch_draw(emitters, handles)
             c = ctx.batch_counts(emitters, handles)   # device -> host: live counts of this frame
             e2e_units += int(c.sum())
+        else:
+            # what an engine's particle system calls once per frame: transforms in, update + draw, live counts out
+            ctx.batch_frame(emitters, DT, nodes, cam, handles, e2e_counts)
+            e2e_units += int(e2e_counts.sum())
     ctx.sync()
     t_e2e = time.perf_counter() - t0
     h2d1, d2h1 = ctx.transfer_bytes()
@@ -444,7 +448,8 @@ def run_cuda(args):
             "e2e": {"value": e2e_units / t_e2e, "unit": "particles/s",
                     "h2d_bytes_per_step": (h2d1 - h2d0) / e2e_steps + matrix_bytes, "d2h_bytes_per_step": (d2h1 - d2h0) / e2e_steps,
                     "steps": e2e_steps,
-                    "what": "per-emitter set_node_world/set_camera_world/update/draw calls + live counts read back every frame; "
+                    "what": "one emitter: set_node_world/set_camera_world/update/draw/getParticlesCount calls; many: t3d_batch_frame per frame "
+                            "(node and camera matrices in, update + draw, live counts read back); "
                             "the vertex stream stays in HBM for a renderer that takes the device pointer or a mapped interop "
                             "buffer (t3d_emitter_vertices / t3d_emitter_draw_to); see e2e_vertices_to_host for the host-buffer figure"},
             "e2e_vertices_to_host": e2e_v,

@@ -164,7 +164,7 @@ int t3d_ctx_reset_statics(t3d_ctx* ctx);
  * update steps under 8 ms, and the frame that latches the rotation, then depend on the split.  Off by default. */
 int t3d_ctx_set_private_statics(t3d_ctx* ctx, int on);
 /* Device time in ms of the last flushed launch of each kind (CUDA events on the context's stream):
- * which = 0 spawn, 1 update, 2 draw, 3 fused update+draw (T3D_FUSED=1).  Waits for that launch to finish. */
+ * which = 0 spawn, 1 update, 2 draw, 3 fused update+draw (the default frame).  Waits for that launch to finish. */
 int t3d_ctx_last_kernel_ms(t3d_ctx* ctx, int which, float* ms);
 /* Cumulative device time (ms) and number of launches of one kind since the context was created; every
  * launch is bracketed by its own event pair, so a caller can difference two readings around a timed region. */
@@ -254,6 +254,12 @@ int t3d_batch_get_counts(t3d_emitter* const* emitters, size_t n, uint32_t* count
 /* Per-frame scene inputs for many emitters at once: node_worlds = n x float[16] (or NULL to leave them),
  * camera_world = one float[16] shared by all (or NULL).  Same meaning as the two per-emitter setters above. */
 int t3d_batch_set_transforms(t3d_emitter* const* emitters, size_t n, const float* node_worlds, const float* camera_world);
+
+/* One frame of the game loop for many emitters in one call: t3d_batch_set_transforms, t3d_batch_update, t3d_batch_draw and
+ * -- when `counts` is not NULL -- t3d_batch_get_counts, in that order and with exactly their effects (the update and the
+ * draw go out as one fused launch).  What an engine's particle system calls once per frame. */
+int t3d_batch_frame(t3d_emitter* const* emitters, size_t n, const float* node_worlds, const float* camera_world, float elapsed_ms,
+                    uint32_t* counts);
 
 /* ---- results ------------------------------------------------------------------------------ */
 /* Device-resident vertex stream of the last draw: 4*n_quads t3d_sprite_vertex, quad i at [4i, 4i+4)

@@ -457,6 +457,22 @@ def test_batch_of_mixed_emitters_one_launch_per_phase():
             assert counts[k] == eo.count(), f"emitter {k}"
             assert np.array_equal(eg.state(), eo.state()), f"emitter {k}"
             assert np.array_equal(eg.vertices().view(np.uint32), eo.vertices().view(np.uint32)), f"emitter {k}"
+        # the same frames through the one-call-per-frame entry point (t3d_batch_frame): moving nodes, a tilted camera, the
+        # live counts back every frame
+        cam = S.rot_xyz(0.1, -0.4, 0.05, (0.5, 2.0, 14.0)).astype(np.float32)
+        nodes = np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (len(pes), 1))
+        got = np.zeros(len(pes), dtype=np.uint32)
+        for f in range(25):
+            nodes[:, 12] = np.float32(0.01) * np.float32(f)
+            nodes[:, 13] = np.arange(len(pes), dtype=np.float32) * np.float32(0.125)
+            lib.ctx.batch_frame(pes, S.DT, nodes, cam, counts_out=got)
+            for k, (_, eo) in enumerate(twins):
+                eo.set_node_world(nodes[k]); eo.set_camera_world(cam)
+                eo.update(S.DT); eo.draw()
+            assert got.tolist() == [eo.count() for _, eo in twins], f"frame {f}"
+        for k, (eg, eo) in enumerate(twins):
+            assert np.array_equal(eg.state(), eo.state()), f"emitter {k}"
+            assert np.array_equal(eg.vertices().view(np.uint32), eo.vertices().view(np.uint32)), f"emitter {k}"
     finally:
         lib.close()
 

@@ -186,6 +186,7 @@ PROTOTYPES = {
     "t3d_batch_draw": (C.c_int, [_P(_vp), C.c_size_t]),
     "t3d_batch_emit_once": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_uint32)]),
     "t3d_batch_get_counts": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_uint32)]),
+    "t3d_batch_frame": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_float), _P(C.c_float), C.c_float, _P(C.c_uint32)]),
     "t3d_batch_set_transforms": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_float), _P(C.c_float)]),
     "t3d_emitter_vertices": (C.c_int, [_vp, _P(_vp), _P(C.c_uint32)]),
     "t3d_emitter_depth_sorted_indices": (C.c_int, [_vp, _P(C.c_float), _P(_vp), _P(C.c_uint64)]),

@@ -2243,6 +2243,16 @@ int t3d_batch_set_transforms(t3d_emitter* const* es, size_t n, const float* node
     return T3D_OK;
 }
 
+int t3d_batch_frame(t3d_emitter* const* es, size_t n, const float* node_worlds, const float* camera_world, float elapsed_ms, uint32_t* counts)
+{
+    if (!es && n) return fail(T3D_ERR_INVALID, "null argument");
+    if (node_worlds || camera_world) T3D_TRY(t3d_batch_set_transforms(es, n, node_worlds, camera_world));
+    T3D_TRY(t3d_batch_update(es, n, elapsed_ms));
+    T3D_TRY(t3d_batch_draw(es, n));
+    if (counts) return t3d_batch_get_counts(es, n, counts);
+    return T3D_OK;
+}
+
 // ---- results ----
 int t3d_emitter_vertices(t3d_emitter* e, const t3d_sprite_vertex** device_ptr, uint32_t* n_quads)
 {

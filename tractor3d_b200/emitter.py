@@ -185,6 +185,16 @@ class Context:
         _check(self.lib, self.lib.t3d_batch_set_transforms(h, len(h), _fptr(nw) if nw is not None else None,
                                                            _fptr(cw) if cw is not None else None))
 
+    def batch_frame(self, emitters, elapsed_ms, node_worlds=None, camera_world=None, handles=None, counts_out=None):
+        """One frame for many emitters in one call (t3d_batch_frame): transforms in, update + draw, and -- when counts_out
+        (a uint32 array of len(emitters)) is given -- the live counts back.  node_worlds / camera_world must already be
+        contiguous float32 arrays (no conversion here: this is the per-frame call)."""
+        h = handles if handles is not None else self._handles(emitters)
+        _check(self.lib, self.lib.t3d_batch_frame(h, len(h), _fptr(node_worlds) if node_worlds is not None else None,
+                                                  _fptr(camera_world) if camera_world is not None else None, elapsed_ms,
+                                                  counts_out.ctypes.data_as(_P(C.c_uint32)) if counts_out is not None else None))
+        return counts_out
+
     def batch_counts(self, emitters, handles=None):
         h = handles if handles is not None else self._handles(emitters)
         out = np.zeros(len(h), dtype=np.uint32)
