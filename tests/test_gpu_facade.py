@@ -233,6 +233,10 @@ def test_short_lived_emitters_reuse_their_storage():
         keep_p, keep_sprite = presets.fire()
         keep = lib.emitter(keep_p); keep.set_sprite_frame_coords(*keep_sprite)
         keep.start()
+        # (the billboard rotation is latched once per process from the first rotated quad: give the long-running context
+        #  and every fresh oracle the same one, so that the vertex streams are comparable)
+        axis, angle = np.array([0.0, 0.0, 1.0], dtype=np.float32), 0.3
+        lib.ctx.set_frozen_rotation(axis, angle)
 
         def burst(k, check):
             p, sprite = presets.explosion()
@@ -243,6 +247,7 @@ def test_short_lived_emitters_reuse_their_storage():
             eo = None
             if check:
                 O = H.oracle(fresh=True)
+                O.set_frozen_rotation(axis.ctypes.data_as(C.POINTER(C.c_float)), angle)
                 eo = O.emitter(p); eo.set_sprite_frame_coords(*sprite)
                 O.emitter_set_device_rng(eo.h, 1, 500 + k)
                 eo.emit_once(40_000)

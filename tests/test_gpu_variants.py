@@ -13,7 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 CASES = [
     {"T3D_UPDATE_VARIANT": "u2t256s8b2"},
-    {"T3D_UPDATE_VARIANT": "u2t128s12b4", "T3D_UPDATE_TICKET": "1"},
+    {"T3D_UPDATE_VARIANT": "u2t192s12b2", "T3D_UPDATE_TICKET": "1"},
+    {"T3D_FUSED": "0", "T3D_UPDATE_TICKET": "1"},
     {"T3D_UPDATE_VARIANT": "u4t128s8b2"},
     {"T3D_DRAW_VARIANT": "lsu"},
     {"T3D_FUSED": "0"},

@@ -906,9 +906,11 @@ struct Variant
 #define T3D_UPDATE_SHAPE(V, T, S, B) { "u" #V "t" #T "s" #S "b" #B, V * T * S, launch_shape<V, T, S, B, false> }
 #define T3D_FUSED_SHAPE(V, T, S, B) { "f" #V "t" #T "s" #S "b" #B, V * T * S, launch_shape<V, T, S, B, true> }
 static const Variant kUpdate[] = {
-    // default: 2 particles per thread x 192 threads x 12 groups = 4 608-particle tiles
-    T3D_UPDATE_SHAPE(2, 192, 12, 2),
-    T3D_UPDATE_SHAPE(2, 256, 8, 2), T3D_UPDATE_SHAPE(2, 128, 12, 4), T3D_UPDATE_SHAPE(4, 128, 8, 2),
+    // default: 2 particles per thread x 128 threads x 12 groups = 3 072-particle tiles, 4 CTAs per SM.  Without the vertex
+    // stage the kernel needs little shared memory, and four small CTAs overlap each other's tile prologues better than two
+    // large ones: 0.90 of the HBM peak on C3 against 0.88 for 192 threads x 2 CTAs (profiles/r2_update_alone_variants.txt)
+    T3D_UPDATE_SHAPE(2, 128, 12, 4),
+    T3D_UPDATE_SHAPE(2, 192, 12, 2), T3D_UPDATE_SHAPE(2, 256, 8, 2), T3D_UPDATE_SHAPE(4, 128, 8, 2),
 };
 static const Variant kFused[] = {
     // default: 2 particles per thread, 192 threads x 12 groups = 4 608-particle tiles, 2 CTAs/SM
@@ -933,7 +935,7 @@ static const Variant& fused_variant() { return pick(kFused, "T3D_FUSED_VARIANT",
 // A launch that is only a few waves of CTAs wide loses the idle part of its last wave; with half-size tiles the tail is
 // half as long (at ~3 % more per-tile overhead).  shape 0 = the variant above, shape 1 = its half-size sibling; only the
 // default variant has one (an explicit T3D_*_VARIANT is taken as is).
-static const Variant kUpdateSmall = T3D_UPDATE_SHAPE(2, 192, 6, 2);
+static const Variant kUpdateSmall = T3D_UPDATE_SHAPE(2, 128, 6, 4);
 static const Variant kFusedSmall = T3D_FUSED_SHAPE(2, 192, 6, 2);
 static const Variant& shaped(const Variant& v, const Variant* table, const Variant& small_one, int shape)
 {
