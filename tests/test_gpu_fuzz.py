@@ -1,5 +1,5 @@
 """Randomised API sequences: several emitters with random parameter sets are driven through random interleavings of
-emitOnce / update / draw / start / stop / setters / node moves, on the GPU (through the C ABI) and on the oracle, and
+emitOnce / update / draw / start / stop / setters / node and camera moves / capacity changes, on the GPU (through the C ABI) and on the oracle, and
 must agree at every checkpoint.  Exercises what the scripted scenarios do not: the command queue (phase changes,
 flushes forced mid-phase), the parity bookkeeping of the live counts, count feedback, the shared rate-cap accumulator
 with several emitters and dt < 8 ms, capacity clamping in the kernel, parameter changes between frames."""
@@ -56,6 +56,7 @@ def test_random_api_sequences(seed, rotate):
             O.emitter_set_device_rng(eo.h, 1, 7000 + k)
             eg.pe.set_rng(abi.RNG_DEVICE, 7000 + k)
             pairs.append((eo, eg, p))
+        caps = [int(p.particle_count_max) for _, _, p in pairs]
         cam = S.rot_xyz(0.3, -0.2, 0.1, (1, 2, 9))
         for eo, eg, _ in pairs:
             eo.set_camera_world(cam); eg.set_camera_world(cam)
@@ -75,7 +76,8 @@ def test_random_api_sequences(seed, rotate):
 
         drawn = False
         for step in range(160):
-            op = rng.choice(["update", "update", "update", "draw", "emit", "start", "stop", "rate", "node", "params", "count", "dt_small"])
+            op = rng.choice(["update", "update", "update", "draw", "emit", "start", "stop", "rate", "node", "params", "count", "dt_small",
+                             "camera", "cap", "frame"])
             k = int(rng.integers(0, len(pairs)))
             eo, eg, p = pairs[k]
             if op == "update":
@@ -113,6 +115,31 @@ def test_random_api_sequences(seed, rotate):
                 pairs[k] = (eo, eg, q)
             elif op == "count":
                 assert eg.count() == eo.count()
+            elif op == "camera":
+                # the camera moves between calls (possibly between an update and the draw behind it)
+                cam = S.rot_xyz(*rng.uniform(-0.5, 0.5, 3), tuple(rng.uniform(-2, 12, 3)))
+                for a, b, _ in pairs:
+                    a.set_camera_world(cam); b.set_camera_world(cam)
+            elif op == "cap":
+                # setParticleCountMax (PE.h:237): anywhere between the live count and the size the storage was created with
+                alloc = caps[k]
+                n_live = eo.count()
+                assert eg.count() == n_live
+                q = p.copy()
+                q.particle_count_max = int(rng.integers(max(n_live, 1), alloc + 1))
+                eo.set_params(q); eg.set_params(q)
+                pairs[k] = (eo, eg, q)
+            elif op == "frame":
+                # one whole game-loop frame on every emitter, and the vertices of one of them checked right away
+                dt = float(rng.choice([16.6667, 20.0]))
+                for a, b, _ in pairs:
+                    a.update(dt); b.update(dt)
+                for a, b, _ in pairs:
+                    assert a.draw() == b.draw()
+                drawn = True
+                va, vb = eg.vertices(), eo.vertices()
+                assert va.shape == vb.shape
+                assert np.allclose(va, vb, rtol=1e-5, atol=1e-6) if rotate else np.array_equal(va.view(np.uint32), vb.view(np.uint32))
             if step % 40 == 39:
                 check(full=True)
         check(full=True)
