@@ -1,0 +1,59 @@
+"""Generates tests/golden/sprites/*.npz from the UNMODIFIED reference (oracle/_ref/libt3dref.so): the vertex streams its
+own SpriteBatch.cpp / TileSet.cpp produce for a list of 2-D sprites (every overload: plain, centred, rotated, clipped)
+and for a tile set with blank cells.  Run here, where /root/reference exists and `make -C oracle ref` has been done:
+    python tests/golden/make_golden_sprites.py
+The fixtures travel to machines without the reference (the GPU box)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import cpu_harness as H  # noqa: E402
+
+fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def main():
+    assert H.ref_available(), "build oracle/_ref first: make -C oracle ref"
+    R = H.ref(fresh=True)
+    out_dir = os.path.join(HERE, "sprites")
+    os.makedirs(out_dir, exist_ok=True)
+
+    n = 3000
+    sp = H.random_sprites(n, seed=2026)
+    verts = np.zeros((n, 36), dtype=np.float32)
+    quads = R.sprites_2d(sp.ctypes.data, n, 512, 256, fp(verts), n, None)
+    np.savez_compressed(os.path.join(out_dir, "sprites_2d.npz"), sprites=sp.view(np.uint32).reshape(n, -1), texture=np.array([512, 256]),
+                        vertices=verts[:quads].view(np.uint32))
+    print(f"sprites_2d: {n} sprites -> {quads} quads")
+
+    rows, cols, tw, th = 37, 53, 33.3, 17.7
+    rng = np.random.default_rng(7)
+    src = np.zeros((rows, cols, 2), dtype=np.float32)
+    src[..., 0] = rng.integers(0, 8, (rows, cols)) * 32.0
+    src[..., 1] = rng.integers(0, 4, (rows, cols)) * 32.0
+    src[rng.random((rows, cols)) < 0.25] = -1.0
+    h = R.tileset_create(256, 128, tw, th, rows, cols)
+    for r in range(rows):
+        for c in range(cols):
+            if src[r, c, 0] >= 0:
+                R.tileset_set_tile_source(h, c, r, float(src[r, c, 0]), float(src[r, c, 1]))
+    node = np.array([12.25, -3.5, 0.75], dtype=np.float32)
+    cam = np.array([100.1, 50.7, 9.0], dtype=np.float32)
+    color = np.array([0.9, 0.8, 0.7, 0.6], dtype=np.float32)
+    opacity = np.float32(0.35)
+    verts = np.zeros((rows * cols, 36), dtype=np.float32)
+    quads = R.tileset_draw(h, fp(node), fp(cam), fp(color), opacity, fp(verts), rows * cols)
+    R.tileset_destroy(h)
+    np.savez_compressed(os.path.join(out_dir, "tileset.npz"), sources=src, tile=np.array([tw, th], dtype=np.float32), texture=np.array([256, 128]),
+                        node=node, camera=cam, color=color, opacity=opacity, vertices=verts[:quads].view(np.uint32))
+    print(f"tileset: {rows} x {cols} cells -> {quads} quads")
+
+
+if __name__ == "__main__":
+    main()

@@ -33,3 +33,41 @@ def test_golden_covers_the_edge_cases():
     g = G.load("burst_extinction")
     counts = [s["count"] for s in g["snaps"]]
     assert counts[0] == g["params"].particle_count_max and counts[-1] < 50 and sorted(counts, reverse=True) == counts
+
+
+# ---- 2-D sprites and tile sets, fixtures from the reference's own SpriteBatch.cpp / TileSet.cpp ----
+def _sprite_fixture(name):
+    import os
+    return np.load(os.path.join(G.GOLDEN_DIR, "sprites", name + ".npz"))
+
+
+def tileset_inputs(z):
+    """What TileSet::draw has made of node and camera translation by TileSet.cpp:205 and of colour and opacity at :226."""
+    node, cam, color = z["node"], z["camera"], z["color"]
+    pos = np.array([np.float32(0) - cam[0] + node[0], np.float32(0) - cam[1] + node[1], np.float32(0) + node[2]], dtype=np.float32)
+    col = color.copy()
+    col[3] = color[3] * z["opacity"]
+    return pos, col
+
+
+def test_oracle_reproduces_reference_golden_sprites():
+    import ctypes as C
+    from tractor3d_b200 import abi
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    O = H.oracle(fresh=True)
+    z = _sprite_fixture("sprites_2d")
+    sp = np.ascontiguousarray(z["sprites"]).view(abi.SPRITE2D_DTYPE).reshape(-1)
+    want = z["vertices"]
+    got = np.zeros((sp.size, 36), dtype=np.float32)
+    n = O.sprites_2d(sp.ctypes.data, sp.size, fp(got), sp.size)
+    assert n == want.shape[0] < sp.size
+    assert np.array_equal(got[:n].view(np.uint32), want)
+    z = _sprite_fixture("tileset")
+    src = np.ascontiguousarray(z["sources"])
+    rows, cols = src.shape[:2]
+    pos, col = tileset_inputs(z)
+    got = np.zeros((rows * cols, 36), dtype=np.float32)
+    n = O.tileset_draw(fp(src), rows, cols, float(z["tile"][0]), float(z["tile"][1]), float(z["texture"][0]), float(z["texture"][1]),
+                       fp(pos), fp(col), fp(got), rows * cols)
+    assert n == z["vertices"].shape[0] == int((src[..., 0] >= 0).sum())
+    assert np.array_equal(got[:n].view(np.uint32), z["vertices"])

@@ -136,3 +136,30 @@ def test_tileset_draw_matches_the_oracle(rows, cols, tw, th):
         ts.release()
     finally:
         ctx.close()
+
+
+def test_sprites_and_tiles_against_the_reference_fixtures():
+    # the committed vectors the reference's own SpriteBatch.cpp / TileSet.cpp produced (tests/golden/make_golden_sprites.py)
+    import os
+    import golden_io as G
+    from test_golden import tileset_inputs
+    ctx = Context(0)
+    try:
+        z = np.load(os.path.join(G.GOLDEN_DIR, "sprites", "sprites_2d.npz"))
+        sp = np.ascontiguousarray(z["sprites"]).view(abi.SPRITE2D_DTYPE).reshape(-1)
+        want = z["vertices"].view(np.float32).reshape(-1, 4, 9)
+        ptr, nq = ctx.draw_sprites(sp)
+        assert nq == want.shape[0]
+        _compare(ctx.download_quads(ptr, nq), want, True)
+        z = np.load(os.path.join(G.GOLDEN_DIR, "sprites", "tileset.npz"))
+        src = np.ascontiguousarray(z["sources"])
+        rows, cols = src.shape[:2]
+        ts = TileSet(ctx, int(z["texture"][0]), int(z["texture"][1]), float(z["tile"][0]), float(z["tile"][1]), rows, cols)
+        ts.set_tiles(src)
+        pos, col = tileset_inputs(z)
+        ptr, nq = ts.draw(pos, col)
+        assert nq == z["vertices"].shape[0]
+        assert np.array_equal(ctx.download_quads(ptr, nq).view(np.uint32).reshape(nq, 36), z["vertices"])
+        ts.release()
+    finally:
+        ctx.close()
