@@ -369,34 +369,47 @@ def run_cuda(args):
     cam = np.eye(4, dtype=np.float32).reshape(16)
     single = len(emitters) == 1
     e2e_counts = np.zeros(len(emitters), dtype=np.uint32)
-    barrier()
-    h2d0, d2h0 = ctx.transfer_bytes()
-    t0 = time.perf_counter()
-    e2e_units = 0
-    for s in range(e2e_steps):
-        nodes[:, 12] = 0.001 * s
-        if single:
-            # exactly the calls a game makes on one emitter (ParticlesSample.cpp:897-898, 916-921)
-            e = emitters[0]
-            e.set_node_world(nodes[0])  # host -> library, every frame (Node::getWorldMatrix, PE.cpp:299)
-            e.set_camera_world(cam)     # (camera node world matrix, PE.cpp:860-861)
-            e.update(DT)
-            e.draw()
-            e2e_units += e.getParticlesCount()   # device -> host: live count (= quads drawn) of this frame
-        elif churn:
-            ctx.batch_set_transforms(emitters, nodes, cam, handles)
-            ctx.batch_emit_once(emitters, [spawn_per_frame] * len(emitters), handles)
-            ctx.batch_update(emitters, DT, handles)
-            ctx.batch_draw(emitters, handles)
-            c = ctx.batch_counts(emitters, handles)   # device -> host: live counts of this frame
-            e2e_units += int(c.sum())
-        else:
-            # what an engine's particle system calls once per frame: transforms in, update + draw, live counts out
-            ctx.batch_frame(emitters, DT, nodes, cam, handles, e2e_counts)
-            e2e_units += int(e2e_counts.sum())
-    ctx.sync()
-    t_e2e = time.perf_counter() - t0
-    h2d1, d2h1 = ctx.transfer_bytes()
+
+    def e2e_run(pipelined):
+        barrier()
+        b0 = ctx.transfer_bytes()
+        t0 = time.perf_counter()
+        units = 0
+        for s in range(e2e_steps):
+            nodes[:, 12] = 0.001 * s
+            if single:
+                # exactly the calls a game makes on one emitter (ParticlesSample.cpp:897-898, 916-921)
+                e = emitters[0]
+                e.set_node_world(nodes[0])  # host -> library, every frame (Node::getWorldMatrix, PE.cpp:299)
+                e.set_camera_world(cam)     # (camera node world matrix, PE.cpp:860-861)
+                e.update(DT)
+                e.draw()
+                units += e.getParticlesCount()   # device -> host: live count (= quads drawn) of this frame
+                continue
+            # what an engine's particle system calls once per frame: transforms in, (spawns,) update + draw, live counts out
+            if churn:
+                ctx.batch_set_transforms(emitters, nodes, cam, handles)
+                ctx.batch_emit_once(emitters, [spawn_per_frame] * len(emitters), handles)
+            nw, cw = (None, None) if churn else (nodes, cam)
+            if pipelined:
+                # the counts of frame s - 1 arrive with call s: the host never waits for the frame it has just enqueued
+                if ctx.batch_frame_pipelined(emitters, DT, nw, cw, handles, e2e_counts):
+                    units += int(e2e_counts.sum())
+            else:
+                ctx.batch_frame(emitters, DT, nw, cw, handles, e2e_counts)
+                units += int(e2e_counts.sum())
+        if pipelined and not single:
+            units += int(ctx.batch_counts(emitters, handles).sum())   # the last frame's counts (waits for it)
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        b1 = ctx.transfer_bytes()
+        return units, dt, (b1[0] - b0[0]) / e2e_steps, (b1[1] - b0[1]) / e2e_steps
+
+    e2e_blocking = None
+    if not single:
+        u, t, _, _ = e2e_run(False)
+        e2e_blocking = (u, t)
+    e2e_units, t_e2e, h2d_step, d2h_step = e2e_run(True)
     matrix_bytes = 2 * 64 * len(emitters)   # the two float[16] the caller hands over per emitter per frame
 
     # ---- e2e with the vertex stream delivered to pinned HOST memory every frame: what a renderer that submits from client
@@ -409,9 +422,9 @@ def run_cuda(args):
 
     # ---- reduce over ranks: max time, sum of work (the only collective, after the run) ----
     from tractor3d_b200 import sharding
-    mx, sm = sharding.reduce_stats({"ms_total": ms_total, "t_e2e": t_e2e},
+    mx, sm = sharding.reduce_stats({"ms_total": ms_total, "t_e2e": t_e2e, "t_e2e_blocking": e2e_blocking[1] if e2e_blocking else 0.0},
                                    {"updates": updates_done, "e2e_units": e2e_units, "particles": local_particles,
-                                    "live": live_after, "launches": launches})
+                                    "live": live_after, "launches": launches, "e2e_blocking_units": e2e_blocking[0] if e2e_blocking else 0})
     ms_total, t_e2e = mx["ms_total"], mx["t_e2e"]
     updates_done, e2e_units, total_particles, live_after, launches = sm["updates"], sm["e2e_units"], sm["particles"], sm["live"], sm["launches"]
 
@@ -446,10 +459,14 @@ def run_cuda(args):
             "roofline": roof.get(dominant), "roofline_dominant_kernel": dominant, "rooflines": roof,
             "kernels": kern, "gpu_launches": launches,
             "e2e": {"value": e2e_units / t_e2e, "unit": "particles/s",
-                    "h2d_bytes_per_step": (h2d1 - h2d0) / e2e_steps + matrix_bytes, "d2h_bytes_per_step": (d2h1 - d2h0) / e2e_steps,
+                    "h2d_bytes_per_step": h2d_step + matrix_bytes, "d2h_bytes_per_step": d2h_step,
                     "steps": e2e_steps,
-                    "what": "one emitter: set_node_world/set_camera_world/update/draw/getParticlesCount calls; many: t3d_batch_frame per frame "
-                            "(node and camera matrices in, update + draw, live counts read back); "
+                    "blocking_counts": (sm["e2e_blocking_units"] / mx["t_e2e_blocking"]) if mx["t_e2e_blocking"] > 0 else None,
+                    "what": "one emitter: set_node_world/set_camera_world/update/draw/getParticlesCount calls, the count read back before the "
+                            "next frame is issued; many emitters: t3d_batch_frame_pipelined per frame (node and camera matrices in, update + "
+                            "draw, the live counts of every frame read back -- call k hands over those of frame k - 1, so the host prepares "
+                            "frame k + 1 while frame k runs; blocking_counts = the same with t3d_batch_frame, which waits for its own "
+                            "frame's counts); "
                             "the vertex stream stays in HBM for a renderer that takes the device pointer or a mapped interop "
                             "buffer (t3d_emitter_vertices / t3d_emitter_draw_to); see e2e_vertices_to_host for the host-buffer figure"},
             "e2e_vertices_to_host": e2e_v,

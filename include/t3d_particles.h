@@ -261,6 +261,16 @@ int t3d_batch_set_transforms(t3d_emitter* const* emitters, size_t n, const float
 int t3d_batch_frame(t3d_emitter* const* emitters, size_t n, const float* node_worlds, const float* camera_world, float elapsed_ms,
                     uint32_t* counts);
 
+/* The same frame without the wait: the call returns as soon as the frame is enqueued, and `previous_counts` (n words, or NULL)
+ * receives the live counts that the PREVIOUS call of this function left for the same emitters -- their read-back travelled
+ * while this frame was being prepared, so the host never idles the device.  `*have_previous` is 0 when there is no such frame
+ * (first call, another emitter set, or a frame whose update the 8 ms rate cap of PE.cpp:720-725 swallowed) and
+ * `previous_counts` is then left untouched.  State, vertices and the order of effects are exactly t3d_batch_frame's; only the
+ * counts reach the caller one frame later (ParticleEmitter::getParticlesCount, PE.h:306, stays exact through
+ * t3d_emitter_get_count / t3d_batch_get_counts at any time). */
+int t3d_batch_frame_pipelined(t3d_emitter* const* emitters, size_t n, const float* node_worlds, const float* camera_world,
+                              float elapsed_ms, uint32_t* previous_counts, int* have_previous);
+
 /* ---- results ------------------------------------------------------------------------------ */
 /* Device-resident vertex stream of the last draw: 4*n_quads t3d_sprite_vertex, quad i at [4i, 4i+4)
  * in live-array order (what SpriteBatch::draw appended to MeshBatch, SB.cpp:355-362).  Flushes and

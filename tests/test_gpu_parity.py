@@ -473,6 +473,26 @@ def test_batch_of_mixed_emitters_one_launch_per_phase():
         for k, (eg, eo) in enumerate(twins):
             assert np.array_equal(eg.state(), eo.state()), f"emitter {k}"
             assert np.array_equal(eg.vertices().view(np.uint32), eo.vertices().view(np.uint32)), f"emitter {k}"
+        # ... and without the wait (t3d_batch_frame_pipelined): the same frames, the counts of frame f - 1 handed over by call f
+        expected_prev = None
+        for f in range(25, 45):
+            nodes[:, 12] = np.float32(0.01) * np.float32(f)
+            have = lib.ctx.batch_frame_pipelined(pes, S.DT, nodes, cam, previous_counts=got)
+            assert have == (expected_prev is not None), f"frame {f}"
+            if have:
+                assert got.tolist() == expected_prev, f"frame {f}"
+            for k, (_, eo) in enumerate(twins):
+                eo.set_node_world(nodes[k]); eo.set_camera_world(cam)
+                eo.update(S.DT); eo.draw()
+            expected_prev = [eo.count() for _, eo in twins]
+        assert lib.ctx.batch_counts(pes).tolist() == expected_prev      # the exact count is still there for the asking
+        assert not lib.ctx.batch_frame_pipelined(pes[:5], S.DT, nodes[:5], cam, previous_counts=got[:5])   # another emitter set: no previous frame
+        for k, (_, eo) in enumerate(twins[:5]):
+            eo.set_node_world(nodes[k]); eo.set_camera_world(cam)
+            eo.update(S.DT); eo.draw()
+        for k, (eg, eo) in enumerate(twins):
+            assert np.array_equal(eg.state(), eo.state()), f"emitter {k}"
+            assert np.array_equal(eg.vertices().view(np.uint32), eo.vertices().view(np.uint32)), f"emitter {k}"
     finally:
         lib.close()
 

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libt3d_particles.so")
+# T3D_LIBRARY: another build of the same library (experiments: scripts/gpu/knobs.sh); the product is the in-tree file
+LIB_PATH = os.environ.get("T3D_LIBRARY") or os.path.join(HERE, "csrc", "libt3d_particles.so")
 
 # t3d_status
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_RNG_UNDERFLOW, ERR_IO, ERR_NO_NODE, ERR_INTERNAL = range(8)
@@ -187,6 +188,7 @@ PROTOTYPES = {
     "t3d_batch_emit_once": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_uint32)]),
     "t3d_batch_get_counts": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_uint32)]),
     "t3d_batch_frame": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_float), _P(C.c_float), C.c_float, _P(C.c_uint32)]),
+    "t3d_batch_frame_pipelined": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_float), _P(C.c_float), C.c_float, _P(C.c_uint32), _P(C.c_int)]),
     "t3d_batch_set_transforms": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_float), _P(C.c_float)]),
     "t3d_emitter_vertices": (C.c_int, [_vp, _P(_vp), _P(C.c_uint32)]),
     "t3d_emitter_depth_sorted_indices": (C.c_int, [_vp, _P(C.c_float), _P(_vp), _P(C.c_uint64)]),

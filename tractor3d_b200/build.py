@@ -55,6 +55,21 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_variant(name, defines):
+    """Another build of the library with extra -D switches (experiments): csrc/_build/libt3d_particles_<name>.so, selected at
+    run time with T3D_LIBRARY=<path>."""
+    nvcc = find_nvcc()
+    out_dir = os.path.join(CSRC, "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"libt3d_particles_{name}.so")
+    cmd = [nvcc] + [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-D" + d for d in defines] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError(f"nvcc failed building variant {name}")
+    return out
+
+
 def build_facade_driver():
     """Compiles the C++ ParticleEmitter facade (tractor3d_b200/host) together with tests/facade_driver.cpp against
     the library; proves the host-side mirror of the reference interface builds and links."""

@@ -287,7 +287,66 @@ __device__ __forceinline__ SpawnedParticle spawn_particle(const SpawnParams& P, 
     return o;
 }
 
-// V x 32-bit streaming accesses (evict-first: every byte of the particle state is touched once per frame).
+// Cache hints of the streaming accesses.  Stores are evict-first (st.global.cs: every byte is written once per frame); loads are
+// plain: evict-first loads (ld.global.cs) measured 0.7 % slower with nothing replaced per frame and 2-4 % slower under churn,
+// where they push the movers' sectors out of L2 before their neighbours are asked for (profiles/r2_cache_hints.txt).  The
+// -DT3D_EXP_* switches build the library with other choices (experiments, scripts/gpu/knobs.sh).
+#if defined(T3D_EXP_ST_PLAIN)
+#define T3D_STCS(p, v) (*(p) = (v))
+#elif defined(T3D_EXP_ST_WT)
+#define T3D_STCS(p, v) __stwt((p), (v))
+#else
+#define T3D_STCS(p, v) __stcs((p), (v))
+#endif
+#if defined(T3D_EXP_LD_QUAL) // a PTX load with the given qualifiers, e.g. -DT3D_EXP_LD_QUAL="ld.global.L2::256B"
+__device__ __forceinline__ uint4 ldq_raw(const uint4* p)
+{
+    uint4 v;
+    asm volatile(T3D_EXP_LD_QUAL ".v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(__cvta_generic_to_global(p)));
+    return v;
+}
+__device__ __forceinline__ uint2 ldq_raw(const uint2* p)
+{
+    uint2 v;
+    asm volatile(T3D_EXP_LD_QUAL ".v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(__cvta_generic_to_global(p)));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldq_raw(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile(T3D_EXP_LD_QUAL ".u32 %0, [%1];" : "=r"(v) : "l"(__cvta_generic_to_global(p)));
+    return v;
+}
+__device__ __forceinline__ float4 ldq(const float4* p)
+{
+    const uint4 v = ldq_raw(reinterpret_cast<const uint4*>(p));
+    return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+__device__ __forceinline__ int4 ldq(const int4* p)
+{
+    const uint4 v = ldq_raw(reinterpret_cast<const uint4*>(p));
+    return make_int4((int)v.x, (int)v.y, (int)v.z, (int)v.w);
+}
+__device__ __forceinline__ float2 ldq(const float2* p)
+{
+    const uint2 v = ldq_raw(reinterpret_cast<const uint2*>(p));
+    return make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
+}
+__device__ __forceinline__ int2 ldq(const int2* p)
+{
+    const uint2 v = ldq_raw(reinterpret_cast<const uint2*>(p));
+    return make_int2((int)v.x, (int)v.y);
+}
+__device__ __forceinline__ uint32_t ldq(const uint32_t* p) { return ldq_raw(p); }
+#define T3D_LDCS(p) ldq(p)
+#elif defined(T3D_EXP_LD_CS)
+#define T3D_LDCS(p) __ldcs(p)
+#elif defined(T3D_EXP_LD_CG)
+#define T3D_LDCS(p) __ldcg(p)
+#else
+#define T3D_LDCS(p) (*(p))
+#endif
+// V x 32-bit streaming accesses.
 template <int V>
 struct Vec;
 template <>
@@ -295,21 +354,21 @@ struct Vec<4>
 {
     static __device__ __forceinline__ void ld(const uint32_t* p, float* a)
     {
-        const float4 v = __ldcs(reinterpret_cast<const float4*>(p));
+        const float4 v = T3D_LDCS(reinterpret_cast<const float4*>(p));
         a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
     }
     static __device__ __forceinline__ void ld(const uint32_t* p, int* a)
     {
-        const int4 v = __ldcs(reinterpret_cast<const int4*>(p));
+        const int4 v = T3D_LDCS(reinterpret_cast<const int4*>(p));
         a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
     }
     static __device__ __forceinline__ void st(uint32_t* p, const float* a)
     {
-        __stcs(reinterpret_cast<float4*>(p), make_float4(a[0], a[1], a[2], a[3]));
+        T3D_STCS(reinterpret_cast<float4*>(p), make_float4(a[0], a[1], a[2], a[3]));
     }
     static __device__ __forceinline__ void st(uint32_t* p, const int* a)
     {
-        __stcs(reinterpret_cast<int4*>(p), make_int4(a[0], a[1], a[2], a[3]));
+        T3D_STCS(reinterpret_cast<int4*>(p), make_int4(a[0], a[1], a[2], a[3]));
     }
 };
 template <>
@@ -317,25 +376,29 @@ struct Vec<2>
 {
     static __device__ __forceinline__ void ld(const uint32_t* p, float* a)
     {
-        const float2 v = __ldcs(reinterpret_cast<const float2*>(p));
+        const float2 v = T3D_LDCS(reinterpret_cast<const float2*>(p));
         a[0] = v.x; a[1] = v.y;
     }
     static __device__ __forceinline__ void ld(const uint32_t* p, int* a)
     {
-        const int2 v = __ldcs(reinterpret_cast<const int2*>(p));
+        const int2 v = T3D_LDCS(reinterpret_cast<const int2*>(p));
         a[0] = v.x; a[1] = v.y;
     }
-    static __device__ __forceinline__ void st(uint32_t* p, const float* a) { __stcs(reinterpret_cast<float2*>(p), make_float2(a[0], a[1])); }
-    static __device__ __forceinline__ void st(uint32_t* p, const int* a) { __stcs(reinterpret_cast<int2*>(p), make_int2(a[0], a[1])); }
+    static __device__ __forceinline__ void st(uint32_t* p, const float* a) { T3D_STCS(reinterpret_cast<float2*>(p), make_float2(a[0], a[1])); }
+    static __device__ __forceinline__ void st(uint32_t* p, const int* a) { T3D_STCS(reinterpret_cast<int2*>(p), make_int2(a[0], a[1])); }
 };
-__device__ __forceinline__ float ld_f(const uint32_t* p) { return __uint_as_float(__ldcs(p)); }
-__device__ __forceinline__ int ld_i(const uint32_t* p) { return (int)__ldcs(p); }
+__device__ __forceinline__ float ld_f(const uint32_t* p) { return __uint_as_float(T3D_LDCS(p)); }
+__device__ __forceinline__ int ld_i(const uint32_t* p) { return (int)T3D_LDCS(p); }
 
 // ---- asynchronous copies -------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
 {
     const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+#if defined(T3D_EXP_CPA_QUAL) // e.g. -DT3D_EXP_CPA_QUAL="cp.async.cg.shared.global.L2::256B"
+    asm volatile(T3D_EXP_CPA_QUAL " [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>

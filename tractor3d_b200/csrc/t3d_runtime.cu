@@ -198,9 +198,12 @@ struct t3d_ctx
         size_t cap{ 0 };
         cudaEvent_t done{ nullptr };
         bool in_flight{ false };
+        uint64_t serial{ 0 };               // which read-back of the context this slot holds (0: none yet)
     };
     Feedback feedback[4];
     int feedback_next{ 0 };
+    uint64_t feedback_serial{ 0 };          // read-backs submitted so far
+    uint64_t pipelined_serial{ 0 };         // the read-back the last t3d_batch_frame_pipelined call left travelling (0: none)
 
     uint32_t* strip_indices{ nullptr }; // cached MeshBatch index pattern
     uint32_t strip_quads{ 0 };
@@ -777,6 +780,7 @@ static int submit_feedback(t3d_ctx* c, const std::vector<PendingOp>& ops, const 
     t3d_ctx::Feedback& fb = c->feedback[c->feedback_next];
     if (fb.in_flight) return T3D_OK; // all slots busy: skip this frame's feedback
     c->feedback_next = (c->feedback_next + 1) % 4;
+    fb.serial = ++c->feedback_serial;
     const size_t n = ops.size();
     // layout: counts (2 words per emitter) + the fault word, padded to `cap` emitters; then 6 x 64-bit box words per emitter
     auto words = [](size_t cap) { return 2 * cap + 2 + 12 * cap; };
@@ -2250,6 +2254,49 @@ int t3d_batch_frame(t3d_emitter* const* es, size_t n, const float* node_worlds, 
     T3D_TRY(t3d_batch_update(es, n, elapsed_ms));
     T3D_TRY(t3d_batch_draw(es, n));
     if (counts) return t3d_batch_get_counts(es, n, counts);
+    return T3D_OK;
+}
+
+int t3d_batch_frame_pipelined(t3d_emitter* const* es, size_t n, const float* node_worlds, const float* camera_world, float elapsed_ms,
+                              uint32_t* previous_counts, int* have_previous)
+{
+    if (!es && n) return fail(T3D_ERR_INVALID, "null argument");
+    if (have_previous) *have_previous = 0;
+    if (n == 0) return T3D_OK;
+    t3d_ctx* c = es[0]->ctx;
+    for (size_t i = 0; i < n; ++i)
+        if (es[i]->ctx != c) return fail(T3D_ERR_INVALID, "t3d_batch_frame_pipelined: emitters belong to different contexts");
+    if (node_worlds || camera_world) T3D_TRY(t3d_batch_set_transforms(es, n, node_worlds, camera_world));
+    T3D_TRY(t3d_batch_update(es, n, elapsed_ms));
+    T3D_TRY(t3d_batch_draw(es, n));
+    const uint64_t serial_before = c->feedback_serial;
+    T3D_TRY(flush(c)); // the frame goes out now (its counts start travelling back behind it); nothing waits for it
+    // The previous pipelined frame's counts: its kernel ran while this frame was being prepared, so the copy has normally landed.
+    if (c->pipelined_serial)
+    {
+        for (t3d_ctx::Feedback& fb : c->feedback)
+        {
+            if (fb.serial != c->pipelined_serial || fb.es.size() != n) continue;
+            bool same = true;
+            for (size_t i = 0; same && i < n; ++i) same = fb.es[i] == es[i];
+            if (!same) break;
+            if (fb.in_flight)
+            {
+                {
+                    HostTimer ht(c, T3D_HOST_WAIT);
+                    T3D_CUDA(cudaEventSynchronize(fb.done));
+                }
+                absorb_feedback(c, fb);
+            }
+            T3D_TRY(check_fault(c));
+            if (previous_counts)
+                for (size_t i = 0; i < n; ++i) previous_counts[i] = fb.host[2 * i];
+            if (have_previous) *have_previous = 1;
+            break;
+        }
+    }
+    // (a frame whose update was suppressed -- rate cap, inactive emitters -- or whose read-back found every slot busy leaves none)
+    c->pipelined_serial = c->feedback_serial == serial_before + 1 ? c->feedback_serial : 0;
     return T3D_OK;
 }
 

@@ -317,7 +317,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         // Every round inspects the 32 * kLook nearest predecessors not yet accounted for: each lane requests kLook status
         // words at once (the windows further back travel while the nearest one is examined), so a tile that starts in the
         // middle of a wave of ~300 concurrent tiles resolves its prefix in two or three L2 round trips instead of ten.
+#if defined(T3D_EXP_LOOK)
+        constexpr int kLook = T3D_EXP_LOOK;
+#else
         constexpr int kLook = 4;
+#endif
         uint32_t excl = 0;
         int look = (int)jt - 1; // nearest predecessor, as a tile index inside the emitter
         bool resolved = false;
@@ -703,7 +707,13 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                     const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage_warp);
                     const uint32_t bytes = warp_quads * (uint32_t)kQuadBytes;
                     float* dst = vtx + (size_t)w0 * T3D_FLOATS_PER_QUAD;
+#if defined(T3D_EXP_BULK_POLICY) // e.g. -DT3D_EXP_BULK_POLICY="evict_first": the vertex stream with an L2 eviction priority
+                    unsigned long long pol;
+                    asm volatile("createpolicy.fractional.L2::" T3D_EXP_BULK_POLICY ".b64 %0, 1.0;" : "=l"(pol));
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(src), "r"(bytes), "l"(pol) : "memory");
+#else
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+#endif
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }

@@ -195,6 +195,17 @@ class Context:
                                                   counts_out.ctypes.data_as(_P(C.c_uint32)) if counts_out is not None else None))
         return counts_out
 
+    def batch_frame_pipelined(self, emitters, elapsed_ms, node_worlds=None, camera_world=None, handles=None, previous_counts=None):
+        """t3d_batch_frame_pipelined: the frame is enqueued without waiting for it; previous_counts (uint32 array) receives the
+        live counts the previous such call left.  Returns True when previous_counts was filled."""
+        h = handles if handles is not None else self._handles(emitters)
+        have = C.c_int(0)
+        _check(self.lib, self.lib.t3d_batch_frame_pipelined(h, len(h), _fptr(node_worlds) if node_worlds is not None else None,
+                                                            _fptr(camera_world) if camera_world is not None else None, elapsed_ms,
+                                                            previous_counts.ctypes.data_as(_P(C.c_uint32)) if previous_counts is not None else None,
+                                                            C.byref(have)))
+        return bool(have.value)
+
     def batch_counts(self, emitters, handles=None):
         h = handles if handles is not None else self._handles(emitters)
         out = np.zeros(len(h), dtype=np.uint32)
