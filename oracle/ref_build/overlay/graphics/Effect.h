@@ -22,6 +22,7 @@ class Effect : public Ref
 {
   public:
     static Effect* createFromFile(const std::string&, const std::string&, const char* = nullptr) { return new Effect(); }
+    static Effect* createFromFile(const std::string&, const std::string&, const std::string&) { return new Effect(); } // (Font.cpp:122)
     unsigned int getUniformCount() const { return 1; }
     Uniform* getUniform(unsigned int) { return &_uniform; }
   private:

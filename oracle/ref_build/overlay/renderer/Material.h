@@ -1,6 +1,7 @@
 // Overlay stub for renderer/Material.h: SpriteBatch::create wraps its effect in a Material and binds
 // two parameters (SpriteBatch.cpp:124-171). Parameters accept and ignore their values.
 #pragma once
+#include <cfloat> // (Font.cpp uses FLT_MAX and gets it through the real Material.h)
 #include <string>
 #include "graphics/Effect.h"
 #include "renderer/RenderState.h"
@@ -10,6 +11,7 @@ class MaterialParameter
 {
   public:
     template <class T> void setValue(T) {}
+    template <class T> void setVector2(T) {} // (Font.cpp:367: the distance-field cutoff)
     template <class C, class R> void bindValue(C*, R (C::*)() const) {}
 };
 class Material : public RenderState

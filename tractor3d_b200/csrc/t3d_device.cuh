@@ -490,14 +490,20 @@ __device__ __host__ __forceinline__ float float_unorder(uint32_t u)
 // Which emitter of the launch owns global tile `tile`: the last item with tile_begin <= tile.  Every step is a
 // dependent load, so the search starts from the interpolated position (exact when emitters have equal tile
 // counts: two loads) and gallops outwards before bisecting.
+// the interpolated position: exact when the emitters of the launch have equal tile counts
+__device__ __forceinline__ uint32_t guess_item(uint32_t n_items, uint32_t tile, uint32_t total_tiles)
+{
+    if (n_items == 1) return 0;
+    const uint32_t g = (uint32_t)(((unsigned long long)tile * n_items) / (total_tiles ? total_tiles : 1u));
+    return g >= n_items ? n_items - 1 : g;
+}
 template <class Item>
 __device__ __forceinline__ uint32_t find_item(const Item* __restrict__ items, uint32_t n_items, uint32_t tile,
                                               uint32_t total_tiles)
 {
     if (n_items == 1) return 0;
     uint32_t lo, hi;
-    uint32_t g = (uint32_t)(((unsigned long long)tile * n_items) / (total_tiles ? total_tiles : 1u));
-    if (g >= n_items) g = n_items - 1;
+    const uint32_t g = guess_item(n_items, tile, total_tiles);
     if (items[g].tile_begin <= tile)
     {
         lo = g;

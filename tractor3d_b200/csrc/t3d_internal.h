@@ -123,7 +123,8 @@ struct EmitterDev
 
 // One entry per emitter taking part in a launch.  tile_begin is the first global tile of the emitter in
 // this launch; entries are sorted by it and a CTA finds its emitter by binary search.
-struct UpdateItem
+// 80 bytes, 16-byte aligned: a CTA requests the whole entry of the emitter it expects to own with five 128-bit loads at once.
+struct alignas(16) UpdateItem
 {
     EmitterDev* dev;
     Storage st;           // copied from the emitter's record so a CTA can start loading after ONE dependent fetch
@@ -135,7 +136,9 @@ struct UpdateItem
     float percent_per_frame;
     float frame_duration_secs;
     uint32_t n_tiles;     // tiles of this launch that belong to the emitter (the kernel checks that they cover the live count)
+    uint32_t pad[2];
 };
+static_assert(sizeof(UpdateItem) == 80, "UpdateItem is fetched as five 128-bit words");
 
 struct SpawnItem
 {

@@ -2266,10 +2266,10 @@ int t3d_batch_frame_pipelined(t3d_emitter* const* es, size_t n, const float* nod
     t3d_ctx* c = es[0]->ctx;
     for (size_t i = 0; i < n; ++i)
         if (es[i]->ctx != c) return fail(T3D_ERR_INVALID, "t3d_batch_frame_pipelined: emitters belong to different contexts");
+    const uint64_t serial_before = c->feedback_serial;
     if (node_worlds || camera_world) T3D_TRY(t3d_batch_set_transforms(es, n, node_worlds, camera_world));
     T3D_TRY(t3d_batch_update(es, n, elapsed_ms));
-    T3D_TRY(t3d_batch_draw(es, n));
-    const uint64_t serial_before = c->feedback_serial;
+    T3D_TRY(t3d_batch_draw(es, n)); // (as two launches -- T3D_FUSED=0 -- the update goes out here, its read-back behind it)
     T3D_TRY(flush(c)); // the frame goes out now (its counts start travelling back behind it); nothing waits for it
     // The previous pipelined frame's counts: its kernel ran while this frame was being prepared, so the copy has normally landed.
     if (c->pipelined_serial)
@@ -2296,7 +2296,7 @@ int t3d_batch_frame_pipelined(t3d_emitter* const* es, size_t n, const float* nod
         }
     }
     // (a frame whose update was suppressed -- rate cap, inactive emitters -- or whose read-back found every slot busy leaves none)
-    c->pipelined_serial = c->feedback_serial == serial_before + 1 ? c->feedback_serial : 0;
+    c->pipelined_serial = c->feedback_serial > serial_before ? c->feedback_serial : 0; // the newest read-back: this frame's update
     return T3D_OK;
 }
 

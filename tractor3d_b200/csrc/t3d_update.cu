@@ -121,9 +121,25 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     }
     if (tile >= total_tiles) return;
 
-    // One dependent fetch (the launch descriptor) and the loads can start; the live count is fetched in parallel.
-    const uint32_t item_index = find_item(items, n_items, tile, total_tiles);
-    const UpdateItem& it = items[item_index];
+    // One dependent fetch (the launch descriptor) and the loads can start; the live count is fetched in parallel.  The whole
+    // entry of the emitter this tile is expected to belong to (exact when the emitters have equal tile counts, and for a single
+    // emitter) is requested at once and checked; only a wrong guess pays for the search (dependent loads, one after another).
+    auto load_item = [&](uint32_t i)
+    {
+        UpdateItem r;
+        const uint4* src = reinterpret_cast<const uint4*>(items + i);
+        uint4* dst = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(UpdateItem) / 16); ++q) dst[q] = __ldg(src + q);
+        return r;
+    };
+    uint32_t item_index = guess_item(n_items, tile, total_tiles);
+    UpdateItem it = load_item(item_index);
+    if (tile - it.tile_begin >= it.n_tiles)
+    {
+        item_index = find_item(items, n_items, tile, total_tiles);
+        it = load_item(item_index);
+    }
     EmitterDev* const d = it.dev;
     const uint32_t parity = it.parity;
     uint32_t* const rw = it.st.rw;
@@ -925,7 +941,7 @@ static const Variant kUpdate[] = {
 static const Variant kFused[] = {
     // default: 2 particles per thread, 192 threads x 12 groups = 4 608-particle tiles, 2 CTAs/SM
     T3D_FUSED_SHAPE(2, 192, 12, 2),
-    T3D_FUSED_SHAPE(2, 192, 6, 2), T3D_FUSED_SHAPE(2, 128, 12, 3),
+    T3D_FUSED_SHAPE(2, 192, 6, 2), T3D_FUSED_SHAPE(2, 128, 12, 3), T3D_FUSED_SHAPE(2, 128, 8, 3), T3D_FUSED_SHAPE(2, 128, 6, 3),
 };
 template <size_t N>
 static const Variant& pick(const Variant (&table)[N], const char* env_name, int& cache)
