@@ -366,6 +366,30 @@ int t3d_tileset_set_tiles(t3d_tileset* t, const float* sources);
  * Destination as in t3d_ctx_draw_sprites; *n_quads = the number of non-blank cells (known on the host: no wait). */
 int t3d_tileset_draw(t3d_tileset* t, const float position[3], const float color[4], void* device_dst, size_t dst_quads,
                      const t3d_sprite_vertex** device_ptr, uint32_t* n_quads);
+
+/* Font::drawText(text, x, y, color, size) (src/renderer/Font.cpp:242-390): one SpriteBatch quad per character that has a glyph,
+ * in reading order, laid out by the reference's pen walk (' ' and '\t' advance by the first glyph's advance, '\r' / '\n'
+ * start a new line `size` pixels down, a glyph advances by floor(advance * scale + spacing); bytes >= 128 are skipped: `char`
+ * is signed there).  A t3d_font is ONE size of a font (Font::create(family, style, size, glyphs, glyphCount, texture,
+ * format), Font.cpp:103-161); choosing among several sizes (findClosestSize, :221-239) stays with the caller. */
+typedef struct t3d_glyph {      /* Font::Glyph, include/renderer/Font.h:296-323 */
+    uint32_t code;
+    uint32_t width;             /* pixels */
+    int32_t  bearing_x;
+    uint32_t advance;
+    float    uvs[4];            /* u1, v1, u2, v2 */
+} t3d_glyph;
+typedef struct t3d_font t3d_font;
+int t3d_font_create(t3d_ctx* ctx, uint32_t size, const t3d_glyph* glyphs, uint32_t glyph_count, t3d_font** out);
+int t3d_font_destroy(t3d_font* f);
+int t3d_font_set_character_spacing(t3d_font* f, float spacing);                                   /* Font.h:246 */
+#define T3D_TEXT_ON_DEVICE 1u   /* `text` is a device pointer (16-byte aligned); nothing is uploaded */
+/* size = 0: the font's own size (Font.cpp:253-256).  right_to_left: T3D_ERR_INVALID (the reference's per-line reversed walk,
+ * Font.cpp:283-327, is not built).  Destination as in t3d_ctx_draw_sprites; *n_quads = characters drawn (counted on the host
+ * for host text; read back from the device, with a wait, for T3D_TEXT_ON_DEVICE). */
+int t3d_font_draw_text(t3d_font* f, const char* text, size_t length, uint32_t text_flags, int x, int y, const float color[4],
+                       uint32_t size, int right_to_left, void* device_dst, size_t dst_quads, const t3d_sprite_vertex** device_ptr,
+                       uint32_t* n_quads);
 int t3d_ctx_download_quads(t3d_ctx* ctx, const t3d_sprite_vertex* device_ptr, uint32_t n_quads, float* out); /* tests */
 
 /* ---- pure host helpers (no GPU needed): the scalar logic of the path ----------------------- */

@@ -866,6 +866,48 @@ uint32_t orc_tileset_draw(const float* sources, uint32_t rows, uint32_t cols, fl
     return quads;
 }
 
+/* Font::drawText(text, x, y, color, size, rightToLeft = false), src/renderer/Font.cpp:242-390, for ONE size of a font
+ * (size delegation, :258-264, is the caller's): the pen walk, one SpriteBatch::draw(x, y, w, h, u1, v1, u2, v2, color) per
+ * character with a glyph (SB.cpp:366-378 -> :475-506, z = 0, position not centred).  36 floats per quad. */
+uint32_t orc_font_draw_text(const t3d_glyph* glyphs, uint32_t glyph_count, uint32_t font_size, float character_spacing,
+                            const char* text, size_t length, int x, int y, const float color[4], uint32_t size, float* out, size_t max_quads)
+{
+    if (size == 0) size = font_size;                                  /* :253-256 */
+    const float scale = (float)size / (float)font_size;               /* :268 */
+    const int spacing = (int)((float)size * character_spacing);       /* :269 */
+    int x_pos = x, y_pos = y;                                         /* :277 */
+    uint32_t quads = 0;
+    float scratch[36];
+    for (size_t i = 0; i < length; ++i) {                             /* :330 (text.length(), so embedded NULs are walked over) */
+        const signed char c = (signed char)text[i];                   /* :340: `char`, signed on the reference's platforms */
+        switch (c) {
+        case ' ':  x_pos = (int)((unsigned)x_pos + glyphs[0].advance); break;          /* :343-345 */
+        case '\r':
+        case '\n': y_pos = (int)((unsigned)y_pos + size); x_pos = x; break;            /* :346-349 */
+        case '\t': x_pos = (int)((unsigned)x_pos + glyphs[0].advance * 4u); break;     /* :350-352 */
+        default: {
+            const int index = c - 32;                                                  /* :354 */
+            if (index >= 0 && index < (int)glyph_count) {
+                const t3d_glyph* g = &glyphs[index];
+                t3d_sprite2d sp;
+                memset(&sp, 0, sizeof(sp));
+                sp.x = (float)(x_pos + (int)((float)g->bearing_x * scale));            /* :369 */
+                sp.y = (float)y_pos;
+                sp.width = (float)g->width * scale;                                    /* :371 */
+                sp.height = (float)size;
+                sp.u1 = g->uvs[0]; sp.v1 = g->uvs[1]; sp.u2 = g->uvs[2]; sp.v2 = g->uvs[3];
+                memcpy(sp.color, color, 16);
+                quads += (uint32_t)sprite_quad(&sp, (out && quads < max_quads) ? out + (size_t)quads * 36 : scratch);
+                /* :378: `xPos += floor(...)` -- the floor is taken in float, the sum in double (exact), back to int */
+                x_pos = (int)((double)x_pos + (double)floorf((float)g->advance * scale + (float)spacing));
+            }
+            break;
+        }
+        }
+    }
+    return quads;
+}
+
 /* =====================================================================================
  * Timing loops.
  * ===================================================================================== */

@@ -25,6 +25,7 @@
 #include "graphics/ParticleEmitter.h"
 #include "graphics/SpriteBatch.h"
 #include "graphics/TileSet.h"
+#include "renderer/Font.h"
 #include "scene/Node.h"
 #include "scene/Scene.h"
 
@@ -543,6 +544,40 @@ uint32_t t3dref_tileset_draw(void* h, const float node_t[3], const float camera_
     r->ts->setOpacity(opacity);
     r->ts->draw(false);
     return copy_captured(r->ts->_batch->_batch.get(), out, max_quads);
+}
+
+// ---- Font::drawText (src/renderer/Font.cpp:242-390), driven headless ----
+static_assert(sizeof(Font::Glyph) == sizeof(t3d_glyph), "t3d_glyph mirrors Font::Glyph (Font.h:296-323)");
+void* t3dref_font_create(uint32_t size, const t3d_glyph* glyphs, uint32_t glyph_count, uint32_t tex_w, uint32_t tex_h)
+{
+    keep_sprite_effect_alive();
+    char name[64];
+    snprintf(name, sizeof(name), "@%ux%u", tex_w, tex_h);
+    Texture* tex = Texture::create(std::string(name));
+    if (!tex) return nullptr;
+    std::vector<Font::Glyph> g(glyph_count);
+    memcpy(g.data(), glyphs, glyph_count * sizeof(Font::Glyph));
+    Font* f = Font::create(std::string("t3d"), Font::PLAIN, size, g.data(), (int)glyph_count, tex, Font::BITMAP); // Font.cpp:103-161
+    tex->release();
+    return f;
+}
+void t3dref_font_destroy(void* h)
+{
+    if (h) ((Font*)h)->release();
+}
+void t3dref_font_set_character_spacing(void* h, float spacing) { ((Font*)h)->setCharacterSpacing(spacing); }
+// start(), drawText(text, x, y, color, size, rightToLeft), finish(); returns the quads the font's batch received.
+uint32_t t3dref_font_draw_text(void* h, const char* text, size_t length, int x, int y, const float color[4], uint32_t size, int right_to_left,
+                               float* out, size_t max_quads, double* time_s)
+{
+    Font* f = (Font*)h;
+    const std::string s(text, length);
+    auto t0 = std::chrono::steady_clock::now();
+    f->start();
+    f->drawText(s, x, y, Vector4(color[0], color[1], color[2], color[3]), size, right_to_left != 0);
+    f->finish();
+    if (time_s) *time_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return copy_captured(f->_batch->_batch.get(), out, max_quads);
 }
 
 } // extern "C"

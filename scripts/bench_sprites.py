@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
 import cpu_harness as H  # noqa: E402
-from tractor3d_b200.emitter import Context, TileSet  # noqa: E402
+from tractor3d_b200.emitter import Context, Font, TileSet  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 rows = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
@@ -106,4 +106,48 @@ for _ in range(3):
     nq = R.tileset_draw(h, fpp(z3), fpp(z3), fpp(col), 0.8, None, 0)
 t = (time.perf_counter() - t0) / 3
 print(f"    reference TileSet.cpp, one host core, {r2} x {c2} grid ({nq} tiles): {t * 1e3:.2f} ms per frame = {nq / t / 1e6:.2f} M tiles/s")
+
+# ---- Font::drawText: 1 byte read per character (+ the tile summaries), 144 B written per glyph ----
+n_text = n
+g = H.random_font(5, 95, 24)
+text = H.random_text(n_text, 6)
+font = Font(ctx, 24, g)
+color4 = np.array([1.0, 1.0, 1.0, 1.0], dtype=np.float32)
+glyphs_drawn = sum(1 for b in text if 32 < b < 127)
+dev_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+dst = torch.empty(n_text * 36, dtype=torch.float32, device="cuda")
+torch.cuda.synchronize()
+_, nq = font.drawText(None, 0, 0, color4, 30, device_dst=dst.data_ptr(), dst_quads=n_text, text_on_device=(dev_text.data_ptr(), n_text))
+assert nq == glyphs_drawn
+# (the timed calls do not ask for the count back: no wait)
+lib, fh = ctx.lib, font.h
+cp = color4.ctypes.data_as(C.POINTER(C.c_float))
+from tractor3d_b200 import abi  # noqa: E402
+
+
+def text_on_device():
+    lib.t3d_font_draw_text(fh, C.c_void_p(dev_text.data_ptr()), n_text, abi.TEXT_ON_DEVICE, 0, 0, cp, 30, 0, C.c_void_p(dst.data_ptr()), n_text, None, None)
+
+
+def text_on_host():
+    lib.t3d_font_draw_text(fh, text, n_text, 0, 0, 0, cp, 30, 0, C.c_void_p(dst.data_ptr()), n_text, None, None)
+
+
+bytes_alg = n_text + 144 * glyphs_drawn
+d_ms, w_ms = timed(text_on_device)
+print(f"  text, {n_text} bytes -> {glyphs_drawn} glyph quads, text resident in HBM (3 launches: tile summaries, scan, expansion):\n"
+      f"    {d_ms:.3f} ms device per text = {glyphs_drawn / d_ms / 1e6:.2f} G glyphs/s, {bytes_alg / d_ms / 1e6:.0f} GB/s algorithmic "
+      f"({bytes_alg / d_ms / 1e6 / PEAK:.2f} of the measured HBM peak)")
+d_ms, w_ms = timed(text_on_host, reps=10)
+print(f"    text in host memory (1 B per character uploaded, glyphs counted on the host): {w_ms:.3f} ms wall per text = {glyphs_drawn / w_ms / 1e6:.3f} G glyphs/s")
+R = H.ref(fresh=True)
+m = min(n_text, 1 << 18)
+h = R.font_create(24, g.ctypes.data, 95, 512, 512)
+t = C.c_double()
+out = np.zeros((m, 36), dtype=np.float32)
+for _ in range(2):
+    nq = R.font_draw_text(h, text, m, 0, 0, cp, 30, 0, out.ctypes.data_as(C.POINTER(C.c_float)), m, C.byref(t))
+print(f"    reference Font.cpp + SpriteBatch.cpp, one host core, {m} bytes ({nq} glyphs): {t.value * 1e3:.2f} ms = {nq / t.value / 1e6:.2f} M glyphs/s")
+R.font_destroy(h)
+font.release()
 ctx.close()

@@ -93,6 +93,8 @@ class CpuLib:
             proto("sprites_2d", C.c_uint32, [_vp, C.c_size_t, _P(C.c_float), C.c_size_t])
             proto("tileset_draw", C.c_uint32, [_P(C.c_float), C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float,
                                                _P(C.c_float), _P(C.c_float), _P(C.c_float), C.c_size_t])
+            proto("font_draw_text", C.c_uint32, [_vp, C.c_uint32, C.c_uint32, C.c_float, C.c_char_p, C.c_size_t, C.c_int, C.c_int, _P(C.c_float),
+                                                 C.c_uint32, _P(C.c_float), C.c_size_t])
             proto("device_rng_draw", C.c_int32, [C.c_uint64, C.c_uint64, C.c_uint32])
             proto("reset_statics", None, [])
             proto("set_rotation_mode", None, [C.c_int])
@@ -108,6 +110,11 @@ class CpuLib:
             proto("tileset_destroy", None, [_vp])
             proto("tileset_set_tile_source", None, [_vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float])
             proto("tileset_draw", C.c_uint32, [_vp, _P(C.c_float), _P(C.c_float), _P(C.c_float), C.c_float, _P(C.c_float), C.c_size_t])
+            proto("font_create", _vp, [C.c_uint32, _vp, C.c_uint32, C.c_uint32, C.c_uint32])
+            proto("font_destroy", None, [_vp])
+            proto("font_set_character_spacing", None, [_vp, C.c_float])
+            proto("font_draw_text", C.c_uint32, [_vp, C.c_char_p, C.c_size_t, C.c_int, C.c_int, _P(C.c_float), C.c_uint32, C.c_int, _P(C.c_float),
+                                                 C.c_size_t, _P(C.c_double)])
             proto("emitter_create_from_file", _vp, [C.c_char_p])
             proto("emitter_clone", _vp, [_vp])
             proto("set_quiet", None, [C.c_int])
@@ -325,3 +332,33 @@ def random_sprites(n, seed, clipped=True, rotated=True):
         s["clip"][:, 2] = rng.uniform(50, 400, n); s["clip"][:, 3] = rng.uniform(50, 300, n)
     s["flags"] = flags
     return s
+
+
+# -- Font::drawText --
+def random_font(seed, glyph_count=95, size=24):
+    """A glyph table like a font bundle's: character 32 + k at index k; widths, bearings (some negative) and advances in
+    pixels, uvs anywhere in the atlas."""
+    rng = np.random.default_rng(seed)
+    g = np.zeros(glyph_count, dtype=abi.GLYPH_DTYPE)
+    g["code"] = 32 + np.arange(glyph_count)
+    g["width"] = rng.integers(1, size + 6, glyph_count)
+    g["bearing_x"] = rng.integers(-3, 4, glyph_count)
+    g["advance"] = rng.integers(1, size + 8, glyph_count)
+    g["uvs"][:, 0] = rng.uniform(0, 0.9, glyph_count); g["uvs"][:, 2] = g["uvs"][:, 0] + rng.uniform(0.01, 0.1, glyph_count)
+    g["uvs"][:, 1] = rng.uniform(0.1, 1, glyph_count); g["uvs"][:, 3] = g["uvs"][:, 1] - rng.uniform(0.01, 0.1, glyph_count)
+    return g
+
+
+def random_text(n, seed, newline_every=60):
+    """n bytes: mostly printable ASCII, with spaces, tabs, '\\n', '\\r', control bytes, NULs and bytes >= 128 (which the
+    reference's signed `char` skips) mixed in."""
+    rng = np.random.default_rng(seed)
+    t = rng.integers(33, 127, n).astype(np.uint8)
+    r = rng.random(n)
+    t[r < 0.15] = 32
+    t[(r >= 0.15) & (r < 0.17)] = 9
+    t[(r >= 0.17) & (r < 0.17 + 1.0 / newline_every)] = 10
+    t[(r >= 0.20) & (r < 0.205)] = 13
+    t[(r >= 0.21) & (r < 0.215)] = rng.integers(128, 256, n)[(r >= 0.21) & (r < 0.215)]
+    t[(r >= 0.22) & (r < 0.223)] = rng.integers(0, 9, n)[(r >= 0.22) & (r < 0.223)]
+    return t.tobytes()

@@ -1,6 +1,6 @@
 """Generates tests/golden/sprites/*.npz from the UNMODIFIED reference (oracle/_ref/libt3dref.so): the vertex streams its
 own SpriteBatch.cpp / TileSet.cpp produce for a list of 2-D sprites (every overload: plain, centred, rotated, clipped)
-and for a tile set with blank cells.  Run here, where /root/reference exists and `make -C oracle ref` has been done:
+and for a tile set with blank cells; and the quads its Font.cpp lays out for a text.  Run here, where /root/reference exists and `make -C oracle ref` has been done:
     python tests/golden/make_golden_sprites.py
 The fixtures travel to machines without the reference (the GPU box)."""
 import ctypes as C
@@ -53,6 +53,22 @@ def main():
     np.savez_compressed(os.path.join(out_dir, "tileset.npz"), sources=src, tile=np.array([tw, th], dtype=np.float32), texture=np.array([256, 128]),
                         node=node, camera=cam, color=color, opacity=opacity, vertices=verts[:quads].view(np.uint32))
     print(f"tileset: {rows} x {cols} cells -> {quads} quads")
+
+    # Font::drawText through the reference's own Font.cpp: a scaled size with character spacing, lines, tabs, control bytes,
+    # NULs and bytes >= 128
+    glyph_count, font_size, size, spacing, n_text = 95, 24, 31, 0.125, 6000
+    g = H.random_font(11, glyph_count, font_size)
+    text = H.random_text(n_text, 12)
+    color = np.array([0.25, 0.5, 0.75, 1.0], dtype=np.float32)
+    h = R.font_create(font_size, g.ctypes.data, glyph_count, 512, 512)
+    R.font_set_character_spacing(h, spacing)
+    verts = np.zeros((n_text, 36), dtype=np.float32)
+    quads = R.font_draw_text(h, text, n_text, -17, 40, fp(color), size, 0, fp(verts), n_text, None)
+    R.font_destroy(h)
+    np.savez_compressed(os.path.join(out_dir, "font_text.npz"), glyphs=g.view(np.uint32).reshape(glyph_count, -1), font_size=np.array(font_size),
+                        size=np.array(size), spacing=np.float32(spacing), text=np.frombuffer(text, dtype=np.uint8), origin=np.array([-17, 40]),
+                        color=color, vertices=verts[:quads].view(np.uint32))
+    print(f"font_text: {n_text} bytes -> {quads} quads")
 
 
 if __name__ == "__main__":

@@ -62,6 +62,14 @@ def test_oracle_reproduces_reference_golden_sprites():
     n = O.sprites_2d(sp.ctypes.data, sp.size, fp(got), sp.size)
     assert n == want.shape[0] < sp.size
     assert np.array_equal(got[:n].view(np.uint32), want)
+    z = _sprite_fixture("font_text")
+    g = np.ascontiguousarray(z["glyphs"]).view(abi.GLYPH_DTYPE).reshape(-1)
+    text = z["text"].tobytes()
+    got = np.zeros((len(text), 36), dtype=np.float32)
+    n = O.font_draw_text(g.ctypes.data, g.size, int(z["font_size"]), float(z["spacing"]), text, len(text), int(z["origin"][0]), int(z["origin"][1]),
+                         fp(np.ascontiguousarray(z["color"])), int(z["size"]), fp(got), len(text))
+    assert n == z["vertices"].shape[0] < len(text)
+    assert np.array_equal(got[:n].view(np.uint32), z["vertices"])
     z = _sprite_fixture("tileset")
     src = np.ascontiguousarray(z["sources"])
     rows, cols = src.shape[:2]

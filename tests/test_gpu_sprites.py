@@ -10,7 +10,7 @@ import pytest
 
 import cpu_harness as H
 from tractor3d_b200 import abi
-from tractor3d_b200.emitter import Context, TileSet
+from tractor3d_b200.emitter import Context, Font, TileSet
 
 pytestmark = pytest.mark.gpu
 fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
@@ -139,7 +139,7 @@ def test_tileset_draw_matches_the_oracle(rows, cols, tw, th):
 
 
 def test_sprites_and_tiles_against_the_reference_fixtures():
-    # the committed vectors the reference's own SpriteBatch.cpp / TileSet.cpp produced (tests/golden/make_golden_sprites.py)
+    # the committed vectors the reference's own SpriteBatch.cpp / TileSet.cpp / Font.cpp produced (tests/golden/make_golden_sprites.py)
     import os
     import golden_io as G
     from test_golden import tileset_inputs
@@ -161,5 +161,77 @@ def test_sprites_and_tiles_against_the_reference_fixtures():
         assert nq == z["vertices"].shape[0]
         assert np.array_equal(ctx.download_quads(ptr, nq).view(np.uint32).reshape(nq, 36), z["vertices"])
         ts.release()
+        z = np.load(os.path.join(G.GOLDEN_DIR, "sprites", "font_text.npz"))
+        font = Font(ctx, int(z["font_size"]), np.ascontiguousarray(z["glyphs"]).view(abi.GLYPH_DTYPE).reshape(-1))
+        font.setCharacterSpacing(float(z["spacing"]))
+        ptr, nq = font.drawText(z["text"].tobytes(), int(z["origin"][0]), int(z["origin"][1]), z["color"], int(z["size"]))
+        assert nq == z["vertices"].shape[0]
+        assert np.array_equal(ctx.download_quads(ptr, nq).view(np.uint32).reshape(nq, 36), z["vertices"])
+        font.release()
+    finally:
+        ctx.close()
+
+
+# ---- Font::drawText (Font.cpp:242-390) ----
+def _oracle_text(O, g, font_size, spacing, text, x, y, color, size):
+    out = np.zeros((max(len(text), 1), 4, 9), dtype=np.float32)
+    n = O.font_draw_text(g.ctypes.data, g.size, font_size, spacing, text, len(text), x, y, fp(color), size, fp(out), len(text))
+    return out[:n]
+
+
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 255, 256, 257, 4095, 4096, 4097, 70_001, 1_300_003])
+def test_text_is_laid_out_like_font_drawtext(n):
+    # the pen walk as a segmented scan (tile summaries of 256 characters, one-CTA scan, expansion): texts that end inside a
+    # 16-byte load, a tile, a summary CTA (4 096 characters), and over a thousand tiles; bit for bit
+    O = H.oracle(fresh=True)
+    ctx = Context(0)
+    try:
+        color = np.array([0.25, 0.5, 0.75, 1.0], dtype=np.float32)
+        for glyph_count, font_size, size, spacing, x0 in ((95, 24, 0, 0.0, -17), (60, 18, 31, 0.125, 5), (95, 32, 20, -0.05, (1 << 25) + 1)):
+            g = H.random_font(n + glyph_count, glyph_count, font_size)
+            text = H.random_text(n, n + 1)
+            font = Font(ctx, font_size, g)
+            font.setCharacterSpacing(spacing)
+            want = _oracle_text(O, g, font_size, spacing, text, x0, 40, color, size)
+            ptr, nq = font.drawText(text, x0, 40, color, size)
+            assert nq == want.shape[0] and (n < 100 or 0 < nq < n)
+            assert np.array_equal(ctx.download_quads(ptr, nq).view(np.uint32), want.view(np.uint32))
+            font.release()
+    finally:
+        ctx.close()
+
+
+def test_text_edge_cases_and_device_resident_text():
+    import torch
+    O = H.oracle(fresh=True)
+    ctx = Context(0)
+    try:
+        color = np.array([1.0, 0.5, 0.25, 0.75], dtype=np.float32)
+        g = H.random_font(3, 95, 24)
+        font = Font(ctx, 24, g)
+        # nothing but line breaks and blanks; one long line without a break; only bytes the walk skips; a break as the last byte
+        for text in (b"\n\r\n   \t\n", bytes(range(33, 127)) * 300, bytes([200, 0, 7, 255]) * 100, b"ab\ncd\n", b"\tx"):
+            want = _oracle_text(O, g, 24, 0.0, text, 3, -9, color, 0)
+            ptr, nq = font.drawText(text, 3, -9, color)
+            assert nq == want.shape[0]
+            if nq:
+                assert np.array_equal(ctx.download_quads(ptr, nq).view(np.uint32), want.view(np.uint32))
+        # the text already on the device, the quads into a foreign allocation; the count comes back from the device
+        text = H.random_text(50_000, 77)
+        want = _oracle_text(O, g, 24, 0.0, text, 0, 0, color, 36)
+        dev_text = torch.frombuffer(bytearray(text), dtype=torch.uint8).cuda()
+        dst = torch.zeros(len(text) * 36, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        ptr, nq = font.drawText(None, 0, 0, color, 36, device_dst=dst.data_ptr(), dst_quads=len(text), text_on_device=(dev_text.data_ptr(), len(text)))
+        ctx.sync()
+        assert ptr == dst.data_ptr() and nq == want.shape[0]
+        assert np.array_equal(dst.cpu().numpy()[:nq * 36].view(np.uint32).reshape(nq, 4, 9), want.view(np.uint32))
+        assert float(dst[nq * 36:].abs().sum()) == 0.0          # nothing written beyond the text's quads
+        # errors are codes: a destination that is too small, the walk that is not built
+        with pytest.raises(Exception):
+            font.drawText(b"abc", 0, 0, color, device_dst=dst.data_ptr(), dst_quads=2)
+        with pytest.raises(Exception):
+            font.drawText(b"abc", 0, 0, color, right_to_left=True)
+        font.release()
     finally:
         ctx.close()

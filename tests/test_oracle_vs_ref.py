@@ -279,3 +279,28 @@ def test_tileset_draw_matches_the_reference():
         no = O.tileset_draw(fp(src), rows, cols, tw, th, 256.0, 128.0, fp(pos), fp(col), fp(got), n_cells)
         assert no == nr == int((src[..., 0] >= 0).sum())
         assert np.array_equal(got[:no].view(np.uint32), want[:nr].view(np.uint32))
+
+
+def test_font_draw_text_matches_the_reference():
+    # Font::drawText(text, x, y, color, size) through the reference's own Font.cpp (left to right): fonts with fewer glyphs than
+    # printable characters, scaled sizes (the floor / truncation paths), character spacing, lines, tabs, control bytes, NULs and
+    # bytes >= 128 -- the restatement must leave the same quads, bit for bit.
+    O, R = H.oracle(fresh=True), H.ref(fresh=True)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    color = np.array([0.25, 0.5, 0.75, 1.0], dtype=np.float32)
+    # (the last case starts the pen beyond 2^24, where a float pen would round: the reference adds the advances in double)
+    cases = [(95, 24, 0, 0.0, 1, 3, -17), (95, 24, 31, 0.125, 300, 4, -17), (60, 18, 7, -0.05, 5000, 5, 0), (95, 32, 64, 0.3, 70000, 6, 123456),
+             (10, 12, 12, 0.0, 999, 7, -17), (95, 24, 17, 0.0, 4000, 8, (1 << 25) + 1)]
+    for glyph_count, font_size, size, spacing, n, seed, x0 in cases:
+        g = H.random_font(seed, glyph_count, font_size)
+        text = H.random_text(n, seed)
+        h = R.font_create(font_size, g.ctypes.data, glyph_count, 512, 512)
+        assert h
+        R.font_set_character_spacing(h, spacing)
+        want = np.zeros((n, 36), dtype=np.float32)
+        nr = R.font_draw_text(h, text, n, x0, 40, fp(color), size, 0, fp(want), n, None)
+        R.font_destroy(h)
+        got = np.zeros((n, 36), dtype=np.float32)
+        no = O.font_draw_text(g.ctypes.data, glyph_count, font_size, spacing, text, n, x0, 40, fp(color), size, fp(got), n)
+        assert no == nr and (n < 100 or 0 < nr < n), (glyph_count, n)
+        assert np.array_equal(got[:no].view(np.uint32), want[:nr].view(np.uint32)), (glyph_count, font_size, size, spacing, n)

@@ -125,6 +125,10 @@ class Sprite2D(C.Structure):
 
 SPRITE_ROTATED, SPRITE_CENTERED, SPRITE_CLIPPED = 1, 2, 4
 SPRITES_ON_DEVICE, SPRITES_NO_CLIP = 1, 2
+# numpy view of an array of t3d_glyph (Font::Glyph, 8 words each)
+GLYPH_DTYPE = [("code", "u4"), ("width", "u4"), ("bearing_x", "i4"), ("advance", "u4"), ("uvs", "f4", (4,))]
+TEXT_ON_DEVICE = 1
+
 # numpy view of an array of t3d_sprite2d (21 words each)
 SPRITE2D_DTYPE = [("x", "f4"), ("y", "f4"), ("z", "f4"), ("width", "f4"), ("height", "f4"), ("u1", "f4"), ("v1", "f4"), ("u2", "f4"),
                   ("v2", "f4"), ("color", "f4", 4), ("rotation_point", "f4", 2), ("rotation_angle", "f4"), ("flags", "u4"), ("clip", "f4", 4)]
@@ -187,6 +191,11 @@ PROTOTYPES = {
     "t3d_batch_draw": (C.c_int, [_P(_vp), C.c_size_t]),
     "t3d_batch_emit_once": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_uint32)]),
     "t3d_batch_get_counts": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_uint32)]),
+    "t3d_font_create": (C.c_int, [_vp, C.c_uint32, _vp, C.c_uint32, _P(_vp)]),
+    "t3d_font_destroy": (C.c_int, [_vp]),
+    "t3d_font_set_character_spacing": (C.c_int, [_vp, C.c_float]),
+    "t3d_font_draw_text": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, C.c_int, C.c_int, _P(C.c_float), C.c_uint32, C.c_int, _vp, C.c_size_t,
+                                     _P(_vp), _P(C.c_uint32)]),
     "t3d_batch_frame": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_float), _P(C.c_float), C.c_float, _P(C.c_uint32)]),
     "t3d_batch_frame_pipelined": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_float), _P(C.c_float), C.c_float, _P(C.c_uint32), _P(C.c_int)]),
     "t3d_batch_set_transforms": (C.c_int, [_P(_vp), C.c_size_t, _P(C.c_float), _P(C.c_float)]),

@@ -150,7 +150,7 @@ def build_engine_callers():
     shim = ["-DT3D_WITH_ENGINE_HEADERS", "-I" + os.path.join(HERE, "host", "engine")]
     run(cxx + shim + overlay + ["-c", caller, "-o", os.path.join(tmp_b200, "caller.o")])
     run(cxx + shim + overlay + ["-c", os.path.join(HERE, "host", "ParticleEmitter.cpp"), "-o", os.path.join(tmp_b200, "facade.o")])
-    engine_objs = [o for o in objs if os.path.basename(o) not in ("ParticleEmitter.o", "SpriteBatch.o", "TileSet.o")]
+    engine_objs = [o for o in objs if os.path.basename(o) not in ("ParticleEmitter.o", "SpriteBatch.o", "TileSet.o", "Font.o")]
     run(["g++", "-o", out_b200, os.path.join(tmp_b200, "caller.o"), os.path.join(tmp_b200, "facade.o"), os.path.join(tmp_ref, "support.o")]
         + engine_objs + ["-L" + CSRC, "-lt3d_particles", "-Wl,-rpath,$ORIGIN/../../csrc"])
     return out_ref, out_b200

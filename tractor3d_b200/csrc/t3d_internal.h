@@ -224,6 +224,21 @@ void launch_export_state(void* stream, const Storage& st, uint32_t n, uint32_t* 
 void launch_import_state(void* stream, const Storage& st, uint32_t n, const uint32_t* in, uint32_t host_stride);
 
 // ---- 2-D sprites and tile sets (t3d_sprites.cu) ----
+// Font::drawText (Font.cpp:242-390): the per-call constants of one text.
+struct TextParams
+{
+    int x, y;               // where the pen starts
+    uint32_t size;          // requested size (the font's own when the caller passed 0)
+    float scale;            // (float)size / font size, Font.cpp:268
+    int spacing;            // (int)(size * character spacing), :269
+    uint32_t glyph_count;
+    uint32_t space_advance; // _glyphs[0].advance: what ' ' and '\t' move the pen by (:344, :351)
+    float color[4];
+};
+uint32_t text_tiles(uint32_t n);          // tiles of 256 characters
+size_t text_scratch_bytes(uint32_t n);    // device scratch a text of n bytes needs; its last 16 bytes end up holding {., line breaks, glyphs, .}
+// text: n bytes on the device, 16-byte aligned; glyphs: the font's table on the device; quads go to dst in reading order
+void launch_text(void* stream, const char* text, uint32_t n, const t3d_glyph* glyphs, const TextParams& P, void* scratch, float* dst);
 uint32_t sprite_tiles(uint32_t n); // CTAs (tiles of 256 sprites) a list of n sprites takes
 // tile_scratch: sprite_tiles(n) + 1 words when some sprite may be culled by its clip rectangle (ordered compaction; the
 // last word receives the number of quads written), nullptr when sprite i simply becomes quad i.

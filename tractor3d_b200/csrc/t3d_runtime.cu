@@ -239,6 +239,7 @@ struct t3d_ctx
     uint32_t* sprite_scratch{ nullptr };
     size_t sprite_scratch_words{ 0 };
     std::vector<struct t3d_tileset*> tilesets;
+    std::vector<struct t3d_font*> fonts;
 
     // depth sort (t3d_emitter_depth_sorted_indices): keys / values / library temp / sorted indices, grown on demand
     uint32_t* sort_scratch{ nullptr };
@@ -1534,6 +1535,8 @@ int t3d_ctx_destroy(t3d_ctx* c)
     {
         std::vector<t3d_tileset*> ts = c->tilesets;
         for (t3d_tileset* t : ts) t3d_tileset_destroy(t);
+        std::vector<t3d_font*> fs = c->fonts;
+        for (t3d_font* f : fs) t3d_font_destroy(f);
     }
     for (t3d_ctx::SpriteStage& st : c->sprite_stage)
     {
@@ -2554,6 +2557,15 @@ struct t3d_tileset
     bool dirty{ true };
 };
 
+struct t3d_font
+{
+    t3d_ctx* ctx{ nullptr };
+    uint32_t size{ 0 };     // Font::_size
+    float spacing{ 0.0f };  // Font::_spacing (Font.h:426)
+    std::vector<t3d_glyph> glyphs;
+    t3d_glyph* glyphs_dev{ nullptr };
+};
+
 // Where a list's quads go: the caller's buffer, or the context's own (grown on demand).
 static int sprite_destination(t3d_ctx* c, size_t quads, void* device_dst, size_t dst_quads, float** out)
 {
@@ -2698,6 +2710,146 @@ int t3d_ctx_draw_sprites(t3d_ctx* c, const t3d_sprite2d* sprites, size_t n, int 
             }
             c->d2h_bytes += sizeof(uint32_t);
             *n_quads = total;
+        }
+    }
+    return T3D_OK;
+}
+
+// ---- Font::drawText ----
+int t3d_font_create(t3d_ctx* c, uint32_t size, const t3d_glyph* glyphs, uint32_t glyph_count, t3d_font** out)
+{
+    if (!c || !out || !glyphs) return fail(T3D_ERR_INVALID, "t3d_font_create: null argument (Font.cpp:111-112)");
+    *out = nullptr;
+    if (!size) return fail(T3D_ERR_INVALID, "a font has a size (Font.cpp:249)");
+    if (!glyph_count) return fail(T3D_ERR_INVALID, "a font has glyphs: ' ' and '\\t' advance by the first one's (Font.cpp:344)");
+    T3D_TRY(use_device(c));
+    t3d_font* f = new t3d_font();
+    f->ctx = c;
+    f->size = size;
+    f->glyphs.assign(glyphs, glyphs + glyph_count);
+    if (cudaMalloc((void**)&f->glyphs_dev, glyph_count * sizeof(t3d_glyph)) != cudaSuccess ||
+        cudaMemcpyAsync(f->glyphs_dev, f->glyphs.data(), glyph_count * sizeof(t3d_glyph), cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+    {
+        cudaFree(f->glyphs_dev);
+        delete f;
+        return fail(T3D_ERR_CUDA, "t3d_font_create: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    // (the copy reads f->glyphs, which lives as long as the font; pageable memory: the call returns once it is staged)
+    c->h2d_bytes += glyph_count * sizeof(t3d_glyph);
+    c->fonts.push_back(f);
+    *out = f;
+    return T3D_OK;
+}
+
+int t3d_font_destroy(t3d_font* f)
+{
+    if (!f) return T3D_OK;
+    t3d_ctx* c = f->ctx;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(f->glyphs_dev);
+    c->fonts.erase(std::remove(c->fonts.begin(), c->fonts.end(), f), c->fonts.end());
+    delete f;
+    return T3D_OK;
+}
+
+int t3d_font_set_character_spacing(t3d_font* f, float spacing)
+{
+    if (!f) return fail(T3D_ERR_INVALID, "null font");
+    f->spacing = spacing;
+    return T3D_OK;
+}
+
+int t3d_font_draw_text(t3d_font* f, const char* text, size_t length, uint32_t text_flags, int x, int y, const float color[4], uint32_t size,
+                       int right_to_left, void* device_dst, size_t dst_quads, const t3d_sprite_vertex** device_ptr, uint32_t* n_quads)
+{
+    if (!f || (!text && length) || !color) return fail(T3D_ERR_INVALID, "t3d_font_draw_text: null argument");
+    if (right_to_left) return fail(T3D_ERR_INVALID, "t3d_font_draw_text: the right-to-left walk (Font.cpp:283-327) is not built");
+    if (length > 0xfffffff0u) return fail(T3D_ERR_INVALID, "t3d_font_draw_text: text too long");
+    t3d_ctx* c = f->ctx;
+    T3D_TRY(use_device(c));
+    if (size == 0) size = f->size; // Font.cpp:253-256
+    const bool on_device = (text_flags & T3D_TEXT_ON_DEVICE) != 0;
+    if (on_device && (reinterpret_cast<uintptr_t>(text) & 15u)) return fail(T3D_ERR_INVALID, "t3d_font_draw_text: device-resident text must be 16-byte aligned");
+    // how many characters draw: known here for host text (Font.cpp:354-357: a signed char with 0 <= c - 32 < glyphCount that
+    // is not ' '); for device text every byte might
+    size_t quads = length;
+    if (!on_device)
+    {
+        HostTimer ht(c, T3D_HOST_BUILD);
+        quads = 0;
+        const uint32_t gc = (uint32_t)f->glyphs.size();
+        for (size_t i = 0; i < length; ++i)
+        {
+            const unsigned char b = (unsigned char)text[i];
+            quads += (b > 32u && b < 128u && b - 32u < gc) ? 1u : 0u;
+        }
+    }
+    float* dst = nullptr;
+    T3D_TRY(sprite_destination(c, quads, device_dst, dst_quads, &dst));
+    if (device_ptr) *device_ptr = reinterpret_cast<const t3d_sprite_vertex*>(dst);
+    if (n_quads) *n_quads = 0;
+    if (length == 0) return T3D_OK;
+    const char* dev_text = text;
+    t3d_ctx::SpriteStage* stage = nullptr;
+    if (!on_device)
+    {
+        T3D_TRY(sprite_stage_acquire(c, length, &stage));
+        c->sprite_stage_next ^= 1;
+        {
+            HostTimer ht(c, T3D_HOST_BUILD);
+            memcpy(stage->host, text, length);
+        }
+        T3D_CUDA(cudaMemcpyAsync(stage->dev, stage->host, length, cudaMemcpyHostToDevice, c->stream));
+        c->h2d_bytes += length;
+        dev_text = stage->dev;
+    }
+    const size_t scratch_words = (text_scratch_bytes((uint32_t)length) + 3) / 4;
+    if (c->sprite_scratch_words < scratch_words)
+    {
+        if (c->sprite_scratch)
+        {
+            T3D_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(c->sprite_scratch);
+            c->sprite_scratch = nullptr;
+            c->sprite_scratch_words = 0;
+        }
+        const size_t cap = std::max<size_t>(scratch_words * 2, 1024);
+        T3D_CUDA(cudaMalloc((void**)&c->sprite_scratch, cap * sizeof(uint32_t)));
+        c->sprite_scratch_words = cap;
+    }
+    TextParams P{};
+    P.x = x;
+    P.y = y;
+    P.size = size;
+    P.scale = (float)size / (float)f->size;   // Font.cpp:268
+    P.spacing = (int)((float)size * f->spacing); // :269
+    P.glyph_count = (uint32_t)f->glyphs.size();
+    P.space_advance = f->glyphs[0].advance;
+    memcpy(P.color, color, sizeof(P.color));
+    launch_text(c->stream, dev_text, (uint32_t)length, f->glyphs_dev, P, c->sprite_scratch, dst);
+    T3D_CUDA(cudaGetLastError());
+    c->launches += 3;
+    if (stage)
+    {
+        T3D_CUDA(cudaEventRecord(stage->done, c->stream));
+        stage->in_flight = true;
+    }
+    if (n_quads)
+    {
+        if (!on_device)
+            *n_quads = (uint32_t)quads;
+        else
+        {
+            uint32_t total[4] = { 0, 0, 0, 0 }; // {advance, line breaks, glyphs, .} of the whole text
+            T3D_CUDA(cudaMemcpyAsync(total, reinterpret_cast<const char*>(c->sprite_scratch) + text_scratch_bytes((uint32_t)length) - 16, 16,
+                                     cudaMemcpyDeviceToHost, c->stream));
+            {
+                HostTimer ht(c, T3D_HOST_WAIT);
+                T3D_CUDA(cudaStreamSynchronize(c->stream));
+            }
+            c->d2h_bytes += 16;
+            *n_quads = total[2];
         }
     }
     return T3D_OK;

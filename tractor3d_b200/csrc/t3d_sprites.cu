@@ -281,8 +281,221 @@ __global__ void __launch_bounds__(kSpriteThreads)
 }
 
 // --------------------------------------------------------------------------------------------------
+// Font::drawText(text, x, y, color, size) (src/renderer/Font.cpp:242-390, left to right): the reference walks the string with a
+// running pen -- ' ' and '\t' advance it by the first glyph's advance (x 4), '\r' / '\n' start a new line, a character with a
+// glyph draws one quad (SpriteBatch::draw(x, y, w, h, u1, v1, u2, v2, color), SB.cpp:366-378 -> :475-506) and advances by
+// floor(advance * scale + spacing); everything else (also every byte >= 128: `char` is signed, Font.cpp:359) is skipped.
+// The pen is an int and the advances are integers (the reference adds them in double, exactly), so the walk is a
+// segmented scan: element = (advance since the last line break, line breaks, glyphs), combined left to right.
+//   k_text_summary   every thread folds 16 characters (one 128-bit load), 16 lanes fold a tile of 256
+//   k_text_scan      exclusive scan of the tile elements (one CTA)
+//   k_text_expand    a tile's characters: in-tile scan, one quad per glyph at its rank among the text's glyphs, bulk store
+// --------------------------------------------------------------------------------------------------
+struct TextElem
+{
+    int adv;          // pen advance since the last line break (or since the start, when there is none)
+    uint32_t breaks;  // line breaks
+    uint32_t glyphs;  // characters that draw
+    uint32_t pad;
+};
+__device__ __forceinline__ TextElem text_combine(const TextElem& a, const TextElem& b) // a before b
+{
+    TextElem r;
+    r.adv = b.breaks ? b.adv : a.adv + b.adv;
+    r.breaks = a.breaks + b.breaks;
+    r.glyphs = a.glyphs + b.glyphs;
+    r.pad = 0;
+    return r;
+}
+__device__ __forceinline__ TextElem text_shfl_up(const TextElem& v, int o, int width)
+{
+    TextElem t;
+    t.adv = __shfl_up_sync(0xffffffffu, v.adv, o, width);
+    t.breaks = __shfl_up_sync(0xffffffffu, v.breaks, o, width);
+    t.glyphs = __shfl_up_sync(0xffffffffu, v.glyphs, o, width);
+    t.pad = 0;
+    return t;
+}
+constexpr int kTextTile = 256;       // characters per tile
+constexpr int kTextClasses = 128;    // a signed char that can have a glyph: 32 .. 127
+// per-character-code tables, built once per CTA: what the code adds to the pen, and whether it draws
+struct TextTables
+{
+    int adv[kTextClasses];           // ' ', '\t', glyph advances (Font.cpp:344, :351, :378); 0 for everything else
+    unsigned char kind[kTextClasses]; // 0 nothing, 1 line break, 2 glyph
+};
+__device__ __forceinline__ void text_build_tables(TextTables& t, const t3d_glyph* __restrict__ glyphs, const TextParams& P, uint32_t tid, uint32_t threads)
+{
+    for (uint32_t c = tid; c < (uint32_t)kTextClasses; c += threads)
+    {
+        int adv = 0;
+        unsigned char kind = 0;
+        if (c == ' ') adv = (int)P.space_advance;                 // Font.cpp:343-345
+        else if (c == '\t') adv = (int)(P.space_advance * 4u);    // :350-352
+        else if (c == '\r' || c == '\n') kind = 1;                // :346-349
+        else if (c >= 32u && c - 32u < P.glyph_count)             // :354-355 (index = c - 32)
+        {
+            kind = 2;
+            adv = (int)floorf(__uint2float_rn(glyphs[c - 32u].advance) * P.scale + (float)P.spacing); // :378
+        }
+        t.adv[c] = adv;
+        t.kind[c] = kind;
+    }
+}
+__device__ __forceinline__ TextElem text_elem(const TextTables& t, unsigned char byte)
+{
+    TextElem e = { 0, 0u, 0u, 0u };
+    if (byte < (unsigned char)kTextClasses)
+    {
+        const unsigned char k = t.kind[byte];
+        e.adv = t.adv[byte];
+        e.breaks = k == 1;
+        e.glyphs = k == 2;
+    }
+    return e;
+}
+
+__global__ void __launch_bounds__(256) k_text_summary(const unsigned char* __restrict__ text, uint32_t n, const t3d_glyph* __restrict__ glyphs,
+                                                      TextParams P, TextElem* __restrict__ tile_elems)
+{
+    __shared__ TextTables s_t;
+    text_build_tables(s_t, glyphs, P, threadIdx.x, 256);
+    __syncthreads();
+    const uint32_t first = (blockIdx.x * 256u + threadIdx.x) * 16u; // 16 threads = one tile of 256 characters
+    unsigned char b[16];
+    if (first + 16u <= n)
+    {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(text + first));
+        memcpy(b, &v, 16);
+    }
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) b[k] = first + k < n ? text[first + k] : (unsigned char)0xff; // past the end: a byte that does nothing
+    }
+    TextElem e = text_elem(s_t, b[0]);
+#pragma unroll
+    for (int k = 1; k < 16; ++k) e = text_combine(e, text_elem(s_t, b[k]));
+    // fold the 16 lanes of a tile (an inclusive scan; its last lane holds the tile's element)
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1)
+    {
+        const TextElem t = text_shfl_up(e, o, 16);
+        if ((int)(threadIdx.x & 15u) >= o) e = text_combine(t, e);
+    }
+    const uint32_t tile = first / (uint32_t)kTextTile;
+    if ((threadIdx.x & 15u) == 15u && (unsigned long long)tile * kTextTile < n) tile_elems[tile] = e;
+}
+
+// elems[0 .. n_tiles) -> exclusive prefix in place; elems[n_tiles] = the whole text.  One CTA.
+__global__ void __launch_bounds__(1024) k_text_scan(TextElem* __restrict__ elems, uint32_t n_tiles)
+{
+    __shared__ TextElem s_warp[32];
+    __shared__ TextElem s_carry;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = TextElem{ 0, 0u, 0u, 0u };
+    __syncthreads();
+    for (uint32_t base = 0; base < n_tiles; base += 1024)
+    {
+        const uint32_t i = base + threadIdx.x;
+        const TextElem own = i < n_tiles ? elems[i] : TextElem{ 0, 0u, 0u, 0u };
+        TextElem incl = own;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const TextElem t = text_shfl_up(incl, o, 32);
+            if ((int)lane >= o) incl = text_combine(t, incl);
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        TextElem before = s_carry;
+        for (uint32_t w = 0; w < warp; ++w) before = text_combine(before, s_warp[w]);
+        // exclusive = everything before this warp, then the lanes before this one
+        const TextElem prev = text_shfl_up(incl, 1, 32);
+        const TextElem excl = lane ? text_combine(before, prev) : before;
+        if (i < n_tiles) elems[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = text_combine(excl, own);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) elems[n_tiles] = s_carry;
+}
+
+__global__ void __launch_bounds__(kTextTile) k_text_expand(const unsigned char* __restrict__ text, uint32_t n, const t3d_glyph* __restrict__ glyphs,
+                                                           TextParams P, const TextElem* __restrict__ tile_prefix, float* __restrict__ dst)
+{
+    __shared__ __align__(128) float4 s_buf[kTextTile * 9];
+    __shared__ TextTables s_t;
+    __shared__ TextElem s_warp[kTextTile / 32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    text_build_tables(s_t, glyphs, P, tid, kTextTile);
+    const uint32_t i = blockIdx.x * (uint32_t)kTextTile + tid;
+    const unsigned char byte = i < n ? text[i] : (unsigned char)0xff;
+    const TextElem before_tile = tile_prefix[blockIdx.x];
+    __syncthreads();
+    const TextElem own = text_elem(s_t, byte);
+    TextElem incl = own;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const TextElem t = text_shfl_up(incl, o, 32);
+        if ((int)lane >= o) incl = text_combine(t, incl);
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    TextElem before = before_tile;
+    TextElem tile_all = before_tile;
+#pragma unroll
+    for (int w = 0; w < kTextTile / 32; ++w)
+    {
+        if ((uint32_t)w < warp) before = text_combine(before, s_warp[w]);
+        tile_all = text_combine(tile_all, s_warp[w]);
+    }
+    const TextElem prev = text_shfl_up(incl, 1, 32);
+    const TextElem excl = lane ? text_combine(before, prev) : before; // the pen before this character
+    if (own.glyphs)
+    {
+        const t3d_glyph g = glyphs[byte - 32u];
+        const int pen_x = P.x + excl.adv;                                   // Font.cpp:272, :344-378
+        const int pen_y = (int)((uint32_t)P.y + excl.breaks * P.size);      // :348 (yPos += size, an unsigned added to an int)
+        const float x = (float)(pen_x + __float2int_rz((float)g.bearing_x * P.scale)); // :369
+        const float y = (float)pen_y;
+        const float w = __uint2float_rn(g.width) * P.scale;                 // :371
+        const float h = __uint2float_rn(P.size);                            // :372
+        const float x2 = x + w, y2 = y + h;                                 // SB.cpp:493-494
+        const float px[4] = { x, x, x2, x2 }, py[4] = { y, y2, y, y2 };     // SB.cpp:496-501
+        write_quad(s_buf + (excl.glyphs - before_tile.glyphs) * 9, px, py, 0.0f, g.uvs[0], g.uvs[1], g.uvs[2], g.uvs[3], P.color);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const uint32_t tile_glyphs = tile_all.glyphs - before_tile.glyphs;
+    if (tid == 0 && tile_glyphs)
+    {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + (size_t)before_tile.glyphs * kQuadFloats),
+                     "r"((uint32_t)__cvta_generic_to_shared(s_buf)), "r"(tile_glyphs * (uint32_t)(kQuadFloats * 4)) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
 // launch wrappers
 // --------------------------------------------------------------------------------------------------
+uint32_t text_tiles(uint32_t n) { return (n + kTextTile - 1) / kTextTile; }
+size_t text_scratch_bytes(uint32_t n) { return ((size_t)text_tiles(n) + 1) * sizeof(TextElem); }
+
+void launch_text(void* stream, const char* text, uint32_t n, const t3d_glyph* glyphs, const TextParams& P, void* scratch, float* dst)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t tiles = text_tiles(n);
+    if (!tiles) return;
+    TextElem* elems = static_cast<TextElem*>(scratch);
+    const unsigned char* t = reinterpret_cast<const unsigned char*>(text);
+    k_text_summary<<<(tiles + 15) / 16, 256, 0, st>>>(t, n, glyphs, P, elems);
+    k_text_scan<<<1, 1024, 0, st>>>(elems, tiles);
+    k_text_expand<<<tiles, kTextTile, 0, st>>>(t, n, glyphs, P, elems, dst);
+}
+
 uint32_t sprite_tiles(uint32_t n) { return (n + kSpriteThreads - 1) / kSpriteThreads; }
 
 void launch_sprites(void* stream, const t3d_sprite2d* sprites, uint32_t n, uint32_t* tile_scratch, float* dst)

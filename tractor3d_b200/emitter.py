@@ -213,6 +213,39 @@ class Context:
         return out
 
 
+class Font:
+    """One size of tractor::Font (include/renderer/Font.h): drawText(text, x, y, color, size) laid out and expanded on the device."""
+
+    def __init__(self, ctx, size, glyphs):
+        """glyphs: numpy array of abi.GLYPH_DTYPE (Font::Glyph: code, width, bearingX, advance, uvs[4]); glyph k is character 32 + k."""
+        self.ctx, self.lib = ctx, ctx.lib
+        g = np.ascontiguousarray(glyphs, dtype=abi.GLYPH_DTYPE)
+        self.h = C.c_void_p()
+        _check(self.lib, self.lib.t3d_font_create(ctx.h, size, g.ctypes.data, len(g), C.byref(self.h)))
+
+    def setCharacterSpacing(self, spacing):
+        _check(self.lib, self.lib.t3d_font_set_character_spacing(self.h, spacing))
+
+    def drawText(self, text, x, y, color, size=0, right_to_left=False, device_dst=None, dst_quads=0, text_on_device=None):
+        """text: bytes (uploaded) -- or, with text_on_device=(pointer, length), text already on the device.  Returns
+        (device pointer of the quads, number of quads)."""
+        col = np.ascontiguousarray(color, dtype=np.float32)
+        ptr, nq = C.c_void_p(), C.c_uint32()
+        if text_on_device is not None:
+            tp, length, flags = C.c_void_p(text_on_device[0]), text_on_device[1], abi.TEXT_ON_DEVICE
+        else:
+            buf = C.create_string_buffer(bytes(text), len(text))
+            tp, length, flags = C.cast(buf, C.c_void_p), len(text), 0
+        _check(self.lib, self.lib.t3d_font_draw_text(self.h, tp, length, flags, x, y, _fptr(col), size, 1 if right_to_left else 0,
+                                                     C.c_void_p(device_dst) if device_dst else None, dst_quads, C.byref(ptr), C.byref(nq)))
+        return ptr.value, nq.value
+
+    def release(self):
+        if self.h:
+            self.lib.t3d_font_destroy(self.h)
+            self.h = None
+
+
 class TileSet:
     """tractor::TileSet's draw path (include/graphics/TileSet.h) with the tile table resident on the device."""
 
