@@ -384,9 +384,10 @@ int t3d_font_create(t3d_ctx* ctx, uint32_t size, const t3d_glyph* glyphs, uint32
 int t3d_font_destroy(t3d_font* f);
 int t3d_font_set_character_spacing(t3d_font* f, float spacing);                                   /* Font.h:246 */
 #define T3D_TEXT_ON_DEVICE 1u   /* `text` is a device pointer (16-byte aligned); nothing is uploaded */
-/* size = 0: the font's own size (Font.cpp:253-256).  right_to_left: T3D_ERR_INVALID (the reference's per-line reversed walk,
- * Font.cpp:283-327, is not built).  Destination as in t3d_ctx_draw_sprites; *n_quads = characters drawn (counted on the host
- * for host text; read back from the device, with a wait, for T3D_TEXT_ON_DEVICE). */
+/* size = 0: the font's own size (Font.cpp:253-256).  right_to_left: the reference's other walk (Font.cpp:283-327) -- the
+ * blanks a line starts with forwards, then the rest of the line from its last character backwards; the text then ends at
+ * its first NUL (c_str()), which device-resident text must not contain.  Destination as in t3d_ctx_draw_sprites; *n_quads =
+ * characters drawn (counted on the host for host text; read back from the device, with a wait, for T3D_TEXT_ON_DEVICE). */
 int t3d_font_draw_text(t3d_font* f, const char* text, size_t length, uint32_t text_flags, int x, int y, const float color[4],
                        uint32_t size, int right_to_left, void* device_dst, size_t dst_quads, const t3d_sprite_vertex** device_ptr,
                        uint32_t* n_quads);

@@ -866,46 +866,77 @@ uint32_t orc_tileset_draw(const float* sources, uint32_t rows, uint32_t cols, fl
     return quads;
 }
 
-/* Font::drawText(text, x, y, color, size, rightToLeft = false), src/renderer/Font.cpp:242-390, for ONE size of a font
- * (size delegation, :258-264, is the caller's): the pen walk, one SpriteBatch::draw(x, y, w, h, u1, v1, u2, v2, color) per
+/* Font::drawText(text, x, y, color, size, rightToLeft), src/renderer/Font.cpp:242-390, for ONE size of a font (size
+ * delegation, :258-264, is the caller's): the pen walk, one SpriteBatch::draw(x, y, w, h, u1, v1, u2, v2, color) per
  * character with a glyph (SB.cpp:366-378 -> :475-506, z = 0, position not centred).  36 floats per quad. */
+typedef struct {
+    const t3d_glyph* glyphs; uint32_t glyph_count; float scale; int spacing; uint32_t size; int x0;
+    int x_pos, y_pos; const float* color; float* out; size_t max_quads; uint32_t quads;
+} font_walk;
+static void font_walk_char(font_walk* w, signed char c)                                /* :340: `char`, signed on the reference's platforms */
+{
+    float scratch[36];
+    switch (c) {                                                                       /* :342-384 */
+    case ' ':  w->x_pos = (int)((unsigned)w->x_pos + w->glyphs[0].advance); break;
+    case '\r':
+    case '\n': w->y_pos = (int)((unsigned)w->y_pos + w->size); w->x_pos = w->x0; break;
+    case '\t': w->x_pos = (int)((unsigned)w->x_pos + w->glyphs[0].advance * 4u); break;
+    default: {
+        const int index = c - 32;                                                      /* :354 */
+        if (index >= 0 && index < (int)w->glyph_count) {
+            const t3d_glyph* g = &w->glyphs[index];
+            t3d_sprite2d sp;
+            memset(&sp, 0, sizeof(sp));
+            sp.x = (float)(w->x_pos + (int)((float)g->bearing_x * w->scale));          /* :369 */
+            sp.y = (float)w->y_pos;
+            sp.width = (float)g->width * w->scale;                                     /* :371 */
+            sp.height = (float)w->size;
+            sp.u1 = g->uvs[0]; sp.v1 = g->uvs[1]; sp.u2 = g->uvs[2]; sp.v2 = g->uvs[3];
+            memcpy(sp.color, w->color, 16);
+            w->quads += (uint32_t)sprite_quad(&sp, (w->out && w->quads < w->max_quads) ? w->out + (size_t)w->quads * 36 : scratch);
+            /* :378: `xPos += floor(...)` -- the floor is taken in float, the sum in double (exact), back to int */
+            w->x_pos = (int)((double)w->x_pos + (double)floorf((float)g->advance * w->scale + (float)w->spacing));
+        }
+        break;
+    }
+    }
+}
 uint32_t orc_font_draw_text(const t3d_glyph* glyphs, uint32_t glyph_count, uint32_t font_size, float character_spacing,
-                            const char* text, size_t length, int x, int y, const float color[4], uint32_t size, float* out, size_t max_quads)
+                            const char* text, size_t length, int x, int y, const float color[4], uint32_t size, int right_to_left,
+                            float* out, size_t max_quads)
 {
     if (size == 0) size = font_size;                                  /* :253-256 */
-    const float scale = (float)size / (float)font_size;               /* :268 */
-    const int spacing = (int)((float)size * character_spacing);       /* :269 */
-    int x_pos = x, y_pos = y;                                         /* :277 */
-    uint32_t quads = 0;
-    float scratch[36];
-    for (size_t i = 0; i < length; ++i) {                             /* :330 (text.length(), so embedded NULs are walked over) */
-        const signed char c = (signed char)text[i];                   /* :340: `char`, signed on the reference's platforms */
-        switch (c) {
-        case ' ':  x_pos = (int)((unsigned)x_pos + glyphs[0].advance); break;          /* :343-345 */
-        case '\r':
-        case '\n': y_pos = (int)((unsigned)y_pos + size); x_pos = x; break;            /* :346-349 */
-        case '\t': x_pos = (int)((unsigned)x_pos + glyphs[0].advance * 4u); break;     /* :350-352 */
-        default: {
-            const int index = c - 32;                                                  /* :354 */
-            if (index >= 0 && index < (int)glyph_count) {
-                const t3d_glyph* g = &glyphs[index];
-                t3d_sprite2d sp;
-                memset(&sp, 0, sizeof(sp));
-                sp.x = (float)(x_pos + (int)((float)g->bearing_x * scale));            /* :369 */
-                sp.y = (float)y_pos;
-                sp.width = (float)g->width * scale;                                    /* :371 */
-                sp.height = (float)size;
-                sp.u1 = g->uvs[0]; sp.v1 = g->uvs[1]; sp.u2 = g->uvs[2]; sp.v2 = g->uvs[3];
-                memcpy(sp.color, color, 16);
-                quads += (uint32_t)sprite_quad(&sp, (out && quads < max_quads) ? out + (size_t)quads * 36 : scratch);
-                /* :378: `xPos += floor(...)` -- the floor is taken in float, the sum in double (exact), back to int */
-                x_pos = (int)((double)x_pos + (double)floorf((float)g->advance * scale + (float)spacing));
-            }
-            break;
-        }
-        }
+    font_walk w;
+    w.glyphs = glyphs; w.glyph_count = glyph_count; w.size = size; w.x0 = x;
+    w.scale = (float)size / (float)font_size;                         /* :268 */
+    w.spacing = (int)((float)size * character_spacing);               /* :269 */
+    w.x_pos = x; w.y_pos = y;                                         /* :277 */
+    w.color = color; w.out = out; w.max_quads = max_quads; w.quads = 0;
+    if (!right_to_left) {
+        for (size_t i = 0; i < length; ++i) font_walk_char(&w, (signed char)text[i]);   /* :330 (text.length(): embedded NULs are walked over) */
+        return w.quads;
     }
-    return quads;
+    /* :283-327, :386-389: per line, the delimiters it starts with going forwards, then the rest of it from its last character
+     * backwards; the walk is over text.c_str(), so it ends at the first NUL */
+    size_t end = 0;
+    while (end < length && text[end] != 0) ++end;
+    size_t cursor = 0;
+    for (;;) {
+        int done = 0;
+        for (;;) {                                                    /* :287-315 */
+            if (cursor >= end) { done = 1; break; }
+            const char d = text[cursor];
+            if (!(d == ' ' || d == '\t' || d == '\r' || d == '\n')) break;
+            font_walk_char(&w, (signed char)d);                       /* (the same three cases of the switch) */
+            ++cursor;
+        }
+        if (done) break;
+        size_t len = 0;                                               /* :317 strcspn(cursor, "\r\n") */
+        while (cursor + len < end && text[cursor + len] != '\r' && text[cursor + len] != '\n') ++len;
+        for (size_t i = len; i-- > 0;) font_walk_char(&w, (signed char)text[cursor + i]); /* :318-319, :330 */
+        cursor += len;                                                /* :387 */
+    }
+    return w.quads;
 }
 
 /* =====================================================================================

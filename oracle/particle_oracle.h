@@ -85,9 +85,10 @@ uint32_t orc_sprites_2d(const t3d_sprite2d* sprites, size_t n, float* out, size_
 /* TileSet::draw (TileSet.cpp:207-236) from the position it has computed by line 205. */
 uint32_t orc_tileset_draw(const float* sources, uint32_t rows, uint32_t cols, float tile_w, float tile_h, float tex_w, float tex_h,
                           const float position[3], const float color[4], float* out, size_t max_quads);
-/* Font::drawText(text, x, y, color, size), Font.cpp:242-390 left to right, one font size; 36 floats per quad. */
+/* Font::drawText(text, x, y, color, size, rightToLeft), Font.cpp:242-390, one font size; 36 floats per quad. */
 uint32_t orc_font_draw_text(const t3d_glyph* glyphs, uint32_t glyph_count, uint32_t font_size, float character_spacing,
-                            const char* text, size_t length, int x, int y, const float color[4], uint32_t size, float* out, size_t max_quads);
+                            const char* text, size_t length, int x, int y, const float color[4], uint32_t size, int right_to_left,
+                            float* out, size_t max_quads);
 
 /* ---- timing loops (seconds) for bench.py's cpu_baseline "port" leg ---- */
 double orc_time_update(orc_emitter* e, float elapsed_ms, int frames);

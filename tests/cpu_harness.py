@@ -94,7 +94,7 @@ class CpuLib:
             proto("tileset_draw", C.c_uint32, [_P(C.c_float), C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float,
                                                _P(C.c_float), _P(C.c_float), _P(C.c_float), C.c_size_t])
             proto("font_draw_text", C.c_uint32, [_vp, C.c_uint32, C.c_uint32, C.c_float, C.c_char_p, C.c_size_t, C.c_int, C.c_int, _P(C.c_float),
-                                                 C.c_uint32, _P(C.c_float), C.c_size_t])
+                                                 C.c_uint32, C.c_int, _P(C.c_float), C.c_size_t])
             proto("device_rng_draw", C.c_int32, [C.c_uint64, C.c_uint64, C.c_uint32])
             proto("reset_statics", None, [])
             proto("set_rotation_mode", None, [C.c_int])

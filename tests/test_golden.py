@@ -67,7 +67,7 @@ def test_oracle_reproduces_reference_golden_sprites():
     text = z["text"].tobytes()
     got = np.zeros((len(text), 36), dtype=np.float32)
     n = O.font_draw_text(g.ctypes.data, g.size, int(z["font_size"]), float(z["spacing"]), text, len(text), int(z["origin"][0]), int(z["origin"][1]),
-                         fp(np.ascontiguousarray(z["color"])), int(z["size"]), fp(got), len(text))
+                         fp(np.ascontiguousarray(z["color"])), int(z["size"]), 0, fp(got), len(text))
     assert n == z["vertices"].shape[0] < len(text)
     assert np.array_equal(got[:n].view(np.uint32), z["vertices"])
     z = _sprite_fixture("tileset")

@@ -173,9 +173,9 @@ def test_sprites_and_tiles_against_the_reference_fixtures():
 
 
 # ---- Font::drawText (Font.cpp:242-390) ----
-def _oracle_text(O, g, font_size, spacing, text, x, y, color, size):
+def _oracle_text(O, g, font_size, spacing, text, x, y, color, size, rtl=False):
     out = np.zeros((max(len(text), 1), 4, 9), dtype=np.float32)
-    n = O.font_draw_text(g.ctypes.data, g.size, font_size, spacing, text, len(text), x, y, fp(color), size, fp(out), len(text))
+    n = O.font_draw_text(g.ctypes.data, g.size, font_size, spacing, text, len(text), x, y, fp(color), size, 1 if rtl else 0, fp(out), len(text))
     return out[:n]
 
 
@@ -196,6 +196,13 @@ def test_text_is_laid_out_like_font_drawtext(n):
             ptr, nq = font.drawText(text, x0, 40, color, size)
             assert nq == want.shape[0] and (n < 100 or 0 < nq < n)
             assert np.array_equal(ctx.download_quads(ptr, nq).view(np.uint32), want.view(np.uint32))
+            # right to left (Font.cpp:283-327): every line from its last character backwards, the text up to its first NUL
+            for t in (text, text.replace(bytes([0]), bytes([1]))):
+                want = _oracle_text(O, g, font_size, spacing, t, x0, 40, color, size, rtl=True)
+                ptr, nq = font.drawText(t, x0, 40, color, size, right_to_left=True)
+                assert nq == want.shape[0]
+                if nq:
+                    assert np.array_equal(ctx.download_quads(ptr, nq).view(np.uint32), want.view(np.uint32))
             font.release()
     finally:
         ctx.close()
@@ -210,12 +217,13 @@ def test_text_edge_cases_and_device_resident_text():
         g = H.random_font(3, 95, 24)
         font = Font(ctx, 24, g)
         # nothing but line breaks and blanks; one long line without a break; only bytes the walk skips; a break as the last byte
-        for text in (b"\n\r\n   \t\n", bytes(range(33, 127)) * 300, bytes([200, 0, 7, 255]) * 100, b"ab\ncd\n", b"\tx"):
-            want = _oracle_text(O, g, 24, 0.0, text, 3, -9, color, 0)
-            ptr, nq = font.drawText(text, 3, -9, color)
-            assert nq == want.shape[0]
-            if nq:
-                assert np.array_equal(ctx.download_quads(ptr, nq).view(np.uint32), want.view(np.uint32))
+        for text in (b"\n\r\n   \t\n", bytes(range(33, 127)) * 300, bytes([200, 0, 7, 255]) * 100, b"ab\ncd\n", b"\tx", b"  a b  \n\t\tc\td \r e"):
+            for rtl in (False, True):
+                want = _oracle_text(O, g, 24, 0.0, text, 3, -9, color, 0, rtl)
+                ptr, nq = font.drawText(text, 3, -9, color, right_to_left=rtl)
+                assert nq == want.shape[0], (text[:20], rtl)
+                if nq:
+                    assert np.array_equal(ctx.download_quads(ptr, nq).view(np.uint32), want.view(np.uint32)), (text[:20], rtl)
         # the text already on the device, the quads into a foreign allocation; the count comes back from the device
         text = H.random_text(50_000, 77)
         want = _oracle_text(O, g, 24, 0.0, text, 0, 0, color, 36)
@@ -227,11 +235,9 @@ def test_text_edge_cases_and_device_resident_text():
         assert ptr == dst.data_ptr() and nq == want.shape[0]
         assert np.array_equal(dst.cpu().numpy()[:nq * 36].view(np.uint32).reshape(nq, 4, 9), want.view(np.uint32))
         assert float(dst[nq * 36:].abs().sum()) == 0.0          # nothing written beyond the text's quads
-        # errors are codes: a destination that is too small, the walk that is not built
+        # errors are codes: a destination that is too small
         with pytest.raises(Exception):
             font.drawText(b"abc", 0, 0, color, device_dst=dst.data_ptr(), dst_quads=2)
-        with pytest.raises(Exception):
-            font.drawText(b"abc", 0, 0, color, right_to_left=True)
         font.release()
     finally:
         ctx.close()

@@ -282,7 +282,7 @@ def test_tileset_draw_matches_the_reference():
 
 
 def test_font_draw_text_matches_the_reference():
-    # Font::drawText(text, x, y, color, size) through the reference's own Font.cpp (left to right): fonts with fewer glyphs than
+    # Font::drawText(text, x, y, color, size, rightToLeft) through the reference's own Font.cpp, both walks: fonts with fewer glyphs than
     # printable characters, scaled sizes (the floor / truncation paths), character spacing, lines, tabs, control bytes, NULs and
     # bytes >= 128 -- the restatement must leave the same quads, bit for bit.
     O, R = H.oracle(fresh=True), H.ref(fresh=True)
@@ -297,10 +297,18 @@ def test_font_draw_text_matches_the_reference():
         h = R.font_create(font_size, g.ctypes.data, glyph_count, 512, 512)
         assert h
         R.font_set_character_spacing(h, spacing)
-        want = np.zeros((n, 36), dtype=np.float32)
-        nr = R.font_draw_text(h, text, n, x0, 40, fp(color), size, 0, fp(want), n, None)
+        for rtl in (0, 1):
+            # (right to left the walk is over c_str(): it ends at the text's first NUL, which these texts do contain)
+            want = np.zeros((n, 36), dtype=np.float32)
+            nr = R.font_draw_text(h, text, n, x0, 40, fp(color), size, rtl, fp(want), n, None)
+            got = np.zeros((n, 36), dtype=np.float32)
+            no = O.font_draw_text(g.ctypes.data, glyph_count, font_size, spacing, text, n, x0, 40, fp(color), size, rtl, fp(got), n)
+            assert no == nr and (n < 100 or 0 < nr < n), (glyph_count, n, rtl)
+            assert np.array_equal(got[:no].view(np.uint32), want[:nr].view(np.uint32)), (glyph_count, font_size, size, spacing, n, rtl)
+            if rtl and n > 100:
+                t2 = text.replace(b"\x00", b"\x01")      # the whole text, right to left
+                nr = R.font_draw_text(h, t2, n, x0, 40, fp(color), size, 1, fp(want), n, None)
+                no = O.font_draw_text(g.ctypes.data, glyph_count, font_size, spacing, t2, n, x0, 40, fp(color), size, 1, fp(got), n)
+                assert no == nr > 0
+                assert np.array_equal(got[:no].view(np.uint32), want[:nr].view(np.uint32)), (glyph_count, n, "rtl, no NUL")
         R.font_destroy(h)
-        got = np.zeros((n, 36), dtype=np.float32)
-        no = O.font_draw_text(g.ctypes.data, glyph_count, font_size, spacing, text, n, x0, 40, fp(color), size, fp(got), n)
-        assert no == nr and (n < 100 or 0 < nr < n), (glyph_count, n)
-        assert np.array_equal(got[:no].view(np.uint32), want[:nr].view(np.uint32)), (glyph_count, font_size, size, spacing, n)

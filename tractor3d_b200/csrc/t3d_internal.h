@@ -236,9 +236,10 @@ struct TextParams
     float color[4];
 };
 uint32_t text_tiles(uint32_t n);          // tiles of 256 characters
-size_t text_scratch_bytes(uint32_t n);    // device scratch a text of n bytes needs; its last 16 bytes end up holding {., line breaks, glyphs, .}
+size_t text_scratch_bytes(uint32_t n);    // device scratch a text of n bytes needs; its last 48 bytes end up holding {., line breaks, glyphs, ...}
 // text: n bytes on the device, 16-byte aligned; glyphs: the font's table on the device; quads go to dst in reading order
-void launch_text(void* stream, const char* text, uint32_t n, const t3d_glyph* glyphs, const TextParams& P, void* scratch, float* dst);
+void launch_text(void* stream, const char* text, uint32_t n, const t3d_glyph* glyphs, const TextParams& P, bool right_to_left, void* scratch,
+                 float* dst);
 uint32_t sprite_tiles(uint32_t n); // CTAs (tiles of 256 sprites) a list of n sprites takes
 // tile_scratch: sprite_tiles(n) + 1 words when some sprite may be culled by its clip rectangle (ordered compaction; the
 // last word receives the number of quads written), nullptr when sprite i simply becomes quad i.

@@ -2764,12 +2764,13 @@ int t3d_font_draw_text(t3d_font* f, const char* text, size_t length, uint32_t te
                        int right_to_left, void* device_dst, size_t dst_quads, const t3d_sprite_vertex** device_ptr, uint32_t* n_quads)
 {
     if (!f || (!text && length) || !color) return fail(T3D_ERR_INVALID, "t3d_font_draw_text: null argument");
-    if (right_to_left) return fail(T3D_ERR_INVALID, "t3d_font_draw_text: the right-to-left walk (Font.cpp:283-327) is not built");
     if (length > 0xfffffff0u) return fail(T3D_ERR_INVALID, "t3d_font_draw_text: text too long");
     t3d_ctx* c = f->ctx;
     T3D_TRY(use_device(c));
     if (size == 0) size = f->size; // Font.cpp:253-256
     const bool on_device = (text_flags & T3D_TEXT_ON_DEVICE) != 0;
+    // right to left the reference walks text.c_str(): the text ends at its first NUL (Font.cpp:275, :301-303)
+    if (right_to_left && !on_device) length = strnlen(text, length);
     if (on_device && (reinterpret_cast<uintptr_t>(text) & 15u)) return fail(T3D_ERR_INVALID, "t3d_font_draw_text: device-resident text must be 16-byte aligned");
     // how many characters draw: known here for host text (Font.cpp:354-357: a signed char with 0 <= c - 32 < glyphCount that
     // is not ' '); for device text every byte might
@@ -2827,7 +2828,7 @@ int t3d_font_draw_text(t3d_font* f, const char* text, size_t length, uint32_t te
     P.glyph_count = (uint32_t)f->glyphs.size();
     P.space_advance = f->glyphs[0].advance;
     memcpy(P.color, color, sizeof(P.color));
-    launch_text(c->stream, dev_text, (uint32_t)length, f->glyphs_dev, P, c->sprite_scratch, dst);
+    launch_text(c->stream, dev_text, (uint32_t)length, f->glyphs_dev, P, right_to_left != 0, c->sprite_scratch, dst);
     T3D_CUDA(cudaGetLastError());
     c->launches += 3;
     if (stage)
@@ -2841,8 +2842,8 @@ int t3d_font_draw_text(t3d_font* f, const char* text, size_t length, uint32_t te
             *n_quads = (uint32_t)quads;
         else
         {
-            uint32_t total[4] = { 0, 0, 0, 0 }; // {advance, line breaks, glyphs, .} of the whole text
-            T3D_CUDA(cudaMemcpyAsync(total, reinterpret_cast<const char*>(c->sprite_scratch) + text_scratch_bytes((uint32_t)length) - 16, 16,
+            uint32_t total[4] = { 0, 0, 0, 0 }; // {advance, line breaks, glyphs, .}: the first words of the whole text's element
+            T3D_CUDA(cudaMemcpyAsync(total, reinterpret_cast<const char*>(c->sprite_scratch) + text_scratch_bytes((uint32_t)length) - 48, 16,
                                      cudaMemcpyDeviceToHost, c->stream));
             {
                 HostTimer ht(c, T3D_HOST_WAIT);

@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kSpriteThreads)
 }
 
 // --------------------------------------------------------------------------------------------------
-// Font::drawText(text, x, y, color, size) (src/renderer/Font.cpp:242-390, left to right): the reference walks the string with a
+// Font::drawText(text, x, y, color, size, rightToLeft) (src/renderer/Font.cpp:242-390): the reference walks the string with a
 // running pen -- ' ' and '\t' advance it by the first glyph's advance (x 4), '\r' / '\n' start a new line, a character with a
 // glyph draws one quad (SpriteBatch::draw(x, y, w, h, u1, v1, u2, v2, color), SB.cpp:366-378 -> :475-506) and advances by
 // floor(advance * scale + spacing); everything else (also every byte >= 128: `char` is signed, Font.cpp:359) is skipped.
@@ -290,39 +290,95 @@ __global__ void __launch_bounds__(kSpriteThreads)
 //   k_text_summary   every thread folds 16 characters (one 128-bit load), 16 lanes fold a tile of 256
 //   k_text_scan      exclusive scan of the tile elements (one CTA)
 //   k_text_expand    a tile's characters: in-tile scan, one quad per glyph at its rank among the text's glyphs, bulk store
+// Right to left (Font.cpp:283-327) the reference skips the blanks at the start of a line going forwards, then walks the rest
+// of the line BACKWARDS from its last character: the pen before character i is the line's leading blanks plus the advances of
+// the characters behind i, and its quad comes after those of the glyphs behind it.  That needs the same scan from the right
+// as well (advance / glyphs until the next line break) and the blanks a line starts with; quads then leave one by one (a
+// tile's quads are no longer one contiguous run).
 // --------------------------------------------------------------------------------------------------
 struct TextElem
 {
-    int adv;          // pen advance since the last line break (or since the start, when there is none)
-    uint32_t breaks;  // line breaks
-    uint32_t glyphs;  // characters that draw
-    uint32_t pad;
+    // from the left
+    int adv;              // pen advance since the last line break (or since the start, when there is none)
+    uint32_t breaks;      // line breaks
+    uint32_t glyphs;      // characters that draw
+    uint32_t line_glyphs; // ... since the last line break
+    int lead;             // advance of the blanks the current line starts with
+    uint32_t open;        // the current line has been blanks only so far
+    // from the right
+    int radv;             // pen advance until the next line break
+    uint32_t rglyphs;     // glyphs until the next line break
+    uint32_t rbreak;      // there is a line break further right
+    uint32_t pad[3];
 };
+static_assert(sizeof(TextElem) == 48, "tile elements are 48 bytes");
+__device__ __forceinline__ TextElem text_identity()
+{
+    TextElem e = {};
+    e.open = 1u;
+    return e;
+}
+template <bool RTL>
 __device__ __forceinline__ TextElem text_combine(const TextElem& a, const TextElem& b) // a before b
 {
-    TextElem r;
+    TextElem r = {};
     r.adv = b.breaks ? b.adv : a.adv + b.adv;
     r.breaks = a.breaks + b.breaks;
     r.glyphs = a.glyphs + b.glyphs;
-    r.pad = 0;
+    if (RTL)
+    {
+        r.line_glyphs = b.breaks ? b.line_glyphs : a.line_glyphs + b.line_glyphs;
+        // the line b ends in started inside b, or is a's current line continued
+        r.lead = b.breaks ? b.lead : (a.open ? a.lead + b.lead : a.lead);
+        r.open = b.breaks ? b.open : (a.open && b.open);
+        r.radv = a.rbreak ? a.radv : a.radv + b.radv;
+        r.rglyphs = a.rbreak ? a.rglyphs : a.rglyphs + b.rglyphs;
+        r.rbreak = a.rbreak | b.rbreak;
+    }
     return r;
 }
-__device__ __forceinline__ TextElem text_shfl_up(const TextElem& v, int o, int width)
+template <bool RTL>
+__device__ __forceinline__ TextElem text_shfl(const TextElem& v, int delta, int width, bool up)
 {
-    TextElem t;
-    t.adv = __shfl_up_sync(0xffffffffu, v.adv, o, width);
-    t.breaks = __shfl_up_sync(0xffffffffu, v.breaks, o, width);
-    t.glyphs = __shfl_up_sync(0xffffffffu, v.glyphs, o, width);
-    t.pad = 0;
+    TextElem t = {};
+    auto S = [&](auto x) { return up ? __shfl_up_sync(0xffffffffu, x, delta, width) : __shfl_down_sync(0xffffffffu, x, delta, width); };
+    t.adv = S(v.adv);
+    t.breaks = S(v.breaks);
+    t.glyphs = S(v.glyphs);
+    if (RTL)
+    {
+        t.line_glyphs = S(v.line_glyphs);
+        t.lead = S(v.lead);
+        t.open = S(v.open);
+        t.radv = S(v.radv);
+        t.rglyphs = S(v.rglyphs);
+        t.rbreak = S(v.rbreak);
+    }
     return t;
+}
+// Tile elements in memory: left to right only the first four words are used (one 128-bit access).
+template <bool RTL>
+__device__ __forceinline__ TextElem text_load(const TextElem* p)
+{
+    if (RTL) return *p;
+    TextElem e = {};
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    e.adv = (int)v.x; e.breaks = v.y; e.glyphs = v.z; e.line_glyphs = v.w;
+    return e;
+}
+template <bool RTL>
+__device__ __forceinline__ void text_store(TextElem* p, const TextElem& e)
+{
+    if (RTL) *p = e;
+    else *reinterpret_cast<uint4*>(p) = make_uint4((uint32_t)e.adv, e.breaks, e.glyphs, e.line_glyphs);
 }
 constexpr int kTextTile = 256;       // characters per tile
 constexpr int kTextClasses = 128;    // a signed char that can have a glyph: 32 .. 127
 // per-character-code tables, built once per CTA: what the code adds to the pen, and whether it draws
 struct TextTables
 {
-    int adv[kTextClasses];           // ' ', '\t', glyph advances (Font.cpp:344, :351, :378); 0 for everything else
-    unsigned char kind[kTextClasses]; // 0 nothing, 1 line break, 2 glyph
+    int adv[kTextClasses];            // ' ', '\t', glyph advances (Font.cpp:344, :351, :378); 0 for everything else
+    unsigned char kind[kTextClasses]; // 0 nothing, 1 line break, 2 glyph, 3 blank (' ' or '\t')
 };
 __device__ __forceinline__ void text_build_tables(TextTables& t, const t3d_glyph* __restrict__ glyphs, const TextParams& P, uint32_t tid, uint32_t threads)
 {
@@ -330,10 +386,10 @@ __device__ __forceinline__ void text_build_tables(TextTables& t, const t3d_glyph
     {
         int adv = 0;
         unsigned char kind = 0;
-        if (c == ' ') adv = (int)P.space_advance;                 // Font.cpp:343-345
-        else if (c == '\t') adv = (int)(P.space_advance * 4u);    // :350-352
-        else if (c == '\r' || c == '\n') kind = 1;                // :346-349
-        else if (c >= 32u && c - 32u < P.glyph_count)             // :354-355 (index = c - 32)
+        if (c == ' ') { adv = (int)P.space_advance; kind = 3; }                  // Font.cpp:343-345
+        else if (c == '\t') { adv = (int)(P.space_advance * 4u); kind = 3; }     // :350-352
+        else if (c == '\r' || c == '\n') kind = 1;                               // :346-349
+        else if (c >= 32u && c - 32u < P.glyph_count)                            // :354-355 (index = c - 32)
         {
             kind = 2;
             adv = (int)floorf(__uint2float_rn(glyphs[c - 32u].advance) * P.scale + (float)P.spacing); // :378
@@ -344,17 +400,20 @@ __device__ __forceinline__ void text_build_tables(TextTables& t, const t3d_glyph
 }
 __device__ __forceinline__ TextElem text_elem(const TextTables& t, unsigned char byte)
 {
-    TextElem e = { 0, 0u, 0u, 0u };
+    TextElem e = {};
     if (byte < (unsigned char)kTextClasses)
     {
         const unsigned char k = t.kind[byte];
-        e.adv = t.adv[byte];
-        e.breaks = k == 1;
-        e.glyphs = k == 2;
+        e.adv = e.radv = t.adv[byte];
+        e.breaks = e.rbreak = k == 1;
+        e.glyphs = e.line_glyphs = e.rglyphs = k == 2;
+        e.open = k == 1 || k == 3; // a line break opens a new (so far blank) line; a blank keeps one open
+        e.lead = k == 3 ? e.adv : 0;
     }
     return e;
 }
 
+template <bool RTL>
 __global__ void __launch_bounds__(256) k_text_summary(const unsigned char* __restrict__ text, uint32_t n, const t3d_glyph* __restrict__ glyphs,
                                                       TextParams P, TextElem* __restrict__ tile_elems)
 {
@@ -375,88 +434,163 @@ __global__ void __launch_bounds__(256) k_text_summary(const unsigned char* __res
     }
     TextElem e = text_elem(s_t, b[0]);
 #pragma unroll
-    for (int k = 1; k < 16; ++k) e = text_combine(e, text_elem(s_t, b[k]));
+    for (int k = 1; k < 16; ++k) e = text_combine<RTL>(e, text_elem(s_t, b[k]));
     // fold the 16 lanes of a tile (an inclusive scan; its last lane holds the tile's element)
 #pragma unroll
     for (int o = 1; o < 16; o <<= 1)
     {
-        const TextElem t = text_shfl_up(e, o, 16);
-        if ((int)(threadIdx.x & 15u) >= o) e = text_combine(t, e);
+        const TextElem t = text_shfl<RTL>(e, o, 16, true);
+        if ((int)(threadIdx.x & 15u) >= o) e = text_combine<RTL>(t, e);
     }
     const uint32_t tile = first / (uint32_t)kTextTile;
-    if ((threadIdx.x & 15u) == 15u && (unsigned long long)tile * kTextTile < n) tile_elems[tile] = e;
+    if ((threadIdx.x & 15u) == 15u && (unsigned long long)tile * kTextTile < n) text_store<RTL>(tile_elems + tile, e);
 }
 
-// elems[0 .. n_tiles) -> exclusive prefix in place; elems[n_tiles] = the whole text.  One CTA.
+// elems[0 .. n_tiles) -> in place: the fields "from the left" become the exclusive prefix (everything before the tile), the
+// fields "from the right" the exclusive suffix (everything behind it); elems[n_tiles] = the whole text.  One CTA.
+template <bool RTL>
 __global__ void __launch_bounds__(1024) k_text_scan(TextElem* __restrict__ elems, uint32_t n_tiles)
 {
     __shared__ TextElem s_warp[32];
     __shared__ TextElem s_carry;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = TextElem{ 0, 0u, 0u, 0u };
+    if (RTL)
+    {
+        // from the right first: the suffix fields are parked in the pad words until the forward pass has read the elements
+        if (threadIdx.x == 0) s_carry = text_identity();
+        __syncthreads();
+        const uint32_t chunks = (n_tiles + 1023u) / 1024u;
+        for (uint32_t ch = chunks; ch-- > 0;)
+        {
+            const uint32_t i = ch * 1024u + threadIdx.x;
+            const TextElem own = i < n_tiles ? elems[i] : text_identity();
+            TextElem incl = own; // fold of [i, end of the warp]
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const TextElem t = text_shfl<true>(incl, o, 32, false);
+                if ((int)lane + o < 32) incl = text_combine<true>(incl, t);
+            }
+            if (lane == 0) s_warp[warp] = incl;
+            __syncthreads();
+            TextElem behind = text_identity(); // warps behind this one in the chunk, then the chunks behind
+            for (uint32_t w = warp + 1; w < 32; ++w) behind = text_combine<true>(behind, s_warp[w]);
+            behind = text_combine<true>(behind, s_carry);
+            const TextElem next = text_shfl<true>(incl, 1, 32, false);
+            const TextElem excl = lane < 31 ? text_combine<true>(next, behind) : behind;
+            if (i < n_tiles)
+            {
+                elems[i].pad[0] = (uint32_t)excl.radv;
+                elems[i].pad[1] = excl.rglyphs;
+                elems[i].pad[2] = excl.rbreak;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_carry = text_combine<true>(own, excl);
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) s_carry = text_identity();
     __syncthreads();
     for (uint32_t base = 0; base < n_tiles; base += 1024)
     {
         const uint32_t i = base + threadIdx.x;
-        const TextElem own = i < n_tiles ? elems[i] : TextElem{ 0, 0u, 0u, 0u };
+        const TextElem own = i < n_tiles ? text_load<RTL>(elems + i) : text_identity();
         TextElem incl = own;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1)
         {
-            const TextElem t = text_shfl_up(incl, o, 32);
-            if ((int)lane >= o) incl = text_combine(t, incl);
+            const TextElem t = text_shfl<RTL>(incl, o, 32, true);
+            if ((int)lane >= o) incl = text_combine<RTL>(t, incl);
         }
         if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
         TextElem before = s_carry;
-        for (uint32_t w = 0; w < warp; ++w) before = text_combine(before, s_warp[w]);
+        for (uint32_t w = 0; w < warp; ++w) before = text_combine<RTL>(before, s_warp[w]);
         // exclusive = everything before this warp, then the lanes before this one
-        const TextElem prev = text_shfl_up(incl, 1, 32);
-        const TextElem excl = lane ? text_combine(before, prev) : before;
-        if (i < n_tiles) elems[i] = excl;
+        const TextElem prev = text_shfl<RTL>(incl, 1, 32, true);
+        TextElem excl = lane ? text_combine<RTL>(before, prev) : before;
+        const TextElem through = text_combine<RTL>(excl, own);
+        if (RTL)
+        {
+            excl.radv = (int)own.pad[0];
+            excl.rglyphs = own.pad[1];
+            excl.rbreak = own.pad[2];
+        }
+        if (i < n_tiles) text_store<RTL>(elems + i, excl);
         __syncthreads();
-        if (threadIdx.x == 1023) s_carry = text_combine(excl, own);
+        if (threadIdx.x == 1023) s_carry = through;
         __syncthreads();
     }
-    if (threadIdx.x == 0) elems[n_tiles] = s_carry;
+    if (threadIdx.x == 0) text_store<RTL>(elems + n_tiles, s_carry);
 }
 
+template <bool RTL>
 __global__ void __launch_bounds__(kTextTile) k_text_expand(const unsigned char* __restrict__ text, uint32_t n, const t3d_glyph* __restrict__ glyphs,
                                                            TextParams P, const TextElem* __restrict__ tile_prefix, float* __restrict__ dst)
 {
-    __shared__ __align__(128) float4 s_buf[kTextTile * 9];
+    __shared__ __align__(128) float4 s_buf[RTL ? 9 : kTextTile * 9];
     __shared__ TextTables s_t;
     __shared__ TextElem s_warp[kTextTile / 32];
+    __shared__ TextElem s_rwarp[kTextTile / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     text_build_tables(s_t, glyphs, P, tid, kTextTile);
     const uint32_t i = blockIdx.x * (uint32_t)kTextTile + tid;
     const unsigned char byte = i < n ? text[i] : (unsigned char)0xff;
-    const TextElem before_tile = tile_prefix[blockIdx.x];
+    const TextElem around = text_load<RTL>(tile_prefix + blockIdx.x); // what lies before the tile (and, right to left, behind it)
     __syncthreads();
     const TextElem own = text_elem(s_t, byte);
     TextElem incl = own;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
     {
-        const TextElem t = text_shfl_up(incl, o, 32);
-        if ((int)lane >= o) incl = text_combine(t, incl);
+        const TextElem t = text_shfl<RTL>(incl, o, 32, true);
+        if ((int)lane >= o) incl = text_combine<RTL>(t, incl);
     }
     if (lane == 31) s_warp[warp] = incl;
+    TextElem rincl = own; // fold of [this character, end of the warp]
+    if (RTL)
+    {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const TextElem t = text_shfl<true>(rincl, o, 32, false);
+            if ((int)lane + o < 32) rincl = text_combine<true>(rincl, t);
+        }
+        if (lane == 0) s_rwarp[warp] = rincl;
+    }
     __syncthreads();
-    TextElem before = before_tile;
-    TextElem tile_all = before_tile;
+    TextElem before = around;
+    before.radv = 0; before.rglyphs = 0; before.rbreak = 0; // (those describe what lies BEHIND the tile)
+    TextElem tile_all = before;
 #pragma unroll
     for (int w = 0; w < kTextTile / 32; ++w)
     {
-        if ((uint32_t)w < warp) before = text_combine(before, s_warp[w]);
-        tile_all = text_combine(tile_all, s_warp[w]);
+        if ((uint32_t)w < warp) before = text_combine<RTL>(before, s_warp[w]);
+        tile_all = text_combine<RTL>(tile_all, s_warp[w]);
     }
-    const TextElem prev = text_shfl_up(incl, 1, 32);
-    const TextElem excl = lane ? text_combine(before, prev) : before; // the pen before this character
+    const TextElem prev = text_shfl<RTL>(incl, 1, 32, true);
+    const TextElem excl = lane ? text_combine<RTL>(before, prev) : before; // the walk before this character
+    int pen_x = P.x + excl.adv;                                            // Font.cpp:272, :344-378
+    uint32_t quad = excl.glyphs;
+    if (RTL)
+    {
+        TextElem behind = text_identity(); // the warps behind this one in the tile, then what lies behind the tile
+#pragma unroll
+        for (int w = 0; w < kTextTile / 32; ++w)
+            if ((uint32_t)w > warp) behind = text_combine<true>(behind, s_rwarp[w]);
+        TextElem after_tile = text_identity();
+        after_tile.radv = around.radv; after_tile.rglyphs = around.rglyphs; after_tile.rbreak = around.rbreak;
+        behind = text_combine<true>(behind, after_tile);
+        const TextElem next = text_shfl<true>(rincl, 1, 32, false);
+        const TextElem rexcl = lane < 31 ? text_combine<true>(next, behind) : behind;
+        // :283-327: the blanks the line starts with, then the characters behind this one (the line is walked backwards)
+        pen_x = P.x + excl.lead + rexcl.radv;
+        quad = (excl.glyphs - excl.line_glyphs) + rexcl.rglyphs;
+    }
+    float4 q[9];
     if (own.glyphs)
     {
         const t3d_glyph g = glyphs[byte - 32u];
-        const int pen_x = P.x + excl.adv;                                   // Font.cpp:272, :344-378
         const int pen_y = (int)((uint32_t)P.y + excl.breaks * P.size);      // :348 (yPos += size, an unsigned added to an int)
         const float x = (float)(pen_x + __float2int_rz((float)g.bearing_x * P.scale)); // :369
         const float y = (float)pen_y;
@@ -464,14 +598,23 @@ __global__ void __launch_bounds__(kTextTile) k_text_expand(const unsigned char* 
         const float h = __uint2float_rn(P.size);                            // :372
         const float x2 = x + w, y2 = y + h;                                 // SB.cpp:493-494
         const float px[4] = { x, x, x2, x2 }, py[4] = { y, y2, y, y2 };     // SB.cpp:496-501
-        write_quad(s_buf + (excl.glyphs - before_tile.glyphs) * 9, px, py, 0.0f, g.uvs[0], g.uvs[1], g.uvs[2], g.uvs[3], P.color);
+        if (RTL)
+        {
+            write_quad(q, px, py, 0.0f, g.uvs[0], g.uvs[1], g.uvs[2], g.uvs[3], P.color);
+            float4* out = reinterpret_cast<float4*>(dst + (size_t)quad * kQuadFloats);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) out[k] = q[k];
+        }
+        else
+            write_quad(s_buf + (quad - around.glyphs) * 9, px, py, 0.0f, g.uvs[0], g.uvs[1], g.uvs[2], g.uvs[3], P.color);
     }
+    if (RTL) return;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    const uint32_t tile_glyphs = tile_all.glyphs - before_tile.glyphs;
+    const uint32_t tile_glyphs = tile_all.glyphs - around.glyphs;
     if (tid == 0 && tile_glyphs)
     {
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + (size_t)before_tile.glyphs * kQuadFloats),
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + (size_t)around.glyphs * kQuadFloats),
                      "r"((uint32_t)__cvta_generic_to_shared(s_buf)), "r"(tile_glyphs * (uint32_t)(kQuadFloats * 4)) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -484,16 +627,26 @@ __global__ void __launch_bounds__(kTextTile) k_text_expand(const unsigned char* 
 uint32_t text_tiles(uint32_t n) { return (n + kTextTile - 1) / kTextTile; }
 size_t text_scratch_bytes(uint32_t n) { return ((size_t)text_tiles(n) + 1) * sizeof(TextElem); }
 
-void launch_text(void* stream, const char* text, uint32_t n, const t3d_glyph* glyphs, const TextParams& P, void* scratch, float* dst)
+void launch_text(void* stream, const char* text, uint32_t n, const t3d_glyph* glyphs, const TextParams& P, bool right_to_left, void* scratch,
+                 float* dst)
 {
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t tiles = text_tiles(n);
     if (!tiles) return;
     TextElem* elems = static_cast<TextElem*>(scratch);
     const unsigned char* t = reinterpret_cast<const unsigned char*>(text);
-    k_text_summary<<<(tiles + 15) / 16, 256, 0, st>>>(t, n, glyphs, P, elems);
-    k_text_scan<<<1, 1024, 0, st>>>(elems, tiles);
-    k_text_expand<<<tiles, kTextTile, 0, st>>>(t, n, glyphs, P, elems, dst);
+    if (right_to_left)
+    {
+        k_text_summary<true><<<(tiles + 15) / 16, 256, 0, st>>>(t, n, glyphs, P, elems);
+        k_text_scan<true><<<1, 1024, 0, st>>>(elems, tiles);
+        k_text_expand<true><<<tiles, kTextTile, 0, st>>>(t, n, glyphs, P, elems, dst);
+    }
+    else
+    {
+        k_text_summary<false><<<(tiles + 15) / 16, 256, 0, st>>>(t, n, glyphs, P, elems);
+        k_text_scan<false><<<1, 1024, 0, st>>>(elems, tiles);
+        k_text_expand<false><<<tiles, kTextTile, 0, st>>>(t, n, glyphs, P, elems, dst);
+    }
 }
 
 uint32_t sprite_tiles(uint32_t n) { return (n + kSpriteThreads - 1) / kSpriteThreads; }
