@@ -2,6 +2,7 @@
 // (t3d_runtime.cu).  Nothing here is part of the ABI.
 #pragma once
 
+#include <cstddef>
 #include <cstdint>
 
 #include "../../include/t3d_particles.h"
@@ -16,6 +17,11 @@ int draw_sub(uint32_t n_items);
 int draw_tile_size(uint32_t n_items); // quads per draw CTA for a launch over n_items emitters
 const char* update_variant_name();
 constexpr int kSpawnThreads = 256; // spawn and draw: one particle per thread
+// A spawn CTA generates this many consecutive groups of kSpawnThreads particles.  Measured with 4: the descriptor fetch is paid a
+// quarter as often, but 1 Mi particles are then 1 024 CTAs = 1.7 waves of the 592 the device holds, and the idle part of the
+// last wave costs more than the fetches saved (50.1 against 47.6 us per 1 Mi particles); 1 = 6.9 waves.
+constexpr int kSpawnSub = 1;
+constexpr int kSpawnTile = kSpawnThreads * kSpawnSub;
 constexpr int kDrawThreads = 256;
 constexpr int kMaxSmemFrames = 256; // sprite uv tables up to this many frames are staged in shared memory (k_draw)
 constexpr int kMaxFusedFrames = 64; // the fused update + draw pass has 1 KB for the table; larger sheets take the two launches
@@ -140,7 +146,8 @@ struct alignas(16) UpdateItem
 };
 static_assert(sizeof(UpdateItem) == 80, "UpdateItem is fetched as five 128-bit words");
 
-struct SpawnItem
+// 112 bytes, 16-byte aligned; a CTA requests the first 48 (everything but the matrix) of the entry it expects to own at once.
+struct alignas(16) SpawnItem
 {
     EmitterDev* dev;
     const int32_t* draws;     // recorded draws for this emit (nullptr: device generator)
@@ -149,10 +156,14 @@ struct SpawnItem
     uint32_t request;         // particles asked for (clamped to free capacity on the device)
     uint32_t parity;
     uint32_t tile_begin;
+    uint32_t n_tiles;         // tiles of this launch that belong to the emitter
+    uint32_t pad;
     float world[16];          // node world matrix (PE.cpp:299)
 };
+static_assert(sizeof(SpawnItem) == 112 && offsetof(SpawnItem, world) == 48, "the head of a SpawnItem is three 128-bit words");
 
-struct DrawItem
+// (the first 80 bytes -- everything but the matrix -- are requested at once by the CTA that expects to own the entry)
+struct alignas(16) DrawItem
 {
     EmitterDev* dev;
     const uint32_t* rw;   // copied from the emitter's record: one dependent fetch, then the loads can start
@@ -168,6 +179,7 @@ struct DrawItem
     float up[3];
     float vp[16];         // view-projection matrix (PE.cpp:846-849); only read by the clip-space draw (T3D_VERTEX_CLIP)
 };
+static_assert(sizeof(DrawItem) == 144 && offsetof(DrawItem, vp) == 80, "the head of a DrawItem is five 128-bit words");
 
 // Process-wide billboard rotation of the reference (SB.cpp:339), kept on the device.
 struct FrozenRotation

@@ -49,13 +49,40 @@ struct DrawSource
 template <bool STREAM>
 __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __restrict__ items, uint32_t n_items)
 {
-    // The tile's life records and rotation records are assembled in shared memory and leave as two contiguous bulk
-    // stores (the appended range [count0, count0 + n) is contiguous in both arrays); the rw words go out column by
-    // column, one coalesced 128-byte line per warp per column.
-    __shared__ __align__(128) uint32_t s_rec[kSpawnThreads * REC_WORDS];
-    __shared__ __align__(128) uint32_t s_rot[kSpawnThreads * ROT_WORDS];
+    // A CTA generates kSpawnSub consecutive groups of kSpawnThreads particles, so the descriptor fetch and the count are paid
+    // once per kSpawnTile particles.  A group's life records and rotation records are assembled in shared memory and leave as
+    // two contiguous bulk stores (the appended range [count0, count0 + n) is contiguous in both arrays) while the next group
+    // is generated into the other half; the rw words go out column by column, one coalesced 128-byte line per warp per column.
+    constexpr int kBufs = kSpawnSub > 1 ? 2 : 1;
+    __shared__ __align__(128) uint32_t s_rec[kBufs][kSpawnThreads * REC_WORDS];
+    __shared__ __align__(128) uint32_t s_rot[kBufs][kSpawnThreads * ROT_WORDS];
     const uint32_t tile = blockIdx.x;
-    const SpawnItem& it = items[find_item(items, n_items, tile, gridDim.x)];
+    // the head of the entry this tile is expected to belong to, requested at once and checked (see k_update)
+    struct Head
+    {
+        EmitterDev* dev;
+        const int32_t* draws;
+        const uint32_t* offsets;
+        uint32_t draw_stride, request, parity, tile_begin, n_tiles, pad;
+    };
+    static_assert(sizeof(Head) == 48, "three 128-bit words");
+    auto load_head = [&](uint32_t i)
+    {
+        Head h;
+        const uint4* src = reinterpret_cast<const uint4*>(items + i);
+        uint4* dst = reinterpret_cast<uint4*>(&h);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) dst[q] = __ldg(src + q);
+        return h;
+    };
+    uint32_t item_index = guess_item(n_items, tile, gridDim.x);
+    Head it = load_head(item_index);
+    if (tile - it.tile_begin >= it.n_tiles)
+    {
+        item_index = find_item(items, n_items, tile, gridDim.x);
+        it = load_head(item_index);
+    }
+    const float* const world = items[item_index].world;
     EmitterDev* d = it.dev;
     const uint32_t parity = it.parity;
     const uint32_t count0 = d->cnt[parity].count;
@@ -64,69 +91,82 @@ __global__ void __launch_bounds__(kSpawnThreads) k_spawn(const SpawnItem* __rest
     // PE.cpp:293-296: never go over particleCountMax.
     const uint32_t room = cap > count0 ? cap - count0 : 0u; // (the cap may have been lowered below the live count: nothing spawns)
     const uint32_t n = it.request < room ? it.request : room;
-    const uint32_t tile_first = (tile - it.tile_begin) * kSpawnThreads;
-    const uint32_t i = tile_first + threadIdx.x;
-    if (i == 0)
+    const uint32_t tile_first = (tile - it.tile_begin) * kSpawnTile;
+    if (tile_first == 0 && threadIdx.x == 0)
     {
         d->cnt[parity ^ 1].count = count0 + n;
         d->cnt[parity ^ 1].serial = serial0 + n;
     }
     if (tile_first >= n) return;
     const Storage st = d->c.st;
-
-    if (i < n)
-    {
     const SpawnParams& P = d->c.sp;
-    DrawSource<STREAM> src;
-    src.p = (STREAM && it.draws) ? it.draws + (it.offsets ? it.offsets[i] : i * it.draw_stride) : nullptr;
-    src.key = device_rng_key(P.rng_seed, serial0 + i);
-    src.j = 0;
-    const SpawnedParticle sp = spawn_particle(P, it.world, src); // PE.cpp:312-364
-    const float* cs = sp.cs; const float* ce = sp.ce; const float* pos = sp.pos; const float* vel = sp.vel; const float* acc = sp.acc;
-    const float* axis = sp.axis;
-    const int energy = sp.energy;
-    const float size_start = sp.size_start, size_end = sp.size_end, spin = sp.spin, angle = sp.angle, rot_speed = sp.rot_speed;
-    const uint32_t frame = sp.frame;
 
-    // what update() rewrites every frame: 15 rw columns
-    uint32_t* const rw = st.rw + (count0 + i);
-    const size_t stride = st.stride;
-    auto F = [&](int c, float v) { rw[(size_t)c * stride] = __float_as_uint(v); };
-    rw[(size_t)RW_ENERGY * stride] = (uint32_t)energy;
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
+#pragma unroll 1
+    for (int sub = 0; sub < kSpawnSub; ++sub)
     {
-        F(RW_POS + k, pos[k]);
-        F(RW_VEL + k, vel[k]);
-    }
-    F(RW_ANGLE, angle);
+        const uint32_t sub_first = tile_first + (uint32_t)sub * kSpawnThreads;
+        if (sub_first >= n) break;
+        const uint32_t i = sub_first + threadIdx.x;
+        const int buf = sub & (kBufs - 1);
+        if (sub >= 2)
+        {
+            // this half of shared memory was handed to the bulk stores two groups ago: they must have read it
+            if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncthreads();
+        }
+        if (i < n)
+        {
+            DrawSource<STREAM> src;
+            src.p = (STREAM && it.draws) ? it.draws + (it.offsets ? it.offsets[i] : i * it.draw_stride) : nullptr;
+            src.key = device_rng_key(P.rng_seed, serial0 + i);
+            src.j = 0;
+            const SpawnedParticle sp = spawn_particle(P, world, src); // PE.cpp:312-364
+            const float* cs = sp.cs; const float* ce = sp.ce; const float* pos = sp.pos; const float* vel = sp.vel; const float* acc = sp.acc;
+            const float* axis = sp.axis;
+            const int energy = sp.energy;
+            const float size_start = sp.size_start, size_end = sp.size_end, spin = sp.spin, angle = sp.angle, rot_speed = sp.rot_speed;
+            const uint32_t frame = sp.frame;
+
+            // what update() rewrites every frame: 15 rw columns
+            uint32_t* const rw = st.rw + (count0 + i);
+            const size_t stride = st.stride;
+            auto F = [&](int c, float v) { rw[(size_t)c * stride] = __float_as_uint(v); };
+            rw[(size_t)RW_ENERGY * stride] = (uint32_t)energy;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) F(RW_COLOR + k, cs[k]); // :314
-    F(RW_SIZE, size_start);
-    F(RW_TIME_ON_FRAME, 0.0f); // :365
-    rw[(size_t)RW_FRAME * stride] = frame;
-    // what the particle keeps for life: the 64-byte record and the rotation record, through shared memory
-    uint4* const r4 = reinterpret_cast<uint4*>(s_rec + threadIdx.x * REC_WORDS);
-    auto U = [](float v) { return __float_as_uint(v); };
-    r4[0] = make_uint4(U(cs[0]), U(cs[1]), U(cs[2]), U(cs[3]));
-    r4[1] = make_uint4(U(ce[0]), U(ce[1]), U(ce[2]), U(ce[3]));
-    r4[2] = make_uint4(U(acc[0]), U(acc[1]), U(acc[2]), U(spin));
-    r4[3] = make_uint4((uint32_t)energy, U(size_start), U(size_end), 0u);
-    *reinterpret_cast<uint4*>(s_rot + threadIdx.x * ROT_WORDS) = make_uint4(U(axis[0]), U(axis[1]), U(axis[2]), U(rot_speed));
+            for (int k = 0; k < 3; ++k)
+            {
+                F(RW_POS + k, pos[k]);
+                F(RW_VEL + k, vel[k]);
+            }
+            F(RW_ANGLE, angle);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) F(RW_COLOR + k, cs[k]); // :314
+            F(RW_SIZE, size_start);
+            F(RW_TIME_ON_FRAME, 0.0f); // :365
+            rw[(size_t)RW_FRAME * stride] = frame;
+            // what the particle keeps for life: the 64-byte record and the rotation record, through shared memory
+            uint4* const r4 = reinterpret_cast<uint4*>(s_rec[buf] + threadIdx.x * REC_WORDS);
+            auto U = [](float v) { return __float_as_uint(v); };
+            r4[0] = make_uint4(U(cs[0]), U(cs[1]), U(cs[2]), U(cs[3]));
+            r4[1] = make_uint4(U(ce[0]), U(ce[1]), U(ce[2]), U(ce[3]));
+            r4[2] = make_uint4(U(acc[0]), U(acc[1]), U(acc[2]), U(spin));
+            r4[3] = make_uint4((uint32_t)energy, U(size_start), U(size_end), 0u);
+            *reinterpret_cast<uint4*>(s_rot[buf] + threadIdx.x * ROT_WORDS) = make_uint4(U(axis[0]), U(axis[1]), U(axis[2]), U(rot_speed));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            const uint32_t nt = (n - sub_first) < (uint32_t)kSpawnThreads ? (n - sub_first) : (uint32_t)kSpawnThreads;
+            const size_t p0 = (size_t)count0 + sub_first;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(st.rec + p0 * REC_WORDS),
+                         "r"((uint32_t)__cvta_generic_to_shared(s_rec[buf])), "r"(nt * (uint32_t)(REC_WORDS * 4)) : "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(st.rot + p0 * ROT_WORDS),
+                         "r"((uint32_t)__cvta_generic_to_shared(s_rot[buf])), "r"(nt * (uint32_t)(ROT_WORDS * 4)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        const uint32_t nt = (n - tile_first) < (uint32_t)kSpawnThreads ? (n - tile_first) : (uint32_t)kSpawnThreads;
-        const size_t p0 = (size_t)count0 + tile_first;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(st.rec + p0 * REC_WORDS),
-                     "r"((uint32_t)__cvta_generic_to_shared(s_rec)), "r"(nt * (uint32_t)(REC_WORDS * 4)) : "memory");
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(st.rot + p0 * ROT_WORDS),
-                     "r"((uint32_t)__cvta_generic_to_shared(s_rot)), "r"(nt * (uint32_t)(ROT_WORDS * 4)) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory must outlive the stores' reads
-    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory must outlive the stores' reads
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -151,7 +191,34 @@ __global__ void __launch_bounds__(kDrawThreads)
     // current one is expanded.
     const uint32_t tile = blockIdx.x;
     const uint32_t tid = threadIdx.x;
-    const DrawItem& it = items[find_item(items, n_items, tile, gridDim.x)];
+    // the head of the entry this tile is expected to belong to (everything but the matrix), requested at once and checked
+    // (see k_update): one dependent fetch instead of three before the particle loads can start
+    struct Head
+    {
+        EmitterDev* dev;
+        const uint32_t* rw;
+        float* vtx;
+        const float* uv;
+        uint32_t parity, tile_begin, stride, seg_capacity, frame_count, n_tiles;
+        float right[3], up[3];
+    };
+    static_assert(sizeof(Head) == 80, "five 128-bit words");
+    auto load_head = [&](uint32_t i)
+    {
+        Head h;
+        const uint4* src = reinterpret_cast<const uint4*>(items + i);
+        uint4* dsth = reinterpret_cast<uint4*>(&h);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) dsth[q] = __ldg(src + q);
+        return h;
+    };
+    uint32_t item_index = guess_item(n_items, tile, gridDim.x);
+    Head it = load_head(item_index);
+    if (tile - it.tile_begin >= it.n_tiles)
+    {
+        item_index = find_item(items, n_items, tile, gridDim.x);
+        it = load_head(item_index);
+    }
     const EmitterDev* d = it.dev;
     const uint32_t first_tile = (tile - it.tile_begin) * (kDrawThreads * DSUB);
     const uint32_t N = d->cnt[it.parity].count;
@@ -186,7 +253,7 @@ __global__ void __launch_bounds__(kDrawThreads)
     const bool uv_in_smem = frame_count <= (uint32_t)kMaxSmemFrames;
     if (uv_in_smem)
         for (uint32_t q = tid; q < frame_count * 4u; q += kDrawThreads) s_uv[q] = uv_g[q];
-    if (CLIP && tid < 16) s_vp[tid] = it.vp[tid];
+    if (CLIP && tid < 16) s_vp[tid] = items[item_index].vp[tid];
     if (first_tile == 0 && tid == 0)
     {
         const_cast<EmitterDev*>(d)->cnt[0].drawn = N;

@@ -722,7 +722,8 @@ static int launch_spawns(t3d_ctx* c)
         e->launch_version++;
         it.tile_begin = tiles;
         memcpy(it.world, e->node_world, sizeof(it.world)); // PE.cpp:299
-        tiles += (op.emit_n + kSpawnThreads - 1) / kSpawnThreads;
+        it.n_tiles = (op.emit_n + kSpawnTile - 1) / kSpawnTile;
+        tiles += it.n_tiles;
     }
     T3D_TRY(staging_submit(c, slot, total));
     T3D_TRY(time_begin(c, KERNEL_SPAWN));
