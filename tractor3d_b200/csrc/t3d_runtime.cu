@@ -2765,7 +2765,7 @@ int t3d_font_draw_text(t3d_font* f, const char* text, size_t length, uint32_t te
                        int right_to_left, void* device_dst, size_t dst_quads, const t3d_sprite_vertex** device_ptr, uint32_t* n_quads)
 {
     if (!f || (!text && length) || !color) return fail(T3D_ERR_INVALID, "t3d_font_draw_text: null argument");
-    if (length > 0xfffffff0u) return fail(T3D_ERR_INVALID, "t3d_font_draw_text: text too long");
+    if (length > 0x7fffffffu) return fail(T3D_ERR_INVALID, "t3d_font_draw_text: text too long (2 GiB per call)");
     t3d_ctx* c = f->ctx;
     T3D_TRY(use_device(c));
     if (size == 0) size = f->size; // Font.cpp:253-256
