@@ -166,7 +166,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     unsigned char* const stage_warp = dyn + (size_t)WARPS * kRecWarp + (size_t)warp * kStageWarp;
     // the words of a mover that the slot's thread only passes on (rotation record, energy, colour, size) land here,
     // requested one group ahead like everything else: [0,16) rotation record, [16,40) energy, colour x 4, size
-    unsigned char* const side_lane = dyn + (size_t)WARPS * (kRecWarp + (FUSED ? kStageWarp : 0)) + (size_t)warp * kSideWarp + lane * kSideLane;
+    // 32 slots per warp, handed out per group by rank among the warp's movers (a thread's second mover takes a slot that another
+    // lane does not need: a group holds ~5 movers per warp at 7 % of the particles replaced per frame)
+    unsigned char* const side_warp = dyn + (size_t)WARPS * (kRecWarp + (FUSED ? kStageWarp : 0)) + (size_t)warp * kSideWarp;
+    const uint32_t lanes_below = (1u << lane) - 1u;
 
     // ---- phase A: the energy column of the whole tile -> dead flags (PE.cpp:753-755: `long -= float`, `> 0`) ----
     // Issued before the live count has arrived: every slot below the padded segment size is safe to read.
@@ -492,14 +495,17 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         //    ahead (below); the words of the mover that this thread only passes on came through the side stage.  Group 0
         //    was requested before the prefix was known: its movers are fetched directly, further down. --
         const bool staged = s > 0;
-        bool fastm[V]; // the thread's first mover of the group: the side stage holds one particle's extras per lane
+        bool fastm[V];        // movers whose extras came through the side stage: the first 32 of the warp's group
+        uint32_t side_slot[V]; // ... and where (the same ranks as when they were requested: slot l of every lane, then slot l + 1)
         {
-            bool taken = false;
+            uint32_t base = 0;
 #pragma unroll
             for (int l = 0; l < V; ++l)
             {
-                fastm[l] = staged && p.mover[l] && !taken;
-                taken = taken || p.mover[l];
+                const unsigned m = __ballot_sync(0xffffffffu, staged && p.mover[l]);
+                side_slot[l] = base + (uint32_t)__popc(m & lanes_below);
+                fastm[l] = staged && p.mover[l] && side_slot[l] < 32u;
+                base += (uint32_t)__popc(m);
             }
         }
         uint32_t rc[V][REC_WORDS];
@@ -518,9 +524,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) rdst[c] = make_uint4(rc[l][c * 4], rc[l][c * 4 + 1], rc[l][c * 4 + 2], rc[l][c * 4 + 3]);
                 if (!fastm[l]) continue;
-                const uint4 ro = *reinterpret_cast<const uint4*>(side_lane);
-                const uint4 w0s = *reinterpret_cast<const uint4*>(side_lane + 16);
-                const uint2 w1s = *reinterpret_cast<const uint2*>(side_lane + 32);
+                const unsigned char* const side = side_warp + side_slot[l] * kSideLane;
+                const uint4 ro = *reinterpret_cast<const uint4*>(side);
+                const uint4 w0s = *reinterpret_cast<const uint4*>(side + 16);
+                const uint2 w1s = *reinterpret_cast<const uint2*>(side + 32);
                 *reinterpret_cast<uint4*>(rot + (size_t)(k0 + l) * ROT_WORDS) = ro;
                 p.e[l] = (int)w0s.x;
                 col_out[0][l] = __uint_as_float(w0s.y);
@@ -557,25 +564,29 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 rec_issue_indexed<V>(rec_warp, rec, nrec, lane, idx);
             }
         }
-        if (mv_next)
+        if (warp_mv)
         {
-            bool taken = false;
+            uint32_t base = 0;
 #pragma unroll
             for (int l = 0; l < V; ++l)
             {
-                if (!pn.mover[l]) continue;
+                const bool mine = mv_next && pn.mover[l];
+                const unsigned m = __ballot_sync(0xffffffffu, mine);
+                const uint32_t slot = base + (uint32_t)__popc(m & lanes_below);
+                base += (uint32_t)__popc(m);
+                if (!mine) continue;
                 const uint32_t i = pn.src[l];
-                if (!taken)
+                if (slot < 32u)
                 {
-                    cp_async16(side_lane, rot + (size_t)i * ROT_WORDS);
-                    cp_async4(side_lane + 16, col(RW_ENERGY) + i);
+                    unsigned char* const side = side_warp + slot * kSideLane;
+                    cp_async16(side, rot + (size_t)i * ROT_WORDS);
+                    cp_async4(side + 16, col(RW_ENERGY) + i);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) cp_async4(side_lane + 20 + 4 * c, col(RW_COLOR + c) + i);
-                    cp_async4(side_lane + 36, col(RW_SIZE) + i);
+                    for (int c = 0; c < 4; ++c) cp_async4(side + 20 + 4 * c, col(RW_COLOR + c) + i);
+                    cp_async4(side + 36, col(RW_SIZE) + i);
                 }
                 else
-                    prefetch_mover(i); // a second mover in the same thread is fetched when its slot is written: ask L2 for it now
-                taken = true;
+                    prefetch_mover(i); // more than 32 movers in the warp's group: fetched when the slot is written, ask L2 for it now
             }
         }
         cp_async_commit();
@@ -665,7 +676,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         }
 
         // -- movers that did not come through the stages: those of group 0 (requested before the prefix was known) and a
-        //    thread's second mover of a group.  Their motion words came with the prefetch; the rest is fetched here, from
+        //    warp's movers beyond the 32nd of a group.  Their motion words came with the prefetch; the rest is fetched here, from
         //    L2 where the prefetch got there in time. --
         if (p.any_mover)
         {
