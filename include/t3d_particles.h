@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define T3D_ABI_VERSION 3
+#define T3D_ABI_VERSION 4 /* 4: + t3d_batch_frame_pipelined, t3d_font_* (additive) */
 
 typedef enum t3d_status {
     T3D_OK = 0,

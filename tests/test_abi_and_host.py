@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} is declared in include/t3d_particles.h but not exported"
     assert set(names) == set(abi.PROTOTYPES), set(names) ^ set(abi.PROTOTYPES)
-    assert lib.t3d_abi_version() == 3
+    assert lib.t3d_abi_version() == 4
 
 
 def test_params_struct_layout_matches_header_defaults():
