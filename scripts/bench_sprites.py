@@ -140,6 +140,23 @@ print(f"  text, {n_text} bytes -> {glyphs_drawn} glyph quads, text resident in H
       f"({bytes_alg / d_ms / 1e6 / PEAK:.2f} of the measured HBM peak)")
 d_ms, w_ms = timed(text_on_host, reps=10)
 print(f"    text in host memory (1 B per character uploaded, glyphs counted on the host): {w_ms:.3f} ms wall per text = {glyphs_drawn / w_ms / 1e6:.3f} G glyphs/s")
+# a longer text: the three launches weigh less
+big = 16 * n_text
+big_text = text * 16
+big_glyphs = 16 * glyphs_drawn
+dev_big = torch.frombuffer(bytearray(big_text), dtype=torch.uint8).cuda()
+dst_big = torch.empty(big * 36, dtype=torch.float32, device="cuda")
+torch.cuda.synchronize()
+
+
+def big_on_device():
+    lib.t3d_font_draw_text(fh, C.c_void_p(dev_big.data_ptr()), big, abi.TEXT_ON_DEVICE, 0, 0, cp, 30, 0, C.c_void_p(dst_big.data_ptr()), big, None, None)
+
+
+d_ms, w_ms = timed(big_on_device, reps=10)
+print(f"    {big} bytes -> {big_glyphs} glyph quads, resident: {d_ms:.3f} ms = {big_glyphs / d_ms / 1e6:.2f} G glyphs/s, "
+      f"{(big + 144 * big_glyphs) / d_ms / 1e6:.0f} GB/s algorithmic ({(big + 144 * big_glyphs) / d_ms / 1e6 / PEAK:.2f} of the measured HBM peak)")
+del dev_big, dst_big
 R = H.ref(fresh=True)
 m = min(n_text, 1 << 18)
 h = R.font_create(24, g.ctypes.data, 95, 512, 512)

@@ -247,11 +247,19 @@ struct TextParams
     uint32_t space_advance; // _glyphs[0].advance: what ' ' and '\t' move the pen by (:344, :351)
     float color[4];
 };
+// Per-character-code tables of one text (a signed char that can have a glyph: 32 .. 127): what the code adds to the pen and
+// what it does.  Built on the host (the glyph table and the per-call constants are there), handed to the kernels by value.
+constexpr int kTextClasses = 128;
+struct TextTables
+{
+    int adv[kTextClasses];            // ' ', '\t', glyph advances (Font.cpp:344, :351, :378); 0 for everything else
+    unsigned char kind[kTextClasses]; // 0 nothing, 1 line break, 2 glyph, 3 blank (' ' or '\t')
+};
 uint32_t text_tiles(uint32_t n);          // tiles of 256 characters
 size_t text_scratch_bytes(uint32_t n);    // device scratch a text of n bytes needs; its last 48 bytes end up holding {., line breaks, glyphs, ...}
 // text: n bytes on the device, 16-byte aligned; glyphs: the font's table on the device; quads go to dst in reading order
-void launch_text(void* stream, const char* text, uint32_t n, const t3d_glyph* glyphs, const TextParams& P, bool right_to_left, void* scratch,
-                 float* dst);
+void launch_text(void* stream, const char* text, uint32_t n, const t3d_glyph* glyphs, const TextTables& T, const TextParams& P, bool right_to_left,
+                 void* scratch, float* dst);
 uint32_t sprite_tiles(uint32_t n); // CTAs (tiles of 256 sprites) a list of n sprites takes
 // tile_scratch: sprite_tiles(n) + 1 words when some sprite may be culled by its clip rectangle (ordered compaction; the
 // last word receives the number of quads written), nullptr when sprite i simply becomes quad i.

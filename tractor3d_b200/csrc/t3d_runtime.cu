@@ -2829,7 +2829,19 @@ int t3d_font_draw_text(t3d_font* f, const char* text, size_t length, uint32_t te
     P.glyph_count = (uint32_t)f->glyphs.size();
     P.space_advance = f->glyphs[0].advance;
     memcpy(P.color, color, sizeof(P.color));
-    launch_text(c->stream, dev_text, (uint32_t)length, f->glyphs_dev, P, right_to_left != 0, c->sprite_scratch, dst);
+    TextTables T{};
+    for (uint32_t ch = 0; ch < (uint32_t)kTextClasses; ++ch)
+    {
+        if (ch == ' ') { T.adv[ch] = (int)P.space_advance; T.kind[ch] = 3; }                  // Font.cpp:343-345
+        else if (ch == '\t') { T.adv[ch] = (int)(P.space_advance * 4u); T.kind[ch] = 3; }     // :350-352
+        else if (ch == '\r' || ch == '\n') T.kind[ch] = 1;                                    // :346-349
+        else if (ch >= 32u && ch - 32u < P.glyph_count)                                       // :354-355 (index = c - 32)
+        {
+            T.kind[ch] = 2;
+            T.adv[ch] = (int)floorf((float)f->glyphs[ch - 32u].advance * P.scale + (float)P.spacing); // :378
+        }
+    }
+    launch_text(c->stream, dev_text, (uint32_t)length, f->glyphs_dev, T, P, right_to_left != 0, c->sprite_scratch, dst);
     T3D_CUDA(cudaGetLastError());
     c->launches += 3;
     if (stage)

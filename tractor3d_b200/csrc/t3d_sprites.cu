@@ -287,8 +287,8 @@ __global__ void __launch_bounds__(kSpriteThreads)
 // floor(advance * scale + spacing); everything else (also every byte >= 128: `char` is signed, Font.cpp:359) is skipped.
 // The pen is an int and the advances are integers (the reference adds them in double, exactly), so the walk is a
 // segmented scan: element = (advance since the last line break, line breaks, glyphs), combined left to right.
-//   k_text_summary   every thread folds 16 characters (one 128-bit load), 16 lanes fold a tile of 256
-//   k_text_scan      exclusive scan of the tile elements (one CTA)
+//   k_text_summary   every thread folds 16 characters (one 128-bit load), 16 lanes a tile of 256, a CTA its block of 16 tiles
+//   k_text_scan      exclusive scan of the elements of blocks of 16 tiles (one CTA; a tile adds its block's tiles in front of it)
 //   k_text_expand    a tile's characters: in-tile scan, one quad per glyph at its rank among the text's glyphs, bulk store
 // Right to left (Font.cpp:283-327) the reference skips the blanks at the start of a line going forwards, then walks the rest
 // of the line BACKWARDS from its last character: the pen before character i is the line's leading blanks plus the advances of
@@ -373,30 +373,14 @@ __device__ __forceinline__ void text_store(TextElem* p, const TextElem& e)
     else *reinterpret_cast<uint4*>(p) = make_uint4((uint32_t)e.adv, e.breaks, e.glyphs, e.line_glyphs);
 }
 constexpr int kTextTile = 256;       // characters per tile
-constexpr int kTextClasses = 128;    // a signed char that can have a glyph: 32 .. 127
-// per-character-code tables, built once per CTA: what the code adds to the pen, and whether it draws
-struct TextTables
+// per-character-code tables (TextTables, t3d_internal.h: built once per text on the host, handed over as a kernel parameter):
+// every CTA copies them into shared memory, where 256 lanes can look up 256 different codes at once
+__device__ __forceinline__ void text_copy_tables(TextTables& dst, const TextTables& src, uint32_t tid, uint32_t threads)
 {
-    int adv[kTextClasses];            // ' ', '\t', glyph advances (Font.cpp:344, :351, :378); 0 for everything else
-    unsigned char kind[kTextClasses]; // 0 nothing, 1 line break, 2 glyph, 3 blank (' ' or '\t')
-};
-__device__ __forceinline__ void text_build_tables(TextTables& t, const t3d_glyph* __restrict__ glyphs, const TextParams& P, uint32_t tid, uint32_t threads)
-{
-    for (uint32_t c = tid; c < (uint32_t)kTextClasses; c += threads)
-    {
-        int adv = 0;
-        unsigned char kind = 0;
-        if (c == ' ') { adv = (int)P.space_advance; kind = 3; }                  // Font.cpp:343-345
-        else if (c == '\t') { adv = (int)(P.space_advance * 4u); kind = 3; }     // :350-352
-        else if (c == '\r' || c == '\n') kind = 1;                               // :346-349
-        else if (c >= 32u && c - 32u < P.glyph_count)                            // :354-355 (index = c - 32)
-        {
-            kind = 2;
-            adv = (int)floorf(__uint2float_rn(glyphs[c - 32u].advance) * P.scale + (float)P.spacing); // :378
-        }
-        t.adv[c] = adv;
-        t.kind[c] = kind;
-    }
+    static_assert(sizeof(TextTables) % 4 == 0, "copied word by word");
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(&src);
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(&dst);
+    for (uint32_t w = tid; w < sizeof(TextTables) / 4; w += threads) d32[w] = s32[w];
 }
 __device__ __forceinline__ TextElem text_elem(const TextTables& t, unsigned char byte)
 {
@@ -414,11 +398,11 @@ __device__ __forceinline__ TextElem text_elem(const TextTables& t, unsigned char
 }
 
 template <bool RTL>
-__global__ void __launch_bounds__(256) k_text_summary(const unsigned char* __restrict__ text, uint32_t n, const t3d_glyph* __restrict__ glyphs,
-                                                      TextParams P, TextElem* __restrict__ tile_elems)
+__global__ void __launch_bounds__(256) k_text_summary(const unsigned char* __restrict__ text, uint32_t n, const __grid_constant__ TextTables T,
+                                                      TextElem* __restrict__ tile_elems, TextElem* __restrict__ block_elems)
 {
     __shared__ TextTables s_t;
-    text_build_tables(s_t, glyphs, P, threadIdx.x, 256);
+    text_copy_tables(s_t, T, threadIdx.x, 256);
     __syncthreads();
     const uint32_t first = (blockIdx.x * 256u + threadIdx.x) * 16u; // 16 threads = one tile of 256 characters
     unsigned char b[16];
@@ -444,6 +428,17 @@ __global__ void __launch_bounds__(256) k_text_summary(const unsigned char* __res
     }
     const uint32_t tile = first / (uint32_t)kTextTile;
     if ((threadIdx.x & 15u) == 15u && (unsigned long long)tile * kTextTile < n) text_store<RTL>(tile_elems + tile, e);
+    // ... and the CTA's 16 tiles one block of 4 096 characters: the scan kernel only walks the blocks
+    __shared__ TextElem s_tiles[16];
+    if ((threadIdx.x & 15u) == 15u) s_tiles[threadIdx.x >> 4] = e;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        TextElem b = s_tiles[0];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) b = text_combine<RTL>(b, s_tiles[k]);
+        text_store<RTL>(block_elems + blockIdx.x, b);
+    }
 }
 
 // elems[0 .. n_tiles) -> in place: the fields "from the left" become the exclusive prefix (everything before the tile), the
@@ -526,18 +521,63 @@ __global__ void __launch_bounds__(1024) k_text_scan(TextElem* __restrict__ elems
 
 template <bool RTL>
 __global__ void __launch_bounds__(kTextTile) k_text_expand(const unsigned char* __restrict__ text, uint32_t n, const t3d_glyph* __restrict__ glyphs,
-                                                           TextParams P, const TextElem* __restrict__ tile_prefix, float* __restrict__ dst)
+                                                           const __grid_constant__ TextTables T, TextParams P,
+                                                           const TextElem* __restrict__ tile_elems, uint32_t n_tiles,
+                                                           const TextElem* __restrict__ block_around, float* __restrict__ dst)
 {
     __shared__ __align__(128) float4 s_buf[RTL ? 9 : kTextTile * 9];
     __shared__ TextTables s_t;
     __shared__ TextElem s_warp[kTextTile / 32];
     __shared__ TextElem s_rwarp[kTextTile / 32];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    text_build_tables(s_t, glyphs, P, tid, kTextTile);
+    text_copy_tables(s_t, T, tid, kTextTile);
     const uint32_t i = blockIdx.x * (uint32_t)kTextTile + tid;
     const unsigned char byte = i < n ? text[i] : (unsigned char)0xff;
-    const TextElem around = text_load<RTL>(tile_prefix + blockIdx.x); // what lies before the tile (and, right to left, behind it)
+    // What lies before the tile (and, right to left, behind it): the scanned element of its block of 16 tiles, then the
+    // block's tiles in front of this one (behind it) -- 16 lanes fold them.
+    __shared__ TextElem s_around;
+    if (warp == 0)
+    {
+        const uint32_t block = blockIdx.x >> 4, j = blockIdx.x & 15u;
+        const uint32_t t = (block << 4) + (lane & 15u);
+        const TextElem mine = (lane < 16u && t < n_tiles) ? text_load<RTL>(tile_elems + t) : text_identity();
+        TextElem fwd = mine; // fold of the block's tiles [0, lane]
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1)
+        {
+            const TextElem u = text_shfl<RTL>(fwd, o, 16, true);
+            if ((int)(lane & 15u) >= o) fwd = text_combine<RTL>(u, fwd);
+        }
+        TextElem bwd = mine; // fold of the block's tiles [lane, 15]
+        if (RTL)
+        {
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1)
+            {
+                const TextElem u = text_shfl<true>(bwd, o, 16, false);
+                if ((int)(lane & 15u) + o < 16) bwd = text_combine<true>(bwd, u);
+            }
+        }
+        const TextElem front = text_shfl<RTL>(fwd, 1, 16, true);   // lane j: fold of tiles [0, j - 1]
+        const TextElem back = text_shfl<RTL>(bwd, 1, 16, false);   // lane j: fold of tiles [j + 1, 15]
+        if (lane == j)
+        {
+            const TextElem blk = text_load<RTL>(block_around + block);
+            TextElem a = blk; // (its right-hand fields describe what lies behind the block: set aside)
+            a.radv = 0; a.rglyphs = 0; a.rbreak = 0;
+            if (j > 0) a = text_combine<RTL>(a, front);
+            if (RTL)
+            {
+                TextElem behind = text_identity();
+                behind.radv = blk.radv; behind.rglyphs = blk.rglyphs; behind.rbreak = blk.rbreak;
+                if (j < 15u) behind = text_combine<true>(back, behind);
+                a.radv = behind.radv; a.rglyphs = behind.rglyphs; a.rbreak = behind.rbreak;
+            }
+            s_around = a;
+        }
+    }
     __syncthreads();
+    const TextElem around = s_around;
     const TextElem own = text_elem(s_t, byte);
     TextElem incl = own;
 #pragma unroll
@@ -625,28 +665,27 @@ __global__ void __launch_bounds__(kTextTile) k_text_expand(const unsigned char* 
 // launch wrappers
 // --------------------------------------------------------------------------------------------------
 uint32_t text_tiles(uint32_t n) { return (n + kTextTile - 1) / kTextTile; }
-size_t text_scratch_bytes(uint32_t n) { return ((size_t)text_tiles(n) + 1) * sizeof(TextElem); }
+static uint32_t text_blocks(uint32_t n) { return (text_tiles(n) + 15) / 16; }
+// tile elements, then block elements, then the whole text's element
+size_t text_scratch_bytes(uint32_t n) { return ((size_t)text_tiles(n) + text_blocks(n) + 1) * sizeof(TextElem); }
 
-void launch_text(void* stream, const char* text, uint32_t n, const t3d_glyph* glyphs, const TextParams& P, bool right_to_left, void* scratch,
-                 float* dst)
+template <bool RTL>
+static void launch_text_dir(cudaStream_t st, const unsigned char* t, uint32_t n, const t3d_glyph* glyphs, const TextTables& T, const TextParams& P,
+                            TextElem* elems, float* dst)
 {
-    cudaStream_t st = (cudaStream_t)stream;
-    const uint32_t tiles = text_tiles(n);
-    if (!tiles) return;
-    TextElem* elems = static_cast<TextElem*>(scratch);
+    const uint32_t tiles = text_tiles(n), blocks = text_blocks(n);
+    TextElem* block_elems = elems + tiles;
+    k_text_summary<RTL><<<blocks, 256, 0, st>>>(t, n, T, elems, block_elems);
+    k_text_scan<RTL><<<1, 1024, 0, st>>>(block_elems, blocks);
+    k_text_expand<RTL><<<tiles, kTextTile, 0, st>>>(t, n, glyphs, T, P, elems, tiles, block_elems, dst);
+}
+void launch_text(void* stream, const char* text, uint32_t n, const t3d_glyph* glyphs, const TextTables& T, const TextParams& P, bool right_to_left,
+                 void* scratch, float* dst)
+{
+    if (!n) return;
     const unsigned char* t = reinterpret_cast<const unsigned char*>(text);
-    if (right_to_left)
-    {
-        k_text_summary<true><<<(tiles + 15) / 16, 256, 0, st>>>(t, n, glyphs, P, elems);
-        k_text_scan<true><<<1, 1024, 0, st>>>(elems, tiles);
-        k_text_expand<true><<<tiles, kTextTile, 0, st>>>(t, n, glyphs, P, elems, dst);
-    }
-    else
-    {
-        k_text_summary<false><<<(tiles + 15) / 16, 256, 0, st>>>(t, n, glyphs, P, elems);
-        k_text_scan<false><<<1, 1024, 0, st>>>(elems, tiles);
-        k_text_expand<false><<<tiles, kTextTile, 0, st>>>(t, n, glyphs, P, elems, dst);
-    }
+    if (right_to_left) launch_text_dir<true>((cudaStream_t)stream, t, n, glyphs, T, P, static_cast<TextElem*>(scratch), dst);
+    else launch_text_dir<false>((cudaStream_t)stream, t, n, glyphs, T, P, static_cast<TextElem*>(scratch), dst);
 }
 
 uint32_t sprite_tiles(uint32_t n) { return (n + kSpriteThreads - 1) / kSpriteThreads; }
