@@ -5,6 +5,9 @@
 //   k_sprite_count /  ordered compaction for lists with clipped sprites (a sprite entirely outside its clip rectangle
 //   k_sprite_scan     leaves no quad, SB.cpp:409-412): kept sprites per tile, exclusive scan over the tiles
 //   k_tileset_draw    TileSet::draw (src/graphics/TileSet.cpp:207-236) from a device-resident tile table
+//   k_text_summary /  Font::drawText (src/renderer/Font.cpp:242-390): the pen walk as a segmented scan, one quad per glyph
+//   k_text_scan /     (see the section further down)
+//   k_text_expand
 //
 // Same output as the particle path: 4 x SpriteVertex {x, y, z, u, v, r, g, b, a} per quad, in call order.  All three are
 // streaming kernels: 84 B read + 144 B written per sprite (8 + 4 B read per tile); numerics as in t3d_kernels.cu
