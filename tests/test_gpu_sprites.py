@@ -179,9 +179,9 @@ def _oracle_text(O, g, font_size, spacing, text, x, y, color, size, rtl=False):
     return out[:n]
 
 
-@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 255, 256, 257, 4095, 4096, 4097, 70_001, 1_300_003])
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 127, 128, 129, 255, 256, 257, 4095, 4096, 4097, 70_001, 1_300_003])
 def test_text_is_laid_out_like_font_drawtext(n):
-    # the pen walk as a segmented scan (tile summaries of 256 characters, one-CTA scan, expansion): texts that end inside a
+    # the pen walk as a segmented scan (tile and block summaries, one-CTA scan, expansion of 128-character tiles): texts that end inside a
     # 16-byte load, a tile, a summary CTA (4 096 characters), and over a thousand tiles; bit for bit
     O = H.oracle(fresh=True)
     ctx = Context(0)

@@ -255,7 +255,7 @@ struct TextTables
     int adv[kTextClasses];            // ' ', '\t', glyph advances (Font.cpp:344, :351, :378); 0 for everything else
     unsigned char kind[kTextClasses]; // 0 nothing, 1 line break, 2 glyph, 3 blank (' ' or '\t')
 };
-uint32_t text_tiles(uint32_t n);          // tiles of 256 characters
+uint32_t text_tiles(uint32_t n);          // tiles (one expansion CTA each)
 size_t text_scratch_bytes(uint32_t n);    // device scratch a text of n bytes needs; its last 48 bytes end up holding {., line breaks, glyphs, ...}
 // text: n bytes on the device, 16-byte aligned; glyphs: the font's table on the device; quads go to dst in reading order
 void launch_text(void* stream, const char* text, uint32_t n, const t3d_glyph* glyphs, const TextTables& T, const TextParams& P, bool right_to_left,

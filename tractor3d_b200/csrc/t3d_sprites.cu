@@ -290,8 +290,8 @@ __global__ void __launch_bounds__(kSpriteThreads)
 // floor(advance * scale + spacing); everything else (also every byte >= 128: `char` is signed, Font.cpp:359) is skipped.
 // The pen is an int and the advances are integers (the reference adds them in double, exactly), so the walk is a
 // segmented scan: element = (advance since the last line break, line breaks, glyphs), combined left to right.
-//   k_text_summary   every thread folds 16 characters (one 128-bit load), 16 lanes a tile of 256, a CTA its block of 16 tiles
-//   k_text_scan      exclusive scan of the elements of blocks of 16 tiles (one CTA; a tile adds its block's tiles in front of it)
+//   k_text_summary   every thread folds 16 characters (one 128-bit load), 8 lanes a tile of 128, a CTA its block of 32 tiles
+//   k_text_scan      exclusive scan of the block elements (one CTA; a tile adds its block's tiles in front of it)
 //   k_text_expand    a tile's characters: in-tile scan, one quad per glyph at its rank among the text's glyphs, bulk store
 // Right to left (Font.cpp:283-327) the reference skips the blanks at the start of a line going forwards, then walks the rest
 // of the line BACKWARDS from its last character: the pen before character i is the line's leading blanks plus the advances of
@@ -375,7 +375,16 @@ __device__ __forceinline__ void text_store(TextElem* p, const TextElem& e)
     if (RTL) *p = e;
     else *reinterpret_cast<uint4*>(p) = make_uint4((uint32_t)e.adv, e.breaks, e.glyphs, e.line_glyphs);
 }
-constexpr int kTextTile = 256;       // characters per tile
+#if defined(T3D_EXP_TEXT_TILE)
+constexpr int kTextTile = T3D_EXP_TEXT_TILE;
+#else
+// characters per tile (one expansion CTA): 128 measured 4 % faster than 256 at 8 Mi characters and more (eleven resident CTAs per
+// SM instead of five cover each other's load -> scan -> store chains better), the same at 1 Mi
+constexpr int kTextTile = 128;
+#endif
+constexpr int kTextLanes = kTextTile / 16;     // lanes of the summary kernel that fold one tile (16 characters each)
+constexpr int kTextBlock = 4096 / kTextTile;   // tiles per block: what one summary CTA (256 threads x 16 characters) covers
+static_assert(kTextTile == 128 || kTextTile == 256, "a block's tiles are folded by the lanes of one warp");
 // per-character-code tables (TextTables, t3d_internal.h: built once per text on the host, handed over as a kernel parameter):
 // every CTA copies them into shared memory, where 256 lanes can look up 256 different codes at once
 __device__ __forceinline__ void text_copy_tables(TextTables& dst, const TextTables& src, uint32_t tid, uint32_t threads)
@@ -407,7 +416,7 @@ __global__ void __launch_bounds__(256) k_text_summary(const unsigned char* __res
     __shared__ TextTables s_t;
     text_copy_tables(s_t, T, threadIdx.x, 256);
     __syncthreads();
-    const uint32_t first = (blockIdx.x * 256u + threadIdx.x) * 16u; // 16 threads = one tile of 256 characters
+    const uint32_t first = (blockIdx.x * 256u + threadIdx.x) * 16u; // kTextLanes threads = one tile
     unsigned char b[16];
     if (first + 16u <= n)
     {
@@ -424,22 +433,22 @@ __global__ void __launch_bounds__(256) k_text_summary(const unsigned char* __res
     for (int k = 1; k < 16; ++k) e = text_combine<RTL>(e, text_elem(s_t, b[k]));
     // fold the 16 lanes of a tile (an inclusive scan; its last lane holds the tile's element)
 #pragma unroll
-    for (int o = 1; o < 16; o <<= 1)
+    for (int o = 1; o < kTextLanes; o <<= 1)
     {
-        const TextElem t = text_shfl<RTL>(e, o, 16, true);
-        if ((int)(threadIdx.x & 15u) >= o) e = text_combine<RTL>(t, e);
+        const TextElem t = text_shfl<RTL>(e, o, kTextLanes, true);
+        if ((int)(threadIdx.x & (kTextLanes - 1)) >= o) e = text_combine<RTL>(t, e);
     }
     const uint32_t tile = first / (uint32_t)kTextTile;
-    if ((threadIdx.x & 15u) == 15u && (unsigned long long)tile * kTextTile < n) text_store<RTL>(tile_elems + tile, e);
-    // ... and the CTA's 16 tiles one block of 4 096 characters: the scan kernel only walks the blocks
-    __shared__ TextElem s_tiles[16];
-    if ((threadIdx.x & 15u) == 15u) s_tiles[threadIdx.x >> 4] = e;
+    if ((threadIdx.x & (kTextLanes - 1)) == kTextLanes - 1 && (unsigned long long)tile * kTextTile < n) text_store<RTL>(tile_elems + tile, e);
+    // ... and the CTA's tiles one block of 4 096 characters: the scan kernel only walks the blocks
+    __shared__ TextElem s_tiles[kTextBlock];
+    if ((threadIdx.x & (kTextLanes - 1)) == kTextLanes - 1) s_tiles[threadIdx.x / kTextLanes] = e;
     __syncthreads();
     if (threadIdx.x == 0)
     {
         TextElem b = s_tiles[0];
 #pragma unroll
-        for (int k = 1; k < 16; ++k) b = text_combine<RTL>(b, s_tiles[k]);
+        for (int k = 1; k < kTextBlock; ++k) b = text_combine<RTL>(b, s_tiles[k]);
         text_store<RTL>(block_elems + blockIdx.x, b);
     }
 }
@@ -536,33 +545,33 @@ __global__ void __launch_bounds__(kTextTile) k_text_expand(const unsigned char* 
     text_copy_tables(s_t, T, tid, kTextTile);
     const uint32_t i = blockIdx.x * (uint32_t)kTextTile + tid;
     const unsigned char byte = i < n ? text[i] : (unsigned char)0xff;
-    // What lies before the tile (and, right to left, behind it): the scanned element of its block of 16 tiles, then the
+    // What lies before the tile (and, right to left, behind it): the scanned element of its block of tiles, then the
     // block's tiles in front of this one (behind it) -- 16 lanes fold them.
     __shared__ TextElem s_around;
     if (warp == 0)
     {
-        const uint32_t block = blockIdx.x >> 4, j = blockIdx.x & 15u;
-        const uint32_t t = (block << 4) + (lane & 15u);
-        const TextElem mine = (lane < 16u && t < n_tiles) ? text_load<RTL>(tile_elems + t) : text_identity();
+        const uint32_t block = blockIdx.x / kTextBlock, j = blockIdx.x % kTextBlock;
+        const uint32_t t = block * kTextBlock + (lane & (kTextBlock - 1));
+        const TextElem mine = (lane < (uint32_t)kTextBlock && t < n_tiles) ? text_load<RTL>(tile_elems + t) : text_identity();
         TextElem fwd = mine; // fold of the block's tiles [0, lane]
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1)
+        for (int o = 1; o < kTextBlock; o <<= 1)
         {
-            const TextElem u = text_shfl<RTL>(fwd, o, 16, true);
-            if ((int)(lane & 15u) >= o) fwd = text_combine<RTL>(u, fwd);
+            const TextElem u = text_shfl<RTL>(fwd, o, kTextBlock, true);
+            if ((int)(lane & (kTextBlock - 1)) >= o) fwd = text_combine<RTL>(u, fwd);
         }
         TextElem bwd = mine; // fold of the block's tiles [lane, 15]
         if (RTL)
         {
 #pragma unroll
-            for (int o = 1; o < 16; o <<= 1)
+            for (int o = 1; o < kTextBlock; o <<= 1)
             {
-                const TextElem u = text_shfl<true>(bwd, o, 16, false);
-                if ((int)(lane & 15u) + o < 16) bwd = text_combine<true>(bwd, u);
+                const TextElem u = text_shfl<true>(bwd, o, kTextBlock, false);
+                if ((int)(lane & (kTextBlock - 1)) + o < kTextBlock) bwd = text_combine<true>(bwd, u);
             }
         }
-        const TextElem front = text_shfl<RTL>(fwd, 1, 16, true);   // lane j: fold of tiles [0, j - 1]
-        const TextElem back = text_shfl<RTL>(bwd, 1, 16, false);   // lane j: fold of tiles [j + 1, 15]
+        const TextElem front = text_shfl<RTL>(fwd, 1, kTextBlock, true);   // lane j: fold of the block's tiles [0, j - 1]
+        const TextElem back = text_shfl<RTL>(bwd, 1, kTextBlock, false);   // lane j: fold of the block's tiles behind j
         if (lane == j)
         {
             const TextElem blk = text_load<RTL>(block_around + block);
@@ -573,7 +582,7 @@ __global__ void __launch_bounds__(kTextTile) k_text_expand(const unsigned char* 
             {
                 TextElem behind = text_identity();
                 behind.radv = blk.radv; behind.rglyphs = blk.rglyphs; behind.rbreak = blk.rbreak;
-                if (j < 15u) behind = text_combine<true>(back, behind);
+                if (j + 1u < (uint32_t)kTextBlock) behind = text_combine<true>(back, behind);
                 a.radv = behind.radv; a.rglyphs = behind.rglyphs; a.rbreak = behind.rbreak;
             }
             s_around = a;
@@ -668,7 +677,7 @@ __global__ void __launch_bounds__(kTextTile) k_text_expand(const unsigned char* 
 // launch wrappers
 // --------------------------------------------------------------------------------------------------
 uint32_t text_tiles(uint32_t n) { return (n + kTextTile - 1) / kTextTile; }
-static uint32_t text_blocks(uint32_t n) { return (text_tiles(n) + 15) / 16; }
+static uint32_t text_blocks(uint32_t n) { return (text_tiles(n) + kTextBlock - 1) / kTextBlock; }
 // tile elements, then block elements, then the whole text's element
 size_t text_scratch_bytes(uint32_t n) { return ((size_t)text_tiles(n) + text_blocks(n) + 1) * sizeof(TextElem); }
 
