@@ -197,7 +197,6 @@ constexpr uint32_t kFaultUpdateGrid = 1u, kFaultDrawGrid = 2u;
 struct UpdateLaunch
 {
     const UpdateItem* items;
-    const UpdateItem* host_items; // the same entries where the host cut them: the first one also travels as a kernel parameter
     const DrawItem* ditems; // fused launches only
     uint32_t n_items, total_tiles;
     unsigned long long* tile_status;

@@ -940,7 +940,6 @@ static int launch_updates(t3d_ctx* c, std::vector<PendingOp>& ops)
     T3D_TRY(time_begin(c, KERNEL_UPDATE));
     UpdateLaunch L{};
     L.items = reinterpret_cast<const UpdateItem*>(slot->dev);
-    L.host_items = reinterpret_cast<const UpdateItem*>(slot->host);
     L.n_items = n_items;
     L.total_tiles = tiles;
     L.tile_status = c->tile_status;
@@ -1099,7 +1098,6 @@ static int launch_fused_frame(t3d_ctx* c)
     T3D_TRY(time_begin(c, KERNEL_UPDATE_DRAW));
     UpdateLaunch L{};
     L.items = reinterpret_cast<const UpdateItem*>(slot->dev);
-    L.host_items = reinterpret_cast<const UpdateItem*>(slot->host);
     L.ditems = reinterpret_cast<const DrawItem*>(slot->dev + items_bytes + queries_bytes);
     L.n_items = n_items;
     L.total_tiles = tiles;

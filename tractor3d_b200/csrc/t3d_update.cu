@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     k_update(const UpdateItem* __restrict__ items, uint32_t n_items, uint32_t total_tiles,
              unsigned long long* __restrict__ tile_status, uint32_t* __restrict__ ticket, uint32_t ticket_base,
              uint32_t epoch, uint32_t* __restrict__ fault, uint32_t zero, const DrawItem* __restrict__ ditems, int rot_mode,
-             const FrozenRotation* __restrict__ frozen, const __grid_constant__ UpdateItem first_item)
+             const FrozenRotation* __restrict__ frozen)
 {
     static_assert(V == 2 || V == 4, "a thread owns 2 or 4 consecutive particles");
     static_assert(V * THREADS * SUB < 65535, "tile-local dead counts are kept as 16-bit values");
@@ -133,19 +133,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         for (int q = 0; q < (int)(sizeof(UpdateItem) / 16); ++q) dst[q] = __ldg(src + q);
         return r;
     };
-    // A launch over ONE emitter (a large emitter updated on its own) carries that entry as a kernel parameter: no fetch at all.
     uint32_t item_index = guess_item(n_items, tile, total_tiles);
-    UpdateItem it;
-    if (n_items == 1)
-        it = first_item;
-    else
+    UpdateItem it = load_item(item_index);
+    if (tile - it.tile_begin >= it.n_tiles)
     {
+        item_index = find_item(items, n_items, tile, total_tiles);
         it = load_item(item_index);
-        if (tile - it.tile_begin >= it.n_tiles)
-        {
-            item_index = find_item(items, n_items, tile, total_tiles);
-            it = load_item(item_index);
-        }
     }
     EmitterDev* const d = it.dev;
     const uint32_t parity = it.parity;
@@ -923,7 +916,7 @@ static void launch_one(cudaStream_t s, const UpdateLaunch& L)
                     THREADS, SUB, MIN_BLOCKS, (int)FUSED, resident, MIN_BLOCKS, smem);
     }
     kernel<<<L.total_tiles, THREADS, smem, s>>>(L.items, L.n_items, L.total_tiles, L.tile_status, L.ticket, L.ticket_base, L.epoch, L.fault, 0u,
-                                                L.ditems, L.rot_mode, L.frozen, L.host_items[0]);
+                                                L.ditems, L.rot_mode, L.frozen);
 }
 template <int V, int THREADS, int SUB, int MIN_BLOCKS, bool FUSED>
 static void launch_shape(cudaStream_t s, const UpdateLaunch& L)
