@@ -410,6 +410,12 @@ uint32_t t3d_host_sprite_frame_coords(uint32_t frame_count, int width, int heigh
 /* Number of draws one spawned particle consumes starting at draws[0] (PE.cpp:312-364); 0 if the
  * stream ends first.  Used to cut a recorded stream into per-particle offsets. */
 size_t t3d_host_particle_draws(const int32_t* draws, size_t n, int ellipsoid, uint32_t frame_random_offset);
+/* Font::measureText(text, size, &width, &height) (src/renderer/Font.cpp:675-731 with getTokenWidth, :1624-1657) for one size of a
+ * font: the widest line and `size` per line -- what a caller needs to place a text before t3d_font_draw_text.  Lines end at
+ * '\n' only ('\r' is skipped here, unlike in drawText), the text at its first NUL; size = 0: the font's own.  Scalar walk over
+ * the bytes: host logic, no GPU. */
+void t3d_host_font_measure_text(const t3d_glyph* glyphs, uint32_t glyph_count, uint32_t font_size, float character_spacing,
+                                const char* text, size_t length, uint32_t size, uint32_t* width, uint32_t* height);
 /* Width and height of a PNG from its header: all ParticleEmitter ever asks of its texture (PE.cpp:244-247). */
 int t3d_host_png_size(const char* path, uint32_t* width, uint32_t* height);
 /* ---- Properties: the slice of tractor::Properties (include/scene/Properties.h, src/scene/Properties.cpp) that

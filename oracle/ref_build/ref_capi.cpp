@@ -580,4 +580,12 @@ uint32_t t3dref_font_draw_text(void* h, const char* text, size_t length, int x, 
     return copy_captured(f->_batch->_batch.get(), out, max_quads);
 }
 
+void t3dref_font_measure_text(void* h, const char* text, size_t length, uint32_t size, uint32_t* width, uint32_t* height)
+{
+    unsigned int w = 0, hh = 0;
+    ((Font*)h)->measureText(std::string(text, length), size, &w, &hh); // Font.cpp:675-731
+    *width = w;
+    *height = hh;
+}
+
 } // extern "C"

@@ -113,6 +113,7 @@ class CpuLib:
             proto("font_create", _vp, [C.c_uint32, _vp, C.c_uint32, C.c_uint32, C.c_uint32])
             proto("font_destroy", None, [_vp])
             proto("font_set_character_spacing", None, [_vp, C.c_float])
+            proto("font_measure_text", None, [_vp, C.c_char_p, C.c_size_t, C.c_uint32, _P(C.c_uint32), _P(C.c_uint32)])
             proto("font_draw_text", C.c_uint32, [_vp, C.c_char_p, C.c_size_t, C.c_int, C.c_int, _P(C.c_float), C.c_uint32, C.c_int, _P(C.c_float),
                                                  C.c_size_t, _P(C.c_double)])
             proto("emitter_create_from_file", _vp, [C.c_char_p])

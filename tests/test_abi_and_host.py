@@ -325,3 +325,43 @@ def test_ellipsoid_acceptance_needs_no_square_root():
     assert np.array_equal(np.sqrt(near_one) > np.float32(1.0), near_one > thr)
     sweep = np.arange(0, 0x7F800000, 61, dtype=np.uint32).view(np.float32)              # and a sweep of all positive floats
     assert np.array_equal(np.sqrt(sweep) > np.float32(1.0), sweep > thr)
+
+
+def _measure(lib, g, font_size, spacing, text, size):
+    w, h = C.c_uint32(), C.c_uint32()
+    lib.t3d_host_font_measure_text(g.ctypes.data, g.size, font_size, spacing, text, len(text), size, C.byref(w), C.byref(h))
+    return w.value, h.value
+
+
+def test_font_measure_text_known_answers():
+    # Font::measureText (Font.cpp:675-731): the widest line, `size` per line; '\n' alone ends a line, ' ' and '\t' advance by
+    # the first glyph's advance (unscaled), a glyph by floor(advance * scale + spacing), everything else by nothing
+    lib = abi.load()
+    g = np.zeros(95, dtype=abi.GLYPH_DTYPE)
+    g["advance"] = 10
+    g["advance"][ord("W") - 32] = 17
+    assert _measure(lib, g, 20, 0.0, b"", 0) == (0, 0)
+    assert _measure(lib, g, 20, 0.0, b"abc", 0) == (30, 20)
+    assert _measure(lib, g, 20, 0.0, b"a c\tW", 0) == (10 + 10 + 10 + 40 + 17, 20)
+    assert _measure(lib, g, 20, 0.0, b"abc\nabcdW\n", 0) == (57, 60)               # a trailing '\n' counts a line
+    assert _measure(lib, g, 20, 0.0, b"ab\rcd", 0) == (40, 20)                     # '\r' is skipped, not a line break
+    assert _measure(lib, g, 20, 0.0, b"ab\x00cdefgh", 0) == (20, 20)               # c_str(): the text ends at its first NUL
+    assert _measure(lib, g, 20, 0.0, b"a\xe9b", 0) == (20, 20)                     # bytes >= 128: signed char, no glyph
+    assert _measure(lib, g, 20, 0.0, b"abc", 30) == (45, 30)                       # scale 1.5
+    assert _measure(lib, g, 20, 0.1, b"abc", 30) == (3 * (15 + 3), 30)             # spacing = (int)(30 * 0.1) pixels per glyph
+    assert _measure(lib, g, 20, 0.0, b"WW", 7) == (2 * 5, 7)                       # floor(17 * 0.35) = 5
+
+
+@pytest.mark.skipif(not H.ref_available(), reason="needs oracle/_ref")
+def test_font_measure_text_matches_the_reference():
+    lib, R = abi.load(), H.ref(fresh=True)
+    for glyph_count, font_size, size, spacing, n, seed in ((95, 24, 0, 0.0, 1, 3), (95, 24, 31, 0.125, 300, 4), (60, 18, 7, -0.05, 5000, 5),
+                                                         (95, 32, 64, 0.3, 70000, 6), (10, 12, 12, 0.0, 999, 7)):
+        g = H.random_font(seed, glyph_count, font_size)
+        h = R.font_create(font_size, g.ctypes.data, glyph_count, 512, 512)
+        R.font_set_character_spacing(h, spacing)
+        for text in (H.random_text(n, seed), H.random_text(n, seed + 100).replace(b"\x00", b"\x01"), b"", b"\n\n", b"   \t"):
+            w, hh = C.c_uint32(), C.c_uint32()
+            R.font_measure_text(h, text, len(text), size, C.byref(w), C.byref(hh))
+            assert _measure(lib, g, font_size, spacing, text, size) == (w.value, hh.value), (glyph_count, size, spacing, len(text))
+        R.font_destroy(h)

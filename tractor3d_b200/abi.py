@@ -221,6 +221,7 @@ PROTOTYPES = {
     "t3d_host_fuse_policy": (C.c_int, [C.c_uint64, C.c_uint64]),
     "t3d_host_rate_cap": (C.c_int, [_P(C.c_double), C.c_float, _P(C.c_float)]),
     "t3d_host_emission_count": (C.c_uint32, [_P(C.c_float), C.c_float, C.c_float]),
+    "t3d_host_font_measure_text": (None, [_vp, C.c_uint32, C.c_uint32, C.c_float, C.c_char_p, C.c_size_t, C.c_uint32, _P(C.c_uint32), _P(C.c_uint32)]),
     "t3d_host_sprite_frame_coords": (C.c_uint32, [C.c_uint32, C.c_int, C.c_int, C.c_float, C.c_float, _P(C.c_float)]),
     "t3d_host_particle_draws": (C.c_size_t, [_P(C.c_int32), C.c_size_t, C.c_int, C.c_uint32]),
     "t3d_host_png_size": (C.c_int, [C.c_char_p, _P(C.c_uint32), _P(C.c_uint32)]),

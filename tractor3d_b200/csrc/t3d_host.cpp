@@ -105,6 +105,48 @@ uint32_t t3d_host_emission_count(float* emit_time, float time_per_emission, floa
     return emit_count;
 }
 
+// Font::measureText(text, size, width, height), Font.cpp:675-731; the width of a line is Font::getTokenWidth, :1624-1657.
+void t3d_host_font_measure_text(const t3d_glyph* glyphs, uint32_t glyph_count, uint32_t font_size, float character_spacing, const char* text,
+                                size_t length, uint32_t size, uint32_t* width, uint32_t* height)
+{
+    uint32_t w = 0, h = 0;
+    if (size == 0) size = font_size;                                   // :684-687
+    size_t end = 0;                                                    // the walk is over text.c_str(): it ends at the first NUL
+    while (end < length && text[end] != 0) ++end;
+    if (length != 0 && glyphs && glyph_count && font_size)             // :699-705: an empty string measures 0 x 0
+    {
+        const float scale = (float)size / (float)font_size;            // :707
+        const int spacing = (int)((float)size * character_spacing);    // :1630
+        h = size;                                                      // :711
+        size_t i = 0;
+        while (i < end)                                                // :714
+        {
+            while (i < end && text[i] == '\n')                         // :716-720
+            {
+                h += size;
+                ++i;
+            }
+            uint32_t line = 0;                                         // :722-723, getTokenWidth over the bytes up to the next '\n'
+            for (; i < end && text[i] != '\n'; ++i)
+            {
+                const signed char c = (signed char)text[i];            // `char`, signed on the reference's platforms
+                if (c == ' ') line += glyphs[0].advance;               // :1638-1640
+                else if (c == '\t') line += glyphs[0].advance * 4u;    // :1641-1643
+                else
+                {
+                    const int index = c - 32;                          // :1645
+                    if (index >= 0 && index < (int)glyph_count)
+                        // :1649 `tokenWidth += floor(...)`: the floor in float, the sum in double, back to unsigned
+                        line = (uint32_t)(long long)((double)line + (double)floorf((float)glyphs[index].advance * scale + (float)spacing));
+                }
+            }
+            if (line > w) w = line;                                    // :724-727
+        }
+    }
+    if (width) *width = w;
+    if (height) *height = h;
+}
+
 uint32_t t3d_host_sprite_frame_coords(uint32_t frame_count, int width, int height, float tex_w, float tex_h, float* tex_coords)
 {
     // PE.cpp:550-582: frames walk the sheet left-to-right, top-to-bottom; rects the walk never reaches stay

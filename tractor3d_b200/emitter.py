@@ -220,11 +220,20 @@ class Font:
         """glyphs: numpy array of abi.GLYPH_DTYPE (Font::Glyph: code, width, bearingX, advance, uvs[4]); glyph k is character 32 + k."""
         self.ctx, self.lib = ctx, ctx.lib
         g = np.ascontiguousarray(glyphs, dtype=abi.GLYPH_DTYPE)
+        self._glyphs, self._size = g, size
         self.h = C.c_void_p()
         _check(self.lib, self.lib.t3d_font_create(ctx.h, size, g.ctypes.data, len(g), C.byref(self.h)))
 
     def setCharacterSpacing(self, spacing):
+        self._spacing = spacing
         _check(self.lib, self.lib.t3d_font_set_character_spacing(self.h, spacing))
+
+    def measureText(self, text, size=0):
+        """Font::measureText(text, size, &width, &height): (width, height) in pixels -- host logic, no GPU work."""
+        w, h = C.c_uint32(), C.c_uint32()
+        self.lib.t3d_host_font_measure_text(self._glyphs.ctypes.data, self._glyphs.size, self._size, getattr(self, "_spacing", 0.0), bytes(text), len(text),
+                                            size, C.byref(w), C.byref(h))
+        return w.value, h.value
 
     def drawText(self, text, x, y, color, size=0, right_to_left=False, device_dst=None, dst_quads=0, text_on_device=None):
         """text: bytes (uploaded) -- or, with text_on_device=(pointer, length), text already on the device.  Returns
