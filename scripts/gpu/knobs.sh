@@ -1,5 +1,6 @@
 #!/bin/bash
-# Cache-hint / look-back-width experiment: the same bench lines with other builds of the library (build.build_variant, T3D_LIBRARY).
+# Cache-hint / look-back-width experiment: the same bench lines with other builds of the library (python scripts/build_variants.py
+# first; T3D_LIBRARY selects one).
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 O=gpurun_out/knobs; mkdir -p $O
 B="python bench.py --no-cpu-baseline --no-also --no-vertices-to-host"
