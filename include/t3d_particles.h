@@ -410,6 +410,25 @@ uint32_t t3d_host_sprite_frame_coords(uint32_t frame_count, int width, int heigh
 /* Number of draws one spawned particle consumes starting at draws[0] (PE.cpp:312-364); 0 if the
  * stream ends first.  Used to cut a recorded stream into per-particle offsets. */
 size_t t3d_host_particle_draws(const int32_t* draws, size_t n, int ellipsoid, uint32_t frame_random_offset);
+/* ui Sprite::draw (src/ui/Sprite.cpp:495-574): what a Sprite node makes of its node, the active camera's node and its own
+ * offset / anchor / flip state before its ONE SpriteBatch::draw(position, frame, scale, color, anchor, angle) call
+ * (SB.cpp:202-216 -> :235-289).  t3d_host_ui_sprite_record fills the t3d_sprite2d that call amounts to (T3D_SPRITE_ROTATED);
+ * a scene's sprites go out together as one t3d_ctx_draw_sprites list.  Scalar per-node logic: host, no GPU. */
+typedef struct t3d_ui_sprite {
+    float    node_translation[3];   /* Node::getTranslationWorld() */
+    float    camera_translation[2]; /* x, y of the active camera node's world translation; 0 when the scene has no camera */
+    float    width, height;         /* Sprite::getWidth / getHeight */
+    uint32_t offset;                /* Sprite::Offset bits (include/graphics/Sprite.h:64-82): 0x02 hcenter, 0x04 right, 0x10 top,
+                                       0x20 vcenter, 0x80 anchor */
+    float    anchor[2];
+    float    node_rotation[4];      /* Node::getRotation(): x, y, z, w */
+    float    node_scale[2];         /* Node::getScaleX / getScaleY */
+    uint32_t flip;                  /* Sprite::FlipFlags: 1 vertical, 2 horizontal */
+    float    frame[4];              /* the current frame's source rectangle in texels: x, y, width, height */
+    float    color[4];
+    float    opacity;
+} t3d_ui_sprite;
+void t3d_host_ui_sprite_record(const t3d_ui_sprite* sprite, uint32_t texture_width, uint32_t texture_height, t3d_sprite2d* out);
 /* Font::measureText(text, size, &width, &height) (src/renderer/Font.cpp:675-731 with getTokenWidth, :1624-1657) for one size of a
  * font: the widest line and `size` per line -- what a caller needs to place a text before t3d_font_draw_text.  Lines end at
  * '\n' only ('\r' is skipped here, unlike in drawText), the text at its first NUL; size = 0: the font's own.  Scalar walk over

@@ -23,6 +23,9 @@
 #include "framework/FileSystem.h"
 #include "framework/Platform.h"
 #include "graphics/ParticleEmitter.h"
+#include "animation/AnimationTarget.h"
+#include "animation/AnimationValue.h"
+#include "graphics/Sprite.h"
 #include "graphics/SpriteBatch.h"
 #include "graphics/TileSet.h"
 #include "renderer/Font.h"
@@ -53,6 +56,13 @@ void print(const char* format, ...)
     vfprintf(stderr, format, args);
     va_end(args);
 }
+// ui/Sprite.cpp is an AnimationTarget; the animation system is not part of the harness: the few symbols it needs, inert
+AnimationTarget::~AnimationTarget() {}
+int AnimationTarget::getPropertyId(TargetType, const std::string&) { return -1; }
+void AnimationTarget::cloneInto(AnimationTarget*, NodeCloneContext&) const {}
+float AnimationValue::getFloat(unsigned int) const { return 0.0f; }
+void AnimationValue::setFloat(unsigned int, float) {}
+float Curve::lerp(float t, float from, float to) { return from + (to - from) * t; }
 std::string Platform::displayFileDialog(size_t, const std::string&, const std::string&, const std::string&,
                                         const std::string&)
 {
@@ -586,6 +596,39 @@ void t3dref_font_measure_text(void* h, const char* text, size_t length, uint32_t
     ((Font*)h)->measureText(std::string(text, length), size, &w, &hh); // Font.cpp:675-731
     *width = w;
     *height = hh;
+}
+
+// ---- ui Sprite::draw (src/ui/Sprite.cpp:495-574), driven headless: a Sprite on a node under a scene with an active camera ----
+uint32_t t3dref_ui_sprite_draw(const t3d_ui_sprite* in, uint32_t tex_w, uint32_t tex_h, float* out, size_t max_quads)
+{
+    keep_sprite_effect_alive();
+    char name[64];
+    snprintf(name, sizeof(name), "@%ux%u", tex_w, tex_h);
+    Sprite* sp = Sprite::create(std::string(name), in->width, in->height, Rectangle(in->frame[0], in->frame[1], in->frame[2], in->frame[3]), 1, nullptr);
+    if (!sp) return 0;
+    sp->setOffset((Sprite::Offset)in->offset);
+    sp->setAnchor(Vector2(in->anchor[0], in->anchor[1]));
+    sp->setFlip((int)in->flip);
+    sp->setColor(Vector4(in->color[0], in->color[1], in->color[2], in->color[3]));
+    sp->setOpacity(in->opacity);
+    Node node, cameraNode;
+    Camera camera;
+    Scene scene;
+    camera._node = &cameraNode;
+    scene._camera = &camera;
+    node._scene = &scene;
+    for (int k = 0; k < 3; ++k) node._world.m[12 + k] = in->node_translation[k];
+    cameraNode._world.m[12] = in->camera_translation[0];
+    cameraNode._world.m[13] = in->camera_translation[1];
+    node._rotation = Quaternion(in->node_rotation[0], in->node_rotation[1], in->node_rotation[2], in->node_rotation[3]);
+    node._scaleX = in->node_scale[0];
+    node._scaleY = in->node_scale[1];
+    sp->setNode(&node);
+    sp->draw(false);
+    const uint32_t quads = copy_captured(sp->_batch->_batch.get(), out, max_quads);
+    sp->setNode(nullptr);
+    sp->release();
+    return quads;
 }
 
 } // extern "C"

@@ -110,6 +110,7 @@ class CpuLib:
             proto("tileset_destroy", None, [_vp])
             proto("tileset_set_tile_source", None, [_vp, C.c_uint32, C.c_uint32, C.c_float, C.c_float])
             proto("tileset_draw", C.c_uint32, [_vp, _P(C.c_float), _P(C.c_float), _P(C.c_float), C.c_float, _P(C.c_float), C.c_size_t])
+            proto("ui_sprite_draw", C.c_uint32, [_vp, C.c_uint32, C.c_uint32, _P(C.c_float), C.c_size_t])
             proto("font_create", _vp, [C.c_uint32, _vp, C.c_uint32, C.c_uint32, C.c_uint32])
             proto("font_destroy", None, [_vp])
             proto("font_set_character_spacing", None, [_vp, C.c_float])
@@ -363,3 +364,29 @@ def random_text(n, seed, newline_every=60):
     t[(r >= 0.21) & (r < 0.215)] = rng.integers(128, 256, n)[(r >= 0.21) & (r < 0.215)]
     t[(r >= 0.22) & (r < 0.223)] = rng.integers(0, 9, n)[(r >= 0.22) & (r < 0.223)]
     return t.tobytes()
+
+
+def random_ui_sprites(n, seed):
+    """n t3d_ui_sprite records: every offset combination, anchors, node rotations (none, about z, about a tilted axis, not
+    normalised), node scales (1 and not), both flips, frames inside a 512 x 256 texture."""
+    rng = np.random.default_rng(seed)
+    s = np.zeros(n, dtype=abi.UI_SPRITE_DTYPE)
+    s["node_translation"] = rng.uniform(-200, 900, (n, 3))
+    s["camera_translation"] = np.where(rng.random((n, 1)) < 0.3, 0.0, rng.uniform(-50, 50, (n, 2)))
+    s["width"] = rng.uniform(1, 300, n); s["height"] = rng.uniform(1, 200, n)
+    s["offset"] = rng.choice([0x01, 0x02, 0x04], n) | rng.choice([0x10, 0x20, 0x40], n) | np.where(rng.random(n) < 0.3, 0x80, 0)
+    s["anchor"] = rng.uniform(0, 1, (n, 2))
+    kind = rng.integers(0, 4, n)
+    q = np.zeros((n, 4), dtype=np.float32); q[:, 3] = 1.0
+    half = rng.uniform(-3, 3, n) * 0.5
+    q[kind == 1, 2] = np.sin(half[kind == 1]); q[kind == 1, 3] = np.cos(half[kind == 1])                  # about z
+    axis = rng.normal(size=(n, 3)); axis /= np.linalg.norm(axis, axis=1, keepdims=True)
+    q[kind == 2, :3] = (axis * np.sin(half)[:, None])[kind == 2]; q[kind == 2, 3] = np.cos(half[kind == 2])  # about a tilted axis
+    q[kind == 3] = rng.uniform(-2, 2, (int((kind == 3).sum()), 4))                                       # not normalised
+    s["node_rotation"] = q
+    s["node_scale"] = np.where(rng.random((n, 2)) < 0.4, 1.0, rng.uniform(0.25, 3, (n, 2)))
+    s["flip"] = rng.integers(0, 4, n)
+    s["frame"][:, 0] = rng.integers(0, 400, n); s["frame"][:, 1] = rng.integers(0, 200, n)
+    s["frame"][:, 2] = rng.integers(1, 112, n); s["frame"][:, 3] = rng.integers(1, 56, n)
+    s["color"] = rng.uniform(0, 1, (n, 4)); s["opacity"] = rng.uniform(0, 1, n)
+    return s

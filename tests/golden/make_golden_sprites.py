@@ -70,6 +70,17 @@ def main():
                         color=color, vertices=verts[:quads].view(np.uint32))
     print(f"font_text: {n_text} bytes -> {quads} quads")
 
+    # ui Sprite::draw through the reference's own src/ui/Sprite.cpp: one quad per sprite node
+    from tractor3d_b200 import abi
+    n_ui = 1500
+    ui = H.random_ui_sprites(n_ui, 33)
+    verts = np.zeros((n_ui, 36), dtype=np.float32)
+    for k in range(n_ui):
+        assert R.ui_sprite_draw(ui[k:k + 1].ctypes.data, 512, 256, fp(verts[k:k + 1]), 1) == 1
+    np.savez_compressed(os.path.join(out_dir, "ui_sprites.npz"), sprites=ui.view(np.uint32).reshape(n_ui, -1), texture=np.array([512, 256]),
+                        vertices=verts.view(np.uint32))
+    print(f"ui_sprites: {n_ui} sprite nodes -> {n_ui} quads")
+
 
 if __name__ == "__main__":
     main()

@@ -70,6 +70,15 @@ def test_oracle_reproduces_reference_golden_sprites():
                          fp(np.ascontiguousarray(z["color"])), int(z["size"]), 0, fp(got), len(text))
     assert n == z["vertices"].shape[0] < len(text)
     assert np.array_equal(got[:n].view(np.uint32), z["vertices"])
+    z = _sprite_fixture("ui_sprites")
+    ui = np.ascontiguousarray(z["sprites"]).view(abi.UI_SPRITE_DTYPE).reshape(-1)
+    rec = np.zeros(ui.size, dtype=abi.SPRITE2D_DTYPE)
+    lib = abi.load()
+    for k in range(ui.size):
+        lib.t3d_host_ui_sprite_record(ui[k:k + 1].ctypes.data, int(z["texture"][0]), int(z["texture"][1]), rec[k:k + 1].ctypes.data)
+    got = np.zeros((ui.size, 36), dtype=np.float32)
+    assert O.sprites_2d(rec.ctypes.data, ui.size, fp(got), ui.size) == ui.size
+    assert np.array_equal(got.view(np.uint32), z["vertices"])
     z = _sprite_fixture("tileset")
     src = np.ascontiguousarray(z["sources"])
     rows, cols = src.shape[:2]

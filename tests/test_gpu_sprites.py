@@ -161,6 +161,15 @@ def test_sprites_and_tiles_against_the_reference_fixtures():
         assert nq == z["vertices"].shape[0]
         assert np.array_equal(ctx.download_quads(ptr, nq).view(np.uint32).reshape(nq, 36), z["vertices"])
         ts.release()
+        # a scene's ui Sprite nodes as ONE list: the host helper makes the records, the expansion kernel the quads
+        z = np.load(os.path.join(G.GOLDEN_DIR, "sprites", "ui_sprites.npz"))
+        ui = np.ascontiguousarray(z["sprites"]).view(abi.UI_SPRITE_DTYPE).reshape(-1)
+        rec = np.zeros(ui.size, dtype=abi.SPRITE2D_DTYPE)
+        for k in range(ui.size):
+            ctx.lib.t3d_host_ui_sprite_record(ui[k:k + 1].ctypes.data, int(z["texture"][0]), int(z["texture"][1]), rec[k:k + 1].ctypes.data)
+        ptr, nq = ctx.draw_sprites(rec, no_clip=True)
+        assert nq == ui.size
+        _compare(ctx.download_quads(ptr, nq), z["vertices"].view(np.float32).reshape(-1, 4, 9), True)
         z = np.load(os.path.join(G.GOLDEN_DIR, "sprites", "font_text.npz"))
         font = Font(ctx, int(z["font_size"]), np.ascontiguousarray(z["glyphs"]).view(abi.GLYPH_DTYPE).reshape(-1))
         font.setCharacterSpacing(float(z["spacing"]))

@@ -312,3 +312,25 @@ def test_font_draw_text_matches_the_reference():
                 assert no == nr > 0
                 assert np.array_equal(got[:no].view(np.uint32), want[:nr].view(np.uint32)), (glyph_count, n, "rtl, no NUL")
         R.font_destroy(h)
+
+
+def test_ui_sprite_records_draw_like_the_reference():
+    # ui Sprite::draw (src/ui/Sprite.cpp:495-574) through the reference's own Sprite.cpp on a node under a scene with a camera,
+    # against the host helper that turns the same state into ONE t3d_sprite2d record + the oracle's SpriteBatch restatement
+    # (the path a scene's sprites take as one t3d_ctx_draw_sprites list): bit for bit
+    from tractor3d_b200 import abi
+    lib = abi.load()
+    O, R = H.oracle(fresh=True), H.ref(fresh=True)
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    n = 2000
+    ui = H.random_ui_sprites(n, 21)
+    rec = np.zeros(n, dtype=abi.SPRITE2D_DTYPE)
+    want = np.zeros((n, 36), dtype=np.float32)
+    for k in range(n):
+        one = ui[k:k + 1]
+        assert R.ui_sprite_draw(one.ctypes.data, 512, 256, fp(want[k:k + 1]), 1) == 1
+        lib.t3d_host_ui_sprite_record(one.ctypes.data, 512, 256, rec[k:k + 1].ctypes.data)
+    assert (rec["flags"] == abi.SPRITE_ROTATED).all() and (rec["rotation_angle"] != 0).mean() > 0.5
+    got = np.zeros((n, 36), dtype=np.float32)
+    assert O.sprites_2d(rec.ctypes.data, n, fp(got), n) == n
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

@@ -125,6 +125,11 @@ class Sprite2D(C.Structure):
 
 SPRITE_ROTATED, SPRITE_CENTERED, SPRITE_CLIPPED = 1, 2, 4
 SPRITES_ON_DEVICE, SPRITES_NO_CLIP = 1, 2
+# numpy view of t3d_ui_sprite (ui Sprite::draw's inputs, 26 words)
+UI_SPRITE_DTYPE = [("node_translation", "f4", (3,)), ("camera_translation", "f4", (2,)), ("width", "f4"), ("height", "f4"), ("offset", "u4"),
+                   ("anchor", "f4", (2,)), ("node_rotation", "f4", (4,)), ("node_scale", "f4", (2,)), ("flip", "u4"), ("frame", "f4", (4,)),
+                   ("color", "f4", (4,)), ("opacity", "f4")]
+
 # numpy view of an array of t3d_glyph (Font::Glyph, 8 words each)
 GLYPH_DTYPE = [("code", "u4"), ("width", "u4"), ("bearing_x", "i4"), ("advance", "u4"), ("uvs", "f4", (4,))]
 TEXT_ON_DEVICE = 1
@@ -221,6 +226,7 @@ PROTOTYPES = {
     "t3d_host_fuse_policy": (C.c_int, [C.c_uint64, C.c_uint64]),
     "t3d_host_rate_cap": (C.c_int, [_P(C.c_double), C.c_float, _P(C.c_float)]),
     "t3d_host_emission_count": (C.c_uint32, [_P(C.c_float), C.c_float, C.c_float]),
+    "t3d_host_ui_sprite_record": (None, [_vp, C.c_uint32, C.c_uint32, _vp]),
     "t3d_host_font_measure_text": (None, [_vp, C.c_uint32, C.c_uint32, C.c_float, C.c_char_p, C.c_size_t, C.c_uint32, _P(C.c_uint32), _P(C.c_uint32)]),
     "t3d_host_sprite_frame_coords": (C.c_uint32, [C.c_uint32, C.c_int, C.c_int, C.c_float, C.c_float, _P(C.c_float)]),
     "t3d_host_particle_draws": (C.c_size_t, [_P(C.c_int32), C.c_size_t, C.c_int, C.c_uint32]),

@@ -105,6 +105,68 @@ uint32_t t3d_host_emission_count(float* emit_time, float time_per_emission, floa
     return emit_count;
 }
 
+// ui Sprite::draw, src/ui/Sprite.cpp:495-574, up to its SpriteBatch::draw call, and that call's own first lines (SB.cpp:202-216).
+void t3d_host_ui_sprite_record(const t3d_ui_sprite* s, uint32_t texture_width, uint32_t texture_height, t3d_sprite2d* out)
+{
+    if (!s || !out) return;
+    float px = 0.0f, py = 0.0f, pz = 0.0f;                           // :498 Vector3::zero()
+    px -= s->camera_translation[0];                                  // :514-515
+    py -= s->camera_translation[1];
+    px += s->node_translation[0];                                    // :520-523
+    py += s->node_translation[1];
+    pz += s->node_translation[2];
+    const uint32_t off = s->offset;
+    if ((off & 0x02u) == 0x02u) px = (float)((double)px - (double)s->width * 0.5); // :527 (`_width * 0.5`: a double product)
+    if ((off & 0x04u) == 0x04u) px -= s->width;                      // :528
+    if ((off & 0x20u) == 0x20u) py -= s->height * 0.5f;              // :529
+    if ((off & 0x10u) == 0x10u) py -= s->height;                     // :530
+    if ((off & 0x80u) == 0x80u)                                      // :531-535
+    {
+        px -= s->width * s->anchor[0];
+        py -= s->height * s->anchor[1];
+    }
+    float angle = 0.0f;                                              // :538
+    float sx = s->width, sy = s->height;                             // :539
+    const float qx = s->node_rotation[0], qy = s->node_rotation[1], qz = s->node_rotation[2];
+    if (qx != 0.0f || qy != 0.0f || qz != 0.0f)                      // :543-544: Quaternion::toAxisAngle(nullptr)
+    {
+        float w = s->node_rotation[3];
+        float n = qx * qx + qy * qy + qz * qz + w * w;               // src/math/Quaternion.cpp:183-196 (normalize)
+        if (n != 1.0f)
+        {
+            n = sqrtf(n);
+            if (!(n < 0.000001f)) w *= 1.0f / n;
+        }
+        angle = (float)(2.0 * acos((double)w));                      // Quaternion.cpp:277: `2.0f * acos(q.w)`, the double acos
+    }
+    if (s->node_scale[0] != 1.0f) sx *= s->node_scale[0];            // :547-548
+    if (s->node_scale[1] != 1.0f) sy *= s->node_scale[1];
+    if ((s->flip & 2u) == 2u)                                        // :551-555 FLIP_HORIZONTAL
+    {
+        px += sx;
+        sx = -sx;
+    }
+    if ((s->flip & 1u) == 1u)                                        // :557-561 FLIP_VERTICAL
+    {
+        py += sy;
+        sy = -sy;
+    }
+    memset(out, 0, sizeof(*out));
+    const float wr = 1.0f / (float)texture_width, hr = 1.0f / (float)texture_height; // SB.cpp:155-156
+    out->x = px; out->y = py; out->z = pz;
+    out->width = sx; out->height = sy;
+    out->u1 = wr * s->frame[0];                                      // SB.cpp:208-211
+    out->v1 = 1.0f - hr * s->frame[1];
+    out->u2 = out->u1 + wr * s->frame[2];
+    out->v2 = out->v1 - hr * s->frame[3];
+    out->color[0] = s->color[0]; out->color[1] = s->color[1]; out->color[2] = s->color[2];
+    out->color[3] = s->color[3] * s->opacity;                        // :568
+    out->rotation_point[0] = s->anchor[0];                           // :569
+    out->rotation_point[1] = s->anchor[1];
+    out->rotation_angle = angle;
+    out->flags = T3D_SPRITE_ROTATED;
+}
+
 // Font::measureText(text, size, width, height), Font.cpp:675-731; the width of a line is Font::getTokenWidth, :1624-1657.
 void t3d_host_font_measure_text(const t3d_glyph* glyphs, uint32_t glyph_count, uint32_t font_size, float character_spacing, const char* text,
                                 size_t length, uint32_t size, uint32_t* width, uint32_t* height)
